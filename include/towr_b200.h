@@ -1,0 +1,194 @@
+/* towr_b200.h — C ABI of the B200-native NLP-evaluation path for towr.
+ *
+ * This is the drop-in boundary: everything below replaces, for
+ * a whole batch of independent problem instances at once, what the reference
+ * serves one instance at a time through ifopt::Problem:
+ *
+ *   ifopt::Problem::GetNumberOfOptimizationVariables / GetNumberOfConstraints
+ *   ifopt::Problem::GetJacobianOfConstraints  (structure: rows then ascending cols)
+ *   ifopt::Problem::GetBoundsOnOptimizationVariables / GetBoundsOnConstraints
+ *   ifopt::Problem::GetVariableValues          (initial guess)
+ *   ifopt::Problem::EvaluateConstraints / EvalNonzerosOfJacobian
+ *   ifopt::Problem::EvaluateCostFunction / EvaluateCostFunctionGradient
+ *
+ * assembled from the reference's
+ *   towr/src/nlp_formulation.cc:63-376   (variable sets, constraint sets, costs)
+ *   towr/src/parameters.cc:40-135        (towr::Parameters defaults)
+ * The per-set views (ifopt Component API: GetValues / GetBounds /
+ * FillJacobianBlock, reference headers towr/include/towr/constraints/) are
+ * served by twb_layout_* + slices of the flat arrays; see INTEGRATION.md.
+ *
+ * Plain C: opaque handles, caller-allocated arrays, int status returns
+ * (0 = TWB_OK), never throws across the boundary.  All reals are fp64, all
+ * indices 32-bit int, 0-based.
+ */
+#ifndef TOWR_B200_H_
+#define TOWR_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWB_MAX_EE 4
+#define TWB_MAX_PHASES 32
+#define TWB_MAX_CONSTRAINTS 16
+#define TWB_MAX_COSTS 8
+
+/* status codes */
+enum {
+  TWB_OK = 0,
+  TWB_ERR_INVALID = 1,     /* bad argument / spec */
+  TWB_ERR_UNSUPPORTED = 2, /* valid towr configuration the device path does not serve yet */
+  TWB_ERR_CUDA = 3,        /* CUDA runtime error; see twb_last_error() */
+  TWB_ERR_NO_DEVICE = 4    /* no CUDA device: there is NO CPU fallback */
+};
+
+/* towr::RobotModel::Robot, towr/include/towr/models/robot_model.h:70-75 */
+enum { TWB_MONOPED = 0, TWB_BIPED = 1, TWB_HYQ = 2, TWB_ANYMAL = 3, TWB_GO1 = 4 };
+
+/* towr::HeightMap::TerrainID, towr/include/towr/terrain/height_map.h:79-86 */
+enum { TWB_FLAT = 0, TWB_BLOCK = 1, TWB_STAIRS = 2, TWB_GAP = 3, TWB_SLOPE = 4,
+       TWB_CHIMNEY = 5, TWB_CHIMNEY_LR = 6, TWB_TERRAIN_COUNT = 7 };
+
+/* towr::Parameters::ConstraintName, towr/include/towr/parameters.h:139-147 */
+enum { TWB_C_DYNAMIC = 0, TWB_C_EE_ROM = 1, TWB_C_TOTAL_TIME = 2, TWB_C_TERRAIN = 3,
+       TWB_C_FORCE = 4, TWB_C_SWING = 5, TWB_C_BASE_ROM = 6, TWB_C_BASE_ACC = 7 };
+
+/* towr::Parameters::CostName, towr/include/towr/parameters.h:148-150 */
+enum { TWB_COST_FORCES = 0, TWB_COST_EE_MOTION = 1 };
+
+/* One NLP "structure class" + the instance data of NlpFormulation's public
+ * fields (towr/include/towr/nlp_formulation.h:100-105) and towr::Parameters
+ * (towr/include/towr/parameters.h:152-214). */
+typedef struct twb_spec {
+  int robot;                              /* TWB_MONOPED.. */
+  int terrain;                            /* default terrain for every instance of a batch */
+  int n_ee;                               /* params_.ee_in_contact_at_start_.size() */
+  int n_phases[TWB_MAX_EE];               /* params_.ee_phase_durations_.at(ee).size() */
+  double phase_durations[TWB_MAX_EE][TWB_MAX_PHASES];
+  int in_contact_at_start[TWB_MAX_EE];
+
+  double initial_base_lin_pos[3], initial_base_lin_vel[3];   /* initial_base_.lin */
+  double initial_base_ang_pos[3], initial_base_ang_vel[3];   /* initial_base_.ang */
+  double final_base_lin_pos[3], final_base_lin_vel[3];       /* final_base_.lin   */
+  double final_base_ang_pos[3], final_base_ang_vel[3];       /* final_base_.ang   */
+  double initial_ee_W[TWB_MAX_EE][3];                        /* initial_ee_W_     */
+
+  double duration_base_polynomial;        /* parameters.cc:43 */
+  int force_polynomials_per_stance_phase; /* :44 */
+  int ee_polynomials_per_swing_phase;     /* :45 */
+  double force_limit_in_normal_direction; /* :48 */
+  double dt_constraint_range_of_motion;   /* :49 */
+  double dt_constraint_dynamic;           /* :50 */
+  double dt_constraint_base_motion;       /* :51 */
+  double bound_phase_duration_min, bound_phase_duration_max; /* :52 */
+
+  int n_constraints;                      /* params_.constraints_ in order */
+  int constraints[TWB_MAX_CONSTRAINTS];
+  int n_costs;                            /* params_.costs_ in order */
+  int cost_ids[TWB_MAX_COSTS];
+  double cost_weights[TWB_MAX_COSTS];
+
+  int bounds_final_lin_pos[3];            /* 1 if that dimension is bounded, parameters.cc:66-69 */
+  int bounds_final_lin_vel[3];
+  int bounds_final_ang_pos[3];
+  int bounds_final_ang_vel[3];
+} twb_spec;
+
+typedef struct twb_problem twb_problem; /* host-side structure class (+ bounds, x0) */
+typedef struct twb_batch twb_batch;     /* B instances of one problem resident on one GPU */
+
+/* ---- setup helpers (host only) ------------------------------------------------ */
+
+/* Parameters::Parameters() defaults (parameters.cc:40-73) + the robot; zero
+ * states; no phases. */
+int twb_spec_default(twb_spec* spec, int robot);
+
+/* Parameters::OptimizePhaseDurations (parameters.cc:77-80): appends TotalTime. */
+int twb_spec_optimize_phase_durations(twb_spec* spec);
+
+/* GaitGenerator::MakeGaitGenerator(n_ee)->SetCombo(combo) then, per foot,
+ * GetPhaseDurations(t_total, ee) / IsInContactAtStart(ee)
+ * (gait_generator.cc:54-105, {monoped,biped,quadruped}_gait_generator.cc).
+ * Fills spec->n_ee, n_phases, phase_durations, in_contact_at_start. */
+int twb_spec_set_gait(twb_spec* spec, int n_ee, int combo, double t_total);
+
+/* KinematicModel::GetNominalStanceInBase / GetMaximumDeviationFromNominal and
+ * the SRBD constants of the robot (models/examples/(robot)_model.h). */
+int twb_robot_info(int robot, int* n_ee, double* mass, double inertia6[6],
+                   double nominal_stance[TWB_MAX_EE][3], double max_dev[3]);
+
+/* HeightMap::GetHeight of the analytic terrains (height_map_examples.cc). */
+double twb_terrain_height(int terrain, double x, double y);
+
+/* ---- structure class ---------------------------------------------------------- */
+
+int twb_problem_create(const twb_spec* spec, twb_problem** out);
+void twb_problem_destroy(twb_problem* p);
+
+/* n = #variables, m = #constraint rows, nnz = #Jacobian non-zeros */
+int twb_problem_dims(const twb_problem* p, int* n, int* m, int* nnz);
+
+/* Jacobian structure exactly as IpoptAdapter reads it from
+ * GetJacobianOfConstraints(): row-major, ascending column inside a row. */
+int twb_problem_structure(const twb_problem* p, int* iRow, int* jCol);
+/* CSR row pointer, m+1 entries */
+int twb_problem_row_ptr(const twb_problem* p, int* row_ptr);
+
+/* Bounds (ifopt::Bounds, inf = 1e20) and initial guess. */
+int twb_problem_bounds(const twb_problem* p, double* x_lower, double* x_upper,
+                       double* g_lower, double* g_upper);
+int twb_problem_x0(const twb_problem* p, double* x0);
+
+/* Component layout: variable sets (column ranges) and constraint sets (row
+ * ranges) in ifopt's Add*Set order; names are the reference's
+ * ("base-lin", "ee-motion_0", "dynamic", "rangeofmotion-1", ...). */
+int twb_layout_num_variable_sets(const twb_problem* p);
+int twb_layout_variable_set(const twb_problem* p, int i, char* name, int name_cap,
+                            int* col_start, int* n_cols);
+int twb_layout_num_constraint_sets(const twb_problem* p);
+int twb_layout_constraint_set(const twb_problem* p, int i, char* name, int name_cap,
+                              int* row_start, int* n_rows);
+
+/* ---- batched evaluation on a B200 --------------------------------------------- */
+
+/* Allocates device state for `batch_size` instances on CUDA device `device`.
+ * Fails with TWB_ERR_NO_DEVICE when there is none (no CPU fallback). */
+int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch** out);
+void twb_batch_destroy(twb_batch* b);
+
+/* Per-instance terrain ids (host array of batch_size ints). The structure does
+ * not depend on the terrain, so one batch may mix terrains. */
+int twb_batch_set_terrains(twb_batch* b, const int* terrain_ids);
+
+#define TWB_EVAL_G 1u     /* constraint values        (Problem::EvaluateConstraints)       */
+#define TWB_EVAL_JAC 2u   /* Jacobian values          (Problem::EvalNonzerosOfJacobian)    */
+#define TWB_EVAL_COST 4u  /* cost + gradient          (EvaluateCostFunction[Gradient])     */
+#define TWB_EVAL_ALL 7u
+
+/* Device-pointer variant: all arrays live on the batch's device.
+ *   x    [B][n]    in
+ *   g    [B][m]    out (may be NULL if !(flags&TWB_EVAL_G))
+ *   jac  [B][nnz]  out (CSR value order of twb_problem_structure)
+ *   cost [B]       out, grad [B][n] out (only written when the problem has cost terms)
+ *   status [B]     out, bit0: non-finite value produced, bit1: sum of phase durations >= T
+ * `stream` is a cudaStream_t (NULL = default stream); the call only enqueues. */
+int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
+                          double* cost, double* grad, int* status,
+                          unsigned flags, void* stream);
+
+/* Host-pointer variant: copies x up, evaluates, copies the requested outputs
+ * back and synchronises. Pinned host memory makes the copies asynchronous. */
+int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac,
+                        double* cost, double* grad, int* status, unsigned flags);
+
+/* number of kernel launches one twb_batch_eval_device(flags) enqueues */
+int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags);
+
+const char* twb_last_error(void);
+const char* twb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOWR_B200_H_ */

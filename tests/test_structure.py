@@ -1,0 +1,137 @@
+"""CPU tests: the product's structure builder against the oracle, hand-verified
+counts, gait tables, and the C ABI surface.  No GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import towr_b200 as tb
+from towr_b200 import capi
+import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = [
+    ("hopper", None, {}),
+    ("anymal_trot_block", None, {}),
+    ("anymal_trot_block", tb.GAP, dict(goal_xy=(2.0, 0.3), goal_yaw=0.4)),
+    ("biped_walk_stairs", None, {}),
+    ("go1_trot_flat", tb.SLOPE, dict(t_total=2.4)),
+    ("anymal_trot_mixed", tb.CHIMNEY_LR, dict(goal_xy=(1.2, -0.2))),
+]
+
+
+@pytest.mark.parametrize("name,terrain,kw", CASES)
+def test_structure_bounds_x0_match_oracle(name, terrain, kw):
+    spec = tb.make_formulation(name, terrain=terrain, **kw).to_spec()
+    p = tb.Problem(spec)
+    o = oracle_lib.Oracle(spec)
+    assert (p.n, p.m, p.nnz) == (o.n, o.m, o.nnz)
+    rp, ci = o.structure()
+    assert np.array_equal(p.row_ptr(), rp)          # bit-exact indices
+    iRow, jCol = p.structure()
+    assert np.array_equal(jCol, ci)
+    assert np.array_equal(iRow, np.repeat(np.arange(o.m), np.diff(rp)))
+    assert np.all(np.diff(jCol)[iRow[1:] == iRow[:-1]] > 0)   # ascending columns inside a row
+    for a, b in zip(p.bounds(), o.bounds()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(p.GetVariableValues(), o.x0())
+    assert p.variable_sets() == o.variable_sets()
+    assert p.constraint_sets() == o.constraint_sets()
+
+
+def test_hand_verified_counts():
+    # hopper n = 126+126+27+60, m = 10+132+57+57+81+50+12
+    p = tb.Problem(tb.make_formulation("hopper").to_spec())
+    assert [k for _, _, k in p.variable_sets()] == [126, 126, 27, 60]
+    assert [k for _, _, k in p.constraint_sets()] == [10, 132, 57, 57, 81, 50, 12]
+    assert [nm for nm, _, _ in p.constraint_sets()] == [
+        "terrain-ee-motion_0", "dynamic", "splineacc-base-lin", "splineacc-base-ang", "rangeofmotion-0",
+        "force-ee-force_0", "swing-ee-motion_0"]
+    assert (p.n, p.m, p.nnz) == (339, 399, 5392)
+    p2 = tb.Problem(tb.make_formulation("anymal_trot_block").to_spec())
+    assert (p2.n, p2.m, p2.nnz) == (640, 892, 15096)
+    p3 = tb.Problem(tb.make_formulation("biped_walk_stairs").to_spec())
+    assert (p3.n, p3.m, p3.nnz) == (466, 586, 8709)
+
+
+def test_gait_tables():
+    # fly trot C1 and biped walk C0 scaled to T = 2.0
+    gg = tb.GaitGenerator.MakeGaitGenerator(4); gg.SetCombo(1)
+    lf = gg.GetPhaseDurations(2.0, 0); rf = gg.GetPhaseDurations(2.0, 1)
+    assert np.allclose(lf, [0.35, 0.3, 0.2, 0.3, 0.2, 0.3, 0.35], atol=1e-15)
+    assert np.allclose(rf, [0.15, 0.25, 0.2, 0.3, 0.2, 0.3, 0.2, 0.25, 0.15], atol=1e-15)
+    assert np.allclose(gg.GetPhaseDurations(2.0, 3), lf, atol=0) and np.allclose(gg.GetPhaseDurations(2.0, 2), rf, atol=0)
+    assert all(gg.IsInContactAtStart(e) for e in range(4))
+    bg = tb.GaitGenerator.MakeGaitGenerator(2); bg.SetCombo(0)
+    assert np.allclose(bg.GetPhaseDurations(2.0, 0), [0.125, 0.1875, 0.25, 0.1875, 0.25, 0.1875, 0.25, 0.1875, 0.375], atol=1e-15)
+    assert np.allclose(bg.GetPhaseDurations(2.0, 1), [0.34375, 0.1875, 0.25, 0.1875, 0.25, 0.1875, 0.25, 0.1875, 0.15625], atol=1e-15)
+    g4 = tb.GaitGenerator.MakeGaitGenerator(4); g4.SetCombo(4)
+    assert all(len(g4.GetPhaseDurations(2.0, e)) == 9 for e in range(4))
+    for e in range(4):
+        assert abs(sum(g4.GetPhaseDurations(2.0, e)) - 2.0) < 1e-12
+
+
+def test_sample_grid_quirks():
+    # duplicated final sample at T = 2.0; 22 dynamic and 27 RoM samples
+    p = tb.Problem(tb.make_formulation("anymal_trot_block").to_spec())
+    rows = dict((nm, k) for nm, _, k in p.constraint_sets())
+    assert rows["dynamic"] == 22 * 6 and rows["rangeofmotion-0"] == 27 * 3
+    p24 = tb.Problem(tb.make_formulation("anymal_trot_block", t_total=2.4).to_spec())
+    rows = dict((nm, k) for nm, _, k in p24.constraint_sets())
+    assert rows["dynamic"] == 25 * 6
+    assert (p24.n, p24.m, p24.nnz) == (688, 994, 17364)
+
+
+def test_terrain_heights_match_oracle():
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([rng.uniform(-1, 5, (200, 2)),
+                          [[0.7, 0], [0.73, 0], [4.2, 0], [1.0, 0.1], [1.4, 0], [2.4, 0], [1.5, 0.2], [2.0, 0], [3.0, 0], [2.5, 1], [0.5, 0], [1.5, -1]]])
+    for t in range(7):
+        for x, y in pts:
+            assert tb.terrain_height(t, x, y) == oracle_lib.lib().oracle_terrain_height(t, x, y)
+
+
+def test_unsupported_and_invalid_specs():
+    f = tb.make_formulation("hyq_gallop_gap")
+    assert f.params_.IsOptimizeTimings()
+    with pytest.raises(tb.TowrB200Error) as e:
+        tb.Problem(f.to_spec())
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    s = tb.make_formulation("hopper").to_spec(); s.n_ee = 2
+    with pytest.raises(tb.TowrB200Error) as e:
+        tb.Problem(s)
+    assert e.value.code == capi.ERR_INVALID
+    s = tb.make_formulation("hopper").to_spec(); s.constraints[0] = 99
+    with pytest.raises(tb.TowrB200Error):
+        tb.Problem(s)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "towr_b200.h")).read()
+    declared = set(re.findall(r"\b(twb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = C.CDLL(capi.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(capi.EXPORTS)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    p = tb.Problem(tb.make_formulation("hopper").to_spec())
+    with pytest.raises(tb.TowrB200Error) as e:
+        p.batch(4)
+    assert e.value.code == capi.ERR_NO_DEVICE
+
+
+def test_product_does_not_reference_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "towr_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cc", ".cu", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "oracle" not in txt.lower(), os.path.join(dirpath, fn)

@@ -1,0 +1,101 @@
+// device_tables.h — plain-old-data tables the host builder (formulation.cc)
+// uploads once per structure class and the CUDA kernels (kernels.cu) read on
+// every evaluation.  Nothing in here depends on the iterate x.
+#ifndef TOWR_B200_DEVICE_TABLES_H_
+#define TOWR_B200_DEVICE_TABLES_H_
+
+#include <cstdint>
+
+namespace twb {
+
+constexpr int kMaxEE = 4;
+
+// One spline evaluated at one constraint sample when phase durations are
+// fixed: the active polynomial (Spline::GetSegmentID, spline.cc:48-63), its
+// local time (Spline::GetLocalTime, spline.cc:66-78) and where its two
+// boundary nodes live in x.  `xi` holds x indices of p0[3], v0[3], p1[3],
+// v1[3]; node values that are not optimised (always 0 in towr) point at the
+// zero slot, index n.
+struct SplineSample {
+  double T, T2, T3;   // polynomial duration and std::pow(T,2), std::pow(T,3)
+  double t, t2, t3;   // local time and std::pow(t,2), std::pow(t,3)
+  int16_t xi[12];
+};
+
+// TerrainConstraint row (terrain_constraint.cc:59-108): one ee-motion node
+struct TerrainUnit {
+  int16_t xi[3];      // x index of node position x,y,z
+  int16_t pad;
+  int32_t g_row;      // constraint row
+  int32_t s_idx;      // S offset of {-dh/dx, -dh/dy}
+};
+
+// ForceConstraint node (force_constraint.cc:64-171): 5 rows
+struct ForceUnit {
+  int16_t xf[3];      // x index of the force node value
+  int16_t xp[3];      // x index of the stance-foot position (phase start node); [2] unused
+  int16_t pad[2];
+  int32_t g_row;      // first of the 5 rows
+  int32_t s_idx;      // S offset of 25 Jacobian values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
+};
+
+// SwingConstraint node (swing_constraint.cc:57-83): 4 rows
+struct SwingUnit {
+  int16_t xc_p[2], xc_v[2];  // current node pos/vel x,y
+  int16_t xprev[2], xnext[2];
+  int32_t g_row;
+  int32_t pad;
+};
+
+// SplineAccConstraint junction (spline_acc_constraint.cc:49-65), fixed durations
+struct AccUnit {
+  double Tp, Tp2, Tp3;  // previous polynomial duration, pow 2, pow 3
+  double Tn, Tn2, Tn3;  // next polynomial
+  int32_t x0;           // x index of node j, dim 0 position (NodesVariablesAll layout)
+  int32_t g_row;        // first of 3 rows
+};
+
+// NodeCost term (node_cost.cc:53-76) flattened: one entry per node value that
+// enters the cost; var >= 0 when the value is an optimisation variable.
+struct CostEntry {
+  int16_t xi;        // x index holding the node value (zero slot if fixed)
+  int16_t grad_col;  // column of the gradient this node contributes to, or -1
+  int32_t pad;
+  double weight;
+};
+
+// Jacobian slot descriptor: value = S[a]*coef  (+ S[a+1]*extra[2e] + S[a+2]*extra[2e+1] if triple)
+constexpr uint32_t kDescTriple = 0x80000000u;
+inline uint32_t MakeDesc(uint32_t a, uint32_t extra_idx, bool triple) {
+  return (a & 0xFFFFu) | ((extra_idx & 0x7FFFu) << 16) | (triple ? kDescTriple : 0u);
+}
+
+struct Plan {
+  int n, m, nnz, n_ee;
+  // sizes
+  int n_dyn, n_rom, n_terr, n_force, n_swing, n_acc, n_totdur, n_cost;
+  // g rows
+  int dyn_row0;
+  int rom_row0[kMaxEE];
+  int totdur_row0;
+  // S layout (doubles, per instance)
+  int S_size, S_dyn0, S_dyn_stride, S_rom0, S_rom_stride;
+  // robot
+  double mass, gravity;
+  double I_b[9];
+  double mu;
+  // tables (device pointers)
+  const SplineSample* dyn_samples;  // [n_dyn][2 + 2*n_ee]: base-lin, base-ang, motion_e.., force_e..
+  const SplineSample* rom_samples;  // [n_rom][2 + n_ee]:  base-lin, base-ang, motion_e..
+  const TerrainUnit* terr;
+  const ForceUnit* force;
+  const SwingUnit* swing;
+  const AccUnit* acc;
+  const CostEntry* cost;
+  const uint32_t* desc;   // [nnz]
+  const double* coef;     // [nnz]
+  const double* extra;    // [2*n_triples]
+};
+
+}  // namespace twb
+#endif

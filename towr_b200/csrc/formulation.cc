@@ -1,0 +1,535 @@
+// formulation.cc — builds one NLP structure class on the host.
+//
+// What the reference obtains implicitly by running Eigen sparse algebra once
+// (IpoptAdapter reads the pattern of the first GetJacobianOfConstraints()),
+// this builder derives explicitly: every Jacobian entry is *emitted* as
+//     (row, col)  ->  S[a] * coef            (or a 3-term variant)
+// where S is the small per-instance state vector the kernels compute per
+// iterate and `coef` is an iterate-independent constant (a Hermite basis value
+// at a fixed sample time, a sign, the mass, ...).  Sorting the emitted entries
+// row-major / ascending column gives the CSR pattern; the sorted (a, coef)
+// pairs are the slot descriptors the fill kernel walks.
+//
+// Reference behaviour restated here (cited per function):
+//   towr/src/nlp_formulation.cc:63-376, parameters.cc:82-135,
+//   nodes_variables*.cc, spline.cc:48-78, polynomial.cc:106-234,
+//   time_discretization_constraint.cc:37-51 and the *_constraint.cc files.
+#include "formulation.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <numeric>
+
+namespace twb {
+namespace {
+
+constexpr double kInf = 1e20;  // ifopt::inf
+enum { kPos = 0, kVel = 1, kAcc = 2 };
+enum { X = 0, Y = 1, Z = 2 };
+
+// ---- node parameterisations ------------------------------------------------
+struct NodeSet {
+  std::string name;
+  int offset = 0, n_vars = 0, n_nodes = 0;
+  std::vector<std::array<int, 6>> var;  // [node][deriv*3+dim] -> local variable index or -1 (fixed 0)
+  std::vector<double> x0, lo, up;
+  struct Poly { int phase, k_in_phase, n_in_phase; bool constant; };
+  std::vector<Poly> poly;  // phase-based sets only
+
+  int Var(int node, int deriv, int dim) const { return var[node][deriv * 3 + dim]; }
+  bool ConstNode(int id) const {  // nodes_variables_phase_based.cc:104-116,156-172
+    if (id == 0) return poly.front().constant;
+    if (id == n_nodes - 1) return poly.back().constant;
+    return poly[id - 1].constant || poly[id].constant;
+  }
+  void Alloc(int nodes) { n_nodes = nodes; var.assign(nodes, {-1, -1, -1, -1, -1, -1}); }
+  void Finish() { x0.assign(n_vars, 0.0); lo.assign(n_vars, -kInf); up.assign(n_vars, +kInf); }
+  // NodesVariables::SetByLinearInterpolation, nodes_variables.cc:126-150; a variable shared by two
+  // nodes ends up holding the later node's value (NodesVariables::GetValues, :53-61)
+  void Interpolate(const double a[3], const double b[3], double t_total) {
+    for (int node = 0; node < n_nodes; ++node)
+      for (int dim = 0; dim < 3; ++dim) {
+        double dp = b[dim] - a[dim];
+        int vp = Var(node, kPos, dim), vv = Var(node, kVel, dim);
+        if (vp >= 0) x0[vp] = a[dim] + node / static_cast<double>(n_nodes - 1) * dp;
+        if (vv >= 0) x0[vv] = dp / t_total;
+      }
+  }
+  void Fix(int node, int deriv, int dim, double val) {  // NodesVariables::AddBound, :161-168
+    int v = Var(node, deriv, dim);
+    if (v >= 0) { lo[v] = val; up[v] = val; }
+  }
+};
+
+NodeSet MakeBaseSet(const std::string& name, int nodes) {  // nodes_variables_all.cc:34-61
+  NodeSet s; s.name = name; s.Alloc(nodes);
+  for (int nd = 0; nd < nodes; ++nd) for (int k = 0; k < 6; ++k) s.var[nd][k] = nd * 6 + k;
+  s.n_vars = nodes * 6; s.Finish();
+  return s;
+}
+void BuildPolys(NodeSet* s, int phases, bool first_constant, int polys_in_changing) {  // nodes_variables_phase_based.cc:38-76
+  bool c = first_constant;
+  for (int ph = 0; ph < phases; ++ph) {
+    if (c) s->poly.push_back({ph, 0, 1, true});
+    else for (int j = 0; j < polys_in_changing; ++j) s->poly.push_back({ph, j, polys_in_changing, false});
+    c = !c;
+  }
+  s->Alloc((int)s->poly.size() + 1);
+}
+NodeSet MakeMotionSet(const std::string& name, int phases, bool contact_at_start, int polys_per_swing) {  // :190-253
+  NodeSet s; s.name = name; BuildPolys(&s, phases, contact_at_start, polys_per_swing);
+  int idx = 0;
+  for (int nd = 0; nd < s.n_nodes; ++nd) {
+    if (!s.ConstNode(nd)) {  // swing node: px, vx, py, vy, pz
+      for (int dim = 0; dim < 3; ++dim) { s.var[nd][dim] = idx++; if (dim != Z) s.var[nd][3 + dim] = idx++; }
+    } else {                 // stance pair shares one position
+      for (int dim = 0; dim < 3; ++dim) { s.var[nd][dim] = idx; s.var[nd + 1][dim] = idx; ++idx; }
+      ++nd;
+    }
+  }
+  s.n_vars = idx; s.Finish();
+  return s;
+}
+NodeSet MakeForceSet(const std::string& name, int phases, bool contact_at_start, int polys_per_stance) {  // :255-298
+  NodeSet s; s.name = name; BuildPolys(&s, phases, !contact_at_start, polys_per_stance);
+  int idx = 0;
+  for (int nd = 0; nd < s.n_nodes; ++nd) {
+    if (!s.ConstNode(nd)) { for (int dim = 0; dim < 3; ++dim) { s.var[nd][dim] = idx++; s.var[nd][3 + dim] = idx++; } }
+    else ++nd;  // swing pair: all zeros, not optimised
+  }
+  s.n_vars = idx; s.Finish();
+  return s;
+}
+
+// ---- splines at fixed durations --------------------------------------------
+struct SplineDef { const NodeSet* set; std::vector<double> T; };
+
+int SegmentID(double t_global, const std::vector<double>& T) {  // spline.cc:48-63
+  const double eps = 1e-10; double t = 0; int i = 0;
+  for (double d : T) { t += d; if (t >= t_global - eps) return i; ++i; }
+  return (int)T.size() - 1;
+}
+void Locate(const SplineDef& s, double t_global, int* poly, double* t_local) {  // spline.cc:66-78
+  *poly = SegmentID(t_global, s.T);
+  double tl = t_global; for (int i = 0; i < *poly; ++i) tl -= s.T[i];
+  *t_local = tl;
+}
+// d(value derivative dxdt at local time t)/d(node value): polynomial.cc:106-234
+double NodeBasis(int side, int dxdt, int node_deriv, double t, double T) {
+  double t2 = std::pow(t, 2), t3 = std::pow(t, 3), T2 = std::pow(T, 2), T3 = std::pow(T, 3);
+  if (side == 0) {
+    if (dxdt == kPos) return node_deriv == kPos ? (2 * t3) / T3 - (3 * t2) / T2 + 1 : t - (2 * t2) / T + t3 / T2;
+    if (dxdt == kVel) return node_deriv == kPos ? (6 * t2) / T3 - (6 * t) / T2 : (3 * t2) / T2 - (4 * t) / T + 1;
+    return node_deriv == kPos ? (12 * t) / T3 - 6 / T2 : (6 * t) / T2 - 4 / T;
+  }
+  if (dxdt == kPos) return node_deriv == kPos ? (3 * t2) / T2 - (2 * t3) / T3 : t3 / T2 - t2 / T;
+  if (dxdt == kVel) return node_deriv == kPos ? (6 * t) / T2 - (6 * t2) / T3 : (3 * t2) / T2 - (2 * t) / T;
+  return node_deriv == kPos ? 6 / T2 - (12 * t) / T3 : (6 * t) / T2 - 2 / T;
+}
+struct BasisEntry { int dim, var; double val; };
+// NodeSpline::FillJacobianWrtNodes, node_spline.cc:85-112: which variables of the set move
+// the spline value (derivative dxdt) of polynomial `poly` at local time tl, and by how much.
+std::vector<BasisEntry> Basis(const SplineDef& s, int poly, double tl, int dxdt) {
+  std::map<int, BasisEntry> acc;  // keyed by variable -> ascending column order
+  for (int side = 0; side < 2; ++side)
+    for (int deriv = 0; deriv < 2; ++deriv)
+      for (int dim = 0; dim < 3; ++dim) {
+        int v = s.set->Var(poly + side, deriv, dim);
+        if (v < 0) continue;
+        double b = NodeBasis(side, dxdt, deriv, tl, s.T[poly]);
+        auto it = acc.find(v);
+        if (it == acc.end()) acc[v] = BasisEntry{dim, v, 0.0 + b};
+        else it->second.val += b;  // stance position shared by both boundary nodes
+      }
+  std::vector<BasisEntry> out;
+  for (auto& kv : acc) out.push_back(kv.second);
+  return out;
+}
+int16_t XIndex(const NodeSet& set, int node, int deriv, int dim, int zero_slot) {
+  int v = set.Var(node, deriv, dim);
+  return (int16_t)(v < 0 ? zero_slot : set.offset + v);
+}
+SplineSample MakeSample(const SplineDef& s, double t_global, int zero_slot) {
+  SplineSample o{};
+  int p; double tl; Locate(s, t_global, &p, &tl);
+  o.T = s.T[p]; o.T2 = std::pow(o.T, 2); o.T3 = std::pow(o.T, 3);
+  o.t = tl; o.t2 = std::pow(tl, 2); o.t3 = std::pow(tl, 3);
+  for (int side = 0; side < 2; ++side) for (int deriv = 0; deriv < 2; ++deriv) for (int dim = 0; dim < 3; ++dim)
+    o.xi[side * 6 + deriv * 3 + dim] = XIndex(*s.set, p + side, deriv, dim, zero_slot);
+  return o;
+}
+
+std::vector<double> SampleTimes(double T, double dt) {  // time_discretization_constraint.cc:37-51
+  double t = 0.0; std::vector<double> v = {t};
+  for (int i = 0; i < std::floor(T / dt); ++i) { t += dt; v.push_back(t); }
+  v.push_back(T);
+  return v;
+}
+std::vector<double> BasePolyDurations(double T, double dt) {  // parameters.cc:82-98
+  std::vector<double> v; double left = T; const double eps = 1e-10;
+  while (left > eps) { v.push_back(left > dt ? dt : left); left -= dt; }
+  return v;
+}
+
+struct Emit { int row, col; uint32_t a; bool triple; double c0, c1, c2; };
+
+// sign/component of Cross(v)[i][d] (single_rigid_body_dynamics.cc:46-57): value = sign * v[comp]
+void CrossEntry(int i, int d, int* comp, double* sign) {
+  static const int c[3][3] = {{-1, 2, 1}, {2, -1, 0}, {1, 0, -1}};
+  static const double s[3][3] = {{0, -1, +1}, {+1, 0, -1}, {-1, +1, 0}};
+  *comp = c[i][d]; *sign = s[i][d];
+}
+
+}  // namespace
+
+int Formulation::Build(const twb_spec& sp, std::string* err) {
+  auto fail = [&](int code, const char* why) { if (err) *err = why; return code; };
+  spec = sp;
+  RobotConst rb;
+  if (!GetRobot(sp.robot, &rb)) return fail(TWB_ERR_INVALID, "unknown robot");
+  if (sp.n_ee != rb.n_ee) return fail(TWB_ERR_INVALID, "n_ee does not match the robot model");
+  if (sp.terrain < 0 || sp.terrain >= TWB_TERRAIN_COUNT) return fail(TWB_ERR_INVALID, "unknown terrain");
+  const int n_ee = sp.n_ee;
+  for (int e = 0; e < n_ee; ++e)
+    if (sp.n_phases[e] < 1 || sp.n_phases[e] > TWB_MAX_PHASES) return fail(TWB_ERR_INVALID, "bad phase count");
+  if (sp.n_constraints < 0 || sp.n_constraints > TWB_MAX_CONSTRAINTS || sp.n_costs < 0 || sp.n_costs > TWB_MAX_COSTS)
+    return fail(TWB_ERR_INVALID, "bad constraint/cost count");
+  optimize_timings = false;
+  for (int i = 0; i < sp.n_constraints; ++i) {
+    if (sp.constraints[i] == TWB_C_TOTAL_TIME) optimize_timings = true;  // parameters.cc:128-135
+    if (sp.constraints[i] == TWB_C_BASE_ROM) return fail(TWB_ERR_UNSUPPORTED, "BaseRom (BaseMotionConstraint) is not served by the device path yet");
+    if (sp.constraints[i] < 0 || sp.constraints[i] > TWB_C_BASE_ACC) return fail(TWB_ERR_INVALID, "constraint not defined!");
+  }
+  if (optimize_timings) return fail(TWB_ERR_UNSUPPORTED, "phase-duration optimisation (PhaseSpline) is not served by the device path yet");
+
+  // Parameters::GetTotalTime, parameters.cc:112-126
+  double T = 0.0; for (int i = 0; i < sp.n_phases[0]; ++i) T += sp.phase_durations[0][i];
+  for (int e = 1; e < n_ee; ++e) {
+    double Te = 0.0; for (int i = 0; i < sp.n_phases[e]; ++i) Te += sp.phase_durations[e][i];
+    if (std::fabs(Te - T) >= 1e-6) return fail(TWB_ERR_INVALID, "feet phase durations do not sum to the same total time");
+  }
+  if (!(T > 0.0)) return fail(TWB_ERR_INVALID, "total time must be positive");
+  const std::vector<double> base_T = BasePolyDurations(T, sp.duration_base_polynomial);
+
+  // ---- variable sets in AddVariableSet order (nlp_formulation.cc:63-93)
+  std::vector<NodeSet> sets;
+  sets.reserve(2 + 2 * n_ee);
+  sets.push_back(MakeBaseSet("base-lin", (int)base_T.size() + 1));
+  sets.push_back(MakeBaseSet("base-ang", (int)base_T.size() + 1));
+  for (int e = 0; e < n_ee; ++e)
+    sets.push_back(MakeMotionSet("ee-motion_" + std::to_string(e), sp.n_phases[e], sp.in_contact_at_start[e] != 0, sp.ee_polynomials_per_swing_phase));
+  for (int e = 0; e < n_ee; ++e)
+    sets.push_back(MakeForceSet("ee-force_" + std::to_string(e), sp.n_phases[e], sp.in_contact_at_start[e] != 0, sp.force_polynomials_per_stance_phase));
+  n = 0; var_sets.clear();
+  for (auto& s : sets) { s.offset = n; var_sets.push_back({s.name, n, s.n_vars}); n += s.n_vars; }
+  if (n + 1 > 32767) return fail(TWB_ERR_UNSUPPORTED, "more than 32766 variables");
+  const int zero_slot = n;
+  NodeSet& lin = sets[0]; NodeSet& ang = sets[1];
+  auto motion = [&](int e) -> NodeSet& { return sets[2 + e]; };
+  auto force = [&](int e) -> NodeSet& { return sets[2 + n_ee + e]; };
+
+  // ---- initial guess and variable bounds (nlp_formulation.cc:95-181)
+  {
+    double fx = sp.final_base_lin_pos[0], fy = sp.final_base_lin_pos[1];
+    double fz = TerrainHeight(sp.terrain, fx, fy) - rb.nominal[0][2];
+    double final_pos[3] = {fx, fy, fz};
+    lin.Interpolate(sp.initial_base_lin_pos, final_pos, T);
+    ang.Interpolate(sp.initial_base_ang_pos, sp.final_base_ang_pos, T);
+    const int last = lin.n_nodes - 1;
+    for (int d = 0; d < 3; ++d) {
+      lin.Fix(0, kPos, d, sp.initial_base_lin_pos[d]); lin.Fix(0, kVel, d, sp.initial_base_lin_vel[d]);
+      ang.Fix(0, kPos, d, sp.initial_base_ang_pos[d]); ang.Fix(0, kVel, d, sp.initial_base_ang_vel[d]);
+      if (sp.bounds_final_lin_pos[d]) lin.Fix(last, kPos, d, sp.final_base_lin_pos[d]);
+      if (sp.bounds_final_lin_vel[d]) lin.Fix(last, kVel, d, sp.final_base_lin_vel[d]);
+      if (sp.bounds_final_ang_pos[d]) ang.Fix(last, kPos, d, sp.final_base_ang_pos[d]);
+      if (sp.bounds_final_ang_vel[d]) ang.Fix(last, kVel, d, sp.final_base_ang_vel[d]);
+    }
+    // yaw-only rotation of the nominal stance (EulerConverter::GetRotationMatrixBaseToWorld with x=y=0)
+    double yaw = sp.final_base_ang_pos[2];
+    double x = 0.0, y = 0.0, z = yaw;
+    double R[3][3] = {{cos(y) * cos(z), cos(z) * sin(x) * sin(y) - cos(x) * sin(z), sin(x) * sin(z) + cos(x) * cos(z) * sin(y)},
+                      {cos(y) * sin(z), cos(x) * cos(z) + sin(x) * sin(y) * sin(z), cos(x) * sin(y) * sin(z) - cos(z) * sin(x)},
+                      {-sin(y), cos(y) * sin(x), cos(x) * cos(y)}};
+    for (int e = 0; e < n_ee; ++e) {
+      const double* nom = rb.nominal[e];
+      double w[3];
+      for (int i = 0; i < 3; ++i) w[i] = sp.final_base_lin_pos[i] + (R[i][0] * nom[0] + R[i][1] * nom[1] + R[i][2] * nom[2]);
+      double goal[3] = {w[0], w[1], TerrainHeight(sp.terrain, w[0], w[1])};
+      motion(e).Interpolate(sp.initial_ee_W[e], goal, T);
+      for (int d = 0; d < 3; ++d) motion(e).Fix(0, kPos, d, sp.initial_ee_W[e][d]);
+      double f_stance[3] = {0.0, 0.0, rb.mass * 9.80665 / n_ee};
+      force(e).Interpolate(f_stance, f_stance, T);
+    }
+  }
+  x0.clear(); x_lower.clear(); x_upper.clear();
+  for (auto& s : sets) {
+    x0.insert(x0.end(), s.x0.begin(), s.x0.end());
+    x_lower.insert(x_lower.end(), s.lo.begin(), s.lo.end());
+    x_upper.insert(x_upper.end(), s.up.begin(), s.up.end());
+  }
+
+  // ---- splines (spline_holder.cc:35-61, fixed durations)
+  auto poly_durations = [&](const NodeSet& s, int e) {  // nodes_variables_phase_based.cc:78-89
+    std::vector<double> d;
+    for (auto& p : s.poly) d.push_back(sp.phase_durations[e][p.phase] / p.n_in_phase);
+    return d;
+  };
+  SplineDef sp_lin{&lin, base_T}, sp_ang{&ang, base_T};
+  std::vector<SplineDef> sp_motion, sp_force;
+  for (int e = 0; e < n_ee; ++e) { sp_motion.push_back({&motion(e), poly_durations(motion(e), e)}); sp_force.push_back({&force(e), poly_durations(force(e), e)}); }
+
+  // ---- S layout
+  HostTables& tb = tables; tb = HostTables{};
+  Plan& pl = tb.plan;
+  int S_top = 1;  // S[0] == 1.0
+  const uint32_t S_ONE = 0;
+
+  std::vector<Emit> em;
+  auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, false, c, 0.0, 0.0}); };
+  auto emit3 = [&](int row, int col, uint32_t a, double c0, double c1, double c2) { em.push_back({row, col, a, true, c0, c1, c2}); };
+
+  m = 0; con_sets.clear(); g_lower.clear(); g_upper.clear();
+  auto add_set = [&](const std::string& name, int rows) { con_sets.push_back({name, m, rows}); int r0 = m; m += rows; g_lower.resize(m, 0.0); g_upper.resize(m, 0.0); return r0; };
+  auto bound = [&](int row, double lo, double up) { g_lower[row] = lo; g_upper[row] = up; };
+
+  pl.n_dyn = pl.n_rom = 0; pl.totdur_row0 = -1; pl.dyn_row0 = -1;
+  for (int e = 0; e < kMaxEE; ++e) pl.rom_row0[e] = -1;
+
+  for (int ci = 0; ci < sp.n_constraints; ++ci) {
+    switch (sp.constraints[ci]) {
+      case TWB_C_DYNAMIC: {  // dynamic_constraint.cc + single_rigid_body_dynamics.cc:103-192
+        if (pl.dyn_row0 >= 0) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
+        std::vector<double> ts = SampleTimes(T, sp.dt_constraint_dynamic);
+        int r0 = add_set("dynamic", (int)ts.size() * 6);
+        pl.dyn_row0 = r0; pl.n_dyn = (int)ts.size();
+        pl.S_dyn_stride = 30 + 6 * n_ee; pl.S_dyn0 = S_top; S_top += pl.S_dyn_stride * pl.n_dyn;
+        for (int k = 0; k < pl.n_dyn; ++k) {
+          const double t = ts[k];
+          const int row = r0 + 6 * k; const uint32_t sb = pl.S_dyn0 + k * pl.S_dyn_stride;
+          for (int r = 0; r < 6; ++r) bound(row + r, 0.0, 0.0);
+          tb.dyn_samples.push_back(MakeSample(sp_lin, t, zero_slot));
+          tb.dyn_samples.push_back(MakeSample(sp_ang, t, zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.dyn_samples.push_back(MakeSample(sp_motion[e], t, zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.dyn_samples.push_back(MakeSample(sp_force[e], t, zero_slot));
+          int p; double tl;
+          // base-lin: angular rows = -sum_e [f_e]x dc ; linear rows = m * d(acc)
+          Locate(sp_lin, t, &p, &tl);
+          for (auto& b : Basis(sp_lin, p, tl, kPos))
+            for (int i = 0; i < 3; ++i) if (i != b.dim) {
+              int comp; double sg; CrossEntry(i, b.dim, &comp, &sg);
+              emit1(row + i, lin.offset + b.var, sb + comp, -sg * b.val);
+            }
+          for (auto& b : Basis(sp_lin, p, tl, kAcc)) emit1(row + 3 + b.dim, lin.offset + b.var, S_ONE, rb.mass * b.val);
+          // base-ang: angular rows = A*dtheta + B*dtheta_dot + C*dtheta_ddot
+          Locate(sp_ang, t, &p, &tl);
+          {
+            auto bp = Basis(sp_ang, p, tl, kPos), bv = Basis(sp_ang, p, tl, kVel), ba = Basis(sp_ang, p, tl, kAcc);
+            for (size_t j = 0; j < bp.size(); ++j)
+              for (int i = 0; i < 3; ++i)
+                emit3(row + i, ang.offset + bp[j].var, sb + 3 + (i * 3 + bp[j].dim) * 3, bp[j].val, bv[j].val, ba[j].val);
+          }
+          for (int e = 0; e < n_ee; ++e) {
+            // ee-motion: angular rows = [f_e]x dp_e
+            Locate(sp_motion[e], t, &p, &tl);
+            for (auto& b : Basis(sp_motion[e], p, tl, kPos))
+              for (int i = 0; i < 3; ++i) if (i != b.dim) {
+                int comp; double sg; CrossEntry(i, b.dim, &comp, &sg);
+                emit1(row + i, motion(e).offset + b.var, sb + 30 + e * 6 + comp, sg * b.val);
+              }
+            // ee-force: angular rows = [c - p_e]x df_e ; linear rows = -df_e
+            Locate(sp_force[e], t, &p, &tl);
+            for (auto& b : Basis(sp_force[e], p, tl, kPos)) {
+              for (int i = 0; i < 3; ++i) if (i != b.dim) {
+                int comp; double sg; CrossEntry(i, b.dim, &comp, &sg);
+                emit1(row + i, force(e).offset + b.var, sb + 30 + e * 6 + 3 + comp, sg * b.val);
+              }
+              emit1(row + 3 + b.dim, force(e).offset + b.var, S_ONE, -b.val);
+            }
+          }
+        }
+        break;
+      }
+      case TWB_C_EE_ROM: {  // range_of_motion_constraint.cc
+        if (pl.n_rom) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
+        std::vector<double> ts = SampleTimes(T, sp.dt_constraint_range_of_motion);
+        pl.n_rom = (int)ts.size();
+        pl.S_rom_stride = 9 + 9 * n_ee; pl.S_rom0 = S_top; S_top += pl.S_rom_stride * pl.n_rom;
+        for (int k = 0; k < pl.n_rom; ++k) {
+          tb.rom_samples.push_back(MakeSample(sp_lin, ts[k], zero_slot));
+          tb.rom_samples.push_back(MakeSample(sp_ang, ts[k], zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.rom_samples.push_back(MakeSample(sp_motion[e], ts[k], zero_slot));
+        }
+        for (int e = 0; e < n_ee; ++e) {
+          int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
+          pl.rom_row0[e] = r0;
+          for (int k = 0; k < pl.n_rom; ++k) {
+            const double t = ts[k]; const int row = r0 + 3 * k; const uint32_t sb = pl.S_rom0 + k * pl.S_rom_stride;
+            for (int d = 0; d < 3; ++d) bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
+            int p; double tl;
+            Locate(sp_lin, t, &p, &tl);   // -R^T dc
+            for (auto& b : Basis(sp_lin, p, tl, kPos)) for (int i = 0; i < 3; ++i) emit1(row + i, lin.offset + b.var, sb + i * 3 + b.dim, -b.val);
+            Locate(sp_ang, t, &p, &tl);   // d(R^T r)/dtheta ; row X does not depend on roll
+            for (auto& b : Basis(sp_ang, p, tl, kPos)) for (int i = 0; i < 3; ++i)
+              if (!(i == 0 && b.dim == 0)) emit1(row + i, ang.offset + b.var, sb + 9 + e * 9 + i * 3 + b.dim, b.val);
+            Locate(sp_motion[e], t, &p, &tl);  // R^T dp_e
+            for (auto& b : Basis(sp_motion[e], p, tl, kPos)) for (int i = 0; i < 3; ++i) emit1(row + i, motion(e).offset + b.var, sb + i * 3 + b.dim, b.val);
+          }
+        }
+        break;
+      }
+      case TWB_C_TERRAIN: {  // terrain_constraint.cc
+        for (int e = 0; e < n_ee; ++e) {
+          const NodeSet& mo = motion(e);
+          int r0 = add_set("terrain-ee-motion_" + std::to_string(e), mo.n_nodes - 1);
+          for (int nd = 1; nd < mo.n_nodes; ++nd) {
+            int row = r0 + nd - 1;
+            if (mo.ConstNode(nd)) bound(row, 0.0, 0.0); else bound(row, 0.0, 1e20);
+            TerrainUnit u{}; for (int d = 0; d < 3; ++d) u.xi[d] = XIndex(mo, nd, kPos, d, zero_slot);
+            u.g_row = row; u.s_idx = S_top; S_top += 2;
+            tb.terr.push_back(u);
+            emit1(row, mo.offset + mo.Var(nd, kPos, X), u.s_idx + 0, 1.0);
+            emit1(row, mo.offset + mo.Var(nd, kPos, Y), u.s_idx + 1, 1.0);
+            emit1(row, mo.offset + mo.Var(nd, kPos, Z), S_ONE, 1.0);
+          }
+        }
+        break;
+      }
+      case TWB_C_FORCE: {  // force_constraint.cc
+        for (int e = 0; e < n_ee; ++e) {
+          const NodeSet& fo = force(e); const NodeSet& mo = motion(e);
+          std::vector<int> ids; for (int nd = 0; nd < fo.n_nodes; ++nd) if (!fo.ConstNode(nd)) ids.push_back(nd);
+          int r0 = add_set("force-ee-force_" + std::to_string(e), (int)ids.size() * 5);
+          int row = r0;
+          for (int nd : ids) {
+            // NodesVariablesPhaseBased::GetPhase (:136-143) and GetNodeIDAtStartOfPhase (:145-168)
+            int phase = fo.poly[nd == 0 ? 0 : (nd == fo.n_nodes - 1 ? nd - 1 : nd - 1)].phase;
+            int mnode = 0; for (int i = 0; i < (int)mo.poly.size(); ++i) if (mo.poly[i].phase == phase) { mnode = i; break; }
+            ForceUnit u{};
+            for (int d = 0; d < 3; ++d) { u.xf[d] = XIndex(fo, nd, kPos, d, zero_slot); u.xp[d] = XIndex(mo, mnode, kPos, d, zero_slot); }
+            u.g_row = row; u.s_idx = S_top; S_top += 25;
+            tb.force.push_back(u);
+            bound(row + 0, 0.0, sp.force_limit_in_normal_direction);
+            bound(row + 1, -kInf, 0.0); bound(row + 2, 0.0, +kInf); bound(row + 3, -kInf, 0.0); bound(row + 4, 0.0, +kInf);
+            for (int r = 0; r < 5; ++r) {
+              for (int d = 0; d < 2; ++d) emit1(row + r, mo.offset + mo.Var(mnode, kPos, d), u.s_idx + r * 5 + d, 1.0);
+              for (int d = 0; d < 3; ++d) emit1(row + r, fo.offset + fo.Var(nd, kPos, d), u.s_idx + r * 5 + 2 + d, 1.0);
+            }
+            row += 5;
+          }
+        }
+        break;
+      }
+      case TWB_C_SWING: {  // swing_constraint.cc
+        const double t_swing_avg = 0.3;  // swing_constraint.h:68
+        for (int e = 0; e < n_ee; ++e) {
+          const NodeSet& mo = motion(e);
+          std::vector<int> ids; for (int nd = 0; nd < mo.n_nodes; ++nd) if (!mo.ConstNode(nd)) ids.push_back(nd);
+          int r0 = add_set("swing-ee-motion_" + std::to_string(e), (int)ids.size() * 4);
+          int row = r0;
+          for (int nd : ids) {
+            if (nd == 0 || nd == mo.n_nodes - 1) return fail(TWB_ERR_UNSUPPORTED, "swing node at the spline boundary");
+            SwingUnit u{};
+            for (int d = 0; d < 2; ++d) {
+              u.xc_p[d] = XIndex(mo, nd, kPos, d, zero_slot); u.xc_v[d] = XIndex(mo, nd, kVel, d, zero_slot);
+              u.xprev[d] = XIndex(mo, nd - 1, kPos, d, zero_slot); u.xnext[d] = XIndex(mo, nd + 1, kPos, d, zero_slot);
+            }
+            u.g_row = row; tb.swing.push_back(u);
+            for (int d = 0; d < 2; ++d) {
+              bound(row, 0.0, 0.0);
+              emit1(row, mo.offset + mo.Var(nd, kPos, d), S_ONE, 1.0);
+              emit1(row, mo.offset + mo.Var(nd + 1, kPos, d), S_ONE, -0.5);
+              emit1(row, mo.offset + mo.Var(nd - 1, kPos, d), S_ONE, -0.5);
+              ++row;
+              bound(row, 0.0, 0.0);
+              emit1(row, mo.offset + mo.Var(nd, kVel, d), S_ONE, 1.0);
+              emit1(row, mo.offset + mo.Var(nd + 1, kPos, d), S_ONE, -1.0 / t_swing_avg);
+              emit1(row, mo.offset + mo.Var(nd - 1, kPos, d), S_ONE, +1.0 / t_swing_avg);
+              ++row;
+            }
+          }
+        }
+        break;
+      }
+      case TWB_C_BASE_ACC: {  // spline_acc_constraint.cc
+        for (int which = 0; which < 2; ++which) {
+          const SplineDef& s = which == 0 ? sp_lin : sp_ang;
+          const NodeSet& ns = *s.set;
+          int nj = (int)s.T.size() - 1;
+          int r0 = add_set("splineacc-" + ns.name, 3 * nj);
+          for (int j = 0; j < nj; ++j) {
+            AccUnit u{};
+            u.Tp = s.T[j]; u.Tp2 = std::pow(u.Tp, 2); u.Tp3 = std::pow(u.Tp, 3);
+            u.Tn = s.T[j + 1]; u.Tn2 = std::pow(u.Tn, 2); u.Tn3 = std::pow(u.Tn, 3);
+            u.x0 = ns.offset + j * 6; u.g_row = r0 + 3 * j;
+            tb.acc.push_back(u);
+            // acc_prev - acc_next with the union of both patterns (:67-80)
+            std::map<int, std::pair<int, double>> u_map;  // var -> (dim, value)
+            for (auto& b : Basis(s, j, s.T[j], kAcc)) u_map[b.var] = {b.dim, b.val};
+            for (auto& b : Basis(s, j + 1, 0.0, kAcc)) {
+              auto it = u_map.find(b.var);
+              if (it == u_map.end()) u_map[b.var] = {b.dim, 0.0 - b.val}; else it->second.second = it->second.second - b.val;
+            }
+            for (auto& kv : u_map) emit1(r0 + 3 * j + kv.second.first, ns.offset + kv.first, S_ONE, kv.second.second);
+            for (int d = 0; d < 3; ++d) bound(r0 + 3 * j + d, 0.0, 0.0);
+          }
+        }
+        break;
+      }
+      default: return fail(TWB_ERR_INVALID, "constraint not defined!");
+    }
+  }
+  pl.S_size = S_top;
+  if (S_top + 2 > 65535) return fail(TWB_ERR_UNSUPPORTED, "state vector too large for 16-bit descriptors");
+
+  // ---- CSR assembly: row-major, ascending column (what setFromTriplets yields)
+  std::stable_sort(em.begin(), em.end(), [](const Emit& a, const Emit& b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
+  for (size_t i = 1; i < em.size(); ++i)
+    if (em[i].row == em[i - 1].row && em[i].col == em[i - 1].col) return fail(TWB_ERR_UNSUPPORTED, "duplicate Jacobian entry emitted");
+  nnz = (int)em.size();
+  row_ptr.assign(m + 1, 0); col_idx.resize(nnz);
+  tb.desc.resize(nnz); tb.coef.resize(nnz);
+  for (int s = 0; s < nnz; ++s) {
+    row_ptr[em[s].row + 1]++; col_idx[s] = em[s].col;
+    uint32_t extra_idx = 0;
+    if (em[s].triple) {
+      extra_idx = (uint32_t)(tb.extra.size() / 2);
+      if (extra_idx > 0x7FFFu) return fail(TWB_ERR_UNSUPPORTED, "too many 3-term Jacobian entries");
+      tb.extra.push_back(em[s].c1); tb.extra.push_back(em[s].c2);
+    }
+    tb.desc[s] = MakeDesc(em[s].a, extra_idx, em[s].triple);
+    tb.coef[s] = em[s].c0;
+  }
+  for (int r = 0; r < m; ++r) row_ptr[r + 1] += row_ptr[r];
+
+  // ---- costs (nlp_formulation.cc:333-376, node_cost.cc:53-76)
+  has_cost = false;
+  for (int i = 0; i < sp.n_costs; ++i) {
+    auto add_term = [&](const NodeSet& ns, int deriv, int dim, double w) {
+      bool first = true;
+      for (int nd = 0; nd < ns.n_nodes; ++nd) {
+        int v = ns.Var(nd, deriv, dim);
+        CostEntry c{}; c.xi = (int16_t)(v < 0 ? zero_slot : ns.offset + v); c.grad_col = (int16_t)(v < 0 ? -1 : ns.offset + v);
+        c.pad = first ? 1 : 0; c.weight = w; first = false;
+        tb.cost.push_back(c);
+      }
+    };
+    if (sp.cost_ids[i] == TWB_COST_FORCES) for (int e = 0; e < n_ee; ++e) add_term(force(e), kPos, Z, sp.cost_weights[i]);
+    else if (sp.cost_ids[i] == TWB_COST_EE_MOTION) for (int e = 0; e < n_ee; ++e) { add_term(motion(e), kVel, X, sp.cost_weights[i]); add_term(motion(e), kVel, Y, sp.cost_weights[i]); }
+    else return fail(TWB_ERR_INVALID, "cost not defined!");
+    has_cost = true;
+  }
+
+  // ---- plan scalars
+  pl.n = n; pl.m = m; pl.nnz = nnz; pl.n_ee = n_ee;
+  pl.n_terr = (int)tb.terr.size(); pl.n_force = (int)tb.force.size(); pl.n_swing = (int)tb.swing.size();
+  pl.n_acc = (int)tb.acc.size(); pl.n_totdur = 0; pl.n_cost = (int)tb.cost.size();
+  pl.mass = rb.mass; pl.gravity = 9.80665;  // dynamic_model.cc:37
+  const double* I = rb.inertia;             // single_rigid_body_dynamics.cc:36-44
+  double Ib[9] = {I[0], -I[3], -I[4], -I[3], I[1], -I[5], -I[4], -I[5], I[2]};
+  for (int i = 0; i < 9; ++i) pl.I_b[i] = Ib[i];
+  pl.mu = 0.5;  // height_map.h:136
+  return TWB_OK;
+}
+
+}  // namespace twb

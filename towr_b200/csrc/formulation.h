@@ -1,0 +1,62 @@
+// formulation.h — host-side structure builder.  Turns a twb_spec (the public
+// fields of towr::NlpFormulation + towr::Parameters) into everything that does
+// not depend on the iterate: dimensions, the CSR pattern of the constraint
+// Jacobian, bounds, the initial guess, the component layout, and the tables
+// the CUDA kernels consume (device_tables.h).
+#ifndef TOWR_B200_FORMULATION_H_
+#define TOWR_B200_FORMULATION_H_
+
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/towr_b200.h"
+#include "device_tables.h"
+
+namespace twb {
+
+struct RobotConst {
+  int n_ee;
+  double mass;
+  double inertia[6];  // Ixx, Iyy, Izz, Ixy, Ixz, Iyz
+  double nominal[kMaxEE][3];
+  double max_dev[3];
+};
+bool GetRobot(int id, RobotConst* r);
+double TerrainHeight(int id, double x, double y);
+bool GaitPhases(int n_ee, int combo, double t_total, std::vector<std::vector<double>>* durations,
+                std::vector<bool>* contact_at_start);
+
+struct Component { std::string name; int start; int count; };
+
+// Everything the kernels need, still on the host (capi.cc uploads it).
+struct HostTables {
+  Plan plan{};  // pointer members are filled in after upload
+  std::vector<SplineSample> dyn_samples, rom_samples;
+  std::vector<TerrainUnit> terr;
+  std::vector<ForceUnit> force;
+  std::vector<SwingUnit> swing;
+  std::vector<AccUnit> acc;
+  std::vector<CostEntry> cost;
+  std::vector<uint32_t> desc;
+  std::vector<double> coef, extra;
+};
+
+class Formulation {
+ public:
+  // returns TWB_OK / TWB_ERR_*; `err` gets a one-line reason on failure
+  int Build(const twb_spec& spec, std::string* err);
+
+  int n = 0, m = 0, nnz = 0;
+  std::vector<int> row_ptr, col_idx;
+  std::vector<double> x_lower, x_upper, g_lower, g_upper, x0;
+  std::vector<Component> var_sets, con_sets;
+  bool has_cost = false;
+  bool optimize_timings = false;
+  twb_spec spec{};
+  HostTables tables;
+};
+
+}  // namespace twb
+#endif

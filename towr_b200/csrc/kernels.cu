@@ -1,0 +1,610 @@
+// kernels.cu — sm_100a kernels of the batched NLP evaluation (fp64).
+//
+// One launch evaluates, for every instance of a batch, all constraint values
+// g(x) and all CSR Jacobian values (the arrays ifopt::Problem::
+// EvaluateConstraints / EvalNonzerosOfJacobian hand to IPOPT), plus the
+// NodeCost value and gradient when cost terms exist.
+//
+// A CTA owns G consecutive instances and works in two phases:
+//   phase 1 ("units"): one thread per (instance, unit).  A unit is one time
+//       sample of the dynamic constraint, one time sample of the range-of-
+//       motion constraints (all feet), or one node of the terrain / force /
+//       swing / spline-acc constraints.  The thread evaluates the Hermite
+//       splines it needs from x (staged in shared memory by a TMA bulk copy),
+//       does the nonlinear math (Euler -> R, omega, omega_dot, SRBD, terrain
+//       basis), writes its constraint rows to g and the handful of scalars the
+//       Jacobian of its rows is linear in into the per-instance state vector S
+//       (shared memory).
+//   phase 2 ("fill"): one thread per CSR slot.  value = S[a]*coef (3 terms
+//       for the base-angular block of the dynamic constraint), with (a, coef)
+//       read from the structure-class descriptor table; stores are fully
+//       coalesced 8-byte streams into jac[b][0..nnz).
+//
+// Reference math restated per device function (file:line cited there).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "device_tables.h"
+#include "launch.h"
+
+namespace twb {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---- TMA 1-D bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// ---- cubic Hermite evaluation ------------------------------------------------
+// CubicHermitePolynomial::UpdateCoeff (polynomial.cc:97-104) followed by
+// Polynomial::GetPoint (polynomial.cc:47-61): sum_c d^k/dt^k(t^c) * coeff_c, c = A..D.
+template <bool kVelocity, bool kAcceleration>
+__device__ __forceinline__ void EvalSpline(const SplineSample& s, const double* __restrict__ xs,
+                                           double p[3], double v[3], double a[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double p0 = xs[s.xi[d]], v0 = xs[s.xi[3 + d]], p1 = xs[s.xi[6 + d]], v1 = xs[s.xi[9 + d]];
+    const double C = -(3 * (p0 - p1) + s.T * (2 * v0 + v1)) / s.T2;
+    const double D = (2 * (p0 - p1) + s.T * (v0 + v1)) / s.T3;
+    p[d] = ((p0 + s.t * v0) + s.t2 * C) + s.t3 * D;
+    if (kVelocity) v[d] = (v0 + (2 * s.t) * C) + (3 * s.t2) * D;
+    if (kAcceleration) a[d] = 2 * C + (6 * s.t) * D;
+  }
+}
+
+// ---- Euler angles (roll x, pitch y, yaw z; applied Z-Y'-X'') -------------------
+struct Trig { double sx, cx, sy, cy, sz, cz; };
+__device__ __forceinline__ Trig MakeTrig(const double th[3]) {
+  Trig t; sincos(th[0], &t.sx, &t.cx); sincos(th[1], &t.sy, &t.cy); sincos(th[2], &t.sz, &t.cz); return t;
+}
+// EulerConverter::GetRotationMatrixBaseToWorld, euler_converter.cc:207-221
+__device__ __forceinline__ void RotationMatrix(const Trig& t, double R[3][3]) {
+  R[0][0] = t.cy * t.cz; R[0][1] = t.cz * t.sx * t.sy - t.cx * t.sz; R[0][2] = t.sx * t.sz + t.cx * t.cz * t.sy;
+  R[1][0] = t.cy * t.sz; R[1][1] = t.cx * t.cz + t.sx * t.sy * t.sz; R[1][2] = t.cx * t.sy * t.sz - t.cz * t.sx;
+  R[2][0] = -t.sy;       R[2][1] = t.cy * t.sx;                      R[2][2] = t.cx * t.cy;
+}
+// d(R_ij)/d(theta_d): coefficients of jac_x / jac_y / jac_z in
+// EulerConverter::GetDerivativeOfRotationMatrixWrtNodes, euler_converter.cc:241-268
+__device__ __forceinline__ void RotationDerivative(const Trig& t, double dR[3][3][3]) {
+  const double sx = t.sx, cx = t.cx, sy = t.sy, cy = t.cy, sz = t.sz, cz = t.cz;
+  dR[0][0][0] = 0.0;                         dR[0][0][1] = -cz * sy;      dR[0][0][2] = -cy * sz;
+  dR[0][1][0] = sx * sz + cx * cz * sy;      dR[0][1][1] = cy * cz * sx;  dR[0][1][2] = -cx * cz - sx * sy * sz;
+  dR[0][2][0] = cx * sz - cz * sx * sy;      dR[0][2][1] = cx * cy * cz;  dR[0][2][2] = cz * sx - cx * sy * sz;
+  dR[1][0][0] = 0.0;                         dR[1][0][1] = -sy * sz;      dR[1][0][2] = cy * cz;
+  dR[1][1][0] = cx * sy * sz - cz * sx;      dR[1][1][1] = cy * sx * sz;  dR[1][1][2] = -cx * sz + cz * sx * sy;
+  dR[1][2][0] = -cx * cz - sx * sy * sz;     dR[1][2][1] = cx * cy * sz;  dR[1][2][2] = sx * sz + cx * cz * sy;
+  dR[2][0][0] = 0.0;                         dR[2][0][1] = -cy;           dR[2][0][2] = 0.0;
+  dR[2][1][0] = cx * cy;                     dR[2][1][1] = -sx * sy;      dR[2][1][2] = 0.0;
+  dR[2][2][0] = -cy * sx;                    dR[2][2][1] = -cx * sy;      dR[2][2][2] = 0.0;
+}
+// EulerConverter::DerivOfRotVecMult (euler_converter.cc:223-239) as a dense 3x3:
+// D[row][d] = sum_col v[col] * d(R or R^T)[row][col] / d(theta_d)
+template <bool kInverse>
+__device__ __forceinline__ void RotVecDerivative(const double dR[3][3][3], const double v[3], double D[3][3]) {
+#pragma unroll
+  for (int row = 0; row < 3; ++row)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int col = 0; col < 3; ++col) s += v[col] * (kInverse ? dR[col][row][d] : dR[row][col][d]);
+      D[row][d] = s;
+    }
+}
+__device__ __forceinline__ void Mul33(const double A[3][3], const double B[3][3], double C[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
+}
+__device__ __forceinline__ void MulVec(const double A[3][3], const double v[3], double o[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = A[i][0] * v[0] + A[i][1] * v[1] + A[i][2] * v[2];
+}
+// C = [w]x * A  (Cross(), single_rigid_body_dynamics.cc:46-57)
+__device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3], double C[3][3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    C[0][j] = -w[2] * A[1][j] + w[1] * A[2][j];
+    C[1][j] = w[2] * A[0][j] - w[0] * A[2][j];
+    C[2][j] = -w[1] * A[0][j] + w[0] * A[1][j];
+  }
+}
+
+// ---- DynamicConstraint sample ------------------------------------------------
+// Values: DynamicConstraint::UpdateModel (dynamic_constraint.cc:119-137) +
+//   SingleRigidBodyDynamics::GetDynamicViolation (single_rigid_body_dynamics.cc:76-101).
+// Jacobian state: the 3x3 maps A, B, C with
+//   d(angular rows)/d(base-ang nodes) = A*dtheta + B*dtheta_dot + C*dtheta_ddot
+//   restating SingleRigidBodyDynamics::GetJacobianWrtBaseAng (:123-165) with
+//   EulerConverter::GetDerivOfAng{Vel,Acc}WrtEulerNodes (euler_converter.cc:85-131),
+//   GetDerivMwrtNodes (:168-198), GetDerivMdotwrtNodes (:270-304);
+//   sum of forces, per-foot force and lever arm for the other blocks (:103-121, :167-192).
+__device__ void DynamicUnit(const Plan& P, int k, const double* __restrict__ xs, double* __restrict__ S,
+                            double* __restrict__ g) {
+  const int n_ee = P.n_ee;
+  const SplineSample* ss = P.dyn_samples + (size_t)k * (2 + 2 * n_ee);
+  double* Sk = S + P.S_dyn0 + k * P.S_dyn_stride;
+
+  double c[3], cdd[3], th[3], thd[3], thdd[3], dummy[3];
+  EvalSpline<false, true>(ss[0], xs, c, dummy, cdd);
+  EvalSpline<true, true>(ss[1], xs, th, thd, thdd);
+
+  const Trig tr = MakeTrig(th);
+  const double sy = tr.sy, cy = tr.cy, sz = tr.sz, cz = tr.cz;
+  double R[3][3]; RotationMatrix(tr, R);
+  const double yd = thd[1], zd = thd[2];
+  // EulerConverter::GetM (:133-148) and GetMdot (:150-166)
+  double M[3][3] = {{cy * cz, -sz, 0.0}, {cy * sz, cz, 0.0}, {-sy, 0.0, 1.0}};
+  double Md[3][3] = {{-cz * sy * yd - cy * sz * zd, -cz * zd, 0.0}, {cy * cz * zd - sy * sz * yd, -sz * zd, 0.0}, {-cy * yd, 0.0, 0.0}};
+  double om[3], omd[3];
+  om[0] = M[0][0] * thd[0] + M[0][1] * thd[1];
+  om[1] = M[1][0] * thd[0] + M[1][1] * thd[1];
+  om[2] = M[2][0] * thd[0] + thd[2];
+  omd[0] = (Md[0][0] * thd[0] + Md[0][1] * thd[1]) + (M[0][0] * thdd[0] + M[0][1] * thdd[1]);
+  omd[1] = (Md[1][0] * thd[0] + Md[1][1] * thd[1]) + (M[1][0] * thdd[0] + M[1][1] * thdd[1]);
+  omd[2] = (Md[2][0] * thd[0]) + (M[2][0] * thdd[0] + thdd[2]);
+
+  // I_w = R I_b R^T
+  double Ib[3][3], RIb[3][3], Rt[3][3], Iw[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { Ib[i][j] = P.I_b[i * 3 + j]; Rt[i][j] = R[j][i]; }
+  Mul33(R, Ib, RIb); Mul33(RIb, Rt, Iw);
+
+  // feet
+  double fsum[3] = {0, 0, 0}, tau[3] = {0, 0, 0};
+  for (int e = 0; e < n_ee; ++e) {
+    double pe[3], f[3];
+    EvalSpline<false, false>(ss[2 + e], xs, pe, dummy, dummy);
+    EvalSpline<false, false>(ss[2 + n_ee + e], xs, f, dummy, dummy);
+    const double r[3] = {c[0] - pe[0], c[1] - pe[1], c[2] - pe[2]};
+    tau[0] += f[1] * r[2] - f[2] * r[1];
+    tau[1] += f[2] * r[0] - f[0] * r[2];
+    tau[2] += f[0] * r[1] - f[1] * r[0];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { fsum[d] += f[d]; Sk[30 + e * 6 + d] = f[d]; Sk[30 + e * 6 + 3 + d] = r[d]; }
+  }
+  Sk[0] = fsum[0]; Sk[1] = fsum[1]; Sk[2] = fsum[2];
+
+  double Iw_om[3], Iw_omd[3];
+  MulVec(Iw, om, Iw_om); MulVec(Iw, omd, Iw_omd);
+  if (g) {
+    const double wx[3] = {om[1] * Iw_om[2] - om[2] * Iw_om[1], om[2] * Iw_om[0] - om[0] * Iw_om[2], om[0] * Iw_om[1] - om[1] * Iw_om[0]};
+    double* gk = g + P.dyn_row0 + 6 * k;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      gk[d] = Iw_omd[d] + wx[d] - tau[d];
+      const double grav = (d == 2) ? -P.mass * P.gravity : 0.0;
+      gk[3 + d] = P.mass * cdd[d] - fsum[d] - grav;
+    }
+  }
+
+  // ---- base-angular Jacobian maps
+  double dR[3][3][3]; RotationDerivative(tr, dR);
+  // d(omega)/d(theta) (GetDerivMwrtNodes contracted with theta_dot) ; d(omega)/d(theta_dot) = M
+  double Jw[3][3] = {{0.0, thd[0] * (-cz * sy), thd[0] * (-cy * sz) + thd[1] * (-cz)},
+                     {0.0, thd[0] * (-sy * sz), thd[0] * (cy * cz) + thd[1] * (-sz)},
+                     {0.0, thd[0] * (-cy), 0.0}};
+  // d(omega_dot)/d(theta): theta_dot * dMdot/dtheta + theta_ddot * dM/dtheta
+  double Jwd_th[3][3] = {
+      {0.0, thd[0] * (-cy * cz * yd + sy * sz * zd) + thdd[0] * (-cz * sy),
+            (thd[0] * (sy * sz * yd - cy * cz * zd) + thd[1] * (sz * zd)) + (thdd[0] * (-cy * sz) + thdd[1] * (-cz))},
+      {0.0, thd[0] * (-cy * sz * yd - cz * sy * zd) + thdd[0] * (-sy * sz),
+            (thd[0] * (-cz * sy * yd - cy * sz * zd) + thd[1] * (-cz * zd)) + (thdd[0] * (cy * cz) + thdd[1] * (-sz))},
+      {0.0, thd[0] * (sy * yd) + thdd[0] * (-cy), 0.0}};
+  // d(omega_dot)/d(theta_dot): theta_dot * dMdot/dtheta_dot + Mdot
+  double Jwd_thd[3][3] = {{Md[0][0], thd[0] * (-cz * sy) + Md[0][1], thd[0] * (-cy * sz) + thd[1] * (-cz)},
+                          {Md[1][0], thd[0] * (-sy * sz) + Md[1][1], thd[0] * (cy * cz) + thd[1] * (-sz)},
+                          {Md[2][0], thd[0] * (-cy), 0.0}};
+
+  double v11[3], v21[3], tmp[3];
+  MulVec(Rt, omd, tmp); MulVec(Ib, tmp, v11);   // I_b R^T omega_dot
+  MulVec(Rt, om, tmp);  MulVec(Ib, tmp, v21);   // I_b R^T omega
+  double D11[3][3], D12[3][3], D21[3][3], D22[3][3], T1[3][3], T2[3][3];
+  RotVecDerivative<false>(dR, v11, D11); RotVecDerivative<true>(dR, omd, D12);
+  RotVecDerivative<false>(dR, v21, D21); RotVecDerivative<true>(dR, om, D22);
+
+  double A[3][3], Bm[3][3], C[3][3];
+  // jac1 = D11 + R I_b D12 + I_w d(omega_dot)
+  Mul33(RIb, D12, T1); Mul33(Iw, Jwd_th, T2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) A[i][d] = (D11[i][d] + T1[i][d]) + T2[i][d];
+  Mul33(Iw, Jwd_thd, Bm);
+  Mul33(Iw, M, C);
+  // jac2 = [omega]x (D21 + R I_b D22 + I_w d(omega)) - [I_w omega]x d(omega)
+  double Gth[3][3], X1[3][3], X2[3][3];
+  Mul33(RIb, D22, T1); Mul33(Iw, Jw, T2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Gth[i][d] = (D21[i][d] + T1[i][d]) + T2[i][d];
+  CrossMul(om, Gth, X1); CrossMul(Iw_om, Jw, X2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) A[i][d] += X1[i][d] - X2[i][d];
+  CrossMul(om, C, X1); CrossMul(Iw_om, M, X2);   // I_w d(omega)/d(theta_dot) = I_w M = C
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Bm[i][d] += X1[i][d] - X2[i][d];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double* q = Sk + 3 + (i * 3 + d) * 3;
+      q[0] = A[i][d]; q[1] = Bm[i][d]; q[2] = C[i][d];
+    }
+}
+
+// ---- RangeOfMotionConstraint sample (all feet) --------------------------------
+// range_of_motion_constraint.cc:58-109: g = R^T (p_ee - c); Jacobian state R^T and
+// D_e = d(R^T r_e)/d(theta) (DerivOfRotVecMult(t, r_W, true)).
+__device__ void RomUnit(const Plan& P, int k, const double* __restrict__ xs, double* __restrict__ S,
+                        double* __restrict__ g) {
+  const int n_ee = P.n_ee;
+  const SplineSample* ss = P.rom_samples + (size_t)k * (2 + n_ee);
+  double* Sk = S + P.S_rom0 + k * P.S_rom_stride;
+  double c[3], th[3], dummy[3];
+  EvalSpline<false, false>(ss[0], xs, c, dummy, dummy);
+  EvalSpline<false, false>(ss[1], xs, th, dummy, dummy);
+  const Trig tr = MakeTrig(th);
+  double R[3][3]; RotationMatrix(tr, R);
+  double dR[3][3][3]; RotationDerivative(tr, dR);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Sk[i * 3 + d] = R[d][i];
+  for (int e = 0; e < n_ee; ++e) {
+    double pe[3];
+    EvalSpline<false, false>(ss[2 + e], xs, pe, dummy, dummy);
+    const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
+    if (g) {
+      double* ge = g + P.rom_row0[e] + 3 * k;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ge[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
+    }
+    double D[3][3]; RotVecDerivative<true>(dR, r, D);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Sk[9 + e * 9 + i * 3 + d] = D[i][d];
+  }
+}
+
+// ---- analytic terrains: height_map_examples.cc:35-211 ------------------------
+struct TerrainPoint { double h, hx, hy, hxx; };
+__device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) {
+  TerrainPoint o{0.0, 0.0, 0.0, 0.0};
+  switch (id) {
+    case 1: {  // Block
+      const double start = 0.7, eps = 0.03, len = 3.5, height = 0.5; const double slope = height / eps;
+      if (start <= x && x <= start + eps) { o.h = slope * (x - start); o.hx = slope; }
+      if (start + eps <= x && x <= start + len) o.h = height;
+      break; }
+    case 2:  // Stairs
+      if (x >= 1.0) o.h = 0.2;
+      if (x >= 1.0 + 0.4) o.h = 0.4;
+      if (x >= 1.0 + 0.4 + 1.0) o.h = 0.0;
+      break;
+    case 3: {  // Gap
+      const double gs = 1.0, w = 0.5, hh = 1.5; const double xc = gs + w / 2.0;
+      const double a = (4 * hh) / (w * w), b = -(8 * hh * xc) / (w * w), c = -(hh * (w - 2 * xc) * (w + 2 * xc)) / (w * w);
+      if (gs <= x && x <= gs + w) { o.h = a * x * x + b * x + c; o.hx = 2 * a * x + b; o.hxx = 2 * a; }
+      break; }
+    case 4: {  // Slope
+      const double s0 = 1.0, up = 1.0, down = 1.0, hc = 0.7; const double slope = hc / up;
+      if (x >= s0) { o.h = slope * (x - s0); o.hx = slope; }
+      if (x >= s0 + up) { o.h = hc - slope * (x - (s0 + up)); o.hx = -slope; }
+      if (x >= (s0 + up) + down) { o.h = 0.0; o.hx = 0.0; }
+      break; }
+    case 5:  // Chimney
+      if (1.0 <= x && x <= 1.0 + 1.5) { o.h = 3.0 * (y - 0.5); o.hy = 3.0; }
+      break;
+    case 6:  // ChimneyLR
+      if (0.5 <= x && x <= 0.5 + 1.0) { o.h = 2.0 * (y - 0.5); o.hy = 2.0; }
+      if (0.5 + 1.0 <= x && x <= 0.5 + 2 * 1.0) { o.h = -2.0 * (y + 0.5); o.hy = -2.0; }
+      break;
+    default: break;  // FlatGround(0.0)
+  }
+  return o;
+}
+
+// TerrainConstraint, terrain_constraint.cc:59-108
+__device__ __forceinline__ void TerrainUnitEval(const TerrainUnit& u, int terrain, const double* __restrict__ xs,
+                                                double* __restrict__ S, double* __restrict__ g) {
+  const double px = xs[u.xi[0]], py = xs[u.xi[1]], pz = xs[u.xi[2]];
+  const TerrainPoint tp = EvalTerrain(terrain, px, py);
+  if (g) g[u.g_row] = pz - tp.h;
+  S[u.s_idx + 0] = -tp.hx; S[u.s_idx + 1] = -tp.hy;
+}
+
+// normalised vector and HeightMap::GetDerivativeOfNormalizedBasisWrt (height_map.cc:62-91,140-146):
+// out[i] = (1/|v|^2 * (|v| * delta(i,dim) - v[dim] * v_hat[i])) * dv[i]   (element-wise, as the reference)
+__device__ __forceinline__ void Normalize(const double v[3], double vh[3], double* sn, double* nrm) {
+  *sn = v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; *nrm = sqrt(*sn);
+  vh[0] = v[0] / *nrm; vh[1] = v[1] / *nrm; vh[2] = v[2] / *nrm;
+}
+__device__ __forceinline__ void NormalizedDeriv(const double v[3], const double vh[3], double sn, double nrm, int dim,
+                                                const double dv[3], double out[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double unit = (i == dim) ? 1.0 : 0.0;
+    out[i] = (1 / sn * (nrm * unit - v[dim] * vh[i])) * dv[i];
+  }
+}
+__device__ __forceinline__ double Dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// ForceConstraint, force_constraint.cc:64-171
+__device__ void ForceUnitEval(const ForceUnit& u, int terrain, double mu, const double* __restrict__ xs,
+                              double* __restrict__ S, double* __restrict__ g) {
+  const double px = xs[u.xp[0]], py = xs[u.xp[1]];
+  const double f[3] = {xs[u.xf[0]], xs[u.xf[1]], xs[u.xf[2]]};
+  const TerrainPoint tp = EvalTerrain(terrain, px, py);
+  // HeightMap::GetNormal / GetTangent1 / GetTangent2, height_map.cc:93-138
+  const double vn[3] = {-tp.hx, -tp.hy, 1.0}, vt1[3] = {1.0, 0.0, tp.hx}, vt2[3] = {0.0, 1.0, tp.hy};
+  double n[3], t1[3], t2[3], sn_n, nr_n, sn_1, nr_1, sn_2, nr_2;
+  Normalize(vn, n, &sn_n, &nr_n); Normalize(vt1, t1, &sn_1, &nr_1); Normalize(vt2, t2, &sn_2, &nr_2);
+  double a1[3], b1[3], a2[3], b2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    a1[d] = t1[d] - mu * n[d]; b1[d] = t1[d] + mu * n[d];
+    a2[d] = t2[d] - mu * n[d]; b2[d] = t2[d] + mu * n[d];
+  }
+  if (g) {
+    double* gr = g + u.g_row;
+    gr[0] = Dot3(f, n); gr[1] = Dot3(f, a1); gr[2] = Dot3(f, b1); gr[3] = Dot3(f, a2); gr[4] = Dot3(f, b2);
+  }
+  double* Su = S + u.s_idx;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    Su[0 * 5 + 2 + d] = n[d]; Su[1 * 5 + 2 + d] = a1[d]; Su[2 * 5 + 2 + d] = b1[d];
+    Su[3 * 5 + 2 + d] = a2[d]; Su[4 * 5 + 2 + d] = b2[d];
+  }
+  // second derivatives of the height: only d2h/dx2 exists in the analytic terrains
+#pragma unroll
+  for (int dim = 0; dim < 2; ++dim) {
+    const double hxd = (dim == 0) ? tp.hxx : 0.0;   // d2h/(dx ddim)
+    const double hyd = 0.0;                          // d2h/(dy ddim)
+    const double dvn[3] = {-hxd, -hyd, 0.0}, dvt1[3] = {0.0, 0.0, hxd}, dvt2[3] = {0.0, 0.0, hyd};
+    double dn[3], dt1[3], dt2[3];
+    NormalizedDeriv(vn, n, sn_n, nr_n, dim, dvn, dn);
+    NormalizedDeriv(vt1, t1, sn_1, nr_1, dim, dvt1, dt1);
+    NormalizedDeriv(vt2, t2, sn_2, nr_2, dim, dvt2, dt2);
+    double m1[3], p1[3], m2[3], p2[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      m1[d] = dt1[d] - mu * dn[d]; p1[d] = dt1[d] + mu * dn[d];
+      m2[d] = dt2[d] - mu * dn[d]; p2[d] = dt2[d] + mu * dn[d];
+    }
+    Su[0 * 5 + dim] = Dot3(f, dn); Su[1 * 5 + dim] = Dot3(f, m1); Su[2 * 5 + dim] = Dot3(f, p1);
+    Su[3 * 5 + dim] = Dot3(f, m2); Su[4 * 5 + dim] = Dot3(f, p2);
+  }
+}
+
+// SwingConstraint::GetValues, swing_constraint.cc:57-83 (Jacobian is constant)
+__device__ __forceinline__ void SwingUnitEval(const SwingUnit& u, const double* __restrict__ xs, double* __restrict__ g) {
+  if (!g) return;
+  const double t_swing_avg = 0.3;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double prev = xs[u.xprev[d]], next = xs[u.xnext[d]];
+    const double dist = next - prev;
+    const double center = prev + 0.5 * dist;
+    const double des_vel = dist / t_swing_avg;
+    g[u.g_row + 2 * d] = xs[u.xc_p[d]] - center;
+    g[u.g_row + 2 * d + 1] = xs[u.xc_v[d]] - des_vel;
+  }
+}
+
+// SplineAccConstraint::GetValues, spline_acc_constraint.cc:49-65 (Jacobian constant for fixed durations)
+__device__ __forceinline__ void AccUnitEval(const AccUnit& u, const double* __restrict__ xs, double* __restrict__ g) {
+  if (!g) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double p0 = xs[u.x0 + d], v0 = xs[u.x0 + 3 + d], p1 = xs[u.x0 + 6 + d], v1 = xs[u.x0 + 9 + d];
+    const double p2 = xs[u.x0 + 12 + d], v2 = xs[u.x0 + 15 + d];
+    const double Cp = -(3 * (p0 - p1) + u.Tp * (2 * v0 + v1)) / u.Tp2;
+    const double Dp = (2 * (p0 - p1) + u.Tp * (v0 + v1)) / u.Tp3;
+    const double Cn = -(3 * (p1 - p2) + u.Tn * (2 * v1 + v2)) / u.Tn2;
+    const double a_prev = 2 * Cp + (6 * u.Tp) * Dp;
+    const double a_next = 2 * Cn;
+    g[u.g_row + d] = a_prev - a_next;
+  }
+}
+
+// ---- the kernel ---------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, double* __restrict__ jac,
+           double* __restrict__ cost, double* __restrict__ grad, int* __restrict__ status,
+           const int* __restrict__ terrain_ids, int default_terrain, int B, unsigned flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int tid = threadIdx.x;
+  const int n = P.n, m = P.m, nnz = P.nnz;
+  const int xs_stride = (n + 2) & ~1;         // even -> every row stays 16-byte aligned
+  const int S_stride = (P.S_size + 1) & ~1;
+  double* xs_all = reinterpret_cast<double*>(smem_raw);
+  double* S_all = xs_all + G * xs_stride;
+  const int b0 = blockIdx.x * G;
+  const int nb = min(G, B - b0);
+
+  // ---- stage x: one TMA bulk copy per instance when rows are 16-byte aligned
+  const bool tma_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (tma_ok) {
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&mbar, (uint32_t)(nb * n * sizeof(double)));
+      for (int gi = 0; gi < nb; ++gi)
+        bulk_g2s(xs_all + gi * xs_stride, x + (size_t)(b0 + gi) * n, (uint32_t)(n * sizeof(double)), &mbar);
+    }
+  } else {
+    for (int gi = 0; gi < nb; ++gi)
+      for (int i = tid; i < n; i += kThreads) xs_all[gi * xs_stride + i] = x[(size_t)(b0 + gi) * n + i];
+  }
+  if (tid < nb) {
+    xs_all[tid * xs_stride + n] = 0.0; S_all[tid * S_stride] = 1.0;
+    if (status) status[b0 + tid] = 0;
+  }
+  if (tma_ok) { while (!mbar_try_wait(&mbar, 0)) {} }
+  __syncthreads();
+
+  const bool want_g = (flags & 1u) != 0, want_jac = (flags & 2u) != 0, want_cost = (flags & 4u) != 0 && P.n_cost > 0;
+
+  // ---- phase 1: units.  Item ranges are padded to warp granularity so a warp runs one unit type.
+  auto pad32 = [](int v) { return (v + 31) & ~31; };
+  const int c_dyn = nb * P.n_dyn, c_rom = nb * P.n_rom, c_force = nb * P.n_force, c_terr = nb * P.n_terr;
+  const int c_swing = nb * P.n_swing, c_acc = nb * P.n_acc, c_cost = want_cost ? nb : 0;
+  const int o_rom = pad32(c_dyn), o_force = o_rom + pad32(c_rom), o_terr = o_force + pad32(c_force);
+  const int o_swing = o_terr + pad32(c_terr), o_acc = o_swing + pad32(c_swing), o_cost = o_acc + pad32(c_acc);
+  const int total = o_cost + pad32(c_cost);
+  for (int item = tid; item < total; item += kThreads) {
+    if (item < o_rom) {
+      if (item < c_dyn) {
+        const int gi = item / P.n_dyn, k = item - gi * P.n_dyn;
+        DynamicUnit(P, k, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+      }
+    } else if (item < o_force) {
+      const int it = item - o_rom;
+      if (it < c_rom) {
+        const int gi = it / P.n_rom, k = it - gi * P.n_rom;
+        RomUnit(P, k, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+      }
+    } else if (item < o_terr) {
+      const int it = item - o_force;
+      if (it < c_force) {
+        const int gi = it / P.n_force, u = it - gi * P.n_force;
+        const int terrain = terrain_ids ? terrain_ids[b0 + gi] : default_terrain;
+        ForceUnitEval(P.force[u], terrain, P.mu, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+      }
+    } else if (item < o_swing) {
+      const int it = item - o_terr;
+      if (it < c_terr) {
+        const int gi = it / P.n_terr, u = it - gi * P.n_terr;
+        const int terrain = terrain_ids ? terrain_ids[b0 + gi] : default_terrain;
+        TerrainUnitEval(P.terr[u], terrain, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+      }
+    } else if (item < o_acc) {
+      const int it = item - o_swing;
+      if (it < c_swing) {
+        const int gi = it / P.n_swing, u = it - gi * P.n_swing;
+        SwingUnitEval(P.swing[u], xs_all + gi * xs_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+      }
+    } else if (item < o_cost) {
+      const int it = item - o_acc;
+      if (it < c_acc) {
+        const int gi = it / P.n_acc, u = it - gi * P.n_acc;
+        AccUnitEval(P.acc[u], xs_all + gi * xs_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+      }
+    } else {
+      const int gi = item - o_cost;
+      if (gi < c_cost) {
+        // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs)
+        // and the dense gradient row (node_cost.cc:65-76), in the reference's order.
+        const double* xr = xs_all + gi * xs_stride;
+        double* gr = grad ? grad + (size_t)(b0 + gi) * n : nullptr;
+        if (gr) for (int i = 0; i < n; ++i) gr[i] = 0.0;
+        double total_cost = 0.0, term = 0.0;
+        for (int i = 0; i < P.n_cost; ++i) {
+          const CostEntry ce = P.cost[i];
+          if (ce.pad && i > 0) { total_cost += term; term = 0.0; }
+          const double val = xr[ce.xi];
+          term += ce.weight * (val * val);
+          if (gr && ce.grad_col >= 0) gr[ce.grad_col] += ce.weight * 2.0 * val;
+        }
+        total_cost += term;
+        if (cost) cost[b0 + gi] = total_cost;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: fill the CSR value arrays
+  if (want_jac) {
+    bool bad = false;
+    for (int slot = tid; slot < nnz; slot += kThreads) {
+      const uint32_t d = __ldg(P.desc + slot);
+      const double c0 = __ldg(P.coef + slot);
+      const uint32_t a = d & 0xFFFFu;
+      double c1 = 0.0, c2 = 0.0;
+      const bool triple = (d & kDescTriple) != 0;
+      if (triple) { const uint32_t e = (d >> 16) & 0x7FFFu; c1 = __ldg(P.extra + 2 * e); c2 = __ldg(P.extra + 2 * e + 1); }
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        if (gi < nb) {
+          const double* Sg = S_all + gi * S_stride;
+          double v = Sg[a] * c0;
+          if (triple) v = (v + Sg[a + 1] * c1) + Sg[a + 2] * c2;
+          bad |= !isfinite(v);
+          __stcs(jac + (size_t)(b0 + gi) * nnz + slot, v);
+        }
+      }
+    }
+    if (status && bad) {
+      // conservative: flags every instance of the CTA group
+      for (int gi = 0; gi < nb; ++gi) atomicOr(status + b0 + gi, 1);
+    }
+  }
+}
+
+}  // namespace
+
+size_t EvalSmemBytes(const Plan& P, int G) {
+  const int xs_stride = (P.n + 2) & ~1, S_stride = (P.S_size + 1) & ~1;
+  return (size_t)G * (xs_stride + S_stride) * sizeof(double);
+}
+
+int LaunchEval(const Plan& P, int G, const double* x, double* g, double* jac, double* cost, double* grad,
+               int* status, const int* terrain_ids, int default_terrain, int B, unsigned flags, cudaStream_t stream,
+               int* n_launches) {
+  if (B <= 0) return 0;
+  int launches = 0;
+  const size_t smem = EvalSmemBytes(P, G);
+  const int grid = (B + G - 1) / G;
+  cudaError_t e = cudaSuccess;
+#define TWB_LAUNCH(GG)                                                                                         \
+  do {                                                                                                         \
+    e = cudaFuncSetAttribute(EvalKernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e == cudaSuccess)                                                                                      \
+      EvalKernel<GG><<<grid, kThreads, smem, stream>>>(P, x, g, jac, cost, grad, status, terrain_ids,          \
+                                                       default_terrain, B, flags);                             \
+  } while (0)
+  switch (G) {
+    case 1: TWB_LAUNCH(1); break;
+    case 2: TWB_LAUNCH(2); break;
+    case 4: TWB_LAUNCH(4); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+#undef TWB_LAUNCH
+  ++launches;
+  if (n_launches) *n_launches = launches;
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace twb

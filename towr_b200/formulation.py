@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference interface for the NLP-evaluation path.
+
+``NlpFormulation`` / ``Parameters`` / ``BaseState`` / ``GaitGenerator`` keep the
+field and method names of the reference (towr/include/towr/nlp_formulation.h:
+100-105, parameters.h:139-214, variables/state.h, initialization/
+gait_generator.h) so a towr user fills them the same way; ``Problem`` stands
+where ``ifopt::Problem`` stands (structure, bounds, initial guess, evaluation),
+for a whole batch of instances.  All work happens in libtowr_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import lib, check
+
+
+class Node:
+    """towr::Node (variables/state.h): value and first derivative."""
+
+    def __init__(self):
+        self.p = np.zeros(3)
+        self.v = np.zeros(3)
+
+
+class BaseState:
+    """towr::BaseState: lin (x,y,z) and ang (roll,pitch,yaw) nodes."""
+
+    def __init__(self):
+        self.lin = Node()
+        self.ang = Node()
+
+
+class Parameters:
+    """towr::Parameters (parameters.cc:40-73 defaults come from the C ABI)."""
+
+    def __init__(self, robot=capi.MONOPED):
+        s = capi.Spec()
+        check(lib.twb_spec_default(C.byref(s), robot))
+        self.ee_phase_durations_ = []
+        self.ee_in_contact_at_start_ = []
+        self.constraints_ = [s.constraints[i] for i in range(s.n_constraints)]
+        self.costs_ = []
+        self.dt_constraint_dynamic_ = s.dt_constraint_dynamic
+        self.dt_constraint_range_of_motion_ = s.dt_constraint_range_of_motion
+        self.dt_constraint_base_motion_ = s.dt_constraint_base_motion
+        self.duration_base_polynomial_ = s.duration_base_polynomial
+        self.ee_polynomials_per_swing_phase_ = s.ee_polynomials_per_swing_phase
+        self.force_polynomials_per_stance_phase_ = s.force_polynomials_per_stance_phase
+        self.force_limit_in_normal_direction_ = s.force_limit_in_normal_direction
+        self.bounds_final_lin_pos_ = [d for d in range(3) if s.bounds_final_lin_pos[d]]
+        self.bounds_final_lin_vel_ = [d for d in range(3) if s.bounds_final_lin_vel[d]]
+        self.bounds_final_ang_pos_ = [d for d in range(3) if s.bounds_final_ang_pos[d]]
+        self.bounds_final_ang_vel_ = [d for d in range(3) if s.bounds_final_ang_vel[d]]
+        self.bound_phase_duration_ = (s.bound_phase_duration_min, s.bound_phase_duration_max)
+
+    def OptimizePhaseDurations(self):
+        self.constraints_.append(capi.C_TOTAL_TIME)
+
+    def IsOptimizeTimings(self):
+        return capi.C_TOTAL_TIME in self.constraints_
+
+    def GetEECount(self):
+        return len(self.ee_in_contact_at_start_)
+
+    def GetPhaseCount(self, ee):
+        return len(self.ee_phase_durations_[ee])
+
+    def GetTotalTime(self):
+        return float(sum(self.ee_phase_durations_[0])) if self.ee_phase_durations_ else 0.0
+
+
+class GaitGenerator:
+    """towr::GaitGenerator::MakeGaitGenerator(n_ee) + SetCombo + GetPhaseDurations."""
+
+    def __init__(self, n_ee):
+        self.n_ee = n_ee
+        self.combo = 0
+
+    @staticmethod
+    def MakeGaitGenerator(leg_count):
+        return GaitGenerator(leg_count)
+
+    def SetCombo(self, combo):
+        self.combo = int(combo)
+
+    def _spec(self, t_total):
+        s = capi.Spec()
+        check(lib.twb_spec_set_gait(C.byref(s), self.n_ee, self.combo, float(t_total)))
+        return s
+
+    def GetPhaseDurations(self, t_total, ee):
+        s = self._spec(t_total)
+        return [s.phase_durations[ee][i] for i in range(s.n_phases[ee])]
+
+    def IsInContactAtStart(self, ee):
+        return bool(self._spec(1.0).in_contact_at_start[ee])
+
+
+def robot_info(robot):
+    n_ee, mass = C.c_int(), C.c_double()
+    inertia = (C.c_double * 6)()
+    nominal = ((C.c_double * 3) * capi.MAX_EE)()
+    dev = (C.c_double * 3)()
+    check(lib.twb_robot_info(robot, C.byref(n_ee), C.byref(mass), inertia,
+                             C.cast(nominal, C.POINTER(C.c_double)), dev))
+    return dict(n_ee=n_ee.value, mass=mass.value, inertia=list(inertia),
+                nominal_stance=[list(nominal[e]) for e in range(n_ee.value)], max_dev=list(dev))
+
+
+def terrain_height(terrain, x, y):
+    return lib.twb_terrain_height(int(terrain), float(x), float(y))
+
+
+class NlpFormulation:
+    """towr::NlpFormulation: public fields + to_spec() instead of Get*Sets()."""
+
+    def __init__(self, robot=capi.MONOPED, terrain=capi.FLAT):
+        self.initial_base_ = BaseState()
+        self.final_base_ = BaseState()
+        self.initial_ee_W_ = []
+        self.model_ = robot
+        self.terrain_ = terrain
+        self.params_ = Parameters(robot)
+
+    def to_spec(self):
+        p = self.params_
+        s = capi.Spec()
+        check(lib.twb_spec_default(C.byref(s), self.model_))
+        s.terrain = int(self.terrain_)
+        s.n_ee = p.GetEECount()
+        if s.n_ee > capi.MAX_EE or len(self.initial_ee_W_) != s.n_ee:
+            raise ValueError("initial_ee_W_ / ee_in_contact_at_start_ size mismatch")
+        for ee in range(s.n_ee):
+            d = p.ee_phase_durations_[ee]
+            if len(d) > capi.MAX_PHASES:
+                raise ValueError("too many phases")
+            s.n_phases[ee] = len(d)
+            for i, v in enumerate(d):
+                s.phase_durations[ee][i] = v
+            s.in_contact_at_start[ee] = int(bool(p.ee_in_contact_at_start_[ee]))
+            for k in range(3):
+                s.initial_ee_W[ee][k] = float(self.initial_ee_W_[ee][k])
+        for k in range(3):
+            s.initial_base_lin_pos[k] = float(self.initial_base_.lin.p[k])
+            s.initial_base_lin_vel[k] = float(self.initial_base_.lin.v[k])
+            s.initial_base_ang_pos[k] = float(self.initial_base_.ang.p[k])
+            s.initial_base_ang_vel[k] = float(self.initial_base_.ang.v[k])
+            s.final_base_lin_pos[k] = float(self.final_base_.lin.p[k])
+            s.final_base_lin_vel[k] = float(self.final_base_.lin.v[k])
+            s.final_base_ang_pos[k] = float(self.final_base_.ang.p[k])
+            s.final_base_ang_vel[k] = float(self.final_base_.ang.v[k])
+            s.bounds_final_lin_pos[k] = int(k in p.bounds_final_lin_pos_)
+            s.bounds_final_lin_vel[k] = int(k in p.bounds_final_lin_vel_)
+            s.bounds_final_ang_pos[k] = int(k in p.bounds_final_ang_pos_)
+            s.bounds_final_ang_vel[k] = int(k in p.bounds_final_ang_vel_)
+        s.duration_base_polynomial = p.duration_base_polynomial_
+        s.force_polynomials_per_stance_phase = p.force_polynomials_per_stance_phase_
+        s.ee_polynomials_per_swing_phase = p.ee_polynomials_per_swing_phase_
+        s.force_limit_in_normal_direction = p.force_limit_in_normal_direction_
+        s.dt_constraint_range_of_motion = p.dt_constraint_range_of_motion_
+        s.dt_constraint_dynamic = p.dt_constraint_dynamic_
+        s.dt_constraint_base_motion = p.dt_constraint_base_motion_
+        s.bound_phase_duration_min, s.bound_phase_duration_max = p.bound_phase_duration_
+        s.n_constraints = len(p.constraints_)
+        for i, c in enumerate(p.constraints_):
+            s.constraints[i] = int(c)
+        s.n_costs = len(p.costs_)
+        for i, (cid, w) in enumerate(p.costs_):
+            s.cost_ids[i] = int(cid)
+            s.cost_weights[i] = float(w)
+        return s
+
+
+class Problem:
+    """One structure class: what ifopt::Problem exposes besides evaluation."""
+
+    def __init__(self, spec):
+        self.spec = spec
+        self._h = C.c_void_p()
+        check(lib.twb_problem_create(C.byref(spec), C.byref(self._h)))
+        n, m, nnz = C.c_int(), C.c_int(), C.c_int()
+        check(lib.twb_problem_dims(self._h, C.byref(n), C.byref(m), C.byref(nnz)))
+        self.n, self.m, self.nnz = n.value, m.value, nnz.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.twb_problem_destroy(self._h)
+            self._h = None
+
+    # ifopt::Problem::GetNumberOfOptimizationVariables / GetNumberOfConstraints
+    def GetNumberOfOptimizationVariables(self):
+        return self.n
+
+    def GetNumberOfConstraints(self):
+        return self.m
+
+    def structure(self):
+        """(iRow, jCol) as IpoptAdapter reads them from GetJacobianOfConstraints()."""
+        r = np.empty(self.nnz, np.int32)
+        c = np.empty(self.nnz, np.int32)
+        ip = C.POINTER(C.c_int)
+        check(lib.twb_problem_structure(self._h, r.ctypes.data_as(ip), c.ctypes.data_as(ip)))
+        return r, c
+
+    def row_ptr(self):
+        rp = np.empty(self.m + 1, np.int32)
+        check(lib.twb_problem_row_ptr(self._h, rp.ctypes.data_as(C.POINTER(C.c_int))))
+        return rp
+
+    def bounds(self):
+        """GetBoundsOnOptimizationVariables / GetBoundsOnConstraints -> xl, xu, gl, gu."""
+        dp = C.POINTER(C.c_double)
+        xl, xu = np.empty(self.n), np.empty(self.n)
+        gl, gu = np.empty(self.m), np.empty(self.m)
+        check(lib.twb_problem_bounds(self._h, xl.ctypes.data_as(dp), xu.ctypes.data_as(dp),
+                                     gl.ctypes.data_as(dp), gu.ctypes.data_as(dp)))
+        return xl, xu, gl, gu
+
+    def GetVariableValues(self):
+        x0 = np.empty(self.n)
+        check(lib.twb_problem_x0(self._h, x0.ctypes.data_as(C.POINTER(C.c_double))))
+        return x0
+
+    def _components(self, count_fn, get_fn):
+        out = []
+        buf = C.create_string_buffer(64)
+        for i in range(count_fn(self._h)):
+            a, b = C.c_int(), C.c_int()
+            check(get_fn(self._h, i, buf, 64, C.byref(a), C.byref(b)))
+            out.append((buf.value.decode(), a.value, b.value))
+        return out
+
+    def variable_sets(self):
+        return self._components(lib.twb_layout_num_variable_sets, lib.twb_layout_variable_set)
+
+    def constraint_sets(self):
+        return self._components(lib.twb_layout_num_constraint_sets, lib.twb_layout_constraint_set)
+
+    def batch(self, batch_size, device=0):
+        return Batch(self, batch_size, device)
+
+
+class Batch:
+    """B instances of one Problem resident on one GPU."""
+
+    def __init__(self, problem, batch_size, device=0):
+        self.problem = problem
+        self.B = int(batch_size)
+        self.device = device
+        self._h = C.c_void_p()
+        check(lib.twb_batch_create(problem._h, self.B, device, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.twb_batch_destroy(self._h)
+            self._h = None
+
+    def set_terrains(self, terrain_ids):
+        if terrain_ids is None:
+            check(lib.twb_batch_set_terrains(self._h, None))
+            return
+        t = np.ascontiguousarray(terrain_ids, np.int32)
+        assert t.shape == (self.B,)
+        check(lib.twb_batch_set_terrains(self._h, t.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def launches_per_eval(self, flags=capi.EVAL_ALL):
+        return lib.twb_batch_launches_per_eval(self._h, flags)
+
+    def eval_host(self, x, flags=capi.EVAL_G | capi.EVAL_JAC, out=None):
+        """x: (B, n) float64 numpy (pinned or pageable). Returns dict of numpy arrays."""
+        p = self.problem
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.shape == (self.B, p.n)
+        out = out or {}
+        g = out.get("g") if flags & capi.EVAL_G else None
+        jac = out.get("jac") if flags & capi.EVAL_JAC else None
+        if flags & capi.EVAL_G and g is None:
+            g = np.empty((self.B, p.m))
+        if flags & capi.EVAL_JAC and jac is None:
+            jac = np.empty((self.B, p.nnz))
+        cost = grad = None
+        if flags & capi.EVAL_COST:
+            cost = out.get("cost", np.empty(self.B))
+            grad = out.get("grad", np.empty((self.B, p.n)))
+        status = out.get("status", np.empty(self.B, np.int32))
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib.twb_batch_eval_host(self._h, ptr(x), ptr(g), ptr(jac), ptr(cost), ptr(grad), ptr(status), flags))
+        return dict(g=g, jac=jac, cost=cost, grad=grad, status=status)
+
+    def eval_device(self, x, g=None, jac=None, cost=None, grad=None, status=None,
+                    flags=capi.EVAL_G | capi.EVAL_JAC, stream=None):
+        """Device-pointer variant. Arguments are torch CUDA float64 tensors (or None);
+        `stream` a torch.cuda.Stream (default: current). Only enqueues."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device)
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+        check(lib.twb_batch_eval_device(self._h, ptr(x), ptr(g), ptr(jac), ptr(cost), ptr(grad), ptr(status),
+                                        flags, C.c_void_p(stream.cuda_stream)))
