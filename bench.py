@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py — NLP evals/sec (constraints + sparse Jacobian, fp64), Anymal batch.
+
+A "step" is one batched evaluation (g and all CSR Jacobian values) of B
+independent Anymal fly-trot / Block-terrain problem instances
+(BASELINE.json configs[1], B = 4096 per GPU, weak scaling: every rank owns its
+own 4096 instances, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # CUDA arm
+  python bench.py --impl reference [...]                        # CPU restatement arm (oracle, all host cores)
+  torchrun --nproc-per-node N bench.py --gpus N ...             # N > 1
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §6 for how every field is measured.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOAD = "anymal_trot_block"
+BATCH_PER_GPU = 4096
+METRIC = "nlp_evals_per_sec"
+UNIT = "evals/s"
+
+
+def read_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([s.strip() for s in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = float(s[1])
+                for nm, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem():
+    import towr_b200 as tb
+    spec = tb.make_formulation(WORKLOAD).to_spec()
+    return tb, spec, tb.Problem(spec)
+
+
+def cpu_arm(spec, problem, X, threads, target_seconds=12.0):
+    """Times the CPU restatement (oracle) on a bounded sample of the same iterates."""
+    import oracle_lib
+    probe = min(len(X), max(threads, 8))
+    t0 = time.perf_counter(); oracle_lib.batch_eval(spec, X[:probe], threads=threads); t_probe = time.perf_counter() - t0
+    per_eval = t_probe / probe
+    sample = int(max(probe, min(len(X), target_seconds / max(per_eval, 1e-9))))
+    t0 = time.perf_counter(); r = oracle_lib.batch_eval(spec, X[:sample], threads=threads); dt = time.perf_counter() - t0
+    assert r["rc"] == 0
+    return sample / dt, sample, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib
+    from towr_b200.configs import synthetic_iterates_fast
+    tb, spec, p = make_problem()
+    threads = oracle_lib.max_threads()
+    X = synthetic_iterates_fast(p, 2048)
+    # each step: a bounded sample of the workload sized for ~1.5 s of CPU time
+    t0 = time.perf_counter(); oracle_lib.batch_eval(spec, X[:max(threads, 8)], threads=threads)
+    per_eval = (time.perf_counter() - t0) / max(threads, 8)
+    sample = int(max(threads, min(len(X), 1.5 / per_eval)))
+    for _ in range(args.warmup):
+        oracle_lib.batch_eval(spec, X[:sample], threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_lib.batch_eval(spec, X[:sample], threads=threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD} (BASELINE configs[1]): Anymal fly-trot C1, Block terrain, T=2.0 s, n={p.n} m={p.m} nnz={p.nnz}",
+                   "note": "reference arm = CPU restatement of towr's evaluation (oracle port; towr itself needs Eigen+ifopt, absent here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} instances per step, OpenMP over instances"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from towr_b200.configs import synthetic_iterates_fast
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (towr_b200 has no CPU evaluation path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tb, spec, p = make_problem()
+    B = BATCH_PER_GPU
+    batch = p.batch(B, device=local)
+
+    # ---- inputs: a ring of distinct iterate sets, together larger than L2 (126 MB)
+    n_ring = 8
+    Xh = synthetic_iterates_fast(p, B, seed=1234 + rank)
+    ring = []
+    for r in range(n_ring):
+        Xr = Xh if r == 0 else synthetic_iterates_fast(p, B, seed=1234 + rank + 1000 * r)
+        ring.append(torch.from_numpy(Xr).to(dev))
+    g = torch.empty((B, p.m), dtype=torch.float64, device=dev)
+    jac = torch.empty((B, p.nnz), dtype=torch.float64, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    flags = tb.EVAL_G | tb.EVAL_JAC
+
+    def step(i):
+        batch.eval_device(ring[i % n_ring], g=g, jac=jac, status=status, flags=flags, stream=stream)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sync_all()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step(i)
+        ev[i + 1].record(stream)
+    sync_all()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+    if sampler:
+        sampler.stop_flag = True
+    assert int(status.sum().item()) == 0, "non-finite values flagged"
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI call: pinned host buffers, H2D + D2H inside the timed region
+    xs_pinned = torch.from_numpy(Xh).pin_memory()
+    out = {"g": torch.empty((B, p.m), dtype=torch.float64).pin_memory().numpy(),
+           "jac": torch.empty((B, p.nnz), dtype=torch.float64).pin_memory().numpy(),
+           "status": torch.empty(B, dtype=torch.int32).pin_memory().numpy()}
+    x_np = xs_pinned.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        batch.eval_host(x_np, flags=flags, out=out)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.eval_host(x_np, flags=flags, out=out)      # synchronises internally; result is on the host
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(te.item())
+    h2d = B * p.n * 8
+    d2h = B * (p.m + p.nnz) * 8 + B * 4
+
+    if rank == 0:
+        import oracle_lib
+        peak, peak_src = read_peak()
+        bytes_per_eval = 8 * (p.n + p.m + p.nnz)
+        avg_kernel_ms = total_ms / args.steps       # one kernel launch per step on this stream
+        achieved = bytes_per_eval * B / (avg_kernel_ms * 1e-3) / 1e9
+        threads = oracle_lib.max_threads()
+        cpu_value, cpu_sample, cpu_dt = cpu_arm(spec, p, Xh, threads)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD} (BASELINE configs[1]): Anymal fly-trot C1, Block terrain, T=2.0 s, "
+                                   f"{B} instances per GPU, n={p.n} m={p.m} nnz={p.nnz}",
+                       "batch_per_gpu": B, "outputs": "g[B][m] + jac[B][nnz] (CSR values), fp64",
+                       "l2": f"inputs rotate over {n_ring} distinct iterate sets ({n_ring * B * p.n * 8 / 1e6:.0f} MB) and each step "
+                             f"writes {B * (p.m + p.nnz) * 8 / 1e6:.0f} MB of outputs (> 126 MB L2)",
+                       "iterates": "x0 + sigma*N(0,1), sigma 0.05 pos / 0.2 vel / 10 N force (SURVEY §8d)"},
+            "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_best": per_step[0],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_eval * B, "kernel": "EvalKernel", "avg_launch_ms": avg_kernel_ms},
+            "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"first {cpu_sample} instances of the same batch, OpenMP over instances, {cpu_dt:.1f} s"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "twb_batch_eval_host (pinned host buffers)"},
+            "gpu_launches": args.steps * batch.launches_per_eval(flags),
+            "clocks": sampler.summary() if sampler else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    import __graft_entry__ as ge
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        ge.build(quiet=True)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

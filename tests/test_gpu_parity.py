@@ -1,0 +1,161 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs; plus size-independent properties at the
+full BASELINE batch sizes."""
+import numpy as np
+import pytest
+
+import towr_b200 as tb
+from towr_b200 import capi
+from towr_b200.configs import synthetic_iterates, synthetic_iterates_fast
+import oracle_lib
+from tolerance import check_rows, check_sets
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(name, B, terrain=None, terrains=None, costs=None, **kw):
+    f = tb.make_formulation(name, terrain=terrain, **kw)
+    if costs:
+        f.params_.costs_ = costs
+    spec = f.to_spec()
+    p = tb.Problem(spec)
+    X = synthetic_iterates(p, B)
+    bt = p.batch(B)
+    if terrains is not None:
+        bt.set_terrains(terrains)
+    flags = capi.EVAL_ALL if costs else capi.EVAL_G | capi.EVAL_JAC
+    out = bt.eval_host(X, flags=flags)
+    ref = oracle_lib.batch_eval(spec, X, terrain_ids=terrains, want_cost=bool(costs))
+    assert ref["rc"] == 0                      # oracle pattern at x == pattern at x0
+    bad_j, strict_j, worst_j = check_rows(out["jac"], ref["jac"], p.row_ptr())
+    bad_g, strict_g, worst_g = check_sets(out["g"], ref["g"], p.constraint_sets())
+    assert bad_j == 0, (bad_j, worst_j)
+    assert bad_g == 0, (bad_g, worst_g)
+    assert strict_j < 1e-4 and strict_g < 1e-4   # entries missing the bare 1e-12/1e-14 criterion are rare
+    assert not out["status"].any()
+    return p, out, ref
+
+
+def test_hopper_config1():
+    _compare("hopper", 32)
+
+
+def test_anymal_trot_block_config2():
+    _compare("anymal_trot_block", 64)
+
+
+def test_biped_walk_stairs_config3():
+    _compare("biped_walk_stairs", 64, goal_xy=(2.0, 0.2), goal_yaw=0.3)
+
+
+def test_anymal_mixed_terrains_config5():
+    B = 63                                      # ragged: not a multiple of the CTA group size
+    terr = np.array([tb.SLOPE, tb.CHIMNEY, tb.GAP] * 21, np.int32)
+    _compare("anymal_trot_mixed", B, terrains=terr)
+
+
+def test_every_terrain_go1():
+    B = 28
+    _compare("go1_trot_flat", B, terrains=(np.arange(B) % 7).astype(np.int32))
+
+
+def test_longer_horizon():
+    _compare("anymal_trot_block", 8, t_total=2.4)
+
+
+def test_node_costs():
+    p, out, ref = _compare("anymal_trot_block", 16, costs=[(capi.COST_FORCES, 1.0), (capi.COST_EE_MOTION, 0.5)])
+    assert np.allclose(out["cost"], ref["cost"], rtol=1e-12, atol=0)
+    assert np.allclose(out["grad"], ref["grad"], rtol=1e-12, atol=1e-14)
+    assert np.abs(out["grad"]).max() > 0
+
+
+def test_batch_of_one_and_flags():
+    f = tb.make_formulation("hopper"); spec = f.to_spec(); p = tb.Problem(spec)
+    X = synthetic_iterates(p, 1)
+    bt = p.batch(1)
+    full = bt.eval_host(X)
+    only_g = bt.eval_host(X, flags=capi.EVAL_G)
+    only_j = bt.eval_host(X, flags=capi.EVAL_JAC)
+    assert only_g["jac"] is None and np.array_equal(only_g["g"], full["g"])
+    assert only_j["g"] is None and np.array_equal(only_j["jac"], full["jac"])
+    zero = bt.eval_host(X, flags=capi.EVAL_ALL)       # no cost terms: cost 0, gradient 0
+    assert zero["cost"][0] == 0.0 and not zero["grad"].any()
+
+
+def test_x0_iterate_and_status_flag():
+    f = tb.make_formulation("anymal_trot_block"); spec = f.to_spec(); p = tb.Problem(spec)
+    X = np.tile(p.GetVariableValues(), (4, 1))
+    out = p.batch(4).eval_host(X)
+    ref = oracle_lib.batch_eval(spec, X)
+    assert check_rows(out["jac"], ref["jac"], p.row_ptr())[0] == 0
+    assert check_sets(out["g"], ref["g"], p.constraint_sets())[0] == 0
+    X[2, 5] = np.nan
+    out = p.batch(4).eval_host(X)
+    assert out["status"][2] & 1
+
+
+def test_device_pointer_variant_matches_host_variant():
+    import torch
+    f = tb.make_formulation("anymal_trot_block"); p = tb.Problem(f.to_spec())
+    B = 33
+    X = synthetic_iterates(p, B)
+    bt = p.batch(B)
+    host = bt.eval_host(X)
+    xd = torch.from_numpy(X).cuda()
+    g = torch.empty((B, p.m), dtype=torch.float64, device="cuda")
+    jac = torch.empty((B, p.nnz), dtype=torch.float64, device="cuda")
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        bt.eval_device(xd, g=g, jac=jac, status=st, stream=s)
+    s.synchronize()
+    assert np.array_equal(g.cpu().numpy(), host["g"]) and np.array_equal(jac.cpu().numpy(), host["jac"])
+
+
+def test_full_size_properties_config2():
+    """BASELINE configs[1] at full size (4096): determinism, instance independence (permutation
+    equivariance), iterate-independent entries constant across the batch, and oracle parity on a
+    seeded subsample."""
+    f = tb.make_formulation("anymal_trot_block"); spec = f.to_spec(); p = tb.Problem(spec)
+    B = 4096
+    X = synthetic_iterates_fast(p, B)
+    bt = p.batch(B)
+    a = bt.eval_host(X)
+    b = bt.eval_host(X)
+    assert np.array_equal(a["jac"], b["jac"]) and np.array_equal(a["g"], b["g"])
+    perm = np.random.default_rng(7).permutation(B)
+    c = bt.eval_host(X[perm])
+    assert np.array_equal(c["jac"], a["jac"][perm]) and np.array_equal(c["g"], a["g"][perm])
+    # SplineAcc / Swing Jacobians and the "1.0" terrain entries do not depend on x
+    rp = p.row_ptr()
+    for name, r0, nr in p.constraint_sets():
+        if name.startswith(("splineacc", "swing")):
+            blk = a["jac"][:, rp[r0]:rp[r0 + nr]]
+            assert np.all(blk == blk[0])
+    idx = np.random.default_rng(11).choice(B, 48, replace=False)
+    ref = oracle_lib.batch_eval(spec, X[idx])
+    assert check_rows(a["jac"][idx], ref["jac"], rp)[0] == 0
+    assert check_sets(a["g"][idx], ref["g"], p.constraint_sets())[0] == 0
+    assert not a["status"].any()
+
+
+def test_linearity_in_forces():
+    """g_dynamic is affine in the force variables: g(x + 2d) - g(x + d) == g(x + d) - g(x) for force-only d,
+    and the Jacobian reproduces the directional derivative."""
+    f = tb.make_formulation("anymal_trot_block"); p = tb.Problem(f.to_spec())
+    X = synthetic_iterates(p, 4)
+    d = np.zeros_like(X)
+    for name, s, k in p.variable_sets():
+        if name.startswith("ee-force"):
+            d[:, s:s + k] = np.random.default_rng(3).standard_normal((4, k))
+    bt = p.batch(4)
+    g0, g1, g2 = (bt.eval_host(X + a * d) for a in (0.0, 1.0, 2.0))
+    (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == "dynamic"]
+    lhs = g2["g"][:, r0:r0 + nr] - g1["g"][:, r0:r0 + nr]
+    rhs = g1["g"][:, r0:r0 + nr] - g0["g"][:, r0:r0 + nr]
+    assert np.allclose(lhs, rhs, rtol=0, atol=1e-9)
+    iRow, jCol = p.structure()
+    for b in range(4):
+        J = np.zeros((p.m, p.n)); J[iRow, jCol] = g0["jac"][b]
+        assert np.allclose((J @ d[b])[r0:r0 + nr], rhs[b], rtol=0, atol=1e-9)

@@ -1,0 +1,128 @@
+"""CPU tests that pin the oracle itself (the reference holds no golden vectors
+for this path — SURVEY.md §8c): finite differences of its own g, closed-form
+checks with mpmath, and the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+import towr_b200 as tb
+from towr_b200.configs import synthetic_iterates
+import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dense(o, vals):
+    rp, ci = o.structure()
+    J = np.zeros((o.m, o.n))
+    J[np.repeat(np.arange(o.m), np.diff(rp)), ci] = vals
+    return J
+
+
+@pytest.mark.parametrize("name,terrain", [("hopper", None), ("hopper", tb.SLOPE), ("biped_walk_stairs", tb.CHIMNEY)])
+def test_oracle_jacobian_matches_finite_differences(name, terrain):
+    """What IPOPT's derivative_test would do (hopper_example.cc:86), on random iterates."""
+    spec = tb.make_formulation(name, terrain=terrain).to_spec()
+    o = oracle_lib.Oracle(spec)
+    p = tb.Problem(spec)
+    x = synthetic_iterates(p, 1, seed=99)[0]
+    r = o.eval(x)
+    assert r["rc"] == 0
+    J = _dense(o, r["jac"])
+    h = 1e-6
+    cols = np.random.default_rng(5).choice(o.n, 90, replace=False)
+    for j in cols:
+        xp, xm = x.copy(), x.copy()
+        xp[j] += h; xm[j] -= h
+        fd = (o.eval(xp)["g"] - o.eval(xm)["g"]) / (2 * h)
+        assert np.allclose(J[:, j], fd, rtol=2e-6, atol=2e-6), j
+
+
+def test_oracle_pattern_is_value_independent():
+    """The reference's pattern comes from Eigen algebra at x0; it must not change with x."""
+    for name in ("hopper", "anymal_trot_block"):
+        spec = tb.make_formulation(name).to_spec()
+        o = oracle_lib.Oracle(spec); p = tb.Problem(spec)
+        for x in synthetic_iterates(p, 3, seed=5):
+            assert o.eval(x)["rc"] == 0
+        assert o.eval(np.zeros(o.n))["rc"] == 0
+
+
+def test_gap_terrain_quirk_reproduced():
+    """the force-row derivative w.r.t. the foot position uses the reference's
+    element-wise 'derivative of the normalised basis', which is NOT the true chain rule on Gap."""
+    spec = tb.make_formulation("hopper", terrain=tb.GAP).to_spec()
+    o = oracle_lib.Oracle(spec); p = tb.Problem(spec)
+    x = p.GetVariableValues().copy()
+    sets = dict((nm, (s, k)) for nm, s, k in p.variable_sets())
+    s, k = sets["ee-motion_0"]
+    x[s:s + k] += 1.2      # move the feet into the gap parabola x in [1.0, 1.5]
+    r = o.eval(x)
+    J = _dense(o, r["jac"])
+    (_, r0, nr), = [c for c in p.constraint_sets() if c[0].startswith("force")]
+    # closed form with mpmath for the first force node's normal-force row
+    import mpmath as mp
+    mp.mp.dps = 40
+    px = mp.mpf(x[s])      # stance position x of phase 0
+    w, hh, gs = mp.mpf("0.5"), mp.mpf("1.5"), mp.mpf(1)
+    xc = gs + w / 2
+    a = 4 * hh / (w * w); b = -8 * hh * xc / (w * w)
+    assert 1.0 <= float(px) <= 1.5
+    hx, hxx = 2 * a * px + b, 2 * a
+    v = [-hx, mp.mpf(0), mp.mpf(1)]
+    sn = sum(c * c for c in v); nrm = mp.sqrt(sn)
+    dn = [(1 / sn * (nrm * (1 if i == 0 else 0) - v[0] * v[i] / nrm)) * dv for i, dv in enumerate([-hxx, 0, 0])]
+    fs, fk = sets["ee-force_0"]
+    fvec = [mp.mpf(x[fs + 0]), mp.mpf(x[fs + 2]), mp.mpf(x[fs + 4])]   # node 0: px,vx,py,vy,pz,vz
+    expect = sum(fi * di for fi, di in zip(fvec, dn))
+    got = J[r0, s]         # d(f.n)/d(foot x)
+    assert abs(got - float(expect)) <= 1e-12 * abs(float(expect))
+
+
+def test_hermite_basis_closed_form():
+    """Spline value and node-Jacobian of the oracle against an independent mpmath Hermite evaluation
+    (SURVEY App. A.1), through the RoM constraint of the hopper (g = R^T (p_ee - c) with zero angles)."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    spec = tb.make_formulation("hopper").to_spec()
+    o = oracle_lib.Oracle(spec); p = tb.Problem(spec)
+    x = synthetic_iterates(p, 1, seed=3)[0]
+    sets = dict((nm, (s, k)) for nm, s, k in p.variable_sets())
+    s_ang, k_ang = sets["base-ang"]
+    x[s_ang:s_ang + k_ang] = 0.0                         # R = I exactly
+    r = o.eval(x)
+    (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == "rangeofmotion-0"]
+    # sample k=3 -> t = 0.24 (3 x 0.08): base poly 2 (t_local 0.04), ee-motion: stance phase 0 (0..0.4) => p = node value
+    k = 3
+    t = 0.0
+    for _ in range(k):
+        t += 0.08
+    s_lin = sets["base-lin"][0]
+    def herm(p0, v0, p1, v1, tl, T):
+        p0, v0, p1, v1, tl, T = map(mp.mpf, (p0, v0, p1, v1, tl, T))
+        C = -(3 * (p0 - p1) + T * (2 * v0 + v1)) / T**2
+        D = (2 * (p0 - p1) + T * (v0 + v1)) / T**3
+        return p0 + v0 * tl + C * tl**2 + D * tl**3
+    tl = t - 0.1 - 0.1
+    for d in range(3):
+        c = herm(x[s_lin + 12 + d], x[s_lin + 15 + d], x[s_lin + 18 + d], x[s_lin + 21 + d], tl, 0.1)
+        pe = mp.mpf(x[sets["ee-motion_0"][0] + d])
+        assert abs(r["g"][r0 + 3 * k + d] - float(pe - c)) < 1e-14
+
+
+def test_golden_fixtures():
+    """Outputs of the oracle committed under tests/golden (made by scripts/make_golden.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "oracle_golden.npz")
+    z = np.load(path)
+    for name in ("hopper", "anymal_trot_block", "biped_walk_stairs"):
+        spec = tb.make_formulation(name).to_spec()
+        o = oracle_lib.Oracle(spec); p = tb.Problem(spec)
+        X = synthetic_iterates(p, 2, seed=int(z["seed"]))
+        assert np.array_equal(X, z[f"{name}_x"])
+        rp, ci = o.structure()
+        assert np.array_equal(rp, z[f"{name}_row_ptr"]) and np.array_equal(ci, z[f"{name}_col_idx"])
+        for b in range(2):
+            r = o.eval(X[b])
+            assert np.allclose(r["g"], z[f"{name}_g"][b], rtol=1e-13, atol=1e-13)
+            assert np.allclose(r["jac"], z[f"{name}_jac"][b], rtol=1e-13, atol=1e-13)
