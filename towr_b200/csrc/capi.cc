@@ -137,19 +137,19 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
     twb_batch_destroy(b);                                                              \
     return CudaFail(e, "table upload");                                                \
   }
-  TWB_UP(dyn_samples) TWB_UP(rom_samples) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc) TWB_UP(cost)
+  TWB_UP(samples) TWB_UP(eval_items) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc) TWB_UP(cost)
   TWB_UP(desc) TWB_UP(coef) TWB_UP(extra)
 #undef TWB_UP
   // instances per CTA: largest G in {4,2,1} that lets two CTAs share an SM's shared memory
   int max_smem = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   b->G = 1;
-  for (int G : {4, 2, 1}) {
+  for (int G : {4, 3, 2, 1}) {
     if (twb::EvalSmemBytes(b->plan, G) * 2 + 4096 <= (size_t)max_smem) { b->G = G; break; }
   }
   if (const char* env = std::getenv("TWB_INSTANCES_PER_CTA")) {
     int G = std::atoi(env);
-    if (G == 1 || G == 2 || G == 4) b->G = G;
+    if (G == 1 || G == 2 || G == 3 || G == 4 || G == 6 || G == 8) b->G = G;
   }
   if (twb::EvalSmemBytes(b->plan, b->G) > (size_t)max_smem) {
     twb_batch_destroy(b);

@@ -9,6 +9,7 @@
 namespace twb {
 
 constexpr int kMaxEE = 4;
+constexpr int kMaxSegments = 16;
 
 // One spline evaluated at one constraint sample when phase durations are
 // fixed: the active polynomial (Spline::GetSegmentID, spline.cc:48-63), its
@@ -18,8 +19,17 @@ constexpr int kMaxEE = 4;
 // zero slot, index n.
 struct SplineSample {
   double T, T2, T3;   // polynomial duration and std::pow(T,2), std::pow(T,3)
+  double rT2, rT3;    // correctly rounded 1/T2, 1/T3 (seed of the exact division on the device)
   double t, t2, t3;   // local time and std::pow(t,2), std::pow(t,3)
   int16_t xi[12];
+};
+
+// One phase-0 work item: evaluate spline sample `sample` into S[scratch..]
+// kind 0: position (3 doubles); 1: position + acceleration (6); 2: position + velocity + acceleration (9)
+struct EvalItem {
+  int32_t sample;
+  int16_t scratch;
+  int16_t kind;
 };
 
 // TerrainConstraint row (terrain_constraint.cc:59-108): one ee-motion node
@@ -27,7 +37,7 @@ struct TerrainUnit {
   int16_t xi[3];      // x index of node position x,y,z
   int16_t pad;
   int32_t g_row;      // constraint row
-  int32_t s_idx;      // S offset of {-dh/dx, -dh/dy}
+  int32_t jac_slot;   // CSR slot of the row's 3 values {-dh/dx, -dh/dy, 1}
 };
 
 // ForceConstraint node (force_constraint.cc:64-171): 5 rows
@@ -36,7 +46,7 @@ struct ForceUnit {
   int16_t xp[3];      // x index of the stance-foot position (phase start node); [2] unused
   int16_t pad[2];
   int32_t g_row;      // first of the 5 rows
-  int32_t s_idx;      // S offset of 25 Jacobian values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
+  int32_t jac_slot;   // CSR slot of the 25 contiguous values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
 };
 
 // SwingConstraint node (swing_constraint.cc:57-83): 4 rows
@@ -49,8 +59,8 @@ struct SwingUnit {
 
 // SplineAccConstraint junction (spline_acc_constraint.cc:49-65), fixed durations
 struct AccUnit {
-  double Tp, Tp2, Tp3;  // previous polynomial duration, pow 2, pow 3
-  double Tn, Tn2, Tn3;  // next polynomial
+  double Tp, Tp2, Tp3, rTp2, rTp3;  // previous polynomial duration, pow 2, pow 3, reciprocals
+  double Tn, Tn2, rTn2;             // next polynomial
   int32_t x0;           // x index of node j, dim 0 position (NodesVariablesAll layout)
   int32_t g_row;        // first of 3 rows
 };
@@ -73,27 +83,30 @@ inline uint32_t MakeDesc(uint32_t a, uint32_t extra_idx, bool triple) {
 struct Plan {
   int n, m, nnz, n_ee;
   // sizes
-  int n_dyn, n_rom, n_terr, n_force, n_swing, n_acc, n_totdur, n_cost;
+  int n_dyn, n_rom, n_terr, n_force, n_swing, n_acc, n_totdur, n_cost, n_eval_items;
   // g rows
   int dyn_row0;
   int rom_row0[kMaxEE];
   int totdur_row0;
   // S layout (doubles, per instance)
   int S_size, S_dyn0, S_dyn_stride, S_rom0, S_rom_stride;
+  // CSR slot ranges filled from descriptors (the rest is written directly by terrain/force units)
+  int n_seg;
+  int seg_start[kMaxSegments], seg_end[kMaxSegments];
   // robot
   double mass, gravity;
   double I_b[9];
   double mu;
   // tables (device pointers)
-  const SplineSample* dyn_samples;  // [n_dyn][2 + 2*n_ee]: base-lin, base-ang, motion_e.., force_e..
-  const SplineSample* rom_samples;  // [n_rom][2 + n_ee]:  base-lin, base-ang, motion_e..
+  const SplineSample* samples;      // every (constraint sample, spline) pair of the dynamic and RoM sets
+  const EvalItem* eval_items;       // [n_eval_items]
   const TerrainUnit* terr;
   const ForceUnit* force;
   const SwingUnit* swing;
   const AccUnit* acc;
   const CostEntry* cost;
-  const uint32_t* desc;   // [nnz]
-  const double* coef;     // [nnz]
+  const uint32_t* desc;   // [nnz padded to even]
+  const double* coef;     // [nnz padded to even]
   const double* extra;    // [2*n_triples]
 };
 

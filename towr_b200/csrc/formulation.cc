@@ -154,6 +154,7 @@ SplineSample MakeSample(const SplineDef& s, double t_global, int zero_slot) {
   SplineSample o{};
   int p; double tl; Locate(s, t_global, &p, &tl);
   o.T = s.T[p]; o.T2 = std::pow(o.T, 2); o.T3 = std::pow(o.T, 3);
+  o.rT2 = 1.0 / o.T2; o.rT3 = 1.0 / o.T3;
   o.t = tl; o.t2 = std::pow(tl, 2); o.t3 = std::pow(tl, 3);
   for (int side = 0; side < 2; ++side) for (int deriv = 0; deriv < 2; ++deriv) for (int dim = 0; dim < 3; ++dim)
     o.xi[side * 6 + deriv * 3 + dim] = XIndex(*s.set, p + side, deriv, dim, zero_slot);
@@ -172,7 +173,7 @@ std::vector<double> BasePolyDurations(double T, double dt) {  // parameters.cc:8
   return v;
 }
 
-struct Emit { int row, col; uint32_t a; bool triple; double c0, c1, c2; };
+struct Emit { int row, col; uint32_t a; bool triple; double c0, c1, c2; bool direct; };
 
 // sign/component of Cross(v)[i][d] (single_rigid_body_dynamics.cc:46-57): value = sign * v[comp]
 void CrossEntry(int i, int d, int* comp, double* sign) {
@@ -286,9 +287,15 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   const uint32_t S_ONE = 0;
 
   std::vector<Emit> em;
-  auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, false, c, 0.0, 0.0}); };
-  auto emit3 = [&](int row, int col, uint32_t a, double c0, double c1, double c2) { em.push_back({row, col, a, true, c0, c1, c2}); };
+  auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, false, c, 0.0, 0.0, false}); };
+  auto emit3 = [&](int row, int col, uint32_t a, double c0, double c1, double c2) { em.push_back({row, col, a, true, c0, c1, c2, false}); };
+  // entries a terrain/force unit writes straight into the CSR array (no descriptor)
+  auto emit_direct = [&](int row, int col) { em.push_back({row, col, 0u, false, 0.0, 0.0, 0.0, true}); };
 
+  auto add_eval = [&](const SplineSample& s, uint32_t scratch, int kind) {
+    EvalItem it{}; it.sample = (int32_t)tb.samples.size(); it.scratch = (int16_t)scratch; it.kind = (int16_t)kind;
+    tb.samples.push_back(s); tb.eval_items.push_back(it);
+  };
   m = 0; con_sets.clear(); g_lower.clear(); g_upper.clear();
   auto add_set = [&](const std::string& name, int rows) { con_sets.push_back({name, m, rows}); int r0 = m; m += rows; g_lower.resize(m, 0.0); g_upper.resize(m, 0.0); return r0; };
   auto bound = [&](int row, double lo, double up) { g_lower[row] = lo; g_upper[row] = up; };
@@ -308,10 +315,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           const double t = ts[k];
           const int row = r0 + 6 * k; const uint32_t sb = pl.S_dyn0 + k * pl.S_dyn_stride;
           for (int r = 0; r < 6; ++r) bound(row + r, 0.0, 0.0);
-          tb.dyn_samples.push_back(MakeSample(sp_lin, t, zero_slot));
-          tb.dyn_samples.push_back(MakeSample(sp_ang, t, zero_slot));
-          for (int e = 0; e < n_ee; ++e) tb.dyn_samples.push_back(MakeSample(sp_motion[e], t, zero_slot));
-          for (int e = 0; e < n_ee; ++e) tb.dyn_samples.push_back(MakeSample(sp_force[e], t, zero_slot));
+          // phase-0 scratch inside the sample's own S block: c, c_ddot | theta, theta_dot, theta_ddot | p_e.. | f_e..
+          add_eval(MakeSample(sp_lin, t, zero_slot), sb + 0, 1);
+          add_eval(MakeSample(sp_ang, t, zero_slot), sb + 6, 2);
+          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], t, zero_slot), sb + 15 + 3 * e, 0);
+          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_force[e], t, zero_slot), sb + 15 + 3 * n_ee + 3 * e, 0);
           int p; double tl;
           // base-lin: angular rows = -sum_e [f_e]x dc ; linear rows = m * d(acc)
           Locate(sp_lin, t, &p, &tl);
@@ -355,10 +363,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_range_of_motion);
         pl.n_rom = (int)ts.size();
         pl.S_rom_stride = 9 + 9 * n_ee; pl.S_rom0 = S_top; S_top += pl.S_rom_stride * pl.n_rom;
-        for (int k = 0; k < pl.n_rom; ++k) {
-          tb.rom_samples.push_back(MakeSample(sp_lin, ts[k], zero_slot));
-          tb.rom_samples.push_back(MakeSample(sp_ang, ts[k], zero_slot));
-          for (int e = 0; e < n_ee; ++e) tb.rom_samples.push_back(MakeSample(sp_motion[e], ts[k], zero_slot));
+        for (int k = 0; k < pl.n_rom; ++k) {  // scratch: c | theta | p_e..
+          const uint32_t sb = pl.S_rom0 + k * pl.S_rom_stride;
+          add_eval(MakeSample(sp_lin, ts[k], zero_slot), sb + 0, 0);
+          add_eval(MakeSample(sp_ang, ts[k], zero_slot), sb + 3, 0);
+          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], ts[k], zero_slot), sb + 6 + 3 * e, 0);
         }
         for (int e = 0; e < n_ee; ++e) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
@@ -386,11 +395,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int row = r0 + nd - 1;
             if (mo.ConstNode(nd)) bound(row, 0.0, 0.0); else bound(row, 0.0, 1e20);
             TerrainUnit u{}; for (int d = 0; d < 3; ++d) u.xi[d] = XIndex(mo, nd, kPos, d, zero_slot);
-            u.g_row = row; u.s_idx = S_top; S_top += 2;
+            u.g_row = row; u.jac_slot = -1;
             tb.terr.push_back(u);
-            emit1(row, mo.offset + mo.Var(nd, kPos, X), u.s_idx + 0, 1.0);
-            emit1(row, mo.offset + mo.Var(nd, kPos, Y), u.s_idx + 1, 1.0);
-            emit1(row, mo.offset + mo.Var(nd, kPos, Z), S_ONE, 1.0);
+            if (!(mo.Var(nd, kPos, X) < mo.Var(nd, kPos, Y) && mo.Var(nd, kPos, Y) < mo.Var(nd, kPos, Z)))
+              return fail(TWB_ERR_UNSUPPORTED, "unexpected ee-motion variable order");
+            for (int d = 0; d < 3; ++d) emit_direct(row, mo.offset + mo.Var(nd, kPos, d));
           }
         }
         break;
@@ -407,13 +416,16 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int mnode = 0; for (int i = 0; i < (int)mo.poly.size(); ++i) if (mo.poly[i].phase == phase) { mnode = i; break; }
             ForceUnit u{};
             for (int d = 0; d < 3; ++d) { u.xf[d] = XIndex(fo, nd, kPos, d, zero_slot); u.xp[d] = XIndex(mo, mnode, kPos, d, zero_slot); }
-            u.g_row = row; u.s_idx = S_top; S_top += 25;
+            u.g_row = row; u.jac_slot = -1;
             tb.force.push_back(u);
+            if (!(mo.offset < fo.offset && mo.Var(mnode, kPos, X) < mo.Var(mnode, kPos, Y) &&
+                  fo.Var(nd, kPos, X) < fo.Var(nd, kPos, Y) && fo.Var(nd, kPos, Y) < fo.Var(nd, kPos, Z)))
+              return fail(TWB_ERR_UNSUPPORTED, "unexpected force/motion variable order");
             bound(row + 0, 0.0, sp.force_limit_in_normal_direction);
             bound(row + 1, -kInf, 0.0); bound(row + 2, 0.0, +kInf); bound(row + 3, -kInf, 0.0); bound(row + 4, 0.0, +kInf);
             for (int r = 0; r < 5; ++r) {
-              for (int d = 0; d < 2; ++d) emit1(row + r, mo.offset + mo.Var(mnode, kPos, d), u.s_idx + r * 5 + d, 1.0);
-              for (int d = 0; d < 3; ++d) emit1(row + r, fo.offset + fo.Var(nd, kPos, d), u.s_idx + r * 5 + 2 + d, 1.0);
+              for (int d = 0; d < 2; ++d) emit_direct(row + r, mo.offset + mo.Var(mnode, kPos, d));
+              for (int d = 0; d < 3; ++d) emit_direct(row + r, fo.offset + fo.Var(nd, kPos, d));
             }
             row += 5;
           }
@@ -459,8 +471,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           int r0 = add_set("splineacc-" + ns.name, 3 * nj);
           for (int j = 0; j < nj; ++j) {
             AccUnit u{};
-            u.Tp = s.T[j]; u.Tp2 = std::pow(u.Tp, 2); u.Tp3 = std::pow(u.Tp, 3);
-            u.Tn = s.T[j + 1]; u.Tn2 = std::pow(u.Tn, 2); u.Tn3 = std::pow(u.Tn, 3);
+            u.Tp = s.T[j]; u.Tp2 = std::pow(u.Tp, 2); u.Tp3 = std::pow(u.Tp, 3); u.rTp2 = 1.0 / u.Tp2; u.rTp3 = 1.0 / u.Tp3;
+            u.Tn = s.T[j + 1]; u.Tn2 = std::pow(u.Tn, 2); u.rTn2 = 1.0 / u.Tn2;
             u.x0 = ns.offset + j * 6; u.g_row = r0 + 3 * j;
             tb.acc.push_back(u);
             // acc_prev - acc_next with the union of both patterns (:67-80)
@@ -480,7 +492,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     }
   }
   pl.S_size = S_top;
-  if (S_top + 2 > 65535) return fail(TWB_ERR_UNSUPPORTED, "state vector too large for 16-bit descriptors");
+  if (S_top + 2 > 32767) return fail(TWB_ERR_UNSUPPORTED, "state vector too large for 16-bit descriptors");
 
   // ---- CSR assembly: row-major, ascending column (what setFromTriplets yields)
   std::stable_sort(em.begin(), em.end(), [](const Emit& a, const Emit& b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
@@ -488,8 +500,16 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     if (em[i].row == em[i - 1].row && em[i].col == em[i - 1].col) return fail(TWB_ERR_UNSUPPORTED, "duplicate Jacobian entry emitted");
   nnz = (int)em.size();
   row_ptr.assign(m + 1, 0); col_idx.resize(nnz);
-  tb.desc.resize(nnz); tb.coef.resize(nnz);
+  tb.desc.assign((nnz + 1) & ~1, 0u); tb.coef.assign((nnz + 1) & ~1, 0.0);
+  pl.n_seg = 0;
   for (int s = 0; s < nnz; ++s) {
+    if (!em[s].direct) {  // maximal runs of descriptor-filled slots
+      if (pl.n_seg > 0 && pl.seg_end[pl.n_seg - 1] == s) pl.seg_end[pl.n_seg - 1] = s + 1;
+      else {
+        if (pl.n_seg == kMaxSegments) return fail(TWB_ERR_UNSUPPORTED, "too many Jacobian segments");
+        pl.seg_start[pl.n_seg] = s; pl.seg_end[pl.n_seg] = s + 1; ++pl.n_seg;
+      }
+    }
     row_ptr[em[s].row + 1]++; col_idx[s] = em[s].col;
     uint32_t extra_idx = 0;
     if (em[s].triple) {
@@ -501,6 +521,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     tb.coef[s] = em[s].c0;
   }
   for (int r = 0; r < m; ++r) row_ptr[r + 1] += row_ptr[r];
+  for (auto& u : tb.terr) { u.jac_slot = row_ptr[u.g_row]; if (row_ptr[u.g_row + 1] - u.jac_slot != 3) return fail(TWB_ERR_UNSUPPORTED, "terrain row layout"); }
+  for (auto& u : tb.force) { u.jac_slot = row_ptr[u.g_row]; if (row_ptr[u.g_row + 5] - u.jac_slot != 25) return fail(TWB_ERR_UNSUPPORTED, "force row layout"); }
 
   // ---- costs (nlp_formulation.cc:333-376, node_cost.cc:53-76)
   has_cost = false;
@@ -523,7 +545,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   // ---- plan scalars
   pl.n = n; pl.m = m; pl.nnz = nnz; pl.n_ee = n_ee;
   pl.n_terr = (int)tb.terr.size(); pl.n_force = (int)tb.force.size(); pl.n_swing = (int)tb.swing.size();
-  pl.n_acc = (int)tb.acc.size(); pl.n_totdur = 0; pl.n_cost = (int)tb.cost.size();
+  pl.n_acc = (int)tb.acc.size(); pl.n_totdur = 0; pl.n_cost = (int)tb.cost.size(); pl.n_eval_items = (int)tb.eval_items.size();
   pl.mass = rb.mass; pl.gravity = 9.80665;  // dynamic_model.cc:37
   const double* I = rb.inertia;             // single_rigid_body_dynamics.cc:36-44
   double Ib[9] = {I[0], -I[3], -I[4], -I[3], I[1], -I[5], -I[4], -I[5], I[2]};

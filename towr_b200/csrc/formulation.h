@@ -33,7 +33,8 @@ struct Component { std::string name; int start; int count; };
 // Everything the kernels need, still on the host (capi.cc uploads it).
 struct HostTables {
   Plan plan{};  // pointer members are filled in after upload
-  std::vector<SplineSample> dyn_samples, rom_samples;
+  std::vector<SplineSample> samples;
+  std::vector<EvalItem> eval_items;
   std::vector<TerrainUnit> terr;
   std::vector<ForceUnit> force;
   std::vector<SwingUnit> swing;

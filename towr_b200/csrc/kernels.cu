@@ -55,19 +55,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- cubic Hermite evaluation ------------------------------------------------
+// a / b, correctly rounded, from y = RN(1/b) (Markstein): two residual corrections with exact
+// FMA residuals.  Replaces the ~35-instruction IEEE division sequence; the divisors (T^2, T^3)
+// are structure-class constants whose reciprocals come with the sample table.
+__device__ __forceinline__ double DivExact(double a, double b, double y) {
+  double q = a * y;
+  double r = fma(-b, q, a);
+  q = fma(r, y, q);
+  r = fma(-b, q, a);
+  return fma(r, y, q);
+}
 // CubicHermitePolynomial::UpdateCoeff (polynomial.cc:97-104) followed by
-// Polynomial::GetPoint (polynomial.cc:47-61): sum_c d^k/dt^k(t^c) * coeff_c, c = A..D.
-template <bool kVelocity, bool kAcceleration>
-__device__ __forceinline__ void EvalSpline(const SplineSample& s, const double* __restrict__ xs,
-                                           double p[3], double v[3], double a[3]) {
+// Polynomial::GetPoint (polynomial.cc:47-61): sum_c d^k/dt^k(t^c) * coeff_c, c = A..D, in the
+// reference's operation order (this translation unit is compiled with -fmad=false, so the
+// products and sums below round exactly like the reference's scalar code).
+// kind 0: position; 1: position + acceleration; 2: position + velocity + acceleration.
+__device__ __forceinline__ void EvalSplineToScratch(const SplineSample& s, int kind, const double* __restrict__ xs,
+                                                    double* __restrict__ out) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[s.xi[d]], v0 = xs[s.xi[3 + d]], p1 = xs[s.xi[6 + d]], v1 = xs[s.xi[9 + d]];
-    const double C = -(3 * (p0 - p1) + s.T * (2 * v0 + v1)) / s.T2;
-    const double D = (2 * (p0 - p1) + s.T * (v0 + v1)) / s.T3;
-    p[d] = ((p0 + s.t * v0) + s.t2 * C) + s.t3 * D;
-    if (kVelocity) v[d] = (v0 + (2 * s.t) * C) + (3 * s.t2) * D;
-    if (kAcceleration) a[d] = 2 * C + (6 * s.t) * D;
+    const double C = DivExact(-(3 * (p0 - p1) + s.T * (2 * v0 + v1)), s.T2, s.rT2);
+    const double D = DivExact(2 * (p0 - p1) + s.T * (v0 + v1), s.T3, s.rT3);
+    out[d] = ((p0 + s.t * v0) + s.t2 * C) + s.t3 * D;
+    if (kind == 1) out[3 + d] = 2 * C + (6 * s.t) * D;
+    if (kind == 2) {
+      out[3 + d] = (v0 + (2 * s.t) * C) + (3 * s.t2) * D;
+      out[6 + d] = 2 * C + (6 * s.t) * D;
+    }
   }
 }
 
@@ -106,7 +121,7 @@ __device__ __forceinline__ void RotVecDerivative(const double dR[3][3][3], const
     for (int d = 0; d < 3; ++d) {
       double s = 0.0;
 #pragma unroll
-      for (int col = 0; col < 3; ++col) s += v[col] * (kInverse ? dR[col][row][d] : dR[row][col][d]);
+      for (int col = 0; col < 3; ++col) s = fma(v[col], kInverse ? dR[col][row][d] : dR[row][col][d], s);
       D[row][d] = s;
     }
 }
@@ -114,7 +129,7 @@ __device__ __forceinline__ void Mul33(const double A[3][3], const double B[3][3]
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
+    for (int j = 0; j < 3; ++j) C[i][j] = fma(A[i][2], B[2][j], fma(A[i][1], B[1][j], A[i][0] * B[0][j]));
 }
 __device__ __forceinline__ void MulVec(const double A[3][3], const double v[3], double o[3]) {
 #pragma unroll
@@ -124,9 +139,9 @@ __device__ __forceinline__ void MulVec(const double A[3][3], const double v[3], 
 __device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3], double C[3][3]) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    C[0][j] = -w[2] * A[1][j] + w[1] * A[2][j];
-    C[1][j] = w[2] * A[0][j] - w[0] * A[2][j];
-    C[2][j] = -w[1] * A[0][j] + w[0] * A[1][j];
+    C[0][j] = fma(w[1], A[2][j], -w[2] * A[1][j]);
+    C[1][j] = fma(w[2], A[0][j], -w[0] * A[2][j]);
+    C[2][j] = fma(w[0], A[1][j], -w[1] * A[0][j]);
   }
 }
 
@@ -139,15 +154,19 @@ __device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3]
 //   EulerConverter::GetDerivOfAng{Vel,Acc}WrtEulerNodes (euler_converter.cc:85-131),
 //   GetDerivMwrtNodes (:168-198), GetDerivMdotwrtNodes (:270-304);
 //   sum of forces, per-foot force and lever arm for the other blocks (:103-121, :167-192).
-__device__ void DynamicUnit(const Plan& P, int k, const double* __restrict__ xs, double* __restrict__ S,
-                            double* __restrict__ g) {
+__device__ void DynamicUnit(const Plan& P, int k, double* __restrict__ S, double* __restrict__ g) {
   const int n_ee = P.n_ee;
-  const SplineSample* ss = P.dyn_samples + (size_t)k * (2 + 2 * n_ee);
   double* Sk = S + P.S_dyn0 + k * P.S_dyn_stride;
-
-  double c[3], cdd[3], th[3], thd[3], thdd[3], dummy[3];
-  EvalSpline<false, true>(ss[0], xs, c, dummy, cdd);
-  EvalSpline<true, true>(ss[1], xs, th, thd, thdd);
+  // phase-0 scratch: c, c_ddot, theta, theta_dot, theta_ddot, p_e.., f_e..
+  double c[3], cdd[3], th[3], thd[3], thdd[3], pe[kMaxEE][3], fe[kMaxEE][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { c[d] = Sk[d]; cdd[d] = Sk[3 + d]; th[d] = Sk[6 + d]; thd[d] = Sk[9 + d]; thdd[d] = Sk[12 + d]; }
+#pragma unroll
+  for (int e = 0; e < kMaxEE; ++e)
+    if (e < n_ee) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { pe[e][d] = Sk[15 + 3 * e + d]; fe[e][d] = Sk[15 + 3 * n_ee + 3 * e + d]; }
+    }
 
   const Trig tr = MakeTrig(th);
   const double sy = tr.sy, cy = tr.cy, sz = tr.sz, cz = tr.cz;
@@ -174,11 +193,11 @@ __device__ void DynamicUnit(const Plan& P, int k, const double* __restrict__ xs,
 
   // feet
   double fsum[3] = {0, 0, 0}, tau[3] = {0, 0, 0};
-  for (int e = 0; e < n_ee; ++e) {
-    double pe[3], f[3];
-    EvalSpline<false, false>(ss[2 + e], xs, pe, dummy, dummy);
-    EvalSpline<false, false>(ss[2 + n_ee + e], xs, f, dummy, dummy);
-    const double r[3] = {c[0] - pe[0], c[1] - pe[1], c[2] - pe[2]};
+#pragma unroll
+  for (int e = 0; e < kMaxEE; ++e) {
+    if (e >= n_ee) break;
+    const double* f = fe[e];
+    const double r[3] = {c[0] - pe[e][0], c[1] - pe[e][1], c[2] - pe[e][2]};
     tau[0] += f[1] * r[2] - f[2] * r[1];
     tau[1] += f[2] * r[0] - f[0] * r[2];
     tau[2] += f[0] * r[1] - f[1] * r[0];
@@ -263,14 +282,18 @@ __device__ void DynamicUnit(const Plan& P, int k, const double* __restrict__ xs,
 // ---- RangeOfMotionConstraint sample (all feet) --------------------------------
 // range_of_motion_constraint.cc:58-109: g = R^T (p_ee - c); Jacobian state R^T and
 // D_e = d(R^T r_e)/d(theta) (DerivOfRotVecMult(t, r_W, true)).
-__device__ void RomUnit(const Plan& P, int k, const double* __restrict__ xs, double* __restrict__ S,
-                        double* __restrict__ g) {
+__device__ void RomUnit(const Plan& P, int k, double* __restrict__ S, double* __restrict__ g) {
   const int n_ee = P.n_ee;
-  const SplineSample* ss = P.rom_samples + (size_t)k * (2 + n_ee);
   double* Sk = S + P.S_rom0 + k * P.S_rom_stride;
-  double c[3], th[3], dummy[3];
-  EvalSpline<false, false>(ss[0], xs, c, dummy, dummy);
-  EvalSpline<false, false>(ss[1], xs, th, dummy, dummy);
+  double c[3], th[3], pes[kMaxEE][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { c[d] = Sk[d]; th[d] = Sk[3 + d]; }
+#pragma unroll
+  for (int e = 0; e < kMaxEE; ++e)
+    if (e < n_ee) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) pes[e][d] = Sk[6 + 3 * e + d];
+    }
   const Trig tr = MakeTrig(th);
   double R[3][3]; RotationMatrix(tr, R);
   double dR[3][3][3]; RotationDerivative(tr, dR);
@@ -278,9 +301,10 @@ __device__ void RomUnit(const Plan& P, int k, const double* __restrict__ xs, dou
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int d = 0; d < 3; ++d) Sk[i * 3 + d] = R[d][i];
-  for (int e = 0; e < n_ee; ++e) {
-    double pe[3];
-    EvalSpline<false, false>(ss[2 + e], xs, pe, dummy, dummy);
+#pragma unroll
+  for (int e = 0; e < kMaxEE; ++e) {
+    if (e >= n_ee) break;
+    const double* pe = pes[e];
     const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
     if (g) {
       double* ge = g + P.rom_row0[e] + 3 * k;
@@ -335,11 +359,11 @@ __device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) 
 
 // TerrainConstraint, terrain_constraint.cc:59-108
 __device__ __forceinline__ void TerrainUnitEval(const TerrainUnit& u, int terrain, const double* __restrict__ xs,
-                                                double* __restrict__ S, double* __restrict__ g) {
+                                                double* __restrict__ jac, double* __restrict__ g) {
   const double px = xs[u.xi[0]], py = xs[u.xi[1]], pz = xs[u.xi[2]];
   const TerrainPoint tp = EvalTerrain(terrain, px, py);
   if (g) g[u.g_row] = pz - tp.h;
-  S[u.s_idx + 0] = -tp.hx; S[u.s_idx + 1] = -tp.hy;
+  if (jac) { double* J = jac + u.jac_slot; __stcs(J + 0, -tp.hx); __stcs(J + 1, -tp.hy); __stcs(J + 2, 1.0); }
 }
 
 // normalised vector and HeightMap::GetDerivativeOfNormalizedBasisWrt (height_map.cc:62-91,140-146):
@@ -360,7 +384,7 @@ __device__ __forceinline__ double Dot3(const double a[3], const double b[3]) { r
 
 // ForceConstraint, force_constraint.cc:64-171
 __device__ void ForceUnitEval(const ForceUnit& u, int terrain, double mu, const double* __restrict__ xs,
-                              double* __restrict__ S, double* __restrict__ g) {
+                              double* __restrict__ jac, double* __restrict__ g) {
   const double px = xs[u.xp[0]], py = xs[u.xp[1]];
   const double f[3] = {xs[u.xf[0]], xs[u.xf[1]], xs[u.xf[2]]};
   const TerrainPoint tp = EvalTerrain(terrain, px, py);
@@ -378,7 +402,8 @@ __device__ void ForceUnitEval(const ForceUnit& u, int terrain, double mu, const 
     double* gr = g + u.g_row;
     gr[0] = Dot3(f, n); gr[1] = Dot3(f, a1); gr[2] = Dot3(f, b1); gr[3] = Dot3(f, a2); gr[4] = Dot3(f, b2);
   }
-  double* Su = S + u.s_idx;
+  if (!jac) return;
+  double Su[25];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     Su[0 * 5 + 2 + d] = n[d]; Su[1 * 5 + 2 + d] = a1[d]; Su[2 * 5 + 2 + d] = b1[d];
@@ -403,6 +428,9 @@ __device__ void ForceUnitEval(const ForceUnit& u, int terrain, double mu, const 
     Su[0 * 5 + dim] = Dot3(f, dn); Su[1 * 5 + dim] = Dot3(f, m1); Su[2 * 5 + dim] = Dot3(f, p1);
     Su[3 * 5 + dim] = Dot3(f, m2); Su[4 * 5 + dim] = Dot3(f, p2);
   }
+  double* J = jac + u.jac_slot;
+#pragma unroll
+  for (int i = 0; i < 25; ++i) __stcs(J + i, Su[i]);
 }
 
 // SwingConstraint::GetValues, swing_constraint.cc:57-83 (Jacobian is constant)
@@ -427,9 +455,9 @@ __device__ __forceinline__ void AccUnitEval(const AccUnit& u, const double* __re
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[u.x0 + d], v0 = xs[u.x0 + 3 + d], p1 = xs[u.x0 + 6 + d], v1 = xs[u.x0 + 9 + d];
     const double p2 = xs[u.x0 + 12 + d], v2 = xs[u.x0 + 15 + d];
-    const double Cp = -(3 * (p0 - p1) + u.Tp * (2 * v0 + v1)) / u.Tp2;
-    const double Dp = (2 * (p0 - p1) + u.Tp * (v0 + v1)) / u.Tp3;
-    const double Cn = -(3 * (p1 - p2) + u.Tn * (2 * v1 + v2)) / u.Tn2;
+    const double Cp = DivExact(-(3 * (p0 - p1) + u.Tp * (2 * v0 + v1)), u.Tp2, u.rTp2);
+    const double Dp = DivExact(2 * (p0 - p1) + u.Tp * (v0 + v1), u.Tp3, u.rTp3);
+    const double Cn = DivExact(-(3 * (p1 - p2) + u.Tn * (2 * v1 + v2)), u.Tn2, u.rTn2);
     const double a_prev = 2 * Cp + (6 * u.Tp) * Dp;
     const double a_next = 2 * Cn;
     g[u.g_row + d] = a_prev - a_next;
@@ -438,7 +466,7 @@ __device__ __forceinline__ void AccUnitEval(const AccUnit& u, const double* __re
 
 // ---- the kernel ---------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, double* __restrict__ jac,
            double* __restrict__ cost, double* __restrict__ grad, int* __restrict__ status,
            const int* __restrict__ terrain_ids, int default_terrain, int B, unsigned flags) {
@@ -476,6 +504,20 @@ EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, d
 
   const bool want_g = (flags & 1u) != 0, want_jac = (flags & 2u) != 0, want_cost = (flags & 4u) != 0 && P.n_cost > 0;
 
+  // ---- phase 0: every (instance, sample, spline) Hermite evaluation, one per thread
+  {
+    const int n_items = P.n_eval_items;
+    for (int gi = 0; gi < nb; ++gi) {
+      const double* xs = xs_all + gi * xs_stride;
+      double* S = S_all + gi * S_stride;
+      for (int j = tid; j < n_items; j += kThreads) {
+        const EvalItem it = P.eval_items[j];
+        EvalSplineToScratch(P.samples[it.sample], it.kind, xs, S + it.scratch);
+      }
+    }
+  }
+  __syncthreads();
+
   // ---- phase 1: units.  Item ranges are padded to warp granularity so a warp runs one unit type.
   auto pad32 = [](int v) { return (v + 31) & ~31; };
   const int c_dyn = nb * P.n_dyn, c_rom = nb * P.n_rom, c_force = nb * P.n_force, c_terr = nb * P.n_terr;
@@ -487,27 +529,29 @@ EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, d
     if (item < o_rom) {
       if (item < c_dyn) {
         const int gi = item / P.n_dyn, k = item - gi * P.n_dyn;
-        DynamicUnit(P, k, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+        DynamicUnit(P, k, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
       }
     } else if (item < o_force) {
       const int it = item - o_rom;
       if (it < c_rom) {
         const int gi = it / P.n_rom, k = it - gi * P.n_rom;
-        RomUnit(P, k, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+        RomUnit(P, k, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
       }
     } else if (item < o_terr) {
       const int it = item - o_force;
       if (it < c_force) {
         const int gi = it / P.n_force, u = it - gi * P.n_force;
         const int terrain = terrain_ids ? terrain_ids[b0 + gi] : default_terrain;
-        ForceUnitEval(P.force[u], terrain, P.mu, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+        ForceUnitEval(P.force[u], terrain, P.mu, xs_all + gi * xs_stride, want_jac ? jac + (size_t)(b0 + gi) * nnz : nullptr,
+                      want_g ? g + (size_t)(b0 + gi) * m : nullptr);
       }
     } else if (item < o_swing) {
       const int it = item - o_terr;
       if (it < c_terr) {
         const int gi = it / P.n_terr, u = it - gi * P.n_terr;
         const int terrain = terrain_ids ? terrain_ids[b0 + gi] : default_terrain;
-        TerrainUnitEval(P.terr[u], terrain, xs_all + gi * xs_stride, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
+        TerrainUnitEval(P.terr[u], terrain, xs_all + gi * xs_stride, want_jac ? jac + (size_t)(b0 + gi) * nnz : nullptr,
+                        want_g ? g + (size_t)(b0 + gi) * m : nullptr);
       }
     } else if (item < o_acc) {
       const int it = item - o_swing;
@@ -544,30 +588,49 @@ EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, d
   }
   __syncthreads();
 
-  // ---- phase 2: fill the CSR value arrays
+  // ---- phase 2: fill the descriptor-driven CSR slots, two slots (16 bytes) per thread
   if (want_jac) {
-    bool bad = false;
-    for (int slot = tid; slot < nnz; slot += kThreads) {
-      const uint32_t d = __ldg(P.desc + slot);
-      const double c0 = __ldg(P.coef + slot);
-      const uint32_t a = d & 0xFFFFu;
-      double c1 = 0.0, c2 = 0.0;
-      const bool triple = (d & kDescTriple) != 0;
-      if (triple) { const uint32_t e = (d >> 16) & 0x7FFFu; c1 = __ldg(P.extra + 2 * e); c2 = __ldg(P.extra + 2 * e + 1); }
+    const bool vec_ok = ((nnz & 1) == 0) && ((reinterpret_cast<uintptr_t>(jac) & 15) == 0);
+    double chk[G];
 #pragma unroll
-      for (int gi = 0; gi < G; ++gi) {
-        if (gi < nb) {
-          const double* Sg = S_all + gi * S_stride;
-          double v = Sg[a] * c0;
-          if (triple) v = (v + Sg[a + 1] * c1) + Sg[a + 2] * c2;
-          bad |= !isfinite(v);
-          __stcs(jac + (size_t)(b0 + gi) * nnz + slot, v);
+    for (int gi = 0; gi < G; ++gi) chk[gi] = 0.0;
+    const uint2* desc2 = reinterpret_cast<const uint2*>(P.desc);
+    const double2* coef2 = reinterpret_cast<const double2*>(P.coef);
+    for (int sg = 0; sg < P.n_seg; ++sg) {
+      const int s_begin = P.seg_start[sg], s_end = P.seg_end[sg];
+      for (int q = (s_begin >> 1) + tid; 2 * q < s_end; q += kThreads) {
+        const int s0 = 2 * q;
+        const uint2 d = __ldg(desc2 + q);
+        const double2 c = __ldg(coef2 + q);
+        const bool in0 = s0 >= s_begin, in1 = s0 + 1 < s_end;
+        const uint32_t a0 = d.x & 0xFFFFu, a1 = d.y & 0xFFFFu;
+        const bool t0 = (d.x & kDescTriple) != 0, t1 = (d.y & kDescTriple) != 0;
+        double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;
+        if (t0) { const uint32_t e = (d.x >> 16) & 0x7FFFu; const double2 ex = __ldg(reinterpret_cast<const double2*>(P.extra) + e); e00 = ex.x; e01 = ex.y; }
+        if (t1) { const uint32_t e = (d.y >> 16) & 0x7FFFu; const double2 ex = __ldg(reinterpret_cast<const double2*>(P.extra) + e); e10 = ex.x; e11 = ex.y; }
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          if (gi < nb) {
+            const double* Sg = S_all + gi * S_stride;
+            double v0 = Sg[a0] * c.x, v1 = Sg[a1] * c.y;
+            if (t0) v0 = fma(Sg[a0 + 2], e01, fma(Sg[a0 + 1], e00, v0));
+            if (t1) v1 = fma(Sg[a1 + 2], e11, fma(Sg[a1 + 1], e10, v1));
+            double* out = jac + (size_t)(b0 + gi) * nnz + s0;
+            if (vec_ok && in0 && in1) {
+              __stcs(reinterpret_cast<double2*>(out), make_double2(v0, v1));
+              chk[gi] = fma(v0, 0.0, fma(v1, 0.0, chk[gi]));
+            } else {
+              if (in0) { __stcs(out, v0); chk[gi] = fma(v0, 0.0, chk[gi]); }
+              if (in1) { __stcs(out + 1, v1); chk[gi] = fma(v1, 0.0, chk[gi]); }
+            }
+          }
         }
       }
     }
-    if (status && bad) {
-      // conservative: flags every instance of the CTA group
-      for (int gi = 0; gi < nb; ++gi) atomicOr(status + b0 + gi, 1);
+    if (status) {
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi)
+        if (gi < nb && chk[gi] != chk[gi]) atomicOr(status + b0 + gi, 1);   // NaN or Inf seen
     }
   }
 }
@@ -597,7 +660,10 @@ int LaunchEval(const Plan& P, int G, const double* x, double* g, double* jac, do
   switch (G) {
     case 1: TWB_LAUNCH(1); break;
     case 2: TWB_LAUNCH(2); break;
+    case 3: TWB_LAUNCH(3); break;
     case 4: TWB_LAUNCH(4); break;
+    case 6: TWB_LAUNCH(6); break;
+    case 8: TWB_LAUNCH(8); break;
     default: return (int)cudaErrorInvalidValue;
   }
 #undef TWB_LAUNCH
