@@ -138,7 +138,7 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
     return CudaFail(e, "table upload");                                                \
   }
   TWB_UP(samples) TWB_UP(eval_items) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc) TWB_UP(cost)
-  TWB_UP(desc) TWB_UP(coef) TWB_UP(extra)
+  TWB_UP(desc) TWB_UP(coef) TWB_UP(dyn_ang_basis)
 #undef TWB_UP
   // instances per CTA: largest G in {4,2,1} that lets two CTAs share an SM's shared memory
   int max_smem = 0;

@@ -17,11 +17,12 @@ constexpr int kMaxSegments = 16;
 // boundary nodes live in x.  `xi` holds x indices of p0[3], v0[3], p1[3],
 // v1[3]; node values that are not optimised (always 0 in towr) point at the
 // zero slot, index n.
-struct SplineSample {
+struct alignas(16) SplineSample {   // 96 bytes = six 16-byte loads
   double T, T2, T3;   // polynomial duration and std::pow(T,2), std::pow(T,3)
   double rT2, rT3;    // correctly rounded 1/T2, 1/T3 (seed of the exact division on the device)
   double t, t2, t3;   // local time and std::pow(t,2), std::pow(t,3)
   int16_t xi[12];
+  int16_t pad[4];
 };
 
 // One phase-0 work item: evaluate spline sample `sample` into S[scratch..]
@@ -74,11 +75,7 @@ struct CostEntry {
   double weight;
 };
 
-// Jacobian slot descriptor: value = S[a]*coef  (+ S[a+1]*extra[2e] + S[a+2]*extra[2e+1] if triple)
-constexpr uint32_t kDescTriple = 0x80000000u;
-inline uint32_t MakeDesc(uint32_t a, uint32_t extra_idx, bool triple) {
-  return (a & 0xFFFFu) | ((extra_idx & 0x7FFFu) << 16) | (triple ? kDescTriple : 0u);
-}
+// Jacobian slot descriptor: value = S[desc] * coef
 
 struct Plan {
   int n, m, nnz, n_ee;
@@ -105,9 +102,9 @@ struct Plan {
   const SwingUnit* swing;
   const AccUnit* acc;
   const CostEntry* cost;
+  const double* dyn_ang_basis;  // [n_dyn][12]: base-ang basis of the active polynomial, {pos, vel, acc} x {p0, v0, p1, v1}
   const uint32_t* desc;   // [nnz padded to even]
   const double* coef;     // [nnz padded to even]
-  const double* extra;    // [2*n_triples]
 };
 
 }  // namespace twb

@@ -173,7 +173,7 @@ std::vector<double> BasePolyDurations(double T, double dt) {  // parameters.cc:8
   return v;
 }
 
-struct Emit { int row, col; uint32_t a; bool triple; double c0, c1, c2; bool direct; };
+struct Emit { int row, col; uint32_t a; double c0; bool direct; };
 
 // sign/component of Cross(v)[i][d] (single_rigid_body_dynamics.cc:46-57): value = sign * v[comp]
 void CrossEntry(int i, int d, int* comp, double* sign) {
@@ -287,10 +287,9 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   const uint32_t S_ONE = 0;
 
   std::vector<Emit> em;
-  auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, false, c, 0.0, 0.0, false}); };
-  auto emit3 = [&](int row, int col, uint32_t a, double c0, double c1, double c2) { em.push_back({row, col, a, true, c0, c1, c2, false}); };
+  auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, c, false}); };
   // entries a terrain/force unit writes straight into the CSR array (no descriptor)
-  auto emit_direct = [&](int row, int col) { em.push_back({row, col, 0u, false, 0.0, 0.0, 0.0, true}); };
+  auto emit_direct = [&](int row, int col) { em.push_back({row, col, 0u, 0.0, true}); };
 
   auto add_eval = [&](const SplineSample& s, uint32_t scratch, int kind) {
     EvalItem it{}; it.sample = (int32_t)tb.samples.size(); it.scratch = (int16_t)scratch; it.kind = (int16_t)kind;
@@ -310,7 +309,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_dynamic);
         int r0 = add_set("dynamic", (int)ts.size() * 6);
         pl.dyn_row0 = r0; pl.n_dyn = (int)ts.size();
-        pl.S_dyn_stride = 30 + 6 * n_ee; pl.S_dyn0 = S_top; S_top += pl.S_dyn_stride * pl.n_dyn;
+        pl.S_dyn_stride = 39 + 6 * n_ee; pl.S_dyn0 = S_top; S_top += pl.S_dyn_stride * pl.n_dyn;
         for (int k = 0; k < pl.n_dyn; ++k) {
           const double t = ts[k];
           const int row = r0 + 6 * k; const uint32_t sb = pl.S_dyn0 + k * pl.S_dyn_stride;
@@ -329,13 +328,19 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
               emit1(row + i, lin.offset + b.var, sb + comp, -sg * b.val);
             }
           for (auto& b : Basis(sp_lin, p, tl, kAcc)) emit1(row + 3 + b.dim, lin.offset + b.var, S_ONE, rb.mass * b.val);
-          // base-ang: angular rows = A*dtheta + B*dtheta_dot + C*dtheta_ddot
+          // base-ang: angular rows = A*dtheta + B*dtheta_dot + C*dtheta_ddot, contracted with the
+          // basis by the dynamic unit itself: S holds the 3 x 12 finished values
           Locate(sp_ang, t, &p, &tl);
           {
             auto bp = Basis(sp_ang, p, tl, kPos), bv = Basis(sp_ang, p, tl, kVel), ba = Basis(sp_ang, p, tl, kAcc);
-            for (size_t j = 0; j < bp.size(); ++j)
-              for (int i = 0; i < 3; ++i)
-                emit3(row + i, ang.offset + bp[j].var, sb + 3 + (i * 3 + bp[j].dim) * 3, bp[j].val, bv[j].val, ba[j].val);
+            if (bp.size() != 12) return fail(TWB_ERR_UNSUPPORTED, "base-ang basis layout");
+            for (int j = 0; j < 12; ++j) {
+              if (bp[j].dim != j % 3 || bp[j].var != p * 6 + j) return fail(TWB_ERR_UNSUPPORTED, "base-ang basis layout");
+              for (int i = 0; i < 3; ++i) emit1(row + i, ang.offset + bp[j].var, sb + 3 + i * 12 + j, 1.0);
+            }
+            for (int q = 0; q < 4; ++q) tb.dyn_ang_basis.push_back(bp[3 * q].val);
+            for (int q = 0; q < 4; ++q) tb.dyn_ang_basis.push_back(bv[3 * q].val);
+            for (int q = 0; q < 4; ++q) tb.dyn_ang_basis.push_back(ba[3 * q].val);
           }
           for (int e = 0; e < n_ee; ++e) {
             // ee-motion: angular rows = [f_e]x dp_e
@@ -343,14 +348,14 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             for (auto& b : Basis(sp_motion[e], p, tl, kPos))
               for (int i = 0; i < 3; ++i) if (i != b.dim) {
                 int comp; double sg; CrossEntry(i, b.dim, &comp, &sg);
-                emit1(row + i, motion(e).offset + b.var, sb + 30 + e * 6 + comp, sg * b.val);
+                emit1(row + i, motion(e).offset + b.var, sb + 39 + e * 6 + comp, sg * b.val);
               }
             // ee-force: angular rows = [c - p_e]x df_e ; linear rows = -df_e
             Locate(sp_force[e], t, &p, &tl);
             for (auto& b : Basis(sp_force[e], p, tl, kPos)) {
               for (int i = 0; i < 3; ++i) if (i != b.dim) {
                 int comp; double sg; CrossEntry(i, b.dim, &comp, &sg);
-                emit1(row + i, force(e).offset + b.var, sb + 30 + e * 6 + 3 + comp, sg * b.val);
+                emit1(row + i, force(e).offset + b.var, sb + 39 + e * 6 + 3 + comp, sg * b.val);
               }
               emit1(row + 3 + b.dim, force(e).offset + b.var, S_ONE, -b.val);
             }
@@ -511,13 +516,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
       }
     }
     row_ptr[em[s].row + 1]++; col_idx[s] = em[s].col;
-    uint32_t extra_idx = 0;
-    if (em[s].triple) {
-      extra_idx = (uint32_t)(tb.extra.size() / 2);
-      if (extra_idx > 0x7FFFu) return fail(TWB_ERR_UNSUPPORTED, "too many 3-term Jacobian entries");
-      tb.extra.push_back(em[s].c1); tb.extra.push_back(em[s].c2);
-    }
-    tb.desc[s] = MakeDesc(em[s].a, extra_idx, em[s].triple);
+    tb.desc[s] = em[s].a;
     tb.coef[s] = em[s].c0;
   }
   for (int r = 0; r < m; ++r) row_ptr[r + 1] += row_ptr[r];

@@ -41,7 +41,7 @@ struct HostTables {
   std::vector<AccUnit> acc;
   std::vector<CostEntry> cost;
   std::vector<uint32_t> desc;
-  std::vector<double> coef, extra;
+  std::vector<double> coef, dyn_ang_basis;
 };
 
 class Formulation {

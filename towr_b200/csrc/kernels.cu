@@ -29,6 +29,8 @@
 #include "device_tables.h"
 #include "launch.h"
 
+#include <cstdint>
+
 namespace twb {
 namespace {
 
@@ -70,7 +72,20 @@ __device__ __forceinline__ double DivExact(double a, double b, double y) {
 // reference's operation order (this translation unit is compiled with -fmad=false, so the
 // products and sums below round exactly like the reference's scalar code).
 // kind 0: position; 1: position + acceleration; 2: position + velocity + acceleration.
-__device__ __forceinline__ void EvalSplineToScratch(const SplineSample& s, int kind, const double* __restrict__ xs,
+struct SampleRegs { double T, T2, T3, rT2, rT3, t, t2, t3; int xi[12]; };
+__device__ __forceinline__ SampleRegs LoadSample(const SplineSample* __restrict__ p) {
+  const double2* d = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(d), b = __ldg(d + 1), c = __ldg(d + 2), e = __ldg(d + 3);
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + 4);
+  const uint2 w = __ldg(reinterpret_cast<const uint2*>(p) + 10);
+  SampleRegs r;
+  r.T = a.x; r.T2 = a.y; r.T3 = b.x; r.rT2 = b.y; r.rT3 = c.x; r.t = c.y; r.t2 = e.x; r.t3 = e.y;
+  const uint32_t v[6] = {u.x, u.y, u.z, u.w, w.x, w.y};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { r.xi[2 * i] = (int)(v[i] & 0xFFFFu); r.xi[2 * i + 1] = (int)(v[i] >> 16); }
+  return r;
+}
+__device__ __forceinline__ void EvalSplineToScratch(const SampleRegs& s, int kind, const double* __restrict__ xs,
                                                     double* __restrict__ out) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -202,7 +217,7 @@ __device__ void DynamicUnit(const Plan& P, int k, double* __restrict__ S, double
     tau[1] += f[2] * r[0] - f[0] * r[2];
     tau[2] += f[0] * r[1] - f[1] * r[0];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) { fsum[d] += f[d]; Sk[30 + e * 6 + d] = f[d]; Sk[30 + e * 6 + 3 + d] = r[d]; }
+    for (int d = 0; d < 3; ++d) { fsum[d] += f[d]; Sk[39 + e * 6 + d] = f[d]; Sk[39 + e * 6 + 3 + d] = r[d]; }
   }
   Sk[0] = fsum[0]; Sk[1] = fsum[1]; Sk[2] = fsum[2];
 
@@ -270,12 +285,17 @@ __device__ void DynamicUnit(const Plan& P, int k, double* __restrict__ S, double
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int d = 0; d < 3; ++d) Bm[i][d] += X1[i][d] - X2[i][d];
+  // contract with the Hermite basis of the active base-ang polynomial: 3 rows x 12 node values
+  const double* bb = P.dyn_ang_basis + 12 * k;
+  double bpv[4], bvv[4], bav[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { bpv[q] = __ldg(bb + q); bvv[q] = __ldg(bb + 4 + q); bav[q] = __ldg(bb + 8 + q); }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      double* q = Sk + 3 + (i * 3 + d) * 3;
-      q[0] = A[i][d]; q[1] = Bm[i][d]; q[2] = C[i][d];
+    for (int j = 0; j < 12; ++j) {
+      const int d = j % 3, q = j / 3;
+      Sk[3 + i * 12 + j] = fma(C[i][d], bav[q], fma(Bm[i][d], bvv[q], A[i][d] * bpv[q]));
     }
 }
 
@@ -507,13 +527,13 @@ EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, d
   // ---- phase 0: every (instance, sample, spline) Hermite evaluation, one per thread
   {
     const int n_items = P.n_eval_items;
-    for (int gi = 0; gi < nb; ++gi) {
-      const double* xs = xs_all + gi * xs_stride;
-      double* S = S_all + gi * S_stride;
-      for (int j = tid; j < n_items; j += kThreads) {
-        const EvalItem it = P.eval_items[j];
-        EvalSplineToScratch(P.samples[it.sample], it.kind, xs, S + it.scratch);
-      }
+    for (int j = tid; j < n_items; j += kThreads) {
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.eval_items) + j);
+      const int sample = (int)raw.x, scratch = (int)(raw.y & 0xFFFFu), kind = (int)(raw.y >> 16);
+      const SampleRegs sr = LoadSample(P.samples + sample);
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi)
+        if (gi < nb) EvalSplineToScratch(sr, kind, xs_all + gi * xs_stride, S_all + gi * S_stride + scratch);
     }
   }
   __syncthreads();
@@ -588,49 +608,62 @@ EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, d
   }
   __syncthreads();
 
-  // ---- phase 2: fill the descriptor-driven CSR slots, two slots (16 bytes) per thread
+  // ---- phase 2: fill the descriptor-driven CSR slots
   if (want_jac) {
-    const bool vec_ok = ((nnz & 1) == 0) && ((reinterpret_cast<uintptr_t>(jac) & 15) == 0);
-    double chk[G];
+    // non-finite detection on the state vector (every descriptor value is S[a] * finite constant)
+    if (status) {
 #pragma unroll
-    for (int gi = 0; gi < G; ++gi) chk[gi] = 0.0;
-    const uint2* desc2 = reinterpret_cast<const uint2*>(P.desc);
-    const double2* coef2 = reinterpret_cast<const double2*>(P.coef);
-    for (int sg = 0; sg < P.n_seg; ++sg) {
-      const int s_begin = P.seg_start[sg], s_end = P.seg_end[sg];
-      for (int q = (s_begin >> 1) + tid; 2 * q < s_end; q += kThreads) {
-        const int s0 = 2 * q;
-        const uint2 d = __ldg(desc2 + q);
-        const double2 c = __ldg(coef2 + q);
-        const bool in0 = s0 >= s_begin, in1 = s0 + 1 < s_end;
-        const uint32_t a0 = d.x & 0xFFFFu, a1 = d.y & 0xFFFFu;
-        const bool t0 = (d.x & kDescTriple) != 0, t1 = (d.y & kDescTriple) != 0;
-        double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;
-        if (t0) { const uint32_t e = (d.x >> 16) & 0x7FFFu; const double2 ex = __ldg(reinterpret_cast<const double2*>(P.extra) + e); e00 = ex.x; e01 = ex.y; }
-        if (t1) { const uint32_t e = (d.y >> 16) & 0x7FFFu; const double2 ex = __ldg(reinterpret_cast<const double2*>(P.extra) + e); e10 = ex.x; e11 = ex.y; }
-#pragma unroll
-        for (int gi = 0; gi < G; ++gi) {
-          if (gi < nb) {
-            const double* Sg = S_all + gi * S_stride;
-            double v0 = Sg[a0] * c.x, v1 = Sg[a1] * c.y;
-            if (t0) v0 = fma(Sg[a0 + 2], e01, fma(Sg[a0 + 1], e00, v0));
-            if (t1) v1 = fma(Sg[a1 + 2], e11, fma(Sg[a1 + 1], e10, v1));
-            double* out = jac + (size_t)(b0 + gi) * nnz + s0;
-            if (vec_ok && in0 && in1) {
-              __stcs(reinterpret_cast<double2*>(out), make_double2(v0, v1));
-              chk[gi] = fma(v0, 0.0, fma(v1, 0.0, chk[gi]));
-            } else {
-              if (in0) { __stcs(out, v0); chk[gi] = fma(v0, 0.0, chk[gi]); }
-              if (in1) { __stcs(out + 1, v1); chk[gi] = fma(v1, 0.0, chk[gi]); }
-            }
-          }
+      for (int gi = 0; gi < G; ++gi) {
+        if (gi < nb) {
+          const double* Sg = S_all + gi * S_stride;
+          double chk = 0.0;
+          for (int i = tid; i < P.S_size; i += kThreads) chk = fma(Sg[i], 0.0, chk);
+          if (chk != chk) atomicOr(status + b0 + gi, 1);
         }
       }
     }
-    if (status) {
+    double* outg[G];
 #pragma unroll
-      for (int gi = 0; gi < G; ++gi)
-        if (gi < nb && chk[gi] != chk[gi]) atomicOr(status + b0 + gi, 1);   // NaN or Inf seen
+    for (int gi = 0; gi < G; ++gi) outg[gi] = jac + (size_t)(b0 + min(gi, nb - 1)) * nnz;
+    const bool vec_ok = ((nnz & 1) == 0) && ((reinterpret_cast<uintptr_t>(jac) & 15) == 0);
+    for (int sg = 0; sg < P.n_seg; ++sg) {
+      const int s_begin = P.seg_start[sg], s_end = P.seg_end[sg];
+      if (vec_ok) {
+        // aligned interior: two slots (16 bytes) per thread, next descriptors prefetched
+        const int q_begin = (s_begin + 1) >> 1, q_end = s_end >> 1;
+        const uint2* desc2 = reinterpret_cast<const uint2*>(P.desc);
+        const double2* coef2 = reinterpret_cast<const double2*>(P.coef);
+        int q = q_begin + tid;
+        uint2 d = make_uint2(0u, 0u); double2 c = make_double2(0.0, 0.0);
+        if (q < q_end) { d = __ldg(desc2 + q); c = __ldg(coef2 + q); }
+        while (q < q_end) {
+          const int qn = q + kThreads;
+          uint2 dn = make_uint2(0u, 0u); double2 cn = make_double2(0.0, 0.0);
+          if (qn < q_end) { dn = __ldg(desc2 + qn); cn = __ldg(coef2 + qn); }
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi) {
+            if (gi < nb) {
+              const double* Sg = S_all + gi * S_stride;
+              __stcs(reinterpret_cast<double2*>(outg[gi]) + q, make_double2(Sg[d.x] * c.x, Sg[d.y] * c.y));
+            }
+          }
+          q = qn; d = dn; c = cn;
+        }
+        // ragged ends of the segment (at most one slot each)
+        if (tid < 2) {
+          const int s = (tid == 0) ? s_begin : s_end - 1;
+          const bool need = (tid == 0) ? ((s_begin & 1) != 0) : (((s_end & 1) != 0) && (s_end - 1 > s_begin || (s_begin & 1) == 0));
+          if (need) {
+            const uint32_t a = __ldg(P.desc + s); const double cf = __ldg(P.coef + s);
+            for (int gi = 0; gi < nb; ++gi) __stcs(outg[gi] + s, S_all[gi * S_stride + a] * cf);
+          }
+        }
+      } else {
+        for (int s = s_begin + tid; s < s_end; s += kThreads) {
+          const uint32_t a = __ldg(P.desc + s); const double cf = __ldg(P.coef + s);
+          for (int gi = 0; gi < nb; ++gi) __stcs(outg[gi] + s, S_all[gi * S_stride + a] * cf);
+        }
+      }
     }
   }
 }
