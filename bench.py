@@ -189,6 +189,11 @@ def run_cuda(args):
     total_ms = float(t.item())
     value = world * B * args.steps / (total_ms * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": total_ms / args.steps, "ms_best": per_step[0],
+                              "frac": 8 * (p.n + p.m + p.nnz) * B / (total_ms / args.steps * 1e-3) / 1e9 / read_peak()[0]}), flush=True)
+        return
     # ---- end to end through the host-pointer C ABI call: pinned host buffers, H2D + D2H inside the timed region
     xs_pinned = torch.from_numpy(Xh).pin_memory()
     out = {"g": torch.empty((B, p.m), dtype=torch.float64).pin_memory().numpy(),
@@ -258,6 +263,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--quick", action="store_true", help="kernel timing only (tuning sweeps): skip e2e and the CPU arm")
     args = ap.parse_args()
     import __graft_entry__ as ge
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:

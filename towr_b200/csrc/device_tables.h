@@ -9,7 +9,7 @@
 namespace twb {
 
 constexpr int kMaxEE = 4;
-constexpr int kMaxSegments = 16;
+constexpr int kFillChunkSlots = 1024;   // CSR slots one fill CTA owns
 
 // One spline evaluated at one constraint sample when phase durations are
 // fixed: the active polynomial (Spline::GetSegmentID, spline.cc:48-63), its
@@ -25,7 +25,7 @@ struct alignas(16) SplineSample {   // 96 bytes = six 16-byte loads
   int16_t pad[4];
 };
 
-// One phase-0 work item: evaluate spline sample `sample` into S[scratch..]
+// One spline-kernel work item: evaluate spline sample `sample` into state rows scratch..
 // kind 0: position (3 doubles); 1: position + acceleration (6); 2: position + velocity + acceleration (9)
 struct EvalItem {
   int32_t sample;
@@ -38,7 +38,7 @@ struct TerrainUnit {
   int16_t xi[3];      // x index of node position x,y,z
   int16_t pad;
   int32_t g_row;      // constraint row
-  int32_t jac_slot;   // CSR slot of the row's 3 values {-dh/dx, -dh/dy, 1}
+  int32_t s_idx;      // state rows of {-dh/dx, -dh/dy}
 };
 
 // ForceConstraint node (force_constraint.cc:64-171): 5 rows
@@ -47,7 +47,7 @@ struct ForceUnit {
   int16_t xp[3];      // x index of the stance-foot position (phase start node); [2] unused
   int16_t pad[2];
   int32_t g_row;      // first of the 5 rows
-  int32_t jac_slot;   // CSR slot of the 25 contiguous values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
+  int32_t s_idx;      // state rows of the 25 Jacobian values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
 };
 
 // SwingConstraint node (swing_constraint.cc:57-83): 4 rows
@@ -85,11 +85,8 @@ struct Plan {
   int dyn_row0;
   int rom_row0[kMaxEE];
   int totdur_row0;
-  // S layout (doubles, per instance)
-  int S_size, S_dyn0, S_dyn_stride, S_rom0, S_rom_stride;
-  // CSR slot ranges filled from descriptors (the rest is written directly by terrain/force units)
-  int n_seg;
-  int seg_start[kMaxSegments], seg_end[kMaxSegments];
+  // state rows: [0] = 1.0 | dynamic blocks | RoM blocks | force / terrain values | g (m rows) | cost gradient (n rows)
+  int S_size, S_dyn0, S_dyn_stride, S_rom0, S_rom_stride, S_g0, S_grad0;
   // robot
   double mass, gravity;
   double I_b[9];
@@ -103,8 +100,14 @@ struct Plan {
   const AccUnit* acc;
   const CostEntry* cost;
   const double* dyn_ang_basis;  // [n_dyn][12]: base-ang basis of the active polynomial, {pos, vel, acc} x {p0, v0, p1, v1}
-  const uint32_t* desc;   // [nnz padded to even]
-  const double* coef;     // [nnz padded to even]
+  const uint32_t* desc;   // [nnz padded to even]  state row of every CSR slot
+  const double* coef;     // [nnz padded to even]  constant of every CSR slot
+  // fill kernel: per chunk of kFillChunkSlots slots the distinct state rows it references, and per slot
+  // the position of its row in that list
+  int fill_chunks, fill_max_rows;
+  const uint32_t* fill_rows;      // concatenated per-chunk lists of distinct state rows
+  const int32_t* fill_row_off;    // [fill_chunks + 1]
+  const uint16_t* fill_local;     // [nnz padded to even]
 };
 
 }  // namespace twb

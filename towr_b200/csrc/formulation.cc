@@ -173,7 +173,7 @@ std::vector<double> BasePolyDurations(double T, double dt) {  // parameters.cc:8
   return v;
 }
 
-struct Emit { int row, col; uint32_t a; double c0; bool direct; };
+struct Emit { int row, col; uint32_t a; double c0; };
 
 // sign/component of Cross(v)[i][d] (single_rigid_body_dynamics.cc:46-57): value = sign * v[comp]
 void CrossEntry(int i, int d, int* comp, double* sign) {
@@ -287,9 +287,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   const uint32_t S_ONE = 0;
 
   std::vector<Emit> em;
-  auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, c, false}); };
-  // entries a terrain/force unit writes straight into the CSR array (no descriptor)
-  auto emit_direct = [&](int row, int col) { em.push_back({row, col, 0u, 0.0, true}); };
+  auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, c}); };
 
   auto add_eval = [&](const SplineSample& s, uint32_t scratch, int kind) {
     EvalItem it{}; it.sample = (int32_t)tb.samples.size(); it.scratch = (int16_t)scratch; it.kind = (int16_t)kind;
@@ -400,11 +398,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int row = r0 + nd - 1;
             if (mo.ConstNode(nd)) bound(row, 0.0, 0.0); else bound(row, 0.0, 1e20);
             TerrainUnit u{}; for (int d = 0; d < 3; ++d) u.xi[d] = XIndex(mo, nd, kPos, d, zero_slot);
-            u.g_row = row; u.jac_slot = -1;
+            u.g_row = row; u.s_idx = S_top; S_top += 2;
             tb.terr.push_back(u);
-            if (!(mo.Var(nd, kPos, X) < mo.Var(nd, kPos, Y) && mo.Var(nd, kPos, Y) < mo.Var(nd, kPos, Z)))
-              return fail(TWB_ERR_UNSUPPORTED, "unexpected ee-motion variable order");
-            for (int d = 0; d < 3; ++d) emit_direct(row, mo.offset + mo.Var(nd, kPos, d));
+            emit1(row, mo.offset + mo.Var(nd, kPos, X), u.s_idx + 0, 1.0);
+            emit1(row, mo.offset + mo.Var(nd, kPos, Y), u.s_idx + 1, 1.0);
+            emit1(row, mo.offset + mo.Var(nd, kPos, Z), S_ONE, 1.0);
           }
         }
         break;
@@ -421,16 +419,13 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int mnode = 0; for (int i = 0; i < (int)mo.poly.size(); ++i) if (mo.poly[i].phase == phase) { mnode = i; break; }
             ForceUnit u{};
             for (int d = 0; d < 3; ++d) { u.xf[d] = XIndex(fo, nd, kPos, d, zero_slot); u.xp[d] = XIndex(mo, mnode, kPos, d, zero_slot); }
-            u.g_row = row; u.jac_slot = -1;
+            u.g_row = row; u.s_idx = S_top; S_top += 25;
             tb.force.push_back(u);
-            if (!(mo.offset < fo.offset && mo.Var(mnode, kPos, X) < mo.Var(mnode, kPos, Y) &&
-                  fo.Var(nd, kPos, X) < fo.Var(nd, kPos, Y) && fo.Var(nd, kPos, Y) < fo.Var(nd, kPos, Z)))
-              return fail(TWB_ERR_UNSUPPORTED, "unexpected force/motion variable order");
             bound(row + 0, 0.0, sp.force_limit_in_normal_direction);
             bound(row + 1, -kInf, 0.0); bound(row + 2, 0.0, +kInf); bound(row + 3, -kInf, 0.0); bound(row + 4, 0.0, +kInf);
             for (int r = 0; r < 5; ++r) {
-              for (int d = 0; d < 2; ++d) emit_direct(row + r, mo.offset + mo.Var(mnode, kPos, d));
-              for (int d = 0; d < 3; ++d) emit_direct(row + r, fo.offset + fo.Var(nd, kPos, d));
+              for (int d = 0; d < 2; ++d) emit1(row + r, mo.offset + mo.Var(mnode, kPos, d), u.s_idx + r * 5 + d, 1.0);
+              for (int d = 0; d < 3; ++d) emit1(row + r, fo.offset + fo.Var(nd, kPos, d), u.s_idx + r * 5 + 2 + d, 1.0);
             }
             row += 5;
           }
@@ -496,8 +491,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
       default: return fail(TWB_ERR_INVALID, "constraint not defined!");
     }
   }
+  if (S_top > 32767) return fail(TWB_ERR_UNSUPPORTED, "state vector too large");
+  pl.S_g0 = S_top; S_top += m;             // constraint values, transposed out at the end
+  pl.S_grad0 = S_top;                      // cost-gradient rows (only if cost terms exist)
+  if (sp.n_costs > 0) S_top += n;
   pl.S_size = S_top;
-  if (S_top + 2 > 32767) return fail(TWB_ERR_UNSUPPORTED, "state vector too large for 16-bit descriptors");
 
   // ---- CSR assembly: row-major, ascending column (what setFromTriplets yields)
   std::stable_sort(em.begin(), em.end(), [](const Emit& a, const Emit& b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
@@ -506,22 +504,27 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   nnz = (int)em.size();
   row_ptr.assign(m + 1, 0); col_idx.resize(nnz);
   tb.desc.assign((nnz + 1) & ~1, 0u); tb.coef.assign((nnz + 1) & ~1, 0.0);
-  pl.n_seg = 0;
   for (int s = 0; s < nnz; ++s) {
-    if (!em[s].direct) {  // maximal runs of descriptor-filled slots
-      if (pl.n_seg > 0 && pl.seg_end[pl.n_seg - 1] == s) pl.seg_end[pl.n_seg - 1] = s + 1;
-      else {
-        if (pl.n_seg == kMaxSegments) return fail(TWB_ERR_UNSUPPORTED, "too many Jacobian segments");
-        pl.seg_start[pl.n_seg] = s; pl.seg_end[pl.n_seg] = s + 1; ++pl.n_seg;
-      }
-    }
     row_ptr[em[s].row + 1]++; col_idx[s] = em[s].col;
     tb.desc[s] = em[s].a;
     tb.coef[s] = em[s].c0;
   }
   for (int r = 0; r < m; ++r) row_ptr[r + 1] += row_ptr[r];
-  for (auto& u : tb.terr) { u.jac_slot = row_ptr[u.g_row]; if (row_ptr[u.g_row + 1] - u.jac_slot != 3) return fail(TWB_ERR_UNSUPPORTED, "terrain row layout"); }
-  for (auto& u : tb.force) { u.jac_slot = row_ptr[u.g_row]; if (row_ptr[u.g_row + 5] - u.jac_slot != 25) return fail(TWB_ERR_UNSUPPORTED, "force row layout"); }
+  // fill-kernel tables: distinct state rows per chunk of slots (each row is staged once per chunk)
+  tb.fill_local.assign((nnz + 1) & ~1, 0);
+  pl.fill_chunks = (nnz + kFillChunkSlots - 1) / kFillChunkSlots; pl.fill_max_rows = 1;
+  tb.fill_row_off.assign(1, 0);
+  for (int c = 0; c < pl.fill_chunks; ++c) {
+    std::map<uint32_t, int> local;
+    const int off = (int)tb.fill_rows.size();
+    for (int s = c * kFillChunkSlots; s < std::min(nnz, (c + 1) * kFillChunkSlots); ++s) {
+      auto it = local.find(tb.desc[s]);
+      if (it == local.end()) { it = local.emplace(tb.desc[s], (int)tb.fill_rows.size() - off).first; tb.fill_rows.push_back(tb.desc[s]); }
+      tb.fill_local[s] = (uint16_t)it->second;
+    }
+    tb.fill_row_off.push_back((int)tb.fill_rows.size());
+    pl.fill_max_rows = std::max(pl.fill_max_rows, (int)tb.fill_rows.size() - off);
+  }
 
   // ---- costs (nlp_formulation.cc:333-376, node_cost.cc:53-76)
   has_cost = false;

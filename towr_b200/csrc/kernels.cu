@@ -1,28 +1,28 @@
 // kernels.cu — sm_100a kernels of the batched NLP evaluation (fp64).
 //
-// One launch evaluates, for every instance of a batch, all constraint values
-// g(x) and all CSR Jacobian values (the arrays ifopt::Problem::
-// EvaluateConstraints / EvalNonzerosOfJacobian hand to IPOPT), plus the
-// NodeCost value and gradient when cost terms exist.
+// Everything is a data-parallel map with LANE = PROBLEM INSTANCE.  All per-iterate
+// intermediates live in one state matrix, stored instance-tiled: ST[tile][S_size][32] (tile = 32
+// consecutive instances, row = state slot, lane = instance), so every global access of every kernel
+// is a 256-byte row segment and all rows of a tile sit in one compact region (DRAM page / L2 locality):
 //
-// A CTA owns G consecutive instances and works in two phases:
-//   phase 1 ("units"): one thread per (instance, unit).  A unit is one time
-//       sample of the dynamic constraint, one time sample of the range-of-
-//       motion constraints (all feet), or one node of the terrain / force /
-//       swing / spline-acc constraints.  The thread evaluates the Hermite
-//       splines it needs from x (staged in shared memory by a TMA bulk copy),
-//       does the nonlinear math (Euler -> R, omega, omega_dot, SRBD, terrain
-//       basis), writes its constraint rows to g and the handful of scalars the
-//       Jacobian of its rows is linear in into the per-instance state vector S
-//       (shared memory).
-//   phase 2 ("fill"): one thread per CSR slot.  value = S[a]*coef (3 terms
-//       for the base-angular block of the dynamic constraint), with (a, coef)
-//       read from the structure-class descriptor table; stores are fully
-//       coalesced 8-byte streams into jac[b][0..nnz).
+//   TransposeIn   x[B][n]            -> XT[tile][n+1][32]     (row n stays 0: "not optimised" node values)
+//   SplineKernel  XT                 -> ST rows (spline values at every constraint sample)
+//   DynKernel     ST rows            -> ST rows (g of the dynamic constraint + its Jacobian state)
+//   RomKernel     ST rows            -> ST rows (g of the range-of-motion constraints + Jacobian state)
+//   NodeKernel    XT                 -> ST rows (terrain / force / swing / spline-acc rows, cost)
+//   FillJac       ST, desc, coef     -> jac[B][nnz]           jac[b][s] = ST[desc[s]][b] * coef[s]
+//   TransposeOut  ST rows 1..m       -> g[B][m]
 //
-// Reference math restated per device function (file:line cited there).
+// The first five are ALU/latency-type kernels (fp64 FMA pipe, sincos); FillJac carries ~95% of the
+// HBM traffic and is a pure stream.  capi.cc pipelines sub-batches over two streams so that the
+// state kernels of sub-batch i+1 run under the HBM-bound fill of sub-batch i.
+//
+// Reference math restated per device function (file:line cited there).  This translation unit is
+// compiled with -fmad=false: plain * and + round like the reference's scalar C++; fused
+// multiply-adds are written explicitly (fma) where the algebra is re-associated anyway.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 
@@ -36,25 +36,28 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// ---- TMA 1-D bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier) ----------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+// output stores: TWB_STORE_MODE 0 = default write-back, 1 = streaming (evict-first), 2 = write-through
+#ifndef TWB_STORE_MODE
+#define TWB_STORE_MODE 1
+#endif
+template <class T>
+__device__ __forceinline__ void StoreOut(T* p, T v) {
+#if TWB_STORE_MODE == 1
+  __stcs(p, v);
+#elif TWB_STORE_MODE == 2
+  __stwt(p, v);
+#else
+  *p = v;
+#endif
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
+
+// column `b` of a row-major [rows][ld] matrix: element r lives at p[r * ld]
+struct Col {
+  double* p;
+  size_t ld;
+  __device__ __forceinline__ double& operator[](int r) const { return p[(size_t)r * ld]; }
+  __device__ __forceinline__ Col at(int r) const { return Col{p + (size_t)r * ld, ld}; }
+};
 
 // ---- cubic Hermite evaluation ------------------------------------------------
 // a / b, correctly rounded, from y = RN(1/b) (Markstein): two residual corrections with exact
@@ -85,8 +88,7 @@ __device__ __forceinline__ SampleRegs LoadSample(const SplineSample* __restrict_
   for (int i = 0; i < 6; ++i) { r.xi[2 * i] = (int)(v[i] & 0xFFFFu); r.xi[2 * i + 1] = (int)(v[i] >> 16); }
   return r;
 }
-__device__ __forceinline__ void EvalSplineToScratch(const SampleRegs& s, int kind, const double* __restrict__ xs,
-                                                    double* __restrict__ out) {
+__device__ __forceinline__ void EvalSplineToState(const SampleRegs& s, int kind, const Col xs, const Col out) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[s.xi[d]], v0 = xs[s.xi[3 + d]], p1 = xs[s.xi[6 + d]], v1 = xs[s.xi[9 + d]];
@@ -169,9 +171,9 @@ __device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3]
 //   EulerConverter::GetDerivOfAng{Vel,Acc}WrtEulerNodes (euler_converter.cc:85-131),
 //   GetDerivMwrtNodes (:168-198), GetDerivMdotwrtNodes (:270-304);
 //   sum of forces, per-foot force and lever arm for the other blocks (:103-121, :167-192).
-__device__ void DynamicUnit(const Plan& P, int k, double* __restrict__ S, double* __restrict__ g) {
+__device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col S) {
   const int n_ee = P.n_ee;
-  double* Sk = S + P.S_dyn0 + k * P.S_dyn_stride;
+  const Col Sk = S.at(P.S_dyn0 + k * P.S_dyn_stride);
   // phase-0 scratch: c, c_ddot, theta, theta_dot, theta_ddot, p_e.., f_e..
   double c[3], cdd[3], th[3], thd[3], thdd[3], pe[kMaxEE][3], fe[kMaxEE][3];
 #pragma unroll
@@ -223,9 +225,9 @@ __device__ void DynamicUnit(const Plan& P, int k, double* __restrict__ S, double
 
   double Iw_om[3], Iw_omd[3];
   MulVec(Iw, om, Iw_om); MulVec(Iw, omd, Iw_omd);
-  if (g) {
+  {
     const double wx[3] = {om[1] * Iw_om[2] - om[2] * Iw_om[1], om[2] * Iw_om[0] - om[0] * Iw_om[2], om[0] * Iw_om[1] - om[1] * Iw_om[0]};
-    double* gk = g + P.dyn_row0 + 6 * k;
+    const Col gk = S.at(P.S_g0 + P.dyn_row0 + 6 * k);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       gk[d] = Iw_omd[d] + wx[d] - tau[d];
@@ -302,9 +304,9 @@ __device__ void DynamicUnit(const Plan& P, int k, double* __restrict__ S, double
 // ---- RangeOfMotionConstraint sample (all feet) --------------------------------
 // range_of_motion_constraint.cc:58-109: g = R^T (p_ee - c); Jacobian state R^T and
 // D_e = d(R^T r_e)/d(theta) (DerivOfRotVecMult(t, r_W, true)).
-__device__ void RomUnit(const Plan& P, int k, double* __restrict__ S, double* __restrict__ g) {
+__device__ __forceinline__ void RomUnit(const Plan& P, int k, const Col S) {
   const int n_ee = P.n_ee;
-  double* Sk = S + P.S_rom0 + k * P.S_rom_stride;
+  const Col Sk = S.at(P.S_rom0 + k * P.S_rom_stride);
   double c[3], th[3], pes[kMaxEE][3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) { c[d] = Sk[d]; th[d] = Sk[3 + d]; }
@@ -326,8 +328,8 @@ __device__ void RomUnit(const Plan& P, int k, double* __restrict__ S, double* __
     if (e >= n_ee) break;
     const double* pe = pes[e];
     const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
-    if (g) {
-      double* ge = g + P.rom_row0[e] + 3 * k;
+    {
+      const Col ge = S.at(P.S_g0 + P.rom_row0[e] + 3 * k);
 #pragma unroll
       for (int i = 0; i < 3; ++i) ge[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
     }
@@ -378,12 +380,11 @@ __device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) 
 }
 
 // TerrainConstraint, terrain_constraint.cc:59-108
-__device__ __forceinline__ void TerrainUnitEval(const TerrainUnit& u, int terrain, const double* __restrict__ xs,
-                                                double* __restrict__ jac, double* __restrict__ g) {
+__device__ __forceinline__ void TerrainUnitEval(const Plan& P, const TerrainUnit& u, int terrain, const Col xs, const Col S) {
   const double px = xs[u.xi[0]], py = xs[u.xi[1]], pz = xs[u.xi[2]];
   const TerrainPoint tp = EvalTerrain(terrain, px, py);
-  if (g) g[u.g_row] = pz - tp.h;
-  if (jac) { double* J = jac + u.jac_slot; __stcs(J + 0, -tp.hx); __stcs(J + 1, -tp.hy); __stcs(J + 2, 1.0); }
+  S[P.S_g0 + u.g_row] = pz - tp.h;
+  S[u.s_idx + 0] = -tp.hx; S[u.s_idx + 1] = -tp.hy;
 }
 
 // normalised vector and HeightMap::GetDerivativeOfNormalizedBasisWrt (height_map.cc:62-91,140-146):
@@ -403,8 +404,8 @@ __device__ __forceinline__ void NormalizedDeriv(const double v[3], const double 
 __device__ __forceinline__ double Dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 // ForceConstraint, force_constraint.cc:64-171
-__device__ void ForceUnitEval(const ForceUnit& u, int terrain, double mu, const double* __restrict__ xs,
-                              double* __restrict__ jac, double* __restrict__ g) {
+__device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u, int terrain, const Col xs, const Col S) {
+  const double mu = P.mu;
   const double px = xs[u.xp[0]], py = xs[u.xp[1]];
   const double f[3] = {xs[u.xf[0]], xs[u.xf[1]], xs[u.xf[2]]};
   const TerrainPoint tp = EvalTerrain(terrain, px, py);
@@ -418,12 +419,11 @@ __device__ void ForceUnitEval(const ForceUnit& u, int terrain, double mu, const 
     a1[d] = t1[d] - mu * n[d]; b1[d] = t1[d] + mu * n[d];
     a2[d] = t2[d] - mu * n[d]; b2[d] = t2[d] + mu * n[d];
   }
-  if (g) {
-    double* gr = g + u.g_row;
+  {
+    const Col gr = S.at(P.S_g0 + u.g_row);
     gr[0] = Dot3(f, n); gr[1] = Dot3(f, a1); gr[2] = Dot3(f, b1); gr[3] = Dot3(f, a2); gr[4] = Dot3(f, b2);
   }
-  if (!jac) return;
-  double Su[25];
+  const Col Su = S.at(u.s_idx);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     Su[0 * 5 + 2 + d] = n[d]; Su[1 * 5 + 2 + d] = a1[d]; Su[2 * 5 + 2 + d] = b1[d];
@@ -448,14 +448,11 @@ __device__ void ForceUnitEval(const ForceUnit& u, int terrain, double mu, const 
     Su[0 * 5 + dim] = Dot3(f, dn); Su[1 * 5 + dim] = Dot3(f, m1); Su[2 * 5 + dim] = Dot3(f, p1);
     Su[3 * 5 + dim] = Dot3(f, m2); Su[4 * 5 + dim] = Dot3(f, p2);
   }
-  double* J = jac + u.jac_slot;
-#pragma unroll
-  for (int i = 0; i < 25; ++i) __stcs(J + i, Su[i]);
 }
 
 // SwingConstraint::GetValues, swing_constraint.cc:57-83 (Jacobian is constant)
-__device__ __forceinline__ void SwingUnitEval(const SwingUnit& u, const double* __restrict__ xs, double* __restrict__ g) {
-  if (!g) return;
+__device__ __forceinline__ void SwingUnitEval(const Plan& P, const SwingUnit& u, const Col xs, const Col S) {
+  const Col g = S.at(P.S_g0);
   const double t_swing_avg = 0.3;
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
@@ -469,8 +466,8 @@ __device__ __forceinline__ void SwingUnitEval(const SwingUnit& u, const double* 
 }
 
 // SplineAccConstraint::GetValues, spline_acc_constraint.cc:49-65 (Jacobian constant for fixed durations)
-__device__ __forceinline__ void AccUnitEval(const AccUnit& u, const double* __restrict__ xs, double* __restrict__ g) {
-  if (!g) return;
+__device__ __forceinline__ void AccUnitEval(const Plan& P, const AccUnit& u, const Col xs, const Col S) {
+  const Col g = S.at(P.S_g0);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[u.x0 + d], v0 = xs[u.x0 + 3 + d], p1 = xs[u.x0 + 6 + d], v1 = xs[u.x0 + 9 + d];
@@ -484,225 +481,238 @@ __device__ __forceinline__ void AccUnitEval(const AccUnit& u, const double* __re
   }
 }
 
-// ---- the kernel ---------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(kThreads, 2)
-EvalKernel(const Plan P, const double* __restrict__ x, double* __restrict__ g, double* __restrict__ jac,
-           double* __restrict__ cost, double* __restrict__ grad, int* __restrict__ status,
-           const int* __restrict__ terrain_ids, int default_terrain, int B, unsigned flags) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t mbar;
-  const int tid = threadIdx.x;
-  const int n = P.n, m = P.m, nnz = P.nnz;
-  const int xs_stride = (n + 2) & ~1;         // even -> every row stays 16-byte aligned
-  const int S_stride = (P.S_size + 1) & ~1;
-  double* xs_all = reinterpret_cast<double*>(smem_raw);
-  double* S_all = xs_all + G * xs_stride;
-  const int b0 = blockIdx.x * G;
-  const int nb = min(G, B - b0);
+// ---- kernels ---------------------------------------------------------------------
+// instance b of a tiled matrix with `rows` rows: element r lives at base[((b/32)*rows + r)*32 + b%32]
+__device__ __forceinline__ Col TiledCol(double* base, int b, int rows) {
+  return Col{base + ((size_t)(b >> 5) * rows) * 32 + (b & 31), 32};
+}
 
-  // ---- stage x: one TMA bulk copy per instance when rows are 16-byte aligned
-  const bool tma_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  if (tma_ok) {
-    if (tid == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(&mbar, (uint32_t)(nb * n * sizeof(double)));
-      for (int gi = 0; gi < nb; ++gi)
-        bulk_g2s(xs_all + gi * xs_stride, x + (size_t)(b0 + gi) * n, (uint32_t)(n * sizeof(double)), &mbar);
+// x[b][i] -> XT[b/32][i][b%32]: 32x32 tiles through shared memory, coalesced on both sides
+__global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x, double* __restrict__ XT, int n, int nb) {
+  __shared__ double tile[32][33];
+  const int i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int b = b0 + r, i = i0 + threadIdx.x;
+    if (b < nb && i < n) tile[r][threadIdx.x] = x[(size_t)b * n + i];
+  }
+  __syncthreads();
+  double* dst = XT + ((size_t)blockIdx.y * (n + 1)) * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, b = b0 + threadIdx.x;
+    if (b < nb && i < n) dst[(size_t)i * 32 + threadIdx.x] = tile[threadIdx.x][r];
+  }
+}
+
+// ST[b/32][row0 + r][b%32] -> out[b][r], r < rows  (constraint values g, cost gradient)
+__global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ ST, double* __restrict__ out, int S_size,
+                                                    int row0, int rows, int nb) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const double* src = ST + ((size_t)blockIdx.y * S_size + row0) * 32;
+  for (int q = threadIdx.y; q < 32; q += 8) {
+    const int r = r0 + q, b = b0 + threadIdx.x;
+    if (r < rows && b < nb) tile[q][threadIdx.x] = src[(size_t)r * 32 + threadIdx.x];
+  }
+  __syncthreads();
+  for (int q = threadIdx.y; q < 32; q += 8) {
+    const int b = b0 + q, r = r0 + threadIdx.x;
+    if (r < rows && b < nb) StoreOut(out + (size_t)b * rows + r, tile[threadIdx.x][q]);
+  }
+}
+
+// one thread per (eval item = blockIdx.y, instance): all lanes of a warp share the sample table entry
+__global__ void __launch_bounds__(128) SplineKernel(const Plan P, double* __restrict__ XT, double* __restrict__ ST,
+                                                    int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.eval_items) + blockIdx.y);
+  const int sample = (int)raw.x, row = (int)(raw.y & 0xFFFFu), kind = (int)(raw.y >> 16);
+  const SampleRegs sr = LoadSample(P.samples + sample);
+  EvalSplineToState(sr, kind, TiledCol(XT, b, P.n + 1), TiledCol(ST, b, P.S_size).at(row));
+}
+
+// one thread per (dynamic sample = blockIdx.y, instance)
+__global__ void __launch_bounds__(128, 2) DynKernel(const Plan P, double* __restrict__ ST, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  DynamicUnit(P, blockIdx.y, TiledCol(ST, b, P.S_size));
+}
+
+// one thread per (range-of-motion sample = blockIdx.y, instance)
+__global__ void __launch_bounds__(128, 2) RomKernel(const Plan P, double* __restrict__ ST, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  RomUnit(P, blockIdx.y, TiledCol(ST, b, P.S_size));
+}
+
+// one thread per (node unit = blockIdx.y, instance): force | terrain | swing | spline-acc | cost
+__global__ void __launch_bounds__(128) NodeKernel(const Plan P, double* __restrict__ XT, double* __restrict__ ST,
+                                                  const int* __restrict__ terrain_ids, int default_terrain,
+                                                  double* __restrict__ cost, int nb, int want_cost) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const Col xs = TiledCol(XT, b, P.n + 1), S = TiledCol(ST, b, P.S_size);
+  int u = blockIdx.y;
+  if (u < P.n_force) {
+    ForceUnitEval(P, P.force[u], terrain_ids ? terrain_ids[b] : default_terrain, xs, S);
+    return;
+  }
+  u -= P.n_force;
+  if (u < P.n_terr) {
+    TerrainUnitEval(P, P.terr[u], terrain_ids ? terrain_ids[b] : default_terrain, xs, S);
+    return;
+  }
+  u -= P.n_terr;
+  if (u < P.n_swing) { SwingUnitEval(P, P.swing[u], xs, S); return; }
+  u -= P.n_swing;
+  if (u < P.n_acc) { AccUnitEval(P, P.acc[u], xs, S); return; }
+  if (want_cost) {
+    // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
+    // dense gradient row (node_cost.cc:65-76), both in the reference's order; gradient rows live in ST.
+    const Col gr = S.at(P.S_grad0);
+    for (int i = 0; i < P.n; ++i) gr[i] = 0.0;
+    double total_cost = 0.0, term = 0.0;
+    for (int i = 0; i < P.n_cost; ++i) {
+      const CostEntry ce = P.cost[i];
+      if (ce.pad && i > 0) { total_cost += term; term = 0.0; }
+      const double val = xs[ce.xi];
+      term += ce.weight * (val * val);
+      if (ce.grad_col >= 0) gr[ce.grad_col] += ce.weight * 2.0 * val;
+    }
+    total_cost += term;
+    if (cost) cost[b] = total_cost;
+  }
+}
+
+// jac[b][s] = ST[tile][desc[s]][b] * coef[s]   — gather state rows, transpose, scale, stream out.
+// A CTA owns 32 instances (one tile of ST) and one chunk of kFillChunkSlots CSR slots.
+//  stage: the chunk's DISTINCT state rows (host-built list, ~4x fewer than slots) are copied with
+//         cp.async, 256 contiguous bytes per row (lane = instance), into a padded shared-memory
+//         array — dozens of row copies in flight per thread, no registers held;
+//  store: lane = slot pair: it reads its two rows for one instance (conflict-free: row stride 33),
+//         scales by its two constants and writes 16 bytes, so each store instruction covers 512
+//         contiguous bytes of one instance's CSR value array.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) FillJac(const Plan P, const double* __restrict__ ST, double* __restrict__ jac,
+                                                    int* __restrict__ status, int nb) {
+  extern __shared__ __align__(16) double fill_rows_smem[];
+  double (*t)[33] = reinterpret_cast<double (*)[33]>(fill_rows_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nnz = P.nnz;
+  const int chunk = blockIdx.x;                                     // chunk fastest: the CTAs of one instance
+  const int b0 = blockIdx.y * 32;                                   // tile run together (L2 locality of its rows)
+  const double* Sb = ST + ((size_t)blockIdx.y * P.S_size) * 32 + lane;
+  const int r_begin = __ldg(P.fill_row_off + chunk), n_rows = __ldg(P.fill_row_off + chunk + 1) - r_begin;
+  for (int r = warp; r < n_rows; r += kThreads / 32)
+    cp_async8(&t[r][lane], Sb + (size_t)__ldg(P.fill_rows + r_begin + r) * 32);
+  const int s_begin = chunk * kFillChunkSlots, s_end = min(nnz, s_begin + kFillChunkSlots);
+  cp_async_wait_all();
+  __syncthreads();
+  if (status) {   // every output is (staged value) x (finite constant): check the staged rows once
+    double chk = 0.0;
+    for (int r = warp; r < n_rows; r += kThreads / 32) chk = fma(t[r][lane], 0.0, chk);
+    if (chk != chk && b0 + lane < nb) atomicOr(status + b0 + lane, 1);   // NaN or Inf in instance b0 + lane
+  }
+  const int n_inst = min(32, nb - b0);
+  if (kVec) {
+    for (int s = s_begin + 2 * threadIdx.x; s < s_end; s += 2 * kThreads) {
+      const uint32_t loc = __ldg(reinterpret_cast<const uint32_t*>(P.fill_local + s));   // two 16-bit row positions
+      const double2 cf = __ldg(reinterpret_cast<const double2*>(P.coef + s));
+      const double* r0 = t[loc & 0xFFFFu];
+      const double* r1 = t[loc >> 16];
+      double2* out = reinterpret_cast<double2*>(jac + (size_t)b0 * nnz + s);
+#pragma unroll 8
+      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * (nnz >> 1), make_double2(r0[j] * cf.x, r1[j] * cf.y));
     }
   } else {
-    for (int gi = 0; gi < nb; ++gi)
-      for (int i = tid; i < n; i += kThreads) xs_all[gi * xs_stride + i] = x[(size_t)(b0 + gi) * n + i];
-  }
-  if (tid < nb) {
-    xs_all[tid * xs_stride + n] = 0.0; S_all[tid * S_stride] = 1.0;
-    if (status) status[b0 + tid] = 0;
-  }
-  if (tma_ok) { while (!mbar_try_wait(&mbar, 0)) {} }
-  __syncthreads();
-
-  const bool want_g = (flags & 1u) != 0, want_jac = (flags & 2u) != 0, want_cost = (flags & 4u) != 0 && P.n_cost > 0;
-
-  // ---- phase 0: every (instance, sample, spline) Hermite evaluation, one per thread
-  {
-    const int n_items = P.n_eval_items;
-    for (int j = tid; j < n_items; j += kThreads) {
-      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.eval_items) + j);
-      const int sample = (int)raw.x, scratch = (int)(raw.y & 0xFFFFu), kind = (int)(raw.y >> 16);
-      const SampleRegs sr = LoadSample(P.samples + sample);
-#pragma unroll
-      for (int gi = 0; gi < G; ++gi)
-        if (gi < nb) EvalSplineToScratch(sr, kind, xs_all + gi * xs_stride, S_all + gi * S_stride + scratch);
+    for (int s = s_begin + threadIdx.x; s < s_end; s += kThreads) {
+      const double cf = __ldg(P.coef + s);
+      const double* r0 = t[__ldg(P.fill_local + s)];
+      double* out = jac + (size_t)b0 * nnz + s;
+      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * nnz, r0[j] * cf);
     }
   }
-  __syncthreads();
+}
 
-  // ---- phase 1: units.  Item ranges are padded to warp granularity so a warp runs one unit type.
-  auto pad32 = [](int v) { return (v + 31) & ~31; };
-  const int c_dyn = nb * P.n_dyn, c_rom = nb * P.n_rom, c_force = nb * P.n_force, c_terr = nb * P.n_terr;
-  const int c_swing = nb * P.n_swing, c_acc = nb * P.n_acc, c_cost = want_cost ? nb : 0;
-  const int o_rom = pad32(c_dyn), o_force = o_rom + pad32(c_rom), o_terr = o_force + pad32(c_force);
-  const int o_swing = o_terr + pad32(c_terr), o_acc = o_swing + pad32(c_swing), o_cost = o_acc + pad32(c_acc);
-  const int total = o_cost + pad32(c_cost);
-  for (int item = tid; item < total; item += kThreads) {
-    if (item < o_rom) {
-      if (item < c_dyn) {
-        const int gi = item / P.n_dyn, k = item - gi * P.n_dyn;
-        DynamicUnit(P, k, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
-      }
-    } else if (item < o_force) {
-      const int it = item - o_rom;
-      if (it < c_rom) {
-        const int gi = it / P.n_rom, k = it - gi * P.n_rom;
-        RomUnit(P, k, S_all + gi * S_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
-      }
-    } else if (item < o_terr) {
-      const int it = item - o_force;
-      if (it < c_force) {
-        const int gi = it / P.n_force, u = it - gi * P.n_force;
-        const int terrain = terrain_ids ? terrain_ids[b0 + gi] : default_terrain;
-        ForceUnitEval(P.force[u], terrain, P.mu, xs_all + gi * xs_stride, want_jac ? jac + (size_t)(b0 + gi) * nnz : nullptr,
-                      want_g ? g + (size_t)(b0 + gi) * m : nullptr);
-      }
-    } else if (item < o_swing) {
-      const int it = item - o_terr;
-      if (it < c_terr) {
-        const int gi = it / P.n_terr, u = it - gi * P.n_terr;
-        const int terrain = terrain_ids ? terrain_ids[b0 + gi] : default_terrain;
-        TerrainUnitEval(P.terr[u], terrain, xs_all + gi * xs_stride, want_jac ? jac + (size_t)(b0 + gi) * nnz : nullptr,
-                        want_g ? g + (size_t)(b0 + gi) * m : nullptr);
-      }
-    } else if (item < o_acc) {
-      const int it = item - o_swing;
-      if (it < c_swing) {
-        const int gi = it / P.n_swing, u = it - gi * P.n_swing;
-        SwingUnitEval(P.swing[u], xs_all + gi * xs_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
-      }
-    } else if (item < o_cost) {
-      const int it = item - o_acc;
-      if (it < c_acc) {
-        const int gi = it / P.n_acc, u = it - gi * P.n_acc;
-        AccUnitEval(P.acc[u], xs_all + gi * xs_stride, want_g ? g + (size_t)(b0 + gi) * m : nullptr);
-      }
-    } else {
-      const int gi = item - o_cost;
-      if (gi < c_cost) {
-        // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs)
-        // and the dense gradient row (node_cost.cc:65-76), in the reference's order.
-        const double* xr = xs_all + gi * xs_stride;
-        double* gr = grad ? grad + (size_t)(b0 + gi) * n : nullptr;
-        if (gr) for (int i = 0; i < n; ++i) gr[i] = 0.0;
-        double total_cost = 0.0, term = 0.0;
-        for (int i = 0; i < P.n_cost; ++i) {
-          const CostEntry ce = P.cost[i];
-          if (ce.pad && i > 0) { total_cost += term; term = 0.0; }
-          const double val = xr[ce.xi];
-          term += ce.weight * (val * val);
-          if (gr && ce.grad_col >= 0) gr[ce.grad_col] += ce.weight * 2.0 * val;
-        }
-        total_cost += term;
-        if (cost) cost[b0 + gi] = total_cost;
-      }
-    }
-  }
-  __syncthreads();
+__global__ void ClearStatus(int* __restrict__ status, int nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) status[i] = 0;
+}
 
-  // ---- phase 2: fill the descriptor-driven CSR slots
-  if (want_jac) {
-    // non-finite detection on the state vector (every descriptor value is S[a] * finite constant)
-    if (status) {
-#pragma unroll
-      for (int gi = 0; gi < G; ++gi) {
-        if (gi < nb) {
-          const double* Sg = S_all + gi * S_stride;
-          double chk = 0.0;
-          for (int i = tid; i < P.S_size; i += kThreads) chk = fma(Sg[i], 0.0, chk);
-          if (chk != chk) atomicOr(status + b0 + gi, 1);
-        }
-      }
-    }
-    double* outg[G];
-#pragma unroll
-    for (int gi = 0; gi < G; ++gi) outg[gi] = jac + (size_t)(b0 + min(gi, nb - 1)) * nnz;
-    const bool vec_ok = ((nnz & 1) == 0) && ((reinterpret_cast<uintptr_t>(jac) & 15) == 0);
-    for (int sg = 0; sg < P.n_seg; ++sg) {
-      const int s_begin = P.seg_start[sg], s_end = P.seg_end[sg];
-      if (vec_ok) {
-        // aligned interior: two slots (16 bytes) per thread, next descriptors prefetched
-        const int q_begin = (s_begin + 1) >> 1, q_end = s_end >> 1;
-        const uint2* desc2 = reinterpret_cast<const uint2*>(P.desc);
-        const double2* coef2 = reinterpret_cast<const double2*>(P.coef);
-        int q = q_begin + tid;
-        uint2 d = make_uint2(0u, 0u); double2 c = make_double2(0.0, 0.0);
-        if (q < q_end) { d = __ldg(desc2 + q); c = __ldg(coef2 + q); }
-        while (q < q_end) {
-          const int qn = q + kThreads;
-          uint2 dn = make_uint2(0u, 0u); double2 cn = make_double2(0.0, 0.0);
-          if (qn < q_end) { dn = __ldg(desc2 + qn); cn = __ldg(coef2 + qn); }
-#pragma unroll
-          for (int gi = 0; gi < G; ++gi) {
-            if (gi < nb) {
-              const double* Sg = S_all + gi * S_stride;
-              __stcs(reinterpret_cast<double2*>(outg[gi]) + q, make_double2(Sg[d.x] * c.x, Sg[d.y] * c.y));
-            }
-          }
-          q = qn; d = dn; c = cn;
-        }
-        // ragged ends of the segment (at most one slot each)
-        if (tid < 2) {
-          const int s = (tid == 0) ? s_begin : s_end - 1;
-          const bool need = (tid == 0) ? ((s_begin & 1) != 0) : (((s_end & 1) != 0) && (s_end - 1 > s_begin || (s_begin & 1) == 0));
-          if (need) {
-            const uint32_t a = __ldg(P.desc + s); const double cf = __ldg(P.coef + s);
-            for (int gi = 0; gi < nb; ++gi) __stcs(outg[gi] + s, S_all[gi * S_stride + a] * cf);
-          }
-        }
-      } else {
-        for (int s = s_begin + tid; s < s_end; s += kThreads) {
-          const uint32_t a = __ldg(P.desc + s); const double cf = __ldg(P.coef + s);
-          for (int gi = 0; gi < nb; ++gi) __stcs(outg[gi] + s, S_all[gi * S_stride + a] * cf);
-        }
-      }
-    }
-  }
+__global__ void InitOnes(double* __restrict__ ST, int S_size, int n_tiles) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tiles * 32) ST[((size_t)(i >> 5) * S_size) * 32 + (i & 31)] = 1.0;   // state row 0 == 1
 }
 
 }  // namespace
 
-size_t EvalSmemBytes(const Plan& P, int G) {
-  const int xs_stride = (P.n + 2) & ~1, S_stride = (P.S_size + 1) & ~1;
-  return (size_t)G * (xs_stride + S_stride) * sizeof(double);
+// ---- host launchers ------------------------------------------------------------------
+void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // profiling hook (capi.cc, TWB_PROFILE=1)
+#define TWB_MARK(label) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
+// XT / ST point at the first TILE of the sub-batch (sub-batches start at multiples of 32 instances).
+int LaunchInitState(double* ST, int S_size, int n_tiles, cudaStream_t stream) {
+  InitOnes<<<(n_tiles * 32 + 255) / 256, 256, 0, stream>>>(ST, S_size, n_tiles);
+  return (int)cudaGetLastError();
 }
 
-int LaunchEval(const Plan& P, int G, const double* x, double* g, double* jac, double* cost, double* grad,
-               int* status, const int* terrain_ids, int default_terrain, int B, unsigned flags, cudaStream_t stream,
-               int* n_launches) {
-  if (B <= 0) return 0;
-  int launches = 0;
-  const size_t smem = EvalSmemBytes(P, G);
-  const int grid = (B + G - 1) / G;
-  cudaError_t e = cudaSuccess;
-#define TWB_LAUNCH(GG)                                                                                         \
-  do {                                                                                                         \
-    e = cudaFuncSetAttribute(EvalKernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-    if (e == cudaSuccess)                                                                                      \
-      EvalKernel<GG><<<grid, kThreads, smem, stream>>>(P, x, g, jac, cost, grad, status, terrain_ids,          \
-                                                       default_terrain, B, flags);                             \
-  } while (0)
-  switch (G) {
-    case 1: TWB_LAUNCH(1); break;
-    case 2: TWB_LAUNCH(2); break;
-    case 3: TWB_LAUNCH(3); break;
-    case 4: TWB_LAUNCH(4); break;
-    case 6: TWB_LAUNCH(6); break;
-    case 8: TWB_LAUNCH(8); break;
-    default: return (int)cudaErrorInvalidValue;
+int LaunchStateKernels(const Plan& P, const double* x, double* XT, double* ST, const int* terrain_ids,
+                       int default_terrain, double* cost, int* status, int nb, bool want_cost, cudaStream_t stream,
+                       int* launches) {
+  if (nb <= 0) return 0;
+  int count = 0;
+  const int bx = (nb + 127) / 128;
+  TWB_MARK("begin");
+  if (status) { ClearStatus<<<(nb + 255) / 256, 256, 0, stream>>>(status, nb); ++count; TWB_MARK("ClearStatus"); }
+  TransposeIn<<<dim3((P.n + 31) / 32, (nb + 31) / 32), dim3(32, 8), 0, stream>>>(x, XT, P.n, nb); ++count; TWB_MARK("TransposeIn");
+  if (P.n_eval_items > 0) { SplineKernel<<<dim3(bx, P.n_eval_items), 128, 0, stream>>>(P, XT, ST, nb); ++count; TWB_MARK("SplineKernel"); }
+  if (P.n_dyn > 0) { DynKernel<<<dim3(bx, P.n_dyn), 128, 0, stream>>>(P, ST, nb); ++count; TWB_MARK("DynKernel"); }
+  if (P.n_rom > 0) { RomKernel<<<dim3(bx, P.n_rom), 128, 0, stream>>>(P, ST, nb); ++count; TWB_MARK("RomKernel"); }
+  const int n_units = P.n_force + P.n_terr + P.n_swing + P.n_acc + (want_cost ? 1 : 0);
+  if (n_units > 0) {
+    NodeKernel<<<dim3(bx, n_units), 128, 0, stream>>>(P, XT, ST, terrain_ids, default_terrain, cost, nb, want_cost ? 1 : 0);
+    ++count; TWB_MARK("NodeKernel");
   }
-#undef TWB_LAUNCH
-  ++launches;
-  if (n_launches) *n_launches = launches;
-  if (e != cudaSuccess) return (int)e;
+  if (launches) *launches += count;
+  return (int)cudaGetLastError();
+}
+
+int LaunchFillJac(const Plan& P, const double* ST, double* jac, int* status, int nb, int n_sms, cudaStream_t stream,
+                  int* launches) {
+  if (nb <= 0) return 0;
+  (void)n_sms;
+  const bool vec = ((P.nnz & 1) == 0) && ((reinterpret_cast<uintptr_t>(jac) & 15) == 0);
+  const size_t smem = (size_t)P.fill_max_rows * 33 * sizeof(double);
+  const dim3 grid(P.fill_chunks, (nb + 31) / 32);
+  cudaError_t e;
+  TWB_MARK("begin");
+  if (vec) {
+    e = cudaFuncSetAttribute(FillJac<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    FillJac<true><<<grid, kThreads, smem, stream>>>(P, ST, jac, status, nb);
+  } else {
+    e = cudaFuncSetAttribute(FillJac<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    FillJac<false><<<grid, kThreads, smem, stream>>>(P, ST, jac, status, nb);
+  }
+  TWB_MARK("FillJac");
+  if (launches) *launches += 1;
+  return (int)cudaGetLastError();
+}
+
+int LaunchTransposeOut(const Plan& P, const double* ST, int row0, int rows, double* out, int nb, cudaStream_t stream,
+                       int* launches) {
+  if (nb <= 0 || rows <= 0) return 0;
+  TWB_MARK("begin");
+  TransposeOut<<<dim3((rows + 31) / 32, (nb + 31) / 32), dim3(32, 8), 0, stream>>>(ST, out, P.S_size, row0, rows, nb);
+  TWB_MARK("TransposeOut");
+  if (launches) *launches += 1;
   return (int)cudaGetLastError();
 }
 
