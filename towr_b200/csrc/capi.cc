@@ -63,7 +63,7 @@ struct twb_problem {
 
 struct twb_batch {
   const twb_problem* prob = nullptr;
-  int B = 0, device = 0, n_sub = 1, n_sms = 148;
+  int B = 0, device = 0, n_sms = 148;
   size_t ld = 0;                  // leading dimension (instances, padded to 32) of XT and ST
   twb::Plan plan{};
   std::vector<void*> owned;       // device allocations of the tables
@@ -73,7 +73,7 @@ struct twb_batch {
   // staging for the host-pointer variant
   double *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_cost = nullptr, *d_grad = nullptr;
   int* d_status = nullptr;
-  cudaStream_t stream = nullptr, fill_stream = nullptr;
+  cudaStream_t stream = nullptr, aux0 = nullptr, aux1 = nullptr;
   std::vector<cudaEvent_t> ev;    // fork/join events of the two-stream pipeline
   int launches_last = 0;
 };
@@ -166,15 +166,12 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
     return CudaFail(e, "table upload");                                                \
   }
   TWB_UP(samples) TWB_UP(eval_items) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc) TWB_UP(cost)
-  TWB_UP(desc) TWB_UP(coef) TWB_UP(dyn_ang_basis) TWB_UP(fill_rows) TWB_UP(fill_row_off) TWB_UP(fill_local)
+  TWB_UP(desc) TWB_UP(coef) TWB_UP(dyn_ang_basis) TWB_UP(dyn_info) TWB_UP(rom_info) TWB_UP(const_seg)
 #undef TWB_UP
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
-  if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d S_size=%d fill_chunks=%d fill_max_rows=%d n_sub=?\n", b->plan.n, b->plan.m, b->plan.nnz, b->plan.S_size, b->plan.fill_chunks, b->plan.fill_max_rows);
+  if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d S_size=%d\n", b->plan.n, b->plan.m, b->plan.nnz, b->plan.S_size);
   b->ld = ((size_t)batch_size + 31) & ~(size_t)31;
   cudaDeviceGetAttribute(&b->n_sms, cudaDevAttrMultiProcessorCount, device);
-  // sub-batches pipelined over two streams: state kernels of sub-batch i+1 under the fill of sub-batch i
-  b->n_sub = batch_size >= 2048 ? 4 : (batch_size >= 512 ? 2 : 1);
-  if (const char* v = std::getenv("TWB_SUB_BATCHES")) b->n_sub = std::max(1, std::min(64, std::atoi(v)));
   const size_t xt_bytes = (size_t)(b->plan.n + 1) * b->ld * sizeof(double);
   const size_t st_bytes = (size_t)b->plan.S_size * b->ld * sizeof(double);
   if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_XT), xt_bytes)) != cudaSuccess ||
@@ -183,17 +180,13 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
     twb_batch_destroy(b);
     return CudaFail(e, "state allocation");
   }
-  if (twb::LaunchInitState(b->d_ST, b->plan.S_size, (int)(b->ld / 32), nullptr) != 0 ||
-      (e = cudaDeviceSynchronize()) != cudaSuccess) {   // state row 0 is the constant 1
-    twb_batch_destroy(b);
-    return CudaFail(cudaGetLastError(), "state initialisation");
-  }
   if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&b->fill_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      (e = cudaStreamCreateWithFlags(&b->aux0, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&b->aux1, cudaStreamNonBlocking)) != cudaSuccess) {
     twb_batch_destroy(b);
     return CudaFail(e, "cudaStreamCreate");
   }
-  b->ev.assign(b->n_sub + 2, nullptr);
+  b->ev.assign(3, nullptr);
   for (auto& ev : b->ev)
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
       twb_batch_destroy(b);
@@ -209,7 +202,8 @@ void twb_batch_destroy(twb_batch* b) {
   for (void* p : b->owned) cudaFree(p);
   cudaFree(b->d_terrain); cudaFree(b->d_XT); cudaFree(b->d_ST);
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
-  if (b->fill_stream) cudaStreamDestroy(b->fill_stream);
+  if (b->aux0) cudaStreamDestroy(b->aux0);
+  if (b->aux1) cudaStreamDestroy(b->aux1);
   cudaFree(b->d_x); cudaFree(b->d_g); cudaFree(b->d_jac); cudaFree(b->d_cost); cudaFree(b->d_grad); cudaFree(b->d_status);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -232,15 +226,11 @@ int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   if (!b) return 0;
   const twb::Plan& p = b->plan;
   const bool want_cost = b->prob->f.has_cost && (flags & TWB_EVAL_COST);
-  int per = 2 /* status clear + transpose in */ + (p.n_eval_items > 0) + (p.n_dyn > 0) + (p.n_rom > 0) +
-            ((p.n_force + p.n_terr + p.n_swing + p.n_acc + (want_cost ? 1 : 0)) > 0);
-  if (flags & TWB_EVAL_JAC) per += 1;
-  if (flags & TWB_EVAL_G) per += 1;
-  if (want_cost) per += 1;
-  int n_sub = 0;
-  const int chunk = (((b->B + b->n_sub - 1) / b->n_sub) + 31) & ~31;
-  for (int first = 0; first < b->B; first += chunk) ++n_sub;
-  return per * n_sub;
+  int n = 1 + (p.n_eval_items > 0);
+  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += (p.n_dyn > 0) + (p.n_rom > 0);
+  n += ((p.n_force + p.n_terr + p.n_swing + p.n_acc + (want_cost ? 1 : 0)) > 0);
+  if ((flags & TWB_EVAL_JAC) && p.n_const_seg > 0) n += 1;
+  return n;
 }
 
 int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac, double* cost, double* grad,
@@ -250,45 +240,13 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   if ((flags & TWB_EVAL_JAC) && !jac) return Fail(TWB_ERR_INVALID, "jac requested but NULL");
   cudaError_t e = cudaSetDevice(b->device);
   if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
-  // Sub-batches flow through the state kernels on the caller's stream and through the HBM-bound
-  // fill / transpose-out kernels on an internal stream, so the two overlap across sub-batches.
-  cudaStream_t s_main = static_cast<cudaStream_t>(stream);
-  cudaStream_t s_fill = g_prof_on ? s_main : b->fill_stream;
   const twb::Formulation& f = b->prob->f;
-  const twb::Plan& P = b->plan;
-  const bool want_jac = (flags & TWB_EVAL_JAC) != 0, want_g = (flags & TWB_EVAL_G) != 0;
-  const bool want_cost = f.has_cost && (flags & TWB_EVAL_COST) != 0;
-  const int n_sub = b->n_sub;
-  const int per = (((b->B + n_sub - 1) / n_sub) + 31) & ~31;
+  unsigned kflags = flags & (TWB_EVAL_G | TWB_EVAL_JAC);
+  if (f.has_cost && (flags & TWB_EVAL_COST)) kflags |= TWB_EVAL_COST;
   int launches = 0;
-  if ((e = cudaEventRecord(b->ev[n_sub], s_main)) != cudaSuccess) return CudaFail(e, "cudaEventRecord");
-  if ((e = cudaStreamWaitEvent(s_fill, b->ev[n_sub], 0)) != cudaSuccess) return CudaFail(e, "cudaStreamWaitEvent");
-  for (int i = 0, first = 0; first < b->B; ++i, first += per) {
-    const int nb = std::min(per, b->B - first);
-    double* XT = b->d_XT + (size_t)(first / 32) * (P.n + 1) * 32;   // first tile of the sub-batch
-    double* ST = b->d_ST + (size_t)(first / 32) * P.S_size * 32;
-    int rc = twb::LaunchStateKernels(P, x + (size_t)first * f.n, XT, ST, b->d_terrain ? b->d_terrain + first : nullptr,
-                                     f.spec.terrain, (want_cost && cost) ? cost + first : nullptr,
-                                     status ? status + first : nullptr, nb, want_cost, s_main, &launches);
-    if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "state kernel launch");
-    cudaEventRecord(b->ev[i], s_main);
-    cudaStreamWaitEvent(s_fill, b->ev[i], 0);
-    if (want_jac) {
-      rc = twb::LaunchFillJac(P, ST, jac + (size_t)first * f.nnz, status ? status + first : nullptr, nb, b->n_sms, s_fill,
-                              &launches);
-      if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "fill kernel launch");
-    }
-    if (want_g) {
-      rc = twb::LaunchTransposeOut(P, ST, P.S_g0, f.m, g + (size_t)first * f.m, nb, s_fill, &launches);
-      if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "transpose launch");
-    }
-    if (want_cost && grad) {
-      rc = twb::LaunchTransposeOut(P, ST, P.S_grad0, f.n, grad + (size_t)first * f.n, nb, s_fill, &launches);
-      if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "transpose launch");
-    }
-  }
-  cudaEventRecord(b->ev[n_sub + 1], s_fill);   // join: the caller's stream continues after the last fill
-  if ((e = cudaStreamWaitEvent(s_main, b->ev[n_sub + 1], 0)) != cudaSuccess) return CudaFail(e, "cudaStreamWaitEvent");
+  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_ST, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
+                           kflags, static_cast<cudaStream_t>(stream), b->aux0, b->aux1, b->ev.data(), &launches);
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
   b->launches_last = launches;
   return TWB_OK;
 }

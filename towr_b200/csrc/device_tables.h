@@ -9,7 +9,6 @@
 namespace twb {
 
 constexpr int kMaxEE = 4;
-constexpr int kFillChunkSlots = 1024;   // CSR slots one fill CTA owns
 
 // One spline evaluated at one constraint sample when phase durations are
 // fixed: the active polynomial (Spline::GetSegmentID, spline.cc:48-63), its
@@ -38,7 +37,7 @@ struct TerrainUnit {
   int16_t xi[3];      // x index of node position x,y,z
   int16_t pad;
   int32_t g_row;      // constraint row
-  int32_t s_idx;      // state rows of {-dh/dx, -dh/dy}
+  int32_t s0;         // first of the row's 3 CSR slots
 };
 
 // ForceConstraint node (force_constraint.cc:64-171): 5 rows
@@ -47,7 +46,7 @@ struct ForceUnit {
   int16_t xp[3];      // x index of the stance-foot position (phase start node); [2] unused
   int16_t pad[2];
   int32_t g_row;      // first of the 5 rows
-  int32_t s_idx;      // state rows of the 25 Jacobian values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
+  int32_t s0;         // first of the 25 CSR slots of these rows
 };
 
 // SwingConstraint node (swing_constraint.cc:57-83): 4 rows
@@ -66,6 +65,12 @@ struct AccUnit {
   int32_t g_row;        // first of 3 rows
 };
 
+// CSR slot range and first constraint row of one dynamic sample (6 rows) / one RoM sample (3 rows per foot)
+struct DynInfo { int32_t s0, s1, g_row, pad; };
+struct RomInfo { int32_t s0[kMaxEE], s1[kMaxEE], g_row[kMaxEE]; };
+// run of CSR slots whose values do not depend on the iterate (SplineAcc, Swing rows): value = coef
+struct ConstSeg { int32_t s0, s1; };
+
 // NodeCost term (node_cost.cc:53-76) flattened: one entry per node value that
 // enters the cost; var >= 0 when the value is an optimisation variable.
 struct CostEntry {
@@ -80,13 +85,15 @@ struct CostEntry {
 struct Plan {
   int n, m, nnz, n_ee;
   // sizes
-  int n_dyn, n_rom, n_terr, n_force, n_swing, n_acc, n_totdur, n_cost, n_eval_items;
+  int n_dyn, n_rom, n_terr, n_force, n_swing, n_acc, n_totdur, n_cost, n_eval_items, n_const_seg, n_const_runs;
+  int max_dyn_slots, max_rom_slots;   // largest number of CSR slots one dynamic / RoM sample owns
   // g rows
   int dyn_row0;
   int rom_row0[kMaxEE];
   int totdur_row0;
-  // state rows: [0] = 1.0 | dynamic blocks | RoM blocks | force / terrain values | g (m rows) | cost gradient (n rows)
-  int S_size, S_dyn0, S_dyn_stride, S_rom0, S_rom_stride, S_g0, S_grad0;
+  // rows of the spline-value matrix ST: per dynamic sample [c, c_dd, th, th_d, th_dd, p_e.., f_e..],
+  // per RoM sample [c, th, p_e..]
+  int S_size, S_dyn0, S_dyn_stride, S_rom0, S_rom_stride;
   // robot
   double mass, gravity;
   double I_b[9];
@@ -100,14 +107,11 @@ struct Plan {
   const AccUnit* acc;
   const CostEntry* cost;
   const double* dyn_ang_basis;  // [n_dyn][12]: base-ang basis of the active polynomial, {pos, vel, acc} x {p0, v0, p1, v1}
-  const uint32_t* desc;   // [nnz padded to even]  state row of every CSR slot
+  const uint32_t* desc;   // [nnz padded to even]  row of the slot's value in its unit's local state block (0 = the constant 1)
   const double* coef;     // [nnz padded to even]  constant of every CSR slot
-  // fill kernel: per chunk of kFillChunkSlots slots the distinct state rows it references, and per slot
-  // the position of its row in that list
-  int fill_chunks, fill_max_rows;
-  const uint32_t* fill_rows;      // concatenated per-chunk lists of distinct state rows
-  const int32_t* fill_row_off;    // [fill_chunks + 1]
-  const uint16_t* fill_local;     // [nnz padded to even]
+  const DynInfo* dyn_info;   // [n_dyn]
+  const RomInfo* rom_info;   // [n_rom]
+  const ConstSeg* const_seg; // [n_const_seg]
 };
 
 }  // namespace twb

@@ -283,8 +283,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   // ---- S layout
   HostTables& tb = tables; tb = HostTables{};
   Plan& pl = tb.plan;
-  int S_top = 1;  // S[0] == 1.0
-  const uint32_t S_ONE = 0;
+  int S_top = 0;                 // rows of the spline-value matrix
+  const uint32_t S_ONE = 0;      // local row 0 of every unit's state block is the constant 1
 
   std::vector<Emit> em;
   auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, c}); };
@@ -307,16 +307,19 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_dynamic);
         int r0 = add_set("dynamic", (int)ts.size() * 6);
         pl.dyn_row0 = r0; pl.n_dyn = (int)ts.size();
-        pl.S_dyn_stride = 39 + 6 * n_ee; pl.S_dyn0 = S_top; S_top += pl.S_dyn_stride * pl.n_dyn;
+        pl.S_dyn_stride = 15 + 6 * n_ee; pl.S_dyn0 = S_top; S_top += pl.S_dyn_stride * pl.n_dyn;
         for (int k = 0; k < pl.n_dyn; ++k) {
           const double t = ts[k];
-          const int row = r0 + 6 * k; const uint32_t sb = pl.S_dyn0 + k * pl.S_dyn_stride;
+          const int row = r0 + 6 * k;
+          const uint32_t gb = pl.S_dyn0 + k * pl.S_dyn_stride;  // spline values of this sample in ST
+          const uint32_t sb = 1;  // local state block: [0]=1 | sum f (3) | base-ang block (36) | f_e, c-p_e (6 per foot)
+          tb.dyn_info.push_back(DynInfo{0, 0, row, 0});
           for (int r = 0; r < 6; ++r) bound(row + r, 0.0, 0.0);
-          // phase-0 scratch inside the sample's own S block: c, c_ddot | theta, theta_dot, theta_ddot | p_e.. | f_e..
-          add_eval(MakeSample(sp_lin, t, zero_slot), sb + 0, 1);
-          add_eval(MakeSample(sp_ang, t, zero_slot), sb + 6, 2);
-          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], t, zero_slot), sb + 15 + 3 * e, 0);
-          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_force[e], t, zero_slot), sb + 15 + 3 * n_ee + 3 * e, 0);
+          // spline values: c, c_ddot | theta, theta_dot, theta_ddot | p_e.. | f_e..
+          add_eval(MakeSample(sp_lin, t, zero_slot), gb + 0, 1);
+          add_eval(MakeSample(sp_ang, t, zero_slot), gb + 6, 2);
+          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], t, zero_slot), gb + 15 + 3 * e, 0);
+          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_force[e], t, zero_slot), gb + 15 + 3 * n_ee + 3 * e, 0);
           int p; double tl;
           // base-lin: angular rows = -sum_e [f_e]x dc ; linear rows = m * d(acc)
           Locate(sp_lin, t, &p, &tl);
@@ -365,25 +368,28 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         if (pl.n_rom) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_range_of_motion);
         pl.n_rom = (int)ts.size();
-        pl.S_rom_stride = 9 + 9 * n_ee; pl.S_rom0 = S_top; S_top += pl.S_rom_stride * pl.n_rom;
-        for (int k = 0; k < pl.n_rom; ++k) {  // scratch: c | theta | p_e..
-          const uint32_t sb = pl.S_rom0 + k * pl.S_rom_stride;
-          add_eval(MakeSample(sp_lin, ts[k], zero_slot), sb + 0, 0);
-          add_eval(MakeSample(sp_ang, ts[k], zero_slot), sb + 3, 0);
-          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], ts[k], zero_slot), sb + 6 + 3 * e, 0);
+        pl.S_rom_stride = 6 + 3 * n_ee; pl.S_rom0 = S_top; S_top += pl.S_rom_stride * pl.n_rom;
+        for (int k = 0; k < pl.n_rom; ++k) {  // spline values: c | theta | p_e..
+          const uint32_t gb = pl.S_rom0 + k * pl.S_rom_stride;
+          add_eval(MakeSample(sp_lin, ts[k], zero_slot), gb + 0, 0);
+          add_eval(MakeSample(sp_ang, ts[k], zero_slot), gb + 3, 0);
+          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], ts[k], zero_slot), gb + 6 + 3 * e, 0);
+          tb.rom_info.push_back(RomInfo{});
         }
         for (int e = 0; e < n_ee; ++e) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
           pl.rom_row0[e] = r0;
           for (int k = 0; k < pl.n_rom; ++k) {
-            const double t = ts[k]; const int row = r0 + 3 * k; const uint32_t sb = pl.S_rom0 + k * pl.S_rom_stride;
+            const double t = ts[k]; const int row = r0 + 3 * k;
+            const uint32_t sb = 1;  // local state block of (sample, foot): [0]=1 | R^T (9) | D_e (9)
+            tb.rom_info[k].g_row[e] = row;
             for (int d = 0; d < 3; ++d) bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
             int p; double tl;
             Locate(sp_lin, t, &p, &tl);   // -R^T dc
             for (auto& b : Basis(sp_lin, p, tl, kPos)) for (int i = 0; i < 3; ++i) emit1(row + i, lin.offset + b.var, sb + i * 3 + b.dim, -b.val);
             Locate(sp_ang, t, &p, &tl);   // d(R^T r)/dtheta ; row X does not depend on roll
             for (auto& b : Basis(sp_ang, p, tl, kPos)) for (int i = 0; i < 3; ++i)
-              if (!(i == 0 && b.dim == 0)) emit1(row + i, ang.offset + b.var, sb + 9 + e * 9 + i * 3 + b.dim, b.val);
+              if (!(i == 0 && b.dim == 0)) emit1(row + i, ang.offset + b.var, sb + 9 + i * 3 + b.dim, b.val);
             Locate(sp_motion[e], t, &p, &tl);  // R^T dp_e
             for (auto& b : Basis(sp_motion[e], p, tl, kPos)) for (int i = 0; i < 3; ++i) emit1(row + i, motion(e).offset + b.var, sb + i * 3 + b.dim, b.val);
           }
@@ -398,10 +404,10 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int row = r0 + nd - 1;
             if (mo.ConstNode(nd)) bound(row, 0.0, 0.0); else bound(row, 0.0, 1e20);
             TerrainUnit u{}; for (int d = 0; d < 3; ++d) u.xi[d] = XIndex(mo, nd, kPos, d, zero_slot);
-            u.g_row = row; u.s_idx = S_top; S_top += 2;
+            u.g_row = row; u.s0 = -1;   // local state block: [0]=1 | -dh/dx | -dh/dy
             tb.terr.push_back(u);
-            emit1(row, mo.offset + mo.Var(nd, kPos, X), u.s_idx + 0, 1.0);
-            emit1(row, mo.offset + mo.Var(nd, kPos, Y), u.s_idx + 1, 1.0);
+            emit1(row, mo.offset + mo.Var(nd, kPos, X), 1, 1.0);
+            emit1(row, mo.offset + mo.Var(nd, kPos, Y), 2, 1.0);
             emit1(row, mo.offset + mo.Var(nd, kPos, Z), S_ONE, 1.0);
           }
         }
@@ -419,13 +425,13 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int mnode = 0; for (int i = 0; i < (int)mo.poly.size(); ++i) if (mo.poly[i].phase == phase) { mnode = i; break; }
             ForceUnit u{};
             for (int d = 0; d < 3; ++d) { u.xf[d] = XIndex(fo, nd, kPos, d, zero_slot); u.xp[d] = XIndex(mo, mnode, kPos, d, zero_slot); }
-            u.g_row = row; u.s_idx = S_top; S_top += 25;
+            u.g_row = row; u.s0 = -1;   // local state block: [0]=1 | 25 values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
             tb.force.push_back(u);
             bound(row + 0, 0.0, sp.force_limit_in_normal_direction);
             bound(row + 1, -kInf, 0.0); bound(row + 2, 0.0, +kInf); bound(row + 3, -kInf, 0.0); bound(row + 4, 0.0, +kInf);
             for (int r = 0; r < 5; ++r) {
-              for (int d = 0; d < 2; ++d) emit1(row + r, mo.offset + mo.Var(mnode, kPos, d), u.s_idx + r * 5 + d, 1.0);
-              for (int d = 0; d < 3; ++d) emit1(row + r, fo.offset + fo.Var(nd, kPos, d), u.s_idx + r * 5 + 2 + d, 1.0);
+              for (int d = 0; d < 2; ++d) emit1(row + r, mo.offset + mo.Var(mnode, kPos, d), 1 + r * 5 + d, 1.0);
+              for (int d = 0; d < 3; ++d) emit1(row + r, fo.offset + fo.Var(nd, kPos, d), 1 + r * 5 + 2 + d, 1.0);
             }
             row += 5;
           }
@@ -491,11 +497,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
       default: return fail(TWB_ERR_INVALID, "constraint not defined!");
     }
   }
-  if (S_top > 32767) return fail(TWB_ERR_UNSUPPORTED, "state vector too large");
-  pl.S_g0 = S_top; S_top += m;             // constraint values, transposed out at the end
-  pl.S_grad0 = S_top;                      // cost-gradient rows (only if cost terms exist)
-  if (sp.n_costs > 0) S_top += n;
-  pl.S_size = S_top;
+  if (S_top > 32767) return fail(TWB_ERR_UNSUPPORTED, "spline-value matrix too large");
+  pl.S_size = std::max(S_top, 1);
 
   // ---- CSR assembly: row-major, ascending column (what setFromTriplets yields)
   std::stable_sort(em.begin(), em.end(), [](const Emit& a, const Emit& b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
@@ -510,21 +513,20 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     tb.coef[s] = em[s].c0;
   }
   for (int r = 0; r < m; ++r) row_ptr[r + 1] += row_ptr[r];
-  // fill-kernel tables: distinct state rows per chunk of slots (each row is staged once per chunk)
-  tb.fill_local.assign((nnz + 1) & ~1, 0);
-  pl.fill_chunks = (nnz + kFillChunkSlots - 1) / kFillChunkSlots; pl.fill_max_rows = 1;
-  tb.fill_row_off.assign(1, 0);
-  for (int c = 0; c < pl.fill_chunks; ++c) {
-    std::map<uint32_t, int> local;
-    const int off = (int)tb.fill_rows.size();
-    for (int s = c * kFillChunkSlots; s < std::min(nnz, (c + 1) * kFillChunkSlots); ++s) {
-      auto it = local.find(tb.desc[s]);
-      if (it == local.end()) { it = local.emplace(tb.desc[s], (int)tb.fill_rows.size() - off).first; tb.fill_rows.push_back(tb.desc[s]); }
-      tb.fill_local[s] = (uint16_t)it->second;
+  // CSR slot ranges of the units (their rows are consecutive, so each range is contiguous)
+  for (auto& u : tb.dyn_info) { u.s0 = row_ptr[u.g_row]; u.s1 = row_ptr[u.g_row + 6]; }
+  for (auto& u : tb.rom_info) for (int e = 0; e < n_ee; ++e) { u.s0[e] = row_ptr[u.g_row[e]]; u.s1[e] = row_ptr[u.g_row[e] + 3]; }
+  for (auto& u : tb.terr) { u.s0 = row_ptr[u.g_row]; if (row_ptr[u.g_row + 1] - u.s0 != 3) return fail(TWB_ERR_UNSUPPORTED, "terrain row layout"); }
+  for (auto& u : tb.force) { u.s0 = row_ptr[u.g_row]; if (row_ptr[u.g_row + 5] - u.s0 != 25) return fail(TWB_ERR_UNSUPPORTED, "force row layout"); }
+  for (auto& cs : con_sets)   // iterate-independent rows: SplineAcc and Swing
+    if (cs.name.rfind("splineacc-", 0) == 0 || cs.name.rfind("swing-", 0) == 0) {
+      const int s0 = row_ptr[cs.start], s1 = row_ptr[cs.start + cs.count];
+      if (s1 > s0) {
+        if (!tb.const_seg.empty() && tb.const_seg.back().s1 == s0) tb.const_seg.back().s1 = s1;
+        else tb.const_seg.push_back(ConstSeg{s0, s1});
+      }
     }
-    tb.fill_row_off.push_back((int)tb.fill_rows.size());
-    pl.fill_max_rows = std::max(pl.fill_max_rows, (int)tb.fill_rows.size() - off);
-  }
+  for (auto& cs : tb.const_seg) for (int s = cs.s0; s < cs.s1; ++s) if (tb.desc[s] != S_ONE) return fail(TWB_ERR_UNSUPPORTED, "constant segment layout");
 
   // ---- costs (nlp_formulation.cc:333-376, node_cost.cc:53-76)
   has_cost = false;
@@ -547,7 +549,10 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   // ---- plan scalars
   pl.n = n; pl.m = m; pl.nnz = nnz; pl.n_ee = n_ee;
   pl.n_terr = (int)tb.terr.size(); pl.n_force = (int)tb.force.size(); pl.n_swing = (int)tb.swing.size();
-  pl.n_acc = (int)tb.acc.size(); pl.n_totdur = 0; pl.n_cost = (int)tb.cost.size(); pl.n_eval_items = (int)tb.eval_items.size();
+  pl.n_acc = (int)tb.acc.size(); pl.n_totdur = 0; pl.n_cost = (int)tb.cost.size(); pl.n_eval_items = (int)tb.eval_items.size(); pl.n_const_seg = (int)tb.const_seg.size();
+  pl.n_const_runs = 0; for (auto& cs : tb.const_seg) pl.n_const_runs += (cs.s1 - cs.s0 + 31) / 32;
+  pl.max_dyn_slots = 0; for (auto& u : tb.dyn_info) pl.max_dyn_slots = std::max(pl.max_dyn_slots, u.s1 - u.s0);
+  pl.max_rom_slots = 0; for (auto& u : tb.rom_info) for (int e = 0; e < n_ee; ++e) pl.max_rom_slots = std::max(pl.max_rom_slots, u.s1[e] - u.s0[e]);
   pl.mass = rb.mass; pl.gravity = 9.80665;  // dynamic_model.cc:37
   const double* I = rb.inertia;             // single_rigid_body_dynamics.cc:36-44
   double Ib[9] = {I[0], -I[3], -I[4], -I[3], I[1], -I[5], -I[4], -I[5], I[2]};

@@ -40,9 +40,10 @@ struct HostTables {
   std::vector<SwingUnit> swing;
   std::vector<AccUnit> acc;
   std::vector<CostEntry> cost;
-  std::vector<uint32_t> desc, fill_rows;
-  std::vector<int32_t> fill_row_off;
-  std::vector<uint16_t> fill_local;
+  std::vector<uint32_t> desc;
+  std::vector<DynInfo> dyn_info;
+  std::vector<RomInfo> rom_info;
+  std::vector<ConstSeg> const_seg;
   std::vector<double> coef, dyn_ang_basis;
 };
 

@@ -1,21 +1,23 @@
 // kernels.cu — sm_100a kernels of the batched NLP evaluation (fp64).
 //
 // Everything is a data-parallel map with LANE = PROBLEM INSTANCE.  All per-iterate
-// intermediates live in one state matrix, stored instance-tiled: ST[tile][S_size][32] (tile = 32
-// consecutive instances, row = state slot, lane = instance), so every global access of every kernel
-// is a 256-byte row segment and all rows of a tile sit in one compact region (DRAM page / L2 locality):
+// intermediates live in instance-tiled matrices [tile][rows][32] (tile = 32 consecutive instances,
+// lane = instance), so every global access of every kernel is a 256-byte row segment:
 //
-//   TransposeIn   x[B][n]            -> XT[tile][n+1][32]     (row n stays 0: "not optimised" node values)
-//   SplineKernel  XT                 -> ST rows (spline values at every constraint sample)
-//   DynKernel     ST rows            -> ST rows (g of the dynamic constraint + its Jacobian state)
-//   RomKernel     ST rows            -> ST rows (g of the range-of-motion constraints + Jacobian state)
-//   NodeKernel    XT                 -> ST rows (terrain / force / swing / spline-acc rows, cost)
-//   FillJac       ST, desc, coef     -> jac[B][nnz]           jac[b][s] = ST[desc[s]][b] * coef[s]
-//   TransposeOut  ST rows 1..m       -> g[B][m]
+//   TransposeIn   x[B][n]   -> XT[tile][n+1][32]   (row n stays 0: "not optimised" node values)
+//   SplineKernel  XT        -> ST[tile][S_size][32] (every spline value every constraint sample needs)
+//   DynOut        ST        -> g rows + CSR values of the dynamic constraint
+//   RomOut        ST        -> g rows + CSR values of the range-of-motion constraints
+//   NodeOut       XT        -> g rows + CSR values of terrain / force rows, g of swing / spline-acc, cost
+//   ConstOut                -> CSR values of the iterate-independent rows (spline-acc, swing)
 //
-// The first five are ALU/latency-type kernels (fp64 FMA pipe, sincos); FillJac carries ~95% of the
-// HBM traffic and is a pure stream.  capi.cc pipelines sub-batches over two streams so that the
-// state kernels of sub-batch i+1 run under the HBM-bound fill of sub-batch i.
+// In the *Out kernels a warp owns one unit (a time sample or a node) of 32 instances: each lane
+// computes its instance's unit state into a padded shared-memory block (row = state slot, column =
+// lane), the warp synchronises, and then the lanes switch roles — lane = CSR slot — and stream
+// value = state[desc[slot]][instance] * coef[slot] for the 32 instances, so that every store
+// instruction covers 256 contiguous bytes of one instance's CSR value array (the unit's rows are
+// consecutive CSR rows).  The state never leaves the SM; HBM sees x once, the spline values once
+// (L2-resident), and g / jac exactly once.  The Out kernels are independent and run on separate streams.
 //
 // Reference math restated per device function (file:line cited there).  This translation unit is
 // compiled with -fmad=false: plain * and + round like the reference's scalar C++; fused
@@ -35,6 +37,12 @@ namespace twb {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef TWB_ROM_CTAS
+#define TWB_ROM_CTAS 2
+#endif
+#ifndef TWB_DYN_CTAS
+#define TWB_DYN_CTAS 1
+#endif
 
 // output stores: TWB_STORE_MODE 0 = default write-back, 1 = streaming (evict-first), 2 = write-through
 #ifndef TWB_STORE_MODE
@@ -171,18 +179,18 @@ __device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3]
 //   EulerConverter::GetDerivOfAng{Vel,Acc}WrtEulerNodes (euler_converter.cc:85-131),
 //   GetDerivMwrtNodes (:168-198), GetDerivMdotwrtNodes (:270-304);
 //   sum of forces, per-foot force and lever arm for the other blocks (:103-121, :167-192).
-__device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col S) {
+// in: spline values of the sample (global); Sk: local state rows 1.. (Sk[0..2] sum f, Sk[3..38] base-ang
+// block, Sk[39 + 6e ..] f_e, c - p_e); gk: the 6 constraint values
+__device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col in, const Col Sk, const Col gk) {
   const int n_ee = P.n_ee;
-  const Col Sk = S.at(P.S_dyn0 + k * P.S_dyn_stride);
-  // phase-0 scratch: c, c_ddot, theta, theta_dot, theta_ddot, p_e.., f_e..
   double c[3], cdd[3], th[3], thd[3], thdd[3], pe[kMaxEE][3], fe[kMaxEE][3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) { c[d] = Sk[d]; cdd[d] = Sk[3 + d]; th[d] = Sk[6 + d]; thd[d] = Sk[9 + d]; thdd[d] = Sk[12 + d]; }
+  for (int d = 0; d < 3; ++d) { c[d] = in[d]; cdd[d] = in[3 + d]; th[d] = in[6 + d]; thd[d] = in[9 + d]; thdd[d] = in[12 + d]; }
 #pragma unroll
   for (int e = 0; e < kMaxEE; ++e)
     if (e < n_ee) {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) { pe[e][d] = Sk[15 + 3 * e + d]; fe[e][d] = Sk[15 + 3 * n_ee + 3 * e + d]; }
+      for (int d = 0; d < 3; ++d) { pe[e][d] = in[15 + 3 * e + d]; fe[e][d] = in[15 + 3 * n_ee + 3 * e + d]; }
     }
 
   const Trig tr = MakeTrig(th);
@@ -227,7 +235,6 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col S) {
   MulVec(Iw, om, Iw_om); MulVec(Iw, omd, Iw_omd);
   {
     const double wx[3] = {om[1] * Iw_om[2] - om[2] * Iw_om[1], om[2] * Iw_om[0] - om[0] * Iw_om[2], om[0] * Iw_om[1] - om[1] * Iw_om[0]};
-    const Col gk = S.at(P.S_g0 + P.dyn_row0 + 6 * k);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       gk[d] = Iw_omd[d] + wx[d] - tau[d];
@@ -304,18 +311,12 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col S) {
 // ---- RangeOfMotionConstraint sample (all feet) --------------------------------
 // range_of_motion_constraint.cc:58-109: g = R^T (p_ee - c); Jacobian state R^T and
 // D_e = d(R^T r_e)/d(theta) (DerivOfRotVecMult(t, r_W, true)).
-__device__ __forceinline__ void RomUnit(const Plan& P, int k, const Col S) {
-  const int n_ee = P.n_ee;
-  const Col Sk = S.at(P.S_rom0 + k * P.S_rom_stride);
-  double c[3], th[3], pes[kMaxEE][3];
+// One foot at one sample.  in: spline values of the sample (global); Sk: local state rows 1..
+// (Sk[0..8] R^T, Sk[9..17] D_e); gk: the foot's 3 constraint values
+__device__ __forceinline__ void RomUnit(const Plan& P, int e, const Col in, const Col Sk, const Col gk) {
+  double c[3], th[3], pe[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) { c[d] = Sk[d]; th[d] = Sk[3 + d]; }
-#pragma unroll
-  for (int e = 0; e < kMaxEE; ++e)
-    if (e < n_ee) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) pes[e][d] = Sk[6 + 3 * e + d];
-    }
+  for (int d = 0; d < 3; ++d) { c[d] = in[d]; th[d] = in[3 + d]; pe[d] = in[6 + 3 * e + d]; }
   const Trig tr = MakeTrig(th);
   double R[3][3]; RotationMatrix(tr, R);
   double dR[3][3][3]; RotationDerivative(tr, dR);
@@ -323,22 +324,14 @@ __device__ __forceinline__ void RomUnit(const Plan& P, int k, const Col S) {
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int d = 0; d < 3; ++d) Sk[i * 3 + d] = R[d][i];
+  const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
 #pragma unroll
-  for (int e = 0; e < kMaxEE; ++e) {
-    if (e >= n_ee) break;
-    const double* pe = pes[e];
-    const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
-    {
-      const Col ge = S.at(P.S_g0 + P.rom_row0[e] + 3 * k);
+  for (int i = 0; i < 3; ++i) gk[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
+  double D[3][3]; RotVecDerivative<true>(dR, r, D);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) ge[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
-    }
-    double D[3][3]; RotVecDerivative<true>(dR, r, D);
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) Sk[9 + e * 9 + i * 3 + d] = D[i][d];
-  }
+    for (int d = 0; d < 3; ++d) Sk[9 + i * 3 + d] = D[i][d];
 }
 
 // ---- analytic terrains: height_map_examples.cc:35-211 ------------------------
@@ -380,11 +373,12 @@ __device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) 
 }
 
 // TerrainConstraint, terrain_constraint.cc:59-108
-__device__ __forceinline__ void TerrainUnitEval(const Plan& P, const TerrainUnit& u, int terrain, const Col xs, const Col S) {
+// Sk: local state rows 1.. ({-dh/dx, -dh/dy}); gk: the constraint value
+__device__ __forceinline__ void TerrainUnitEval(const TerrainUnit& u, int terrain, const Col xs, const Col Sk, const Col gk) {
   const double px = xs[u.xi[0]], py = xs[u.xi[1]], pz = xs[u.xi[2]];
   const TerrainPoint tp = EvalTerrain(terrain, px, py);
-  S[P.S_g0 + u.g_row] = pz - tp.h;
-  S[u.s_idx + 0] = -tp.hx; S[u.s_idx + 1] = -tp.hy;
+  gk[0] = pz - tp.h;
+  Sk[0] = -tp.hx; Sk[1] = -tp.hy;
 }
 
 // normalised vector and HeightMap::GetDerivativeOfNormalizedBasisWrt (height_map.cc:62-91,140-146):
@@ -404,7 +398,8 @@ __device__ __forceinline__ void NormalizedDeriv(const double v[3], const double 
 __device__ __forceinline__ double Dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 // ForceConstraint, force_constraint.cc:64-171
-__device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u, int terrain, const Col xs, const Col S) {
+// Su: local state rows 1.. (25 Jacobian values); gr: the 5 constraint values
+__device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u, int terrain, const Col xs, const Col Su, const Col gr) {
   const double mu = P.mu;
   const double px = xs[u.xp[0]], py = xs[u.xp[1]];
   const double f[3] = {xs[u.xf[0]], xs[u.xf[1]], xs[u.xf[2]]};
@@ -419,11 +414,7 @@ __device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u,
     a1[d] = t1[d] - mu * n[d]; b1[d] = t1[d] + mu * n[d];
     a2[d] = t2[d] - mu * n[d]; b2[d] = t2[d] + mu * n[d];
   }
-  {
-    const Col gr = S.at(P.S_g0 + u.g_row);
-    gr[0] = Dot3(f, n); gr[1] = Dot3(f, a1); gr[2] = Dot3(f, b1); gr[3] = Dot3(f, a2); gr[4] = Dot3(f, b2);
-  }
-  const Col Su = S.at(u.s_idx);
+  gr[0] = Dot3(f, n); gr[1] = Dot3(f, a1); gr[2] = Dot3(f, b1); gr[3] = Dot3(f, a2); gr[4] = Dot3(f, b2);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     Su[0 * 5 + 2 + d] = n[d]; Su[1 * 5 + 2 + d] = a1[d]; Su[2 * 5 + 2 + d] = b1[d];
@@ -451,8 +442,7 @@ __device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u,
 }
 
 // SwingConstraint::GetValues, swing_constraint.cc:57-83 (Jacobian is constant)
-__device__ __forceinline__ void SwingUnitEval(const Plan& P, const SwingUnit& u, const Col xs, const Col S) {
-  const Col g = S.at(P.S_g0);
+__device__ __forceinline__ void SwingUnitEval(const SwingUnit& u, const Col xs, const Col gk) {
   const double t_swing_avg = 0.3;
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
@@ -460,14 +450,13 @@ __device__ __forceinline__ void SwingUnitEval(const Plan& P, const SwingUnit& u,
     const double dist = next - prev;
     const double center = prev + 0.5 * dist;
     const double des_vel = dist / t_swing_avg;
-    g[u.g_row + 2 * d] = xs[u.xc_p[d]] - center;
-    g[u.g_row + 2 * d + 1] = xs[u.xc_v[d]] - des_vel;
+    gk[2 * d] = xs[u.xc_p[d]] - center;
+    gk[2 * d + 1] = xs[u.xc_v[d]] - des_vel;
   }
 }
 
 // SplineAccConstraint::GetValues, spline_acc_constraint.cc:49-65 (Jacobian constant for fixed durations)
-__device__ __forceinline__ void AccUnitEval(const Plan& P, const AccUnit& u, const Col xs, const Col S) {
-  const Col g = S.at(P.S_g0);
+__device__ __forceinline__ void AccUnitEval(const AccUnit& u, const Col xs, const Col gk) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[u.x0 + d], v0 = xs[u.x0 + 3 + d], p1 = xs[u.x0 + 6 + d], v1 = xs[u.x0 + 9 + d];
@@ -477,7 +466,7 @@ __device__ __forceinline__ void AccUnitEval(const Plan& P, const AccUnit& u, con
     const double Cn = DivExact(-(3 * (p1 - p2) + u.Tn * (2 * v1 + v2)), u.Tn2, u.rTn2);
     const double a_prev = 2 * Cp + (6 * u.Tp) * Dp;
     const double a_next = 2 * Cn;
-    g[u.g_row + d] = a_prev - a_next;
+    gk[d] = a_prev - a_next;
   }
 }
 
@@ -487,10 +476,12 @@ __device__ __forceinline__ Col TiledCol(double* base, int b, int rows) {
   return Col{base + ((size_t)(b >> 5) * rows) * 32 + (b & 31), 32};
 }
 
-// x[b][i] -> XT[b/32][i][b%32]: 32x32 tiles through shared memory, coalesced on both sides
-__global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x, double* __restrict__ XT, int n, int nb) {
+// x[b][i] -> XT[b/32][i][b%32]: 32x32 tiles through shared memory, coalesced on both sides; clears status
+__global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x, double* __restrict__ XT,
+                                                   int* __restrict__ status, int n, int nb) {
   __shared__ double tile[32][33];
   const int i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  if (status && blockIdx.x == 0 && threadIdx.y == 0 && b0 + threadIdx.x < nb) status[b0 + threadIdx.x] = 0;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int b = b0 + r, i = i0 + threadIdx.x;
     if (b < nb && i < n) tile[r][threadIdx.x] = x[(size_t)b * n + i];
@@ -500,23 +491,6 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int i = i0 + r, b = b0 + threadIdx.x;
     if (b < nb && i < n) dst[(size_t)i * 32 + threadIdx.x] = tile[threadIdx.x][r];
-  }
-}
-
-// ST[b/32][row0 + r][b%32] -> out[b][r], r < rows  (constraint values g, cost gradient)
-__global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ ST, double* __restrict__ out, int S_size,
-                                                    int row0, int rows, int nb) {
-  __shared__ double tile[32][33];
-  const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
-  const double* src = ST + ((size_t)blockIdx.y * S_size + row0) * 32;
-  for (int q = threadIdx.y; q < 32; q += 8) {
-    const int r = r0 + q, b = b0 + threadIdx.x;
-    if (r < rows && b < nb) tile[q][threadIdx.x] = src[(size_t)r * 32 + threadIdx.x];
-  }
-  __syncthreads();
-  for (int q = threadIdx.y; q < 32; q += 8) {
-    const int b = b0 + q, r = r0 + threadIdx.x;
-    if (r < rows && b < nb) StoreOut(out + (size_t)b * rows + r, tile[threadIdx.x][q]);
   }
 }
 
@@ -531,188 +505,274 @@ __global__ void __launch_bounds__(128) SplineKernel(const Plan P, double* __rest
   EvalSplineToState(sr, kind, TiledCol(XT, b, P.n + 1), TiledCol(ST, b, P.S_size).at(row));
 }
 
-// one thread per (dynamic sample = blockIdx.y, instance)
-__global__ void __launch_bounds__(128, 2) DynKernel(const Plan P, double* __restrict__ ST, int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  DynamicUnit(P, blockIdx.y, TiledCol(ST, b, P.S_size));
+// ---- warp-collective output of one unit: lanes switch from "instance" to "CSR slot" ----------------
+using Tile = double (*)[33];   // [state row][lane], padded: column reads by 32 different rows are conflict-free
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// The four warps of a CTA work on the same unit for four instance tiles, so the unit's slot descriptors
+// are staged once per CTA in shared memory (asynchronously, under the unit math).
+__device__ __forceinline__ void StageSlots(const Plan& P, int s0, int s1, double* sm_coef, uint32_t* sm_desc, int tid, int nthreads) {
+  for (int i = tid; i < s1 - s0; i += nthreads) { cp_async8(sm_coef + i, P.coef + s0 + i); cp_async4(sm_desc + i, P.desc + s0 + i); }
+}
+// jac[b0 + j][s0 + i] = t[sm_desc[i]][j] * sm_coef[i], i < n_slots, j < n_inst
+__device__ __forceinline__ void StoreSlots(const Tile t, const double* sm_coef, const uint32_t* sm_desc, int n_slots,
+                                           double* __restrict__ out0, size_t nnz, int n_inst, int lane) {
+  for (int i = lane; i < n_slots; i += 32) {
+    const double* row = t[sm_desc[i]];
+    const double cf = sm_coef[i];
+    double* out = out0 + i;
+    if (n_inst == 32) {
+#pragma unroll 16
+      for (int j = 0; j < 32; ++j) StoreOut(out + j * nnz, row[j] * cf);
+    } else {
+      for (int j = 0; j < n_inst; ++j) StoreOut(out + j * nnz, row[j] * cf);
+    }
+  }
+}
+// g[b0 + j][g_row + r] = t[g_local + r][j], r < n_g
+__device__ __forceinline__ void StoreG(const Tile t, int g_local, int n_g, double* __restrict__ g_tile, int m, int n_inst,
+                                       int lane) {
+  for (int idx = lane; idx < n_g * n_inst; idx += 32) {
+    const int j = idx / n_g, r = idx - j * n_g;
+    StoreOut(g_tile + (size_t)j * m + r, t[g_local + r][j]);
+  }
+}
+// non-finite check of this lane's own column (rows 1 .. n_rows-1); flags instance b
+__device__ __forceinline__ void FlagNonFinite(const Tile t, int n_rows, int lane, int* __restrict__ status, int b, int nb) {
+  if (!status) return;
+  double chk = 0.0;
+  for (int r = 1; r < n_rows; ++r) chk = fma(t[r][lane], 0.0, chk);
+  if (chk != chk && b < nb) atomicOr(status + b, 1);
 }
 
-// one thread per (range-of-motion sample = blockIdx.y, instance)
-__global__ void __launch_bounds__(128, 2) RomKernel(const Plan P, double* __restrict__ ST, int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  RomUnit(P, blockIdx.y, TiledCol(ST, b, P.S_size));
+constexpr int kOutWarps = 4;   // warps per CTA of NodeOut / ConstOut (warp = instance tile)
+constexpr int kDynWarps = 8;   // consecutive samples per CTA of DynOut
+
+// DynamicConstraint: blockIdx.y = instance tile, warp = one of kOutWarps CONSECUTIVE samples, so a CTA writes
+// several KB of contiguous CSR values per instance (the samples' rows are adjacent) — DRAM page locality.
+__global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, double* __restrict__ ST, double* __restrict__ g,
+                                                           double* __restrict__ jac, int* __restrict__ status, int nb,
+                                                           unsigned flags, int max_slots) {
+  extern __shared__ __align__(16) double out_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * kDynWarps + warp, b0 = blockIdx.y * 32;
+  if (k >= P.n_dyn) return;
+  const int n_rows = 40 + 6 * P.n_ee, G0 = n_rows;   // local rows: 1 | 3 | 36 | 6 per foot, then g
+  const size_t per_warp = (size_t)max_slots + (max_slots + 1) / 2 + (size_t)(n_rows + 6) * 33;
+  double* sm_coef = out_smem + warp * per_warp;
+  uint32_t* sm_desc = reinterpret_cast<uint32_t*>(sm_coef + max_slots);
+  Tile t = reinterpret_cast<Tile>(sm_coef + max_slots + (max_slots + 1) / 2);
+  const DynInfo u = P.dyn_info[k];
+  if (flags & 2u) StageSlots(P, u.s0, u.s1, sm_coef, sm_desc, lane, 32);
+  cp_async_commit();
+  t[0][lane] = 1.0;
+  DynamicUnit(P, k, TiledCol(ST, b0 + lane, P.S_size).at(P.S_dyn0 + k * P.S_dyn_stride), Col{&t[1][lane], 33},
+              Col{&t[G0][lane], 33});
+  FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
+  cp_async_wait_all();
+  __syncwarp();
+  const int n_inst = min(32, nb - b0);
+  if (flags & 2u) StoreSlots(t, sm_coef, sm_desc, u.s1 - u.s0, jac + (size_t)b0 * P.nnz + u.s0, (size_t)P.nnz, n_inst, lane);
+  if (flags & 1u) StoreG(t, G0, 6, g + (size_t)b0 * P.m + u.g_row, P.m, n_inst, lane);
 }
 
-// one thread per (node unit = blockIdx.y, instance): force | terrain | swing | spline-acc | cost
-__global__ void __launch_bounds__(128) NodeKernel(const Plan P, double* __restrict__ XT, double* __restrict__ ST,
-                                                  const int* __restrict__ terrain_ids, int default_terrain,
-                                                  double* __restrict__ cost, int nb, int want_cost) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  const Col xs = TiledCol(XT, b, P.n + 1), S = TiledCol(ST, b, P.S_size);
+// RangeOfMotionConstraint: blockIdx.z = foot, blockIdx.y = instance tile, warp = one of kRomWarps consecutive
+// samples of that foot (their rows are adjacent: one CTA writes a contiguous run of CSR values per instance)
+constexpr int kRomWarps = 8;
+__global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomOut(const Plan P, double* __restrict__ ST, double* __restrict__ g,
+                                                           double* __restrict__ jac, int* __restrict__ status, int nb,
+                                                           unsigned flags, int max_slots) {
+  extern __shared__ __align__(16) double out_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * kRomWarps + warp, b0 = blockIdx.y * 32, e = blockIdx.z;
+  if (k >= P.n_rom) return;
+  constexpr int n_rows = 19, G0 = 19;   // local rows: 1 | R^T 9 | D_e 9, then g (3)
+  const size_t per_warp = (size_t)max_slots + (max_slots + 1) / 2 + (size_t)(n_rows + 3) * 33;
+  double* sm_coef = out_smem + warp * per_warp;
+  uint32_t* sm_desc = reinterpret_cast<uint32_t*>(sm_coef + max_slots);
+  Tile t = reinterpret_cast<Tile>(sm_coef + max_slots + (max_slots + 1) / 2);
+  const RomInfo info = P.rom_info[k];
+  const int s0 = info.s0[e], n_slots = info.s1[e] - s0;
+  if (flags & 2u) StageSlots(P, s0, s0 + n_slots, sm_coef, sm_desc, lane, 32);
+  cp_async_commit();
+  t[0][lane] = 1.0;
+  RomUnit(P, e, TiledCol(ST, b0 + lane, P.S_size).at(P.S_rom0 + k * P.S_rom_stride), Col{&t[1][lane], 33}, Col{&t[G0][lane], 33});
+  FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
+  cp_async_wait_all();
+  __syncwarp();
+  const int n_inst = min(32, nb - b0);
+  if (flags & 2u) StoreSlots(t, sm_coef, sm_desc, n_slots, jac + (size_t)b0 * P.nnz + s0, (size_t)P.nnz, n_inst, lane);
+  if (flags & 1u) StoreG(t, G0, 3, g + (size_t)b0 * P.m + info.g_row[e], P.m, n_inst, lane);
+}
+
+// node units: blockIdx.y = unit (force | terrain | swing | spline-acc | cost), warp = instance tile
+constexpr int kNodeRows = 32;   // local rows: 1 | <= 25 state | <= 5 g
+__global__ void __launch_bounds__(kOutWarps * 32) NodeOut(const Plan P, double* __restrict__ XT, double* __restrict__ g,
+                                                          double* __restrict__ jac, double* __restrict__ cost,
+                                                          double* __restrict__ grad, int* __restrict__ status,
+                                                          const int* __restrict__ terrain_ids, int default_terrain, int nb,
+                                                          unsigned flags) {
+  __shared__ __align__(16) double node_smem[kOutWarps * kNodeRows * 33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * kOutWarps + warp, b0 = tile * 32, b = b0 + lane;
+  if (b0 >= nb) return;
+  Tile t = reinterpret_cast<Tile>(node_smem + (size_t)warp * kNodeRows * 33);
+  const Col xs = TiledCol(XT, b, P.n + 1);
+  const int n_inst = min(32, nb - b0);
+  const int terrain = (terrain_ids && b < nb) ? terrain_ids[b] : default_terrain;
+  double* jac_tile = jac + (size_t)b0 * P.nnz;
+  double* g_tile = g + (size_t)b0 * P.m;
+  t[0][lane] = 1.0;
   int u = blockIdx.y;
   if (u < P.n_force) {
-    ForceUnitEval(P, P.force[u], terrain_ids ? terrain_ids[b] : default_terrain, xs, S);
+    const ForceUnit fu = P.force[u];
+    const uint32_t my_a = (lane < 25) ? __ldg(P.desc + fu.s0 + lane) : 0u;   // issued before the unit math
+    const double my_c = (lane < 25) ? __ldg(P.coef + fu.s0 + lane) : 0.0;
+    ForceUnitEval(P, fu, terrain, xs, Col{&t[1][lane], 33}, Col{&t[26][lane], 33});
+    FlagNonFinite(t, 26, lane, status, b, nb);
+    __syncwarp();
+    if ((flags & 2u) && lane < 25) {
+      const double* row = t[my_a];
+      double* out = jac_tile + fu.s0 + lane;
+      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * P.nnz, row[j] * my_c);
+    }
+    if (flags & 1u) StoreG(t, 26, 5, g_tile + fu.g_row, P.m, n_inst, lane);
     return;
   }
   u -= P.n_force;
   if (u < P.n_terr) {
-    TerrainUnitEval(P, P.terr[u], terrain_ids ? terrain_ids[b] : default_terrain, xs, S);
+    const TerrainUnit tu = P.terr[u];
+    const uint32_t my_a = (lane < 3) ? __ldg(P.desc + tu.s0 + lane) : 0u;
+    const double my_c = (lane < 3) ? __ldg(P.coef + tu.s0 + lane) : 0.0;
+    TerrainUnitEval(tu, terrain, xs, Col{&t[1][lane], 33}, Col{&t[3][lane], 33});
+    FlagNonFinite(t, 3, lane, status, b, nb);
+    __syncwarp();
+    if ((flags & 2u) && lane < 3) {
+      const double* row = t[my_a];
+      double* out = jac_tile + tu.s0 + lane;
+      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * P.nnz, row[j] * my_c);
+    }
+    if (flags & 1u) StoreG(t, 3, 1, g_tile + tu.g_row, P.m, n_inst, lane);
     return;
   }
   u -= P.n_terr;
-  if (u < P.n_swing) { SwingUnitEval(P, P.swing[u], xs, S); return; }
+  if (u < P.n_swing) {
+    if (flags & 1u) {
+      const SwingUnit su = P.swing[u];
+      SwingUnitEval(su, xs, Col{&t[1][lane], 33});
+      __syncwarp();
+      StoreG(t, 1, 4, g_tile + su.g_row, P.m, n_inst, lane);
+    }
+    return;
+  }
   u -= P.n_swing;
-  if (u < P.n_acc) { AccUnitEval(P, P.acc[u], xs, S); return; }
-  if (want_cost) {
+  if (u < P.n_acc) {
+    if (flags & 1u) {
+      const AccUnit au = P.acc[u];
+      AccUnitEval(au, xs, Col{&t[1][lane], 33});
+      __syncwarp();
+      StoreG(t, 1, 3, g_tile + au.g_row, P.m, n_inst, lane);
+    }
+    return;
+  }
+  if ((flags & 4u) && P.n_cost > 0 && b < nb) {
     // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
-    // dense gradient row (node_cost.cc:65-76), both in the reference's order; gradient rows live in ST.
-    const Col gr = S.at(P.S_grad0);
-    for (int i = 0; i < P.n; ++i) gr[i] = 0.0;
+    // dense gradient row (node_cost.cc:65-76), both in the reference's order
+    double* gr = grad ? grad + (size_t)b * P.n : nullptr;
+    if (gr) for (int i = 0; i < P.n; ++i) gr[i] = 0.0;
     double total_cost = 0.0, term = 0.0;
     for (int i = 0; i < P.n_cost; ++i) {
       const CostEntry ce = P.cost[i];
       if (ce.pad && i > 0) { total_cost += term; term = 0.0; }
       const double val = xs[ce.xi];
       term += ce.weight * (val * val);
-      if (ce.grad_col >= 0) gr[ce.grad_col] += ce.weight * 2.0 * val;
+      if (gr && ce.grad_col >= 0) gr[ce.grad_col] += ce.weight * 2.0 * val;
     }
     total_cost += term;
     if (cost) cost[b] = total_cost;
   }
 }
 
-// jac[b][s] = ST[tile][desc[s]][b] * coef[s]   — gather state rows, transpose, scale, stream out.
-// A CTA owns 32 instances (one tile of ST) and one chunk of kFillChunkSlots CSR slots.
-//  stage: the chunk's DISTINCT state rows (host-built list, ~4x fewer than slots) are copied with
-//         cp.async, 256 contiguous bytes per row (lane = instance), into a padded shared-memory
-//         array — dozens of row copies in flight per thread, no registers held;
-//  store: lane = slot pair: it reads its two rows for one instance (conflict-free: row stride 33),
-//         scales by its two constants and writes 16 bytes, so each store instruction covers 512
-//         contiguous bytes of one instance's CSR value array.
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-template <bool kVec>
-__global__ void __launch_bounds__(kThreads) FillJac(const Plan P, const double* __restrict__ ST, double* __restrict__ jac,
-                                                    int* __restrict__ status, int nb) {
-  extern __shared__ __align__(16) double fill_rows_smem[];
-  double (*t)[33] = reinterpret_cast<double (*)[33]>(fill_rows_smem);
+// iterate-independent CSR values (SplineAcc, Swing rows): blockIdx.y = 32-slot run, warp = instance tile
+__global__ void __launch_bounds__(kOutWarps * 32) ConstOut(const Plan P, double* __restrict__ jac, int nb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nnz = P.nnz;
-  const int chunk = blockIdx.x;                                     // chunk fastest: the CTAs of one instance
-  const int b0 = blockIdx.y * 32;                                   // tile run together (L2 locality of its rows)
-  const double* Sb = ST + ((size_t)blockIdx.y * P.S_size) * 32 + lane;
-  const int r_begin = __ldg(P.fill_row_off + chunk), n_rows = __ldg(P.fill_row_off + chunk + 1) - r_begin;
-  for (int r = warp; r < n_rows; r += kThreads / 32)
-    cp_async8(&t[r][lane], Sb + (size_t)__ldg(P.fill_rows + r_begin + r) * 32);
-  const int s_begin = chunk * kFillChunkSlots, s_end = min(nnz, s_begin + kFillChunkSlots);
-  cp_async_wait_all();
-  __syncthreads();
-  if (status) {   // every output is (staged value) x (finite constant): check the staged rows once
-    double chk = 0.0;
-    for (int r = warp; r < n_rows; r += kThreads / 32) chk = fma(t[r][lane], 0.0, chk);
-    if (chk != chk && b0 + lane < nb) atomicOr(status + b0 + lane, 1);   // NaN or Inf in instance b0 + lane
+  const int b0 = (blockIdx.x * kOutWarps + warp) * 32;
+  if (b0 >= nb) return;
+  int run = blockIdx.y, s = -1;
+  for (int i = 0; i < P.n_const_seg; ++i) {   // locate the run inside the segment list
+    const ConstSeg seg = P.const_seg[i];
+    const int runs = (seg.s1 - seg.s0 + 31) / 32;
+    if (run < runs) { s = seg.s0 + run * 32 + lane; if (s >= seg.s1) s = -1; break; }
+    run -= runs;
   }
+  if (s < 0) return;
   const int n_inst = min(32, nb - b0);
-  if (kVec) {
-    for (int s = s_begin + 2 * threadIdx.x; s < s_end; s += 2 * kThreads) {
-      const uint32_t loc = __ldg(reinterpret_cast<const uint32_t*>(P.fill_local + s));   // two 16-bit row positions
-      const double2 cf = __ldg(reinterpret_cast<const double2*>(P.coef + s));
-      const double* r0 = t[loc & 0xFFFFu];
-      const double* r1 = t[loc >> 16];
-      double2* out = reinterpret_cast<double2*>(jac + (size_t)b0 * nnz + s);
+  const size_t nnz = (size_t)P.nnz;
+  const double cf = __ldg(P.coef + s);
+  double* out = jac + (size_t)b0 * nnz + s;
 #pragma unroll 8
-      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * (nnz >> 1), make_double2(r0[j] * cf.x, r1[j] * cf.y));
-    }
-  } else {
-    for (int s = s_begin + threadIdx.x; s < s_end; s += kThreads) {
-      const double cf = __ldg(P.coef + s);
-      const double* r0 = t[__ldg(P.fill_local + s)];
-      double* out = jac + (size_t)b0 * nnz + s;
-      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * nnz, r0[j] * cf);
-    }
-  }
-}
-
-__global__ void ClearStatus(int* __restrict__ status, int nb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nb) status[i] = 0;
-}
-
-__global__ void InitOnes(double* __restrict__ ST, int S_size, int n_tiles) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_tiles * 32) ST[((size_t)(i >> 5) * S_size) * 32 + (i & 31)] = 1.0;   // state row 0 == 1
+  for (int j = 0; j < n_inst; ++j) StoreOut(out + j * nnz, cf);
 }
 
 }  // namespace
 
 // ---- host launchers ------------------------------------------------------------------
 void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // profiling hook (capi.cc, TWB_PROFILE=1)
-#define TWB_MARK(label) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
-// XT / ST point at the first TILE of the sub-batch (sub-batches start at multiples of 32 instances).
-int LaunchInitState(double* ST, int S_size, int n_tiles, cudaStream_t stream) {
-  InitOnes<<<(n_tiles * 32 + 255) / 256, 256, 0, stream>>>(ST, S_size, n_tiles);
-  return (int)cudaGetLastError();
-}
+#define TWB_MARK(label, stream) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
 
-int LaunchStateKernels(const Plan& P, const double* x, double* XT, double* ST, const int* terrain_ids,
-                       int default_terrain, double* cost, int* status, int nb, bool want_cost, cudaStream_t stream,
-                       int* launches) {
+// XT / ST are the tiled matrices of the whole batch (first tile = first instance of x / g / jac).
+// Streams: `s` carries TransposeIn -> SplineKernel -> DynOut; RomOut / NodeOut+ConstOut run on aux[0] / aux[1]
+// after the spline values exist (ev[0]) and are joined back into `s` (ev[1], ev[2]).
+int LaunchEval(const Plan& P, const double* x, double* XT, double* ST, double* g, double* jac, double* cost, double* grad,
+               int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
+               cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches) {
   if (nb <= 0) return 0;
   int count = 0;
-  const int bx = (nb + 127) / 128;
-  TWB_MARK("begin");
-  if (status) { ClearStatus<<<(nb + 255) / 256, 256, 0, stream>>>(status, nb); ++count; TWB_MARK("ClearStatus"); }
-  TransposeIn<<<dim3((P.n + 31) / 32, (nb + 31) / 32), dim3(32, 8), 0, stream>>>(x, XT, P.n, nb); ++count; TWB_MARK("TransposeIn");
-  if (P.n_eval_items > 0) { SplineKernel<<<dim3(bx, P.n_eval_items), 128, 0, stream>>>(P, XT, ST, nb); ++count; TWB_MARK("SplineKernel"); }
-  if (P.n_dyn > 0) { DynKernel<<<dim3(bx, P.n_dyn), 128, 0, stream>>>(P, ST, nb); ++count; TWB_MARK("DynKernel"); }
-  if (P.n_rom > 0) { RomKernel<<<dim3(bx, P.n_rom), 128, 0, stream>>>(P, ST, nb); ++count; TWB_MARK("RomKernel"); }
+  const bool serial = (g_after_launch != nullptr);
+  if (serial) aux0 = aux1 = s;
+  const int tiles = (nb + 31) / 32, bx = (tiles + kOutWarps - 1) / kOutWarps;
+  const unsigned out_flags = flags & 7u;
+  TWB_MARK("begin", s);
+  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, status, P.n, nb); ++count; TWB_MARK("TransposeIn", s);
+  if (P.n_eval_items > 0) { SplineKernel<<<dim3((nb + 127) / 128, P.n_eval_items), 128, 0, s>>>(P, XT, ST, nb); ++count; TWB_MARK("SplineKernel", s); }
+  if (!serial) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
+  cudaError_t e = cudaSuccess;
+  if (P.n_dyn > 0 && (out_flags & 3u)) {
+    const int ms = (P.max_dyn_slots + 1) & ~1;
+    const size_t smem = (size_t)kDynWarps * ((size_t)(46 + 6 * P.n_ee) * 33 + ms + (ms + 1) / 2) * sizeof(double);
+    e = cudaFuncSetAttribute(DynOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    DynOut<<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, s>>>(P, ST, g, jac, status, nb, out_flags, ms); ++count; TWB_MARK("DynOut", s);
+  }
+  if (P.n_rom > 0 && (out_flags & 3u)) {
+    const int ms = (P.max_rom_slots + 1) & ~1;
+    const size_t smem = (size_t)kRomWarps * ((size_t)22 * 33 + ms + (ms + 1) / 2) * sizeof(double);
+    e = cudaFuncSetAttribute(RomOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    RomOut<<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles, P.n_ee), kRomWarps * 32, smem, aux0>>>(P, ST, g, jac, status, nb, out_flags, ms); ++count; TWB_MARK("RomOut", aux0);
+  }
+  const bool want_cost = (out_flags & 4u) && P.n_cost > 0;
   const int n_units = P.n_force + P.n_terr + P.n_swing + P.n_acc + (want_cost ? 1 : 0);
   if (n_units > 0) {
-    NodeKernel<<<dim3(bx, n_units), 128, 0, stream>>>(P, XT, ST, terrain_ids, default_terrain, cost, nb, want_cost ? 1 : 0);
-    ++count; TWB_MARK("NodeKernel");
+    NodeOut<<<dim3(bx, n_units), kOutWarps * 32, 0, aux1>>>(P, XT, g, jac, cost, grad, status, terrain_ids, default_terrain, nb, out_flags);
+    ++count; TWB_MARK("NodeOut", aux1);
+  }
+  if (P.n_const_seg > 0 && (out_flags & 2u)) {
+    ConstOut<<<dim3(bx, P.n_const_runs), kOutWarps * 32, 0, aux1>>>(P, jac, nb); ++count; TWB_MARK("ConstOut", aux1);
+  }
+  if (!serial) {
+    cudaEventRecord(ev[1], aux0); cudaEventRecord(ev[2], aux1);
+    cudaStreamWaitEvent(s, ev[1], 0); cudaStreamWaitEvent(s, ev[2], 0);
   }
   if (launches) *launches += count;
-  return (int)cudaGetLastError();
-}
-
-int LaunchFillJac(const Plan& P, const double* ST, double* jac, int* status, int nb, int n_sms, cudaStream_t stream,
-                  int* launches) {
-  if (nb <= 0) return 0;
-  (void)n_sms;
-  const bool vec = ((P.nnz & 1) == 0) && ((reinterpret_cast<uintptr_t>(jac) & 15) == 0);
-  const size_t smem = (size_t)P.fill_max_rows * 33 * sizeof(double);
-  const dim3 grid(P.fill_chunks, (nb + 31) / 32);
-  cudaError_t e;
-  TWB_MARK("begin");
-  if (vec) {
-    e = cudaFuncSetAttribute(FillJac<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    FillJac<true><<<grid, kThreads, smem, stream>>>(P, ST, jac, status, nb);
-  } else {
-    e = cudaFuncSetAttribute(FillJac<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    FillJac<false><<<grid, kThreads, smem, stream>>>(P, ST, jac, status, nb);
-  }
-  TWB_MARK("FillJac");
-  if (launches) *launches += 1;
-  return (int)cudaGetLastError();
-}
-
-int LaunchTransposeOut(const Plan& P, const double* ST, int row0, int rows, double* out, int nb, cudaStream_t stream,
-                       int* launches) {
-  if (nb <= 0 || rows <= 0) return 0;
-  TWB_MARK("begin");
-  TransposeOut<<<dim3((rows + 31) / 32, (nb + 31) / 32), dim3(32, 8), 0, stream>>>(ST, out, P.S_size, row0, rows, nb);
-  TWB_MARK("TransposeOut");
-  if (launches) *launches += 1;
   return (int)cudaGetLastError();
 }
 
