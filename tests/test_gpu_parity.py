@@ -59,6 +59,11 @@ def test_every_terrain_go1():
     _compare("go1_trot_flat", B, terrains=(np.arange(B) % 7).astype(np.int32))
 
 
+def test_base_motion_constraint():
+    _compare("anymal_trot_block_base_rom", 40)
+    _compare("hopper_base_rom", 5)
+
+
 def test_longer_horizon():
     _compare("anymal_trot_block", 8, t_total=2.4)
 

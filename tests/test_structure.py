@@ -20,6 +20,8 @@ CASES = [
     ("biped_walk_stairs", None, {}),
     ("go1_trot_flat", tb.SLOPE, dict(t_total=2.4)),
     ("anymal_trot_mixed", tb.CHIMNEY_LR, dict(goal_xy=(1.2, -0.2))),
+    ("anymal_trot_block_base_rom", None, {}),
+    ("hopper_base_rom", None, {}),
 ]
 
 

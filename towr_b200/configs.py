@@ -20,6 +20,11 @@ def _standing(f, robot, goal_xy=(1.0, 0.0), goal_yaw=0.0):
 
 
 def make_formulation(name, goal_xy=None, goal_yaw=0.0, terrain=None, t_total=2.0):
+    if name.endswith("_base_rom"):
+        # every Parameters::ConstraintName at once: the default list plus BaseRom (BaseMotionConstraint)
+        f = make_formulation(name[:-len("_base_rom")], goal_xy, goal_yaw, terrain, t_total)
+        f.params_.constraints_.insert(2, capi.C_BASE_ROM)
+        return f
     if name == "hopper":
         # towr/test/hopper_example.cc:47-68
         f = NlpFormulation(capi.MONOPED, capi.FLAT)

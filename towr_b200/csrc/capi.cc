@@ -64,12 +64,11 @@ struct twb_problem {
 struct twb_batch {
   const twb_problem* prob = nullptr;
   int B = 0, device = 0, n_sms = 148;
-  size_t ld = 0;                  // leading dimension (instances, padded to 32) of XT and ST
+  size_t ld = 0;                  // instances padded to a multiple of 32 (whole tiles of XT)
   twb::Plan plan{};
   std::vector<void*> owned;       // device allocations of the tables
   int* d_terrain = nullptr;       // per-instance terrain ids (optional)
-  double* d_XT = nullptr;         // [n+1][ld]   transposed iterates; row n == 0
-  double* d_ST = nullptr;         // [S_size][ld] state matrix; row 0 == 1
+  double* d_XT = nullptr;         // [ld/32][n+1][32] instance-tiled iterates; row n == 0
   // staging for the host-pointer variant
   double *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_cost = nullptr, *d_grad = nullptr;
   int* d_status = nullptr;
@@ -165,18 +164,16 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
     twb_batch_destroy(b);                                                              \
     return CudaFail(e, "table upload");                                                \
   }
-  TWB_UP(samples) TWB_UP(eval_items) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc) TWB_UP(cost)
-  TWB_UP(desc) TWB_UP(coef) TWB_UP(dyn_ang_basis) TWB_UP(dyn_info) TWB_UP(rom_info) TWB_UP(const_seg)
+  TWB_UP(samples) TWB_UP(dyn) TWB_UP(rom) TWB_UP(groups) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc)
+  TWB_UP(base_motion) TWB_UP(cost) TWB_UP(pairs) TWB_UP(coefs) TWB_UP(dyn_ang_basis)
 #undef TWB_UP
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
-  if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d S_size=%d\n", b->plan.n, b->plan.m, b->plan.nnz, b->plan.S_size);
+  if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
   b->ld = ((size_t)batch_size + 31) & ~(size_t)31;
   cudaDeviceGetAttribute(&b->n_sms, cudaDevAttrMultiProcessorCount, device);
   const size_t xt_bytes = (size_t)(b->plan.n + 1) * b->ld * sizeof(double);
-  const size_t st_bytes = (size_t)b->plan.S_size * b->ld * sizeof(double);
   if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_XT), xt_bytes)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&b->d_ST), st_bytes)) != cudaSuccess ||
-      (e = cudaMemset(b->d_XT, 0, xt_bytes)) != cudaSuccess || (e = cudaMemset(b->d_ST, 0, st_bytes)) != cudaSuccess) {
+      (e = cudaMemset(b->d_XT, 0, xt_bytes)) != cudaSuccess) {
     twb_batch_destroy(b);
     return CudaFail(e, "state allocation");
   }
@@ -200,7 +197,7 @@ void twb_batch_destroy(twb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   for (void* p : b->owned) cudaFree(p);
-  cudaFree(b->d_terrain); cudaFree(b->d_XT); cudaFree(b->d_ST);
+  cudaFree(b->d_terrain); cudaFree(b->d_XT);
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
@@ -226,10 +223,9 @@ int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   if (!b) return 0;
   const twb::Plan& p = b->plan;
   const bool want_cost = b->prob->f.has_cost && (flags & TWB_EVAL_COST);
-  int n = 1 + (p.n_eval_items > 0);
-  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += (p.n_dyn > 0) + (p.n_rom > 0);
-  n += ((p.n_force + p.n_terr + p.n_swing + p.n_acc + (want_cost ? 1 : 0)) > 0);
-  if ((flags & TWB_EVAL_JAC) && p.n_const_seg > 0) n += 1;
+  int n = 1;   // TransposeIn
+  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += (p.n_dyn > 0) + (p.n_rom > 0) + (p.n_groups > 0);
+  if (want_cost) n += 1;
   return n;
 }
 
@@ -244,7 +240,7 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   unsigned kflags = flags & (TWB_EVAL_G | TWB_EVAL_JAC);
   if (f.has_cost && (flags & TWB_EVAL_COST)) kflags |= TWB_EVAL_COST;
   int launches = 0;
-  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_ST, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
+  int rc = twb::LaunchEval(b->plan, x, b->d_XT, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
                            kflags, static_cast<cudaStream_t>(stream), b->aux0, b->aux1, b->ev.data(), &launches);
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
   b->launches_last = launches;

@@ -24,94 +24,83 @@ struct alignas(16) SplineSample {   // 96 bytes = six 16-byte loads
   int16_t pad[4];
 };
 
-// One spline-kernel work item: evaluate spline sample `sample` into state rows scratch..
-// kind 0: position (3 doubles); 1: position + acceleration (6); 2: position + velocity + acceleration (9)
-struct EvalItem {
-  int32_t sample;
-  int16_t scratch;
-  int16_t kind;
+// ---- output lists -------------------------------------------------------------
+// Every value a unit produces — a CSR Jacobian value or a constraint value — is
+//     out[instance][off + h] = state[d_h][instance] * c_h,     h = 0, 1
+// where `state` is the unit's local state block (row 0 holds the constant 1) and (off, off + 1) is a
+// 16-byte aligned pair of elements of the instance's output row, so that one lane issues one
+// 16-byte store per instance and a warp covers 512 contiguous bytes.  A half whose element belongs
+// to a neighbouring unit has d_h = kNoRow and is skipped.
+constexpr uint16_t kNoRow = 0xFFFFu;
+struct OutPair { int32_t off; uint16_t d0, d1; };       // off: element index of the pair's first half in the row (-1: first half precedes the row)
+struct alignas(16) OutCoef { double c0, c1; };
+// The pair lists of one unit.  When a row length (nnz or m) is odd, rows of odd instances start
+// 8 bytes off a 16-byte boundary, so those instances use a second list with the other pairing.
+struct OutList {
+  int32_t jac[2], n_jac[2];   // [parity of the instance]: first pair / number of pairs, Jacobian values
+  int32_t g[2], n_g[2];       // same for constraint values
 };
 
-// TerrainConstraint row (terrain_constraint.cc:59-108): one ee-motion node
-struct TerrainUnit {
-  int16_t xi[3];      // x index of node position x,y,z
-  int16_t pad;
-  int32_t g_row;      // constraint row
-  int32_t s0;         // first of the row's 3 CSR slots
-};
-
-// ForceConstraint node (force_constraint.cc:64-171): 5 rows
-struct ForceUnit {
-  int16_t xf[3];      // x index of the force node value
-  int16_t xp[3];      // x index of the stance-foot position (phase start node); [2] unused
-  int16_t pad[2];
-  int32_t g_row;      // first of the 5 rows
-  int32_t s0;         // first of the 25 CSR slots of these rows
-};
-
-// SwingConstraint node (swing_constraint.cc:57-83): 4 rows
-struct SwingUnit {
-  int16_t xc_p[2], xc_v[2];  // current node pos/vel x,y
-  int16_t xprev[2], xnext[2];
-  int32_t g_row;
-  int32_t pad;
-};
-
-// SplineAccConstraint junction (spline_acc_constraint.cc:49-65), fixed durations
+// TerrainConstraint row (terrain_constraint.cc:59-108): one ee-motion node.
+// local state: [base + 0] = -dh/dx, [base + 1] = -dh/dy, g at [g_base]
+struct TerrainUnit { int16_t xi[3]; int16_t pad; };
+// ForceConstraint node (force_constraint.cc:64-171): 5 rows.  local state: 25 values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
+struct ForceUnit { int16_t xf[3]; int16_t xp[3]; int16_t pad[2]; };
+// SwingConstraint node (swing_constraint.cc:57-83): 4 rows (values only; the Jacobian is constant)
+struct SwingUnit { int16_t xc_p[2], xc_v[2]; int16_t xprev[2], xnext[2]; };
+// SplineAccConstraint junction (spline_acc_constraint.cc:49-65), fixed durations (values only)
 struct AccUnit {
   double Tp, Tp2, Tp3, rTp2, rTp3;  // previous polynomial duration, pow 2, pow 3, reciprocals
   double Tn, Tn2, rTn2;             // next polynomial
   int32_t x0;           // x index of node j, dim 0 position (NodesVariablesAll layout)
-  int32_t g_row;        // first of 3 rows
+  int32_t pad;
 };
+// BaseMotionConstraint sample (base_motion_constraint.cc:56-66): values only, 6 rows
+struct BaseMotionUnit { int32_t sample_lin, sample_ang; };
 
-// CSR slot range and first constraint row of one dynamic sample (6 rows) / one RoM sample (3 rows per foot)
-struct DynInfo { int32_t s0, s1, g_row, pad; };
-struct RomInfo { int32_t s0[kMaxEE], s1[kMaxEE], g_row[kMaxEE]; };
-// run of CSR slots whose values do not depend on the iterate (SplineAcc, Swing rows): value = coef
-struct ConstSeg { int32_t s0, s1; };
+// A dynamic sample (6 rows): 2 + 2 n_ee spline samples starting at `sample0`
+// (base-lin, base-ang, ee-motion.., ee-force..) and its output lists.
+struct DynUnit { int32_t sample0; int32_t pad; OutList out; };
+// A range-of-motion sample (3 rows for every foot): 2 + n_ee spline samples (base-lin, base-ang, ee-motion..)
+struct RomUnit { int32_t sample0; int32_t pad; OutList out; };
+
+// Node-wise work of one warp: `count` consecutive units of one kind evaluated into one state block,
+// then one pass over the group's output lists.
+enum NodeKind : int32_t { kGroupForce = 0, kGroupTerrain = 1, kGroupSwing = 2, kGroupAcc = 3, kGroupConst = 4, kGroupBaseMotion = 5 };
+struct NodeGroup { int32_t kind, first, count, pad; OutList out; };
+constexpr int kNodeStateRows = 64;   // local state rows of a node group (row 0 = 1)
 
 // NodeCost term (node_cost.cc:53-76) flattened: one entry per node value that
 // enters the cost; var >= 0 when the value is an optimisation variable.
 struct CostEntry {
   int16_t xi;        // x index holding the node value (zero slot if fixed)
   int16_t grad_col;  // column of the gradient this node contributes to, or -1
-  int32_t pad;
+  int32_t pad;       // 1: first entry of a cost term
   double weight;
 };
 
-// Jacobian slot descriptor: value = S[desc] * coef
-
 struct Plan {
   int n, m, nnz, n_ee;
-  // sizes
-  int n_dyn, n_rom, n_terr, n_force, n_swing, n_acc, n_totdur, n_cost, n_eval_items, n_const_seg, n_const_runs;
-  int max_dyn_slots, max_rom_slots;   // largest number of CSR slots one dynamic / RoM sample owns
-  // g rows
-  int dyn_row0;
-  int rom_row0[kMaxEE];
-  int totdur_row0;
-  // rows of the spline-value matrix ST: per dynamic sample [c, c_dd, th, th_d, th_dd, p_e.., f_e..],
-  // per RoM sample [c, th, p_e..]
-  int S_size, S_dyn0, S_dyn_stride, S_rom0, S_rom_stride;
+  int n_dyn, n_rom, n_groups, n_cost;
+  int max_dyn_pairs, max_rom_pairs, max_group_pairs;   // longest output list (pairs, Jacobian + values) of a unit
   // robot
   double mass, gravity;
   double I_b[9];
   double mu;
   // tables (device pointers)
-  const SplineSample* samples;      // every (constraint sample, spline) pair of the dynamic and RoM sets
-  const EvalItem* eval_items;       // [n_eval_items]
+  const SplineSample* samples;
+  const DynUnit* dyn;
+  const RomUnit* rom;
+  const NodeGroup* groups;
   const TerrainUnit* terr;
   const ForceUnit* force;
   const SwingUnit* swing;
   const AccUnit* acc;
+  const BaseMotionUnit* base_motion;
   const CostEntry* cost;
   const double* dyn_ang_basis;  // [n_dyn][12]: base-ang basis of the active polynomial, {pos, vel, acc} x {p0, v0, p1, v1}
-  const uint32_t* desc;   // [nnz padded to even]  row of the slot's value in its unit's local state block (0 = the constant 1)
-  const double* coef;     // [nnz padded to even]  constant of every CSR slot
-  const DynInfo* dyn_info;   // [n_dyn]
-  const RomInfo* rom_info;   // [n_rom]
-  const ConstSeg* const_seg; // [n_const_seg]
+  const OutPair* pairs;
+  const OutCoef* coefs;
 };
 
 }  // namespace twb

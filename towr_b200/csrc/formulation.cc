@@ -173,7 +173,13 @@ std::vector<double> BasePolyDurations(double T, double dt) {  // parameters.cc:8
   return v;
 }
 
-struct Emit { int row, col; uint32_t a; double c0; };
+struct Emit { int row, col; uint32_t a; double c0; };   // a: local state row of the owning unit (0 = the constant 1)
+
+// Who computes a constraint row: a dynamic sample, a range-of-motion sample (all feet) or a node unit.
+enum OwnerKind { kOwnDyn, kOwnRom, kOwnNode };
+struct RowOwner { int kind = -1, index = -1; uint32_t g_local = 0; };   // g_local: state row of the row's value inside the unit
+// node unit before grouping: kind, index into its table, rows of local state / values it needs
+struct NodeUnitRef { int kind, index, n_state, n_g, set_id; };
 
 // sign/component of Cross(v)[i][d] (single_rigid_body_dynamics.cc:46-57): value = sign * v[comp]
 void CrossEntry(int i, int d, int* comp, double* sign) {
@@ -199,7 +205,6 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   optimize_timings = false;
   for (int i = 0; i < sp.n_constraints; ++i) {
     if (sp.constraints[i] == TWB_C_TOTAL_TIME) optimize_timings = true;  // parameters.cc:128-135
-    if (sp.constraints[i] == TWB_C_BASE_ROM) return fail(TWB_ERR_UNSUPPORTED, "BaseRom (BaseMotionConstraint) is not served by the device path yet");
     if (sp.constraints[i] < 0 || sp.constraints[i] > TWB_C_BASE_ACC) return fail(TWB_ERR_INVALID, "constraint not defined!");
   }
   if (optimize_timings) return fail(TWB_ERR_UNSUPPORTED, "phase-duration optimisation (PhaseSpline) is not served by the device path yet");
@@ -280,46 +285,57 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   std::vector<SplineDef> sp_motion, sp_force;
   for (int e = 0; e < n_ee; ++e) { sp_motion.push_back({&motion(e), poly_durations(motion(e), e)}); sp_force.push_back({&force(e), poly_durations(force(e), e)}); }
 
-  // ---- S layout
+  // ---- units and their Jacobian entries
   HostTables& tb = tables; tb = HostTables{};
   Plan& pl = tb.plan;
-  int S_top = 0;                 // rows of the spline-value matrix
   const uint32_t S_ONE = 0;      // local row 0 of every unit's state block is the constant 1
 
   std::vector<Emit> em;
   auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, c}); };
+  std::vector<RowOwner> owner;         // per constraint row
+  std::vector<NodeUnitRef> node_units; // node-wise units in row order
+  int set_counter = 0;
 
-  auto add_eval = [&](const SplineSample& s, uint32_t scratch, int kind) {
-    EvalItem it{}; it.sample = (int32_t)tb.samples.size(); it.scratch = (int16_t)scratch; it.kind = (int16_t)kind;
-    tb.samples.push_back(s); tb.eval_items.push_back(it);
-  };
   m = 0; con_sets.clear(); g_lower.clear(); g_upper.clear();
-  auto add_set = [&](const std::string& name, int rows) { con_sets.push_back({name, m, rows}); int r0 = m; m += rows; g_lower.resize(m, 0.0); g_upper.resize(m, 0.0); return r0; };
+  auto add_set = [&](const std::string& name, int rows) {
+    con_sets.push_back({name, m, rows}); int r0 = m; m += rows;
+    g_lower.resize(m, 0.0); g_upper.resize(m, 0.0); owner.resize(m); ++set_counter;
+    return r0;
+  };
   auto bound = [&](int row, double lo, double up) { g_lower[row] = lo; g_upper[row] = up; };
+  auto own = [&](int row, int kind, int index, uint32_t g_local) { owner[row].kind = kind; owner[row].index = index; owner[row].g_local = g_local; };
+  // node unit `index` of table `kind` owns `n_g` rows starting at `row`; returns its id
+  auto add_node_unit = [&](int kind, int index, int n_state, int n_g, int row) {
+    const int id = (int)node_units.size();
+    node_units.push_back({kind, index, n_state, n_g, set_counter});
+    for (int r = 0; r < n_g; ++r) own(row + r, kOwnNode, id, (uint32_t)r);
+    return id;
+  };
 
-  pl.n_dyn = pl.n_rom = 0; pl.totdur_row0 = -1; pl.dyn_row0 = -1;
-  for (int e = 0; e < kMaxEE; ++e) pl.rom_row0[e] = -1;
+  pl.n_dyn = pl.n_rom = 0;
+  bool have_dyn = false, have_rom = false, have_base_motion = false;
 
   for (int ci = 0; ci < sp.n_constraints; ++ci) {
     switch (sp.constraints[ci]) {
       case TWB_C_DYNAMIC: {  // dynamic_constraint.cc + single_rigid_body_dynamics.cc:103-192
-        if (pl.dyn_row0 >= 0) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
+        if (have_dyn) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
+        have_dyn = true;
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_dynamic);
         int r0 = add_set("dynamic", (int)ts.size() * 6);
-        pl.dyn_row0 = r0; pl.n_dyn = (int)ts.size();
-        pl.S_dyn_stride = 15 + 6 * n_ee; pl.S_dyn0 = S_top; S_top += pl.S_dyn_stride * pl.n_dyn;
+        pl.n_dyn = (int)ts.size();
+        const uint32_t G0 = 40 + 6 * n_ee;   // local state: [0]=1 | sum f (3) | base-ang block (36) | f_e, c-p_e (6 per foot) | g (6)
         for (int k = 0; k < pl.n_dyn; ++k) {
           const double t = ts[k];
           const int row = r0 + 6 * k;
-          const uint32_t gb = pl.S_dyn0 + k * pl.S_dyn_stride;  // spline values of this sample in ST
-          const uint32_t sb = 1;  // local state block: [0]=1 | sum f (3) | base-ang block (36) | f_e, c-p_e (6 per foot)
-          tb.dyn_info.push_back(DynInfo{0, 0, row, 0});
-          for (int r = 0; r < 6; ++r) bound(row + r, 0.0, 0.0);
-          // spline values: c, c_ddot | theta, theta_dot, theta_ddot | p_e.. | f_e..
-          add_eval(MakeSample(sp_lin, t, zero_slot), gb + 0, 1);
-          add_eval(MakeSample(sp_ang, t, zero_slot), gb + 6, 2);
-          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], t, zero_slot), gb + 15 + 3 * e, 0);
-          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_force[e], t, zero_slot), gb + 15 + 3 * n_ee + 3 * e, 0);
+          const uint32_t sb = 1;
+          DynUnit du{}; du.sample0 = (int32_t)tb.samples.size();
+          tb.dyn.push_back(du);
+          for (int r = 0; r < 6; ++r) { bound(row + r, 0.0, 0.0); own(row + r, kOwnDyn, k, G0 + r); }
+          // spline samples: base-lin, base-ang, ee-motion.., ee-force..
+          tb.samples.push_back(MakeSample(sp_lin, t, zero_slot));
+          tb.samples.push_back(MakeSample(sp_ang, t, zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(MakeSample(sp_motion[e], t, zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(MakeSample(sp_force[e], t, zero_slot));
           int p; double tl;
           // base-lin: angular rows = -sum_e [f_e]x dc ; linear rows = m * d(acc)
           Locate(sp_lin, t, &p, &tl);
@@ -365,34 +381,61 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         break;
       }
       case TWB_C_EE_ROM: {  // range_of_motion_constraint.cc
-        if (pl.n_rom) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
+        if (have_rom) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
+        have_rom = true;
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_range_of_motion);
         pl.n_rom = (int)ts.size();
-        pl.S_rom_stride = 6 + 3 * n_ee; pl.S_rom0 = S_top; S_top += pl.S_rom_stride * pl.n_rom;
-        for (int k = 0; k < pl.n_rom; ++k) {  // spline values: c | theta | p_e..
-          const uint32_t gb = pl.S_rom0 + k * pl.S_rom_stride;
-          add_eval(MakeSample(sp_lin, ts[k], zero_slot), gb + 0, 0);
-          add_eval(MakeSample(sp_ang, ts[k], zero_slot), gb + 3, 0);
-          for (int e = 0; e < n_ee; ++e) add_eval(MakeSample(sp_motion[e], ts[k], zero_slot), gb + 6 + 3 * e, 0);
-          tb.rom_info.push_back(RomInfo{});
+        const uint32_t G0 = 10 + 9 * n_ee;   // local state: [0]=1 | R^T (9) | D_e (9 per foot) | g (3 per foot)
+        for (int k = 0; k < pl.n_rom; ++k) {  // spline samples: base-lin, base-ang, ee-motion..
+          RomUnit ru{}; ru.sample0 = (int32_t)tb.samples.size();
+          tb.rom.push_back(ru);
+          tb.samples.push_back(MakeSample(sp_lin, ts[k], zero_slot));
+          tb.samples.push_back(MakeSample(sp_ang, ts[k], zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(MakeSample(sp_motion[e], ts[k], zero_slot));
         }
         for (int e = 0; e < n_ee; ++e) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
-          pl.rom_row0[e] = r0;
           for (int k = 0; k < pl.n_rom; ++k) {
             const double t = ts[k]; const int row = r0 + 3 * k;
-            const uint32_t sb = 1;  // local state block of (sample, foot): [0]=1 | R^T (9) | D_e (9)
-            tb.rom_info[k].g_row[e] = row;
-            for (int d = 0; d < 3; ++d) bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
+            const uint32_t sb = 1, sd = 10 + 9 * e;
+            for (int d = 0; d < 3; ++d) {
+              bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
+              own(row + d, kOwnRom, k, G0 + 3 * e + d);
+            }
             int p; double tl;
             Locate(sp_lin, t, &p, &tl);   // -R^T dc
             for (auto& b : Basis(sp_lin, p, tl, kPos)) for (int i = 0; i < 3; ++i) emit1(row + i, lin.offset + b.var, sb + i * 3 + b.dim, -b.val);
             Locate(sp_ang, t, &p, &tl);   // d(R^T r)/dtheta ; row X does not depend on roll
             for (auto& b : Basis(sp_ang, p, tl, kPos)) for (int i = 0; i < 3; ++i)
-              if (!(i == 0 && b.dim == 0)) emit1(row + i, ang.offset + b.var, sb + 9 + i * 3 + b.dim, b.val);
+              if (!(i == 0 && b.dim == 0)) emit1(row + i, ang.offset + b.var, sd + i * 3 + b.dim, b.val);
             Locate(sp_motion[e], t, &p, &tl);  // R^T dp_e
             for (auto& b : Basis(sp_motion[e], p, tl, kPos)) for (int i = 0; i < 3; ++i) emit1(row + i, motion(e).offset + b.var, sb + i * 3 + b.dim, b.val);
           }
+        }
+        break;
+      }
+      case TWB_C_BASE_ROM: {  // base_motion_constraint.cc:38-91
+        if (have_base_motion) return fail(TWB_ERR_UNSUPPORTED, "constraint listed twice");
+        have_base_motion = true;
+        std::vector<double> ts = SampleTimes(T, sp.dt_constraint_base_motion);
+        int r0 = add_set("baseMotion", (int)ts.size() * 6);
+        const double dev_rad = 0.05;
+        // z_init = base_linear_->GetPoint(0.0).p().z() at construction (:51): polynomial 0 of the initial guess at t = 0
+        const double z_init = lin.x0[lin.Var(0, kPos, Z)];
+        for (int k = 0; k < (int)ts.size(); ++k) {
+          const int row = r0 + 6 * k;   // rows AX, AY, AZ, LX, LY, LZ
+          BaseMotionUnit u{}; u.sample_lin = (int32_t)tb.samples.size(); u.sample_ang = u.sample_lin + 1;
+          tb.samples.push_back(MakeSample(sp_lin, ts[k], zero_slot));
+          tb.samples.push_back(MakeSample(sp_ang, ts[k], zero_slot));
+          tb.base_motion.push_back(u);
+          add_node_unit(kGroupBaseMotion, (int)tb.base_motion.size() - 1, 0, 6, row);
+          bound(row + 0, -dev_rad, dev_rad); bound(row + 1, -dev_rad, dev_rad); bound(row + 2, -kInf, +kInf);
+          bound(row + 3, -kInf, +kInf); bound(row + 4, -kInf, +kInf); bound(row + 5, z_init - 0.02, z_init + 0.1);
+          int p; double tl;
+          Locate(sp_ang, ts[k], &p, &tl);
+          for (auto& b : Basis(sp_ang, p, tl, kPos)) emit1(row + b.dim, ang.offset + b.var, S_ONE, b.val);
+          Locate(sp_lin, ts[k], &p, &tl);
+          for (auto& b : Basis(sp_lin, p, tl, kPos)) emit1(row + 3 + b.dim, lin.offset + b.var, S_ONE, b.val);
         }
         break;
       }
@@ -404,8 +447,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int row = r0 + nd - 1;
             if (mo.ConstNode(nd)) bound(row, 0.0, 0.0); else bound(row, 0.0, 1e20);
             TerrainUnit u{}; for (int d = 0; d < 3; ++d) u.xi[d] = XIndex(mo, nd, kPos, d, zero_slot);
-            u.g_row = row; u.s0 = -1;   // local state block: [0]=1 | -dh/dx | -dh/dy
             tb.terr.push_back(u);
+            add_node_unit(kGroupTerrain, (int)tb.terr.size() - 1, 2, 1, row);   // unit state: -dh/dx | -dh/dy
             emit1(row, mo.offset + mo.Var(nd, kPos, X), 1, 1.0);
             emit1(row, mo.offset + mo.Var(nd, kPos, Y), 2, 1.0);
             emit1(row, mo.offset + mo.Var(nd, kPos, Z), S_ONE, 1.0);
@@ -425,8 +468,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             int mnode = 0; for (int i = 0; i < (int)mo.poly.size(); ++i) if (mo.poly[i].phase == phase) { mnode = i; break; }
             ForceUnit u{};
             for (int d = 0; d < 3; ++d) { u.xf[d] = XIndex(fo, nd, kPos, d, zero_slot); u.xp[d] = XIndex(mo, mnode, kPos, d, zero_slot); }
-            u.g_row = row; u.s0 = -1;   // local state block: [0]=1 | 25 values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
             tb.force.push_back(u);
+            add_node_unit(kGroupForce, (int)tb.force.size() - 1, 25, 5, row);   // unit state: 25 values [row][{d/dpx,d/dpy,d/dfx,d/dfy,d/dfz}]
             bound(row + 0, 0.0, sp.force_limit_in_normal_direction);
             bound(row + 1, -kInf, 0.0); bound(row + 2, 0.0, +kInf); bound(row + 3, -kInf, 0.0); bound(row + 4, 0.0, +kInf);
             for (int r = 0; r < 5; ++r) {
@@ -452,7 +495,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
               u.xc_p[d] = XIndex(mo, nd, kPos, d, zero_slot); u.xc_v[d] = XIndex(mo, nd, kVel, d, zero_slot);
               u.xprev[d] = XIndex(mo, nd - 1, kPos, d, zero_slot); u.xnext[d] = XIndex(mo, nd + 1, kPos, d, zero_slot);
             }
-            u.g_row = row; tb.swing.push_back(u);
+            tb.swing.push_back(u);
+            add_node_unit(kGroupSwing, (int)tb.swing.size() - 1, 0, 4, row);
             for (int d = 0; d < 2; ++d) {
               bound(row, 0.0, 0.0);
               emit1(row, mo.offset + mo.Var(nd, kPos, d), S_ONE, 1.0);
@@ -479,8 +523,9 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             AccUnit u{};
             u.Tp = s.T[j]; u.Tp2 = std::pow(u.Tp, 2); u.Tp3 = std::pow(u.Tp, 3); u.rTp2 = 1.0 / u.Tp2; u.rTp3 = 1.0 / u.Tp3;
             u.Tn = s.T[j + 1]; u.Tn2 = std::pow(u.Tn, 2); u.rTn2 = 1.0 / u.Tn2;
-            u.x0 = ns.offset + j * 6; u.g_row = r0 + 3 * j;
+            u.x0 = ns.offset + j * 6;
             tb.acc.push_back(u);
+            add_node_unit(kGroupAcc, (int)tb.acc.size() - 1, 0, 3, r0 + 3 * j);
             // acc_prev - acc_next with the union of both patterns (:67-80)
             std::map<int, std::pair<int, double>> u_map;  // var -> (dim, value)
             for (auto& b : Basis(s, j, s.T[j], kAcc)) u_map[b.var] = {b.dim, b.val};
@@ -497,8 +542,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
       default: return fail(TWB_ERR_INVALID, "constraint not defined!");
     }
   }
-  if (S_top > 32767) return fail(TWB_ERR_UNSUPPORTED, "spline-value matrix too large");
-  pl.S_size = std::max(S_top, 1);
+  if (tb.samples.size() > 0x7FFFFFFFu) return fail(TWB_ERR_UNSUPPORTED, "too many spline samples");
 
   // ---- CSR assembly: row-major, ascending column (what setFromTriplets yields)
   std::stable_sort(em.begin(), em.end(), [](const Emit& a, const Emit& b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
@@ -506,27 +550,87 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     if (em[i].row == em[i - 1].row && em[i].col == em[i - 1].col) return fail(TWB_ERR_UNSUPPORTED, "duplicate Jacobian entry emitted");
   nnz = (int)em.size();
   row_ptr.assign(m + 1, 0); col_idx.resize(nnz);
-  tb.desc.assign((nnz + 1) & ~1, 0u); tb.coef.assign((nnz + 1) & ~1, 0.0);
-  for (int s = 0; s < nnz; ++s) {
-    row_ptr[em[s].row + 1]++; col_idx[s] = em[s].col;
-    tb.desc[s] = em[s].a;
-    tb.coef[s] = em[s].c0;
-  }
+  for (int s = 0; s < nnz; ++s) { row_ptr[em[s].row + 1]++; col_idx[s] = em[s].col; }
   for (int r = 0; r < m; ++r) row_ptr[r + 1] += row_ptr[r];
-  // CSR slot ranges of the units (their rows are consecutive, so each range is contiguous)
-  for (auto& u : tb.dyn_info) { u.s0 = row_ptr[u.g_row]; u.s1 = row_ptr[u.g_row + 6]; }
-  for (auto& u : tb.rom_info) for (int e = 0; e < n_ee; ++e) { u.s0[e] = row_ptr[u.g_row[e]]; u.s1[e] = row_ptr[u.g_row[e] + 3]; }
-  for (auto& u : tb.terr) { u.s0 = row_ptr[u.g_row]; if (row_ptr[u.g_row + 1] - u.s0 != 3) return fail(TWB_ERR_UNSUPPORTED, "terrain row layout"); }
-  for (auto& u : tb.force) { u.s0 = row_ptr[u.g_row]; if (row_ptr[u.g_row + 5] - u.s0 != 25) return fail(TWB_ERR_UNSUPPORTED, "force row layout"); }
-  for (auto& cs : con_sets)   // iterate-independent rows: SplineAcc and Swing
-    if (cs.name.rfind("splineacc-", 0) == 0 || cs.name.rfind("swing-", 0) == 0) {
-      const int s0 = row_ptr[cs.start], s1 = row_ptr[cs.start + cs.count];
-      if (s1 > s0) {
-        if (!tb.const_seg.empty() && tb.const_seg.back().s1 == s0) tb.const_seg.back().s1 = s1;
-        else tb.const_seg.push_back(ConstSeg{s0, s1});
-      }
+
+  // ---- node groups: consecutive units of one kind and one constraint set share a warp's state block
+  struct GroupBuild { int kind, first, count; std::vector<int> unit_ids; };
+  std::vector<GroupBuild> groups;
+  std::vector<int> unit_group(node_units.size(), -1), unit_state0(node_units.size(), 0), unit_g0(node_units.size(), 0);
+  {
+    auto cap = [](int kind) { return kind == kGroupForce ? 2 : kind == kGroupTerrain ? 12 : kind == kGroupSwing ? 8 : kind == kGroupAcc ? 8 : 8; };
+    for (size_t u = 0; u < node_units.size(); ++u) {
+      const NodeUnitRef& nu = node_units[u];
+      bool open = !groups.empty() && groups.back().kind == nu.kind && groups.back().count < cap(nu.kind) &&
+                  node_units[groups.back().unit_ids.back()].set_id == nu.set_id && groups.back().first + groups.back().count == nu.index;
+      if (!open) groups.push_back({nu.kind, nu.index, 0, {}});
+      groups.back().count++; groups.back().unit_ids.push_back((int)u);
+      unit_group[u] = (int)groups.size() - 1;
     }
-  for (auto& cs : tb.const_seg) for (int s = cs.s0; s < cs.s1; ++s) if (tb.desc[s] != S_ONE) return fail(TWB_ERR_UNSUPPORTED, "constant segment layout");
+    for (auto& gb : groups) {   // state block: [0]=1 | unit states | unit values
+      int top = 1;
+      for (int u : gb.unit_ids) { unit_state0[u] = top; top += node_units[u].n_state; }
+      for (int u : gb.unit_ids) { unit_g0[u] = top; top += node_units[u].n_g; }
+      if (top > kNodeStateRows) return fail(TWB_ERR_UNSUPPORTED, "node group state block too large");
+    }
+  }
+
+  // ---- output lists: every unit writes the Jacobian values and constraint values of the rows it owns
+  struct OutItem { int off; uint16_t d; double c; };
+  auto block_of = [&](const RowOwner& o) -> std::pair<int, int> {   // (block kind, block index)
+    if (o.kind == kOwnNode) return {kOwnNode, unit_group[o.index]};
+    return {o.kind, o.index};
+  };
+  std::vector<std::vector<OutItem>> jac_items[3], g_items[3];
+  jac_items[kOwnDyn].resize(pl.n_dyn); g_items[kOwnDyn].resize(pl.n_dyn);
+  jac_items[kOwnRom].resize(pl.n_rom); g_items[kOwnRom].resize(pl.n_rom);
+  jac_items[kOwnNode].resize(groups.size()); g_items[kOwnNode].resize(groups.size());
+  for (int r = 0; r < m; ++r) {
+    const RowOwner& o = owner[r];
+    if (o.kind < 0) return fail(TWB_ERR_UNSUPPORTED, "constraint row without an owner");
+    auto blk = block_of(o);
+    uint32_t g_row = o.g_local, state0 = 1;
+    if (o.kind == kOwnNode) { g_row = unit_g0[o.index] + o.g_local; state0 = unit_state0[o.index]; }
+    if (g_row >= kNoRow) return fail(TWB_ERR_UNSUPPORTED, "state block too large");
+    g_items[blk.first][blk.second].push_back({r, (uint16_t)g_row, 1.0});
+    for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) {
+      uint32_t a = em[s].a;
+      if (o.kind == kOwnNode && a != S_ONE) a = state0 + (a - 1);
+      jac_items[blk.first][blk.second].push_back({s, (uint16_t)a, em[s].c0});
+    }
+  }
+  // pairs of 16-byte aligned elements; `parity` = parity of the instance's row start (odd row length, odd instance)
+  auto make_pairs = [&](const std::vector<OutItem>& items, int parity, int32_t* first, int32_t* count) {
+    *first = (int32_t)tb.pairs.size();
+    size_t i = 0;
+    while (i < items.size()) {
+      const int key = (items[i].off + parity) >> 1;
+      OutPair pr{key * 2 - parity, kNoRow, kNoRow}; OutCoef cf{0.0, 0.0};
+      while (i < items.size() && ((items[i].off + parity) >> 1) == key) {
+        if (((items[i].off + parity) & 1) == 0) { pr.d0 = items[i].d; cf.c0 = items[i].c; } else { pr.d1 = items[i].d; cf.c1 = items[i].c; }
+        ++i;
+      }
+      tb.pairs.push_back(pr); tb.coefs.push_back(cf);
+    }
+    *count = (int32_t)tb.pairs.size() - *first;
+  };
+  auto make_list = [&](std::vector<OutItem>& jac, std::vector<OutItem>& g, OutList* out, int* max_pairs) {
+    auto by_off = [](const OutItem& a, const OutItem& b) { return a.off < b.off; };
+    std::sort(jac.begin(), jac.end(), by_off); std::sort(g.begin(), g.end(), by_off);
+    make_pairs(jac, 0, &out->jac[0], &out->n_jac[0]);
+    if (nnz & 1) make_pairs(jac, 1, &out->jac[1], &out->n_jac[1]); else { out->jac[1] = out->jac[0]; out->n_jac[1] = out->n_jac[0]; }
+    make_pairs(g, 0, &out->g[0], &out->n_g[0]);
+    if (m & 1) make_pairs(g, 1, &out->g[1], &out->n_g[1]); else { out->g[1] = out->g[0]; out->n_g[1] = out->n_g[0]; }
+    *max_pairs = std::max(*max_pairs, std::max(out->n_jac[0], out->n_jac[1]) + std::max(out->n_g[0], out->n_g[1]));
+  };
+  pl.max_dyn_pairs = pl.max_rom_pairs = pl.max_group_pairs = 0;
+  for (int k = 0; k < pl.n_dyn; ++k) make_list(jac_items[kOwnDyn][k], g_items[kOwnDyn][k], &tb.dyn[k].out, &pl.max_dyn_pairs);
+  for (int k = 0; k < pl.n_rom; ++k) make_list(jac_items[kOwnRom][k], g_items[kOwnRom][k], &tb.rom[k].out, &pl.max_rom_pairs);
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    NodeGroup ng{}; ng.kind = groups[gi].kind; ng.first = groups[gi].first; ng.count = groups[gi].count;
+    make_list(jac_items[kOwnNode][gi], g_items[kOwnNode][gi], &ng.out, &pl.max_group_pairs);
+    tb.groups.push_back(ng);
+  }
 
   // ---- costs (nlp_formulation.cc:333-376, node_cost.cc:53-76)
   has_cost = false;
@@ -548,11 +652,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
 
   // ---- plan scalars
   pl.n = n; pl.m = m; pl.nnz = nnz; pl.n_ee = n_ee;
-  pl.n_terr = (int)tb.terr.size(); pl.n_force = (int)tb.force.size(); pl.n_swing = (int)tb.swing.size();
-  pl.n_acc = (int)tb.acc.size(); pl.n_totdur = 0; pl.n_cost = (int)tb.cost.size(); pl.n_eval_items = (int)tb.eval_items.size(); pl.n_const_seg = (int)tb.const_seg.size();
-  pl.n_const_runs = 0; for (auto& cs : tb.const_seg) pl.n_const_runs += (cs.s1 - cs.s0 + 31) / 32;
-  pl.max_dyn_slots = 0; for (auto& u : tb.dyn_info) pl.max_dyn_slots = std::max(pl.max_dyn_slots, u.s1 - u.s0);
-  pl.max_rom_slots = 0; for (auto& u : tb.rom_info) for (int e = 0; e < n_ee; ++e) pl.max_rom_slots = std::max(pl.max_rom_slots, u.s1[e] - u.s0[e]);
+  pl.n_groups = (int)tb.groups.size(); pl.n_cost = (int)tb.cost.size();
   pl.mass = rb.mass; pl.gravity = 9.80665;  // dynamic_model.cc:37
   const double* I = rb.inertia;             // single_rigid_body_dynamics.cc:36-44
   double Ib[9] = {I[0], -I[3], -I[4], -I[3], I[1], -I[5], -I[4], -I[5], I[2]};

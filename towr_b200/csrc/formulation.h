@@ -34,17 +34,18 @@ struct Component { std::string name; int start; int count; };
 struct HostTables {
   Plan plan{};  // pointer members are filled in after upload
   std::vector<SplineSample> samples;
-  std::vector<EvalItem> eval_items;
+  std::vector<DynUnit> dyn;
+  std::vector<RomUnit> rom;
+  std::vector<NodeGroup> groups;
   std::vector<TerrainUnit> terr;
   std::vector<ForceUnit> force;
   std::vector<SwingUnit> swing;
   std::vector<AccUnit> acc;
+  std::vector<BaseMotionUnit> base_motion;
   std::vector<CostEntry> cost;
-  std::vector<uint32_t> desc;
-  std::vector<DynInfo> dyn_info;
-  std::vector<RomInfo> rom_info;
-  std::vector<ConstSeg> const_seg;
-  std::vector<double> coef, dyn_ang_basis;
+  std::vector<OutPair> pairs;
+  std::vector<OutCoef> coefs;
+  std::vector<double> dyn_ang_basis;
 };
 
 class Formulation {

@@ -1,23 +1,24 @@
 // kernels.cu — sm_100a kernels of the batched NLP evaluation (fp64).
 //
-// Everything is a data-parallel map with LANE = PROBLEM INSTANCE.  All per-iterate
-// intermediates live in instance-tiled matrices [tile][rows][32] (tile = 32 consecutive instances,
-// lane = instance), so every global access of every kernel is a 256-byte row segment:
+// Everything is a data-parallel map with LANE = PROBLEM INSTANCE.  The iterates are first brought into
+// an instance-tiled matrix XT[tile][n+1][32] (tile = 32 consecutive instances, lane = instance), so that
+// every read of a node value by a warp is one 256-byte row segment:
 //
 //   TransposeIn   x[B][n]   -> XT[tile][n+1][32]   (row n stays 0: "not optimised" node values)
-//   SplineKernel  XT        -> ST[tile][S_size][32] (every spline value every constraint sample needs)
-//   DynOut        ST        -> g rows + CSR values of the dynamic constraint
-//   RomOut        ST        -> g rows + CSR values of the range-of-motion constraints
-//   NodeOut       XT        -> g rows + CSR values of terrain / force rows, g of swing / spline-acc, cost
-//   ConstOut                -> CSR values of the iterate-independent rows (spline-acc, swing)
+//   DynOut        XT        -> g rows + CSR values of the dynamic constraint          (warp = sample x tile)
+//   RomOut        XT        -> g rows + CSR values of the range-of-motion constraints (warp = sample x tile, all feet)
+//   NodeOut       XT        -> g rows + CSR values of the node-wise sets: terrain, force, swing, spline-acc,
+//                              base-motion (warp = group of consecutive nodes x tile)
+//   CostKernel    XT        -> cost + gradient (only when the formulation has cost terms)
 //
-// In the *Out kernels a warp owns one unit (a time sample or a node) of 32 instances: each lane
-// computes its instance's unit state into a padded shared-memory block (row = state slot, column =
-// lane), the warp synchronises, and then the lanes switch roles — lane = CSR slot — and stream
-// value = state[desc[slot]][instance] * coef[slot] for the 32 instances, so that every store
-// instruction covers 256 contiguous bytes of one instance's CSR value array (the unit's rows are
-// consecutive CSR rows).  The state never leaves the SM; HBM sees x once, the spline values once
-// (L2-resident), and g / jac exactly once.  The Out kernels are independent and run on separate streams.
+// In the *Out kernels a warp owns one unit of 32 instances: each lane evaluates the splines its unit
+// needs (reference operation order), computes its instance's unit state into a padded shared-memory
+// block (row = state slot, column = lane), the warp synchronises, and then the lanes switch roles —
+// lane = 16-byte pair of output elements — and stream
+//     out[instance][off + h] = state[d_h][instance] * c_h
+// for the 32 instances, so that every store instruction covers 512 contiguous bytes of one instance's
+// CSR value array (a unit's rows are consecutive CSR rows).  The state never leaves the SM; HBM sees x
+// once and g / jac exactly once.  The Out kernels are independent and run on separate streams.
 //
 // Reference math restated per device function (file:line cited there).  This translation unit is
 // compiled with -fmad=false: plain * and + round like the reference's scalar C++; fused
@@ -31,32 +32,35 @@
 #include "device_tables.h"
 #include "launch.h"
 
-#include <cstdint>
-
 namespace twb {
+void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // profiling hook (capi.cc, TWB_PROFILE=1)
+#define TWB_MARK(label, stream) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
 namespace {
 
-constexpr int kThreads = 256;
-#ifndef TWB_ROM_CTAS
-#define TWB_ROM_CTAS 2
+#ifndef TWB_DYN_WARPS
+#define TWB_DYN_WARPS 4
 #endif
 #ifndef TWB_DYN_CTAS
-#define TWB_DYN_CTAS 1
+#define TWB_DYN_CTAS 2
 #endif
+#ifndef TWB_ROM_WARPS
+#define TWB_ROM_WARPS 4
+#endif
+#ifndef TWB_ROM_CTAS
+#define TWB_ROM_CTAS 3
+#endif
+#ifndef TWB_NODE_WARPS
+#define TWB_NODE_WARPS 4
+#endif
+constexpr int kDynWarps = TWB_DYN_WARPS;     // consecutive samples per CTA of DynOut (one instance tile)
+constexpr int kRomWarps = TWB_ROM_WARPS;     // consecutive samples per CTA of RomOut
+constexpr int kNodeWarps = TWB_NODE_WARPS;   // consecutive node groups per CTA of NodeOut
+constexpr int kLD = 34;                      // leading dimension of a state block: 32 instances, padded; even keeps rows 16-byte aligned
 
-// output stores: TWB_STORE_MODE 0 = default write-back, 1 = streaming (evict-first), 2 = write-through
-#ifndef TWB_STORE_MODE
-#define TWB_STORE_MODE 1
-#endif
-template <class T>
-__device__ __forceinline__ void StoreOut(T* p, T v) {
-#if TWB_STORE_MODE == 1
-  __stcs(p, v);
-#elif TWB_STORE_MODE == 2
-  __stwt(p, v);
-#else
-  *p = v;
-#endif
+// output stores: streaming (evict-first) — the values are consumed by the host / a solver, not by these kernels
+__device__ __forceinline__ void StoreOut(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void StoreOut2(double* p, double a, double b) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
 // column `b` of a row-major [rows][ld] matrix: element r lives at p[r * ld]
@@ -64,7 +68,10 @@ struct Col {
   double* p;
   size_t ld;
   __device__ __forceinline__ double& operator[](int r) const { return p[(size_t)r * ld]; }
-  __device__ __forceinline__ Col at(int r) const { return Col{p + (size_t)r * ld, ld}; }
+};
+struct ConstCol {
+  const double* __restrict__ p;
+  __device__ __forceinline__ double operator[](int r) const { return __ldg(p + (size_t)r * 32); }
 };
 
 // ---- cubic Hermite evaluation ------------------------------------------------
@@ -82,7 +89,6 @@ __device__ __forceinline__ double DivExact(double a, double b, double y) {
 // Polynomial::GetPoint (polynomial.cc:47-61): sum_c d^k/dt^k(t^c) * coeff_c, c = A..D, in the
 // reference's operation order (this translation unit is compiled with -fmad=false, so the
 // products and sums below round exactly like the reference's scalar code).
-// kind 0: position; 1: position + acceleration; 2: position + velocity + acceleration.
 struct SampleRegs { double T, T2, T3, rT2, rT3, t, t2, t3; int xi[12]; };
 __device__ __forceinline__ SampleRegs LoadSample(const SplineSample* __restrict__ p) {
   const double2* d = reinterpret_cast<const double2*>(p);
@@ -96,18 +102,18 @@ __device__ __forceinline__ SampleRegs LoadSample(const SplineSample* __restrict_
   for (int i = 0; i < 6; ++i) { r.xi[2 * i] = (int)(v[i] & 0xFFFFu); r.xi[2 * i + 1] = (int)(v[i] >> 16); }
   return r;
 }
-__device__ __forceinline__ void EvalSplineToState(const SampleRegs& s, int kind, const Col xs, const Col out) {
+// kWant: 0 position; 1 position + acceleration; 2 position + velocity + acceleration
+template <int kWant>
+__device__ __forceinline__ void EvalSpline(const SplineSample* __restrict__ sp, const ConstCol xs, double pos[3], double vel[3], double acc[3]) {
+  const SampleRegs s = LoadSample(sp);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[s.xi[d]], v0 = xs[s.xi[3 + d]], p1 = xs[s.xi[6 + d]], v1 = xs[s.xi[9 + d]];
     const double C = DivExact(-(3 * (p0 - p1) + s.T * (2 * v0 + v1)), s.T2, s.rT2);
     const double D = DivExact(2 * (p0 - p1) + s.T * (v0 + v1), s.T3, s.rT3);
-    out[d] = ((p0 + s.t * v0) + s.t2 * C) + s.t3 * D;
-    if (kind == 1) out[3 + d] = 2 * C + (6 * s.t) * D;
-    if (kind == 2) {
-      out[3 + d] = (v0 + (2 * s.t) * C) + (3 * s.t2) * D;
-      out[6 + d] = 2 * C + (6 * s.t) * D;
-    }
+    pos[d] = ((p0 + s.t * v0) + s.t2 * C) + s.t3 * D;
+    if (kWant == 2) vel[d] = (v0 + (2 * s.t) * C) + (3 * s.t2) * D;
+    if (kWant >= 1) acc[d] = 2 * C + (6 * s.t) * D;
   }
 }
 
@@ -179,19 +185,30 @@ __device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3]
 //   EulerConverter::GetDerivOfAng{Vel,Acc}WrtEulerNodes (euler_converter.cc:85-131),
 //   GetDerivMwrtNodes (:168-198), GetDerivMdotwrtNodes (:270-304);
 //   sum of forces, per-foot force and lever arm for the other blocks (:103-121, :167-192).
-// in: spline values of the sample (global); Sk: local state rows 1.. (Sk[0..2] sum f, Sk[3..38] base-ang
-// block, Sk[39 + 6e ..] f_e, c - p_e); gk: the 6 constraint values
-__device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col in, const Col Sk, const Col gk) {
-  const int n_ee = P.n_ee;
-  double c[3], cdd[3], th[3], thd[3], thdd[3], pe[kMaxEE][3], fe[kMaxEE][3];
+// Sk: local state rows 1.. (Sk[0..2] sum f, Sk[3..38] base-ang block, Sk[39 + 6e ..] f_e, c - p_e);
+// gk: the 6 constraint values
+template <int kNEE>
+__device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSample* __restrict__ sp, const ConstCol xs,
+                                            const Col Sk, const Col gk) {
+  double c[3], cdd[3], th[3], thd[3], thdd[3], unused[3];
+  EvalSpline<1>(sp + 0, xs, c, unused, cdd);
+  EvalSpline<2>(sp + 1, xs, th, thd, thdd);
+
+  // feet
+  double fsum[3] = {0, 0, 0}, tau[3] = {0, 0, 0};
 #pragma unroll
-  for (int d = 0; d < 3; ++d) { c[d] = in[d]; cdd[d] = in[3 + d]; th[d] = in[6 + d]; thd[d] = in[9 + d]; thdd[d] = in[12 + d]; }
+  for (int e = 0; e < kNEE; ++e) {
+    double pe[3], f[3];
+    EvalSpline<0>(sp + 2 + e, xs, pe, unused, unused);
+    EvalSpline<0>(sp + 2 + kNEE + e, xs, f, unused, unused);
+    const double r[3] = {c[0] - pe[0], c[1] - pe[1], c[2] - pe[2]};
+    tau[0] += f[1] * r[2] - f[2] * r[1];
+    tau[1] += f[2] * r[0] - f[0] * r[2];
+    tau[2] += f[0] * r[1] - f[1] * r[0];
 #pragma unroll
-  for (int e = 0; e < kMaxEE; ++e)
-    if (e < n_ee) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) { pe[e][d] = in[15 + 3 * e + d]; fe[e][d] = in[15 + 3 * n_ee + 3 * e + d]; }
-    }
+    for (int d = 0; d < 3; ++d) { fsum[d] += f[d]; Sk[39 + e * 6 + d] = f[d]; Sk[39 + e * 6 + 3 + d] = r[d]; }
+  }
+  Sk[0] = fsum[0]; Sk[1] = fsum[1]; Sk[2] = fsum[2];
 
   const Trig tr = MakeTrig(th);
   const double sy = tr.sy, cy = tr.cy, sz = tr.sz, cz = tr.cz;
@@ -215,21 +232,6 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col in, 
 #pragma unroll
     for (int j = 0; j < 3; ++j) { Ib[i][j] = P.I_b[i * 3 + j]; Rt[i][j] = R[j][i]; }
   Mul33(R, Ib, RIb); Mul33(RIb, Rt, Iw);
-
-  // feet
-  double fsum[3] = {0, 0, 0}, tau[3] = {0, 0, 0};
-#pragma unroll
-  for (int e = 0; e < kMaxEE; ++e) {
-    if (e >= n_ee) break;
-    const double* f = fe[e];
-    const double r[3] = {c[0] - pe[e][0], c[1] - pe[e][1], c[2] - pe[e][2]};
-    tau[0] += f[1] * r[2] - f[2] * r[1];
-    tau[1] += f[2] * r[0] - f[0] * r[2];
-    tau[2] += f[0] * r[1] - f[1] * r[0];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { fsum[d] += f[d]; Sk[39 + e * 6 + d] = f[d]; Sk[39 + e * 6 + 3 + d] = r[d]; }
-  }
-  Sk[0] = fsum[0]; Sk[1] = fsum[1]; Sk[2] = fsum[2];
 
   double Iw_om[3], Iw_omd[3];
   MulVec(Iw, om, Iw_om); MulVec(Iw, omd, Iw_omd);
@@ -309,14 +311,15 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const Col in, 
 }
 
 // ---- RangeOfMotionConstraint sample (all feet) --------------------------------
-// range_of_motion_constraint.cc:58-109: g = R^T (p_ee - c); Jacobian state R^T and
-// D_e = d(R^T r_e)/d(theta) (DerivOfRotVecMult(t, r_W, true)).
-// One foot at one sample.  in: spline values of the sample (global); Sk: local state rows 1..
-// (Sk[0..8] R^T, Sk[9..17] D_e); gk: the foot's 3 constraint values
-__device__ __forceinline__ void RomUnit(const Plan& P, int e, const Col in, const Col Sk, const Col gk) {
-  double c[3], th[3], pe[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) { c[d] = in[d]; th[d] = in[3 + d]; pe[d] = in[6 + 3 * e + d]; }
+// range_of_motion_constraint.cc:58-109: g_e = R^T (p_e - c); Jacobian state R^T and
+// D_e = d(R^T r_e)/d(theta) (DerivOfRotVecMult(t, r_W, true)).  The rotation and its derivative are
+// computed once per sample and shared by the feet.
+// Sk: local state rows 1.. (Sk[0..8] R^T, Sk[9 + 9e ..] D_e); gk: 3 constraint values per foot
+template <int kNEE>
+__device__ __forceinline__ void RomUnitEval(const SplineSample* __restrict__ sp, const ConstCol xs, const Col Sk, const Col gk) {
+  double c[3], th[3], unused[3];
+  EvalSpline<0>(sp + 0, xs, c, unused, unused);
+  EvalSpline<0>(sp + 1, xs, th, unused, unused);
   const Trig tr = MakeTrig(th);
   double R[3][3]; RotationMatrix(tr, R);
   double dR[3][3][3]; RotationDerivative(tr, dR);
@@ -324,14 +327,19 @@ __device__ __forceinline__ void RomUnit(const Plan& P, int e, const Col in, cons
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int d = 0; d < 3; ++d) Sk[i * 3 + d] = R[d][i];
-  const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
 #pragma unroll
-  for (int i = 0; i < 3; ++i) gk[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
-  double D[3][3]; RotVecDerivative<true>(dR, r, D);
+  for (int e = 0; e < kNEE; ++e) {
+    double pe[3];
+    EvalSpline<0>(sp + 2 + e, xs, pe, unused, unused);
+    const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) gk[3 * e + i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
+    double D[3][3]; RotVecDerivative<true>(dR, r, D);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) Sk[9 + i * 3 + d] = D[i][d];
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Sk[9 + 9 * e + i * 3 + d] = D[i][d];
+  }
 }
 
 // ---- analytic terrains: height_map_examples.cc:35-211 ------------------------
@@ -372,9 +380,8 @@ __device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) 
   return o;
 }
 
-// TerrainConstraint, terrain_constraint.cc:59-108
-// Sk: local state rows 1.. ({-dh/dx, -dh/dy}); gk: the constraint value
-__device__ __forceinline__ void TerrainUnitEval(const TerrainUnit& u, int terrain, const Col xs, const Col Sk, const Col gk) {
+// TerrainConstraint, terrain_constraint.cc:59-108.  Sk: {-dh/dx, -dh/dy}; gk: the constraint value
+__device__ __forceinline__ void TerrainUnitEval(const TerrainUnit& u, int terrain, const ConstCol xs, const Col Sk, const Col gk) {
   const double px = xs[u.xi[0]], py = xs[u.xi[1]], pz = xs[u.xi[2]];
   const TerrainPoint tp = EvalTerrain(terrain, px, py);
   gk[0] = pz - tp.h;
@@ -397,9 +404,8 @@ __device__ __forceinline__ void NormalizedDeriv(const double v[3], const double 
 }
 __device__ __forceinline__ double Dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-// ForceConstraint, force_constraint.cc:64-171
-// Su: local state rows 1.. (25 Jacobian values); gr: the 5 constraint values
-__device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u, int terrain, const Col xs, const Col Su, const Col gr) {
+// ForceConstraint, force_constraint.cc:64-171.  Su: 25 Jacobian values; gr: the 5 constraint values
+__device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u, int terrain, const ConstCol xs, const Col Su, const Col gr) {
   const double mu = P.mu;
   const double px = xs[u.xp[0]], py = xs[u.xp[1]];
   const double f[3] = {xs[u.xf[0]], xs[u.xf[1]], xs[u.xf[2]]};
@@ -442,7 +448,7 @@ __device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u,
 }
 
 // SwingConstraint::GetValues, swing_constraint.cc:57-83 (Jacobian is constant)
-__device__ __forceinline__ void SwingUnitEval(const SwingUnit& u, const Col xs, const Col gk) {
+__device__ __forceinline__ void SwingUnitEval(const SwingUnit& u, const ConstCol xs, const Col gk) {
   const double t_swing_avg = 0.3;
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
@@ -456,7 +462,7 @@ __device__ __forceinline__ void SwingUnitEval(const SwingUnit& u, const Col xs, 
 }
 
 // SplineAccConstraint::GetValues, spline_acc_constraint.cc:49-65 (Jacobian constant for fixed durations)
-__device__ __forceinline__ void AccUnitEval(const AccUnit& u, const Col xs, const Col gk) {
+__device__ __forceinline__ void AccUnitEval(const AccUnit& u, const ConstCol xs, const Col gk) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[u.x0 + d], v0 = xs[u.x0 + 3 + d], p1 = xs[u.x0 + 6 + d], v1 = xs[u.x0 + 9 + d];
@@ -470,10 +476,19 @@ __device__ __forceinline__ void AccUnitEval(const AccUnit& u, const Col xs, cons
   }
 }
 
+// BaseMotionConstraint::UpdateConstraintAtInstance, base_motion_constraint.cc:56-66: rows AX.. = base-ang, LX.. = base-lin position
+__device__ __forceinline__ void BaseMotionUnitEval(const Plan& P, const BaseMotionUnit& u, const ConstCol xs, const Col gk) {
+  double lin[3], ang[3], unused[3];
+  EvalSpline<0>(P.samples + u.sample_lin, xs, lin, unused, unused);
+  EvalSpline<0>(P.samples + u.sample_ang, xs, ang, unused, unused);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { gk[d] = ang[d]; gk[3 + d] = lin[d]; }
+}
+
 // ---- kernels ---------------------------------------------------------------------
-// instance b of a tiled matrix with `rows` rows: element r lives at base[((b/32)*rows + r)*32 + b%32]
-__device__ __forceinline__ Col TiledCol(double* base, int b, int rows) {
-  return Col{base + ((size_t)(b >> 5) * rows) * 32 + (b & 31), 32};
+// instance b of the tiled iterate matrix with `rows` rows: element r lives at base[((b/32)*rows + r)*32 + b%32]
+__device__ __forceinline__ ConstCol TiledCol(const double* base, int b, int rows) {
+  return ConstCol{base + ((size_t)(b >> 5) * rows) * 32 + (b & 31)};
 }
 
 // x[b][i] -> XT[b/32][i][b%32]: 32x32 tiles through shared memory, coalesced on both sides; clears status
@@ -482,291 +497,240 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
   __shared__ double tile[32][33];
   const int i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
   if (status && blockIdx.x == 0 && threadIdx.y == 0 && b0 + threadIdx.x < nb) status[b0 + threadIdx.x] = 0;
+#pragma unroll
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int b = b0 + r, i = i0 + threadIdx.x;
-    if (b < nb && i < n) tile[r][threadIdx.x] = x[(size_t)b * n + i];
+    if (b < nb && i < n) tile[r][threadIdx.x] = __ldcs(x + (size_t)b * n + i);
   }
   __syncthreads();
   double* dst = XT + ((size_t)blockIdx.y * (n + 1)) * 32;
+#pragma unroll
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int i = i0 + r, b = b0 + threadIdx.x;
     if (b < nb && i < n) dst[(size_t)i * 32 + threadIdx.x] = tile[threadIdx.x][r];
   }
 }
 
-// one thread per (eval item = blockIdx.y, instance): all lanes of a warp share the sample table entry
-__global__ void __launch_bounds__(128) SplineKernel(const Plan P, double* __restrict__ XT, double* __restrict__ ST,
-                                                    int nb) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.eval_items) + blockIdx.y);
-  const int sample = (int)raw.x, row = (int)(raw.y & 0xFFFFu), kind = (int)(raw.y >> 16);
-  const SampleRegs sr = LoadSample(P.samples + sample);
-  EvalSplineToState(sr, kind, TiledCol(XT, b, P.n + 1), TiledCol(ST, b, P.S_size).at(row));
-}
-
-// ---- warp-collective output of one unit: lanes switch from "instance" to "CSR slot" ----------------
-using Tile = double (*)[33];   // [state row][lane], padded: column reads by 32 different rows are conflict-free
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// The four warps of a CTA work on the same unit for four instance tiles, so the unit's slot descriptors
-// are staged once per CTA in shared memory (asynchronously, under the unit math).
-__device__ __forceinline__ void StageSlots(const Plan& P, int s0, int s1, double* sm_coef, uint32_t* sm_desc, int tid, int nthreads) {
-  for (int i = tid; i < s1 - s0; i += nthreads) { cp_async8(sm_coef + i, P.coef + s0 + i); cp_async4(sm_desc + i, P.desc + s0 + i); }
-}
-// jac[b0 + j][s0 + i] = t[sm_desc[i]][j] * sm_coef[i], i < n_slots, j < n_inst
-__device__ __forceinline__ void StoreSlots(const Tile t, const double* sm_coef, const uint32_t* sm_desc, int n_slots,
-                                           double* __restrict__ out0, size_t nnz, int n_inst, int lane) {
-  for (int i = lane; i < n_slots; i += 32) {
-    const double* row = t[sm_desc[i]];
-    const double cf = sm_coef[i];
-    double* out = out0 + i;
-    if (n_inst == 32) {
+// ---- warp-collective output of one unit: lanes switch from "instance" to "pair of output elements" ----
+// out[j][off + h] = t[d_h][j] * c_h for the instances j = j0, j0 + jstep, .. < n_inst of the tile;
+// `out` points at element 0 of the tile's first instance, `stride` is the row length (nnz or m).
+__device__ __forceinline__ void StorePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
+                                           int n_pairs, double* __restrict__ out, size_t stride, int j0, int jstep, int n_inst, int lane) {
+  if (n_pairs <= 0) return;
+  int i = lane;
+  OutPair pr{0, kNoRow, kNoRow}; OutCoef cf{0.0, 0.0};
+  if (i < n_pairs) { const uint2 raw = __ldg(reinterpret_cast<const uint2*>(pairs) + i); pr.off = (int)raw.x; pr.d0 = raw.y & 0xFFFFu; pr.d1 = raw.y >> 16;
+                     const double2 c = __ldg(reinterpret_cast<const double2*>(coefs) + i); cf.c0 = c.x; cf.c1 = c.y; }
+  for (; i < n_pairs; i += 32) {
+    // prefetch the next entry of this lane under the stores of the current one
+    OutPair npr{0, kNoRow, kNoRow}; OutCoef ncf{0.0, 0.0};
+    if (i + 32 < n_pairs) { const uint2 raw = __ldg(reinterpret_cast<const uint2*>(pairs) + i + 32); npr.off = (int)raw.x; npr.d0 = raw.y & 0xFFFFu; npr.d1 = raw.y >> 16;
+                            const double2 c = __ldg(reinterpret_cast<const double2*>(coefs) + i + 32); ncf.c0 = c.x; ncf.c1 = c.y; }
+    double* o = out + pr.off;
+    if (pr.d0 != kNoRow && pr.d1 != kNoRow) {
+      const double* r0 = t + pr.d0 * kLD; const double* r1 = t + pr.d1 * kLD;
+      if (n_inst == 32 && jstep == 1) {
 #pragma unroll 16
-      for (int j = 0; j < 32; ++j) StoreOut(out + j * nnz, row[j] * cf);
+        for (int j = 0; j < 32; ++j) StoreOut2(o + j * stride, r0[j] * cf.c0, r1[j] * cf.c1);
+      } else {
+#pragma unroll 4
+        for (int j = j0; j < n_inst; j += jstep) StoreOut2(o + j * stride, r0[j] * cf.c0, r1[j] * cf.c1);
+      }
+    } else if (pr.d0 != kNoRow) {
+      const double* r0 = t + pr.d0 * kLD;
+      for (int j = j0; j < n_inst; j += jstep) StoreOut(o + j * stride, r0[j] * cf.c0);
+    } else if (pr.d1 != kNoRow) {
+      const double* r1 = t + pr.d1 * kLD;
+      for (int j = j0; j < n_inst; j += jstep) StoreOut(o + 1 + j * stride, r1[j] * cf.c1);
+    }
+    pr = npr; cf = ncf;
+  }
+}
+// all outputs of one unit: Jacobian values (flags & 2) and constraint values (flags & 1)
+__device__ __forceinline__ void StoreUnit(const Plan& P, const double* t, const OutList& L, double* __restrict__ g_tile,
+                                          double* __restrict__ jac_tile, unsigned flags, int n_inst, int lane) {
+  if (flags & 2u) {
+    if (P.nnz & 1) {
+      StorePairs(t, P.pairs + L.jac[0], P.coefs + L.jac[0], L.n_jac[0], jac_tile, (size_t)P.nnz, 0, 2, n_inst, lane);
+      StorePairs(t, P.pairs + L.jac[1], P.coefs + L.jac[1], L.n_jac[1], jac_tile, (size_t)P.nnz, 1, 2, n_inst, lane);
     } else {
-      for (int j = 0; j < n_inst; ++j) StoreOut(out + j * nnz, row[j] * cf);
+      StorePairs(t, P.pairs + L.jac[0], P.coefs + L.jac[0], L.n_jac[0], jac_tile, (size_t)P.nnz, 0, 1, n_inst, lane);
+    }
+  }
+  if (flags & 1u) {
+    if (P.m & 1) {
+      StorePairs(t, P.pairs + L.g[0], P.coefs + L.g[0], L.n_g[0], g_tile, (size_t)P.m, 0, 2, n_inst, lane);
+      StorePairs(t, P.pairs + L.g[1], P.coefs + L.g[1], L.n_g[1], g_tile, (size_t)P.m, 1, 2, n_inst, lane);
+    } else {
+      StorePairs(t, P.pairs + L.g[0], P.coefs + L.g[0], L.n_g[0], g_tile, (size_t)P.m, 0, 1, n_inst, lane);
     }
   }
 }
-// g[b0 + j][g_row + r] = t[g_local + r][j], r < n_g
-__device__ __forceinline__ void StoreG(const Tile t, int g_local, int n_g, double* __restrict__ g_tile, int m, int n_inst,
-                                       int lane) {
-  for (int idx = lane; idx < n_g * n_inst; idx += 32) {
-    const int j = idx / n_g, r = idx - j * n_g;
-    StoreOut(g_tile + (size_t)j * m + r, t[g_local + r][j]);
-  }
-}
 // non-finite check of this lane's own column (rows 1 .. n_rows-1); flags instance b
-__device__ __forceinline__ void FlagNonFinite(const Tile t, int n_rows, int lane, int* __restrict__ status, int b, int nb) {
+__device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int lane, int* __restrict__ status, int b, int nb) {
   if (!status) return;
   double chk = 0.0;
-  for (int r = 1; r < n_rows; ++r) chk = fma(t[r][lane], 0.0, chk);
+  for (int r = 1; r < n_rows; ++r) chk = fma(t[r * kLD + lane], 0.0, chk);
   if (chk != chk && b < nb) atomicOr(status + b, 1);
 }
 
-constexpr int kOutWarps = 4;   // warps per CTA of NodeOut / ConstOut (warp = instance tile)
-constexpr int kDynWarps = 8;   // consecutive samples per CTA of DynOut
-
-// DynamicConstraint: blockIdx.y = instance tile, warp = one of kOutWarps CONSECUTIVE samples, so a CTA writes
+// DynamicConstraint: blockIdx.y = instance tile, warp = one of kDynWarps CONSECUTIVE samples, so a CTA writes
 // several KB of contiguous CSR values per instance (the samples' rows are adjacent) — DRAM page locality.
-__global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, double* __restrict__ ST, double* __restrict__ g,
-                                                           double* __restrict__ jac, int* __restrict__ status, int nb,
-                                                           unsigned flags, int max_slots) {
+template <int kNEE>
+__global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, const double* __restrict__ XT, double* __restrict__ g,
+                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * kDynWarps + warp, b0 = blockIdx.y * 32;
   if (k >= P.n_dyn) return;
-  const int n_rows = 40 + 6 * P.n_ee, G0 = n_rows;   // local rows: 1 | 3 | 36 | 6 per foot, then g
-  const size_t per_warp = (size_t)max_slots + (max_slots + 1) / 2 + (size_t)(n_rows + 6) * 33;
-  double* sm_coef = out_smem + warp * per_warp;
-  uint32_t* sm_desc = reinterpret_cast<uint32_t*>(sm_coef + max_slots);
-  Tile t = reinterpret_cast<Tile>(sm_coef + max_slots + (max_slots + 1) / 2);
-  const DynInfo u = P.dyn_info[k];
-  if (flags & 2u) StageSlots(P, u.s0, u.s1, sm_coef, sm_desc, lane, 32);
-  cp_async_commit();
-  t[0][lane] = 1.0;
-  DynamicUnit(P, k, TiledCol(ST, b0 + lane, P.S_size).at(P.S_dyn0 + k * P.S_dyn_stride), Col{&t[1][lane], 33},
-              Col{&t[G0][lane], 33});
+  constexpr int G0 = 40 + 6 * kNEE, n_rows = G0 + 6;   // local rows: 1 | 3 | 36 | 6 per foot | g (6)
+  double* t = out_smem + (size_t)warp * n_rows * kLD;
+  const DynUnit* u = P.dyn + k;
+  t[lane] = 1.0;
+  DynamicUnit<kNEE>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
   FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
-  cp_async_wait_all();
   __syncwarp();
-  const int n_inst = min(32, nb - b0);
-  if (flags & 2u) StoreSlots(t, sm_coef, sm_desc, u.s1 - u.s0, jac + (size_t)b0 * P.nnz + u.s0, (size_t)P.nnz, n_inst, lane);
-  if (flags & 1u) StoreG(t, G0, 6, g + (size_t)b0 * P.m + u.g_row, P.m, n_inst, lane);
+  StoreUnit(P, t, u->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
 }
 
-// RangeOfMotionConstraint: blockIdx.z = foot, blockIdx.y = instance tile, warp = one of kRomWarps consecutive
-// samples of that foot (their rows are adjacent: one CTA writes a contiguous run of CSR values per instance)
-constexpr int kRomWarps = 8;
-__global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomOut(const Plan P, double* __restrict__ ST, double* __restrict__ g,
-                                                           double* __restrict__ jac, int* __restrict__ status, int nb,
-                                                           unsigned flags, int max_slots) {
+// RangeOfMotionConstraint: blockIdx.y = instance tile, warp = one of kRomWarps consecutive samples, all feet
+template <int kNEE>
+__global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomOut(const Plan P, const double* __restrict__ XT, double* __restrict__ g,
+                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = blockIdx.x * kRomWarps + warp, b0 = blockIdx.y * 32, e = blockIdx.z;
+  const int k = blockIdx.x * kRomWarps + warp, b0 = blockIdx.y * 32;
   if (k >= P.n_rom) return;
-  constexpr int n_rows = 19, G0 = 19;   // local rows: 1 | R^T 9 | D_e 9, then g (3)
-  const size_t per_warp = (size_t)max_slots + (max_slots + 1) / 2 + (size_t)(n_rows + 3) * 33;
-  double* sm_coef = out_smem + warp * per_warp;
-  uint32_t* sm_desc = reinterpret_cast<uint32_t*>(sm_coef + max_slots);
-  Tile t = reinterpret_cast<Tile>(sm_coef + max_slots + (max_slots + 1) / 2);
-  const RomInfo info = P.rom_info[k];
-  const int s0 = info.s0[e], n_slots = info.s1[e] - s0;
-  if (flags & 2u) StageSlots(P, s0, s0 + n_slots, sm_coef, sm_desc, lane, 32);
-  cp_async_commit();
-  t[0][lane] = 1.0;
-  RomUnit(P, e, TiledCol(ST, b0 + lane, P.S_size).at(P.S_rom0 + k * P.S_rom_stride), Col{&t[1][lane], 33}, Col{&t[G0][lane], 33});
+  constexpr int G0 = 10 + 9 * kNEE, n_rows = G0 + 3 * kNEE;   // local rows: 1 | R^T 9 | D_e 9 per foot | g 3 per foot
+  double* t = out_smem + (size_t)warp * n_rows * kLD;
+  const RomUnit* u = P.rom + k;
+  t[lane] = 1.0;
+  RomUnitEval<kNEE>(P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
   FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
-  cp_async_wait_all();
   __syncwarp();
-  const int n_inst = min(32, nb - b0);
-  if (flags & 2u) StoreSlots(t, sm_coef, sm_desc, n_slots, jac + (size_t)b0 * P.nnz + s0, (size_t)P.nnz, n_inst, lane);
-  if (flags & 1u) StoreG(t, G0, 3, g + (size_t)b0 * P.m + info.g_row[e], P.m, n_inst, lane);
+  StoreUnit(P, t, u->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
 }
 
-// node units: blockIdx.y = unit (force | terrain | swing | spline-acc | cost), warp = instance tile
-constexpr int kNodeRows = 32;   // local rows: 1 | <= 25 state | <= 5 g
-__global__ void __launch_bounds__(kOutWarps * 32) NodeOut(const Plan P, double* __restrict__ XT, double* __restrict__ g,
-                                                          double* __restrict__ jac, double* __restrict__ cost,
-                                                          double* __restrict__ grad, int* __restrict__ status,
-                                                          const int* __restrict__ terrain_ids, int default_terrain, int nb,
-                                                          unsigned flags) {
-  __shared__ __align__(16) double node_smem[kOutWarps * kNodeRows * 33];
+// node groups: blockIdx.y = instance tile, warp = one of kNodeWarps consecutive groups
+__global__ void __launch_bounds__(kNodeWarps * 32) NodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ g,
+                                                           double* __restrict__ jac, int* __restrict__ status,
+                                                           const int* __restrict__ terrain_ids, int default_terrain, int nb,
+                                                           unsigned flags) {
+  extern __shared__ __align__(16) double node_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x * kOutWarps + warp, b0 = tile * 32, b = b0 + lane;
-  if (b0 >= nb) return;
-  Tile t = reinterpret_cast<Tile>(node_smem + (size_t)warp * kNodeRows * 33);
-  const Col xs = TiledCol(XT, b, P.n + 1);
-  const int n_inst = min(32, nb - b0);
-  const int terrain = (terrain_ids && b < nb) ? terrain_ids[b] : default_terrain;
-  double* jac_tile = jac + (size_t)b0 * P.nnz;
-  double* g_tile = g + (size_t)b0 * P.m;
-  t[0][lane] = 1.0;
-  int u = blockIdx.y;
-  if (u < P.n_force) {
-    const ForceUnit fu = P.force[u];
-    const uint32_t my_a = (lane < 25) ? __ldg(P.desc + fu.s0 + lane) : 0u;   // issued before the unit math
-    const double my_c = (lane < 25) ? __ldg(P.coef + fu.s0 + lane) : 0.0;
-    ForceUnitEval(P, fu, terrain, xs, Col{&t[1][lane], 33}, Col{&t[26][lane], 33});
-    FlagNonFinite(t, 26, lane, status, b, nb);
-    __syncwarp();
-    if ((flags & 2u) && lane < 25) {
-      const double* row = t[my_a];
-      double* out = jac_tile + fu.s0 + lane;
-      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * P.nnz, row[j] * my_c);
-    }
-    if (flags & 1u) StoreG(t, 26, 5, g_tile + fu.g_row, P.m, n_inst, lane);
-    return;
+  const int gi = blockIdx.x * kNodeWarps + warp, b0 = blockIdx.y * 32, b = b0 + lane;
+  if (gi >= P.n_groups) return;
+  double* t = node_smem + (size_t)warp * kNodeStateRows * kLD;
+  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const NodeGroup* grp = P.groups + gi;
+  const int kind = __ldg(&grp->kind), first = __ldg(&grp->first), count = __ldg(&grp->count);
+  t[lane] = 1.0;
+  int n_rows = 1;
+  if (kind == kGroupForce) {
+    const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
+    for (int q = 0; q < count; ++q)
+      ForceUnitEval(P, P.force[first + q], terrain, xs, Col{t + (1 + 25 * q) * kLD + lane, kLD}, Col{t + (1 + 25 * count + 5 * q) * kLD + lane, kLD});
+    n_rows = 1 + 30 * count;
+  } else if (kind == kGroupTerrain) {
+    const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
+    for (int q = 0; q < count; ++q)
+      TerrainUnitEval(P.terr[first + q], terrain, xs, Col{t + (1 + 2 * q) * kLD + lane, kLD}, Col{t + (1 + 2 * count + q) * kLD + lane, kLD});
+    n_rows = 1 + 3 * count;
+  } else if (kind == kGroupSwing) {
+    if (flags & 1u) for (int q = 0; q < count; ++q) SwingUnitEval(P.swing[first + q], xs, Col{t + (1 + 4 * q) * kLD + lane, kLD});
+    n_rows = (flags & 1u) ? 1 + 4 * count : 1;
+  } else if (kind == kGroupAcc) {
+    if (flags & 1u) for (int q = 0; q < count; ++q) AccUnitEval(P.acc[first + q], xs, Col{t + (1 + 3 * q) * kLD + lane, kLD});
+    n_rows = (flags & 1u) ? 1 + 3 * count : 1;
+  } else if (kind == kGroupBaseMotion) {
+    if (flags & 1u) for (int q = 0; q < count; ++q) BaseMotionUnitEval(P, P.base_motion[first + q], xs, Col{t + (1 + 6 * q) * kLD + lane, kLD});
+    n_rows = (flags & 1u) ? 1 + 6 * count : 1;
   }
-  u -= P.n_force;
-  if (u < P.n_terr) {
-    const TerrainUnit tu = P.terr[u];
-    const uint32_t my_a = (lane < 3) ? __ldg(P.desc + tu.s0 + lane) : 0u;
-    const double my_c = (lane < 3) ? __ldg(P.coef + tu.s0 + lane) : 0.0;
-    TerrainUnitEval(tu, terrain, xs, Col{&t[1][lane], 33}, Col{&t[3][lane], 33});
-    FlagNonFinite(t, 3, lane, status, b, nb);
-    __syncwarp();
-    if ((flags & 2u) && lane < 3) {
-      const double* row = t[my_a];
-      double* out = jac_tile + tu.s0 + lane;
-      for (int j = 0; j < n_inst; ++j) StoreOut(out + (size_t)j * P.nnz, row[j] * my_c);
-    }
-    if (flags & 1u) StoreG(t, 3, 1, g_tile + tu.g_row, P.m, n_inst, lane);
-    return;
-  }
-  u -= P.n_terr;
-  if (u < P.n_swing) {
-    if (flags & 1u) {
-      const SwingUnit su = P.swing[u];
-      SwingUnitEval(su, xs, Col{&t[1][lane], 33});
-      __syncwarp();
-      StoreG(t, 1, 4, g_tile + su.g_row, P.m, n_inst, lane);
-    }
-    return;
-  }
-  u -= P.n_swing;
-  if (u < P.n_acc) {
-    if (flags & 1u) {
-      const AccUnit au = P.acc[u];
-      AccUnitEval(au, xs, Col{&t[1][lane], 33});
-      __syncwarp();
-      StoreG(t, 1, 3, g_tile + au.g_row, P.m, n_inst, lane);
-    }
-    return;
-  }
-  if ((flags & 4u) && P.n_cost > 0 && b < nb) {
-    // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
-    // dense gradient row (node_cost.cc:65-76), both in the reference's order
-    double* gr = grad ? grad + (size_t)b * P.n : nullptr;
-    if (gr) for (int i = 0; i < P.n; ++i) gr[i] = 0.0;
-    double total_cost = 0.0, term = 0.0;
-    for (int i = 0; i < P.n_cost; ++i) {
-      const CostEntry ce = P.cost[i];
-      if (ce.pad && i > 0) { total_cost += term; term = 0.0; }
-      const double val = xs[ce.xi];
-      term += ce.weight * (val * val);
-      if (gr && ce.grad_col >= 0) gr[ce.grad_col] += ce.weight * 2.0 * val;
-    }
-    total_cost += term;
-    if (cost) cost[b] = total_cost;
-  }
+  FlagNonFinite(t, n_rows, lane, status, b, nb);
+  __syncwarp();
+  StoreUnit(P, t, grp->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
 }
 
-// iterate-independent CSR values (SplineAcc, Swing rows): blockIdx.y = 32-slot run, warp = instance tile
-__global__ void __launch_bounds__(kOutWarps * 32) ConstOut(const Plan P, double* __restrict__ jac, int nb) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b0 = (blockIdx.x * kOutWarps + warp) * 32;
-  if (b0 >= nb) return;
-  int run = blockIdx.y, s = -1;
-  for (int i = 0; i < P.n_const_seg; ++i) {   // locate the run inside the segment list
-    const ConstSeg seg = P.const_seg[i];
-    const int runs = (seg.s1 - seg.s0 + 31) / 32;
-    if (run < runs) { s = seg.s0 + run * 32 + lane; if (s >= seg.s1) s = -1; break; }
-    run -= runs;
+// NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
+// dense gradient row (node_cost.cc:65-76), both in the reference's order.  One thread per instance.
+__global__ void __launch_bounds__(128) CostKernel(const Plan P, const double* __restrict__ XT, double* __restrict__ cost,
+                                                  double* __restrict__ grad, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  double* gr = grad ? grad + (size_t)b * P.n : nullptr;
+  if (gr) for (int i = 0; i < P.n; ++i) gr[i] = 0.0;
+  double total_cost = 0.0, term = 0.0;
+  for (int i = 0; i < P.n_cost; ++i) {
+    const CostEntry ce = P.cost[i];
+    if (ce.pad && i > 0) { total_cost += term; term = 0.0; }
+    const double val = xs[ce.xi];
+    term += ce.weight * (val * val);
+    if (gr && ce.grad_col >= 0) gr[ce.grad_col] += ce.weight * 2.0 * val;
   }
-  if (s < 0) return;
-  const int n_inst = min(32, nb - b0);
-  const size_t nnz = (size_t)P.nnz;
-  const double cf = __ldg(P.coef + s);
-  double* out = jac + (size_t)b0 * nnz + s;
-#pragma unroll 8
-  for (int j = 0; j < n_inst; ++j) StoreOut(out + j * nnz, cf);
+  total_cost += term;
+  if (cost) cost[b] = total_cost;
+}
+
+template <int kNEE>
+cudaError_t LaunchDynRom(const Plan& P, const double* XT, double* g, double* jac, int* status, int nb, unsigned flags, int tiles,
+                         cudaStream_t s_dyn, cudaStream_t s_rom, int* count) {
+  cudaError_t e = cudaSuccess;
+  if (P.n_dyn > 0) {
+    const size_t smem = (size_t)kDynWarps * (46 + 6 * kNEE) * kLD * sizeof(double);
+    e = cudaFuncSetAttribute(DynOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    DynOut<kNEE><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, s_dyn>>>(P, XT, g, jac, status, nb, flags);
+    ++*count; TWB_MARK("DynOut", s_dyn);
+  }
+  if (P.n_rom > 0) {
+    const size_t smem = (size_t)kRomWarps * (10 + 12 * kNEE) * kLD * sizeof(double);
+    e = cudaFuncSetAttribute(RomOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    RomOut<kNEE><<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles), kRomWarps * 32, smem, s_rom>>>(P, XT, g, jac, status, nb, flags);
+    ++*count; TWB_MARK("RomOut", s_rom);
+  }
+  return cudaSuccess;
 }
 
 }  // namespace
 
 // ---- host launchers ------------------------------------------------------------------
-void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // profiling hook (capi.cc, TWB_PROFILE=1)
-#define TWB_MARK(label, stream) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
 
-// XT / ST are the tiled matrices of the whole batch (first tile = first instance of x / g / jac).
-// Streams: `s` carries TransposeIn -> SplineKernel -> DynOut; RomOut / NodeOut+ConstOut run on aux[0] / aux[1]
-// after the spline values exist (ev[0]) and are joined back into `s` (ev[1], ev[2]).
-int LaunchEval(const Plan& P, const double* x, double* XT, double* ST, double* g, double* jac, double* cost, double* grad,
+// XT is the tiled iterate matrix of the whole batch (first tile = first instance of x / g / jac).
+// Streams: `s` carries TransposeIn -> RomOut; DynOut / NodeOut (+ CostKernel) run on aux[0] / aux[1]
+// after the transposition (ev[0]) and are joined back into `s` (ev[1], ev[2]).
+int LaunchEval(const Plan& P, const double* x, double* XT, double* g, double* jac, double* cost, double* grad,
                int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
                cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches) {
   if (nb <= 0) return 0;
   int count = 0;
   const bool serial = (g_after_launch != nullptr);
   if (serial) aux0 = aux1 = s;
-  const int tiles = (nb + 31) / 32, bx = (tiles + kOutWarps - 1) / kOutWarps;
-  const unsigned out_flags = flags & 7u;
+  const int tiles = (nb + 31) / 32;
+  const unsigned out_flags = flags & 3u;
   TWB_MARK("begin", s);
   TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, status, P.n, nb); ++count; TWB_MARK("TransposeIn", s);
-  if (P.n_eval_items > 0) { SplineKernel<<<dim3((nb + 127) / 128, P.n_eval_items), 128, 0, s>>>(P, XT, ST, nb); ++count; TWB_MARK("SplineKernel", s); }
   if (!serial) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
-  if (P.n_dyn > 0 && (out_flags & 3u)) {
-    const int ms = (P.max_dyn_slots + 1) & ~1;
-    const size_t smem = (size_t)kDynWarps * ((size_t)(46 + 6 * P.n_ee) * 33 + ms + (ms + 1) / 2) * sizeof(double);
-    e = cudaFuncSetAttribute(DynOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (out_flags) {
+    switch (P.n_ee) {
+      case 1: e = LaunchDynRom<1>(P, XT, g, jac, status, nb, out_flags, tiles, aux0, s, &count); break;
+      case 2: e = LaunchDynRom<2>(P, XT, g, jac, status, nb, out_flags, tiles, aux0, s, &count); break;
+      case 4: e = LaunchDynRom<4>(P, XT, g, jac, status, nb, out_flags, tiles, aux0, s, &count); break;
+      default: return (int)cudaErrorInvalidValue;
+    }
     if (e != cudaSuccess) return (int)e;
-    DynOut<<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, s>>>(P, ST, g, jac, status, nb, out_flags, ms); ++count; TWB_MARK("DynOut", s);
+    if (P.n_groups > 0) {
+      const size_t smem = (size_t)kNodeWarps * kNodeStateRows * kLD * sizeof(double);
+      e = cudaFuncSetAttribute(NodeOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      NodeOut<<<dim3((P.n_groups + kNodeWarps - 1) / kNodeWarps, tiles), kNodeWarps * 32, smem, aux1>>>(P, XT, g, jac, status, terrain_ids, default_terrain, nb, out_flags);
+      ++count; TWB_MARK("NodeOut", aux1);
+    }
   }
-  if (P.n_rom > 0 && (out_flags & 3u)) {
-    const int ms = (P.max_rom_slots + 1) & ~1;
-    const size_t smem = (size_t)kRomWarps * ((size_t)22 * 33 + ms + (ms + 1) / 2) * sizeof(double);
-    e = cudaFuncSetAttribute(RomOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    RomOut<<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles, P.n_ee), kRomWarps * 32, smem, aux0>>>(P, ST, g, jac, status, nb, out_flags, ms); ++count; TWB_MARK("RomOut", aux0);
-  }
-  const bool want_cost = (out_flags & 4u) && P.n_cost > 0;
-  const int n_units = P.n_force + P.n_terr + P.n_swing + P.n_acc + (want_cost ? 1 : 0);
-  if (n_units > 0) {
-    NodeOut<<<dim3(bx, n_units), kOutWarps * 32, 0, aux1>>>(P, XT, g, jac, cost, grad, status, terrain_ids, default_terrain, nb, out_flags);
-    ++count; TWB_MARK("NodeOut", aux1);
-  }
-  if (P.n_const_seg > 0 && (out_flags & 2u)) {
-    ConstOut<<<dim3(bx, P.n_const_runs), kOutWarps * 32, 0, aux1>>>(P, jac, nb); ++count; TWB_MARK("ConstOut", aux1);
+  if ((flags & 4u) && P.n_cost > 0) {
+    CostKernel<<<(nb + 127) / 128, 128, 0, aux1>>>(P, XT, cost, grad, nb); ++count; TWB_MARK("CostKernel", aux1);
   }
   if (!serial) {
     cudaEventRecord(ev[1], aux0); cudaEventRecord(ev[2], aux1);
