@@ -49,7 +49,8 @@ class Spec(C.Structure):
     ]
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtowr_b200.so")
+# TWB_LIB: developer knob for tuning sweeps (scripts/build_variants.sh) — another build of the same library
+LIB_PATH = os.environ.get("TWB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtowr_b200.so")
 
 
 def _load():

@@ -69,6 +69,7 @@ struct twb_batch {
   std::vector<void*> owned;       // device allocations of the tables
   int* d_terrain = nullptr;       // per-instance terrain ids (optional)
   double* d_XT = nullptr;         // [ld/32][n+1][32] instance-tiled iterates; row n == 0
+  double* d_GT = nullptr;         // [ld/32][m][32] instance-tiled constraint values (staging of g)
   // staging for the host-pointer variant
   double *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_cost = nullptr, *d_grad = nullptr;
   int* d_status = nullptr;
@@ -171,9 +172,11 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
   b->ld = ((size_t)batch_size + 31) & ~(size_t)31;
   cudaDeviceGetAttribute(&b->n_sms, cudaDevAttrMultiProcessorCount, device);
+  b->plan.n_sms = b->n_sms;
   const size_t xt_bytes = (size_t)(b->plan.n + 1) * b->ld * sizeof(double);
   if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_XT), xt_bytes)) != cudaSuccess ||
-      (e = cudaMemset(b->d_XT, 0, xt_bytes)) != cudaSuccess) {
+      (e = cudaMemset(b->d_XT, 0, xt_bytes)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&b->d_GT), (size_t)std::max(b->plan.m, 1) * b->ld * sizeof(double))) != cudaSuccess) {
     twb_batch_destroy(b);
     return CudaFail(e, "state allocation");
   }
@@ -197,7 +200,7 @@ void twb_batch_destroy(twb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   for (void* p : b->owned) cudaFree(p);
-  cudaFree(b->d_terrain); cudaFree(b->d_XT);
+  cudaFree(b->d_terrain); cudaFree(b->d_XT); cudaFree(b->d_GT);
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
@@ -224,7 +227,8 @@ int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   const twb::Plan& p = b->plan;
   const bool want_cost = b->prob->f.has_cost && (flags & TWB_EVAL_COST);
   int n = 1;   // TransposeIn
-  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += (p.n_dyn > 0) + (p.n_rom > 0) + (p.n_groups > 0);
+  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += (p.n_dyn > 0) + (p.n_rom > 0) + (p.n_groups > 0);   // DynOut, RomOut, NodeOut
+  if (flags & TWB_EVAL_G) n += 1;   // TransposeOut
   if (want_cost) n += 1;
   return n;
 }
@@ -240,7 +244,7 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   unsigned kflags = flags & (TWB_EVAL_G | TWB_EVAL_JAC);
   if (f.has_cost && (flags & TWB_EVAL_COST)) kflags |= TWB_EVAL_COST;
   int launches = 0;
-  int rc = twb::LaunchEval(b->plan, x, b->d_XT, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
+  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
                            kflags, static_cast<cudaStream_t>(stream), b->aux0, b->aux1, b->ev.data(), &launches);
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
   b->launches_last = launches;

@@ -28,18 +28,54 @@ struct alignas(16) SplineSample {   // 96 bytes = six 16-byte loads
 // Every value a unit produces — a CSR Jacobian value or a constraint value — is
 //     out[instance][off + h] = state[d_h][instance] * c_h,     h = 0, 1
 // where `state` is the unit's local state block (row 0 holds the constant 1) and (off, off + 1) is a
-// 16-byte aligned pair of elements of the instance's output row, so that one lane issues one
-// 16-byte store per instance and a warp covers 512 contiguous bytes.  A half whose element belongs
-// to a neighbouring unit has d_h = kNoRow and is skipped.
-constexpr uint16_t kNoRow = 0xFFFFu;
-struct OutPair { int32_t off; uint16_t d0, d1; };       // off: element index of the pair's first half in the row (-1: first half precedes the row)
+// 16-byte aligned pair of elements of the instance's output row, so that one lane issues one 16-byte store
+// per instance and a warp covers 512 contiguous bytes.
+//
+// HBM only sustains its write bandwidth for whole 32-byte sectors (a partially written sector that has left
+// the L2 costs a read-modify-write), so the lists are built sector by sector: a sector is written, whole, by
+// the unit that owns its LAST element; elements of that sector owned by the preceding unit of the same CTA
+// reach the writer through CARRY rows — the preceding warp publishes `state * coef` into rows appended to
+// the writer's state block before the CTA-wide barrier.  Only sectors that straddle a CTA or a constraint-set
+// boundary fall back to 8-byte single-element stores.
+//
+// The alignment of an instance's row inside its sectors depends on (instance * row length) mod 4, so a list
+// exists per alignment class q = instance mod n_classes (n_classes = 1 when the row length is a multiple of 4).
+constexpr int kMaxClasses = 4;
+constexpr int kCarryRows = 6;           // carry-in rows of a state block: 3 for Jacobian values, 3 for constraint values
+struct OutPair { int32_t off; uint16_t d0, d1; };       // pair: element index of the first half; single / publish entry: element index / carry row, d0 = state row
 struct alignas(16) OutCoef { double c0, c1; };
-// The pair lists of one unit.  When a row length (nnz or m) is odd, rows of odd instances start
-// 8 bytes off a 16-byte boundary, so those instances use a second list with the other pairing.
-struct OutList {
-  int32_t jac[2], n_jac[2];   // [parity of the instance]: first pair / number of pairs, Jacobian values
-  int32_t g[2], n_g[2];       // same for constraint values
+struct OutRange { int32_t first, count; };
+struct OutList {                        // [0: Jacobian values, 1: constraint values][alignment class]
+  OutRange pairs[2][kMaxClasses];       // whole sectors, two pairs each
+  OutRange singles[2][kMaxClasses];     // single elements (lane = instance)
+  OutRange publish[2][kMaxClasses];     // carry values for the next warp of the CTA (lane = instance)
 };
+
+// warps per CTA of the output kernels = consecutive units whose output ranges are chained through carry rows.
+// TWB_FUSED = 1: one kernel (EvalOut) serves all three unit kinds with CTAs of TWB_WARPS warps.
+#ifndef TWB_FUSED
+#define TWB_FUSED 0
+#endif
+#if TWB_FUSED
+#ifndef TWB_WARPS
+#define TWB_WARPS 5
+#endif
+constexpr int kWarps = TWB_WARPS;
+constexpr int kDynWarps = kWarps, kRomWarps = kWarps, kNodeWarps = kWarps;
+#else
+#ifndef TWB_DYN_WARPS
+#define TWB_DYN_WARPS 4
+#endif
+#ifndef TWB_ROM_WARPS
+#define TWB_ROM_WARPS 7
+#endif
+#ifndef TWB_NODE_WARPS
+#define TWB_NODE_WARPS 8
+#endif
+constexpr int kDynWarps = TWB_DYN_WARPS;     // consecutive dynamic samples per CTA (one instance tile)
+constexpr int kRomWarps = TWB_ROM_WARPS;     // consecutive range-of-motion samples per CTA
+constexpr int kNodeWarps = TWB_NODE_WARPS;   // consecutive node groups per CTA
+#endif
 
 // TerrainConstraint row (terrain_constraint.cc:59-108): one ee-motion node.
 // local state: [base + 0] = -dh/dx, [base + 1] = -dh/dy, g at [g_base]
@@ -61,14 +97,16 @@ struct BaseMotionUnit { int32_t sample_lin, sample_ang; };
 // A dynamic sample (6 rows): 2 + 2 n_ee spline samples starting at `sample0`
 // (base-lin, base-ang, ee-motion.., ee-force..) and its output lists.
 struct DynUnit { int32_t sample0; int32_t pad; OutList out; };
-// A range-of-motion sample (3 rows for every foot): 2 + n_ee spline samples (base-lin, base-ang, ee-motion..)
-struct RomUnit { int32_t sample0; int32_t pad; OutList out; };
+// A range-of-motion sample (3 rows for every foot): 2 + n_ee spline samples (base-lin, base-ang, ee-motion..);
+// the feet are evaluated and written one after the other through the same state rows (out[foot]).
+struct RomUnit { int32_t sample0; int32_t pad; OutList out[kMaxEE]; };
+constexpr int kRomStateRows = 22;    // [0]=1 | R^T (9) | D_e (9) | g_e (3); followed by kCarryRows carry-in rows per foot
 
 // Node-wise work of one warp: `count` consecutive units of one kind evaluated into one state block,
 // then one pass over the group's output lists.
 enum NodeKind : int32_t { kGroupForce = 0, kGroupTerrain = 1, kGroupSwing = 2, kGroupAcc = 3, kGroupConst = 4, kGroupBaseMotion = 5 };
 struct NodeGroup { int32_t kind, first, count, pad; OutList out; };
-constexpr int kNodeStateRows = 64;   // local state rows of a node group (row 0 = 1)
+constexpr int kNodeStateRowsMax = 64;   // upper bound of the local state rows of a node group (row 0 = 1); Plan::node_rows is the actual maximum
 
 // NodeCost term (node_cost.cc:53-76) flattened: one entry per node value that
 // enters the cost; var >= 0 when the value is an optimisation variable.
@@ -81,8 +119,10 @@ struct CostEntry {
 
 struct Plan {
   int n, m, nnz, n_ee;
+  int n_sms;       // multiprocessors of the batch's device (persistent grids); set by twb_batch_create
   int n_dyn, n_rom, n_groups, n_cost;
-  int max_dyn_pairs, max_rom_pairs, max_group_pairs;   // longest output list (pairs, Jacobian + values) of a unit
+  int node_rows;   // state rows of the largest node group (without carry rows)
+  int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz) and constraint rows (length m)
   // robot
   double mass, gravity;
   double I_b[9];

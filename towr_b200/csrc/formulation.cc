@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <numeric>
 
@@ -171,6 +172,13 @@ std::vector<double> BasePolyDurations(double T, double dt) {  // parameters.cc:8
   std::vector<double> v; double left = T; const double eps = 1e-10;
   while (left > eps) { v.push_back(left > dt ? dt : left); left -= dt; }
   return v;
+}
+
+// tuning knob read from the environment (clamped); the default is what ships
+int EnvInt(const char* name, int def, int lo, int hi) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return def;
+  return std::max(lo, std::min(hi, std::atoi(v)));
 }
 
 struct Emit { int row, col; uint32_t a; double c0; };   // a: local state row of the owning unit (0 = the constant 1)
@@ -385,7 +393,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         have_rom = true;
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_range_of_motion);
         pl.n_rom = (int)ts.size();
-        const uint32_t G0 = 10 + 9 * n_ee;   // local state: [0]=1 | R^T (9) | D_e (9 per foot) | g (3 per foot)
+        const uint32_t G0 = 19;   // local state (re-used by the feet in turn): [0]=1 | R^T (9) | D_e (9) | g_e (3)
         for (int k = 0; k < pl.n_rom; ++k) {  // spline samples: base-lin, base-ang, ee-motion..
           RomUnit ru{}; ru.sample0 = (int32_t)tb.samples.size();
           tb.rom.push_back(ru);
@@ -397,10 +405,10 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
           for (int k = 0; k < pl.n_rom; ++k) {
             const double t = ts[k]; const int row = r0 + 3 * k;
-            const uint32_t sb = 1, sd = 10 + 9 * e;
+            const uint32_t sb = 1, sd = 10;
             for (int d = 0; d < 3; ++d) {
               bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
-              own(row + d, kOwnRom, k, G0 + 3 * e + d);
+              own(row + d, kOwnRom, k * n_ee + e, G0 + d);
             }
             int p; double tl;
             Locate(sp_lin, t, &p, &tl);   // -R^T dc
@@ -558,7 +566,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   std::vector<GroupBuild> groups;
   std::vector<int> unit_group(node_units.size(), -1), unit_state0(node_units.size(), 0), unit_g0(node_units.size(), 0);
   {
-    auto cap = [](int kind) { return kind == kGroupForce ? 2 : kind == kGroupTerrain ? 12 : kind == kGroupSwing ? 8 : kind == kGroupAcc ? 8 : 8; };
+    const int force_cap = EnvInt("TWB_FORCE_CAP", 1, 1, 2);
+    auto cap = [&](int kind) { return kind == kGroupForce ? force_cap : kind == kGroupTerrain ? 10 : kind == kGroupSwing ? 7 : kind == kGroupAcc ? 10 : 5; };
     for (size_t u = 0; u < node_units.size(); ++u) {
       const NodeUnitRef& nu = node_units[u];
       bool open = !groups.empty() && groups.back().kind == nu.kind && groups.back().count < cap(nu.kind) &&
@@ -567,68 +576,114 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
       groups.back().count++; groups.back().unit_ids.push_back((int)u);
       unit_group[u] = (int)groups.size() - 1;
     }
+    pl.node_rows = 1;
     for (auto& gb : groups) {   // state block: [0]=1 | unit states | unit values
       int top = 1;
       for (int u : gb.unit_ids) { unit_state0[u] = top; top += node_units[u].n_state; }
       for (int u : gb.unit_ids) { unit_g0[u] = top; top += node_units[u].n_g; }
-      if (top > kNodeStateRows) return fail(TWB_ERR_UNSUPPORTED, "node group state block too large");
+      if (top > kNodeStateRowsMax) return fail(TWB_ERR_UNSUPPORTED, "node group state block too large");
+      pl.node_rows = std::max(pl.node_rows, top);
     }
   }
 
-  // ---- output lists: every unit writes the Jacobian values and constraint values of the rows it owns
-  struct OutItem { int off; uint16_t d; double c; };
-  auto block_of = [&](const RowOwner& o) -> std::pair<int, int> {   // (block kind, block index)
-    if (o.kind == kOwnNode) return {kOwnNode, unit_group[o.index]};
-    return {o.kind, o.index};
+  // ---- output lists (device_tables.h): every 32-byte sector of an instance's g / Jacobian-value row is written
+  // whole by the unit that owns its last element; elements owned by the preceding unit of the same CTA arrive
+  // through carry rows; sectors that straddle a CTA / set / row boundary fall back to single-element stores.
+  const int n_rom_blocks = pl.n_rom * n_ee, n_blocks = pl.n_dyn + n_rom_blocks + (int)groups.size();
+  auto block_id = [&](const RowOwner& o) {   // global block number: dynamic samples | (rom sample, foot) | node groups
+    if (o.kind == kOwnDyn) return o.index;
+    if (o.kind == kOwnRom) return pl.n_dyn + o.index;
+    return pl.n_dyn + n_rom_blocks + unit_group[o.index];
   };
-  std::vector<std::vector<OutItem>> jac_items[3], g_items[3];
-  jac_items[kOwnDyn].resize(pl.n_dyn); g_items[kOwnDyn].resize(pl.n_dyn);
-  jac_items[kOwnRom].resize(pl.n_rom); g_items[kOwnRom].resize(pl.n_rom);
-  jac_items[kOwnNode].resize(groups.size()); g_items[kOwnNode].resize(groups.size());
+  std::vector<int> pred(n_blocks, -1), carry0(n_blocks, 0);   // chained predecessor inside the CTA; first carry-in row of the block
+  for (int k = 0; k < pl.n_dyn; ++k) { if (k % kDynWarps) pred[k] = k - 1; carry0[k] = 46 + 6 * n_ee; }
+  for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) {
+    const int b = pl.n_dyn + k * n_ee + e;
+    if (k % kRomWarps) pred[b] = b - n_ee;
+    carry0[b] = kRomStateRows + kCarryRows * e;
+  }
+  for (int gi = 0; gi < (int)groups.size(); ++gi) { const int b = pl.n_dyn + n_rom_blocks + gi; if (gi % kNodeWarps) pred[b] = b - 1; carry0[b] = pl.node_rows; }
+  struct Elem { int block; uint16_t d; double c; };
+  std::vector<Elem> elems[2];   // [0]: Jacobian values (nnz), [1]: constraint values (m)
+  elems[0].resize(nnz); elems[1].resize(m);
   for (int r = 0; r < m; ++r) {
     const RowOwner& o = owner[r];
     if (o.kind < 0) return fail(TWB_ERR_UNSUPPORTED, "constraint row without an owner");
-    auto blk = block_of(o);
     uint32_t g_row = o.g_local, state0 = 1;
     if (o.kind == kOwnNode) { g_row = unit_g0[o.index] + o.g_local; state0 = unit_state0[o.index]; }
-    if (g_row >= kNoRow) return fail(TWB_ERR_UNSUPPORTED, "state block too large");
-    g_items[blk.first][blk.second].push_back({r, (uint16_t)g_row, 1.0});
+    const int blk = block_id(o);
+    elems[1][r] = Elem{blk, (uint16_t)g_row, 1.0};
     for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) {
       uint32_t a = em[s].a;
       if (o.kind == kOwnNode && a != S_ONE) a = state0 + (a - 1);
-      jac_items[blk.first][blk.second].push_back({s, (uint16_t)a, em[s].c0});
+      elems[0][s] = Elem{blk, (uint16_t)a, em[s].c0};
     }
   }
-  // pairs of 16-byte aligned elements; `parity` = parity of the instance's row start (odd row length, odd instance)
-  auto make_pairs = [&](const std::vector<OutItem>& items, int parity, int32_t* first, int32_t* count) {
-    *first = (int32_t)tb.pairs.size();
-    size_t i = 0;
-    while (i < items.size()) {
-      const int key = (items[i].off + parity) >> 1;
-      OutPair pr{key * 2 - parity, kNoRow, kNoRow}; OutCoef cf{0.0, 0.0};
-      while (i < items.size() && ((items[i].off + parity) >> 1) == key) {
-        if (((items[i].off + parity) & 1) == 0) { pr.d0 = items[i].d; cf.c0 = items[i].c; } else { pr.d1 = items[i].d; cf.c1 = items[i].c; }
-        ++i;
+  struct Entry { OutPair p; OutCoef c; };
+  // lists[block][array][class][0: pairs, 1: singles, 2: publish]
+  std::vector<std::array<std::array<std::array<std::vector<Entry>, 3>, kMaxClasses>, 2>> lists(n_blocks);
+  const int len[2] = {nnz, m};
+  const bool g_as_singles = true;   // constraint values go through the instance-tiled staging matrix GT (kernels.cu, StoreValuesTiled)
+  int n_classes[2];
+  for (int A = 0; A < 2; ++A) {
+    const int L = len[A];
+    const int NC = (A == 1 && g_as_singles) ? 1 : (L % 4 == 0) ? 1 : (L % 2 == 0) ? 2 : 4;
+    n_classes[A] = NC;
+    for (int q = 0; q < NC; ++q) {
+      const int c = (int)(((long long)q * L) % 4);   // position of the row's first element inside its sector
+      for (int S = 0; 4 * S < c + L; ++S) {
+        int first = std::max(0, 4 * S - c), last = std::min(L - 1, 4 * S + 3 - c);
+        const bool whole_in_row = (4 * S - c >= 0) && (4 * S + 3 - c <= L - 1);
+        const int writer = elems[A][last].block;
+        // constraint values: the g array is small and stays in L2, where partial-sector writes are cheap, and a
+        // unit owns only 3 - 10 of them: they are written with lane = instance (no transposition)
+        bool full = whole_in_row && (A == 0 || !g_as_singles);
+        for (int i = first; i <= last && full; ++i) { const int b = elems[A][i].block; if (b != writer && b != pred[writer]) full = false; }
+        if (!full) {
+          for (int i = first; i <= last; ++i) { const Elem& el = elems[A][i]; lists[el.block][A][q][1].push_back({OutPair{i, el.d, 0}, OutCoef{el.c, 0.0}}); }
+          continue;
+        }
+        uint16_t d[4]; double cf[4];
+        for (int h = 0; h < 4; ++h) {
+          const Elem& el = elems[A][first + h];
+          if (el.block == writer) { d[h] = el.d; cf[h] = el.c; }
+          else {   // owned by the preceding warp: published into this block's carry row
+            const int row = carry0[writer] + 3 * A + h;
+            lists[el.block][A][q][2].push_back({OutPair{row, el.d, 0}, OutCoef{el.c, 0.0}});
+            d[h] = (uint16_t)row; cf[h] = 1.0;
+          }
+        }
+        lists[writer][A][q][0].push_back({OutPair{first, d[0], d[1]}, OutCoef{cf[0], cf[1]}});
+        lists[writer][A][q][0].push_back({OutPair{first + 2, d[2], d[3]}, OutCoef{cf[2], cf[3]}});
       }
-      tb.pairs.push_back(pr); tb.coefs.push_back(cf);
     }
-    *count = (int32_t)tb.pairs.size() - *first;
+  }
+  pl.nc_jac = n_classes[0]; pl.nc_g = n_classes[1];
+  // self-check: for every alignment class, every element is written exactly once
+  for (int A = 0; A < 2; ++A) for (int q = 0; q < n_classes[A]; ++q) {
+    std::vector<int> hits(len[A], 0);
+    for (int b = 0; b < n_blocks; ++b) {
+      for (const Entry& en : lists[b][A][q][0]) { hits[en.p.off]++; hits[en.p.off + 1]++; }
+      for (const Entry& en : lists[b][A][q][1]) hits[en.p.off]++;
+    }
+    for (int i = 0; i < len[A]; ++i) if (hits[i] != 1) return fail(TWB_ERR_UNSUPPORTED, "output lists do not cover every element exactly once");
+  }
+  auto flush = [&](int block, OutList* out) {
+    *out = OutList{};
+    for (int A = 0; A < 2; ++A) for (int q = 0; q < n_classes[A]; ++q) {
+      OutRange* dst[3] = {&out->pairs[A][q], &out->singles[A][q], &out->publish[A][q]};
+      for (int w = 0; w < 3; ++w) {
+        const auto& v = lists[block][A][q][w];
+        dst[w]->first = (int32_t)tb.pairs.size(); dst[w]->count = (int32_t)v.size();
+        for (const Entry& en : v) { tb.pairs.push_back(en.p); tb.coefs.push_back(en.c); }
+      }
+    }
   };
-  auto make_list = [&](std::vector<OutItem>& jac, std::vector<OutItem>& g, OutList* out, int* max_pairs) {
-    auto by_off = [](const OutItem& a, const OutItem& b) { return a.off < b.off; };
-    std::sort(jac.begin(), jac.end(), by_off); std::sort(g.begin(), g.end(), by_off);
-    make_pairs(jac, 0, &out->jac[0], &out->n_jac[0]);
-    if (nnz & 1) make_pairs(jac, 1, &out->jac[1], &out->n_jac[1]); else { out->jac[1] = out->jac[0]; out->n_jac[1] = out->n_jac[0]; }
-    make_pairs(g, 0, &out->g[0], &out->n_g[0]);
-    if (m & 1) make_pairs(g, 1, &out->g[1], &out->n_g[1]); else { out->g[1] = out->g[0]; out->n_g[1] = out->n_g[0]; }
-    *max_pairs = std::max(*max_pairs, std::max(out->n_jac[0], out->n_jac[1]) + std::max(out->n_g[0], out->n_g[1]));
-  };
-  pl.max_dyn_pairs = pl.max_rom_pairs = pl.max_group_pairs = 0;
-  for (int k = 0; k < pl.n_dyn; ++k) make_list(jac_items[kOwnDyn][k], g_items[kOwnDyn][k], &tb.dyn[k].out, &pl.max_dyn_pairs);
-  for (int k = 0; k < pl.n_rom; ++k) make_list(jac_items[kOwnRom][k], g_items[kOwnRom][k], &tb.rom[k].out, &pl.max_rom_pairs);
+  for (int k = 0; k < pl.n_dyn; ++k) flush(k, &tb.dyn[k].out);
+  for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) flush(pl.n_dyn + k * n_ee + e, &tb.rom[k].out[e]);
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     NodeGroup ng{}; ng.kind = groups[gi].kind; ng.first = groups[gi].first; ng.count = groups[gi].count;
-    make_list(jac_items[kOwnNode][gi], g_items[kOwnNode][gi], &ng.out, &pl.max_group_pairs);
+    flush(pl.n_dyn + n_rom_blocks + (int)gi, &ng.out);
     tb.groups.push_back(ng);
   }
 

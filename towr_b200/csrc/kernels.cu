@@ -37,24 +37,21 @@ void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // p
 #define TWB_MARK(label, stream) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
 namespace {
 
-#ifndef TWB_DYN_WARPS
-#define TWB_DYN_WARPS 4
+#if TWB_FUSED
+#ifndef TWB_CTAS
+#define TWB_CTAS 2   // CTAs per SM the fused output kernel is compiled for (bounds its registers)
 #endif
+#else
 #ifndef TWB_DYN_CTAS
 #define TWB_DYN_CTAS 2
 #endif
-#ifndef TWB_ROM_WARPS
-#define TWB_ROM_WARPS 4
-#endif
 #ifndef TWB_ROM_CTAS
-#define TWB_ROM_CTAS 3
+#define TWB_ROM_CTAS 2
 #endif
-#ifndef TWB_NODE_WARPS
-#define TWB_NODE_WARPS 4
+#ifndef TWB_NODE_CTAS
+#define TWB_NODE_CTAS 2
 #endif
-constexpr int kDynWarps = TWB_DYN_WARPS;     // consecutive samples per CTA of DynOut (one instance tile)
-constexpr int kRomWarps = TWB_ROM_WARPS;     // consecutive samples per CTA of RomOut
-constexpr int kNodeWarps = TWB_NODE_WARPS;   // consecutive node groups per CTA of NodeOut
+#endif
 constexpr int kLD = 34;                      // leading dimension of a state block: 32 instances, padded; even keeps rows 16-byte aligned
 
 // output stores: streaming (evict-first) — the values are consumed by the host / a solver, not by these kernels
@@ -310,38 +307,6 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSa
     }
 }
 
-// ---- RangeOfMotionConstraint sample (all feet) --------------------------------
-// range_of_motion_constraint.cc:58-109: g_e = R^T (p_e - c); Jacobian state R^T and
-// D_e = d(R^T r_e)/d(theta) (DerivOfRotVecMult(t, r_W, true)).  The rotation and its derivative are
-// computed once per sample and shared by the feet.
-// Sk: local state rows 1.. (Sk[0..8] R^T, Sk[9 + 9e ..] D_e); gk: 3 constraint values per foot
-template <int kNEE>
-__device__ __forceinline__ void RomUnitEval(const SplineSample* __restrict__ sp, const ConstCol xs, const Col Sk, const Col gk) {
-  double c[3], th[3], unused[3];
-  EvalSpline<0>(sp + 0, xs, c, unused, unused);
-  EvalSpline<0>(sp + 1, xs, th, unused, unused);
-  const Trig tr = MakeTrig(th);
-  double R[3][3]; RotationMatrix(tr, R);
-  double dR[3][3][3]; RotationDerivative(tr, dR);
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int d = 0; d < 3; ++d) Sk[i * 3 + d] = R[d][i];
-#pragma unroll
-  for (int e = 0; e < kNEE; ++e) {
-    double pe[3];
-    EvalSpline<0>(sp + 2 + e, xs, pe, unused, unused);
-    const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) gk[3 * e + i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
-    double D[3][3]; RotVecDerivative<true>(dR, r, D);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) Sk[9 + 9 * e + i * 3 + d] = D[i][d];
-  }
-}
-
 // ---- analytic terrains: height_map_examples.cc:35-211 ------------------------
 struct TerrainPoint { double h, hx, hy, hxx; };
 __device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) {
@@ -511,122 +476,256 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
   }
 }
 
+// GT[b/32][r][b%32] -> g[b][r]: 32x32 tiles through shared memory, coalesced on both sides
+__global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ GT, double* __restrict__ g, int m, int nb) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const double* src = GT + ((size_t)blockIdx.y * m) * 32;
+#pragma unroll
+  for (int q = threadIdx.y; q < 32; q += 8) {
+    const int r = r0 + q;
+    if (r < m) tile[q][threadIdx.x] = __ldcs(src + (size_t)r * 32 + threadIdx.x);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = threadIdx.y; q < 32; q += 8) {
+    const int b = b0 + q, r = r0 + threadIdx.x;
+    if (b < nb && r < m) StoreOut(g + (size_t)b * m + r, tile[threadIdx.x][q]);
+  }
+}
+
 // ---- warp-collective output of one unit: lanes switch from "instance" to "pair of output elements" ----
 // out[j][off + h] = t[d_h][j] * c_h for the instances j = j0, j0 + jstep, .. < n_inst of the tile;
 // `out` points at element 0 of the tile's first instance, `stride` is the row length (nnz or m).
+// The list holds whole 32-byte sectors (two consecutive pairs = two adjacent lanes).
+__device__ __forceinline__ void LoadPair(const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs, int i, int n,
+                                         int* off, int* d0, int* d1, double* c0, double* c1) {
+  if (i < n) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(pairs) + i);
+    const double2 c = __ldg(reinterpret_cast<const double2*>(coefs) + i);
+    *off = (int)raw.x; *d0 = (int)(raw.y & 0xFFFFu); *d1 = (int)(raw.y >> 16); *c0 = c.x; *c1 = c.y;
+  }
+}
 __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
                                            int n_pairs, double* __restrict__ out, size_t stride, int j0, int jstep, int n_inst, int lane) {
   if (n_pairs <= 0) return;
-  int i = lane;
-  OutPair pr{0, kNoRow, kNoRow}; OutCoef cf{0.0, 0.0};
-  if (i < n_pairs) { const uint2 raw = __ldg(reinterpret_cast<const uint2*>(pairs) + i); pr.off = (int)raw.x; pr.d0 = raw.y & 0xFFFFu; pr.d1 = raw.y >> 16;
-                     const double2 c = __ldg(reinterpret_cast<const double2*>(coefs) + i); cf.c0 = c.x; cf.c1 = c.y; }
-  for (; i < n_pairs; i += 32) {
+  int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
+  LoadPair(pairs, coefs, lane, n_pairs, &off, &d0, &d1, &c0, &c1);
+  for (int i = lane; i < n_pairs; i += 32) {
     // prefetch the next entry of this lane under the stores of the current one
-    OutPair npr{0, kNoRow, kNoRow}; OutCoef ncf{0.0, 0.0};
-    if (i + 32 < n_pairs) { const uint2 raw = __ldg(reinterpret_cast<const uint2*>(pairs) + i + 32); npr.off = (int)raw.x; npr.d0 = raw.y & 0xFFFFu; npr.d1 = raw.y >> 16;
-                            const double2 c = __ldg(reinterpret_cast<const double2*>(coefs) + i + 32); ncf.c0 = c.x; ncf.c1 = c.y; }
-    double* o = out + pr.off;
-    if (pr.d0 != kNoRow && pr.d1 != kNoRow) {
-      const double* r0 = t + pr.d0 * kLD; const double* r1 = t + pr.d1 * kLD;
-      if (n_inst == 32 && jstep == 1) {
-#pragma unroll 16
-        for (int j = 0; j < 32; ++j) StoreOut2(o + j * stride, r0[j] * cf.c0, r1[j] * cf.c1);
-      } else {
-#pragma unroll 4
-        for (int j = j0; j < n_inst; j += jstep) StoreOut2(o + j * stride, r0[j] * cf.c0, r1[j] * cf.c1);
+    int noff = 0, nd0 = 0, nd1 = 0; double nc0 = 0.0, nc1 = 0.0;
+    LoadPair(pairs, coefs, i + 32, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
+    double* o = out + off;
+    const double* r0 = t + d0 * kLD; const double* r1 = t + d1 * kLD;
+    if (n_inst == 32 && jstep == 1) {
+      // rows are 16-byte aligned (kLD even): two instances per shared-memory load
+#pragma unroll 8
+      for (int j = 0; j < 32; j += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
+        StoreOut2(o, a.x * c0, b.x * c1); o += stride;
+        StoreOut2(o, a.y * c0, b.y * c1); o += stride;
       }
-    } else if (pr.d0 != kNoRow) {
-      const double* r0 = t + pr.d0 * kLD;
-      for (int j = j0; j < n_inst; j += jstep) StoreOut(o + j * stride, r0[j] * cf.c0);
-    } else if (pr.d1 != kNoRow) {
-      const double* r1 = t + pr.d1 * kLD;
-      for (int j = j0; j < n_inst; j += jstep) StoreOut(o + 1 + j * stride, r1[j] * cf.c1);
+    } else {
+#pragma unroll 4
+      for (int j = j0; j < n_inst; j += jstep) StoreOut2(o + j * stride, r0[j] * c0, r1[j] * c1);
     }
-    pr = npr; cf = ncf;
+    off = noff; d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1;
   }
 }
-// all outputs of one unit: Jacobian values (flags & 2) and constraint values (flags & 1)
-__device__ __forceinline__ void StoreUnit(const Plan& P, const double* t, const OutList& L, double* __restrict__ g_tile,
+// single elements: lane = instance (8-byte stores, one per instance).  The entries are fetched with one
+// coalesced load (lane = entry) and broadcast with shuffles, so a list costs one memory round trip.
+__device__ __forceinline__ void StoreSingles(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
+                                             int n, double* __restrict__ out, size_t stride, bool active, int lane) {
+#ifdef TWB_EXP_NOSINGLES
+  return;
+#endif
+  double* o = out + (size_t)lane * stride;
+  const double* tl = t + lane;
+  for (int base = 0; base < n; base += 32) {
+    uint2 raw = make_uint2(0u, 0u); double c = 0.0;
+    if (base + lane < n) { raw = __ldg(reinterpret_cast<const uint2*>(pairs) + base + lane); c = __ldg(reinterpret_cast<const double*>(coefs + base + lane)); }
+    const int cnt = min(32, n - base);
+    for (int s = 0; s < cnt; ++s) {
+      const int off = __shfl_sync(0xffffffffu, (int)raw.x, s), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), s);
+      const double cs = __shfl_sync(0xffffffffu, c, s);
+      if (active) StoreOut(o + off, tl[d * kLD] * cs);
+    }
+  }
+}
+// constraint values: lane = instance writes GT[row][lane] (instance-tiled, 256 contiguous bytes per row and
+// warp); TransposeOut turns the tiles into g[B][m] afterwards.  One unit owns only 3 - 10 constraint values per
+// instance — written straight into g[B][m] they would be 8-byte pieces of sectors shared with other units.
+__device__ __forceinline__ void StoreValuesTiled(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
+                                                 int n, double* __restrict__ gt_tile, int lane) {
+  const double* tl = t + lane;
+  for (int base = 0; base < n; base += 32) {
+    uint2 raw = make_uint2(0u, 0u); double c = 0.0;
+    if (base + lane < n) { raw = __ldg(reinterpret_cast<const uint2*>(pairs) + base + lane); c = __ldg(reinterpret_cast<const double*>(coefs + base + lane)); }
+    const int cnt = min(32, n - base);
+    for (int s = 0; s < cnt; ++s) {
+      const int off = __shfl_sync(0xffffffffu, (int)raw.x, s), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), s);
+      const double cs = __shfl_sync(0xffffffffu, c, s);
+      gt_tile[(size_t)off * 32 + lane] = tl[d * kLD] * cs;
+    }
+  }
+}
+// carry values for the next warp of the CTA: lane = instance, next[row][lane] = t[d][lane] * c
+__device__ __forceinline__ void PublishList(const double* t, double* next, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
+                                            int n, bool active, int lane) {
+  uint2 raw = make_uint2(0u, 0u); double c = 0.0;   // at most 3 entries per list
+  if (lane < n) { raw = __ldg(reinterpret_cast<const uint2*>(pairs) + lane); c = __ldg(reinterpret_cast<const double*>(coefs + lane)); }
+  for (int s = 0; s < n; ++s) {
+    const int row = __shfl_sync(0xffffffffu, (int)raw.x, s), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), s);
+    const double cs = __shfl_sync(0xffffffffu, c, s);
+    if (active) next[row * kLD + lane] = t[d * kLD + lane] * cs;
+  }
+}
+__device__ __forceinline__ OutRange LoadRange(const OutRange* r) {
+  const int2 v = __ldg(reinterpret_cast<const int2*>(r)); return OutRange{v.x, v.y};
+}
+// before the CTA barrier: hand the tail elements of this unit's last, incomplete sectors to the next warp
+__device__ __forceinline__ void PublishUnit(const Plan& P, const double* t, double* next, const OutList& L, unsigned flags, int lane) {
+#ifdef TWB_EXP_NOSINGLES
+  return;
+#endif
+  if (!(flags & 2u)) return;
+  const int nc = P.nc_jac;
+  for (int q = 0; q < nc; ++q) {
+    const OutRange r = LoadRange(&L.publish[0][q]);
+    if (r.count > 0) PublishList(t, next, P.pairs + r.first, P.coefs + r.first, r.count, (lane % nc) == q, lane);
+  }
+}
+// all outputs of one unit: Jacobian values (flags & 2) into the tile's rows of jac[B][nnz], constraint values
+// (flags & 1) into the tile of GT
+__device__ __forceinline__ void StoreUnit(const Plan& P, const double* t, const OutList& L, double* __restrict__ gt_tile,
                                           double* __restrict__ jac_tile, unsigned flags, int n_inst, int lane) {
+#ifdef TWB_EXP_NOSTORE   // timing experiment: compute phase only
+  return;
+#endif
+#ifdef TWB_EXP_NOG
+  flags &= ~1u;
+#endif
   if (flags & 2u) {
-    if (P.nnz & 1) {
-      StorePairs(t, P.pairs + L.jac[0], P.coefs + L.jac[0], L.n_jac[0], jac_tile, (size_t)P.nnz, 0, 2, n_inst, lane);
-      StorePairs(t, P.pairs + L.jac[1], P.coefs + L.jac[1], L.n_jac[1], jac_tile, (size_t)P.nnz, 1, 2, n_inst, lane);
-    } else {
-      StorePairs(t, P.pairs + L.jac[0], P.coefs + L.jac[0], L.n_jac[0], jac_tile, (size_t)P.nnz, 0, 1, n_inst, lane);
+    const int nc = P.nc_jac;
+    for (int q = 0; q < nc; ++q) {
+      const OutRange rp = LoadRange(&L.pairs[0][q]), rs = LoadRange(&L.singles[0][q]);
+      StorePairs(t, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, lane);
+      if (rs.count > 0) StoreSingles(t, P.pairs + rs.first, P.coefs + rs.first, rs.count, jac_tile, (size_t)P.nnz, lane < n_inst && (lane % nc) == q, lane);
     }
   }
   if (flags & 1u) {
-    if (P.m & 1) {
-      StorePairs(t, P.pairs + L.g[0], P.coefs + L.g[0], L.n_g[0], g_tile, (size_t)P.m, 0, 2, n_inst, lane);
-      StorePairs(t, P.pairs + L.g[1], P.coefs + L.g[1], L.n_g[1], g_tile, (size_t)P.m, 1, 2, n_inst, lane);
-    } else {
-      StorePairs(t, P.pairs + L.g[0], P.coefs + L.g[0], L.n_g[0], g_tile, (size_t)P.m, 0, 1, n_inst, lane);
-    }
+    const OutRange rs = LoadRange(&L.singles[1][0]);
+    StoreValuesTiled(t, P.pairs + rs.first, P.coefs + rs.first, rs.count, gt_tile, lane);
   }
 }
 // non-finite check of this lane's own column (rows 1 .. n_rows-1); flags instance b
-__device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int lane, int* __restrict__ status, int b, int nb) {
+__device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int lane, int* __restrict__ status, int b, int nb, int first_row = 1) {
   if (!status) return;
   double chk = 0.0;
-  for (int r = 1; r < n_rows; ++r) chk = fma(t[r * kLD + lane], 0.0, chk);
+  for (int r = first_row; r < n_rows; ++r) chk = fma(t[r * kLD + lane], 0.0, chk);
   if (chk != chk && b < nb) atomicOr(status + b, 1);
 }
 
 // DynamicConstraint: blockIdx.y = instance tile, warp = one of kDynWarps CONSECUTIVE samples, so a CTA writes
-// several KB of contiguous CSR values per instance (the samples' rows are adjacent) — DRAM page locality.
+// several KB of contiguous CSR values per instance (the samples' rows are adjacent) and the sectors shared by
+// two samples are completed through the carry rows.
 template <int kNEE>
-__global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, const double* __restrict__ XT, double* __restrict__ g,
-                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
-  extern __shared__ __align__(16) double out_smem[];
+__device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
+                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = blockIdx.x * kDynWarps + warp, b0 = blockIdx.y * 32;
-  if (k >= P.n_dyn) return;
-  constexpr int G0 = 40 + 6 * kNEE, n_rows = G0 + 6;   // local rows: 1 | 3 | 36 | 6 per foot | g (6)
-  double* t = out_smem + (size_t)warp * n_rows * kLD;
+  const int k = cta * kDynWarps + warp, b0 = tile * 32;
+  const bool valid = k < P.n_dyn;
+  constexpr int G0 = 40 + 6 * kNEE, n_rows = G0 + 6, block_rows = n_rows + kCarryRows;   // local rows: 1 | 3 | 36 | 6 per foot | g (6) | carry-in
+  double* t = out_smem + (size_t)warp * block_rows * kLD;
   const DynUnit* u = P.dyn + k;
-  t[lane] = 1.0;
-  DynamicUnit<kNEE>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
-  FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
-  __syncwarp();
-  StoreUnit(P, t, u->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
+  if (valid) {
+    t[lane] = 1.0;
+#ifndef TWB_EXP_NOCOMPUTE   // (timing experiment: store phase only)
+    DynamicUnit<kNEE>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
+    FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
+#endif
+    __syncwarp();
+    if (warp + 1 < kDynWarps) PublishUnit(P, t, t + block_rows * kLD, u->out, flags, lane);
+  }
+  __syncthreads();
+  if (valid) StoreUnit(P, t, u->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);   // g = GT: tile at b0 * m
 }
 
-// RangeOfMotionConstraint: blockIdx.y = instance tile, warp = one of kRomWarps consecutive samples, all feet
+// RangeOfMotionConstraint (range_of_motion_constraint.cc:58-109): g_e = R^T (p_e - c); Jacobian state R^T and
+// D_e = d(R^T r_e)/d(theta) (EulerConverter::DerivOfRotVecMult(t, r_W, true)).  blockIdx.y = instance tile,
+// warp = one of kRomWarps consecutive samples.  The rotation and its derivative are computed once per sample;
+// the feet then take turns: foot e's D_e and g_e overwrite the previous foot's state rows once its values have
+// been written, so a warp needs 22 state rows (+ 6 carry-in rows per foot) instead of 10 + 12 n_ee.
 template <int kNEE>
-__global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomOut(const Plan P, const double* __restrict__ XT, double* __restrict__ g,
-                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
-  extern __shared__ __align__(16) double out_smem[];
+__device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
+                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = blockIdx.x * kRomWarps + warp, b0 = blockIdx.y * 32;
-  if (k >= P.n_rom) return;
-  constexpr int G0 = 10 + 9 * kNEE, n_rows = G0 + 3 * kNEE;   // local rows: 1 | R^T 9 | D_e 9 per foot | g 3 per foot
-  double* t = out_smem + (size_t)warp * n_rows * kLD;
-  const RomUnit* u = P.rom + k;
+  const int k = cta * kRomWarps + warp, b0 = tile * 32;
+  const bool valid = k < P.n_rom;
+  constexpr int block_rows = kRomStateRows + kCarryRows * kNEE;
+  double* t = out_smem + (size_t)warp * block_rows * kLD;
+  const RomUnit* u = P.rom + (valid ? k : 0);
+  const SplineSample* __restrict__ sp = P.samples + __ldg(&u->sample0);
+  const ConstCol xs = TiledCol(XT, b0 + lane, P.n + 1);
+  const Col Sk{t + kLD + lane, kLD};   // local state rows 1..: R^T (0..8) | D_e (9..17) | g_e (18..20)
+  const int n_inst = min(32, nb - b0);
+  double* g_tile = g + (size_t)b0 * P.m; double* jac_tile = jac + (size_t)b0 * P.nnz;
   t[lane] = 1.0;
-  RomUnitEval<kNEE>(P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
-  FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
-  __syncwarp();
-  StoreUnit(P, t, u->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
+#ifndef TWB_EXP_NOCOMPUTE
+  double c[3], th[3], unused[3];
+  EvalSpline<0>(sp + 0, xs, c, unused, unused);
+  EvalSpline<0>(sp + 1, xs, th, unused, unused);
+  const Trig tr = MakeTrig(th);
+  double R[3][3]; RotationMatrix(tr, R);
+  double dR[3][3][3]; RotationDerivative(tr, dR);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Sk[i * 3 + d] = R[d][i];
+#endif
+#pragma unroll 1
+  for (int e = 0; e < kNEE; ++e) {
+#ifndef TWB_EXP_NOCOMPUTE
+    double pe[3];
+    EvalSpline<0>(sp + 2 + e, xs, pe, unused, unused);
+    const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
+    double D[3][3]; RotVecDerivative<true>(dR, r, D);
+    if (e > 0) __syncwarp();   // the previous foot's values have left the state rows
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Sk[18 + i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Sk[9 + i * 3 + d] = D[i][d];
+    if (valid) FlagNonFinite(t, kRomStateRows, lane, status, b0 + lane, nb, e == 0 ? 1 : 10);
+#endif
+    __syncwarp();
+    if (valid && warp + 1 < kRomWarps) PublishUnit(P, t, t + block_rows * kLD, u->out[e], flags, lane);
+    __syncthreads();
+    if (valid) StoreUnit(P, t, u->out[e], g_tile, jac_tile, flags, n_inst, lane);
+  }
 }
 
 // node groups: blockIdx.y = instance tile, warp = one of kNodeWarps consecutive groups
-__global__ void __launch_bounds__(kNodeWarps * 32) NodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ g,
-                                                           double* __restrict__ jac, int* __restrict__ status,
-                                                           const int* __restrict__ terrain_ids, int default_terrain, int nb,
-                                                           unsigned flags) {
-  extern __shared__ __align__(16) double node_smem[];
+__device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
+                                         int* __restrict__ status, const int* __restrict__ terrain_ids, int default_terrain, int nb,
+                                         unsigned flags, double* node_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gi = blockIdx.x * kNodeWarps + warp, b0 = blockIdx.y * 32, b = b0 + lane;
-  if (gi >= P.n_groups) return;
-  double* t = node_smem + (size_t)warp * kNodeStateRows * kLD;
+  const int gi = cta * kNodeWarps + warp, b0 = tile * 32, b = b0 + lane;
+  const bool valid = gi < P.n_groups;
+  const int block_rows = P.node_rows + kCarryRows;
+  double* t = node_smem + (size_t)warp * block_rows * kLD;
   const ConstCol xs = TiledCol(XT, b, P.n + 1);
-  const NodeGroup* grp = P.groups + gi;
+  const NodeGroup* grp = P.groups + (valid ? gi : 0);
   const int kind = __ldg(&grp->kind), first = __ldg(&grp->first), count = __ldg(&grp->count);
   t[lane] = 1.0;
   int n_rows = 1;
-  if (kind == kGroupForce) {
+#ifdef TWB_EXP_NOCOMPUTE
+  if (true) {
+#else
+  if (!valid) {
+#endif
+  } else if (kind == kGroupForce) {
     const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
     for (int q = 0; q < count; ++q)
       ForceUnitEval(P, P.force[first + q], terrain, xs, Col{t + (1 + 25 * q) * kLD + lane, kLD}, Col{t + (1 + 25 * count + 5 * q) * kLD + lane, kLD});
@@ -646,9 +745,11 @@ __global__ void __launch_bounds__(kNodeWarps * 32) NodeOut(const Plan P, const d
     if (flags & 1u) for (int q = 0; q < count; ++q) BaseMotionUnitEval(P, P.base_motion[first + q], xs, Col{t + (1 + 6 * q) * kLD + lane, kLD});
     n_rows = (flags & 1u) ? 1 + 6 * count : 1;
   }
-  FlagNonFinite(t, n_rows, lane, status, b, nb);
+  if (valid) FlagNonFinite(t, n_rows, lane, status, b, nb);
   __syncwarp();
-  StoreUnit(P, t, grp->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
+  if (valid && warp + 1 < kNodeWarps) PublishUnit(P, t, t + block_rows * kLD, grp->out, flags, lane);
+  __syncthreads();
+  if (valid) StoreUnit(P, t, grp->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
 }
 
 // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
@@ -672,24 +773,78 @@ __global__ void __launch_bounds__(128) CostKernel(const Plan P, const double* __
   if (cost) cost[b] = total_cost;
 }
 
+#if TWB_FUSED
+// One kernel writes a whole tile of rows: blockIdx.y = instance tile, blockIdx.x walks the tile's CTAs in row
+// order — dynamic samples, range-of-motion samples, node groups.
 template <int kNEE>
-cudaError_t LaunchDynRom(const Plan& P, const double* XT, double* g, double* jac, int* status, int nb, unsigned flags, int tiles,
-                         cudaStream_t s_dyn, cudaStream_t s_rom, int* count) {
+__global__ void __launch_bounds__(kWarps * 32, TWB_CTAS) EvalOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
+                                                              double* __restrict__ jac, int* __restrict__ status,
+                                                              const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags) {
+  extern __shared__ __align__(16) double out_smem[];
+  const int n_dyn_ctas = (P.n_dyn + kWarps - 1) / kWarps, n_rom_ctas = (P.n_rom + kWarps - 1) / kWarps;
+  int cta = blockIdx.x;
+  if (cta < n_dyn_ctas) { DynBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
+  cta -= n_dyn_ctas;
+  if (cta < n_rom_ctas) { RomBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
+  cta -= n_rom_ctas;
+  NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, cta, blockIdx.y);
+}
+#else
+template <int kNEE>
+__global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
+                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
+  extern __shared__ __align__(16) double out_smem[];
+  DynBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+}
+template <int kNEE>
+__global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
+                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
+  extern __shared__ __align__(16) double out_smem[];
+  RomBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+}
+__global__ void __launch_bounds__(kNodeWarps * 32, TWB_NODE_CTAS) NodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
+                                                           double* __restrict__ jac, int* __restrict__ status,
+                                                           const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags) {
+  extern __shared__ __align__(16) double out_smem[];
+  NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+}
+#endif
+
+// s: caller's stream (after TransposeIn); a0, a1: auxiliary streams already waiting on the transposition
+template <int kNEE>
+cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, int* status, const int* terrain_ids, int default_terrain,
+                      int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
+  const size_t row_bytes = (size_t)kLD * sizeof(double);
+  const int dyn_rows = 46 + 6 * kNEE + kCarryRows, rom_rows = kRomStateRows + kCarryRows * kNEE, node_rows = P.node_rows + kCarryRows;
   cudaError_t e = cudaSuccess;
-  if (P.n_dyn > 0) {
-    const size_t smem = (size_t)kDynWarps * (46 + 6 * kNEE) * kLD * sizeof(double);
-    e = cudaFuncSetAttribute(DynOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    DynOut<kNEE><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, s_dyn>>>(P, XT, g, jac, status, nb, flags);
-    ++*count; TWB_MARK("DynOut", s_dyn);
-  }
+#if TWB_FUSED
+  const int n_ctas = (P.n_dyn + kWarps - 1) / kWarps + (P.n_rom + kWarps - 1) / kWarps + (P.n_groups + kWarps - 1) / kWarps;
+  if (n_ctas == 0) return cudaSuccess;
+  const int rows = std::max(std::max(P.n_dyn > 0 ? dyn_rows : 0, P.n_rom > 0 ? rom_rows : 0), P.n_groups > 0 ? node_rows : 0);
+  const size_t smem = (size_t)kWarps * rows * row_bytes;
+  if ((e = cudaFuncSetAttribute(EvalOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  EvalOut<kNEE><<<dim3(n_ctas, tiles), kWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
+  ++*count; TWB_MARK("EvalOut", s);
+#else
   if (P.n_rom > 0) {
-    const size_t smem = (size_t)kRomWarps * (10 + 12 * kNEE) * kLD * sizeof(double);
-    e = cudaFuncSetAttribute(RomOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    RomOut<kNEE><<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles), kRomWarps * 32, smem, s_rom>>>(P, XT, g, jac, status, nb, flags);
-    ++*count; TWB_MARK("RomOut", s_rom);
+    const size_t smem = (size_t)kRomWarps * rom_rows * row_bytes;
+    if ((e = cudaFuncSetAttribute(RomOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    RomOut<kNEE><<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, nb, flags);
+    ++*count; TWB_MARK("RomOut", s);
   }
+  if (P.n_dyn > 0) {
+    const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
+    if ((e = cudaFuncSetAttribute(DynOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    DynOut<kNEE><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
+    ++*count; TWB_MARK("DynOut", a0);
+  }
+  if (P.n_groups > 0) {
+    const size_t smem = (size_t)kNodeWarps * node_rows * row_bytes;
+    if ((e = cudaFuncSetAttribute(NodeOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    NodeOut<<<dim3((P.n_groups + kNodeWarps - 1) / kNodeWarps, tiles), kNodeWarps * 32, smem, a1>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
+    ++*count; TWB_MARK("NodeOut", a1);
+  }
+#endif
   return cudaSuccess;
 }
 
@@ -697,10 +852,11 @@ cudaError_t LaunchDynRom(const Plan& P, const double* XT, double* g, double* jac
 
 // ---- host launchers ------------------------------------------------------------------
 
-// XT is the tiled iterate matrix of the whole batch (first tile = first instance of x / g / jac).
-// Streams: `s` carries TransposeIn -> RomOut; DynOut / NodeOut (+ CostKernel) run on aux[0] / aux[1]
-// after the transposition (ev[0]) and are joined back into `s` (ev[1], ev[2]).
-int LaunchEval(const Plan& P, const double* x, double* XT, double* g, double* jac, double* cost, double* grad,
+// XT / GT are the instance-tiled iterate and constraint-value matrices of the whole batch (first tile = first
+// instance of x / g / jac).  Streams: `s` carries TransposeIn -> [out kernels] -> TransposeOut; with separate
+// out kernels DynOut / NodeOut (and the CostKernel) run beside RomOut on aux0 / aux1 after the transposition
+// (ev[0]) and are joined back into `s` (ev[1], ev[2]) before TransposeOut.
+int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,
                int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
                cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches) {
   if (nb <= 0) return 0;
@@ -709,33 +865,27 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* g, double* ja
   if (serial) aux0 = aux1 = s;
   const int tiles = (nb + 31) / 32;
   const unsigned out_flags = flags & 3u;
+  const bool want_cost = (flags & 4u) && P.n_cost > 0;
   TWB_MARK("begin", s);
   TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, status, P.n, nb); ++count; TWB_MARK("TransposeIn", s);
-  if (!serial) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
+  const bool fork = !serial && (want_cost || (!TWB_FUSED && out_flags));
+  if (fork) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
   if (out_flags) {
     switch (P.n_ee) {
-      case 1: e = LaunchDynRom<1>(P, XT, g, jac, status, nb, out_flags, tiles, aux0, s, &count); break;
-      case 2: e = LaunchDynRom<2>(P, XT, g, jac, status, nb, out_flags, tiles, aux0, s, &count); break;
-      case 4: e = LaunchDynRom<4>(P, XT, g, jac, status, nb, out_flags, tiles, aux0, s, &count); break;
+      case 1: e = LaunchOut<1>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 2: e = LaunchOut<2>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 4: e = LaunchOut<4>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
       default: return (int)cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return (int)e;
-    if (P.n_groups > 0) {
-      const size_t smem = (size_t)kNodeWarps * kNodeStateRows * kLD * sizeof(double);
-      e = cudaFuncSetAttribute(NodeOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      NodeOut<<<dim3((P.n_groups + kNodeWarps - 1) / kNodeWarps, tiles), kNodeWarps * 32, smem, aux1>>>(P, XT, g, jac, status, terrain_ids, default_terrain, nb, out_flags);
-      ++count; TWB_MARK("NodeOut", aux1);
-    }
   }
-  if ((flags & 4u) && P.n_cost > 0) {
-    CostKernel<<<(nb + 127) / 128, 128, 0, aux1>>>(P, XT, cost, grad, nb); ++count; TWB_MARK("CostKernel", aux1);
-  }
-  if (!serial) {
+  if (want_cost) { CostKernel<<<(nb + 127) / 128, 128, 0, aux1>>>(P, XT, cost, grad, nb); ++count; TWB_MARK("CostKernel", aux1); }
+  if (fork) {
     cudaEventRecord(ev[1], aux0); cudaEventRecord(ev[2], aux1);
     cudaStreamWaitEvent(s, ev[1], 0); cudaStreamWaitEvent(s, ev[2], 0);
   }
+  if (out_flags & 1u) { TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
   return (int)cudaGetLastError();
 }

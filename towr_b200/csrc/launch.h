@@ -14,10 +14,10 @@ namespace twb {
 extern void (*g_after_launch)(const char* label, cudaStream_t stream);
 
 // One batched evaluation of `nb` instances.  XT is [tiles][n+1][32] (zero-initialised once; row n stays 0;
-// tile = 32 consecutive instances).  x, g, jac, cost, grad, status and terrain_ids point at the first
+// tile = 32 consecutive instances), GT is [tiles][m][32] (staging of the constraint values).  x, g, jac, cost, grad, status and terrain_ids point at the first
 // instance.  `flags` are the TWB_EVAL_* bits.  Work is enqueued on `s` and on two auxiliary streams that
 // are forked from / joined back into `s` with ev[0..2].
-int LaunchEval(const Plan& P, const double* x, double* XT, double* g, double* jac, double* cost, double* grad,
+int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,
                int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
                cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches);
 
