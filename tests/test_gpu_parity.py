@@ -13,7 +13,7 @@ from tolerance import check_rows, check_sets
 pytestmark = pytest.mark.gpu
 
 
-def _compare(name, B, terrain=None, terrains=None, costs=None, **kw):
+def _compare(name, B, terrain=None, terrains=None, costs=None, strict=1e-4, **kw):
     f = tb.make_formulation(name, terrain=terrain, **kw)
     if costs:
         f.params_.costs_ = costs
@@ -31,7 +31,7 @@ def _compare(name, B, terrain=None, terrains=None, costs=None, **kw):
     bad_g, strict_g, worst_g = check_sets(out["g"], ref["g"], p.constraint_sets())
     assert bad_j == 0, (bad_j, worst_j)
     assert bad_g == 0, (bad_g, worst_g)
-    assert strict_j < 1e-4 and strict_g < 1e-4   # entries missing the bare 1e-12/1e-14 criterion are rare
+    assert strict_j < strict and strict_g < strict   # entries missing the bare (unscaled) 1e-12/1e-14 criterion are rare
     assert not out["status"].any()
     return p, out, ref
 
@@ -52,6 +52,37 @@ def test_anymal_mixed_terrains_config5():
     B = 63                                      # ragged: not a multiple of the CTA group size
     terr = np.array([tb.SLOPE, tb.CHIMNEY, tb.GAP] * 21, np.int32)
     _compare("anymal_trot_mixed", B, terrains=terr)
+
+
+def test_hyq_gallop_gap_durations_config4():
+    """Phase durations optimised: PhaseSpline / PhaseDurations Jacobians, TotalDurationConstraint."""
+    # optimised durations enter as T^-2 .. T^-4 (std::pow in the reference, products here: 1 ulp apart) in front of
+    # cancelling sums, inside rows that also hold force-scaled entries (~1e3): more entries need the row scale
+    p, out, ref = _compare("hyq_gallop_gap", 48, strict=1e-2)
+    (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == "totalduration-2"]
+    assert np.array_equal(out["g"][:, r0], ref["g"][:, r0])
+
+
+def test_durations_other_robots_and_terrains():
+    f = tb.make_formulation("hopper"); f.params_.OptimizePhaseDurations()
+    spec = f.to_spec(); p = tb.Problem(spec)
+    X = synthetic_iterates(p, 33)
+    out = p.batch(33).eval_host(X)
+    ref = oracle_lib.batch_eval(spec, X)
+    assert ref["rc"] == 0
+    assert check_rows(out["jac"], ref["jac"], p.row_ptr())[0] == 0
+    assert check_sets(out["g"], ref["g"], p.constraint_sets())[0] == 0
+    f = tb.make_formulation("biped_walk_stairs", terrain=tb.SLOPE); f.params_.OptimizePhaseDurations()
+    spec = f.to_spec(); p = tb.Problem(spec)
+    X = synthetic_iterates(p, 40)
+    X[3] = p.GetVariableValues()                 # nominal durations: samples sit exactly on phase junctions
+    out = p.batch(40).eval_host(X)
+    ref = oracle_lib.batch_eval(spec, X)
+    assert check_rows(out["jac"], ref["jac"], p.row_ptr())[0] == 0
+    assert check_sets(out["g"], ref["g"], p.constraint_sets())[0] == 0
+    X[5, p.n - 3:] = 5.0                         # durations summing to more than T: flagged, not fatal
+    out = p.batch(40).eval_host(X)
+    assert out["status"][5] & 2 and not (out["status"][4] & 2)
 
 
 def test_every_terrain_go1():

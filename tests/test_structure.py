@@ -22,7 +22,26 @@ CASES = [
     ("anymal_trot_mixed", tb.CHIMNEY_LR, dict(goal_xy=(1.2, -0.2))),
     ("anymal_trot_block_base_rom", None, {}),
     ("hopper_base_rom", None, {}),
+    ("hyq_gallop_gap", None, {}),                      # BASELINE configs[3]: phase durations optimised
+    ("hyq_gallop_gap", tb.STAIRS, dict(t_total=2.4)),
 ]
+
+
+def test_duration_optimised_variants_match_oracle():
+    """OptimizePhaseDurations on the other robots: ee-schedule sets, dense PhaseSpline pattern, total-duration rows."""
+    for name in ("hopper", "biped_walk_stairs", "anymal_trot_block"):
+        f = tb.make_formulation(name); f.params_.OptimizePhaseDurations()
+        spec = f.to_spec()
+        p = tb.Problem(spec); o = oracle_lib.Oracle(spec)
+        assert (p.n, p.m, p.nnz) == (o.n, o.m, o.nnz)
+        rp, ci = o.structure()
+        assert np.array_equal(p.row_ptr(), rp) and np.array_equal(p.structure()[1], ci)
+        for a, b in zip(p.bounds(), o.bounds()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(p.GetVariableValues(), o.x0())
+        assert p.variable_sets() == o.variable_sets() and p.constraint_sets() == o.constraint_sets()
+    p4 = tb.Problem(tb.make_formulation("hyq_gallop_gap").to_spec())
+    assert (p4.n, p4.m, p4.nnz) == (712, 930, 54516)   # SURVEY.md 8d / BASELINE.md config 4
 
 
 @pytest.mark.parametrize("name,terrain,kw", CASES)
@@ -97,11 +116,6 @@ def test_terrain_heights_match_oracle():
 
 
 def test_unsupported_and_invalid_specs():
-    f = tb.make_formulation("hyq_gallop_gap")
-    assert f.params_.IsOptimizeTimings()
-    with pytest.raises(tb.TowrB200Error) as e:
-        tb.Problem(f.to_spec())
-    assert e.value.code == capi.ERR_UNSUPPORTED
     s = tb.make_formulation("hopper").to_spec(); s.n_ee = 2
     with pytest.raises(tb.TowrB200Error) as e:
         tb.Problem(s)

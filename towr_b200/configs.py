@@ -93,6 +93,9 @@ def synthetic_iterates(problem, batch, seed=1234, first=0):
     for b in range(batch):
         rng = np.random.default_rng(seed + first + b)
         X[b] = x0 + sig * rng.standard_normal(problem.n)
+        for name, start, count in problem.variable_sets():
+            if name.startswith("ee-schedule"):   # durations: nominal x U[0.9, 1.1] (their sum stays below T)
+                X[b, start:start + count] = x0[start:start + count] * rng.uniform(0.9, 1.1, count)
     for name, start, count in problem.variable_sets():
         if name == "base-ang":           # keep pitch/yaw nodes within +-1 rad (far from gimbal lock)
             blk = X[:, start:start + count].reshape(batch, -1, 6)
@@ -107,6 +110,8 @@ def synthetic_iterates_fast(problem, batch, seed=1234):
     rng = np.random.default_rng(seed)
     X = x0 + sig * rng.standard_normal((batch, problem.n))
     for name, start, count in problem.variable_sets():
+        if name.startswith("ee-schedule"):
+            X[:, start:start + count] = x0[start:start + count] * rng.uniform(0.9, 1.1, (batch, count))
         if name == "base-ang":
             blk = X[:, start:start + count].reshape(batch, -1, 6)
             blk[:, :, :3] = np.clip(blk[:, :, :3], -1.0, 1.0)

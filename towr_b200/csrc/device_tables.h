@@ -24,6 +24,33 @@ struct alignas(16) SplineSample {   // 96 bytes = six 16-byte loads
   int16_t pad[4];
 };
 
+// ---- phase-duration optimisation (Parameters::OptimizePhaseDurations) --------------------------------
+// With "ee-schedule" variable sets the foot splines are PhaseSplines (phase_spline.cc): their polynomial
+// durations, hence the active polynomial and the local time of every constraint sample, depend on the
+// iterate.  A SplineSample with xi[0] == kPhaseMarker refers to such a spline: xi[1] = index into
+// Plan::phase_defs, T = the GLOBAL sample time.
+constexpr uint16_t kPhaseMarker = 0xFFFFu;
+struct PhasePoly {       // one polynomial of a phase-based node set (nodes_variables_phase_based.cc:38-89)
+  int16_t xi[12];        // x indices of p0[3], v0[3], p1[3], v1[3] (zero slot if not optimised)
+  int16_t phase, n_in_phase, k_in_phase, pad;
+};
+struct PhaseSplineDef {
+  int32_t poly0, n_polys;     // range in Plan::phase_polys
+  int32_t sched0, n_phases;   // x index of the foot's first duration variable; number of phases (variables: n_phases - 1)
+  double t_total;
+};
+// Work item of the PhaseJac kernel: the Jacobian entries of one constraint sample w.r.t. the ee-motion /
+// ee-force node variables (active polynomial only — everything else stays at the zero the output kernels
+// wrote) and w.r.t. the phase durations.
+enum PhaseUnitKind : int32_t { kPhaseDyn = 0, kPhaseRom = 1, kPhaseTotal = 2 };
+struct PhaseUnit {
+  int32_t kind;
+  int32_t row0;               // dynamic: first of the sample's 6 rows; total duration: unused
+  int32_t sample_lin, sample_ang;   // fixed-duration samples of the base splines (Plan::samples)
+  int32_t rows[kMaxEE];       // range of motion: first of the foot's 3 rows; total duration: the foot's row
+  double t;                   // global sample time
+};
+
 // ---- output lists -------------------------------------------------------------
 // Every value a unit produces — a CSR Jacobian value or a constraint value — is
 //     out[instance][off + h] = state[d_h][instance] * c_h,     h = 0, 1
@@ -141,6 +168,12 @@ struct Plan {
   const double* dyn_ang_basis;  // [n_dyn][12]: base-ang basis of the active polynomial, {pos, vel, acc} x {p0, v0, p1, v1}
   const OutPair* pairs;
   const OutCoef* coefs;
+  // phase-duration optimisation (all null / 0 otherwise)
+  int n_phase_units, n_phase_defs;
+  const PhaseSplineDef* phase_defs;   // [2 * n_ee]: ee-motion_e at 2e, ee-force_e at 2e + 1
+  const PhasePoly* phase_polys;
+  const PhaseUnit* phase_units;
+  const int32_t* slot_of;             // [m][n]: CSR slot of (row, column) or -1
 };
 
 }  // namespace twb

@@ -184,7 +184,7 @@ int EnvInt(const char* name, int def, int lo, int hi) {
 struct Emit { int row, col; uint32_t a; double c0; };   // a: local state row of the owning unit (0 = the constant 1)
 
 // Who computes a constraint row: a dynamic sample, a range-of-motion sample (all feet) or a node unit.
-enum OwnerKind { kOwnDyn, kOwnRom, kOwnNode };
+enum OwnerKind { kOwnDyn, kOwnRom, kOwnNode, kOwnPhase };   // kOwnPhase: rows written by the PhaseJac kernel (total duration)
 struct RowOwner { int kind = -1, index = -1; uint32_t g_local = 0; };   // g_local: state row of the row's value inside the unit
 // node unit before grouping: kind, index into its table, rows of local state / values it needs
 struct NodeUnitRef { int kind, index, n_state, n_g, set_id; };
@@ -215,7 +215,6 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     if (sp.constraints[i] == TWB_C_TOTAL_TIME) optimize_timings = true;  // parameters.cc:128-135
     if (sp.constraints[i] < 0 || sp.constraints[i] > TWB_C_BASE_ACC) return fail(TWB_ERR_INVALID, "constraint not defined!");
   }
-  if (optimize_timings) return fail(TWB_ERR_UNSUPPORTED, "phase-duration optimisation (PhaseSpline) is not served by the device path yet");
 
   // Parameters::GetTotalTime, parameters.cc:112-126
   double T = 0.0; for (int i = 0; i < sp.n_phases[0]; ++i) T += sp.phase_durations[0][i];
@@ -237,6 +236,10 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     sets.push_back(MakeForceSet("ee-force_" + std::to_string(e), sp.n_phases[e], sp.in_contact_at_start[e] != 0, sp.force_polynomials_per_stance_phase));
   n = 0; var_sets.clear();
   for (auto& s : sets) { s.offset = n; var_sets.push_back({s.name, n, s.n_vars}); n += s.n_vars; }
+  // MakeContactScheduleVariables (nlp_formulation.cc:183-198): PhaseDurations sets "ee-schedule<ee>" hold all but the last phase
+  std::vector<int> sched0(n_ee, -1);
+  if (optimize_timings)
+    for (int e = 0; e < n_ee; ++e) { sched0[e] = n; var_sets.push_back({"ee-schedule" + std::to_string(e), n, sp.n_phases[e] - 1}); n += sp.n_phases[e] - 1; }
   if (n + 1 > 32767) return fail(TWB_ERR_UNSUPPORTED, "more than 32766 variables");
   const int zero_slot = n;
   NodeSet& lin = sets[0]; NodeSet& ang = sets[1];
@@ -282,6 +285,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     x_lower.insert(x_lower.end(), s.lo.begin(), s.lo.end());
     x_upper.insert(x_upper.end(), s.up.begin(), s.up.end());
   }
+  if (optimize_timings)   // PhaseDurations::GetValues / GetBounds, phase_durations.cc:68-77, 102-110
+    for (int e = 0; e < n_ee; ++e)
+      for (int i = 0; i + 1 < sp.n_phases[e]; ++i) {
+        x0.push_back(sp.phase_durations[e][i]); x_lower.push_back(sp.bound_phase_duration_min); x_upper.push_back(sp.bound_phase_duration_max);
+      }
 
   // ---- splines (spline_holder.cc:35-61, fixed durations)
   auto poly_durations = [&](const NodeSet& s, int e) {  // nodes_variables_phase_based.cc:78-89
@@ -295,6 +303,36 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
 
   // ---- units and their Jacobian entries
   HostTables& tb = tables; tb = HostTables{};
+  // foot splines: fixed-duration samples, or a reference to the PhaseSpline when the durations are optimised
+  auto foot_sample = [&](int e, int kind, double t) {   // kind 0: ee-motion, 1: ee-force
+    if (!optimize_timings) return MakeSample(kind == 0 ? sp_motion[e] : sp_force[e], t, zero_slot);
+    SplineSample o{};
+    o.T = t; o.xi[0] = (int16_t)kPhaseMarker; o.xi[1] = (int16_t)(2 * e + kind);
+    return o;
+  };
+  if (optimize_timings) {
+    for (int e = 0; e < n_ee; ++e)
+      for (int kind = 0; kind < 2; ++kind) {
+        const NodeSet& ns = kind == 0 ? motion(e) : force(e);
+        PhaseSplineDef def{}; def.poly0 = (int32_t)tb.phase_polys.size(); def.n_polys = (int32_t)ns.poly.size();
+        def.sched0 = sched0[e]; def.n_phases = sp.n_phases[e];
+        def.t_total = 0.0; for (int i = 0; i < sp.n_phases[e]; ++i) def.t_total += sp.phase_durations[e][i];   // std::accumulate, phase_durations.cc:47
+        for (int p = 0; p < (int)ns.poly.size(); ++p) {
+          PhasePoly pp{};
+          for (int side = 0; side < 2; ++side) for (int deriv = 0; deriv < 2; ++deriv) for (int dim = 0; dim < 3; ++dim)
+            pp.xi[side * 6 + deriv * 3 + dim] = XIndex(ns, p + side, deriv, dim, zero_slot);
+          pp.phase = (int16_t)ns.poly[p].phase; pp.n_in_phase = (int16_t)ns.poly[p].n_in_phase; pp.k_in_phase = (int16_t)ns.poly[p].k_in_phase;
+          tb.phase_polys.push_back(pp);
+        }
+        tb.phase_defs.push_back(def);
+      }
+  }
+  // PhaseSpline pattern (phase_spline.cc:45-51): every variable of the set is structurally non-zero in the row of its dimension
+  auto all_vars = [&](const NodeSet& ns) {
+    std::vector<std::pair<int, int>> v(ns.n_vars, {-1, -1});   // (column, dim)
+    for (int nd = 0; nd < ns.n_nodes; ++nd) for (int k = 0; k < 6; ++k) { int var = ns.var[nd][k]; if (var >= 0) v[var] = {ns.offset + var, k % 3}; }
+    return v;
+  };
   Plan& pl = tb.plan;
   const uint32_t S_ONE = 0;      // local row 0 of every unit's state block is the constant 1
 
@@ -342,8 +380,12 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           // spline samples: base-lin, base-ang, ee-motion.., ee-force..
           tb.samples.push_back(MakeSample(sp_lin, t, zero_slot));
           tb.samples.push_back(MakeSample(sp_ang, t, zero_slot));
-          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(MakeSample(sp_motion[e], t, zero_slot));
-          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(MakeSample(sp_force[e], t, zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(foot_sample(e, 0, t));
+          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(foot_sample(e, 1, t));
+          if (optimize_timings) {
+            PhaseUnit pu{}; pu.kind = kPhaseDyn; pu.row0 = row; pu.sample_lin = du.sample0; pu.sample_ang = du.sample0 + 1; pu.t = t;
+            tb.phase_units.push_back(pu);
+          }
           int p; double tl;
           // base-lin: angular rows = -sum_e [f_e]x dc ; linear rows = m * d(acc)
           Locate(sp_lin, t, &p, &tl);
@@ -367,7 +409,17 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             for (int q = 0; q < 4; ++q) tb.dyn_ang_basis.push_back(bv[3 * q].val);
             for (int q = 0; q < 4; ++q) tb.dyn_ang_basis.push_back(ba[3 * q].val);
           }
-          for (int e = 0; e < n_ee; ++e) {
+          for (int e = 0; e < n_ee && optimize_timings; ++e) {
+            // structural entries only (value 0 from the output kernel); the PhaseJac kernel overwrites the active ones
+            for (auto& cv : all_vars(motion(e))) for (int i = 0; i < 3; ++i) if (i != cv.second) emit1(row + i, cv.first, S_ONE, 0.0);
+            for (auto& cv : all_vars(force(e))) {
+              for (int i = 0; i < 3; ++i) if (i != cv.second) emit1(row + i, cv.first, S_ONE, 0.0);
+              emit1(row + 3 + cv.second, cv.first, S_ONE, 0.0);
+            }
+            // ee-schedule: JacWrtForce + JacWrtEEPos of the dense 3 x (P-1) duration Jacobians (dynamic_constraint.cc:106-112)
+            for (int ph = 0; ph + 1 < sp.n_phases[e]; ++ph) for (int r = 0; r < 6; ++r) emit1(row + r, sched0[e] + ph, S_ONE, 0.0);
+          }
+          for (int e = 0; e < n_ee && !optimize_timings; ++e) {
             // ee-motion: angular rows = [f_e]x dp_e
             Locate(sp_motion[e], t, &p, &tl);
             for (auto& b : Basis(sp_motion[e], p, tl, kPos))
@@ -399,8 +451,13 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           tb.rom.push_back(ru);
           tb.samples.push_back(MakeSample(sp_lin, ts[k], zero_slot));
           tb.samples.push_back(MakeSample(sp_ang, ts[k], zero_slot));
-          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(MakeSample(sp_motion[e], ts[k], zero_slot));
+          for (int e = 0; e < n_ee; ++e) tb.samples.push_back(foot_sample(e, 0, ts[k]));
+          if (optimize_timings) {
+            PhaseUnit pu{}; pu.kind = kPhaseRom; pu.sample_lin = ru.sample0; pu.sample_ang = ru.sample0 + 1; pu.t = ts[k];
+            tb.phase_units.push_back(pu);   // rows[] filled below
+          }
         }
+        const size_t first_rom_phase_unit = tb.phase_units.size() - (optimize_timings ? (size_t)pl.n_rom : 0);
         for (int e = 0; e < n_ee; ++e) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
           for (int k = 0; k < pl.n_rom; ++k) {
@@ -416,6 +473,12 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             Locate(sp_ang, t, &p, &tl);   // d(R^T r)/dtheta ; row X does not depend on roll
             for (auto& b : Basis(sp_ang, p, tl, kPos)) for (int i = 0; i < 3; ++i)
               if (!(i == 0 && b.dim == 0)) emit1(row + i, ang.offset + b.var, sd + i * 3 + b.dim, b.val);
+            if (optimize_timings) {
+              tb.phase_units[first_rom_phase_unit + k].rows[e] = row;
+              for (auto& cv : all_vars(motion(e))) for (int i = 0; i < 3; ++i) emit1(row + i, cv.first, S_ONE, 0.0);
+              for (int ph = 0; ph + 1 < sp.n_phases[e]; ++ph) for (int i = 0; i < 3; ++i) emit1(row + i, sched0[e] + ph, S_ONE, 0.0);
+              continue;
+            }
             Locate(sp_motion[e], t, &p, &tl);  // R^T dp_e
             for (auto& b : Basis(sp_motion[e], p, tl, kPos)) for (int i = 0; i < 3; ++i) emit1(row + i, motion(e).offset + b.var, sb + i * 3 + b.dim, b.val);
           }
@@ -547,6 +610,18 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         }
         break;
       }
+      case TWB_C_TOTAL_TIME: {  // total_duration_constraint.cc:36-72 — written by the PhaseJac kernel
+        PhaseUnit pu{}; pu.kind = kPhaseTotal;
+        for (int e = 0; e < n_ee; ++e) {
+          int row = add_set("totalduration-" + std::to_string(e), 1);
+          bound(row, 0.1, T - 0.2);
+          own(row, kOwnPhase, e, 0);
+          pu.rows[e] = row;
+          for (int ph = 0; ph + 1 < sp.n_phases[e]; ++ph) emit1(row, sched0[e] + ph, S_ONE, 1.0);
+        }
+        tb.phase_units.push_back(pu);
+        break;
+      }
       default: return fail(TWB_ERR_INVALID, "constraint not defined!");
     }
   }
@@ -590,7 +665,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   // whole by the unit that owns its last element; elements owned by the preceding unit of the same CTA arrive
   // through carry rows; sectors that straddle a CTA / set / row boundary fall back to single-element stores.
   const int n_rom_blocks = pl.n_rom * n_ee, n_blocks = pl.n_dyn + n_rom_blocks + (int)groups.size();
-  auto block_id = [&](const RowOwner& o) {   // global block number: dynamic samples | (rom sample, foot) | node groups
+  auto block_id = [&](const RowOwner& o) {   // global block number: dynamic samples | (rom sample, foot) | node groups; -1: not an output-kernel row
+    if (o.kind == kOwnPhase) return -1;
     if (o.kind == kOwnDyn) return o.index;
     if (o.kind == kOwnRom) return pl.n_dyn + o.index;
     return pl.n_dyn + n_rom_blocks + unit_group[o.index];
@@ -635,12 +711,16 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         int first = std::max(0, 4 * S - c), last = std::min(L - 1, 4 * S + 3 - c);
         const bool whole_in_row = (4 * S - c >= 0) && (4 * S + 3 - c <= L - 1);
         const int writer = elems[A][last].block;
+        if (writer < 0) {   // sector ends in a row of the PhaseJac kernel: the output kernels' elements in it are singles
+          for (int i = first; i <= last; ++i) { const Elem& el = elems[A][i]; if (el.block >= 0) lists[el.block][A][q][1].push_back({OutPair{i, el.d, 0}, OutCoef{el.c, 0.0}}); }
+          continue;
+        }
         // constraint values: the g array is small and stays in L2, where partial-sector writes are cheap, and a
         // unit owns only 3 - 10 of them: they are written with lane = instance (no transposition)
         bool full = whole_in_row && (A == 0 || !g_as_singles);
-        for (int i = first; i <= last && full; ++i) { const int b = elems[A][i].block; if (b != writer && b != pred[writer]) full = false; }
+        for (int i = first; i <= last && full; ++i) { const int b = elems[A][i].block; if (b != writer && (b < 0 || b != pred[writer])) full = false; }
         if (!full) {
-          for (int i = first; i <= last; ++i) { const Elem& el = elems[A][i]; lists[el.block][A][q][1].push_back({OutPair{i, el.d, 0}, OutCoef{el.c, 0.0}}); }
+          for (int i = first; i <= last; ++i) { const Elem& el = elems[A][i]; if (el.block >= 0) lists[el.block][A][q][1].push_back({OutPair{i, el.d, 0}, OutCoef{el.c, 0.0}}); }
           continue;
         }
         uint16_t d[4]; double cf[4];
@@ -666,7 +746,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
       for (const Entry& en : lists[b][A][q][0]) { hits[en.p.off]++; hits[en.p.off + 1]++; }
       for (const Entry& en : lists[b][A][q][1]) hits[en.p.off]++;
     }
-    for (int i = 0; i < len[A]; ++i) if (hits[i] != 1) return fail(TWB_ERR_UNSUPPORTED, "output lists do not cover every element exactly once");
+    for (int i = 0; i < len[A]; ++i) if (hits[i] != (elems[A][i].block >= 0 ? 1 : 0)) return fail(TWB_ERR_UNSUPPORTED, "output lists do not cover every element exactly once");
   }
   auto flush = [&](int block, OutList* out) {
     *out = OutList{};
@@ -705,6 +785,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     has_cost = true;
   }
 
+  if (optimize_timings) {   // (row, column) -> CSR slot, for the PhaseJac kernel
+    tb.slot_of.assign((size_t)m * n, -1);
+    for (int r = 0; r < m; ++r) for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) tb.slot_of[(size_t)r * n + col_idx[s]] = s;
+  }
+  pl.n_phase_units = (int)tb.phase_units.size(); pl.n_phase_defs = (int)tb.phase_defs.size();
   // ---- plan scalars
   pl.n = n; pl.m = m; pl.nnz = nnz; pl.n_ee = n_ee;
   pl.n_groups = (int)tb.groups.size(); pl.n_cost = (int)tb.cost.size();

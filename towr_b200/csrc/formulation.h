@@ -46,6 +46,10 @@ struct HostTables {
   std::vector<OutPair> pairs;
   std::vector<OutCoef> coefs;
   std::vector<double> dyn_ang_basis;
+  std::vector<PhaseSplineDef> phase_defs;
+  std::vector<PhasePoly> phase_polys;
+  std::vector<PhaseUnit> phase_units;
+  std::vector<int32_t> slot_of;
 };
 
 class Formulation {

@@ -99,10 +99,50 @@ __device__ __forceinline__ SampleRegs LoadSample(const SplineSample* __restrict_
   for (int i = 0; i < 6; ++i) { r.xi[2 * i] = (int)(v[i] & 0xFFFFu); r.xi[2 * i + 1] = (int)(v[i] >> 16); }
   return r;
 }
+// ---- PhaseSpline (phase_spline.cc, phase_durations.cc): polynomial durations are functions of the iterate ----
+// Active polynomial and local time of global time t: PhaseDurations::SetVariables (phase_durations.cc:79-100),
+// NodesVariablesPhaseBased::ConvertPhaseToPolyDurations (nodes_variables_phase_based.cc:78-89),
+// Spline::GetSegmentID / GetLocalTime (spline.cc:48-78) — same operations in the same order, per instance.
+struct PhaseLoc { int poly; double tl, T, last; };
+__device__ __forceinline__ PhaseLoc LocatePhasePoly(const Plan& P, const PhaseSplineDef& def, double t, const ConstCol xs) {
+  double sum = 0.0;
+  for (int i = 0; i + 1 < def.n_phases; ++i) sum += xs[def.sched0 + i];
+  PhaseLoc o; o.last = def.t_total - sum; o.poly = def.n_polys - 1; o.tl = t; o.T = 0.0;
+  const double eps = 1e-10;
+  double acc = 0.0, tl_run = t; bool found = false;
+  for (int p = 0; p < def.n_polys; ++p) {
+    const PhasePoly* pp = P.phase_polys + def.poly0 + p;
+    const int ph = pp->phase;
+    const double d = (ph == def.n_phases - 1) ? o.last : xs[def.sched0 + ph];
+    const double Tp = d / (double)pp->n_in_phase;
+    acc += Tp;
+    if (!found) {
+      if (acc >= t - eps || p == def.n_polys - 1) { found = true; o.poly = p; o.T = Tp; o.tl = tl_run; }
+      tl_run -= Tp;
+    }
+  }
+  return o;
+}
 // kWant: 0 position; 1 position + acceleration; 2 position + velocity + acceleration
 template <int kWant>
-__device__ __forceinline__ void EvalSpline(const SplineSample* __restrict__ sp, const ConstCol xs, double pos[3], double vel[3], double acc[3]) {
+__device__ __forceinline__ void EvalSpline(const Plan& P, const SplineSample* __restrict__ sp, const ConstCol xs, double pos[3], double vel[3], double acc[3]) {
   const SampleRegs s = LoadSample(sp);
+  if (s.xi[0] == (int)kPhaseMarker) {   // PhaseSpline: s.T holds the global sample time (warp-uniform branch)
+    const PhaseSplineDef def = P.phase_defs[s.xi[1]];
+    const PhaseLoc L = LocatePhasePoly(P, def, s.T, xs);
+    const PhasePoly* pp = P.phase_polys + def.poly0 + L.poly;
+    const double T = L.T, T2 = T * T, T3 = T2 * T, t = L.tl, t2 = t * t, t3 = t2 * t;   // std::pow(x, 3) ~ x*x*x (<= 1 ulp)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double p0 = xs[pp->xi[d]], v0 = xs[pp->xi[3 + d]], p1 = xs[pp->xi[6 + d]], v1 = xs[pp->xi[9 + d]];
+      const double C = -(3 * (p0 - p1) + T * (2 * v0 + v1)) / T2;
+      const double D = (2 * (p0 - p1) + T * (v0 + v1)) / T3;
+      pos[d] = ((p0 + t * v0) + t2 * C) + t3 * D;
+      if (kWant == 2) vel[d] = (v0 + (2 * t) * C) + (3 * t2) * D;
+      if (kWant >= 1) acc[d] = 2 * C + (6 * t) * D;
+    }
+    return;
+  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double p0 = xs[s.xi[d]], v0 = xs[s.xi[3 + d]], p1 = xs[s.xi[6 + d]], v1 = xs[s.xi[9 + d]];
@@ -188,16 +228,16 @@ template <int kNEE>
 __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSample* __restrict__ sp, const ConstCol xs,
                                             const Col Sk, const Col gk) {
   double c[3], cdd[3], th[3], thd[3], thdd[3], unused[3];
-  EvalSpline<1>(sp + 0, xs, c, unused, cdd);
-  EvalSpline<2>(sp + 1, xs, th, thd, thdd);
+  EvalSpline<1>(P, sp + 0, xs, c, unused, cdd);
+  EvalSpline<2>(P, sp + 1, xs, th, thd, thdd);
 
   // feet
   double fsum[3] = {0, 0, 0}, tau[3] = {0, 0, 0};
 #pragma unroll
   for (int e = 0; e < kNEE; ++e) {
     double pe[3], f[3];
-    EvalSpline<0>(sp + 2 + e, xs, pe, unused, unused);
-    EvalSpline<0>(sp + 2 + kNEE + e, xs, f, unused, unused);
+    EvalSpline<0>(P, sp + 2 + e, xs, pe, unused, unused);
+    EvalSpline<0>(P, sp + 2 + kNEE + e, xs, f, unused, unused);
     const double r[3] = {c[0] - pe[0], c[1] - pe[1], c[2] - pe[2]};
     tau[0] += f[1] * r[2] - f[2] * r[1];
     tau[1] += f[2] * r[0] - f[0] * r[2];
@@ -444,8 +484,8 @@ __device__ __forceinline__ void AccUnitEval(const AccUnit& u, const ConstCol xs,
 // BaseMotionConstraint::UpdateConstraintAtInstance, base_motion_constraint.cc:56-66: rows AX.. = base-ang, LX.. = base-lin position
 __device__ __forceinline__ void BaseMotionUnitEval(const Plan& P, const BaseMotionUnit& u, const ConstCol xs, const Col gk) {
   double lin[3], ang[3], unused[3];
-  EvalSpline<0>(P.samples + u.sample_lin, xs, lin, unused, unused);
-  EvalSpline<0>(P.samples + u.sample_ang, xs, ang, unused, unused);
+  EvalSpline<0>(P, P.samples + u.sample_lin, xs, lin, unused, unused);
+  EvalSpline<0>(P, P.samples + u.sample_ang, xs, ang, unused, unused);
 #pragma unroll
   for (int d = 0; d < 3; ++d) { gk[d] = ang[d]; gk[3 + d] = lin[d]; }
 }
@@ -673,8 +713,8 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
   t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE
   double c[3], th[3], unused[3];
-  EvalSpline<0>(sp + 0, xs, c, unused, unused);
-  EvalSpline<0>(sp + 1, xs, th, unused, unused);
+  EvalSpline<0>(P, sp + 0, xs, c, unused, unused);
+  EvalSpline<0>(P, sp + 1, xs, th, unused, unused);
   const Trig tr = MakeTrig(th);
   double R[3][3]; RotationMatrix(tr, R);
   double dR[3][3][3]; RotationDerivative(tr, dR);
@@ -687,7 +727,7 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
   for (int e = 0; e < kNEE; ++e) {
 #ifndef TWB_EXP_NOCOMPUTE
     double pe[3];
-    EvalSpline<0>(sp + 2 + e, xs, pe, unused, unused);
+    EvalSpline<0>(P, sp + 2 + e, xs, pe, unused, unused);
     const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
     double D[3][3]; RotVecDerivative<true>(dR, r, D);
     if (e > 0) __syncwarp();   // the previous foot's values have left the state rows
@@ -771,6 +811,153 @@ __global__ void __launch_bounds__(128) CostKernel(const Plan P, const double* __
   }
   total_cost += term;
   if (cost) cost[b] = total_cost;
+}
+
+// ---- PhaseJac: Jacobian entries that exist only with optimised phase durations -----------------------------
+// Everything a PhaseSpline contributes at one sample: value, velocity, the four Hermite basis values of the active
+// polynomial (polynomial.cc:106-234), d(pos)/d(phase duration) (polynomial.cc:236-257, phase_spline.cc:77-93) and
+// the phase the sample falls into (phase_durations.cc:122-154).
+struct PhaseFull {
+  const PhasePoly* pp;
+  double B[2][2];          // [side][node derivative]: d(pos)/d(node value)
+  double pos[3], vel[3], dxdT[3];
+  int cur, n_phases;       // current phase, number of phases
+};
+__device__ __forceinline__ PhaseFull EvalPhaseFull(const Plan& P, int def_index, double tg, const ConstCol xs) {
+  const PhaseSplineDef def = P.phase_defs[def_index];
+  const PhaseLoc L = LocatePhasePoly(P, def, tg, xs);
+  PhaseFull o; o.pp = P.phase_polys + def.poly0 + L.poly; o.n_phases = def.n_phases;
+  const double T = L.T, T2 = T * T, T3 = T2 * T, T4 = T2 * T2, t = L.tl, t2 = t * t, t3 = t2 * t;
+  o.B[0][0] = (2 * t3) / T3 - (3 * t2) / T2 + 1; o.B[0][1] = t - (2 * t2) / T + t3 / T2;
+  o.B[1][0] = (3 * t2) / T2 - (2 * t3) / T3;     o.B[1][1] = t3 / T2 - t2 / T;
+  const double inner = 1. / (double)o.pp->n_in_phase, prev = (double)o.pp->k_in_phase;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double x0 = xs[o.pp->xi[d]], v0 = xs[o.pp->xi[3 + d]], x1 = xs[o.pp->xi[6 + d]], v1 = xs[o.pp->xi[9 + d]];
+    const double C = -(3 * (x0 - x1) + T * (2 * v0 + v1)) / T2;
+    const double D = (2 * (x0 - x1) + T * (v0 + v1)) / T3;
+    o.pos[d] = ((x0 + t * v0) + t2 * C) + t3 * D;
+    o.vel[d] = (v0 + (2 * t) * C) + (3 * t2) * D;
+    const double dT = (t3 * (v0 + v1)) / T3 - (t2 * (2 * v0 + v1)) / T2 - (3 * t3 * (2 * x0 - 2 * x1 + T * v0 + T * v1)) / T4 +
+                      (2 * t2 * (3 * x0 - 3 * x1 + 2 * T * v0 + T * v1)) / T3;
+    o.dxdT[d] = inner * (dT - prev * o.vel[d]);
+  }
+  // Spline::GetSegmentID over the PHASE durations
+  const double eps = 1e-10;
+  double acc = 0.0; o.cur = def.n_phases - 1; bool found = false;
+  for (int ph = 0; ph < def.n_phases; ++ph) {
+    acc += (ph == def.n_phases - 1) ? L.last : xs[def.sched0 + ph];
+    if (!found && acc >= tg - eps) { found = true; o.cur = ph; }
+  }
+  return o;
+}
+// column `ph` of PhaseDurations::GetJacobianOfPos (phase_durations.cc:122-154)
+__device__ __forceinline__ void DurationColumn(const PhaseFull& f, int ph, double col[3]) {
+  const bool in_last = f.cur == f.n_phases - 1;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double v = 0.0;
+    if (!in_last && ph == f.cur) v = f.dxdT[d];
+    else if (ph < f.cur) { v = -1 * f.vel[d]; if (in_last) v = v - f.dxdT[d]; }
+    col[d] = v;
+  }
+}
+// C = Cross(v) of single_rigid_body_dynamics.cc:46-57
+__device__ __forceinline__ void CrossMatrix(const double v[3], double C[3][3]) {
+  C[0][0] = 0.0;   C[0][1] = -v[2]; C[0][2] = v[1];
+  C[1][0] = v[2];  C[1][1] = 0.0;   C[1][2] = -v[0];
+  C[2][0] = -v[1]; C[2][1] = v[0];  C[2][2] = 0.0;
+}
+// The node variables of the active polynomial: up to 12 (column, dim, weight) entries; a stance position shared
+// by both boundary nodes gets the sum of both basis values (NodeSpline::FillJacobianWrtNodes, node_spline.cc:85-112).
+template <class F>
+__device__ __forceinline__ void ForEachActiveNodeVar(const PhaseFull& f, int zero_slot, F&& fn) {
+#pragma unroll
+  for (int deriv = 0; deriv < 2; ++deriv)
+#pragma unroll
+    for (int dim = 0; dim < 3; ++dim) {
+      const int c0 = f.pp->xi[deriv * 3 + dim], c1 = f.pp->xi[6 + deriv * 3 + dim];
+      if (c0 == c1) { if (c0 != zero_slot) fn(c0, dim, f.B[0][deriv] + f.B[1][deriv]); }
+      else { if (c0 != zero_slot) fn(c0, dim, f.B[0][deriv]); if (c1 != zero_slot) fn(c1, dim, f.B[1][deriv]); }
+    }
+}
+// warp = one phase unit (a dynamic sample, a range-of-motion sample, or the total-duration rows) x one tile of 32
+// instances; lane = instance writes its own entries with 8-byte stores (a few dozen per sample; the bulk of these
+// rows — structural zeros — was written, coalesced, by the output kernels).
+template <int kNEE>
+__global__ void __launch_bounds__(128) PhaseJac(const Plan P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
+                                                int* __restrict__ status, int nb, unsigned flags) {
+  const int lane = threadIdx.x & 31, ui = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ui >= P.n_phase_units) return;
+  const int b = blockIdx.y * 32 + lane;
+  const bool live = b < nb, want_jac = (flags & 2u) != 0;
+  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const PhaseUnit* u = P.phase_units + ui;
+  const int kind = __ldg(&u->kind);
+  double* J = jac + (size_t)b * P.nnz;
+  auto put = [&](int row, int col, double v) {
+    const int slot = __ldg(P.slot_of + (size_t)row * P.n + col);
+    if (live && slot >= 0) StoreOut(J + slot, v);
+  };
+  double unused[3];
+  if (kind == kPhaseTotal) {   // TotalDurationConstraint, total_duration_constraint.cc:48-72
+    for (int e = 0; e < kNEE; ++e) {
+      const PhaseSplineDef def = P.phase_defs[2 * e];
+      const int row = __ldg(&u->rows[e]);
+      double sum = 0.0;
+      for (int i = 0; i + 1 < def.n_phases; ++i) { sum += xs[def.sched0 + i]; if (want_jac) put(row, def.sched0 + i, 1.0); }
+      if (flags & 1u) GT[((size_t)blockIdx.y * P.m + row) * 32 + lane] = sum;
+      if (live && status && !(def.t_total - sum > 0.0)) atomicOr(status + b, 2);
+    }
+    return;
+  }
+  if (!want_jac) return;
+  const double tg = u->t;
+  double c[3];
+  EvalSpline<0>(P, P.samples + __ldg(&u->sample_lin), xs, c, unused, unused);
+  if (kind == kPhaseDyn) {   // dynamic_constraint.cc:91-113 with single_rigid_body_dynamics.cc:167-192
+    const int row0 = __ldg(&u->row0);
+    for (int e = 0; e < kNEE; ++e) {
+      const PhaseFull mo = EvalPhaseFull(P, 2 * e, tg, xs), fo = EvalPhaseFull(P, 2 * e + 1, tg, xs);
+      const double r[3] = {c[0] - mo.pos[0], c[1] - mo.pos[1], c[2] - mo.pos[2]};
+      double Cf[3][3], Cr[3][3];
+      CrossMatrix(fo.pos, Cf); CrossMatrix(r, Cr);
+      ForEachActiveNodeVar(mo, P.n, [&](int col, int dim, double w) {
+        for (int i = 0; i < 3; ++i) if (i != dim) put(row0 + i, col, Cf[i][dim] * w);
+      });
+      ForEachActiveNodeVar(fo, P.n, [&](int col, int dim, double w) {
+        for (int i = 0; i < 3; ++i) if (i != dim) put(row0 + i, col, Cr[i][dim] * w);
+        put(row0 + 3 + dim, col, -w);
+      });
+      const int sched0 = P.phase_defs[2 * e].sched0;
+      for (int ph = 0; ph + 1 < mo.n_phases; ++ph) {
+        double jf[3], jm[3];
+        DurationColumn(fo, ph, jf); DurationColumn(mo, ph, jm);
+        for (int i = 0; i < 3; ++i) {
+          const int d1 = (i == 0) ? 1 : 0, d2 = (i == 2) ? 1 : 2;
+          put(row0 + i, sched0 + ph, (Cr[i][d1] * jf[d1] + Cr[i][d2] * jf[d2]) + (Cf[i][d1] * jm[d1] + Cf[i][d2] * jm[d2]));
+          put(row0 + 3 + i, sched0 + ph, -jf[i]);
+        }
+      }
+    }
+  } else {   // range_of_motion_constraint.cc:83-109
+    double th[3];
+    EvalSpline<0>(P, P.samples + __ldg(&u->sample_ang), xs, th, unused, unused);
+    const Trig tr = MakeTrig(th);
+    double R[3][3]; RotationMatrix(tr, R);
+    for (int e = 0; e < kNEE; ++e) {
+      const int row0 = __ldg(&u->rows[e]);
+      const PhaseFull mo = EvalPhaseFull(P, 2 * e, tg, xs);
+      ForEachActiveNodeVar(mo, P.n, [&](int col, int dim, double w) {
+        for (int i = 0; i < 3; ++i) put(row0 + i, col, R[dim][i] * w);
+      });
+      const int sched0 = P.phase_defs[2 * e].sched0;
+      for (int ph = 0; ph + 1 < mo.n_phases; ++ph) {
+        double jm[3]; DurationColumn(mo, ph, jm);
+        for (int i = 0; i < 3; ++i) put(row0 + i, sched0 + ph, (R[0][i] * jm[0] + R[1][i] * jm[1]) + R[2][i] * jm[2]);
+      }
+    }
+  }
 }
 
 #if TWB_FUSED
@@ -884,6 +1071,15 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
   if (fork) {
     cudaEventRecord(ev[1], aux0); cudaEventRecord(ev[2], aux1);
     cudaStreamWaitEvent(s, ev[1], 0); cudaStreamWaitEvent(s, ev[2], 0);
+  }
+  if (out_flags && P.n_phase_units > 0) {   // after every output kernel: overwrites zeros they wrote
+    const dim3 grid((P.n_phase_units + 3) / 4, tiles);
+    switch (P.n_ee) {
+      case 1: PhaseJac<1><<<grid, 128, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      case 2: PhaseJac<2><<<grid, 128, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      default: PhaseJac<4><<<grid, 128, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
+    }
+    ++count; TWB_MARK("PhaseJac", s);
   }
   if (out_flags & 1u) { TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
