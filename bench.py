@@ -24,8 +24,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORKLOAD = "anymal_trot_block"
+WORKLOAD = "anymal_trot_block"   # --workload overrides (other BASELINE configs; not the driver's line)
 BATCH_PER_GPU = 4096
+DESCR = {
+    "anymal_trot_block": "BASELINE configs[1]: Anymal fly-trot C1, Block terrain, T=2.0 s",
+    "biped_walk_stairs": "BASELINE configs[2]: Biped walk C0, Stairs, fpowr recipe, T=2.0 s",
+    "hyq_gallop_gap": "BASELINE configs[3]: HyQ gallop C4, Gap terrain, phase durations optimised, T=2.0 s",
+    "anymal_trot_mixed": "BASELINE configs[4], one GPU's shard: Anymal fly-trot C1, terrains drawn from Slope/Chimney/Gap per instance",
+    "hopper": "BASELINE configs[0]: Monoped hopper, FlatGround, T=2.0 s",
+}
 METRIC = "nlp_evals_per_sec"
 UNIT = "evals/s"
 
@@ -78,6 +85,42 @@ def make_problem():
     return tb, spec, tb.Problem(spec)
 
 
+def kernel_breakdown(p, B):
+    """Per-kernel durations from a second, serialised pass (TWB_PROFILE=1: every kernel on one stream, CUDA events
+    around each launch) in a child process, with each kernel's own algorithmic bytes.  The timed region of the main
+    pass runs the three output kernels concurrently on three streams, so their durations are not separable there."""
+    env = dict(os.environ, TWB_PROFILE="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--quick", "--steps", "30", "--warmup", "5",
+                              "--workload", WORKLOAD, "--batch", str(B)],
+                             capture_output=True, text=True, timeout=300, env=env).stderr
+    except Exception:
+        return None
+    rows = {}
+    for nm, r0, nr in p.constraint_sets():
+        rows[nm] = (r0, nr)
+    rp = p.row_ptr()
+    def share(pred):
+        nz = sum(int(rp[r0 + nr] - rp[r0]) for nm, (r0, nr) in rows.items() if pred(nm))
+        mm = sum(nr for nm, (r0, nr) in rows.items() if pred(nm))
+        return 8 * B * (nz + mm)
+    alg = {"DynOut": share(lambda n: n == "dynamic"), "RomOut": share(lambda n: n.startswith("rangeofmotion")),
+           "NodeOut": share(lambda n: n != "dynamic" and not n.startswith(("rangeofmotion", "totalduration"))),
+           "TransposeIn": 2 * 8 * B * p.n, "TransposeOut": 2 * 8 * B * p.m}
+    res = {}
+    for line in out.splitlines():
+        parts = line.split()
+        if line.startswith("[twb profile]") and "avg" in parts:
+            name, us = parts[2], float(parts[parts.index("avg") + 1])
+            res[name] = {"avg_us": us}
+            if name in alg and us > 0:
+                res[name]["algorithmic_bytes"] = alg[name]
+                res[name]["gbs"] = alg[name] / (us * 1e-6) / 1e9
+    return res or None
+
+
 def cpu_arm(spec, problem, X, threads, target_seconds=12.0):
     """Times the CPU restatement (oracle) on a bounded sample of the same iterates."""
     import oracle_lib
@@ -114,7 +157,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD} (BASELINE configs[1]): Anymal fly-trot C1, Block terrain, T=2.0 s, n={p.n} m={p.m} nnz={p.nnz}",
+        "config": {"workload": f"{WORKLOAD} ({DESCR.get(WORKLOAD, WORKLOAD)}), n={p.n} m={p.m} nnz={p.nnz}",
                    "note": "reference arm = CPU restatement of towr's evaluation (oracle port; towr itself needs Eigen+ifopt, absent here)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} instances per step, OpenMP over instances"},
@@ -140,8 +183,10 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tb, spec, p = make_problem()
-    B = BATCH_PER_GPU
+    B = args.batch or BATCH_PER_GPU
     batch = p.batch(B, device=local)
+    if WORKLOAD == "anymal_trot_mixed":
+        batch.set_terrains(np.random.default_rng(7 + rank).choice([tb.SLOPE, tb.CHIMNEY, tb.GAP], B).astype(np.int32))
 
     # ---- inputs: a ring of distinct iterate sets, together larger than L2 (126 MB)
     n_ring = 8
@@ -165,12 +210,12 @@ def run_cuda(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local) if rank == 0 and not args.quick else None
+    if sampler:
+        sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
     sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     sync_all()
     ev[0].record(stream)
@@ -181,6 +226,15 @@ def run_cuda(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
     if sampler:
+        # the timed region lasts a few milliseconds; keep the same loop running ~1 s more so that nvidia-smi (one
+        # sample per ~60 ms) sees the clocks under this load; these steps are not part of any reported number
+        t_end = time.perf_counter() + 1.0
+        i = 0
+        while time.perf_counter() < t_end:
+            step(i); i += 1
+            if i % 64 == 0:
+                torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
         sampler.stop_flag = True
     assert int(status.sum().item()) == 0, "non-finite values flagged"
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -223,6 +277,14 @@ def run_cuda(args):
         achieved = bytes_per_eval * B / (avg_kernel_ms * 1e-3) / 1e9
         threads = oracle_lib.max_threads()
         cpu_value, cpu_sample, cpu_dt = cpu_arm(spec, p, Xh, threads)
+        kernels = kernel_breakdown(p, B)
+        dominant = None
+        if kernels:
+            cand = [(k, v) for k, v in kernels.items() if "gbs" in v and k.endswith("Out") and k != "TransposeOut"]
+            if cand:
+                k, v = max(cand, key=lambda kv: kv[1]["avg_us"])
+                dominant = {"name": k, "avg_launch_ms": v["avg_us"] * 1e-3, "algorithmic_bytes_per_launch": v["algorithmic_bytes"],
+                            "achieved": v["gbs"], "frac": v["gbs"] / peak, "how": "serialised pass, CUDA events around each launch"}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
         if os.path.exists(tpath):
@@ -234,7 +296,7 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD} (BASELINE configs[1]): Anymal fly-trot C1, Block terrain, T=2.0 s, "
+            "config": {"workload": f"{WORKLOAD} ({DESCR.get(WORKLOAD, WORKLOAD)}), "
                                    f"{B} instances per GPU, n={p.n} m={p.m} nnz={p.nnz}",
                        "batch_per_gpu": B, "outputs": "g[B][m] + jac[B][nnz] (CSR values), fp64",
                        "l2": f"inputs rotate over {n_ring} distinct iterate sets ({n_ring * B * p.n * 8 / 1e6:.0f} MB) and each step "
@@ -243,7 +305,11 @@ def run_cuda(args):
             "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_best": per_step[0],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_eval * B, "kernel": "EvalKernel", "avg_launch_ms": avg_kernel_ms},
+                         "algorithmic_bytes_per_launch": bytes_per_eval * B, "avg_launch_ms": avg_kernel_ms,
+                         "kernel": "whole evaluation: TransposeIn -> DynOut | RomOut | NodeOut (three streams) -> TransposeOut; "
+                                   "CUDA events on the launching stream around every step of the timed region",
+                         "dominant_kernel": dominant},
+            "kernels": kernels,
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"first {cpu_sample} instances of the same batch, OpenMP over instances, {cpu_dt:.1f} s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -264,7 +330,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--quick", action="store_true", help="kernel timing only (tuning sweeps): skip e2e and the CPU arm")
+    ap.add_argument("--workload", default=None, help="recipe name of towr_b200.configs (default: BASELINE configs[1])")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default 4096)")
     args = ap.parse_args()
+    global WORKLOAD
+    if args.workload:
+        WORKLOAD = args.workload
     import __graft_entry__ as ge
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         ge.build(quiet=True)

@@ -6,3 +6,4 @@ from ._capi import (ANYMAL, BIPED, BLOCK, CHIMNEY, CHIMNEY_LR, EVAL_ALL, EVAL_CO
 from .formulation import (BaseState, Batch, GaitGenerator, NlpFormulation, Parameters, Problem, robot_info,
                           terrain_height)
 from .configs import make_formulation, CONFIGS
+from .sharding import shard_range, gather_cost_status

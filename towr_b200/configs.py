@@ -85,6 +85,16 @@ def variable_sigma(problem):
     return sig
 
 
+def _renormalise(problem, set_name, d):
+    """Scale the optimised phase durations of one foot (last axis) so that the remaining last phase keeps at least
+    2 % of the horizon (phase_durations.cc:92 needs sum < T)."""
+    ee = int(set_name[len("ee-schedule"):])
+    spec = problem.spec
+    t_total = sum(spec.phase_durations[ee][i] for i in range(spec.n_phases[ee]))
+    tot = d.sum(axis=-1, keepdims=True)
+    return d * np.minimum(1.0, 0.98 * t_total / tot)
+
+
 def synthetic_iterates(problem, batch, seed=1234, first=0):
     """(batch, n) float64 iterates; instance b uses numpy default_rng(seed + first + b)."""
     x0 = problem.GetVariableValues()
@@ -94,8 +104,8 @@ def synthetic_iterates(problem, batch, seed=1234, first=0):
         rng = np.random.default_rng(seed + first + b)
         X[b] = x0 + sig * rng.standard_normal(problem.n)
         for name, start, count in problem.variable_sets():
-            if name.startswith("ee-schedule"):   # durations: nominal x U[0.9, 1.1] (their sum stays below T)
-                X[b, start:start + count] = x0[start:start + count] * rng.uniform(0.9, 1.1, count)
+            if name.startswith("ee-schedule"):   # durations: nominal x U[0.9, 1.1], re-normalised so that their sum stays below T
+                X[b, start:start + count] = _renormalise(problem, name, x0[start:start + count] * rng.uniform(0.9, 1.1, count))
     for name, start, count in problem.variable_sets():
         if name == "base-ang":           # keep pitch/yaw nodes within +-1 rad (far from gimbal lock)
             blk = X[:, start:start + count].reshape(batch, -1, 6)
@@ -111,7 +121,7 @@ def synthetic_iterates_fast(problem, batch, seed=1234):
     X = x0 + sig * rng.standard_normal((batch, problem.n))
     for name, start, count in problem.variable_sets():
         if name.startswith("ee-schedule"):
-            X[:, start:start + count] = x0[start:start + count] * rng.uniform(0.9, 1.1, (batch, count))
+            X[:, start:start + count] = _renormalise(problem, name, x0[start:start + count] * rng.uniform(0.9, 1.1, (batch, count)))
         if name == "base-ang":
             blk = X[:, start:start + count].reshape(batch, -1, 6)
             blk[:, :, :3] = np.clip(blk[:, :, :3], -1.0, 1.0)

@@ -124,10 +124,12 @@ __device__ __forceinline__ PhaseLoc LocatePhasePoly(const Plan& P, const PhaseSp
   return o;
 }
 // kWant: 0 position; 1 position + acceleration; 2 position + velocity + acceleration
-template <int kWant>
+// kPhase: the sample may refer to a PhaseSpline (only in kernels instantiated for duration-optimised problems, so
+// that the fixed-duration kernels carry neither the branch nor the code)
+template <int kWant, bool kPhase = false>
 __device__ __forceinline__ void EvalSpline(const Plan& P, const SplineSample* __restrict__ sp, const ConstCol xs, double pos[3], double vel[3], double acc[3]) {
   const SampleRegs s = LoadSample(sp);
-  if (s.xi[0] == (int)kPhaseMarker) {   // PhaseSpline: s.T holds the global sample time (warp-uniform branch)
+  if (kPhase && s.xi[0] == (int)kPhaseMarker) {   // PhaseSpline: s.T holds the global sample time (warp-uniform branch)
     const PhaseSplineDef def = P.phase_defs[s.xi[1]];
     const PhaseLoc L = LocatePhasePoly(P, def, s.T, xs);
     const PhasePoly* pp = P.phase_polys + def.poly0 + L.poly;
@@ -224,7 +226,7 @@ __device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3]
 //   sum of forces, per-foot force and lever arm for the other blocks (:103-121, :167-192).
 // Sk: local state rows 1.. (Sk[0..2] sum f, Sk[3..38] base-ang block, Sk[39 + 6e ..] f_e, c - p_e);
 // gk: the 6 constraint values
-template <int kNEE>
+template <int kNEE, bool kPhase>
 __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSample* __restrict__ sp, const ConstCol xs,
                                             const Col Sk, const Col gk) {
   double c[3], cdd[3], th[3], thd[3], thdd[3], unused[3];
@@ -236,8 +238,8 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSa
 #pragma unroll
   for (int e = 0; e < kNEE; ++e) {
     double pe[3], f[3];
-    EvalSpline<0>(P, sp + 2 + e, xs, pe, unused, unused);
-    EvalSpline<0>(P, sp + 2 + kNEE + e, xs, f, unused, unused);
+    EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
+    EvalSpline<0, kPhase>(P, sp + 2 + kNEE + e, xs, f, unused, unused);
     const double r[3] = {c[0] - pe[0], c[1] - pe[1], c[2] - pe[2]};
     tau[0] += f[1] * r[2] - f[2] * r[1];
     tau[1] += f[2] * r[0] - f[0] * r[2];
@@ -669,7 +671,7 @@ __device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int l
 // DynamicConstraint: blockIdx.y = instance tile, warp = one of kDynWarps CONSECUTIVE samples, so a CTA writes
 // several KB of contiguous CSR values per instance (the samples' rows are adjacent) and the sectors shared by
 // two samples are completed through the carry rows.
-template <int kNEE>
+template <int kNEE, bool kPhase>
 __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -681,7 +683,7 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
   if (valid) {
     t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE   // (timing experiment: store phase only)
-    DynamicUnit<kNEE>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
+    DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
     FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
 #endif
     __syncwarp();
@@ -696,7 +698,7 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
 // warp = one of kRomWarps consecutive samples.  The rotation and its derivative are computed once per sample;
 // the feet then take turns: foot e's D_e and g_e overwrite the previous foot's state rows once its values have
 // been written, so a warp needs 22 state rows (+ 6 carry-in rows per foot) instead of 10 + 12 n_ee.
-template <int kNEE>
+template <int kNEE, bool kPhase>
 __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -727,7 +729,7 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
   for (int e = 0; e < kNEE; ++e) {
 #ifndef TWB_EXP_NOCOMPUTE
     double pe[3];
-    EvalSpline<0>(P, sp + 2 + e, xs, pe, unused, unused);
+    EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
     const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
     double D[3][3]; RotVecDerivative<true>(dR, r, D);
     if (e > 0) __syncwarp();   // the previous foot's values have left the state rows
@@ -963,31 +965,31 @@ __global__ void __launch_bounds__(128) PhaseJac(const Plan P, const double* __re
 #if TWB_FUSED
 // One kernel writes a whole tile of rows: blockIdx.y = instance tile, blockIdx.x walks the tile's CTAs in row
 // order — dynamic samples, range-of-motion samples, node groups.
-template <int kNEE>
+template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kWarps * 32, TWB_CTAS) EvalOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                               double* __restrict__ jac, int* __restrict__ status,
                                                               const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
   const int n_dyn_ctas = (P.n_dyn + kWarps - 1) / kWarps, n_rom_ctas = (P.n_rom + kWarps - 1) / kWarps;
   int cta = blockIdx.x;
-  if (cta < n_dyn_ctas) { DynBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
+  if (cta < n_dyn_ctas) { DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
   cta -= n_dyn_ctas;
-  if (cta < n_rom_ctas) { RomBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
+  if (cta < n_rom_ctas) { RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
   cta -= n_rom_ctas;
   NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, cta, blockIdx.y);
 }
 #else
-template <int kNEE>
+template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                            double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
-  DynBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+  DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
 }
-template <int kNEE>
+template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                            double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
-  RomBody<kNEE>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+  RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
 }
 __global__ void __launch_bounds__(kNodeWarps * 32, TWB_NODE_CTAS) NodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                            double* __restrict__ jac, int* __restrict__ status,
@@ -998,7 +1000,7 @@ __global__ void __launch_bounds__(kNodeWarps * 32, TWB_NODE_CTAS) NodeOut(const 
 #endif
 
 // s: caller's stream (after TransposeIn); a0, a1: auxiliary streams already waiting on the transposition
-template <int kNEE>
+template <int kNEE, bool kPhase>
 cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, int* status, const int* terrain_ids, int default_terrain,
                       int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
   const size_t row_bytes = (size_t)kLD * sizeof(double);
@@ -1009,20 +1011,20 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
   if (n_ctas == 0) return cudaSuccess;
   const int rows = std::max(std::max(P.n_dyn > 0 ? dyn_rows : 0, P.n_rom > 0 ? rom_rows : 0), P.n_groups > 0 ? node_rows : 0);
   const size_t smem = (size_t)kWarps * rows * row_bytes;
-  if ((e = cudaFuncSetAttribute(EvalOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-  EvalOut<kNEE><<<dim3(n_ctas, tiles), kWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
+  if ((e = cudaFuncSetAttribute(EvalOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  EvalOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
   ++*count; TWB_MARK("EvalOut", s);
 #else
   if (P.n_rom > 0) {
     const size_t smem = (size_t)kRomWarps * rom_rows * row_bytes;
-    if ((e = cudaFuncSetAttribute(RomOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    RomOut<kNEE><<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, nb, flags);
+    if ((e = cudaFuncSetAttribute(RomOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    RomOut<kNEE, kPhase><<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, nb, flags);
     ++*count; TWB_MARK("RomOut", s);
   }
   if (P.n_dyn > 0) {
     const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
-    if ((e = cudaFuncSetAttribute(DynOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    DynOut<kNEE><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
+    if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
     ++*count; TWB_MARK("DynOut", a0);
   }
   if (P.n_groups > 0) {
@@ -1059,10 +1061,14 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
   if (fork) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
   if (out_flags) {
+    const bool phase = P.n_phase_defs > 0;
     switch (P.n_ee) {
-      case 1: e = LaunchOut<1>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
-      case 2: e = LaunchOut<2>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
-      case 4: e = LaunchOut<4>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 1: e = phase ? LaunchOut<1, true>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<1, false>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 2: e = phase ? LaunchOut<2, true>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<2, false>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 4: e = phase ? LaunchOut<4, true>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<4, false>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
       default: return (int)cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return (int)e;
