@@ -121,6 +121,15 @@ def kernel_breakdown(p, B):
     return res or None
 
 
+def host_threads():
+    """Host threads the CPU legs use: every core this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    which must not throttle the CPU arm — the thread count is passed to the oracle explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_arm(spec, problem, X, threads, target_seconds=12.0):
     """Times the CPU restatement (oracle) on a bounded sample of the same iterates."""
     import oracle_lib
@@ -140,7 +149,7 @@ def run_reference(args):
     import oracle_lib
     from towr_b200.configs import synthetic_iterates_fast
     tb, spec, p = make_problem()
-    threads = oracle_lib.max_threads()
+    threads = host_threads()
     X = synthetic_iterates_fast(p, 2048)
     # each step: a bounded sample of the workload sized for ~1.5 s of CPU time
     t0 = time.perf_counter(); oracle_lib.batch_eval(spec, X[:max(threads, 8)], threads=threads)
@@ -273,9 +282,9 @@ def run_cuda(args):
         import oracle_lib
         peak, peak_src = read_peak()
         bytes_per_eval = 8 * (p.n + p.m + p.nnz)
-        avg_kernel_ms = total_ms / args.steps       # one kernel launch per step on this stream
+        avg_kernel_ms = total_ms / args.steps       # one evaluation (all its kernels) per step
         achieved = bytes_per_eval * B / (avg_kernel_ms * 1e-3) / 1e9
-        threads = oracle_lib.max_threads()
+        threads = host_threads()
         cpu_value, cpu_sample, cpu_dt = cpu_arm(spec, p, Xh, threads)
         kernels = kernel_breakdown(p, B)
         dominant = None
@@ -285,13 +294,16 @@ def run_cuda(args):
                 k, v = max(cand, key=lambda kv: kv[1]["avg_us"])
                 dominant = {"name": k, "avg_launch_ms": v["avg_us"] * 1e-3, "algorithmic_bytes_per_launch": v["algorithmic_bytes"],
                             "achieved": v["gbs"], "frac": v["gbs"] / peak, "how": "serialised pass, CUDA events around each launch"}
-        traffic = None
+        traffic, traffic_kernels = None, {}
         tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and WORKLOAD == "anymal_trot_block" and B == BATCH_PER_GPU:
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic, traffic_kernels = tj.get("dram_bytes_per_launch"), tj.get("kernels", {})
             except Exception:
                 traffic = None
+        if dominant and dominant["name"] in traffic_kernels:
+            dominant["traffic"] = traffic_kernels[dominant["name"]]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
