@@ -59,24 +59,22 @@ struct PhaseUnit {
 // per instance and a warp covers 512 contiguous bytes.
 //
 // HBM only sustains its write bandwidth for whole 32-byte sectors (a partially written sector that has left
-// the L2 costs a read-modify-write), so the lists are built sector by sector: a sector is written, whole, by
-// the unit that owns its LAST element; elements of that sector owned by the preceding unit of the same CTA
-// reach the writer through CARRY rows — the preceding warp publishes `state * coef` into rows appended to
-// the writer's state block before the CTA-wide barrier.  Only sectors that straddle a CTA or a constraint-set
-// boundary fall back to 8-byte single-element stores.
-//
-// The alignment of an instance's row inside its sectors depends on (instance * row length) mod 4, so a list
-// exists per alignment class q = instance mod n_classes (n_classes = 1 when the row length is a multiple of 4).
+// the L2 costs a read-modify-write), so the Jacobian values are written by whole CTAs: after the CTA barrier all
+// threads walk ONE list of pairs that covers the output of the CTA's consecutive units (`d` = row in the CTA's
+// shared memory = warp * block rows + local row).  The lists are built sector by sector: a sector is written, whole,
+// by the CTA that owns its last element; only sectors shared with another CTA fall back to 8-byte single-element
+// stores.  The alignment of an instance's row inside its sectors depends on (instance * row length) mod 4, so a
+// list exists per alignment class q = instance mod n_classes (n_classes = 1 when the row length is a multiple of 4).
+// The constraint values of a unit go, lane = instance, into the instance-tiled staging matrix GT.
 constexpr int kMaxClasses = 4;
-constexpr int kCarryRows = 6;           // carry-in rows of a state block: 3 for Jacobian values, 3 for constraint values
-struct OutPair { int32_t off; uint16_t d0, d1; };       // pair: element index of the first half; single / publish entry: element index / carry row, d0 = state row
+struct OutPair { int32_t off; uint16_t d0, d1; };       // pair: element index of the first half; single / value entry: element index / g row, d0 = state row
 struct alignas(16) OutCoef { double c0, c1; };
 struct OutRange { int32_t first, count; };
-struct OutList {                        // [0: Jacobian values, 1: constraint values][alignment class]
+struct OutList {                        // [0][alignment class]
   OutRange pairs[2][kMaxClasses];       // whole sectors, two pairs each
   OutRange singles[2][kMaxClasses];     // single elements (lane = instance)
-  OutRange publish[2][kMaxClasses];     // carry values for the next warp of the CTA (lane = instance)
 };
+constexpr int kRomBlockRows = 34;       // [0]=1 | R^T (9) | 2 x { D_e (9) | g_e (3) }
 
 // warps per CTA of the output kernels = consecutive units whose output ranges are chained through carry rows.
 // TWB_FUSED = 1: one kernel (EvalOut) serves all three unit kinds with CTAs of TWB_WARPS warps.
@@ -123,16 +121,15 @@ struct BaseMotionUnit { int32_t sample_lin, sample_ang; };
 
 // A dynamic sample (6 rows): 2 + 2 n_ee spline samples starting at `sample0`
 // (base-lin, base-ang, ee-motion.., ee-force..) and its output lists.
-struct DynUnit { int32_t sample0; int32_t pad; OutList out; };
+struct DynUnit { int32_t sample0; int32_t pad; OutRange values; };
 // A range-of-motion sample (3 rows for every foot): 2 + n_ee spline samples (base-lin, base-ang, ee-motion..);
-// the feet are evaluated and written one after the other through the same state rows (out[foot]).
-struct RomUnit { int32_t sample0; int32_t pad; OutList out[kMaxEE]; };
-constexpr int kRomStateRows = 22;    // [0]=1 | R^T (9) | D_e (9) | g_e (3); followed by kCarryRows carry-in rows per foot
+// the feet are evaluated and written one after the other (values[foot]: the foot's constraint values).
+struct RomUnit { int32_t sample0; int32_t pad; OutRange values[kMaxEE]; };
 
 // Node-wise work of one warp: `count` consecutive units of one kind evaluated into one state block,
 // then one pass over the group's output lists.
 enum NodeKind : int32_t { kGroupForce = 0, kGroupTerrain = 1, kGroupSwing = 2, kGroupAcc = 3, kGroupConst = 4, kGroupBaseMotion = 5 };
-struct NodeGroup { int32_t kind, first, count, pad; OutList out; };
+struct NodeGroup { int32_t kind, first, count, pad; OutRange values; };
 constexpr int kNodeStateRowsMax = 64;   // upper bound of the local state rows of a node group (row 0 = 1); Plan::node_rows is the actual maximum
 
 // NodeCost term (node_cost.cc:53-76) flattened: one entry per node value that
@@ -148,8 +145,9 @@ struct Plan {
   int n, m, nnz, n_ee;
   int n_sms;       // multiprocessors of the batch's device (persistent grids); set by twb_batch_create
   int n_dyn, n_rom, n_groups, n_cost;
-  int node_rows;   // state rows of the largest node group (without carry rows)
-  int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz) and constraint rows (length m)
+  int node_rows, dyn_rows, rom_rows;   // state rows of one unit's block: node groups (largest), dynamic samples, range-of-motion samples
+  int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz); nc_g = 1 (constraint values go through GT)
+  int dyn_list0, rom_list0, node_list0;   // first entry of cta_lists of the dynamic CTAs, (rom CTA, foot) pairs, node CTAs
   // robot
   double mass, gravity;
   double I_b[9];
@@ -168,6 +166,7 @@ struct Plan {
   const double* dyn_ang_basis;  // [n_dyn][12]: base-ang basis of the active polynomial, {pos, vel, acc} x {p0, v0, p1, v1}
   const OutPair* pairs;
   const OutCoef* coefs;
+  const OutList* cta_lists;
   // phase-duration optimisation (all null / 0 otherwise)
   int n_phase_units, n_phase_defs;
   const PhaseSplineDef* phase_defs;   // [2 * n_ee]: ee-motion_e at 2e, ee-force_e at 2e + 1

@@ -445,7 +445,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         have_rom = true;
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_range_of_motion);
         pl.n_rom = (int)ts.size();
-        const uint32_t G0 = 19;   // local state (re-used by the feet in turn): [0]=1 | R^T (9) | D_e (9) | g_e (3)
+        // local state: [0]=1 | R^T (9) | two buffers of D_e (9) + g_e (3) used by the feet in turn (foot e: buffer e & 1)
         for (int k = 0; k < pl.n_rom; ++k) {  // spline samples: base-lin, base-ang, ee-motion..
           RomUnit ru{}; ru.sample0 = (int32_t)tb.samples.size();
           tb.rom.push_back(ru);
@@ -462,7 +462,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
           for (int k = 0; k < pl.n_rom; ++k) {
             const double t = ts[k]; const int row = r0 + 3 * k;
-            const uint32_t sb = 1, sd = 10;
+            const uint32_t sb = 1, sd = 10 + 12 * (e & 1), G0 = 19 + 12 * (e & 1);
             for (int d = 0; d < 3; ++d) {
               bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
               own(row + d, kOwnRom, k * n_ee + e, G0 + d);
@@ -661,9 +661,12 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     }
   }
 
-  // ---- output lists (device_tables.h): every 32-byte sector of an instance's g / Jacobian-value row is written
-  // whole by the unit that owns its last element; elements owned by the preceding unit of the same CTA arrive
-  // through carry rows; sectors that straddle a CTA / set / row boundary fall back to single-element stores.
+  // ---- output lists (device_tables.h).  The Jacobian values are written by CTAs: a CTA holds the state blocks of
+  // kDynWarps / kRomWarps / kNodeWarps consecutive units (one per warp) and, after its barrier, ALL its threads walk one
+  // combined list of 16-byte pairs (`d` = row in the CTA's shared memory = warp * block_rows + local row).  Every
+  // 32-byte sector is written whole by the list that owns its last element; only sectors shared with another CTA (or a
+  // row of the PhaseJac kernel, or the ends of the row) fall back to single-element stores.  The constraint values
+  // are per unit (lane = instance, into GT).
   const int n_rom_blocks = pl.n_rom * n_ee, n_blocks = pl.n_dyn + n_rom_blocks + (int)groups.size();
   auto block_id = [&](const RowOwner& o) {   // global block number: dynamic samples | (rom sample, foot) | node groups; -1: not an output-kernel row
     if (o.kind == kOwnPhase) return -1;
@@ -671,101 +674,86 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     if (o.kind == kOwnRom) return pl.n_dyn + o.index;
     return pl.n_dyn + n_rom_blocks + unit_group[o.index];
   };
-  std::vector<int> pred(n_blocks, -1), carry0(n_blocks, 0);   // chained predecessor inside the CTA; first carry-in row of the block
-  for (int k = 0; k < pl.n_dyn; ++k) { if (k % kDynWarps) pred[k] = k - 1; carry0[k] = 46 + 6 * n_ee; }
+  const int n_dyn_ctas = (pl.n_dyn + kDynWarps - 1) / kDynWarps, n_rom_ctas = (pl.n_rom + kRomWarps - 1) / kRomWarps;
+  const int n_node_ctas = ((int)groups.size() + kNodeWarps - 1) / kNodeWarps;
+  const int n_lists = n_dyn_ctas + n_rom_ctas * n_ee + n_node_ctas;   // dynamic CTAs | (rom CTA, foot) | node CTAs
+  pl.dyn_rows = 46 + 6 * n_ee; pl.rom_rows = kRomBlockRows;
+  std::vector<int> list_of(n_blocks, -1), row_base(n_blocks, 0);   // list a block's elements belong to; first row of the block inside its CTA
+  for (int k = 0; k < pl.n_dyn; ++k) { list_of[k] = k / kDynWarps; row_base[k] = (k % kDynWarps) * pl.dyn_rows; }
   for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) {
     const int b = pl.n_dyn + k * n_ee + e;
-    if (k % kRomWarps) pred[b] = b - n_ee;
-    carry0[b] = kRomStateRows + kCarryRows * e;
+    list_of[b] = n_dyn_ctas + (k / kRomWarps) * n_ee + e; row_base[b] = (k % kRomWarps) * pl.rom_rows;
   }
-  for (int gi = 0; gi < (int)groups.size(); ++gi) { const int b = pl.n_dyn + n_rom_blocks + gi; if (gi % kNodeWarps) pred[b] = b - 1; carry0[b] = pl.node_rows; }
-  struct Elem { int block; uint16_t d; double c; };
-  std::vector<Elem> elems[2];   // [0]: Jacobian values (nnz), [1]: constraint values (m)
-  elems[0].resize(nnz); elems[1].resize(m);
+  for (int gi = 0; gi < (int)groups.size(); ++gi) {
+    const int b = pl.n_dyn + n_rom_blocks + gi;
+    list_of[b] = n_dyn_ctas + n_rom_ctas * n_ee + gi / kNodeWarps; row_base[b] = (gi % kNodeWarps) * pl.node_rows;
+  }
+  struct Elem { int list; uint16_t d; double c; };
+  std::vector<Elem> elems(nnz);
+  struct Entry { OutPair p; OutCoef c; };
+  std::vector<std::vector<Entry>> values(n_blocks);   // constraint values of a block: (g row, local state row, 1)
   for (int r = 0; r < m; ++r) {
     const RowOwner& o = owner[r];
     if (o.kind < 0) return fail(TWB_ERR_UNSUPPORTED, "constraint row without an owner");
     uint32_t g_row = o.g_local, state0 = 1;
     if (o.kind == kOwnNode) { g_row = unit_g0[o.index] + o.g_local; state0 = unit_state0[o.index]; }
     const int blk = block_id(o);
-    elems[1][r] = Elem{blk, (uint16_t)g_row, 1.0};
+    if (blk >= 0) values[blk].push_back({OutPair{r, (uint16_t)g_row, 0}, OutCoef{1.0, 0.0}});
     for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) {
       uint32_t a = em[s].a;
       if (o.kind == kOwnNode && a != S_ONE) a = state0 + (a - 1);
-      elems[0][s] = Elem{blk, (uint16_t)a, em[s].c0};
+      elems[s] = blk >= 0 ? Elem{list_of[blk], (uint16_t)(row_base[blk] + a), em[s].c0} : Elem{-1, 0, 0.0};
     }
   }
-  struct Entry { OutPair p; OutCoef c; };
-  // lists[block][array][class][0: pairs, 1: singles, 2: publish]
-  std::vector<std::array<std::array<std::array<std::vector<Entry>, 3>, kMaxClasses>, 2>> lists(n_blocks);
-  const int len[2] = {nnz, m};
-  const bool g_as_singles = true;   // constraint values go through the instance-tiled staging matrix GT (kernels.cu, StoreValuesTiled)
-  int n_classes[2];
-  for (int A = 0; A < 2; ++A) {
-    const int L = len[A];
-    const int NC = (A == 1 && g_as_singles) ? 1 : (L % 4 == 0) ? 1 : (L % 2 == 0) ? 2 : 4;
-    n_classes[A] = NC;
-    for (int q = 0; q < NC; ++q) {
-      const int c = (int)(((long long)q * L) % 4);   // position of the row's first element inside its sector
-      for (int S = 0; 4 * S < c + L; ++S) {
-        int first = std::max(0, 4 * S - c), last = std::min(L - 1, 4 * S + 3 - c);
-        const bool whole_in_row = (4 * S - c >= 0) && (4 * S + 3 - c <= L - 1);
-        const int writer = elems[A][last].block;
-        if (writer < 0) {   // sector ends in a row of the PhaseJac kernel: the output kernels' elements in it are singles
-          for (int i = first; i <= last; ++i) { const Elem& el = elems[A][i]; if (el.block >= 0) lists[el.block][A][q][1].push_back({OutPair{i, el.d, 0}, OutCoef{el.c, 0.0}}); }
-          continue;
-        }
-        // constraint values: the g array is small and stays in L2, where partial-sector writes are cheap, and a
-        // unit owns only 3 - 10 of them: they are written with lane = instance (no transposition)
-        bool full = whole_in_row && (A == 0 || !g_as_singles);
-        for (int i = first; i <= last && full; ++i) { const int b = elems[A][i].block; if (b != writer && (b < 0 || b != pred[writer])) full = false; }
-        if (!full) {
-          for (int i = first; i <= last; ++i) { const Elem& el = elems[A][i]; if (el.block >= 0) lists[el.block][A][q][1].push_back({OutPair{i, el.d, 0}, OutCoef{el.c, 0.0}}); }
-          continue;
-        }
-        uint16_t d[4]; double cf[4];
-        for (int h = 0; h < 4; ++h) {
-          const Elem& el = elems[A][first + h];
-          if (el.block == writer) { d[h] = el.d; cf[h] = el.c; }
-          else {   // owned by the preceding warp: published into this block's carry row
-            const int row = carry0[writer] + 3 * A + h;
-            lists[el.block][A][q][2].push_back({OutPair{row, el.d, 0}, OutCoef{el.c, 0.0}});
-            d[h] = (uint16_t)row; cf[h] = 1.0;
-          }
-        }
-        lists[writer][A][q][0].push_back({OutPair{first, d[0], d[1]}, OutCoef{cf[0], cf[1]}});
-        lists[writer][A][q][0].push_back({OutPair{first + 2, d[2], d[3]}, OutCoef{cf[2], cf[3]}});
+  // lists[list][class][0: pairs, 1: singles]
+  std::vector<std::array<std::array<std::vector<Entry>, 2>, kMaxClasses>> lists(n_lists);
+  const int NC = (nnz % 4 == 0) ? 1 : (nnz % 2 == 0) ? 2 : 4;
+  pl.nc_jac = NC; pl.nc_g = 1;
+  for (int q = 0; q < NC; ++q) {
+    const int L = nnz, c = (int)(((long long)q * L) % 4);   // position of the row's first element inside its sector
+    std::vector<int> hits(L, 0);
+    for (int S = 0; 4 * S < c + L; ++S) {
+      const int first = std::max(0, 4 * S - c), last = std::min(L - 1, 4 * S + 3 - c);
+      const int writer = elems[last].list;
+      bool full = (4 * S - c >= 0) && (4 * S + 3 - c <= L - 1) && writer >= 0;
+      for (int i = first; i <= last && full; ++i) if (elems[i].list != writer) full = false;
+      if (!full) {
+        for (int i = first; i <= last; ++i) if (elems[i].list >= 0) { lists[elems[i].list][q][1].push_back({OutPair{i, elems[i].d, 0}, OutCoef{elems[i].c, 0.0}}); hits[i]++; }
+        continue;
       }
+      lists[writer][q][0].push_back({OutPair{first, elems[first].d, elems[first + 1].d}, OutCoef{elems[first].c, elems[first + 1].c}});
+      lists[writer][q][0].push_back({OutPair{first + 2, elems[first + 2].d, elems[first + 3].d}, OutCoef{elems[first + 2].c, elems[first + 3].c}});
+      for (int i = first; i <= last; ++i) hits[i]++;
     }
+    // self-check: every element of an output-kernel row is written exactly once
+    for (int i = 0; i < L; ++i) if (hits[i] != (elems[i].list >= 0 ? 1 : 0)) return fail(TWB_ERR_UNSUPPORTED, "output lists do not cover every element exactly once");
   }
-  pl.nc_jac = n_classes[0]; pl.nc_g = n_classes[1];
-  // self-check: for every alignment class, every element is written exactly once
-  for (int A = 0; A < 2; ++A) for (int q = 0; q < n_classes[A]; ++q) {
-    std::vector<int> hits(len[A], 0);
-    for (int b = 0; b < n_blocks; ++b) {
-      for (const Entry& en : lists[b][A][q][0]) { hits[en.p.off]++; hits[en.p.off + 1]++; }
-      for (const Entry& en : lists[b][A][q][1]) hits[en.p.off]++;
-    }
-    for (int i = 0; i < len[A]; ++i) if (hits[i] != (elems[A][i].block >= 0 ? 1 : 0)) return fail(TWB_ERR_UNSUPPORTED, "output lists do not cover every element exactly once");
-  }
-  auto flush = [&](int block, OutList* out) {
-    *out = OutList{};
-    for (int A = 0; A < 2; ++A) for (int q = 0; q < n_classes[A]; ++q) {
-      OutRange* dst[3] = {&out->pairs[A][q], &out->singles[A][q], &out->publish[A][q]};
-      for (int w = 0; w < 3; ++w) {
-        const auto& v = lists[block][A][q][w];
+  auto flush_list = [&](int list) {
+    OutList out{};
+    for (int q = 0; q < NC; ++q) {
+      OutRange* dst[2] = {&out.pairs[0][q], &out.singles[0][q]};
+      for (int w = 0; w < 2; ++w) {
+        const auto& v = lists[list][q][w];
         dst[w]->first = (int32_t)tb.pairs.size(); dst[w]->count = (int32_t)v.size();
         for (const Entry& en : v) { tb.pairs.push_back(en.p); tb.coefs.push_back(en.c); }
       }
     }
+    return out;
   };
-  for (int k = 0; k < pl.n_dyn; ++k) flush(k, &tb.dyn[k].out);
-  for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) flush(pl.n_dyn + k * n_ee + e, &tb.rom[k].out[e]);
+  auto flush_values = [&](int block) {
+    OutRange r{(int32_t)tb.pairs.size(), (int32_t)values[block].size()};
+    for (const Entry& en : values[block]) { tb.pairs.push_back(en.p); tb.coefs.push_back(en.c); }
+    return r;
+  };
+  for (int i = 0; i < n_lists; ++i) tb.cta_lists.push_back(flush_list(i));
+  for (int k = 0; k < pl.n_dyn; ++k) tb.dyn[k].values = flush_values(k);
+  for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) tb.rom[k].values[e] = flush_values(pl.n_dyn + k * n_ee + e);
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     NodeGroup ng{}; ng.kind = groups[gi].kind; ng.first = groups[gi].first; ng.count = groups[gi].count;
-    flush(pl.n_dyn + n_rom_blocks + (int)gi, &ng.out);
+    ng.values = flush_values(pl.n_dyn + n_rom_blocks + (int)gi);
     tb.groups.push_back(ng);
   }
+  pl.dyn_list0 = 0; pl.rom_list0 = n_dyn_ctas; pl.node_list0 = n_dyn_ctas + n_rom_ctas * n_ee;
 
   // ---- costs (nlp_formulation.cc:333-376, node_cost.cc:53-76)
   has_cost = false;

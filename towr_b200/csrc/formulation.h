@@ -45,6 +45,7 @@ struct HostTables {
   std::vector<CostEntry> cost;
   std::vector<OutPair> pairs;
   std::vector<OutCoef> coefs;
+  std::vector<OutList> cta_lists;
   std::vector<double> dyn_ang_basis;
   std::vector<PhaseSplineDef> phase_defs;
   std::vector<PhasePoly> phase_polys;

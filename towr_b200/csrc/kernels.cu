@@ -536,10 +536,11 @@ __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ G
   }
 }
 
-// ---- warp-collective output of one unit: lanes switch from "instance" to "pair of output elements" ----
-// out[j][off + h] = t[d_h][j] * c_h for the instances j = j0, j0 + jstep, .. < n_inst of the tile;
-// `out` points at element 0 of the tile's first instance, `stride` is the row length (nnz or m).
-// The list holds whole 32-byte sectors (two consecutive pairs = two adjacent lanes).
+// ---- CTA-collective output: threads switch from "instance" to "pair of output elements" ----------------------
+// out[j][off + h] = t[d_h][j] * c_h for the instances j = j0, j0 + jstep, .. < n_inst of the tile; `t` is the CTA's
+// shared memory (all state blocks), `out` points at element 0 of the tile's first instance, `stride` is the row length
+// (nnz).  The list holds whole 32-byte sectors (two consecutive pairs = two adjacent lanes); thread `tid` of
+// `n_threads` takes the pairs tid, tid + n_threads, ..
 __device__ __forceinline__ void LoadPair(const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs, int i, int n,
                                          int* off, int* d0, int* d1, double* c0, double* c1) {
   if (i < n) {
@@ -549,14 +550,15 @@ __device__ __forceinline__ void LoadPair(const OutPair* __restrict__ pairs, cons
   }
 }
 __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
-                                           int n_pairs, double* __restrict__ out, size_t stride, int j0, int jstep, int n_inst, int lane) {
-  if (n_pairs <= 0) return;
+                                           int n_pairs, double* __restrict__ out, size_t stride, int j0, int jstep, int n_inst,
+                                           int tid, int n_threads) {
+  if (tid >= n_pairs) return;
   int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
-  LoadPair(pairs, coefs, lane, n_pairs, &off, &d0, &d1, &c0, &c1);
-  for (int i = lane; i < n_pairs; i += 32) {
-    // prefetch the next entry of this lane under the stores of the current one
+  LoadPair(pairs, coefs, tid, n_pairs, &off, &d0, &d1, &c0, &c1);
+  for (int i = tid; i < n_pairs; i += n_threads) {
+    // prefetch the next entry of this thread under the stores of the current one
     int noff = 0, nd0 = 0, nd1 = 0; double nc0 = 0.0, nc1 = 0.0;
-    LoadPair(pairs, coefs, i + 32, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
+    LoadPair(pairs, coefs, i + n_threads, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
     double* o = out + off;
     const double* r0 = t + d0 * kLD; const double* r1 = t + d1 * kLD;
     if (n_inst == 32 && jstep == 1) {
@@ -574,90 +576,46 @@ __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __res
     off = noff; d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1;
   }
 }
-// single elements: lane = instance (8-byte stores, one per instance).  The entries are fetched with one
-// coalesced load (lane = entry) and broadcast with shuffles, so a list costs one memory round trip.
-__device__ __forceinline__ void StoreSingles(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
-                                             int n, double* __restrict__ out, size_t stride, bool active, int lane) {
-#ifdef TWB_EXP_NOSINGLES
-  return;
-#endif
-  double* o = out + (size_t)lane * stride;
-  const double* tl = t + lane;
+// Entries handled with lane = instance: fetched with one coalesced load (lane = entry), broadcast with shuffles.
+// fn(first, d0, coefficient) is called by every lane of the warp for every entry.
+template <class F>
+__device__ __forceinline__ void ForEachEntry(const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs, int n, int lane, F&& fn) {
   for (int base = 0; base < n; base += 32) {
     uint2 raw = make_uint2(0u, 0u); double c = 0.0;
     if (base + lane < n) { raw = __ldg(reinterpret_cast<const uint2*>(pairs) + base + lane); c = __ldg(reinterpret_cast<const double*>(coefs + base + lane)); }
     const int cnt = min(32, n - base);
-    for (int s = 0; s < cnt; ++s) {
-      const int off = __shfl_sync(0xffffffffu, (int)raw.x, s), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), s);
-      const double cs = __shfl_sync(0xffffffffu, c, s);
-      if (active) StoreOut(o + off, tl[d * kLD] * cs);
-    }
-  }
-}
-// constraint values: lane = instance writes GT[row][lane] (instance-tiled, 256 contiguous bytes per row and
-// warp); TransposeOut turns the tiles into g[B][m] afterwards.  One unit owns only 3 - 10 constraint values per
-// instance — written straight into g[B][m] they would be 8-byte pieces of sectors shared with other units.
-__device__ __forceinline__ void StoreValuesTiled(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
-                                                 int n, double* __restrict__ gt_tile, int lane) {
-  const double* tl = t + lane;
-  for (int base = 0; base < n; base += 32) {
-    uint2 raw = make_uint2(0u, 0u); double c = 0.0;
-    if (base + lane < n) { raw = __ldg(reinterpret_cast<const uint2*>(pairs) + base + lane); c = __ldg(reinterpret_cast<const double*>(coefs + base + lane)); }
-    const int cnt = min(32, n - base);
-    for (int s = 0; s < cnt; ++s) {
-      const int off = __shfl_sync(0xffffffffu, (int)raw.x, s), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), s);
-      const double cs = __shfl_sync(0xffffffffu, c, s);
-      gt_tile[(size_t)off * 32 + lane] = tl[d * kLD] * cs;
-    }
-  }
-}
-// carry values for the next warp of the CTA: lane = instance, next[row][lane] = t[d][lane] * c
-__device__ __forceinline__ void PublishList(const double* t, double* next, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
-                                            int n, bool active, int lane) {
-  uint2 raw = make_uint2(0u, 0u); double c = 0.0;   // at most 3 entries per list
-  if (lane < n) { raw = __ldg(reinterpret_cast<const uint2*>(pairs) + lane); c = __ldg(reinterpret_cast<const double*>(coefs + lane)); }
-  for (int s = 0; s < n; ++s) {
-    const int row = __shfl_sync(0xffffffffu, (int)raw.x, s), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), s);
-    const double cs = __shfl_sync(0xffffffffu, c, s);
-    if (active) next[row * kLD + lane] = t[d * kLD + lane] * cs;
+    for (int s = 0; s < cnt; ++s)
+      fn(__shfl_sync(0xffffffffu, (int)raw.x, s), __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), s), __shfl_sync(0xffffffffu, c, s));
   }
 }
 __device__ __forceinline__ OutRange LoadRange(const OutRange* r) {
   const int2 v = __ldg(reinterpret_cast<const int2*>(r)); return OutRange{v.x, v.y};
 }
-// before the CTA barrier: hand the tail elements of this unit's last, incomplete sectors to the next warp
-__device__ __forceinline__ void PublishUnit(const Plan& P, const double* t, double* next, const OutList& L, unsigned flags, int lane) {
-#ifdef TWB_EXP_NOSINGLES
-  return;
-#endif
-  if (!(flags & 2u)) return;
-  const int nc = P.nc_jac;
-  for (int q = 0; q < nc; ++q) {
-    const OutRange r = LoadRange(&L.publish[0][q]);
-    if (r.count > 0) PublishList(t, next, P.pairs + r.first, P.coefs + r.first, r.count, (lane % nc) == q, lane);
-  }
+// constraint values of one unit: lane = instance writes GT[row][lane] (instance-tiled, 256 contiguous bytes per row and
+// warp); TransposeOut turns the tiles into g[B][m] afterwards.  One unit owns only 3 - 10 constraint values per
+// instance — written straight into g[B][m] they would be 8-byte pieces of sectors shared with other units.
+__device__ __forceinline__ void StoreValuesTiled(const Plan& P, const double* t, const OutRange* values, double* __restrict__ gt_tile, int lane) {
+  const OutRange r = LoadRange(values);
+  ForEachEntry(P.pairs + r.first, P.coefs + r.first, r.count, lane,
+               [&](int g_row, int d, double c) { gt_tile[(size_t)g_row * 32 + lane] = t[d * kLD + lane] * c; });
 }
-// all outputs of one unit: Jacobian values (flags & 2) into the tile's rows of jac[B][nnz], constraint values
-// (flags & 1) into the tile of GT
-__device__ __forceinline__ void StoreUnit(const Plan& P, const double* t, const OutList& L, double* __restrict__ gt_tile,
-                                          double* __restrict__ jac_tile, unsigned flags, int n_inst, int lane) {
+// Jacobian values of a whole CTA (after its barrier): every thread takes pairs of the CTA's list; warp 0 writes the
+// single elements (sectors shared with a neighbouring CTA) with lane = instance.
+__device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst) {
 #ifdef TWB_EXP_NOSTORE   // timing experiment: compute phase only
   return;
 #endif
-#ifdef TWB_EXP_NOG
-  flags &= ~1u;
-#endif
-  if (flags & 2u) {
-    const int nc = P.nc_jac;
-    for (int q = 0; q < nc; ++q) {
-      const OutRange rp = LoadRange(&L.pairs[0][q]), rs = LoadRange(&L.singles[0][q]);
-      StorePairs(t, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, lane);
-      if (rs.count > 0) StoreSingles(t, P.pairs + rs.first, P.coefs + rs.first, rs.count, jac_tile, (size_t)P.nnz, lane < n_inst && (lane % nc) == q, lane);
+  const int nc = P.nc_jac, lane = threadIdx.x & 31;
+  for (int q = 0; q < nc; ++q) {
+    const OutRange rp = LoadRange(&list->pairs[0][q]);
+    StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, threadIdx.x, blockDim.x);
+    if (threadIdx.x < 32) {
+      const OutRange rs = LoadRange(&list->singles[0][q]);
+      const bool active = lane < n_inst && (lane % nc) == q;
+      double* o = jac_tile + (size_t)lane * P.nnz;
+      ForEachEntry(P.pairs + rs.first, P.coefs + rs.first, rs.count, lane,
+                   [&](int off, int d, double c) { if (active) StoreOut(o + off, cta_smem[d * kLD + lane] * c); });
     }
-  }
-  if (flags & 1u) {
-    const OutRange rs = LoadRange(&L.singles[1][0]);
-    StoreValuesTiled(t, P.pairs + rs.first, P.coefs + rs.first, rs.count, gt_tile, lane);
   }
 }
 // non-finite check of this lane's own column (rows 1 .. n_rows-1); flags instance b
@@ -669,49 +627,46 @@ __device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int l
 }
 
 // DynamicConstraint: blockIdx.y = instance tile, warp = one of kDynWarps CONSECUTIVE samples, so a CTA writes
-// several KB of contiguous CSR values per instance (the samples' rows are adjacent) and the sectors shared by
-// two samples are completed through the carry rows.
+// several KB of contiguous CSR values per instance (the samples' rows are adjacent).
 template <int kNEE, bool kPhase>
-__device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
+__device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kDynWarps + warp, b0 = tile * 32;
-  const bool valid = k < P.n_dyn;
-  constexpr int G0 = 40 + 6 * kNEE, n_rows = G0 + 6, block_rows = n_rows + kCarryRows;   // local rows: 1 | 3 | 36 | 6 per foot | g (6) | carry-in
-  double* t = out_smem + (size_t)warp * block_rows * kLD;
-  const DynUnit* u = P.dyn + k;
-  if (valid) {
+  constexpr int G0 = 40 + 6 * kNEE, n_rows = G0 + 6;   // local rows: 1 | 3 | 36 | 6 per foot | g (6)
+  double* t = out_smem + (size_t)warp * n_rows * kLD;
+  if (k < P.n_dyn) {
+    const DynUnit* u = P.dyn + k;
     t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE   // (timing experiment: store phase only)
     DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
     FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
 #endif
-    __syncwarp();
-    if (warp + 1 < kDynWarps) PublishUnit(P, t, t + block_rows * kLD, u->out, flags, lane);
+    if (flags & 1u) StoreValuesTiled(P, t, &u->values, GT + (size_t)b0 * P.m, lane);
   }
   __syncthreads();
-  if (valid) StoreUnit(P, t, u->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);   // g = GT: tile at b0 * m
+  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.dyn_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0));
 }
 
 // RangeOfMotionConstraint (range_of_motion_constraint.cc:58-109): g_e = R^T (p_e - c); Jacobian state R^T and
 // D_e = d(R^T r_e)/d(theta) (EulerConverter::DerivOfRotVecMult(t, r_W, true)).  blockIdx.y = instance tile,
-// warp = one of kRomWarps consecutive samples.  The rotation and its derivative are computed once per sample;
-// the feet then take turns: foot e's D_e and g_e overwrite the previous foot's state rows once its values have
-// been written, so a warp needs 22 state rows (+ 6 carry-in rows per foot) instead of 10 + 12 n_ee.
+// warp = one of kRomWarps consecutive samples.  The rotation and its derivative are computed once per sample; the
+// feet then take turns through two alternating buffers of 12 state rows (D_e, g_e): while the CTA writes the
+// Jacobian values of foot e (one list per foot: the foot's rows of the CTA's samples are adjacent), every warp
+// already evaluates foot e + 1 — one CTA barrier per foot.
 template <int kNEE, bool kPhase>
-__device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
+__device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kRomWarps + warp, b0 = tile * 32;
   const bool valid = k < P.n_rom;
-  constexpr int block_rows = kRomStateRows + kCarryRows * kNEE;
-  double* t = out_smem + (size_t)warp * block_rows * kLD;
+  double* t = out_smem + (size_t)warp * kRomBlockRows * kLD;
   const RomUnit* u = P.rom + (valid ? k : 0);
   const SplineSample* __restrict__ sp = P.samples + __ldg(&u->sample0);
   const ConstCol xs = TiledCol(XT, b0 + lane, P.n + 1);
-  const Col Sk{t + kLD + lane, kLD};   // local state rows 1..: R^T (0..8) | D_e (9..17) | g_e (18..20)
+  const Col Sk{t + kLD + lane, kLD};   // local state rows 1..: R^T (0..8) | buffer 0: D_e (9..17), g_e (18..20) | buffer 1: (21..29), (30..32)
   const int n_inst = min(32, nb - b0);
-  double* g_tile = g + (size_t)b0 * P.m; double* jac_tile = jac + (size_t)b0 * P.nnz;
+  double* jac_tile = jac + (size_t)b0 * P.nnz;
   t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE
   double c[3], th[3], unused[3];
@@ -727,71 +682,69 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
 #endif
 #pragma unroll 1
   for (int e = 0; e < kNEE; ++e) {
+    const int buf = 12 * (e & 1);
 #ifndef TWB_EXP_NOCOMPUTE
     double pe[3];
     EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
     const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
     double D[3][3]; RotVecDerivative<true>(dR, r, D);
-    if (e > 0) __syncwarp();   // the previous foot's values have left the state rows
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Sk[18 + i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
+    for (int i = 0; i < 3; ++i) Sk[18 + buf + i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int d = 0; d < 3; ++d) Sk[9 + i * 3 + d] = D[i][d];
-    if (valid) FlagNonFinite(t, kRomStateRows, lane, status, b0 + lane, nb, e == 0 ? 1 : 10);
+      for (int d = 0; d < 3; ++d) Sk[9 + buf + i * 3 + d] = D[i][d];
+    if (valid) {
+      if (e == 0) FlagNonFinite(t, 10, lane, status, b0 + lane, nb);
+      FlagNonFinite(t, 22 + buf, lane, status, b0 + lane, nb, 10 + buf);
+    }
 #endif
-    __syncwarp();
-    if (valid && warp + 1 < kRomWarps) PublishUnit(P, t, t + block_rows * kLD, u->out[e], flags, lane);
-    __syncthreads();
-    if (valid) StoreUnit(P, t, u->out[e], g_tile, jac_tile, flags, n_inst, lane);
+    if (valid && (flags & 1u)) StoreValuesTiled(P, t, &u->values[e], GT + (size_t)b0 * P.m, lane);
+    __syncthreads();   // foot e complete in every block; everybody is done reading buffer (e + 1) & 1 (the list of foot e - 1)
+    if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst);
   }
 }
 
 // node groups: blockIdx.y = instance tile, warp = one of kNodeWarps consecutive groups
-__device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ g, double* __restrict__ jac,
+__device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                          int* __restrict__ status, const int* __restrict__ terrain_ids, int default_terrain, int nb,
                                          unsigned flags, double* node_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = cta * kNodeWarps + warp, b0 = tile * 32, b = b0 + lane;
-  const bool valid = gi < P.n_groups;
-  const int block_rows = P.node_rows + kCarryRows;
-  double* t = node_smem + (size_t)warp * block_rows * kLD;
-  const ConstCol xs = TiledCol(XT, b, P.n + 1);
-  const NodeGroup* grp = P.groups + (valid ? gi : 0);
-  const int kind = __ldg(&grp->kind), first = __ldg(&grp->first), count = __ldg(&grp->count);
-  t[lane] = 1.0;
-  int n_rows = 1;
-#ifdef TWB_EXP_NOCOMPUTE
-  if (true) {
-#else
-  if (!valid) {
+  double* t = node_smem + (size_t)warp * P.node_rows * kLD;
+  if (gi < P.n_groups) {
+    const ConstCol xs = TiledCol(XT, b, P.n + 1);
+    const NodeGroup* grp = P.groups + gi;
+    const int kind = __ldg(&grp->kind), first = __ldg(&grp->first), count = __ldg(&grp->count);
+    t[lane] = 1.0;
+    int n_rows = 1;
+#ifndef TWB_EXP_NOCOMPUTE
+    if (kind == kGroupForce) {
+      const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
+      for (int q = 0; q < count; ++q)
+        ForceUnitEval(P, P.force[first + q], terrain, xs, Col{t + (1 + 25 * q) * kLD + lane, kLD}, Col{t + (1 + 25 * count + 5 * q) * kLD + lane, kLD});
+      n_rows = 1 + 30 * count;
+    } else if (kind == kGroupTerrain) {
+      const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
+      for (int q = 0; q < count; ++q)
+        TerrainUnitEval(P.terr[first + q], terrain, xs, Col{t + (1 + 2 * q) * kLD + lane, kLD}, Col{t + (1 + 2 * count + q) * kLD + lane, kLD});
+      n_rows = 1 + 3 * count;
+    } else if (kind == kGroupSwing) {
+      if (flags & 1u) for (int q = 0; q < count; ++q) SwingUnitEval(P.swing[first + q], xs, Col{t + (1 + 4 * q) * kLD + lane, kLD});
+      n_rows = (flags & 1u) ? 1 + 4 * count : 1;
+    } else if (kind == kGroupAcc) {
+      if (flags & 1u) for (int q = 0; q < count; ++q) AccUnitEval(P.acc[first + q], xs, Col{t + (1 + 3 * q) * kLD + lane, kLD});
+      n_rows = (flags & 1u) ? 1 + 3 * count : 1;
+    } else if (kind == kGroupBaseMotion) {
+      if (flags & 1u) for (int q = 0; q < count; ++q) BaseMotionUnitEval(P, P.base_motion[first + q], xs, Col{t + (1 + 6 * q) * kLD + lane, kLD});
+      n_rows = (flags & 1u) ? 1 + 6 * count : 1;
+    }
+    FlagNonFinite(t, n_rows, lane, status, b, nb);
 #endif
-  } else if (kind == kGroupForce) {
-    const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
-    for (int q = 0; q < count; ++q)
-      ForceUnitEval(P, P.force[first + q], terrain, xs, Col{t + (1 + 25 * q) * kLD + lane, kLD}, Col{t + (1 + 25 * count + 5 * q) * kLD + lane, kLD});
-    n_rows = 1 + 30 * count;
-  } else if (kind == kGroupTerrain) {
-    const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
-    for (int q = 0; q < count; ++q)
-      TerrainUnitEval(P.terr[first + q], terrain, xs, Col{t + (1 + 2 * q) * kLD + lane, kLD}, Col{t + (1 + 2 * count + q) * kLD + lane, kLD});
-    n_rows = 1 + 3 * count;
-  } else if (kind == kGroupSwing) {
-    if (flags & 1u) for (int q = 0; q < count; ++q) SwingUnitEval(P.swing[first + q], xs, Col{t + (1 + 4 * q) * kLD + lane, kLD});
-    n_rows = (flags & 1u) ? 1 + 4 * count : 1;
-  } else if (kind == kGroupAcc) {
-    if (flags & 1u) for (int q = 0; q < count; ++q) AccUnitEval(P.acc[first + q], xs, Col{t + (1 + 3 * q) * kLD + lane, kLD});
-    n_rows = (flags & 1u) ? 1 + 3 * count : 1;
-  } else if (kind == kGroupBaseMotion) {
-    if (flags & 1u) for (int q = 0; q < count; ++q) BaseMotionUnitEval(P, P.base_motion[first + q], xs, Col{t + (1 + 6 * q) * kLD + lane, kLD});
-    n_rows = (flags & 1u) ? 1 + 6 * count : 1;
+    if (flags & 1u) StoreValuesTiled(P, t, &grp->values, GT + (size_t)b0 * P.m, lane);
   }
-  if (valid) FlagNonFinite(t, n_rows, lane, status, b, nb);
-  __syncwarp();
-  if (valid && warp + 1 < kNodeWarps) PublishUnit(P, t, t + block_rows * kLD, grp->out, flags, lane);
   __syncthreads();
-  if (valid) StoreUnit(P, t, grp->out, g + (size_t)b0 * P.m, jac + (size_t)b0 * P.nnz, flags, min(32, nb - b0), lane);
+  if (flags & 2u) StoreCta(P, node_smem, P.cta_lists + P.node_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0));
 }
 
 // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
@@ -1004,7 +957,7 @@ template <int kNEE, bool kPhase>
 cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, int* status, const int* terrain_ids, int default_terrain,
                       int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
   const size_t row_bytes = (size_t)kLD * sizeof(double);
-  const int dyn_rows = 46 + 6 * kNEE + kCarryRows, rom_rows = kRomStateRows + kCarryRows * kNEE, node_rows = P.node_rows + kCarryRows;
+  const int dyn_rows = 46 + 6 * kNEE, rom_rows = kRomBlockRows, node_rows = P.node_rows;
   cudaError_t e = cudaSuccess;
 #if TWB_FUSED
   const int n_ctas = (P.n_dyn + kWarps - 1) / kWarps + (P.n_rom + kWarps - 1) / kWarps + (P.n_groups + kWarps - 1) / kWarps;
