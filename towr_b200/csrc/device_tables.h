@@ -92,7 +92,7 @@ constexpr int kDynWarps = kWarps, kRomWarps = kWarps, kNodeWarps = kWarps;
 #define TWB_DYN_WARPS 4
 #endif
 #ifndef TWB_ROM_WARPS
-#define TWB_ROM_WARPS 7
+#define TWB_ROM_WARPS 5
 #endif
 #ifndef TWB_NODE_WARPS
 #define TWB_NODE_WARPS 8

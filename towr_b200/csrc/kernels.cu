@@ -46,10 +46,10 @@ namespace {
 #define TWB_DYN_CTAS 2
 #endif
 #ifndef TWB_ROM_CTAS
-#define TWB_ROM_CTAS 2
+#define TWB_ROM_CTAS 3
 #endif
 #ifndef TWB_NODE_CTAS
-#define TWB_NODE_CTAS 2
+#define TWB_NODE_CTAS 3
 #endif
 #endif
 constexpr int kLD = 34;                      // leading dimension of a state block: 32 instances, padded; even keeps rows 16-byte aligned
