@@ -91,11 +91,17 @@ constexpr int kDynWarps = kWarps, kRomWarps = kWarps, kNodeWarps = kWarps;
 #ifndef TWB_DYN_WARPS
 #define TWB_DYN_WARPS 4
 #endif
+// TWB_ROMNODE = 1 (default): the range-of-motion and node CTAs of a tile run in ONE kernel (RomNodeOut, equal CTA sizes),
+// so that the CTAs resident at any moment fill long contiguous stretches of the tile's rows; the dynamic samples
+// (different register budget) keep their own kernel on a second stream.
+#ifndef TWB_ROMNODE
+#define TWB_ROMNODE 1
+#endif
 #ifndef TWB_ROM_WARPS
-#define TWB_ROM_WARPS 5
+#define TWB_ROM_WARPS 4
 #endif
 #ifndef TWB_NODE_WARPS
-#define TWB_NODE_WARPS 8
+#define TWB_NODE_WARPS (TWB_ROMNODE ? TWB_ROM_WARPS : 8)
 #endif
 constexpr int kDynWarps = TWB_DYN_WARPS;     // consecutive dynamic samples per CTA (one instance tile)
 constexpr int kRomWarps = TWB_ROM_WARPS;     // consecutive range-of-motion samples per CTA

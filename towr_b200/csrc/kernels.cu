@@ -46,7 +46,7 @@ namespace {
 #define TWB_DYN_CTAS 2
 #endif
 #ifndef TWB_ROM_CTAS
-#define TWB_ROM_CTAS 3
+#define TWB_ROM_CTAS 4
 #endif
 #ifndef TWB_NODE_CTAS
 #define TWB_NODE_CTAS 3
@@ -950,6 +950,18 @@ __global__ void __launch_bounds__(kNodeWarps * 32, TWB_NODE_CTAS) NodeOut(const 
   extern __shared__ __align__(16) double out_smem[];
   NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x, blockIdx.y);
 }
+#if TWB_ROMNODE   // experiment: range-of-motion and node CTAs of a tile in one kernel (kRomWarps == kNodeWarps)
+template <int kNEE, bool kPhase>
+__global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
+                                                               double* __restrict__ jac, int* __restrict__ status,
+                                                               const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags) {
+  extern __shared__ __align__(16) double out_smem[];
+  static_assert(kRomWarps == kNodeWarps, "TWB_ROMNODE needs equal CTA sizes");
+  const int n_rom_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps;
+  if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+  else NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x - n_rom_ctas, blockIdx.y);
+}
+#endif
 #endif
 
 // s: caller's stream (after TransposeIn); a0, a1: auxiliary streams already waiting on the transposition
@@ -968,6 +980,22 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
   EvalOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
   ++*count; TWB_MARK("EvalOut", s);
 #else
+#if TWB_ROMNODE
+  {
+    const size_t smem = (size_t)kRomWarps * std::max(rom_rows, node_rows) * row_bytes;
+    if ((e = cudaFuncSetAttribute(RomNodeOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps;
+    RomNodeOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
+    ++*count; TWB_MARK("RomNodeOut", s);
+  }
+  if (P.n_dyn > 0) {
+    const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
+    if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
+    ++*count; TWB_MARK("DynOut", a0);
+  }
+  return cudaSuccess;
+#endif
   if (P.n_rom > 0) {
     const size_t smem = (size_t)kRomWarps * rom_rows * row_bytes;
     if ((e = cudaFuncSetAttribute(RomOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
