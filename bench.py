@@ -108,6 +108,7 @@ def kernel_breakdown(p, B):
         return 8 * B * (nz + mm)
     alg = {"DynOut": share(lambda n: n == "dynamic"), "RomOut": share(lambda n: n.startswith("rangeofmotion")),
            "NodeOut": share(lambda n: n != "dynamic" and not n.startswith(("rangeofmotion", "totalduration"))),
+           "RomNodeOut": share(lambda n: n != "dynamic" and not n.startswith("totalduration")),
            "TransposeIn": 2 * 8 * B * p.n, "TransposeOut": 2 * 8 * B * p.m}
     res = {}
     for line in out.splitlines():
@@ -115,6 +116,9 @@ def kernel_breakdown(p, B):
         if line.startswith("[twb profile]") and "avg" in parts:
             name, us = parts[2], float(parts[parts.index("avg") + 1])
             res[name] = {"avg_us": us}
+            if name == "TransposeIn":
+                res[name]["note"] = "first kernel of a step: includes the host launch gap of the serialised pass (ncu: 13 us)"
+                continue
             if name in alg and us > 0:
                 res[name]["algorithmic_bytes"] = alg[name]
                 res[name]["gbs"] = alg[name] / (us * 1e-6) / 1e9
@@ -137,9 +141,13 @@ def cpu_arm(spec, problem, X, threads, target_seconds=12.0):
     t0 = time.perf_counter(); oracle_lib.batch_eval(spec, X[:probe], threads=threads); t_probe = time.perf_counter() - t0
     per_eval = t_probe / probe
     sample = int(max(probe, min(len(X), target_seconds / max(per_eval, 1e-9))))
-    t0 = time.perf_counter(); r = oracle_lib.batch_eval(spec, X[:sample], threads=threads); dt = time.perf_counter() - t0
-    assert r["rc"] == 0
-    return sample / dt, sample, dt
+    reps = int(max(1, min(64, round(target_seconds / max(per_eval * sample, 1e-9)))))   # small batches: repeat them
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = oracle_lib.batch_eval(spec, X[:sample], threads=threads)
+        assert r["rc"] == 0
+    dt = time.perf_counter() - t0
+    return sample * reps / dt, sample * reps, dt
 
 
 def run_reference(args):
@@ -318,12 +326,12 @@ def run_cuda(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_eval * B, "avg_launch_ms": avg_kernel_ms,
-                         "kernel": "whole evaluation: TransposeIn -> DynOut | RomOut | NodeOut (three streams) -> TransposeOut; "
+                         "kernel": "whole evaluation: TransposeIn -> RomNodeOut | DynOut (two streams) -> TransposeOut; "
                                    "CUDA events on the launching stream around every step of the timed region",
                          "dominant_kernel": dominant},
             "kernels": kernels,
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"first {cpu_sample} instances of the same batch, OpenMP over instances, {cpu_dt:.1f} s"},
+                             "sample": f"{cpu_sample} evaluations of instances of the same batch, OpenMP over instances, {cpu_dt:.1f} s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "twb_batch_eval_host (pinned host buffers)"},
             "gpu_launches": args.steps * batch.launches_per_eval(flags),

@@ -228,7 +228,7 @@ int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   const twb::Plan& p = b->plan;
   const bool want_cost = b->prob->f.has_cost && (flags & TWB_EVAL_COST);
   int n = 1;   // TransposeIn
-  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += (p.n_dyn > 0) + (p.n_rom > 0) + (p.n_groups > 0);   // DynOut, RomOut, NodeOut
+  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += twb::OutKernelsPerEval(p);   // DynOut + RomNodeOut (or RomOut, NodeOut)
   if ((flags & (TWB_EVAL_G | TWB_EVAL_JAC)) && p.n_phase_units > 0) n += 1;   // PhaseJac
   if (flags & TWB_EVAL_G) n += 1;   // TransposeOut
   if (want_cost) n += 1;

@@ -985,8 +985,10 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     const size_t smem = (size_t)kRomWarps * std::max(rom_rows, node_rows) * row_bytes;
     if ((e = cudaFuncSetAttribute(RomNodeOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps;
-    RomNodeOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
-    ++*count; TWB_MARK("RomNodeOut", s);
+    if (n_ctas > 0) {
+      RomNodeOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
+      ++*count; TWB_MARK("RomNodeOut", s);
+    }
   }
   if (P.n_dyn > 0) {
     const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
@@ -1021,6 +1023,16 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
 }  // namespace
 
 // ---- host launchers ------------------------------------------------------------------
+
+int OutKernelsPerEval(const Plan& P) {
+#if TWB_FUSED
+  return (P.n_dyn + P.n_rom + P.n_groups) > 0;
+#elif TWB_ROMNODE
+  return (P.n_dyn > 0) + ((P.n_rom + P.n_groups) > 0);
+#else
+  return (P.n_dyn > 0) + (P.n_rom > 0) + (P.n_groups > 0);
+#endif
+}
 
 // XT / GT are the instance-tiled iterate and constraint-value matrices of the whole batch (first tile = first
 // instance of x / g / jac).  Streams: `s` carries TransposeIn -> [out kernels] -> TransposeOut; with separate

@@ -17,6 +17,8 @@ extern void (*g_after_launch)(const char* label, cudaStream_t stream);
 // tile = 32 consecutive instances), GT is [tiles][m][32] (staging of the constraint values).  x, g, jac, cost, grad, status and terrain_ids point at the first
 // instance.  `flags` are the TWB_EVAL_* bits.  Work is enqueued on `s` and on two auxiliary streams that
 // are forked from / joined back into `s` with ev[0..2].
+// number of output kernels one evaluation launches for this plan
+int OutKernelsPerEval(const Plan& P);
 int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,
                int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
                cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches);
