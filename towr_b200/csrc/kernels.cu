@@ -5,20 +5,23 @@
 // every read of a node value by a warp is one 256-byte row segment:
 //
 //   TransposeIn   x[B][n]   -> XT[tile][n+1][32]   (row n stays 0: "not optimised" node values)
-//   DynOut        XT        -> g rows + CSR values of the dynamic constraint          (warp = sample x tile)
-//   RomOut        XT        -> g rows + CSR values of the range-of-motion constraints (warp = sample x tile, all feet)
-//   NodeOut       XT        -> g rows + CSR values of the node-wise sets: terrain, force, swing, spline-acc,
-//                              base-motion (warp = group of consecutive nodes x tile)
+//   DynOut        XT        -> CSR values + constraint values of the dynamic constraint (warp = sample x tile)
+//   RomNodeOut    XT        -> CSR values + constraint values of the range-of-motion constraints (warp = sample x
+//                              tile, all feet) and of the node-wise sets: terrain, force, swing, spline-acc,
+//                              base-motion (warp = group of consecutive nodes x tile); the CTAs of a tile in row order
+//   TransposeOut  GT[tile][m][32] -> g[B][m]       (the constraint values are staged instance-tiled)
+//   PhaseJac      (optimised phase durations only) per-instance entries of the PhaseSpline columns
 //   CostKernel    XT        -> cost + gradient (only when the formulation has cost terms)
 //
-// In the *Out kernels a warp owns one unit of 32 instances: each lane evaluates the splines its unit
-// needs (reference operation order), computes its instance's unit state into a padded shared-memory
-// block (row = state slot, column = lane), the warp synchronises, and then the lanes switch roles —
-// lane = 16-byte pair of output elements — and stream
+// In the output kernels a warp owns one unit of 32 instances: each lane evaluates the splines its unit needs
+// (reference operation order) and computes its instance's unit state into a padded shared-memory block (row =
+// state slot, column = lane).  After the CTA barrier ALL threads of the CTA switch roles — thread = 16-byte pair
+// of output elements — and stream
 //     out[instance][off + h] = state[d_h][instance] * c_h
-// for the 32 instances, so that every store instruction covers 512 contiguous bytes of one instance's
-// CSR value array (a unit's rows are consecutive CSR rows).  The state never leaves the SM; HBM sees x
-// once and g / jac exactly once.  The Out kernels are independent and run on separate streams.
+// for the 32 instances from ONE list that covers the CTA's consecutive units (adjacent CSR rows): every store
+// instruction covers 512 contiguous bytes of one instance's CSR value row, whole 32-byte sectors only.  The
+// state never leaves the SM; HBM sees x once and g / jac exactly once.  DynOut runs beside RomNodeOut on a
+// second stream.
 //
 // Reference math restated per device function (file:line cited there).  This translation unit is
 // compiled with -fmad=false: plain * and + round like the reference's scalar C++; fused
@@ -950,7 +953,7 @@ __global__ void __launch_bounds__(kNodeWarps * 32, TWB_NODE_CTAS) NodeOut(const 
   extern __shared__ __align__(16) double out_smem[];
   NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x, blockIdx.y);
 }
-#if TWB_ROMNODE   // experiment: range-of-motion and node CTAs of a tile in one kernel (kRomWarps == kNodeWarps)
+#if TWB_ROMNODE   // range-of-motion and node CTAs of a tile in one kernel (kRomWarps == kNodeWarps), in row order
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                                double* __restrict__ jac, int* __restrict__ status,
