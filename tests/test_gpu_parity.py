@@ -195,3 +195,90 @@ def test_linearity_in_forces():
     for b in range(4):
         J = np.zeros((p.m, p.n)); J[iRow, jCol] = g0["jac"][b]
         assert np.allclose((J @ d[b])[r0:r0 + nr], rhs[b], rtol=0, atol=1e-9)
+
+
+def _device_eval(p, bt, X, terrains=None):
+    """Device-resident evaluation (no 10+ GB host copies): returns torch tensors g, jac, status."""
+    import torch
+    B = X.shape[0]
+    xd = torch.from_numpy(X).cuda()
+    g = torch.empty((B, p.m), dtype=torch.float64, device="cuda")
+    jac = torch.empty((B, p.nnz), dtype=torch.float64, device="cuda")
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    bt.eval_device(xd, g=g, jac=jac, status=st)
+    torch.cuda.synchronize()
+    return g, jac, st
+
+
+def test_full_size_properties_config3_biped_16384():
+    """BASELINE configs[2] at full size: determinism, instance independence, oracle parity on a seeded subsample
+    (odd nnz: four alignment classes of the output rows)."""
+    f = tb.make_formulation("biped_walk_stairs"); spec = f.to_spec(); p = tb.Problem(spec)
+    B = 16384
+    X = synthetic_iterates_fast(p, B)
+    bt = p.batch(B)
+    g1, j1, s1 = _device_eval(p, bt, X)
+    g2, j2, s2 = _device_eval(p, bt, X)
+    assert bool((j1 == j2).all()) and bool((g1 == g2).all()) and int(s1.sum()) == 0
+    perm = np.random.default_rng(3).permutation(B)
+    g3, j3, _ = _device_eval(p, bt, X[perm])
+    import torch
+    pt = torch.from_numpy(perm).cuda()
+    assert bool((j3 == j1[pt]).all()) and bool((g3 == g1[pt]).all())
+    idx = np.sort(np.random.default_rng(5).choice(B, 40, replace=False))
+    ref = oracle_lib.batch_eval(spec, X[idx])
+    it = torch.from_numpy(idx).cuda()
+    assert check_rows(j1[it].cpu().numpy(), ref["jac"], p.row_ptr())[0] == 0
+    assert check_sets(g1[it].cpu().numpy(), ref["g"], p.constraint_sets())[0] == 0
+
+
+def test_full_size_properties_config4_hyq_32768():
+    """BASELINE configs[3] at full size (14 GB of Jacobian values, device-resident): determinism, oracle parity on a
+    seeded subsample, total-duration rows = sum of the duration variables, no status flags."""
+    import torch
+    f = tb.make_formulation("hyq_gallop_gap"); spec = f.to_spec(); p = tb.Problem(spec)
+    B = 32768
+    X = synthetic_iterates_fast(p, B)
+    bt = p.batch(B)
+    g1, j1, s1 = _device_eval(p, bt, X)
+    assert int(s1.sum()) == 0
+    chk1 = (float(j1.sum()), float(g1.sum()), float(j1.abs().max()))
+    g1c = g1.clone(); del g1
+    idx = np.sort(np.random.default_rng(9).choice(B, 24, replace=False))
+    it = torch.from_numpy(idx).cuda()
+    jsub, gsub = j1[it].cpu().numpy(), g1c[it].cpu().numpy()
+    g2, j2, _ = _device_eval(p, bt, X)                 # same buffers' worth of work again
+    assert chk1 == (float(j2.sum()), float(g2.sum()), float(j2.abs().max()))
+    ref = oracle_lib.batch_eval(spec, X[idx])
+    assert ref["rc"] == 0
+    assert check_rows(jsub, ref["jac"], p.row_ptr())[0] == 0
+    assert check_sets(gsub, ref["g"], p.constraint_sets())[0] == 0
+    sets = dict((nm, (s, k)) for nm, s, k in p.variable_sets())
+    for ee in range(4):
+        (_, r0, _), = [c for c in p.constraint_sets() if c[0] == f"totalduration-{ee}"]
+        s, k = sets[f"ee-schedule{ee}"]
+        assert np.allclose(g1c[:, r0].cpu().numpy(), X[:, s:s + k].sum(axis=1), rtol=1e-15, atol=0)
+
+
+def test_full_size_properties_config5_shard_mixed_terrains():
+    """BASELINE configs[4]: one GPU's shard (65536 / 8 instances) with terrains drawn per instance."""
+    import torch
+    f = tb.make_formulation("anymal_trot_mixed"); spec = f.to_spec(); p = tb.Problem(spec)
+    B = 65536 // 8
+    X = synthetic_iterates_fast(p, B, seed=77)
+    terr = np.random.default_rng(7).choice([tb.SLOPE, tb.CHIMNEY, tb.GAP], B).astype(np.int32)
+    bt = p.batch(B); bt.set_terrains(terr)
+    g1, j1, s1 = _device_eval(p, bt, X)
+    assert int(s1.sum()) == 0
+    idx = np.sort(np.random.default_rng(13).choice(B, 48, replace=False))
+    ref = oracle_lib.batch_eval(spec, X[idx], terrain_ids=terr[idx])
+    it = torch.from_numpy(idx).cuda()
+    assert check_rows(j1[it].cpu().numpy(), ref["jac"], p.row_ptr())[0] == 0
+    assert check_sets(g1[it].cpu().numpy(), ref["g"], p.constraint_sets())[0] == 0
+    # the terrain only enters the terrain / force rows: everything else equals the single-terrain evaluation
+    bt2 = p.batch(B)
+    g0, j0, _ = _device_eval(p, bt2, X)
+    rp = p.row_ptr()
+    for name, r0, nr in p.constraint_sets():
+        if not name.startswith(("terrain", "force")):
+            assert bool((j1[:, rp[r0]:rp[r0 + nr]] == j0[:, rp[r0]:rp[r0 + nr]]).all()), name
