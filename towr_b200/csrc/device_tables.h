@@ -127,7 +127,7 @@ struct BaseMotionUnit { int32_t sample_lin, sample_ang; };
 
 // A dynamic sample (6 rows): 2 + 2 n_ee spline samples starting at `sample0`
 // (base-lin, base-ang, ee-motion.., ee-force..) and its output lists.
-struct DynUnit { int32_t sample0; int32_t pad; OutRange values; };
+struct DynUnit { int32_t sample0; int32_t g_row0; OutRange values; };   // g_row0: first of the sample's 6 constraint rows
 // A range-of-motion sample (3 rows for every foot): 2 + n_ee spline samples (base-lin, base-ang, ee-motion..);
 // the feet are evaluated and written one after the other (values[foot]: the foot's constraint values).
 struct RomUnit { int32_t sample0; int32_t pad; OutRange values[kMaxEE]; };

@@ -186,6 +186,7 @@ struct Emit { int row, col; uint32_t a; double c0; };   // a: local state row of
 // Who computes a constraint row: a dynamic sample, a range-of-motion sample (all feet) or a node unit.
 enum OwnerKind { kOwnDyn, kOwnRom, kOwnNode, kOwnPhase };   // kOwnPhase: rows written by the PhaseJac kernel (total duration)
 struct RowOwner { int kind = -1, index = -1; uint32_t g_local = 0; };   // g_local: state row of the row's value inside the unit
+constexpr uint32_t kDirectValue = 0xFFFFFFFFu;   // the unit writes this row's value straight into GT (no state row)
 // node unit before grouping: kind, index into its table, rows of local state / values it needs
 struct NodeUnitRef { int kind, index, n_state, n_g, set_id; };
 
@@ -369,14 +370,14 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         std::vector<double> ts = SampleTimes(T, sp.dt_constraint_dynamic);
         int r0 = add_set("dynamic", (int)ts.size() * 6);
         pl.n_dyn = (int)ts.size();
-        const uint32_t G0 = 40 + 6 * n_ee;   // local state: [0]=1 | sum f (3) | base-ang block (36) | f_e, c-p_e (6 per foot) | g (6)
+        // local state: [0]=1 | sum f (3) | base-ang block (36) | f_e, c-p_e (6 per foot); the 6 constraint values go straight to GT
         for (int k = 0; k < pl.n_dyn; ++k) {
           const double t = ts[k];
           const int row = r0 + 6 * k;
           const uint32_t sb = 1;
-          DynUnit du{}; du.sample0 = (int32_t)tb.samples.size();
+          DynUnit du{}; du.sample0 = (int32_t)tb.samples.size(); du.g_row0 = row;
           tb.dyn.push_back(du);
-          for (int r = 0; r < 6; ++r) { bound(row + r, 0.0, 0.0); own(row + r, kOwnDyn, k, G0 + r); }
+          for (int r = 0; r < 6; ++r) { bound(row + r, 0.0, 0.0); own(row + r, kOwnDyn, k, kDirectValue); }
           // spline samples: base-lin, base-ang, ee-motion.., ee-force..
           tb.samples.push_back(MakeSample(sp_lin, t, zero_slot));
           tb.samples.push_back(MakeSample(sp_ang, t, zero_slot));
@@ -677,7 +678,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   const int n_dyn_ctas = (pl.n_dyn + kDynWarps - 1) / kDynWarps, n_rom_ctas = (pl.n_rom + kRomWarps - 1) / kRomWarps;
   const int n_node_ctas = ((int)groups.size() + kNodeWarps - 1) / kNodeWarps;
   const int n_lists = n_dyn_ctas + n_rom_ctas * n_ee + n_node_ctas;   // dynamic CTAs | (rom CTA, foot) | node CTAs
-  pl.dyn_rows = 46 + 6 * n_ee; pl.rom_rows = kRomBlockRows;
+  pl.dyn_rows = 40 + 6 * n_ee; pl.rom_rows = kRomBlockRows;
   std::vector<int> list_of(n_blocks, -1), row_base(n_blocks, 0);   // list a block's elements belong to; first row of the block inside its CTA
   for (int k = 0; k < pl.n_dyn; ++k) { list_of[k] = k / kDynWarps; row_base[k] = (k % kDynWarps) * pl.dyn_rows; }
   for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) {
@@ -698,7 +699,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     uint32_t g_row = o.g_local, state0 = 1;
     if (o.kind == kOwnNode) { g_row = unit_g0[o.index] + o.g_local; state0 = unit_state0[o.index]; }
     const int blk = block_id(o);
-    if (blk >= 0) values[blk].push_back({OutPair{r, (uint16_t)g_row, 0}, OutCoef{1.0, 0.0}});
+    if (blk >= 0 && o.g_local != kDirectValue) values[blk].push_back({OutPair{r, (uint16_t)g_row, 0}, OutCoef{1.0, 0.0}});
     for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) {
       uint32_t a = em[s].a;
       if (o.kind == kOwnNode && a != S_ONE) a = state0 + (a - 1);

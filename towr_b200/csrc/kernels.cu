@@ -636,16 +636,16 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kDynWarps + warp, b0 = tile * 32;
-  constexpr int G0 = 40 + 6 * kNEE, n_rows = G0 + 6;   // local rows: 1 | 3 | 36 | 6 per foot | g (6)
+  constexpr int n_rows = 40 + 6 * kNEE;   // local rows: 1 | 3 | 36 | 6 per foot; the 6 constraint values go straight into GT (coalesced)
   double* t = out_smem + (size_t)warp * n_rows * kLD;
   if (k < P.n_dyn) {
     const DynUnit* u = P.dyn + k;
     t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE   // (timing experiment: store phase only)
-    DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD}, Col{t + G0 * kLD + lane, kLD});
+    DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD},
+                              Col{GT + ((size_t)b0 * P.m + (size_t)__ldg(&u->g_row0) * 32) + lane, 32});
     FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
 #endif
-    if (flags & 1u) StoreValuesTiled(P, t, &u->values, GT + (size_t)b0 * P.m, lane);
   }
   __syncthreads();
   if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.dyn_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0));
@@ -972,7 +972,7 @@ template <int kNEE, bool kPhase>
 cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, int* status, const int* terrain_ids, int default_terrain,
                       int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
   const size_t row_bytes = (size_t)kLD * sizeof(double);
-  const int dyn_rows = 46 + 6 * kNEE, rom_rows = kRomBlockRows, node_rows = P.node_rows;
+  const int dyn_rows = 40 + 6 * kNEE, rom_rows = kRomBlockRows, node_rows = P.node_rows;
   cudaError_t e = cudaSuccess;
 #if TWB_FUSED
   const int n_ctas = (P.n_dyn + kWarps - 1) / kWarps + (P.n_rom + kWarps - 1) / kWarps + (P.n_groups + kWarps - 1) / kWarps;
