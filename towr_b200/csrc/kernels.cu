@@ -555,23 +555,48 @@ __device__ __forceinline__ void LoadPair(const OutPair* __restrict__ pairs, cons
 __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
                                            int n_pairs, double* __restrict__ out, size_t stride, int j0, int jstep, int n_inst,
                                            int tid, int n_threads) {
-  if (tid >= n_pairs) return;
-  int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
-  LoadPair(pairs, coefs, tid, n_pairs, &off, &d0, &d1, &c0, &c1);
-  for (int i = tid; i < n_pairs; i += n_threads) {
-    // prefetch the next entry of this thread under the stores of the current one
-    int noff = 0, nd0 = 0, nd1 = 0; double nc0 = 0.0, nc1 = 0.0;
-    LoadPair(pairs, coefs, i + n_threads, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
-    double* o = out + off;
-    const double* r0 = t + d0 * kLD; const double* r1 = t + d1 * kLD;
-    if (n_inst == 32 && jstep == 1) {
-      // rows are 16-byte aligned (kLD even): two instances per shared-memory load
-#pragma unroll 8
-      for (int j = 0; j < 32; j += 2) {
+  if (n_inst == 32 && jstep == 1) {
+    // Work items are (pair, half of the tile's instances): twice as many items as pairs keep the threads of a CTA
+    // evenly busy when a list is only 1 - 2 pairs per thread long.  Items 0 .. n_pairs-1 are the first 16 instances,
+    // n_pairs .. 2 n_pairs-1 the last 16, so consecutive threads still hold consecutive pairs (whole sectors).
+    const int n_items = 2 * n_pairs;
+    if (tid >= n_items) return;
+    int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
+    LoadPair(pairs, coefs, tid < n_pairs ? tid : tid - n_pairs, n_pairs, &off, &d0, &d1, &c0, &c1);
+    for (int i = tid; i < n_items; i += n_threads) {
+      // prefetch the next entry of this thread under the stores of the current one
+      int noff = 0, nd0 = 0, nd1 = 0; double nc0 = 0.0, nc1 = 0.0;
+      const int ni = i + n_threads;
+      if (ni < n_items) LoadPair(pairs, coefs, ni < n_pairs ? ni : ni - n_pairs, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
+      const int jb = i < n_pairs ? 0 : 16;
+      double* o = out + off + (size_t)jb * stride;
+      const double* r0 = t + d0 * kLD + jb; const double* r1 = t + d1 * kLD + jb;   // rows are 16-byte aligned (kLD even)
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
         const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
         StoreOut2(o, a.x * c0, b.x * c1); o += stride;
         StoreOut2(o, a.y * c0, b.y * c1); o += stride;
       }
+      off = noff; d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1;
+    }
+    return;
+  }
+  if (tid >= n_pairs) return;
+  int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
+  LoadPair(pairs, coefs, tid, n_pairs, &off, &d0, &d1, &c0, &c1);
+  for (int i = tid; i < n_pairs; i += n_threads) {
+    int noff = 0, nd0 = 0, nd1 = 0; double nc0 = 0.0, nc1 = 0.0;
+    LoadPair(pairs, coefs, i + n_threads, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
+    double* o = out + off;
+    const double* r0 = t + d0 * kLD; const double* r1 = t + d1 * kLD;
+    if (n_inst == 32 && jstep == 2) {   // rows of two alignment classes: every other instance
+      o += (size_t)j0 * stride;
+#pragma unroll 8
+      for (int j = 0; j < 32; j += 2) { StoreOut2(o, r0[j0 + j] * c0, r1[j0 + j] * c1); o += 2 * stride; }
+    } else if (n_inst == 32 && jstep == 4) {   // four alignment classes: every fourth instance
+      o += (size_t)j0 * stride;
+#pragma unroll 8
+      for (int j = 0; j < 32; j += 4) { StoreOut2(o, r0[j0 + j] * c0, r1[j0 + j] * c1); o += 4 * stride; }
     } else {
 #pragma unroll 4
       for (int j = j0; j < n_inst; j += jstep) StoreOut2(o + j * stride, r0[j] * c0, r1[j] * c1);
