@@ -98,6 +98,7 @@ __global__ void FillFromSmem(double* out, const PairDesc* __restrict__ descs, in
 // variant for isolating what slows the real store phase: `shift` doubles of misalignment (the first/last
 // `shift` elements of a segment are written as 8-byte singles, lane = instance), optional g-like side array
 // (3 doubles per segment and instance), and a sub-range of segments [seg_lo, seg_hi) of every row.
+__device__ int g_tile_mul = 1;   // tile order experiment: tile = (blockIdx.y * g_tile_mul) % gridDim.y
 __global__ void FillExp(double* out, double* gout, const PairDesc* __restrict__ descs, int row_len, int seg, int seg_lo, int seg_hi,
                         int warps, int rows, int shift, int g_len) {
   extern __shared__ __align__(16) double sm[];
@@ -107,7 +108,8 @@ __global__ void FillExp(double* out, double* gout, const PairDesc* __restrict__ 
   double* t = sm + (size_t)warp * rows * 34;
   for (int r = 0; r < rows; ++r) t[r * 34 + lane] = r + lane;
   __syncwarp();
-  double* base = out + (size_t)blockIdx.y * 32 * row_len;
+  const int tile = (int)(((long long)blockIdx.y * g_tile_mul) % gridDim.y);
+  double* base = out + (size_t)tile * 32 * row_len;
   const int pairs = seg / 2 - (shift ? 1 : 0);
   const PairDesc* dl = descs + (size_t)s * (seg / 2);
   for (int i = lane; i < pairs; i += 32) {
@@ -175,7 +177,7 @@ float TimeIt(F f, int reps = 10) {
 }
 
 int main(int argc, char** argv) {
-  const int B = 4096, row_len = 15096;   // config 2: nnz
+  const int B = argc > 1 ? atoi(argv[1]) : 4096, row_len = 15096;   // config 2: nnz
   const size_t n = (size_t)B * row_len;
   double* out; CK(cudaMalloc(&out, n * 8));
   const double gb = n * 8 / 1e9;
@@ -258,6 +260,16 @@ int main(int argc, char** argv) {
     run("middle 60% of every row, aligned", n_seg / 5, n_seg / 5 + (n_seg * 3) / 5, 0, false);
     run("middle 60% of every row, shift 1 + g", n_seg / 5, n_seg / 5 + (n_seg * 3) / 5, 1, true);
     run("first 25% of every row, aligned", 0, n_seg / 4, 0, false);
+    for (int mul : {37, 63, 127}) {
+      CK(cudaMemcpyToSymbol(g_tile_mul, &mul, sizeof(int)));
+      char label[96]; snprintf(label, sizeof label, "first 25%%, tile order x%d mod tiles", mul);
+      run(label, 0, n_seg / 4, 0, false);
+      snprintf(label, sizeof label, "all segments, tile order x%d mod tiles", mul);
+      run(label, 0, n_seg, 0, false);
+    }
+    { int one = 1; CK(cudaMemcpyToSymbol(g_tile_mul, &one, sizeof(int))); }
+    // grid transposed: segment-major (all tiles of one segment group first) instead of tile-major
+
     {   // three kernels on three streams, each covering its own column range (the current pipeline's shape)
       cudaStream_t st[3]; for (auto& x : st) cudaStreamCreate(&x);
       cudaEvent_t e0, e1[3]; cudaEventCreate(&e0); for (auto& x : e1) cudaEventCreate(&x);
