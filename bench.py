@@ -135,19 +135,19 @@ def host_threads():
 
 
 def cpu_arm(spec, problem, X, threads, target_seconds=12.0):
-    """Times the CPU restatement (oracle) on a bounded sample of the same iterates."""
+    """Times the CPU restatement (oracle) on a bounded sample of the same iterates: whole passes over the batch
+    (at most 4096 instances each) until ~target_seconds of CPU work have been done."""
     import oracle_lib
-    probe = min(len(X), max(threads, 8))
-    t0 = time.perf_counter(); oracle_lib.batch_eval(spec, X[:probe], threads=threads); t_probe = time.perf_counter() - t0
-    per_eval = t_probe / probe
-    sample = int(max(probe, min(len(X), target_seconds / max(per_eval, 1e-9))))
-    reps = int(max(1, min(64, round(target_seconds / max(per_eval * sample, 1e-9)))))   # small batches: repeat them
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    sample = min(len(X), 4096)
+    oracle_lib.batch_eval(spec, X[:min(sample, 4 * threads)], threads=threads)      # warm-up (thread pool, page faults)
+    done, t0 = 0, time.perf_counter()
+    while True:
         r = oracle_lib.batch_eval(spec, X[:sample], threads=threads)
         assert r["rc"] == 0
-    dt = time.perf_counter() - t0
-    return sample * reps / dt, sample * reps, dt
+        done += sample
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds or done >= 64 * sample:
+            return done / dt, done, dt
 
 
 def run_reference(args):
