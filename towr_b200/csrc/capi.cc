@@ -63,7 +63,7 @@ struct twb_problem {
 
 struct twb_batch {
   const twb_problem* prob = nullptr;
-  int B = 0, device = 0, n_sms = 148;
+  int B = 0, device = 0;
   size_t ld = 0;                  // instances padded to a multiple of 32 (whole tiles of XT)
   twb::Plan plan{};
   std::vector<void*> owned;       // device allocations of the tables
@@ -172,8 +172,6 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
   b->ld = ((size_t)batch_size + 31) & ~(size_t)31;
-  cudaDeviceGetAttribute(&b->n_sms, cudaDevAttrMultiProcessorCount, device);
-  b->plan.n_sms = b->n_sms;
   const size_t xt_bytes = (size_t)(b->plan.n + 1) * b->ld * sizeof(double);
   if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_XT), xt_bytes)) != cudaSuccess ||
       (e = cudaMemset(b->d_XT, 0, xt_bytes)) != cudaSuccess ||

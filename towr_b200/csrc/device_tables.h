@@ -70,9 +70,9 @@ constexpr int kMaxClasses = 4;
 struct OutPair { int32_t off; uint16_t d0, d1; };       // pair: element index of the first half; single / value entry: element index / g row, d0 = state row
 struct alignas(16) OutCoef { double c0, c1; };
 struct OutRange { int32_t first, count; };
-struct OutList {                        // [0][alignment class]
-  OutRange pairs[2][kMaxClasses];       // whole sectors, two pairs each
-  OutRange singles[2][kMaxClasses];     // single elements (lane = instance)
+struct OutList {                        // per alignment class
+  OutRange pairs[kMaxClasses];          // whole sectors, two pairs each
+  OutRange singles[kMaxClasses];        // single elements (lane = instance)
 };
 constexpr int kRomBlockRows = 34;       // [0]=1 | R^T (9) | 2 x { D_e (9) | g_e (3) }
 
@@ -149,7 +149,6 @@ struct CostEntry {
 
 struct Plan {
   int n, m, nnz, n_ee;
-  int n_sms;       // multiprocessors of the batch's device (persistent grids); set by twb_batch_create
   int n_dyn, n_rom, n_groups, n_cost;
   int node_rows, dyn_rows, rom_rows;   // state rows of one unit's block: node groups (largest), dynamic samples, range-of-motion samples
   int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz); nc_g = 1 (constraint values go through GT)

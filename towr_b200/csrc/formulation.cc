@@ -732,7 +732,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   auto flush_list = [&](int list) {
     OutList out{};
     for (int q = 0; q < NC; ++q) {
-      OutRange* dst[2] = {&out.pairs[0][q], &out.singles[0][q]};
+      OutRange* dst[2] = {&out.pairs[q], &out.singles[q]};
       for (int w = 0; w < 2; ++w) {
         const auto& v = lists[list][q][w];
         dst[w]->first = (int32_t)tb.pairs.size(); dst[w]->count = (int32_t)v.size();

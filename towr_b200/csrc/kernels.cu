@@ -635,10 +635,10 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
 #endif
   const int nc = P.nc_jac, lane = threadIdx.x & 31;
   for (int q = 0; q < nc; ++q) {
-    const OutRange rp = LoadRange(&list->pairs[0][q]);
+    const OutRange rp = LoadRange(&list->pairs[q]);
     StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, threadIdx.x, blockDim.x);
     if (threadIdx.x < 32) {
-      const OutRange rs = LoadRange(&list->singles[0][q]);
+      const OutRange rs = LoadRange(&list->singles[q]);
       const bool active = lane < n_inst && (lane % nc) == q;
       double* o = jac_tile + (size_t)lane * P.nnz;
       ForEachEntry(P.pairs + rs.first, P.coefs + rs.first, rs.count, lane,
