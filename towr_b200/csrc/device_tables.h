@@ -74,7 +74,14 @@ struct OutList {                        // per alignment class
   OutRange pairs[kMaxClasses];          // whole sectors, two pairs each
   OutRange singles[kMaxClasses];        // single elements (lane = instance)
 };
-constexpr int kRomBlockRows = 34;       // [0]=1 | R^T (9) | 2 x { D_e (9) | g_e (3) }
+// Range-of-motion state block: [0]=1 | R^T (9) | buffers of { D_e (9) | g_e (3) }.  TWB_ROM_ALLFEET = 0: two buffers
+// used by the feet in turn (one CTA barrier and one list per foot); 1: one buffer per foot (one barrier, one list).
+#ifndef TWB_ROM_ALLFEET
+#define TWB_ROM_ALLFEET 0
+#endif
+#define RomBuffer(e) (TWB_ROM_ALLFEET ? 12 * (e) : 12 * ((e) & 1))            /* first row of foot e's buffer, relative to row 10 */
+#define RomBlockRows(n_ee) (10 + 12 * (TWB_ROM_ALLFEET ? (n_ee) : 2))
+#define RomListsPerCta(n_ee) (TWB_ROM_ALLFEET ? 1 : (n_ee))
 
 // warps per CTA of the output kernels = consecutive units whose output ranges are chained through carry rows.
 // TWB_FUSED = 1: one kernel (EvalOut) serves all three unit kinds with CTAs of TWB_WARPS warps.

@@ -463,7 +463,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
           for (int k = 0; k < pl.n_rom; ++k) {
             const double t = ts[k]; const int row = r0 + 3 * k;
-            const uint32_t sb = 1, sd = 10 + 12 * (e & 1), G0 = 19 + 12 * (e & 1);
+            const uint32_t sb = 1, sd = 10 + RomBuffer(e), G0 = 19 + RomBuffer(e);
             for (int d = 0; d < 3; ++d) {
               bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
               own(row + d, kOwnRom, k * n_ee + e, G0 + d);
@@ -677,17 +677,18 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   };
   const int n_dyn_ctas = (pl.n_dyn + kDynWarps - 1) / kDynWarps, n_rom_ctas = (pl.n_rom + kRomWarps - 1) / kRomWarps;
   const int n_node_ctas = ((int)groups.size() + kNodeWarps - 1) / kNodeWarps;
-  const int n_lists = n_dyn_ctas + n_rom_ctas * n_ee + n_node_ctas;   // dynamic CTAs | (rom CTA, foot) | node CTAs
-  pl.dyn_rows = 40 + 6 * n_ee; pl.rom_rows = kRomBlockRows;
+  const int rom_lists = RomListsPerCta(n_ee);
+  const int n_lists = n_dyn_ctas + n_rom_ctas * rom_lists + n_node_ctas;   // dynamic CTAs | (rom CTA[, foot]) | node CTAs
+  pl.dyn_rows = 40 + 6 * n_ee; pl.rom_rows = RomBlockRows(n_ee);
   std::vector<int> list_of(n_blocks, -1), row_base(n_blocks, 0);   // list a block's elements belong to; first row of the block inside its CTA
   for (int k = 0; k < pl.n_dyn; ++k) { list_of[k] = k / kDynWarps; row_base[k] = (k % kDynWarps) * pl.dyn_rows; }
   for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) {
     const int b = pl.n_dyn + k * n_ee + e;
-    list_of[b] = n_dyn_ctas + (k / kRomWarps) * n_ee + e; row_base[b] = (k % kRomWarps) * pl.rom_rows;
+    list_of[b] = n_dyn_ctas + (k / kRomWarps) * rom_lists + (rom_lists > 1 ? e : 0); row_base[b] = (k % kRomWarps) * pl.rom_rows;
   }
   for (int gi = 0; gi < (int)groups.size(); ++gi) {
     const int b = pl.n_dyn + n_rom_blocks + gi;
-    list_of[b] = n_dyn_ctas + n_rom_ctas * n_ee + gi / kNodeWarps; row_base[b] = (gi % kNodeWarps) * pl.node_rows;
+    list_of[b] = n_dyn_ctas + n_rom_ctas * rom_lists + gi / kNodeWarps; row_base[b] = (gi % kNodeWarps) * pl.node_rows;
   }
   struct Elem { int list; uint16_t d; double c; };
   std::vector<Elem> elems(nnz);
@@ -754,7 +755,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     ng.values = flush_values(pl.n_dyn + n_rom_blocks + (int)gi);
     tb.groups.push_back(ng);
   }
-  pl.dyn_list0 = 0; pl.rom_list0 = n_dyn_ctas; pl.node_list0 = n_dyn_ctas + n_rom_ctas * n_ee;
+  pl.dyn_list0 = 0; pl.rom_list0 = n_dyn_ctas; pl.node_list0 = n_dyn_ctas + n_rom_ctas * rom_lists;
 
   // ---- costs (nlp_formulation.cc:333-376, node_cost.cc:53-76)
   has_cost = false;

@@ -688,7 +688,8 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kRomWarps + warp, b0 = tile * 32;
   const bool valid = k < P.n_rom;
-  double* t = out_smem + (size_t)warp * kRomBlockRows * kLD;
+  constexpr int block_rows = RomBlockRows(kNEE);
+  double* t = out_smem + (size_t)warp * block_rows * kLD;
   const RomUnit* u = P.rom + (valid ? k : 0);
   const SplineSample* __restrict__ sp = P.samples + __ldg(&u->sample0);
   const ConstCol xs = TiledCol(XT, b0 + lane, P.n + 1);
@@ -710,7 +711,7 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
 #endif
 #pragma unroll 1
   for (int e = 0; e < kNEE; ++e) {
-    const int buf = 12 * (e & 1);
+    const int buf = RomBuffer(e);
 #ifndef TWB_EXP_NOCOMPUTE
     double pe[3];
     EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
@@ -728,9 +729,15 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
     }
 #endif
     if (valid && (flags & 1u)) StoreValuesTiled(P, t, &u->values[e], GT + (size_t)b0 * P.m, lane);
+#if !TWB_ROM_ALLFEET
     __syncthreads();   // foot e complete in every block; everybody is done reading buffer (e + 1) & 1 (the list of foot e - 1)
     if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst);
+#endif
   }
+#if TWB_ROM_ALLFEET
+  __syncthreads();
+  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta, jac_tile, n_inst);
+#endif
 }
 
 // node groups: blockIdx.y = instance tile, warp = one of kNodeWarps consecutive groups
@@ -997,7 +1004,7 @@ template <int kNEE, bool kPhase>
 cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, int* status, const int* terrain_ids, int default_terrain,
                       int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
   const size_t row_bytes = (size_t)kLD * sizeof(double);
-  const int dyn_rows = 40 + 6 * kNEE, rom_rows = kRomBlockRows, node_rows = P.node_rows;
+  const int dyn_rows = 40 + 6 * kNEE, rom_rows = RomBlockRows(kNEE), node_rows = P.node_rows;
   cudaError_t e = cudaSuccess;
 #if TWB_FUSED
   const int n_ctas = (P.n_dyn + kWarps - 1) / kWarps + (P.n_rom + kWarps - 1) / kWarps + (P.n_groups + kWarps - 1) / kWarps;
