@@ -48,7 +48,11 @@ enum { TWB_MONOPED = 0, TWB_BIPED = 1, TWB_HYQ = 2, TWB_ANYMAL = 3, TWB_GO1 = 4 
 
 /* towr::HeightMap::TerrainID, towr/include/towr/terrain/height_map.h:79-86 */
 enum { TWB_FLAT = 0, TWB_BLOCK = 1, TWB_STAIRS = 2, TWB_GAP = 3, TWB_SLOPE = 4,
-       TWB_CHIMNEY = 5, TWB_CHIMNEY_LR = 6, TWB_TERRAIN_COUNT = 7 };
+       TWB_CHIMNEY = 5, TWB_CHIMNEY_LR = 6, TWB_TERRAIN_COUNT = 7,
+       /* towr::HeightMapFromCSV (towr/include/towr/terrain/height_map_from_csv.h:29-111): a cell-constant height grid
+        * with one-sided edge slopes; the grid is per-batch data (twb_batch_set_grid_terrain), usable as a per-instance
+        * terrain id in twb_batch_set_terrains but not as twb_spec.terrain */
+       TWB_GRID_CSV = 7 };
 
 /* towr::Parameters::ConstraintName, towr/include/towr/parameters.h:139-147 */
 enum { TWB_C_DYNAMIC = 0, TWB_C_EE_ROM = 1, TWB_C_TOTAL_TIME = 2, TWB_C_TERRAIN = 3,
@@ -160,6 +164,10 @@ void twb_batch_destroy(twb_batch* b);
 /* Per-instance terrain ids (host array of batch_size ints). The structure does
  * not depend on the terrain, so one batch may mix terrains. */
 int twb_batch_set_terrains(twb_batch* b, const int* terrain_ids);
+
+/* The height grid of TWB_GRID_CSV for this batch: heights[y_cell * cols + x_cell] in metres, cells of 0.17 m
+ * (HeightMapFromCSV::res_m_p_cell_), uploaded to the device.  NULL removes it (every height is then 0). */
+int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, int cols);
 
 #define TWB_EVAL_G 1u     /* constraint values        (Problem::EvaluateConstraints)       */
 #define TWB_EVAL_JAC 2u   /* Jacobian values          (Problem::EvalNonzerosOfJacobian)    */

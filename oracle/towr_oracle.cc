@@ -184,6 +184,51 @@ V3 m3_mulvec(const M3& m, const V3& v) {
 // Terrains — towr/src/height_map.cc:52-163, height_map_examples.cc:35-211,
 // constants towr/include/towr/terrain/examples/height_map_examples.h:45-166
 // ---------------------------------------------------------------------------
+// towr::HeightMapFromCSV (towr/include/towr/terrain/height_map_from_csv.h:29-111): the grid the reference reads from
+// a CSV file is process-global test data here (oracle_set_grid); grid_(y_cell, x_cell), row-major.
+struct CsvGrid {
+  std::vector<double> h; int rows = 0, cols = 0;
+  const double res = 0.17;        // res_m_p_cell_, :113
+  const double eps = 0.17 / 50;   // eps_, :114
+  // static_cast<size_t>(x / res) of a negative x is a huge cell index in practice: "outside the grid"
+  bool Cell(double x, double y, long long* xc, long long* yc) const {
+    double fx = x / res, fy = y / res;
+    if (!(fx >= 0.0) || !(fy >= 0.0)) return false;
+    *xc = (long long)fx; *yc = (long long)fy;
+    return *xc < cols && *yc < rows;      // isCellValid, :47-49
+  }
+  double At(long long yc, long long xc) const { return h[(size_t)yc * cols + xc]; }
+  double Height(double x, double y) const {  // :29-37
+    long long xc, yc; if (!Cell(x, y, &xc, &yc)) return 0.0;
+    return At(yc, xc);
+  }
+  double Hx(double x, double y) const {  // :40-74
+    long long xc, yc; if (!Cell(x, y, &xc, &yc)) return 0.0;
+    if (xc + 1 < cols) {
+      double diff_end = At(yc, xc + 1) - At(yc, xc), x_end = (xc + 1) * res;
+      if ((diff_end > 0) && (x <= x_end) && (x >= x_end - eps)) return diff_end / eps;
+    }
+    if (xc - 1 >= 0) {
+      double diff_start = At(yc, xc) - At(yc, xc - 1), x_start = xc * res;
+      if ((diff_start < 0) && (x >= x_start) && (x <= x_start + eps)) return diff_start / eps;
+    }
+    return 0.0;
+  }
+  double Hy(double x, double y) const {  // :77-111
+    long long xc, yc; if (!Cell(x, y, &xc, &yc)) return 0.0;
+    if (yc + 1 < rows) {
+      double diff_end = At(yc + 1, xc) - At(yc, xc), y_end = (yc + 1) * res;
+      if ((diff_end > 0) && (y <= y_end) && (y >= y_end - eps)) return diff_end / eps;
+    }
+    if (yc - 1 >= 0) {
+      double diff_start = At(yc, xc) - At(yc - 1, xc), y_start = yc * res;
+      if ((diff_start < 0) && (y >= y_start) && (y <= y_start + eps)) return diff_start / eps;
+    }
+    return 0.0;
+  }
+};
+CsvGrid g_grid;
+
 struct Terrain {
   int id = TWB_FLAT;
   double flat_height = 0.0;
@@ -191,6 +236,7 @@ struct Terrain {
 
   double Height(double x, double y) const {
     switch (id) {
+      case TWB_GRID_CSV: return g_grid.Height(x, y);
       case TWB_FLAT: return flat_height;
       case TWB_BLOCK: {  // height_map_examples.cc:40-53
         const double block_start = 0.7, length = 3.5, height = 0.5, eps = 0.03; const double slope = height / eps;
@@ -229,8 +275,9 @@ struct Terrain {
     }
     return 0.0;
   }
-  double Hx(double x, double) const {
+  double Hx(double x, double y) const {
     switch (id) {
+      case TWB_GRID_CSV: return g_grid.Hx(x, y);
       case TWB_BLOCK: { const double block_start = 0.7, height = 0.5, eps = 0.03; const double slope = height / eps;
         double d = 0.0; if (block_start <= x && x <= block_start + eps) d = slope; return d; }  // :55-65
       case TWB_GAP: { GapC g; double d = 0.0; if (g.gap_start <= x && x <= g.gap_end_x) d = 2 * g.a * x + g.b; return d; }  // :100-109
@@ -242,8 +289,9 @@ struct Terrain {
       default: return 0.0;
     }
   }
-  double Hy(double x, double) const {
+  double Hy(double x, double y) const {
     switch (id) {
+      case TWB_GRID_CSV: return g_grid.Hy(x, y);
       case TWB_CHIMNEY: { const double x_start = 1.0, length = 1.5, slope = 3.0; const double x_end = x_start + length;
         double d = 0.0; if (x_start <= x && x <= x_end) d = slope; return d; }  // :172-181
       case TWB_CHIMNEY_LR: { const double x_start = 0.5, length = 1.0, slope = 2; const double x_end1 = x_start + length, x_end2 = x_start + 2 * length;
@@ -1445,6 +1493,13 @@ int oracle_eval(void* h, const double* x, double* g, double* vals, double* cost,
   return static_cast<Problem*>(h)->Eval(x, g, vals, cost, grad);
 }
 double oracle_terrain_height(int terrain, double x, double y) { Terrain t; t.id = terrain; return t.Height(x, y); }
+// grid of the TWB_GRID_CSV terrain (process-global; set before evaluating)
+void oracle_set_grid(const double* heights, int rows, int cols) {
+  g_grid.h.assign(heights, heights + (size_t)rows * cols); g_grid.rows = rows; g_grid.cols = cols;
+}
+void oracle_terrain_point(int terrain, double x, double y, double* out3) {
+  Terrain t; t.id = terrain; out3[0] = t.Height(x, y); out3[1] = t.DerivOfHeightWrt(0, x, y); out3[2] = t.DerivOfHeightWrt(1, x, y);
+}
 
 // Batched evaluation over independent instances (CPU baseline): one Problem
 // clone per thread (the reference's objects are mutable and not re-entrant).

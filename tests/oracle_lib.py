@@ -27,7 +27,8 @@ def lib():
         _lib.oracle_create.restype = C.c_void_p
         _lib.oracle_create.argtypes = [C.c_void_p]
         _lib.oracle_destroy.argtypes = [C.c_void_p]
-        for fn in ("oracle_dims", "oracle_structure", "oracle_bounds", "oracle_x0", "oracle_set_terrain"):
+        for fn in ("oracle_dims", "oracle_structure", "oracle_bounds", "oracle_x0", "oracle_set_terrain", "oracle_set_grid",
+                   "oracle_terrain_point"):
             getattr(_lib, fn).restype = None
         _lib.oracle_eval.restype = C.c_int
         _lib.oracle_batch_eval.restype = C.c_int
@@ -109,6 +110,18 @@ def batch_eval(spec, X, terrain_ids=None, want_cost=False, threads=0, want_jac=T
     t = None if terrain_ids is None else np.ascontiguousarray(terrain_ids, np.int32)
     rc = lib().oracle_batch_eval(C.byref(spec), B, _p(t), _p(X), _p(g), _p(vals), _p(cost), _p(grad), int(threads))
     return dict(rc=rc, g=g, jac=vals, cost=cost, grad=grad)
+
+
+def set_grid(heights):
+    """Height grid of the GRID_CSV terrain (process-global in the oracle)."""
+    h = np.ascontiguousarray(heights, np.float64)
+    lib().oracle_set_grid(_p(h), C.c_int(h.shape[0]), C.c_int(h.shape[1]))
+
+
+def terrain_point(terrain, x, y):
+    out = np.empty(3)
+    lib().oracle_terrain_point(C.c_int(int(terrain)), C.c_double(x), C.c_double(y), _p(out))
+    return out
 
 
 def max_threads():

@@ -282,3 +282,35 @@ def test_full_size_properties_config5_shard_mixed_terrains():
     for name, r0, nr in p.constraint_sets():
         if not name.startswith(("terrain", "force")):
             assert bool((j1[:, rp[r0]:rp[r0 + nr]] == j0[:, rp[r0]:rp[r0 + nr]]).all()), name
+
+
+def test_csv_grid_terrain():
+    """towr::HeightMapFromCSV as per-batch terrain data (TWB_GRID_CSV), mixed with analytic terrains per instance."""
+    rng = np.random.default_rng(21)
+    grid = rng.integers(0, 4, (12, 20)) * 0.04
+    B = 45
+    terr = np.where(np.arange(B) % 3 == 2, tb.BLOCK, tb.GRID_CSV).astype(np.int32)
+    f = tb.make_formulation("anymal_trot_block"); spec = f.to_spec(); p = tb.Problem(spec)
+    X = synthetic_iterates(p, B)
+    # put some feet right into the edge bands of the grid (one-sided slopes)
+    for name, s, k in p.variable_sets():
+        if name == "ee-motion_0":
+            X[0:8, s] = np.arange(1, 9) * 0.17 - 0.001
+            X[8:16, s] = np.arange(1, 9) * 0.17 + 0.001
+    bt = p.batch(B); bt.set_terrains(terr); bt.set_grid_terrain(grid)
+    out = bt.eval_host(X)
+    oracle_lib.set_grid(grid)
+    ref = oracle_lib.batch_eval(spec, X, terrain_ids=terr)
+    assert ref["rc"] == 0
+    assert check_rows(out["jac"], ref["jac"], p.row_ptr())[0] == 0
+    assert check_sets(out["g"], ref["g"], p.constraint_sets())[0] == 0
+    assert not out["status"].any()
+    rp = p.row_ptr()
+    (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == "terrain-ee-motion_0"]
+    blk = out["jac"][:16, rp[r0]:rp[r0 + nr]]
+    assert np.abs(blk).max() > 1.5               # an edge slope (0.04 / (0.17 / 50) = 11.8) showed up in the terrain rows
+    bt.set_grid_terrain(None)                    # without a grid every height is 0
+    flat = bt.eval_host(X)
+    oracle_lib.set_grid(np.zeros((1, 1)))
+    ref0 = oracle_lib.batch_eval(spec, X, terrain_ids=terr)
+    assert check_sets(flat["g"], ref0["g"], p.constraint_sets())[0] == 0

@@ -129,3 +129,42 @@ def test_golden_fixtures():
             r = o.eval(X[b])
             assert np.allclose(r["g"], z[f"{name}_g"][b], rtol=1e-13, atol=1e-13)
             assert np.allclose(r["jac"], z[f"{name}_jac"][b], rtol=1e-13, atol=1e-13)
+
+
+def _csv_grid_reference(grid, x, y):
+    """Independent restatement of towr::HeightMapFromCSV (height_map_from_csv.h:29-111) in plain Python."""
+    res, eps = 0.17, 0.17 / 50
+    rows, cols = grid.shape
+    if x / res < 0 or y / res < 0:
+        return 0.0, 0.0, 0.0
+    xc, yc = int(x / res), int(y / res)
+    if xc >= cols or yc >= rows:
+        return 0.0, 0.0, 0.0
+    def slope(c, n, at, coord):
+        if c + 1 < n:
+            d = at(c + 1) - at(c); end = (c + 1) * res
+            if d > 0 and end - eps <= coord <= end:
+                return d / eps
+        if c - 1 >= 0:
+            d = at(c) - at(c - 1); start = c * res
+            if d < 0 and start <= coord <= start + eps:
+                return d / eps
+        return 0.0
+    return (grid[yc, xc], slope(xc, cols, lambda k: grid[yc, k], x), slope(yc, rows, lambda k: grid[k, xc], y))
+
+
+def test_csv_grid_terrain_of_the_oracle():
+    rng = np.random.default_rng(4)
+    grid = rng.integers(0, 4, (9, 14)) * 0.05
+    oracle_lib.set_grid(grid)
+    res, eps = 0.17, 0.17 / 50
+    pts = list(rng.uniform(-0.3, 2.6, (300, 2)))
+    for k in range(1, 12):                       # points inside the eps bands at the cell edges, both directions
+        pts += [(k * res - 0.4 * eps, 0.5), (k * res + 0.4 * eps, 0.5), (0.6, (k % 8 + 1) * res - 0.3 * eps), (0.6, (k % 8 + 1) * res + 0.3 * eps)]
+    hit = 0
+    for x, y in pts:
+        got = oracle_lib.terrain_point(tb.GRID_CSV, x, y)
+        want = _csv_grid_reference(grid, x, y)
+        assert tuple(got) == tuple(float(v) for v in want), (x, y, got, want)
+        hit += (want[1] != 0.0) or (want[2] != 0.0)
+    assert hit > 5                               # the edge-slope branches were exercised

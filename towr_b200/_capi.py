@@ -16,6 +16,7 @@ EVAL_G, EVAL_JAC, EVAL_COST, EVAL_ALL = 1, 2, 4, 7
 MONOPED, BIPED, HYQ, ANYMAL, GO1 = range(5)
 # towr::HeightMap::TerrainID (height_map.h:79-86)
 FLAT, BLOCK, STAIRS, GAP, SLOPE, CHIMNEY, CHIMNEY_LR = range(7)
+GRID_CSV = 7   # towr::HeightMapFromCSV; grid data per batch (Batch.set_grid_terrain)
 # towr::Parameters::ConstraintName (parameters.h:139-147)
 C_DYNAMIC, C_EE_ROM, C_TOTAL_TIME, C_TERRAIN, C_FORCE, C_SWING, C_BASE_ROM, C_BASE_ACC = range(8)
 # towr::Parameters::CostName
@@ -80,6 +81,7 @@ def _load():
         "twb_batch_create": (C.c_int, [P, C.c_int, C.c_int, C.POINTER(P)]),
         "twb_batch_destroy": (None, [P]),
         "twb_batch_set_terrains": (C.c_int, [P, I]),
+        "twb_batch_set_grid_terrain": (C.c_int, [P, D, C.c_int, C.c_int]),
         "twb_batch_eval_device": (C.c_int, [P, P, P, P, P, P, P, C.c_uint, P]),
         "twb_batch_eval_host": (C.c_int, [P, P, P, P, P, P, P, C.c_uint]),
         "twb_batch_launches_per_eval": (C.c_int, [P, C.c_uint]),

@@ -68,6 +68,7 @@ struct twb_batch {
   twb::Plan plan{};
   std::vector<void*> owned;       // device allocations of the tables
   int* d_terrain = nullptr;       // per-instance terrain ids (optional)
+  double* d_grid = nullptr;       // height grid of TWB_GRID_CSV (optional)
   double* d_XT = nullptr;         // [ld/32][n+1][32] instance-tiled iterates; row n == 0
   double* d_GT = nullptr;         // [ld/32][m][32] instance-tiled constraint values (staging of g)
   // staging for the host-pointer variant
@@ -199,7 +200,7 @@ void twb_batch_destroy(twb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   for (void* p : b->owned) cudaFree(p);
-  cudaFree(b->d_terrain); cudaFree(b->d_XT); cudaFree(b->d_GT);
+  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_XT); cudaFree(b->d_GT);
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
@@ -213,11 +214,26 @@ int twb_batch_set_terrains(twb_batch* b, const int* terrain_ids) {
   cudaSetDevice(b->device);
   if (!terrain_ids) { cudaFree(b->d_terrain); b->d_terrain = nullptr; return TWB_OK; }
   for (int i = 0; i < b->B; ++i)
-    if (terrain_ids[i] < 0 || terrain_ids[i] >= TWB_TERRAIN_COUNT) return Fail(TWB_ERR_INVALID, "unknown terrain id");
+    if (terrain_ids[i] < 0 || terrain_ids[i] > TWB_GRID_CSV) return Fail(TWB_ERR_INVALID, "unknown terrain id");
   cudaError_t e;
   if (!b->d_terrain && (e = cudaMalloc(&b->d_terrain, sizeof(int) * b->B)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
   if ((e = cudaMemcpy(b->d_terrain, terrain_ids, sizeof(int) * b->B, cudaMemcpyHostToDevice)) != cudaSuccess)
     return CudaFail(e, "cudaMemcpy");
+  return TWB_OK;
+}
+
+int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, int cols) {
+  if (!b) return Fail(TWB_ERR_INVALID, "null batch");
+  cudaSetDevice(b->device);
+  cudaFree(b->d_grid); b->d_grid = nullptr;
+  b->plan.grid = nullptr; b->plan.grid_rows = b->plan.grid_cols = 0;
+  if (!heights) return TWB_OK;
+  if (rows <= 0 || cols <= 0 || (long long)rows * cols > (1ll << 28)) return Fail(TWB_ERR_INVALID, "bad grid size");
+  cudaError_t e;
+  const size_t bytes = sizeof(double) * (size_t)rows * cols;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_grid), bytes)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(b->d_grid, heights, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return CudaFail(e, "cudaMemcpy");
+  b->plan.grid = b->d_grid; b->plan.grid_rows = rows; b->plan.grid_cols = cols;
   return TWB_OK;
 }
 

@@ -179,6 +179,9 @@ struct Plan {
   const OutPair* pairs;
   const OutCoef* coefs;
   const OutList* cta_lists;
+  // height grid of the TWB_GRID_CSV terrain (per batch; null: heights 0)
+  const double* grid;
+  int grid_rows, grid_cols;
   // phase-duration optimisation (all null / 0 otherwise)
   int n_phase_units, n_phase_defs;
   const PhaseSplineDef* phase_defs;   // [2 * n_ee]: ee-motion_e at 2e, ee-force_e at 2e + 1

@@ -354,9 +354,41 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSa
 
 // ---- analytic terrains: height_map_examples.cc:35-211 ------------------------
 struct TerrainPoint { double h, hx, hy, hxx; };
-__device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) {
+// HeightMapFromCSV (height_map_from_csv.h:29-111): cell-constant heights, cells of 0.17 m; slope diff/eps on the last
+// eps = res/50 before a rising edge and the first eps after a falling edge, 0 elsewhere; outside the grid everything is 0
+// (a negative coordinate converts to a huge size_t cell index in the reference, i.e. "outside").
+__device__ __forceinline__ bool GridCell(const Plan& P, double x, double y, long long* xc, long long* yc) {
+  const double res = 0.17;
+  const double fx = x / res, fy = y / res;
+  if (!(fx >= 0.0) || !(fy >= 0.0) || !P.grid) return false;
+  *xc = (long long)fx; *yc = (long long)fy;
+  return *xc < P.grid_cols && *yc < P.grid_rows;
+}
+__device__ __forceinline__ double GridEdgeSlope(const Plan& P, long long c, long long o, bool along_x, double coord) {
+  const double res = 0.17, eps = res / 50;
+  const long long n = along_x ? P.grid_cols : P.grid_rows;
+  auto at = [&](long long k) { return along_x ? __ldg(P.grid + o * P.grid_cols + k) : __ldg(P.grid + k * P.grid_cols + o); };
+  if (c + 1 < n) {   // next cell higher: slope just before it
+    const double diff_end = at(c + 1) - at(c), end = (double)(c + 1) * res;
+    if (diff_end > 0 && coord <= end && coord >= end - eps) return diff_end / eps;
+  }
+  if (c - 1 >= 0) {  // previous cell higher: slope just after it
+    const double diff_start = at(c) - at(c - 1), start = (double)c * res;
+    if (diff_start < 0 && coord >= start && coord <= start + eps) return diff_start / eps;
+  }
+  return 0.0;
+}
+__device__ __forceinline__ TerrainPoint EvalTerrain(const Plan& P, int id, double x, double y) {
   TerrainPoint o{0.0, 0.0, 0.0, 0.0};
   switch (id) {
+    case 7: {  // Grid (CSV)
+      long long xc, yc;
+      if (GridCell(P, x, y, &xc, &yc)) {
+        o.h = __ldg(P.grid + yc * P.grid_cols + xc);
+        o.hx = GridEdgeSlope(P, xc, yc, true, x);
+        o.hy = GridEdgeSlope(P, yc, xc, false, y);
+      }
+      break; }
     case 1: {  // Block
       const double start = 0.7, eps = 0.03, len = 3.5, height = 0.5; const double slope = height / eps;
       if (start <= x && x <= start + eps) { o.h = slope * (x - start); o.hx = slope; }
@@ -391,9 +423,9 @@ __device__ __forceinline__ TerrainPoint EvalTerrain(int id, double x, double y) 
 }
 
 // TerrainConstraint, terrain_constraint.cc:59-108.  Sk: {-dh/dx, -dh/dy}; gk: the constraint value
-__device__ __forceinline__ void TerrainUnitEval(const TerrainUnit& u, int terrain, const ConstCol xs, const Col Sk, const Col gk) {
+__device__ __forceinline__ void TerrainUnitEval(const Plan& P, const TerrainUnit& u, int terrain, const ConstCol xs, const Col Sk, const Col gk) {
   const double px = xs[u.xi[0]], py = xs[u.xi[1]], pz = xs[u.xi[2]];
-  const TerrainPoint tp = EvalTerrain(terrain, px, py);
+  const TerrainPoint tp = EvalTerrain(P, terrain, px, py);
   gk[0] = pz - tp.h;
   Sk[0] = -tp.hx; Sk[1] = -tp.hy;
 }
@@ -419,7 +451,7 @@ __device__ __forceinline__ void ForceUnitEval(const Plan& P, const ForceUnit& u,
   const double mu = P.mu;
   const double px = xs[u.xp[0]], py = xs[u.xp[1]];
   const double f[3] = {xs[u.xf[0]], xs[u.xf[1]], xs[u.xf[2]]};
-  const TerrainPoint tp = EvalTerrain(terrain, px, py);
+  const TerrainPoint tp = EvalTerrain(P, terrain, px, py);
   // HeightMap::GetNormal / GetTangent1 / GetTangent2, height_map.cc:93-138
   const double vn[3] = {-tp.hx, -tp.hy, 1.0}, vt1[3] = {1.0, 0.0, tp.hx}, vt2[3] = {0.0, 1.0, tp.hy};
   double n[3], t1[3], t2[3], sn_n, nr_n, sn_1, nr_1, sn_2, nr_2;
@@ -762,7 +794,7 @@ __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict
     } else if (kind == kGroupTerrain) {
       const int terrain = (terrain_ids && b < nb) ? __ldg(terrain_ids + b) : default_terrain;
       for (int q = 0; q < count; ++q)
-        TerrainUnitEval(P.terr[first + q], terrain, xs, Col{t + (1 + 2 * q) * kLD + lane, kLD}, Col{t + (1 + 2 * count + q) * kLD + lane, kLD});
+        TerrainUnitEval(P, P.terr[first + q], terrain, xs, Col{t + (1 + 2 * q) * kLD + lane, kLD}, Col{t + (1 + 2 * count + q) * kLD + lane, kLD});
       n_rows = 1 + 3 * count;
     } else if (kind == kGroupSwing) {
       if (flags & 1u) for (int q = 0; q < count; ++q) SwingUnitEval(P.swing[first + q], xs, Col{t + (1 + 4 * q) * kLD + lane, kLD});

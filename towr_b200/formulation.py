@@ -264,6 +264,15 @@ class Batch:
         assert t.shape == (self.B,)
         check(lib.twb_batch_set_terrains(self._h, t.ctypes.data_as(C.POINTER(C.c_int))))
 
+    def set_grid_terrain(self, heights):
+        """heights[y_cell, x_cell] (2-D float64, cells of 0.17 m) of the GRID_CSV terrain; None removes it."""
+        if heights is None:
+            check(lib.twb_batch_set_grid_terrain(self._h, None, 0, 0))
+            return
+        h = np.ascontiguousarray(heights, np.float64)
+        assert h.ndim == 2
+        check(lib.twb_batch_set_grid_terrain(self._h, h.ctypes.data_as(C.POINTER(C.c_double)), h.shape[0], h.shape[1]))
+
     def launches_per_eval(self, flags=capi.EVAL_ALL):
         return lib.twb_batch_launches_per_eval(self._h, flags)
 
