@@ -144,6 +144,14 @@ int twb_problem_bounds(const twb_problem* p, double* x_lower, double* x_upper,
                        double* g_lower, double* g_upper);
 int twb_problem_x0(const twb_problem* p, double* x0);
 
+/* Goal-randomised instances of one structure class (BASELINE configs[2]: "randomized goal/initial-guess instances"):
+ * initial guess and variable bounds NlpFormulation::GetVariableSets (nlp_formulation.cc:95-181) produces when only
+ * final_base_.lin.p / final_base_.ang.p differ from the spec.  `goals` holds n_goals x {x, y, z, roll, pitch, yaw};
+ * x0 / x_lower / x_upper receive n_goals rows of n values (any of them may be NULL).  Structure, constraint bounds
+ * and dimensions do not depend on the goal. */
+int twb_problem_goal_instances(const twb_problem* p, int n_goals, const double* goals, double* x0, double* x_lower,
+                               double* x_upper);
+
 /* Component layout: variable sets (column ranges) and constraint sets (row
  * ranges) in ifopt's Add*Set order; names are the reference's
  * ("base-lin", "ee-motion_0", "dynamic", "rangeofmotion-1", ...). */

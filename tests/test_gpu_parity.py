@@ -215,7 +215,13 @@ def test_full_size_properties_config3_biped_16384():
     (odd nnz: four alignment classes of the output rows)."""
     f = tb.make_formulation("biped_walk_stairs"); spec = f.to_spec(); p = tb.Problem(spec)
     B = 16384
-    X = synthetic_iterates_fast(p, B)
+    rng = np.random.default_rng(16384)                    # SURVEY 8d: goal x in U[0.5, 2.5], y, yaw in U[-0.3, 0.3]
+    goals = np.zeros((B, 6))
+    goals[:, 0] = rng.uniform(0.5, 2.5, B); goals[:, 1] = rng.uniform(-0.3, 0.3, B)
+    goals[:, 2] = f.final_base_.lin.p[2]; goals[:, 5] = rng.uniform(-0.3, 0.3, B)
+    x0s, xl, xu = p.goal_instances(goals)                 # per-instance initial guess / bounds, one structure class
+    assert np.all(xl <= xu) and np.ptp(x0s[:, 120]) > 0.5    # (the reference's interpolated guess need not satisfy the bounds)
+    X = synthetic_iterates_fast(p, B, x0=x0s)
     bt = p.batch(B)
     g1, j1, s1 = _device_eval(p, bt, X)
     g2, j2, s2 = _device_eval(p, bt, X)

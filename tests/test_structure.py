@@ -151,3 +151,26 @@ def test_product_does_not_reference_oracle():
             if fn.endswith((".py", ".cc", ".cu", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "oracle" not in txt.lower(), os.path.join(dirpath, fn)
+
+
+def test_goal_randomised_instances_match_oracle():
+    """BASELINE configs[2]: x0 / bounds of goal-randomised instances of one structure class, without re-building it."""
+    rng = np.random.default_rng(8)
+    for name in ("biped_walk_stairs", "anymal_trot_block", "hyq_gallop_gap"):
+        base = tb.make_formulation(name)
+        p = tb.Problem(base.to_spec())
+        G = 5
+        goals = np.zeros((G, 6))
+        goals[:, 0] = rng.uniform(0.5, 2.5, G); goals[:, 1] = rng.uniform(-0.3, 0.3, G)
+        goals[:, 2] = base.final_base_.lin.p[2]; goals[:, 5] = rng.uniform(-0.3, 0.3, G)
+        x0, xl, xu = p.goal_instances(goals)
+        for i in range(G):
+            f = tb.make_formulation(name, goal_xy=(goals[i, 0], goals[i, 1]), goal_yaw=goals[i, 5])
+            o = oracle_lib.Oracle(f.to_spec())
+            oxl, oxu, _, _ = o.bounds()
+            assert np.array_equal(x0[i], o.x0()) and np.array_equal(xl[i], oxl) and np.array_equal(xu[i], oxu)
+    # the spec's own goal reproduces the problem's x0 / bounds
+    fb = base.final_base_
+    own = np.array([[*fb.lin.p, *fb.ang.p]])
+    x0, xl, xu = p.goal_instances(own)
+    assert np.array_equal(x0[0], p.GetVariableValues()) and np.array_equal(xl[0], p.bounds()[0])

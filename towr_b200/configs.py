@@ -113,15 +113,16 @@ def synthetic_iterates(problem, batch, seed=1234, first=0):
     return X
 
 
-def synthetic_iterates_fast(problem, batch, seed=1234):
-    """Same distribution, one generator for the whole batch (for the large bench batches)."""
-    x0 = problem.GetVariableValues()
+def synthetic_iterates_fast(problem, batch, seed=1234, x0=None):
+    """Same distribution, one generator for the whole batch (for the large bench batches).  `x0`: optional (batch, n)
+    per-instance initial guesses (goal-randomised instances, Problem.goal_instances)."""
+    x0 = problem.GetVariableValues() if x0 is None else np.asarray(x0)
     sig = variable_sigma(problem)
     rng = np.random.default_rng(seed)
     X = x0 + sig * rng.standard_normal((batch, problem.n))
     for name, start, count in problem.variable_sets():
         if name.startswith("ee-schedule"):
-            X[:, start:start + count] = _renormalise(problem, name, x0[start:start + count] * rng.uniform(0.9, 1.1, (batch, count)))
+            X[:, start:start + count] = _renormalise(problem, name, x0[..., start:start + count] * rng.uniform(0.9, 1.1, (batch, count)))
         if name == "base-ang":
             blk = X[:, start:start + count].reshape(batch, -1, 6)
             blk[:, :, :3] = np.clip(blk[:, :, :3], -1.0, 1.0)

@@ -129,6 +129,16 @@ int twb_problem_x0(const twb_problem* p, double* x0) {
   std::memcpy(x0, p->f.x0.data(), sizeof(double) * p->f.n);
   return TWB_OK;
 }
+int twb_problem_goal_instances(const twb_problem* p, int n_goals, const double* goals, double* x0, double* xl, double* xu) {
+  if (!p || !goals || n_goals < 0) return Fail(TWB_ERR_INVALID, "bad argument");
+  const size_t n = (size_t)p->f.n;
+  for (int i = 0; i < n_goals; ++i) {
+    const double* gpose = goals + 6 * (size_t)i;
+    int rc = p->f.GoalInstance(gpose, gpose + 3, x0 ? x0 + i * n : nullptr, xl ? xl + i * n : nullptr, xu ? xu + i * n : nullptr);
+    if (rc != TWB_OK) return Fail(rc, "goal instance");
+  }
+  return TWB_OK;
+}
 int twb_layout_num_variable_sets(const twb_problem* p) { return p ? (int)p->f.var_sets.size() : 0; }
 int twb_layout_num_constraint_sets(const twb_problem* p) { return p ? (int)p->f.con_sets.size() : 0; }
 static int CopyComponent(const std::vector<twb::Component>& v, int i, char* name, int cap, int* start, int* count) {

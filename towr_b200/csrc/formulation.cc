@@ -197,7 +197,80 @@ void CrossEntry(int i, int d, int* comp, double* sign) {
   *comp = c[i][d]; *sign = s[i][d];
 }
 
+// NlpFormulation::GetVariableSets' initial guess and bounds (nlp_formulation.cc:95-181) for the goal / initial state in
+// `sp`; `sets` supplies the variable maps and receives the per-set x0 / bounds.
+void InitialGuessAndBounds(const twb_spec& sp, const RobotConst& rb, double T, bool optimize_timings, std::vector<NodeSet>* sets_io,
+                           std::vector<double>* x0_out, std::vector<double>* lo_out, std::vector<double>* up_out) {
+  std::vector<NodeSet>& sets = *sets_io;
+  const int n_ee = sp.n_ee;
+  NodeSet& lin = sets[0]; NodeSet& ang = sets[1];
+  auto motion = [&](int e) -> NodeSet& { return sets[2 + e]; };
+  auto force = [&](int e) -> NodeSet& { return sets[2 + n_ee + e]; };
+  for (auto& s : sets) s.Finish();
+  std::vector<double>& x0 = *x0_out; std::vector<double>& x_lower = *lo_out; std::vector<double>& x_upper = *up_out;
+  {
+    double fx = sp.final_base_lin_pos[0], fy = sp.final_base_lin_pos[1];
+    double fz = TerrainHeight(sp.terrain, fx, fy) - rb.nominal[0][2];
+    double final_pos[3] = {fx, fy, fz};
+    lin.Interpolate(sp.initial_base_lin_pos, final_pos, T);
+    ang.Interpolate(sp.initial_base_ang_pos, sp.final_base_ang_pos, T);
+    const int last = lin.n_nodes - 1;
+    for (int d = 0; d < 3; ++d) {
+      lin.Fix(0, kPos, d, sp.initial_base_lin_pos[d]); lin.Fix(0, kVel, d, sp.initial_base_lin_vel[d]);
+      ang.Fix(0, kPos, d, sp.initial_base_ang_pos[d]); ang.Fix(0, kVel, d, sp.initial_base_ang_vel[d]);
+      if (sp.bounds_final_lin_pos[d]) lin.Fix(last, kPos, d, sp.final_base_lin_pos[d]);
+      if (sp.bounds_final_lin_vel[d]) lin.Fix(last, kVel, d, sp.final_base_lin_vel[d]);
+      if (sp.bounds_final_ang_pos[d]) ang.Fix(last, kPos, d, sp.final_base_ang_pos[d]);
+      if (sp.bounds_final_ang_vel[d]) ang.Fix(last, kVel, d, sp.final_base_ang_vel[d]);
+    }
+    // yaw-only rotation of the nominal stance (EulerConverter::GetRotationMatrixBaseToWorld with x=y=0)
+    double yaw = sp.final_base_ang_pos[2];
+    double x = 0.0, y = 0.0, z = yaw;
+    double R[3][3] = {{cos(y) * cos(z), cos(z) * sin(x) * sin(y) - cos(x) * sin(z), sin(x) * sin(z) + cos(x) * cos(z) * sin(y)},
+                      {cos(y) * sin(z), cos(x) * cos(z) + sin(x) * sin(y) * sin(z), cos(x) * sin(y) * sin(z) - cos(z) * sin(x)},
+                      {-sin(y), cos(y) * sin(x), cos(x) * cos(y)}};
+    for (int e = 0; e < n_ee; ++e) {
+      const double* nom = rb.nominal[e];
+      double w[3];
+      for (int i = 0; i < 3; ++i) w[i] = sp.final_base_lin_pos[i] + (R[i][0] * nom[0] + R[i][1] * nom[1] + R[i][2] * nom[2]);
+      double goal[3] = {w[0], w[1], TerrainHeight(sp.terrain, w[0], w[1])};
+      motion(e).Interpolate(sp.initial_ee_W[e], goal, T);
+      for (int d = 0; d < 3; ++d) motion(e).Fix(0, kPos, d, sp.initial_ee_W[e][d]);
+      double f_stance[3] = {0.0, 0.0, rb.mass * 9.80665 / n_ee};
+      force(e).Interpolate(f_stance, f_stance, T);
+    }
+  }
+  x0.clear(); x_lower.clear(); x_upper.clear();
+  for (auto& s : sets) {
+    x0.insert(x0.end(), s.x0.begin(), s.x0.end());
+    x_lower.insert(x_lower.end(), s.lo.begin(), s.lo.end());
+    x_upper.insert(x_upper.end(), s.up.begin(), s.up.end());
+  }
+  if (optimize_timings)   // PhaseDurations::GetValues / GetBounds, phase_durations.cc:68-77, 102-110
+    for (int e = 0; e < n_ee; ++e)
+      for (int i = 0; i + 1 < sp.n_phases[e]; ++i) {
+        x0.push_back(sp.phase_durations[e][i]); x_lower.push_back(sp.bound_phase_duration_min); x_upper.push_back(sp.bound_phase_duration_max);
+      }
+
+}
+
 }  // namespace
+
+struct SetsHolder { std::vector<NodeSet> sets; RobotConst robot; double T = 0.0; };
+
+// x0 and variable bounds of an instance that differs from the spec only in its goal pose (NlpFormulation::final_base_)
+int Formulation::GoalInstance(const double final_lin_pos[3], const double final_ang_pos[3], double* x0_out, double* lo_out, double* up_out) const {
+  if (!holder) return TWB_ERR_INVALID;
+  twb_spec sp = spec;
+  for (int k = 0; k < 3; ++k) { sp.final_base_lin_pos[k] = final_lin_pos[k]; sp.final_base_ang_pos[k] = final_ang_pos[k]; }
+  std::vector<NodeSet> sets = holder->sets;
+  std::vector<double> a, b, c;
+  InitialGuessAndBounds(sp, holder->robot, holder->T, optimize_timings, &sets, &a, &b, &c);
+  if (x0_out) std::copy(a.begin(), a.end(), x0_out);
+  if (lo_out) std::copy(b.begin(), b.end(), lo_out);
+  if (up_out) std::copy(c.begin(), c.end(), up_out);
+  return TWB_OK;
+}
 
 int Formulation::Build(const twb_spec& sp, std::string* err) {
   auto fail = [&](int code, const char* why) { if (err) *err = why; return code; };
@@ -248,49 +321,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   auto force = [&](int e) -> NodeSet& { return sets[2 + n_ee + e]; };
 
   // ---- initial guess and variable bounds (nlp_formulation.cc:95-181)
-  {
-    double fx = sp.final_base_lin_pos[0], fy = sp.final_base_lin_pos[1];
-    double fz = TerrainHeight(sp.terrain, fx, fy) - rb.nominal[0][2];
-    double final_pos[3] = {fx, fy, fz};
-    lin.Interpolate(sp.initial_base_lin_pos, final_pos, T);
-    ang.Interpolate(sp.initial_base_ang_pos, sp.final_base_ang_pos, T);
-    const int last = lin.n_nodes - 1;
-    for (int d = 0; d < 3; ++d) {
-      lin.Fix(0, kPos, d, sp.initial_base_lin_pos[d]); lin.Fix(0, kVel, d, sp.initial_base_lin_vel[d]);
-      ang.Fix(0, kPos, d, sp.initial_base_ang_pos[d]); ang.Fix(0, kVel, d, sp.initial_base_ang_vel[d]);
-      if (sp.bounds_final_lin_pos[d]) lin.Fix(last, kPos, d, sp.final_base_lin_pos[d]);
-      if (sp.bounds_final_lin_vel[d]) lin.Fix(last, kVel, d, sp.final_base_lin_vel[d]);
-      if (sp.bounds_final_ang_pos[d]) ang.Fix(last, kPos, d, sp.final_base_ang_pos[d]);
-      if (sp.bounds_final_ang_vel[d]) ang.Fix(last, kVel, d, sp.final_base_ang_vel[d]);
-    }
-    // yaw-only rotation of the nominal stance (EulerConverter::GetRotationMatrixBaseToWorld with x=y=0)
-    double yaw = sp.final_base_ang_pos[2];
-    double x = 0.0, y = 0.0, z = yaw;
-    double R[3][3] = {{cos(y) * cos(z), cos(z) * sin(x) * sin(y) - cos(x) * sin(z), sin(x) * sin(z) + cos(x) * cos(z) * sin(y)},
-                      {cos(y) * sin(z), cos(x) * cos(z) + sin(x) * sin(y) * sin(z), cos(x) * sin(y) * sin(z) - cos(z) * sin(x)},
-                      {-sin(y), cos(y) * sin(x), cos(x) * cos(y)}};
-    for (int e = 0; e < n_ee; ++e) {
-      const double* nom = rb.nominal[e];
-      double w[3];
-      for (int i = 0; i < 3; ++i) w[i] = sp.final_base_lin_pos[i] + (R[i][0] * nom[0] + R[i][1] * nom[1] + R[i][2] * nom[2]);
-      double goal[3] = {w[0], w[1], TerrainHeight(sp.terrain, w[0], w[1])};
-      motion(e).Interpolate(sp.initial_ee_W[e], goal, T);
-      for (int d = 0; d < 3; ++d) motion(e).Fix(0, kPos, d, sp.initial_ee_W[e][d]);
-      double f_stance[3] = {0.0, 0.0, rb.mass * 9.80665 / n_ee};
-      force(e).Interpolate(f_stance, f_stance, T);
-    }
-  }
-  x0.clear(); x_lower.clear(); x_upper.clear();
-  for (auto& s : sets) {
-    x0.insert(x0.end(), s.x0.begin(), s.x0.end());
-    x_lower.insert(x_lower.end(), s.lo.begin(), s.lo.end());
-    x_upper.insert(x_upper.end(), s.up.begin(), s.up.end());
-  }
-  if (optimize_timings)   // PhaseDurations::GetValues / GetBounds, phase_durations.cc:68-77, 102-110
-    for (int e = 0; e < n_ee; ++e)
-      for (int i = 0; i + 1 < sp.n_phases[e]; ++i) {
-        x0.push_back(sp.phase_durations[e][i]); x_lower.push_back(sp.bound_phase_duration_min); x_upper.push_back(sp.bound_phase_duration_max);
-      }
+  InitialGuessAndBounds(sp, rb, T, optimize_timings, &sets, &x0, &x_lower, &x_upper);
+  holder = std::make_shared<SetsHolder>(); holder->sets = sets; holder->robot = rb; holder->T = T;
 
   // ---- splines (spline_holder.cc:35-61, fixed durations)
   auto poly_durations = [&](const NodeSet& s, int e) {  // nodes_variables_phase_based.cc:78-89

@@ -8,6 +8,7 @@
 
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,7 @@ bool GaitPhases(int n_ee, int combo, double t_total, std::vector<std::vector<dou
                 std::vector<bool>* contact_at_start);
 
 struct Component { std::string name; int start; int count; };
+struct SetsHolder;   // variable maps of the node sets (formulation.cc)
 
 // Everything the kernels need, still on the host (capi.cc uploads it).
 struct HostTables {
@@ -57,6 +59,8 @@ class Formulation {
  public:
   // returns TWB_OK / TWB_ERR_*; `err` gets a one-line reason on failure
   int Build(const twb_spec& spec, std::string* err);
+  // NlpFormulation::GetVariableSets with another final_base_: x0 / bounds of a goal-randomised instance (n values each)
+  int GoalInstance(const double final_lin_pos[3], const double final_ang_pos[3], double* x0, double* x_lower, double* x_upper) const;
 
   int n = 0, m = 0, nnz = 0;
   std::vector<int> row_ptr, col_idx;
@@ -66,6 +70,7 @@ class Formulation {
   bool optimize_timings = false;
   twb_spec spec{};
   HostTables tables;
+  std::shared_ptr<SetsHolder> holder;
 };
 
 }  // namespace twb

@@ -222,6 +222,18 @@ class Problem:
         check(lib.twb_problem_x0(self._h, x0.ctypes.data_as(C.POINTER(C.c_double))))
         return x0
 
+    def goal_instances(self, goals):
+        """x0, x_lower, x_upper (each (G, n)) of instances that differ from the spec only in their goal pose;
+        goals: (G, 6) = final base x, y, z, roll, pitch, yaw (NlpFormulation::final_base_)."""
+        goals = np.ascontiguousarray(goals, np.float64)
+        assert goals.ndim == 2 and goals.shape[1] == 6
+        G = goals.shape[0]
+        x0, xl, xu = np.empty((G, self.n)), np.empty((G, self.n)), np.empty((G, self.n))
+        dp = C.POINTER(C.c_double)
+        check(lib.twb_problem_goal_instances(self._h, G, goals.ctypes.data_as(dp), x0.ctypes.data_as(dp),
+                                             xl.ctypes.data_as(dp), xu.ctypes.data_as(dp)))
+        return x0, xl, xu
+
     def _components(self, count_fn, get_fn):
         out = []
         buf = C.create_string_buffer(64)
