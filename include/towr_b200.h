@@ -198,6 +198,14 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
 int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac,
                         double* cost, double* grad, int* status, unsigned flags);
 
+/* ---- solution post-processing: fpowr::GetTrajectory (fpowr/include/fpowr/footstep_plan_extractor.h:19-53) --------
+ * The splines of every instance sampled at t = 0, dt, 2 dt, ... <= T + 1e-5.  Per sample n_values = 19 + 13 n_ee
+ * doubles: base lin p, v, a (9) | base orientation quaternion w, x, y, z (4) | angular velocity (3) | angular
+ * acceleration (3) | per foot: contact flag 0/1, ee-motion p, v, a (9), ee-force (3). */
+int twb_problem_trajectory_dims(const twb_problem* p, double dt, int* n_samples, int* n_values);
+/* x: host [B][n] (e.g. converged solutions); out: host [B][n_samples][n_values] */
+int twb_batch_sample_trajectory_host(twb_batch* b, const double* x, double dt, double* out);
+
 /* number of kernel launches one twb_batch_eval_device(flags) enqueues */
 int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags);
 

@@ -1523,6 +1523,57 @@ int oracle_batch_eval(const twb_spec* spec, int B, const int* terrain_ids, const
   }
   return rc;
 }
+// fpowr::GetTrajectory (fpowr/include/fpowr/footstep_plan_extractor.h:19-53): the solution sampled every dt.
+// Per sample: base lin p, v, a (9) | base orientation quaternion w, x, y, z (4) | angular velocity (3) | angular
+// acceleration (3) | per foot: contact flag (1), ee-motion p, v, a (9), ee-force (3).
+// The quaternion is Eigen::Quaterniond(Matrix3d) (Eigen 3.3 Quaternion.h, quaternionbase_assign_impl<Other,3,3>) restated.
+static void QuaternionFromMatrix(const M3& m, double q[4]) {   // q = w, x, y, z
+  double t = m.a[0][0] + m.a[1][1] + m.a[2][2];
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0); q[0] = 0.5 * t; t = 0.5 / t;
+    q[1] = (m.a[2][1] - m.a[1][2]) * t; q[2] = (m.a[0][2] - m.a[2][0]) * t; q[3] = (m.a[1][0] - m.a[0][1]) * t;
+  } else {
+    int i = 0; if (m.a[1][1] > m.a[0][0]) i = 1; if (m.a[2][2] > m.a[i][i]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m.a[i][i] - m.a[j][j] - m.a[k][k] + 1.0);
+    q[1 + i] = 0.5 * t; t = 0.5 / t;
+    q[0] = (m.a[k][j] - m.a[j][k]) * t; q[1 + j] = (m.a[j][i] + m.a[i][j]) * t; q[1 + k] = (m.a[k][i] + m.a[i][k]) * t;
+  }
+}
+int oracle_trajectory_dims(void* h, double dt, int* n_samples, int* n_values) {
+  Problem* p = static_cast<Problem*>(h);
+  double T = 0.0; for (double d : p->ctx.base_lin->T) T += d;   // Spline::GetTotalTime
+  int n = 0; for (double t = 0.0; t <= T + 1e-5; t += dt) ++n;
+  *n_samples = n; *n_values = 19 + 13 * p->robot.n_ee;
+  return 0;
+}
+int oracle_trajectory(void* h, const double* x, double dt, double* out) {
+  Problem* p = static_cast<Problem*>(h);
+  p->SetVariables(x);
+  const int n_ee = p->robot.n_ee, K = 19 + 13 * n_ee;
+  double T = 0.0; for (double d : p->ctx.base_lin->T) T += d;
+  Euler eu; eu.s = p->ctx.base_ang;
+  int k = 0;
+  for (double t = 0.0; t <= T + 1e-5; t += dt, ++k) {
+    double* o = out + (size_t)k * K;
+    State3 lin = p->ctx.base_lin->GetPoint(t);
+    for (int d = 0; d < 3; ++d) { o[d] = lin.p[d]; o[3 + d] = lin.v[d]; o[6 + d] = lin.a[d]; }
+    QuaternionFromMatrix(sp_to_dense3(eu.RotBaseToWorld(t)), o + 9);
+    V3 w = eu.AngVel(t), wd = eu.AngAcc(t);
+    for (int d = 0; d < 3; ++d) { o[13 + d] = w[d]; o[16 + d] = wd[d]; }
+    for (int ee = 0; ee < n_ee; ++ee) {
+      double* e = o + 19 + 13 * ee;
+      const Durations* pd = p->ctx.durations[ee];
+      int phase = GetSegmentID(t, pd->durations);                       // PhaseDurations::IsContactPhase, phase_durations.cc:120-124
+      e[0] = (phase % 2 == 0 ? pd->initial_contact : !pd->initial_contact) ? 1.0 : 0.0;
+      State3 mo = p->ctx.ee_motion[ee]->GetPoint(t);
+      for (int d = 0; d < 3; ++d) { e[1 + d] = mo.p[d]; e[4 + d] = mo.v[d]; e[7 + d] = mo.a[d]; }
+      V3 f = p->ctx.ee_force[ee]->GetPoint(t).p;
+      for (int d = 0; d < 3; ++d) e[10 + d] = f[d];
+    }
+  }
+  return 0;
+}
 int oracle_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -90,6 +90,15 @@ class Oracle:
     def set_terrain(self, terrain):
         lib().oracle_set_terrain(self._h, int(terrain))
 
+    def trajectory(self, x, dt):
+        """fpowr::GetTrajectory: (n_samples, 19 + 13 n_ee) samples of the solution x every dt."""
+        ns, nv = C.c_int(), C.c_int()
+        lib().oracle_trajectory_dims(self._h, C.c_double(dt), C.byref(ns), C.byref(nv))
+        out = np.empty((ns.value, nv.value))
+        x = np.ascontiguousarray(x, np.float64)
+        lib().oracle_trajectory(self._h, _p(x), C.c_double(dt), _p(out))
+        return out
+
     def eval(self, x, want_cost=False):
         x = np.ascontiguousarray(x, np.float64)
         g, vals = np.empty(self.m), np.empty(self.nnz)

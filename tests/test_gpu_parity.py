@@ -320,3 +320,21 @@ def test_csv_grid_terrain():
     oracle_lib.set_grid(np.zeros((1, 1)))
     ref0 = oracle_lib.batch_eval(spec, X, terrain_ids=terr)
     assert check_sets(flat["g"], ref0["g"], p.constraint_sets())[0] == 0
+
+
+def test_trajectory_sampling_matches_oracle():
+    """fpowr::GetTrajectory (footstep_plan_extractor.h:19-53) batched on the device: splines, quaternion, angular
+    velocity / acceleration, contact flags — against the oracle, for fixed and for optimised phase durations."""
+    for name, B, dt in (("hopper", 5, 0.05), ("anymal_trot_block", 33, 0.01), ("hyq_gallop_gap", 12, 0.02)):
+        spec = tb.make_formulation(name).to_spec(); p = tb.Problem(spec)
+        X = synthetic_iterates(p, B)
+        got = p.batch(B).sample_trajectory(X, dt)
+        o = oracle_lib.Oracle(spec)
+        for b in range(B):
+            ref = o.trajectory(X[b], dt)
+            assert got[b].shape == ref.shape
+            scale = np.maximum(1.0, np.abs(ref).max(axis=0, keepdims=True))
+            assert np.all(np.abs(got[b] - ref) <= 1e-12 * np.abs(ref) + 1e-13 * scale), (name, b, np.abs(got[b] - ref).max())
+        n_ee = (got.shape[2] - 19) // 13
+        assert np.allclose((got[..., 9:13] ** 2).sum(-1), 1.0, atol=1e-12)          # unit quaternions
+        assert set(np.unique(got[..., [19 + 13 * e for e in range(n_ee)]])) <= {0.0, 1.0}

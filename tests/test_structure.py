@@ -174,3 +174,12 @@ def test_goal_randomised_instances_match_oracle():
     own = np.array([[*fb.lin.p, *fb.ang.p]])
     x0, xl, xu = p.goal_instances(own)
     assert np.array_equal(x0[0], p.GetVariableValues()) and np.array_equal(xl[0], p.bounds()[0])
+
+
+def test_trajectory_dims_match_oracle():
+    for name, dt in (("hopper", 0.05), ("anymal_trot_block", 0.01), ("hyq_gallop_gap", 0.1)):
+        spec = tb.make_formulation(name).to_spec(); p = tb.Problem(spec)
+        ns, nv = C.c_int(), C.c_int()
+        capi.check(capi.lib.twb_problem_trajectory_dims(p._h, dt, C.byref(ns), C.byref(nv)))
+        ref = oracle_lib.Oracle(spec).trajectory(p.GetVariableValues(), dt)
+        assert (ns.value, nv.value) == ref.shape

@@ -247,6 +247,45 @@ int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, in
   return TWB_OK;
 }
 
+int twb_problem_trajectory_dims(const twb_problem* p, double dt, int* n_samples, int* n_values) {
+  if (!p) return Fail(TWB_ERR_INVALID, "null problem");
+  std::vector<double> times; std::vector<twb::SplineSample> samples; std::vector<int> contact;
+  int rc = p->f.TrajectoryTables(dt, &times, &samples, &contact);
+  if (rc != TWB_OK) return Fail(rc, "bad dt");
+  if (n_samples) *n_samples = (int)times.size();
+  if (n_values) *n_values = 19 + 13 * p->f.spec.n_ee;
+  return TWB_OK;
+}
+
+int twb_batch_sample_trajectory_host(twb_batch* b, const double* x, double dt, double* out) {
+  if (!b || !x || !out) return Fail(TWB_ERR_INVALID, "null argument");
+  const twb::Formulation& f = b->prob->f;
+  std::vector<double> times; std::vector<twb::SplineSample> samples; std::vector<int> contact;
+  int rc = f.TrajectoryTables(dt, &times, &samples, &contact);
+  if (rc != TWB_OK) return Fail(rc, "bad dt");
+  if (f.optimize_timings) { contact.clear(); for (int e = 0; e < f.spec.n_ee; ++e) contact.push_back(f.spec.in_contact_at_start[e] != 0); }
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  const size_t B = b->B, K = 19 + 13 * (size_t)f.spec.n_ee, n_steps = times.size();
+  twb::SplineSample* d_samples = nullptr; int* d_contact = nullptr; double* d_out = nullptr;
+  auto cleanup = [&] { cudaFree(d_samples); cudaFree(d_contact); cudaFree(d_out); };
+  if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_contact), sizeof(int) * contact.size())) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(double) * B * n_steps * K)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  cudaStream_t s = b->stream;
+  cudaMemcpyAsync(d_samples, samples.data(), sizeof(twb::SplineSample) * samples.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_contact, contact.data(), sizeof(int) * contact.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(b->d_x, x, sizeof(double) * B * f.n, cudaMemcpyHostToDevice, s);
+  rc = twb::LaunchTrajectory(b->plan, b->d_x, b->d_XT, d_samples, d_contact, (int)n_steps, d_out, b->B, s);
+  if (rc == 0) cudaMemcpyAsync(out, d_out, sizeof(double) * B * n_steps * K, cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "trajectory kernel launch");
+  if (e != cudaSuccess) return CudaFail(e, "trajectory sampling");
+  return TWB_OK;
+}
+
 int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   if (!b) return 0;
   const twb::Plan& p = b->plan;

@@ -256,7 +256,41 @@ void InitialGuessAndBounds(const twb_spec& sp, const RobotConst& rb, double T, b
 
 }  // namespace
 
-struct SetsHolder { std::vector<NodeSet> sets; RobotConst robot; double T = 0.0; };
+struct SetsHolder { std::vector<NodeSet> sets; RobotConst robot; double T = 0.0; std::vector<double> base_T; };
+
+int Formulation::TrajectoryTables(double dt, std::vector<double>* times, std::vector<SplineSample>* samples, std::vector<int>* contact) const {
+  if (!holder || !(dt > 0.0)) return TWB_ERR_INVALID;
+  const std::vector<NodeSet>& sets = holder->sets;
+  const int n_ee = spec.n_ee, zero_slot = n;
+  // Spline::GetTotalTime of the base spline (sum of its polynomial durations), then t += dt while t <= T + 1e-5
+  double T = 0.0; for (double d : holder->base_T) T += d;
+  times->clear(); samples->clear(); contact->clear();
+  for (double t = 0.0; t <= T + 1e-5; t += dt) times->push_back(t);
+  auto poly_durations = [&](const NodeSet& s, int e) {
+    std::vector<double> d; for (auto& p : s.poly) d.push_back(spec.phase_durations[e][p.phase] / p.n_in_phase); return d;
+  };
+  SplineDef lin{&sets[0], holder->base_T}, ang{&sets[1], holder->base_T};
+  std::vector<SplineDef> mo, fo;
+  for (int e = 0; e < n_ee; ++e) { mo.push_back({&sets[2 + e], poly_durations(sets[2 + e], e)}); fo.push_back({&sets[2 + n_ee + e], poly_durations(sets[2 + n_ee + e], e)}); }
+  auto foot = [&](int e, int kind, double t) {
+    if (!optimize_timings) return MakeSample(kind == 0 ? mo[e] : fo[e], t, zero_slot);
+    SplineSample o{}; o.T = t; o.xi[0] = (int16_t)kPhaseMarker; o.xi[1] = (int16_t)(2 * e + kind); return o;
+  };
+  for (double t : *times) {
+    samples->push_back(MakeSample(lin, t, zero_slot));
+    samples->push_back(MakeSample(ang, t, zero_slot));
+    for (int e = 0; e < n_ee; ++e) samples->push_back(foot(e, 0, t));
+    for (int e = 0; e < n_ee; ++e) samples->push_back(foot(e, 1, t));
+    if (!optimize_timings)
+      for (int e = 0; e < n_ee; ++e) {   // PhaseDurations::IsContactPhase, phase_durations.cc:120-124
+        std::vector<double> ph(spec.phase_durations[e], spec.phase_durations[e] + spec.n_phases[e]);
+        const int phase = SegmentID(t, ph);
+        const bool first = spec.in_contact_at_start[e] != 0;
+        contact->push_back((phase % 2 == 0 ? first : !first) ? 1 : 0);
+      }
+  }
+  return TWB_OK;
+}
 
 // x0 and variable bounds of an instance that differs from the spec only in its goal pose (NlpFormulation::final_base_)
 int Formulation::GoalInstance(const double final_lin_pos[3], const double final_ang_pos[3], double* x0_out, double* lo_out, double* up_out) const {
@@ -322,7 +356,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
 
   // ---- initial guess and variable bounds (nlp_formulation.cc:95-181)
   InitialGuessAndBounds(sp, rb, T, optimize_timings, &sets, &x0, &x_lower, &x_upper);
-  holder = std::make_shared<SetsHolder>(); holder->sets = sets; holder->robot = rb; holder->T = T;
+  holder = std::make_shared<SetsHolder>(); holder->sets = sets; holder->robot = rb; holder->T = T; holder->base_T = base_T;
 
   // ---- splines (spline_holder.cc:35-61, fixed durations)
   auto poly_durations = [&](const NodeSet& s, int e) {  // nodes_variables_phase_based.cc:78-89

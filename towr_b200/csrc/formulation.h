@@ -60,6 +60,9 @@ class Formulation {
   // returns TWB_OK / TWB_ERR_*; `err` gets a one-line reason on failure
   int Build(const twb_spec& spec, std::string* err);
   // NlpFormulation::GetVariableSets with another final_base_: x0 / bounds of a goal-randomised instance (n values each)
+  // time grid and spline samples of fpowr::GetTrajectory(dt): per time step 2 + 2 n_ee samples (base-lin, base-ang,
+  // ee-motion.., ee-force..); contact[step][foot] (fixed durations) or empty (durations optimised: per instance on the device)
+  int TrajectoryTables(double dt, std::vector<double>* times, std::vector<SplineSample>* samples, std::vector<int>* contact) const;
   int GoalInstance(const double final_lin_pos[3], const double final_ang_pos[3], double* x0, double* x_lower, double* x_upper) const;
 
   int n = 0, m = 0, nnz = 0;

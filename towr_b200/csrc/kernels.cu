@@ -982,6 +982,78 @@ __global__ void __launch_bounds__(128) PhaseJac(const Plan P, const double* __re
   }
 }
 
+// ---- solution post-processing: fpowr::GetTrajectory (footstep_plan_extractor.h:19-53) --------------------------
+// Eigen::Quaterniond(Matrix3d) (Eigen 3.3 Quaternion.h, quaternionbase_assign_impl<Other,3,3>); q = w, x, y, z
+__device__ __forceinline__ void QuaternionFromMatrix(const double m[3][3], double q[4]) {
+  double t = m[0][0] + m[1][1] + m[2][2];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0); q[0] = 0.5 * t; t = 0.5 / t;
+    q[1] = (m[2][1] - m[1][2]) * t; q[2] = (m[0][2] - m[2][0]) * t; q[3] = (m[1][0] - m[0][1]) * t;
+  } else {
+    int i = 0; if (m[1][1] > m[0][0]) i = 1; if (m[2][2] > m[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t; t = 0.5 / t;
+    q[0] = (m[k][j] - m[j][k]) * t; v[j] = (m[j][i] + m[i][j]) * t; v[k] = (m[k][i] + m[i][k]) * t;
+    q[1] = v[0]; q[2] = v[1]; q[3] = v[2];
+  }
+}
+// warp = (time step, tile of 32 instances), lane = instance; every lane writes its instance's 19 + 13 n_ee values
+template <int kNEE, bool kPhase>
+__global__ void __launch_bounds__(128) TrajectoryKernel(const Plan P, const double* __restrict__ XT, const SplineSample* __restrict__ samples,
+                                                        const int* __restrict__ contact, int n_steps, double* __restrict__ out, int nb) {
+  const int lane = threadIdx.x & 31, ti = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y * 32 + lane;
+  if (ti >= n_steps) return;
+  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const SplineSample* sp = samples + (size_t)ti * (2 + 2 * kNEE);
+  constexpr int K = 19 + 13 * kNEE;
+  double o[K];
+  double th[3], thd[3], thdd[3], unused[3];
+  EvalSpline<2>(P, sp + 0, xs, o, o + 3, o + 6);
+  EvalSpline<2>(P, sp + 1, xs, th, thd, thdd);
+  const Trig tr = MakeTrig(th);
+  double R[3][3]; RotationMatrix(tr, R);
+  QuaternionFromMatrix(R, o + 9);
+  {  // EulerConverter::GetAngularVelocityInWorld / GetAngularAccelerationInWorld (euler_converter.cc:58-83), as in DynamicUnit
+    const double sy = tr.sy, cy = tr.cy, sz = tr.sz, cz = tr.cz, yd = thd[1], zd = thd[2];
+    const double M[3][3] = {{cy * cz, -sz, 0.0}, {cy * sz, cz, 0.0}, {-sy, 0.0, 1.0}};
+    const double Md[3][3] = {{-cz * sy * yd - cy * sz * zd, -cz * zd, 0.0}, {cy * cz * zd - sy * sz * yd, -sz * zd, 0.0}, {-cy * yd, 0.0, 0.0}};
+    o[13] = M[0][0] * thd[0] + M[0][1] * thd[1];
+    o[14] = M[1][0] * thd[0] + M[1][1] * thd[1];
+    o[15] = M[2][0] * thd[0] + thd[2];
+    o[16] = (Md[0][0] * thd[0] + Md[0][1] * thd[1]) + (M[0][0] * thdd[0] + M[0][1] * thdd[1]);
+    o[17] = (Md[1][0] * thd[0] + Md[1][1] * thd[1]) + (M[1][0] * thdd[0] + M[1][1] * thdd[1]);
+    o[18] = (Md[2][0] * thd[0]) + (M[2][0] * thdd[0] + thdd[2]);
+  }
+#pragma unroll
+  for (int e = 0; e < kNEE; ++e) {
+    double* f = o + 19 + 13 * e;
+    EvalSpline<2, kPhase>(P, sp + 2 + e, xs, f + 1, f + 4, f + 7);
+    EvalSpline<0, kPhase>(P, sp + 2 + kNEE + e, xs, f + 10, unused, unused);
+    if (kPhase) {   // PhaseDurations::IsContactPhase (phase_durations.cc:120-124) with this instance's durations
+      const PhaseSplineDef def = P.phase_defs[2 * e];
+      double sum = 0.0;
+      for (int i = 0; i + 1 < def.n_phases; ++i) sum += xs[def.sched0 + i];
+      const double last = def.t_total - sum, tg = __ldg(&sp[2 + e].T);
+      double acc = 0.0; int phase = def.n_phases - 1; bool found = false;
+      for (int ph = 0; ph < def.n_phases; ++ph) {
+        acc += (ph == def.n_phases - 1) ? last : xs[def.sched0 + ph];
+        if (!found && acc >= tg - 1e-10) { found = true; phase = ph; }
+      }
+      const bool first = __ldg(contact + e) != 0;   // contact: in_contact_at_start per foot
+      f[0] = ((phase % 2 == 0) ? first : !first) ? 1.0 : 0.0;
+    } else {
+      f[0] = (double)__ldg(contact + (size_t)ti * kNEE + e);
+    }
+  }
+  if (b < nb) {
+    double* dst = out + ((size_t)b * n_steps + ti) * K;
+#pragma unroll
+    for (int i = 0; i < K; ++i) dst[i] = o[i];
+  }
+}
+
 #if TWB_FUSED
 // One kernel writes a whole tile of rows: blockIdx.y = instance tile, blockIdx.x walks the tile's CTAs in row
 // order — dynamic samples, range-of-motion samples, node groups.
@@ -1090,6 +1162,25 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
 }  // namespace
 
 // ---- host launchers ------------------------------------------------------------------
+
+int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSample* samples, const int* contact, int n_steps,
+                     double* out, int nb, cudaStream_t s) {
+  if (nb <= 0 || n_steps <= 0) return 0;
+  const int tiles = (nb + 31) / 32;
+  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb);
+  const dim3 grid((n_steps + 3) / 4, tiles);
+  const bool phase = P.n_phase_defs > 0;
+#define TWB_TRAJ(NEE) (phase ? TrajectoryKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, contact, n_steps, out, nb) \
+                             : TrajectoryKernel<NEE, false><<<grid, 128, 0, s>>>(P, XT, samples, contact, n_steps, out, nb))
+  switch (P.n_ee) {
+    case 1: TWB_TRAJ(1); break;
+    case 2: TWB_TRAJ(2); break;
+    case 4: TWB_TRAJ(4); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+#undef TWB_TRAJ
+  return (int)cudaGetLastError();
+}
 
 int OutKernelsPerEval(const Plan& P) {
 #if TWB_FUSED

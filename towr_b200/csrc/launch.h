@@ -17,6 +17,10 @@ extern void (*g_after_launch)(const char* label, cudaStream_t stream);
 // tile = 32 consecutive instances), GT is [tiles][m][32] (staging of the constraint values).  x, g, jac, cost, grad, status and terrain_ids point at the first
 // instance.  `flags` are the TWB_EVAL_* bits.  Work is enqueued on `s` and on two auxiliary streams that
 // are forked from / joined back into `s` with ev[0..2].
+// fpowr::GetTrajectory for `nb` instances: x -> XT, then out[b][step][19 + 13 n_ee]; `samples` / `contact` are the device
+// copies of Formulation::TrajectoryTables (contact null when the durations are optimised)
+int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSample* samples, const int* contact, int n_steps,
+                     double* out, int nb, cudaStream_t s);
 // number of output kernels one evaluation launches for this plan
 int OutKernelsPerEval(const Plan& P);
 int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,

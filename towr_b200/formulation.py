@@ -268,6 +268,17 @@ class Batch:
             lib.twb_batch_destroy(self._h)
             self._h = None
 
+    def sample_trajectory(self, x, dt):
+        """fpowr::GetTrajectory for every instance: (B, n_samples, 19 + 13 n_ee) — see include/towr_b200.h."""
+        p = self.problem
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.shape == (self.B, p.n)
+        ns, nv = C.c_int(), C.c_int()
+        check(lib.twb_problem_trajectory_dims(p._h, float(dt), C.byref(ns), C.byref(nv)))
+        out = np.empty((self.B, ns.value, nv.value))
+        check(lib.twb_batch_sample_trajectory_host(self._h, x.ctypes.data_as(C.c_void_p), float(dt), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def set_terrains(self, terrain_ids):
         if terrain_ids is None:
             check(lib.twb_batch_set_terrains(self._h, None))
