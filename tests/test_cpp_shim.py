@@ -20,6 +20,17 @@ def _build():
                            "-o", EXE, "-L" + libdir, "-ltowr_b200", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"])
 
 
+def test_c_abi_from_plain_c99():
+    """include/towr_b200.h is a C header: compile and drive it from C99."""
+    exe = os.path.join(os.path.dirname(EXE), "c_abi_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", os.path.join(ROOT, "tests", "cpp", "c_abi_test.c"), "-o", exe,
+                           "-L" + libdir, "-ltowr_b200", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
 def test_cpp_shim_structure_and_block_slicing():
     _build()
     out = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
