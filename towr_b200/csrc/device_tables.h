@@ -142,7 +142,9 @@ struct RomUnit { int32_t sample0; int32_t pad; OutRange values[kMaxEE]; };
 // Node-wise work of one warp: `count` consecutive units of one kind evaluated into one state block,
 // then one pass over the group's output lists.
 enum NodeKind : int32_t { kGroupForce = 0, kGroupTerrain = 1, kGroupSwing = 2, kGroupAcc = 3, kGroupConst = 4, kGroupBaseMotion = 5 };
-struct NodeGroup { int32_t kind, first, count, pad; OutRange values; };
+// g_row0 >= 0: the group's constraint values are the consecutive rows g_row0 .. g_row0 + g_n - 1 taken from the
+// consecutive state rows g_d0 ..: written without a table (no dependent loads); otherwise the `values` entries are used.
+struct NodeGroup { int32_t kind, first, count, g_row0; OutRange values; int32_t g_d0, g_n; };
 constexpr int kNodeStateRowsMax = 64;   // upper bound of the local state rows of a node group (row 0 = 1); Plan::node_rows is the actual maximum
 
 // NodeCost term (node_cost.cc:53-76) flattened: one entry per node value that
@@ -160,6 +162,7 @@ struct Plan {
   int node_rows, dyn_rows, rom_rows;   // state rows of one unit's block: node groups (largest), dynamic samples, range-of-motion samples
   int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz); nc_g = 1 (constraint values go through GT)
   int dyn_list0, rom_list0, node_list0;   // first entry of cta_lists of the dynamic CTAs, (rom CTA, foot) pairs, node CTAs
+  int rom_row0[kMaxEE];                   // first constraint row of foot e's range-of-motion set (sample k owns rows rom_row0[e] + 3k ..+2)
   // robot
   double mass, gravity;
   double I_b[9];

@@ -527,6 +527,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         const size_t first_rom_phase_unit = tb.phase_units.size() - (optimize_timings ? (size_t)pl.n_rom : 0);
         for (int e = 0; e < n_ee; ++e) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
+          pl.rom_row0[e] = r0;
           for (int k = 0; k < pl.n_rom; ++k) {
             const double t = ts[k]; const int row = r0 + 3 * k;
             const uint32_t sb = 1, sd = 10 + RomBuffer(e), G0 = 19 + RomBuffer(e);
@@ -818,6 +819,11 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) tb.rom[k].values[e] = flush_values(pl.n_dyn + k * n_ee + e);
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     NodeGroup ng{}; ng.kind = groups[gi].kind; ng.first = groups[gi].first; ng.count = groups[gi].count;
+    const auto& vals = values[pl.n_dyn + n_rom_blocks + (int)gi];
+    bool consecutive = !vals.empty();
+    for (size_t i = 1; i < vals.size() && consecutive; ++i)
+      consecutive = vals[i].p.off == vals[0].p.off + (int)i && vals[i].p.d0 == vals[0].p.d0 + (int)i;
+    ng.g_row0 = consecutive ? vals[0].p.off : -1; ng.g_d0 = consecutive ? vals[0].p.d0 : 0; ng.g_n = consecutive ? (int32_t)vals.size() : 0;
     ng.values = flush_values(pl.n_dyn + n_rom_blocks + (int)gi);
     tb.groups.push_back(ng);
   }

@@ -40,6 +40,12 @@ void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // p
 #define TWB_MARK(label, stream) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
 namespace {
 
+#ifndef TWB_PDL
+#define TWB_PDL 1        // >= 1: RomNodeOut is launched with programmatic stream serialization behind TransposeIn (138.9 vs 144.6 us); >= 2: TransposeOut as well (no further gain)
+#endif
+#ifndef TWB_DYN_FIRST
+#define TWB_DYN_FIRST 0  // 1: DynOut is enqueued before RomNodeOut
+#endif
 #if TWB_FUSED
 #ifndef TWB_CTAS
 #define TWB_CTAS 2   // CTAs per SM the fused output kernel is compiled for (bounds its registers)
@@ -537,6 +543,9 @@ __device__ __forceinline__ ConstCol TiledCol(const double* base, int b, int rows
 __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x, double* __restrict__ XT,
                                                    int* __restrict__ status, int n, int nb) {
   __shared__ double tile[32][33];
+#if TWB_PDL
+  asm volatile("griddepcontrol.launch_dependents;");   // the dependent output kernel may become resident while this grid drains
+#endif
   const int i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
   if (status && blockIdx.x == 0 && threadIdx.y == 0 && b0 + threadIdx.x < nb) status[b0 + threadIdx.x] = 0;
 #pragma unroll
@@ -556,6 +565,9 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
 // GT[b/32][r][b%32] -> g[b][r]: 32x32 tiles through shared memory, coalesced on both sides
 __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ GT, double* __restrict__ g, int m, int nb) {
   __shared__ double tile[32][33];
+#if TWB_PDL >= 2
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the preceding output kernel of this stream is complete and its GT rows visible
+#endif
   const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
   const double* src = GT + ((size_t)blockIdx.y * m) * 32;
 #pragma unroll
@@ -668,13 +680,25 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
   const int nc = P.nc_jac, lane = threadIdx.x & 31;
   for (int q = 0; q < nc; ++q) {
     const OutRange rp = LoadRange(&list->pairs[q]);
+    // warp 0 also owns the single elements: their range (and, below, their first 32 entries) is fetched BEFORE the pair
+    // loop, so that the two dependent loads are in flight under the warp's pair stores instead of after them
+    OutRange rs{0, 0};
+    if (threadIdx.x < 32) rs = LoadRange(&list->singles[q]);
+    uint2 raw = make_uint2(0u, 0u); double cs = 0.0;
+    if (lane < rs.count) { raw = __ldg(reinterpret_cast<const uint2*>(P.pairs + rs.first) + lane); cs = __ldg(reinterpret_cast<const double*>(P.coefs + rs.first + lane)); }
     StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, threadIdx.x, blockDim.x);
-    if (threadIdx.x < 32) {
-      const OutRange rs = LoadRange(&list->singles[q]);
+    if (threadIdx.x < 32 && rs.count > 0) {
       const bool active = lane < n_inst && (lane % nc) == q;
       double* o = jac_tile + (size_t)lane * P.nnz;
-      ForEachEntry(P.pairs + rs.first, P.coefs + rs.first, rs.count, lane,
-                   [&](int off, int d, double c) { if (active) StoreOut(o + off, cta_smem[d * kLD + lane] * c); });
+      const int cnt = min(32, rs.count);
+      for (int sidx = 0; sidx < cnt; ++sidx) {
+        const int off = __shfl_sync(0xffffffffu, (int)raw.x, sidx), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), sidx);
+        const double c = __shfl_sync(0xffffffffu, cs, sidx);
+        if (active) StoreOut(o + off, cta_smem[d * kLD + lane] * c);
+      }
+      if (rs.count > 32)
+        ForEachEntry(P.pairs + rs.first + 32, P.coefs + rs.first + 32, rs.count - 32, lane,
+                     [&](int off, int d, double c) { if (active) StoreOut(o + off, cta_smem[d * kLD + lane] * c); });
     }
   }
 }
@@ -749,8 +773,9 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
     EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
     const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
     double D[3][3]; RotVecDerivative<true>(dR, r, D);
+    double ge[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Sk[18 + buf + i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2];
+    for (int i = 0; i < 3; ++i) { ge[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2]; Sk[18 + buf + i] = ge[i]; }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -760,7 +785,15 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
       FlagNonFinite(t, 22 + buf, lane, status, b0 + lane, nb, 10 + buf);
     }
 #endif
-    if (valid && (flags & 1u)) StoreValuesTiled(P, t, &u->values[e], GT + (size_t)b0 * P.m, lane);
+    if (valid && (flags & 1u)) {   // rows rom_row0[e] + 3k .. + 2 (range_of_motion_constraint.cc:58-66), lane = instance into GT
+      double* gt = GT + ((size_t)b0 * P.m + (size_t)(P.rom_row0[e] + 3 * k) * 32) + lane;
+#ifndef TWB_EXP_NOCOMPUTE
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gt[i * 32] = ge[i];
+#else
+      for (int i = 0; i < 3; ++i) gt[i * 32] = t[(19 + buf + i) * kLD + lane];
+#endif
+    }
 #if !TWB_ROM_ALLFEET
     __syncthreads();   // foot e complete in every block; everybody is done reading buffer (e + 1) & 1 (the list of foot e - 1)
     if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst);
@@ -808,7 +841,16 @@ __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict
     }
     FlagNonFinite(t, n_rows, lane, status, b, nb);
 #endif
-    if (flags & 1u) StoreValuesTiled(P, t, &grp->values, GT + (size_t)b0 * P.m, lane);
+    if (flags & 1u) {
+      const int g_row0 = __ldg(&grp->g_row0);
+      if (g_row0 >= 0) {
+        const int d0 = __ldg(&grp->g_d0), gn = __ldg(&grp->g_n);
+        double* gt = GT + ((size_t)b0 * P.m + (size_t)g_row0 * 32) + lane;
+        for (int i = 0; i < gn; ++i) gt[(size_t)i * 32] = t[(d0 + i) * kLD + lane];
+      } else {
+        StoreValuesTiled(P, t, &grp->values, GT + (size_t)b0 * P.m, lane);
+      }
+    }
   }
   __syncthreads();
   if (flags & 2u) StoreCta(P, node_smem, P.cta_lists + P.node_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0));
@@ -1096,9 +1138,17 @@ __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const
                                                                const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
   static_assert(kRomWarps == kNodeWarps, "TWB_ROMNODE needs equal CTA sizes");
+#if TWB_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // XT complete and visible (programmatic dependency on TransposeIn)
+#endif
+#if TWB_PDL >= 2
+  asm volatile("griddepcontrol.launch_dependents;");   // TransposeOut may become resident while this grid drains (it waits for completion itself)
+#endif
   const int n_rom_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps;
   if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+#ifndef TWB_EXP_NONODE   // (timing experiment: node CTAs return at once)
   else NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x - n_rom_ctas, blockIdx.y);
+#endif
 }
 #endif
 #endif
@@ -1124,12 +1174,27 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     const size_t smem = (size_t)kRomWarps * std::max(rom_rows, node_rows) * row_bytes;
     if ((e = cudaFuncSetAttribute(RomNodeOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps;
+#if TWB_DYN_FIRST
+    if (P.n_dyn > 0) {
+      const size_t dsmem = (size_t)kDynWarps * dyn_rows * row_bytes;
+      if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem)) != cudaSuccess) return e;
+      DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, dsmem, a0>>>(P, XT, GT, jac, status, nb, flags);
+      ++*count; TWB_MARK("DynOut", a0);
+    }
+#endif
     if (n_ctas > 0) {
+#if TWB_PDL
+      cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(n_ctas, tiles); cfg.blockDim = dim3(kRomWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+      cudaLaunchAttribute attr{}; attr.id = cudaLaunchAttributeProgrammaticStreamSerialization; attr.val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = &attr; cfg.numAttrs = 1;
+      if ((e = cudaLaunchKernelEx(&cfg, RomNodeOut<kNEE, kPhase>, P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags)) != cudaSuccess) return e;
+#else
       RomNodeOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
+#endif
       ++*count; TWB_MARK("RomNodeOut", s);
     }
   }
-  if (P.n_dyn > 0) {
+  if (P.n_dyn > 0 && !TWB_DYN_FIRST) {
     const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
     if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
@@ -1238,7 +1303,18 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
     }
     ++count; TWB_MARK("PhaseJac", s);
   }
-  if (out_flags & 1u) { TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb); ++count; TWB_MARK("TransposeOut", s); }
+  if (out_flags & 1u) {
+#if TWB_PDL >= 2
+    cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3((P.m + 31) / 32, tiles); cfg.blockDim = dim3(32, 8); cfg.stream = s;
+    cudaLaunchAttribute attr{}; attr.id = cudaLaunchAttributeProgrammaticStreamSerialization; attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    const double* gt_in = GT;
+    if ((e = cudaLaunchKernelEx(&cfg, TransposeOut, gt_in, g, P.m, nb)) != cudaSuccess) return (int)e;
+#else
+    TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb);
+#endif
+    ++count; TWB_MARK("TransposeOut", s);
+  }
   if (launches) *launches += count;
   return (int)cudaGetLastError();
 }
