@@ -41,10 +41,7 @@ void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // p
 namespace {
 
 #ifndef TWB_PDL
-#define TWB_PDL 1        // >= 1: RomNodeOut is launched with programmatic stream serialization behind TransposeIn (138.9 vs 144.6 us); >= 2: TransposeOut as well (no further gain)
-#endif
-#ifndef TWB_DYN_FIRST
-#define TWB_DYN_FIRST 0  // 1: DynOut is enqueued before RomNodeOut
+#define TWB_PDL 1        // 1: RomNodeOut is launched with programmatic stream serialization behind TransposeIn (138.9 vs 144.6 us per step on config 2)
 #endif
 #if TWB_FUSED
 #ifndef TWB_CTAS
@@ -565,9 +562,6 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
 // GT[b/32][r][b%32] -> g[b][r]: 32x32 tiles through shared memory, coalesced on both sides
 __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ GT, double* __restrict__ g, int m, int nb) {
   __shared__ double tile[32][33];
-#if TWB_PDL >= 2
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // the preceding output kernel of this stream is complete and its GT rows visible
-#endif
   const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
   const double* src = GT + ((size_t)blockIdx.y * m) * 32;
 #pragma unroll
@@ -1141,9 +1135,6 @@ __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const
 #if TWB_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");   // XT complete and visible (programmatic dependency on TransposeIn)
 #endif
-#if TWB_PDL >= 2
-  asm volatile("griddepcontrol.launch_dependents;");   // TransposeOut may become resident while this grid drains (it waits for completion itself)
-#endif
   const int n_rom_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps;
   if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
 #ifndef TWB_EXP_NONODE   // (timing experiment: node CTAs return at once)
@@ -1174,14 +1165,6 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     const size_t smem = (size_t)kRomWarps * std::max(rom_rows, node_rows) * row_bytes;
     if ((e = cudaFuncSetAttribute(RomNodeOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps;
-#if TWB_DYN_FIRST
-    if (P.n_dyn > 0) {
-      const size_t dsmem = (size_t)kDynWarps * dyn_rows * row_bytes;
-      if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem)) != cudaSuccess) return e;
-      DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, dsmem, a0>>>(P, XT, GT, jac, status, nb, flags);
-      ++*count; TWB_MARK("DynOut", a0);
-    }
-#endif
     if (n_ctas > 0) {
 #if TWB_PDL
       cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(n_ctas, tiles); cfg.blockDim = dim3(kRomWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1194,7 +1177,7 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
       ++*count; TWB_MARK("RomNodeOut", s);
     }
   }
-  if (P.n_dyn > 0 && !TWB_DYN_FIRST) {
+  if (P.n_dyn > 0) {
     const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
     if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
@@ -1303,18 +1286,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
     }
     ++count; TWB_MARK("PhaseJac", s);
   }
-  if (out_flags & 1u) {
-#if TWB_PDL >= 2
-    cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3((P.m + 31) / 32, tiles); cfg.blockDim = dim3(32, 8); cfg.stream = s;
-    cudaLaunchAttribute attr{}; attr.id = cudaLaunchAttributeProgrammaticStreamSerialization; attr.val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
-    const double* gt_in = GT;
-    if ((e = cudaLaunchKernelEx(&cfg, TransposeOut, gt_in, g, P.m, nb)) != cudaSuccess) return (int)e;
-#else
-    TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb);
-#endif
-    ++count; TWB_MARK("TransposeOut", s);
-  }
+  if (out_flags & 1u) { TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
   return (int)cudaGetLastError();
 }
