@@ -206,6 +206,23 @@ int twb_problem_trajectory_dims(const twb_problem* p, double dt, int* n_samples,
 /* x: host [B][n] (e.g. converged solutions); out: host [B][n_samples][n_values] */
 int twb_batch_sample_trajectory_host(twb_batch* b, const double* x, double dt, double* out);
 
+/* fpowr::ExtractInitialGuess (fpowr/include/fpowr/initial_guess_extractor.h:17-34) for every instance at the caller's
+ * sample times (FootstepPlanGoal::state_sample_times).  Per time 49 doubles: time | state[12] = base lin p, base ang p
+ * (Euler angles), base lin v, base ang v | controls[36] = ee-motion accelerations (3 per foot, 12), joint torques = 0
+ * (12), ee-forces (3 per foot, 12); feet beyond n_ee stay 0 (the reference's layout is sized for four feet).
+ * x: host [B][n]; times: host [n_times]; out: host [B][n_times][49] */
+int twb_batch_initial_guess_host(twb_batch* b, const double* x, const double* times, int n_times, double* out);
+
+/* fpowr::ExtractFootstepPlan (fpowr/include/fpowr/footstep_plan_extractor.h:55-133) for every instance, without the
+ * nearest-plane lookup (boost::geometry over a ROS PlanarTerrain message: stays with the caller, who gets the contact
+ * positions): the trajectory sampled every 0.01 s is scanned for changes of the contact set; the first state and every
+ * change are footstep states.  Per footstep state n_values = 2 + 4 n_ee doubles: t_global | duration (to the next
+ * footstep state; the last one up to time_horizon) | per foot: contact flag 0/1, ee position (3).
+ * max_states = 1 + sum over feet of (phases - 1) bounds the number of footstep states. */
+int twb_problem_footstep_plan_dims(const twb_problem* p, int* max_states, int* n_values);
+/* x: host [B][n]; n_states: host [B]; out: host [B][max_states][n_values] (unused states are 0) */
+int twb_batch_footstep_plan_host(twb_batch* b, const double* x, double time_horizon, int* n_states, double* out);
+
 /* number of kernel launches one twb_batch_eval_device(flags) enqueues */
 int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags);
 

@@ -1574,6 +1574,55 @@ int oracle_trajectory(void* h, const double* x, double dt, double* out) {
   }
   return 0;
 }
+// fpowr::ExtractInitialGuess (fpowr/include/fpowr/initial_guess_extractor.h:17-34) at each of `n_times` sample times
+// (ExtractInitialGuesses, :36-48): out[k] = time | state(12) | controls(36).
+int oracle_initial_guess(void* h, const double* x, const double* times, int n_times, double* out) {
+  Problem* p = static_cast<Problem*>(h);
+  if (p->robot.n_ee > 4) return 1;
+  p->SetVariables(x);
+  for (int k = 0; k < n_times; ++k) {
+    const double t = times[k];
+    double* o = out + (size_t)k * 49;
+    for (int i = 0; i < 49; ++i) o[i] = 0.0;
+    o[0] = t;
+    double* state = o + 1; double* controls = o + 13;
+    State3 lin = p->ctx.base_lin->GetPoint(t), ang = p->ctx.base_ang->GetPoint(t);
+    for (int d = 0; d < 3; ++d) { state[d] = lin.p[d]; state[3 + d] = ang.p[d]; state[6 + d] = lin.v[d]; state[9 + d] = ang.v[d]; }
+    for (int i = 0; i < p->robot.n_ee; ++i) {
+      State3 mo = p->ctx.ee_motion[i]->GetPoint(t);
+      V3 f = p->ctx.ee_force[i]->GetPoint(t).p;
+      for (int d = 0; d < 3; ++d) { controls[i * 3 + d] = mo.a[d]; controls[12 + i * 3 + d] = 0.0; controls[24 + i * 3 + d] = f[d]; }
+    }
+  }
+  return 0;
+}
+// fpowr::ExtractFootstepPlan (fpowr/include/fpowr/footstep_plan_extractor.h:68-133) without the nearest-plane lookup
+// (boost::geometry + ROS message, outside the tree): GetTrajectory(solution, 0.01), the first state and every state whose
+// contact set differs from the previous one (HasEndEffectorContactChanged, :55-66) are footstep states; duration = time
+// to the next footstep state, the last one up to time_horizon.  out[i] = t_global | duration | per foot: contact, ee p.
+int oracle_footstep_plan(void* h, const double* x, double time_horizon, int max_states, int* n_states, double* out) {
+  Problem* p = static_cast<Problem*>(h);
+  const int n_ee = p->robot.n_ee, K = 19 + 13 * n_ee, V = 2 + 4 * n_ee;
+  int n_samples = 0, n_values = 0;
+  oracle_trajectory_dims(h, 0.01, &n_samples, &n_values);
+  std::vector<double> traj((size_t)n_samples * K);
+  oracle_trajectory(h, x, 0.01, traj.data());
+  std::vector<double> t_global; std::vector<int> index;
+  double t = 0.0;
+  for (int k = 0; k < n_samples; ++k, t += 0.01) {
+    bool changed = (k == 0);
+    for (int e = 0; e < n_ee && !changed; ++e) changed = traj[(size_t)k * K + 19 + 13 * e] != traj[(size_t)(k - 1) * K + 19 + 13 * e];
+    if (changed) { t_global.push_back(t); index.push_back(k); }
+  }
+  *n_states = (int)index.size();
+  for (int i = 0; i < (int)index.size() && i < max_states; ++i) {
+    double* o = out + (size_t)i * V; const double* st = traj.data() + (size_t)index[i] * K;
+    o[0] = t_global[i];
+    o[1] = (i + 1 < (int)index.size()) ? (t_global[i + 1] - t_global[i]) : (time_horizon - t_global[i]);
+    for (int e = 0; e < n_ee; ++e) { o[2 + 4 * e] = st[19 + 13 * e]; for (int d = 0; d < 3; ++d) o[3 + 4 * e + d] = st[20 + 13 * e + d]; }
+  }
+  return 0;
+}
 int oracle_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -99,6 +99,25 @@ class Oracle:
         lib().oracle_trajectory(self._h, _p(x), C.c_double(dt), _p(out))
         return out
 
+    def initial_guesses(self, x, times):
+        """fpowr::ExtractInitialGuesses: (n_times, 49) = time | state[12] | controls[36]."""
+        x = np.ascontiguousarray(x, np.float64); times = np.ascontiguousarray(times, np.float64)
+        out = np.empty((times.size, 49))
+        rc = lib().oracle_initial_guess(self._h, _p(x), _p(times), C.c_int(times.size), _p(out))
+        assert rc == 0
+        return out
+
+    def footstep_plan(self, x, time_horizon, max_states=64):
+        """fpowr::ExtractFootstepPlan without the plane lookup: (n_states, 2 + 4 n_ee)."""
+        x = np.ascontiguousarray(x, np.float64)
+        ns, nv = C.c_int(), C.c_int()
+        lib().oracle_trajectory_dims(self._h, C.c_double(0.01), C.byref(ns), C.byref(nv))
+        n_ee = (nv.value - 19) // 13
+        out = np.zeros((max_states, 2 + 4 * n_ee)); count = C.c_int()
+        lib().oracle_footstep_plan(self._h, _p(x), C.c_double(time_horizon), C.c_int(max_states), C.byref(count), _p(out))
+        assert count.value <= max_states
+        return out[:count.value]
+
     def eval(self, x, want_cost=False):
         x = np.ascontiguousarray(x, np.float64)
         g, vals = np.empty(self.m), np.empty(self.nnz)

@@ -338,3 +338,39 @@ def test_trajectory_sampling_matches_oracle():
         n_ee = (got.shape[2] - 19) // 13
         assert np.allclose((got[..., 9:13] ** 2).sum(-1), 1.0, atol=1e-12)          # unit quaternions
         assert set(np.unique(got[..., [19 + 13 * e for e in range(n_ee)]])) <= {0.0, 1.0}
+
+
+def test_initial_guess_extraction_matches_oracle():
+    """fpowr::ExtractInitialGuesses (initial_guess_extractor.h:17-48) batched on the device — time | state[12] |
+    controls[36] at caller-given sample times — against the oracle, for fixed and for optimised phase durations."""
+    times = np.array([0.0, 0.013, 0.4, 0.99, 1.0, 1.37, 2.0])
+    for name, B in (("hopper", 5), ("anymal_trot_block", 33), ("biped_walk_stairs", 7), ("hyq_gallop_gap", 12)):
+        spec = tb.make_formulation(name).to_spec(); p = tb.Problem(spec)
+        X = synthetic_iterates(p, B)
+        got = p.batch(B).initial_guesses(X, times)
+        o = oracle_lib.Oracle(spec)
+        for b in range(B):
+            ref = o.initial_guesses(X[b], times)
+            scale = np.maximum(1.0, np.abs(ref).max(axis=0, keepdims=True))
+            assert np.all(np.abs(got[b] - ref) <= 1e-12 * np.abs(ref) + 1e-13 * scale), (name, b, np.abs(got[b] - ref).max())
+        assert np.all(got[..., 0] == times) and np.all(got[..., 25:37] == 0.0)      # joint torques are zero
+
+
+def test_footstep_plan_extraction_matches_oracle():
+    """fpowr::ExtractFootstepPlan (footstep_plan_extractor.h:55-133, without the nearest-plane lookup): contact-change
+    scan of the 0.01 s trajectory — footstep times and contact sets identical, durations and positions within 1e-12."""
+    for name, B in (("hopper", 5), ("anymal_trot_block", 33), ("hyq_gallop_gap", 12)):
+        spec = tb.make_formulation(name).to_spec(); p = tb.Problem(spec)
+        X = synthetic_iterates(p, B)
+        T = 2.0
+        plans = p.batch(B).footstep_plans(X, T)
+        o = oracle_lib.Oracle(spec)
+        for b in range(B):
+            ref = o.footstep_plan(X[b], T)
+            got = plans[b]
+            assert got.shape == ref.shape and got.shape[0] >= 2, (name, b, got.shape, ref.shape)
+            n_ee = (got.shape[1] - 2) // 4
+            flags = [2 + 4 * e for e in range(n_ee)]
+            assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, flags], ref[:, flags])
+            assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref) + 1e-13), (name, b, np.abs(got - ref).max())
+            assert abs(got[:, 1].sum() - T) < 1e-9                                     # durations tile the horizon

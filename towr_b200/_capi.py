@@ -87,6 +87,9 @@ def _load():
         "twb_batch_eval_host": (C.c_int, [P, P, P, P, P, P, P, C.c_uint]),
         "twb_problem_trajectory_dims": (C.c_int, [P, C.c_double, I, I]),
         "twb_batch_sample_trajectory_host": (C.c_int, [P, P, C.c_double, P]),
+        "twb_batch_initial_guess_host": (C.c_int, [P, P, P, C.c_int, P]),
+        "twb_problem_footstep_plan_dims": (C.c_int, [P, I, I]),
+        "twb_batch_footstep_plan_host": (C.c_int, [P, P, C.c_double, P, P]),
         "twb_batch_launches_per_eval": (C.c_int, [P, C.c_uint]),
         "twb_last_error": (C.c_char_p, []),
         "twb_version": (C.c_char_p, []),

@@ -286,6 +286,83 @@ int twb_batch_sample_trajectory_host(twb_batch* b, const double* x, double dt, d
   return TWB_OK;
 }
 
+int twb_batch_initial_guess_host(twb_batch* b, const double* x, const double* times, int n_times, double* out) {
+  if (!b || !x || !times || !out || n_times <= 0) return Fail(TWB_ERR_INVALID, "null argument");
+  const twb::Formulation& f = b->prob->f;
+  if (f.spec.n_ee > 4) return Fail(TWB_ERR_UNSUPPORTED, "the initial-guess layout holds at most 4 feet");
+  std::vector<double> at(times, times + n_times); std::vector<twb::SplineSample> samples; std::vector<int> contact;
+  int rc = f.SampleTables(at, &samples, &contact);
+  if (rc != TWB_OK) return Fail(rc, "bad sample times");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  const size_t B = b->B;
+  twb::SplineSample* d_samples = nullptr; double* d_times = nullptr; double* d_out = nullptr;
+  auto cleanup = [&] { cudaFree(d_samples); cudaFree(d_times); cudaFree(d_out); };
+  if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_times), sizeof(double) * n_times)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(double) * B * n_times * 49)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  cudaStream_t s = b->stream;
+  cudaMemcpyAsync(d_samples, samples.data(), sizeof(twb::SplineSample) * samples.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_times, times, sizeof(double) * n_times, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(b->d_x, x, sizeof(double) * B * f.n, cudaMemcpyHostToDevice, s);
+  rc = twb::LaunchInitialGuess(b->plan, b->d_x, b->d_XT, d_samples, d_times, n_times, d_out, b->B, s);
+  if (rc == 0) cudaMemcpyAsync(out, d_out, sizeof(double) * B * n_times * 49, cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "initial-guess kernel launch");
+  if (e != cudaSuccess) return CudaFail(e, "initial-guess sampling");
+  return TWB_OK;
+}
+
+int twb_problem_footstep_plan_dims(const twb_problem* p, int* max_states, int* n_values) {
+  if (!p) return Fail(TWB_ERR_INVALID, "null problem");
+  int changes = 0;
+  for (int e = 0; e < p->f.spec.n_ee; ++e) changes += p->f.spec.n_phases[e] - 1;
+  if (max_states) *max_states = 1 + changes;   // the first state + at most one footstep state per phase change of a foot
+  if (n_values) *n_values = 2 + 4 * p->f.spec.n_ee;
+  return TWB_OK;
+}
+
+int twb_batch_footstep_plan_host(twb_batch* b, const double* x, double time_horizon, int* n_states, double* out) {
+  if (!b || !x || !n_states || !out) return Fail(TWB_ERR_INVALID, "null argument");
+  const twb::Formulation& f = b->prob->f;
+  const double dt = 0.01;   // footstep_plan_extractor.h:87
+  std::vector<double> times; std::vector<twb::SplineSample> samples; std::vector<int> contact;
+  int rc = f.TrajectoryTables(dt, &times, &samples, &contact);
+  if (rc != TWB_OK) return Fail(rc, "trajectory tables");
+  if (f.optimize_timings) { contact.clear(); for (int e = 0; e < f.spec.n_ee; ++e) contact.push_back(f.spec.in_contact_at_start[e] != 0); }
+  int max_states = 0, V = 0;
+  twb_problem_footstep_plan_dims(b->prob, &max_states, &V);
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  const size_t B = b->B, K = 19 + 13 * (size_t)f.spec.n_ee, n_steps = times.size();
+  twb::SplineSample* d_samples = nullptr; int* d_contact = nullptr; double* d_traj = nullptr; double* d_out = nullptr; int* d_count = nullptr;
+  auto cleanup = [&] { cudaFree(d_samples); cudaFree(d_contact); cudaFree(d_traj); cudaFree(d_out); cudaFree(d_count); };
+  if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_contact), sizeof(int) * contact.size())) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_traj), sizeof(double) * B * n_steps * K)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(double) * B * max_states * V)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_count), sizeof(int) * B)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  cudaStream_t s = b->stream;
+  cudaMemcpyAsync(d_samples, samples.data(), sizeof(twb::SplineSample) * samples.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_contact, contact.data(), sizeof(int) * contact.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(b->d_x, x, sizeof(double) * B * f.n, cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(d_out, 0, sizeof(double) * B * max_states * V, s);
+  rc = twb::LaunchTrajectory(b->plan, b->d_x, b->d_XT, d_samples, d_contact, (int)n_steps, d_traj, b->B, s);
+  if (rc == 0) rc = twb::LaunchFootstepScan(d_traj, (int)n_steps, f.spec.n_ee, dt, time_horizon, max_states, d_count, d_out, b->B, s);
+  if (rc == 0) {
+    cudaMemcpyAsync(out, d_out, sizeof(double) * B * max_states * V, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(n_states, d_count, sizeof(int) * B, cudaMemcpyDeviceToHost, s);
+  }
+  e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "footstep-plan kernel launch");
+  if (e != cudaSuccess) return CudaFail(e, "footstep-plan extraction");
+  return TWB_OK;
+}
+
 int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   if (!b) return 0;
   const twb::Plan& p = b->plan;

@@ -260,12 +260,19 @@ struct SetsHolder { std::vector<NodeSet> sets; RobotConst robot; double T = 0.0;
 
 int Formulation::TrajectoryTables(double dt, std::vector<double>* times, std::vector<SplineSample>* samples, std::vector<int>* contact) const {
   if (!holder || !(dt > 0.0)) return TWB_ERR_INVALID;
-  const std::vector<NodeSet>& sets = holder->sets;
-  const int n_ee = spec.n_ee, zero_slot = n;
   // Spline::GetTotalTime of the base spline (sum of its polynomial durations), then t += dt while t <= T + 1e-5
   double T = 0.0; for (double d : holder->base_T) T += d;
-  times->clear(); samples->clear(); contact->clear();
+  times->clear();
   for (double t = 0.0; t <= T + 1e-5; t += dt) times->push_back(t);
+  return SampleTables(*times, samples, contact);
+}
+
+int Formulation::SampleTables(const std::vector<double>& at, std::vector<SplineSample>* samples, std::vector<int>* contact) const {
+  if (!holder) return TWB_ERR_INVALID;
+  const std::vector<double>* times = &at;
+  const std::vector<NodeSet>& sets = holder->sets;
+  const int n_ee = spec.n_ee, zero_slot = n;
+  samples->clear(); contact->clear();
   auto poly_durations = [&](const NodeSet& s, int e) {
     std::vector<double> d; for (auto& p : s.poly) d.push_back(spec.phase_durations[e][p.phase] / p.n_in_phase); return d;
   };

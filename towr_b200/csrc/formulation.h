@@ -63,6 +63,8 @@ class Formulation {
   // time grid and spline samples of fpowr::GetTrajectory(dt): per time step 2 + 2 n_ee samples (base-lin, base-ang,
   // ee-motion.., ee-force..); contact[step][foot] (fixed durations) or empty (durations optimised: per instance on the device)
   int TrajectoryTables(double dt, std::vector<double>* times, std::vector<SplineSample>* samples, std::vector<int>* contact) const;
+  // the same tables at caller-given times (fpowr::ExtractInitialGuess)
+  int SampleTables(const std::vector<double>& times, std::vector<SplineSample>* samples, std::vector<int>* contact) const;
   int GoalInstance(const double final_lin_pos[3], const double final_ang_pos[3], double* x0, double* x_lower, double* x_upper) const;
 
   int n = 0, m = 0, nnz = 0;

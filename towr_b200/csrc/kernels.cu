@@ -1090,6 +1090,68 @@ __global__ void __launch_bounds__(128) TrajectoryKernel(const Plan P, const doub
   }
 }
 
+// fpowr::ExtractInitialGuess (initial_guess_extractor.h:17-34) at caller-given times: per sample 49 doubles —
+// time | state: base lin p, base ang p (Euler angles), base lin v, base ang v (12) | controls: ee-motion accelerations
+// (12), joint torques = 0 (12), ee-forces (12); feet beyond n_ee stay 0.  warp = (time, tile), lane = instance.
+template <int kNEE, bool kPhase>
+__global__ void __launch_bounds__(128) InitialGuessKernel(const Plan P, const double* __restrict__ XT, const SplineSample* __restrict__ samples,
+                                                          const double* __restrict__ times, int n_times, double* __restrict__ out, int nb) {
+  const int lane = threadIdx.x & 31, ti = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y * 32 + lane;
+  if (ti >= n_times) return;
+  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const SplineSample* sp = samples + (size_t)ti * (2 + 2 * kNEE);
+  double o[49];
+#pragma unroll
+  for (int i = 0; i < 49; ++i) o[i] = 0.0;
+  o[0] = __ldg(times + ti);
+  double unused[3];
+  EvalSpline<2>(P, sp + 0, xs, o + 1, o + 7, unused);
+  EvalSpline<2>(P, sp + 1, xs, o + 4, o + 10, unused);
+#pragma unroll
+  for (int e = 0; e < kNEE; ++e) {
+    double pos[3];
+    EvalSpline<1, kPhase>(P, sp + 2 + e, xs, pos, unused, o + 13 + 3 * e);
+    EvalSpline<0, kPhase>(P, sp + 2 + kNEE + e, xs, o + 13 + 24 + 3 * e, unused, unused);
+  }
+  if (b < nb) {
+    double* dst = out + ((size_t)b * n_times + ti) * 49;
+#pragma unroll
+    for (int i = 0; i < 49; ++i) dst[i] = o[i];
+  }
+}
+
+// fpowr::ExtractFootstepPlan (footstep_plan_extractor.h:68-133) without the nearest-plane lookup: the trajectory of
+// fpowr::GetTrajectory(dt) is scanned for changes of the contact set (HasEndEffectorContactChanged, :55-66); every change
+// (and the first state) is a footstep state.  Per footstep state 2 + 4 n_ee doubles: t_global | duration (time to the next
+// footstep state, the last one up to time_horizon) | per foot: contact flag, ee position.  One thread per instance.
+__global__ void __launch_bounds__(128) FootstepKernel(const double* __restrict__ traj, int n_steps, int n_ee, double dt, double time_horizon,
+                                                      int max_states, int* __restrict__ n_states, double* __restrict__ out, int nb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int K = 19 + 13 * n_ee, V = 2 + 4 * n_ee;
+  const double* tr = traj + (size_t)b * n_steps * K;
+  double* o = out + (size_t)b * max_states * V;
+  int count = 0; double t = 0.0;
+  for (int k = 0; k < n_steps; ++k, t += dt) {   // t accumulates like the reference's loop (t += dt)
+    const double* cur = tr + (size_t)k * K;
+    bool changed = (k == 0);
+    for (int e = 0; e < n_ee && !changed; ++e) changed = cur[19 + 13 * e] != cur[19 + 13 * e - K];
+    if (!changed) continue;
+    if (count > 0 && count <= max_states) o[(size_t)(count - 1) * V + 1] = t - o[(size_t)(count - 1) * V];
+    if (count < max_states) {
+      double* s = o + (size_t)count * V;
+      s[0] = t; s[1] = 0.0;
+      for (int e = 0; e < n_ee; ++e) {
+        s[2 + 4 * e] = cur[19 + 13 * e];
+        for (int d = 0; d < 3; ++d) s[3 + 4 * e + d] = cur[20 + 13 * e + d];
+      }
+    }
+    ++count;
+  }
+  if (count > 0 && count <= max_states) o[(size_t)(count - 1) * V + 1] = time_horizon - o[(size_t)(count - 1) * V];
+  n_states[b] = count;
+}
+
 #if TWB_FUSED
 // One kernel writes a whole tile of rows: blockIdx.y = instance tile, blockIdx.x walks the tile's CTAs in row
 // order — dynamic samples, range-of-motion samples, node groups.
@@ -1227,6 +1289,32 @@ int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSam
     default: return (int)cudaErrorInvalidValue;
   }
 #undef TWB_TRAJ
+  return (int)cudaGetLastError();
+}
+
+int LaunchInitialGuess(const Plan& P, const double* x, double* XT, const SplineSample* samples, const double* times, int n_times,
+                       double* out, int nb, cudaStream_t s) {
+  if (nb <= 0 || n_times <= 0) return 0;
+  const int tiles = (nb + 31) / 32;
+  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb);
+  const dim3 grid((n_times + 3) / 4, tiles);
+  const bool phase = P.n_phase_defs > 0;
+#define TWB_IG(NEE) (phase ? InitialGuessKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, times, n_times, out, nb) \
+                           : InitialGuessKernel<NEE, false><<<grid, 128, 0, s>>>(P, XT, samples, times, n_times, out, nb))
+  switch (P.n_ee) {
+    case 1: TWB_IG(1); break;
+    case 2: TWB_IG(2); break;
+    case 4: TWB_IG(4); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+#undef TWB_IG
+  return (int)cudaGetLastError();
+}
+
+int LaunchFootstepScan(const double* traj, int n_steps, int n_ee, double dt, double time_horizon, int max_states, int* n_states,
+                       double* out, int nb, cudaStream_t s) {
+  if (nb <= 0) return 0;
+  FootstepKernel<<<(nb + 127) / 128, 128, 0, s>>>(traj, n_steps, n_ee, dt, time_horizon, max_states, n_states, out, nb);
   return (int)cudaGetLastError();
 }
 

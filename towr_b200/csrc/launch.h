@@ -21,6 +21,13 @@ extern void (*g_after_launch)(const char* label, cudaStream_t stream);
 // copies of Formulation::TrajectoryTables (contact null when the durations are optimised)
 int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSample* samples, const int* contact, int n_steps,
                      double* out, int nb, cudaStream_t s);
+// fpowr::ExtractInitialGuess at `n_times` caller-given times: x -> XT, then out[b][time][49]; `samples` as for the trajectory
+int LaunchInitialGuess(const Plan& P, const double* x, double* XT, const SplineSample* samples, const double* times, int n_times,
+                       double* out, int nb, cudaStream_t s);
+// contact-change scan of a sampled trajectory (fpowr::ExtractFootstepPlan): traj[b][n_steps][19 + 13 n_ee] ->
+// out[b][max_states][2 + 4 n_ee], n_states[b]
+int LaunchFootstepScan(const double* traj, int n_steps, int n_ee, double dt, double time_horizon, int max_states, int* n_states,
+                       double* out, int nb, cudaStream_t s);
 // number of output kernels one evaluation launches for this plan
 int OutKernelsPerEval(const Plan& P);
 int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,

@@ -279,6 +279,32 @@ class Batch:
         check(lib.twb_batch_sample_trajectory_host(self._h, x.ctypes.data_as(C.c_void_p), float(dt), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def initial_guesses(self, x, times):
+        """fpowr::ExtractInitialGuesses for every instance: (B, n_times, 49) = time | state[12] | controls[36]."""
+        p = self.problem
+        x = np.ascontiguousarray(x, np.float64)
+        times = np.ascontiguousarray(times, np.float64)
+        assert x.shape == (self.B, p.n)
+        out = np.empty((self.B, times.size, 49))
+        check(lib.twb_batch_initial_guess_host(self._h, x.ctypes.data_as(C.c_void_p), times.ctypes.data_as(C.c_void_p),
+                                               int(times.size), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def footstep_plans(self, x, time_horizon):
+        """fpowr::ExtractFootstepPlan for every instance (without the nearest-plane lookup): list of (n_states_b,
+        2 + 4 n_ee) arrays — t_global | duration | per foot: contact flag, ee position."""
+        p = self.problem
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.shape == (self.B, p.n)
+        ms, nv = C.c_int(), C.c_int()
+        check(lib.twb_problem_footstep_plan_dims(p._h, C.byref(ms), C.byref(nv)))
+        out = np.empty((self.B, ms.value, nv.value))
+        count = np.empty(self.B, np.int32)
+        check(lib.twb_batch_footstep_plan_host(self._h, x.ctypes.data_as(C.c_void_p), float(time_horizon),
+                                               count.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        assert count.max() <= ms.value
+        return [out[b, :count[b]] for b in range(self.B)]
+
     def set_terrains(self, terrain_ids):
         if terrain_ids is None:
             check(lib.twb_batch_set_terrains(self._h, None))
