@@ -40,6 +40,12 @@ void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // p
 #define TWB_MARK(label, stream) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
 namespace {
 
+#ifndef TWB_TOUT_LD
+#define TWB_TOUT_LD 0    // cache operator of TransposeOut's loads of GT: 0 .cs, 1 .cg, 2 default, 3 .lu
+#endif
+#ifndef TWB_DISCARD
+#define TWB_DISCARD 1    // TransposeOut drops the dead L2 lines of GT and XT (discard.global.L2) instead of letting them be written back
+#endif
 #ifndef TWB_PDL
 #define TWB_PDL 1        // 1: RomNodeOut is launched with programmatic stream serialization behind TransposeIn (138.9 vs 144.6 us per step on config 2)
 #endif
@@ -560,16 +566,41 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
 }
 
 // GT[b/32][r][b%32] -> g[b][r]: 32x32 tiles through shared memory, coalesced on both sides
-__global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ GT, double* __restrict__ g, int m, int nb) {
+// TWB_DISCARD: GT is dead once it has been read, and so is XT (rows 0 .. n-1; row n is the permanent zero row) — both
+// are still dirty in the L2; `discard.global.L2` drops the lines instead of writing them back to HBM (50 MB per step
+// on config 2, 9 % of the step's DRAM writes).  Both matrices are rewritten by the next evaluation before they are read.
+__device__ __forceinline__ void DiscardLine(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
+__global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ GT, double* __restrict__ g, int m, int nb,
+                                                    const double* __restrict__ XT, int n) {
   __shared__ double tile[32][33];
   const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
   const double* src = GT + ((size_t)blockIdx.y * m) * 32;
 #pragma unroll
   for (int q = threadIdx.y; q < 32; q += 8) {
     const int r = r0 + q;
+#if TWB_TOUT_LD == 1
+    if (r < m) tile[q][threadIdx.x] = __ldcg(src + (size_t)r * 32 + threadIdx.x);
+#elif TWB_TOUT_LD == 2
+    if (r < m) tile[q][threadIdx.x] = src[(size_t)r * 32 + threadIdx.x];
+#elif TWB_TOUT_LD == 3
+    if (r < m) tile[q][threadIdx.x] = __ldlu(src + (size_t)r * 32 + threadIdx.x);
+#else
     if (r < m) tile[q][threadIdx.x] = __ldcs(src + (size_t)r * 32 + threadIdx.x);
+#endif
   }
   __syncthreads();
+#if TWB_DISCARD
+  {
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 64) {                       // the 32 GT rows of this CTA: two 128-byte lines each
+      const int r = r0 + (tid >> 1);
+      if (r < m) DiscardLine(src + (size_t)r * 32 + (tid & 1) * 16);
+    } else if (XT && tid < 128) {         // XT rows of this tile, 32 per CTA of the tile (CTAs wrap around when m < n)
+      const double* xt = XT + ((size_t)blockIdx.y * (n + 1)) * 32;
+      for (int r = r0 + ((tid - 64) >> 1); r < n; r += gridDim.x * 32) DiscardLine(xt + (size_t)r * 32 + (tid & 1) * 16);
+    }
+  }
+#endif
 #pragma unroll
   for (int q = threadIdx.y; q < 32; q += 8) {
     const int b = b0 + q, r = r0 + threadIdx.x;
@@ -1374,7 +1405,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
     }
     ++count; TWB_MARK("PhaseJac", s);
   }
-  if (out_flags & 1u) { TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb); ++count; TWB_MARK("TransposeOut", s); }
+  if (out_flags & 1u) { TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb, XT, P.n); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
   return (int)cudaGetLastError();
 }
