@@ -184,6 +184,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU runs: pin this rank's host threads to the CPUs next to its GPU (NVML's CPU affinity mask), so that the
+    pinned host buffers of the end-to-end leg are first-touched on the GPU's NUMA node and the D2H copies of the ranks do
+    not all cross one socket link.  Returns the number of CPUs bound to (0: left alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_cuda(args):
     import numpy as np
     import torch
@@ -197,6 +217,7 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device (towr_b200 has no CPU evaluation path; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("TWB_NO_NUMA_BIND") else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tb, spec, p = make_problem()
@@ -333,7 +354,8 @@ def run_cuda(args):
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{cpu_sample} evaluations of instances of the same batch, OpenMP over instances, {cpu_dt:.1f} s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "twb_batch_eval_host (pinned host buffers)"},
+                    "steps": e2e_steps, "api": "twb_batch_eval_host (pinned host buffers)",
+                    "host_cpus_bound_per_rank": numa_cpus},
             "gpu_launches": args.steps * batch.launches_per_eval(flags),
             "clocks": sampler.summary() if sampler else None,
         }
