@@ -168,3 +168,48 @@ def test_csv_grid_terrain_of_the_oracle():
         assert tuple(got) == tuple(float(v) for v in want), (x, y, got, want)
         hit += (want[1] != 0.0) or (want[2] != 0.0)
     assert hit > 5                               # the edge-slope branches were exercised
+
+
+def _quat_from_euler_zyx(roll, pitch, yaw):
+    """Independent check: quaternion (w, x, y, z) of R = Rz(yaw) Ry(pitch) Rx(roll)."""
+    cr, sr, cp, sp, cy, sy = np.cos(roll / 2), np.sin(roll / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(yaw / 2), np.sin(yaw / 2)
+    return np.array([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy])
+
+
+@pytest.mark.parametrize("name", ["hopper", "anymal_trot_block", "hyq_gallop_gap"])
+def test_oracle_initial_guess_is_consistent_with_trajectory(name):
+    """fpowr::ExtractInitialGuess (initial_guess_extractor.h:17-34) restated by the oracle: the state / controls entries
+    are the same spline points fpowr::GetTrajectory samples; the Euler angles reproduce the trajectory's quaternion."""
+    spec = tb.make_formulation(name).to_spec(); p = tb.Problem(spec); o = oracle_lib.Oracle(spec)
+    x = synthetic_iterates(p, 1, seed=3)[0]
+    dt = 0.25
+    tr = o.trajectory(x, dt)
+    times = np.arange(tr.shape[0]) * dt
+    ig = o.initial_guesses(x, times)
+    n_ee = (tr.shape[1] - 19) // 13
+    assert np.array_equal(ig[:, 0], times)
+    assert np.allclose(ig[:, 1:4], tr[:, 0:3], rtol=0, atol=1e-13) and np.allclose(ig[:, 7:10], tr[:, 3:6], rtol=0, atol=1e-13)
+    for k in range(len(times)):
+        q = _quat_from_euler_zyx(*ig[k, 4:7])
+        assert min(np.abs(q - tr[k, 9:13]).max(), np.abs(q + tr[k, 9:13]).max()) < 1e-12
+    for e in range(n_ee):
+        assert np.allclose(ig[:, 13 + 3 * e:16 + 3 * e], tr[:, 19 + 13 * e + 7:19 + 13 * e + 10], rtol=0, atol=1e-12)   # ee acceleration
+        assert np.allclose(ig[:, 37 + 3 * e:40 + 3 * e], tr[:, 19 + 13 * e + 10:19 + 13 * e + 13], rtol=0, atol=1e-12)  # ee force
+    assert np.all(ig[:, 25:37] == 0.0) and np.all(ig[:, 13 + 3 * n_ee:25] == 0.0)
+
+
+def test_oracle_footstep_plan_of_the_hopper():
+    """fpowr::ExtractFootstepPlan (footstep_plan_extractor.h:68-133) on hopper_example's gait (phases 0.4 0.2 0.4 0.2 0.4
+    0.2 0.2, in contact at the start): a phase boundary belongs to the ending phase (Spline::GetSegmentID), so every
+    contact change shows up at the first 0.01 s sample after it; durations tile the horizon."""
+    spec = tb.make_formulation("hopper").to_spec(); p = tb.Problem(spec); o = oracle_lib.Oracle(spec)
+    x0 = p.GetVariableValues()
+    plan = o.footstep_plan(x0, 2.0)
+    assert plan.shape == (7, 6)
+    assert np.allclose(plan[:, 0], [0.0, 0.41, 0.61, 1.01, 1.21, 1.61, 1.81], rtol=0, atol=1e-9)
+    assert list(plan[:, 2]) == [1.0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0]
+    assert abs(plan[:, 1].sum() - 2.0) < 1e-12 and np.allclose(plan[:-1, 1], np.diff(plan[:, 0]), rtol=0, atol=1e-15)
+    tr = o.trajectory(x0, 0.01)
+    for row in plan:                                   # positions are those of the trajectory sample at t_global
+        k = int(round(row[0] / 0.01))
+        assert np.array_equal(row[3:6], tr[k, 20:23])
