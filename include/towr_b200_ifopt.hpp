@@ -110,6 +110,37 @@ class BatchedProblem {
     if (!batch_) throw std::runtime_error("BatchedProblem: no device batch");
     Check(twb_batch_eval_host(batch_, X.data(), G.data(), JAC.data(), COST.data(), GRAD.data(), STATUS.data(), flags), "twb_batch_eval_host");
   }
+  // ---- solution post-processing of the current X (fpowr) ----
+  // fpowr::GetTrajectory(solution, dt) for every instance: [B][n_samples][19 + 13 n_ee]
+  std::vector<double> SampleTrajectory(double dt, int* n_samples = nullptr, int* n_values = nullptr) {
+    if (!batch_) throw std::runtime_error("BatchedProblem: no device batch");
+    int ns = 0, nv = 0;
+    Check(twb_problem_trajectory_dims(prob_, dt, &ns, &nv), "twb_problem_trajectory_dims");
+    std::vector<double> out((size_t)B_ * ns * nv);
+    Check(twb_batch_sample_trajectory_host(batch_, X.data(), dt, out.data()), "twb_batch_sample_trajectory_host");
+    if (n_samples) *n_samples = ns;
+    if (n_values) *n_values = nv;
+    return out;
+  }
+  // fpowr::ExtractInitialGuesses at the given sample times: [B][times.size()][49] = time | state[12] | controls[36]
+  std::vector<double> ExtractInitialGuesses(const std::vector<double>& times) {
+    if (!batch_) throw std::runtime_error("BatchedProblem: no device batch");
+    std::vector<double> out((size_t)B_ * times.size() * 49);
+    Check(twb_batch_initial_guess_host(batch_, X.data(), times.data(), (int)times.size(), out.data()), "twb_batch_initial_guess_host");
+    return out;
+  }
+  // fpowr::ExtractFootstepPlan without the plane lookup: [B][max_states][2 + 4 n_ee], n_states[b] footstep states each
+  std::vector<double> ExtractFootstepPlans(double time_horizon, std::vector<int>* n_states, int* max_states = nullptr, int* n_values = nullptr) {
+    if (!batch_) throw std::runtime_error("BatchedProblem: no device batch");
+    int ms = 0, nv = 0;
+    Check(twb_problem_footstep_plan_dims(prob_, &ms, &nv), "twb_problem_footstep_plan_dims");
+    std::vector<double> out((size_t)B_ * ms * nv);
+    n_states->assign(B_, 0);
+    Check(twb_batch_footstep_plan_host(batch_, X.data(), time_horizon, n_states->data(), out.data()), "twb_batch_footstep_plan_host");
+    if (max_states) *max_states = ms;
+    if (n_values) *n_values = nv;
+    return out;
+  }
   int GetNumberOfOptimizationVariables() const { return n_; }
   int GetNumberOfConstraints() const { return m_; }
   int nnz() const { return nnz_; }

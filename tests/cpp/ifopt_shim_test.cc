@@ -68,6 +68,18 @@ int main(int argc, char** argv) {
   if (gpu) {
     double g_sum = 0.0; for (double v : cons[1]->GetValues()) g_sum += v;
     std::printf("dynamic_g_sum %.17g\njac_sum %.17g\ncost %.17g\nstatus %d\n", g_sum, csr_sum, costs[0]->GetValues()[0], nlp.STATUS[b]);
+    // post-processing of the current X (fpowr): footstep plan of the hopper gait, initial guesses at two times
+    std::vector<int> n_states; int max_states = 0, nv = 0;
+    std::vector<double> plans = nlp.ExtractFootstepPlans(2.0, &n_states, &max_states, &nv);
+    REQUIRE(nv == 6 && n_states[b] == 7 && max_states >= 7);
+    double dur = 0.0; for (int i = 0; i < n_states[b]; ++i) dur += plans[((size_t)b * max_states + i) * nv + 1];
+    REQUIRE(std::fabs(dur - 2.0) < 1e-12);
+    std::vector<double> ig = nlp.ExtractInitialGuesses({0.0, 1.0});
+    REQUIRE(ig.size() == (size_t)B * 2 * 49 && ig[((size_t)b * 2 + 1) * 49] == 1.0);
+    int ns = 0, nvt = 0;
+    std::vector<double> traj = nlp.SampleTrajectory(0.5, &ns, &nvt);
+    REQUIRE(ns == 5 && nvt == 32 && std::fabs(traj[((size_t)b * ns + 2) * nvt + 0] - ig[((size_t)b * 2 + 1) * 49 + 1]) < 1e-13);   // base x at t = 1
+    std::printf("footstep_states %d\n", n_states[b]);
   }
   std::printf("ok\n");
   return 0;
