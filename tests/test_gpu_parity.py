@@ -1,6 +1,8 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the
 CPU oracle on the same seeded inputs; plus size-independent properties at the
 full BASELINE batch sizes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -374,3 +376,20 @@ def test_footstep_plan_extraction_matches_oracle():
             assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, flags], ref[:, flags])
             assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref) + 1e-13), (name, b, np.abs(got - ref).max())
             assert abs(got[:, 1].sum() - T) < 1e-9                                     # durations tile the horizon
+
+
+def test_postprocessing_matches_golden_fixtures():
+    """The batched CUDA post-processing against the committed fixtures (tests/golden/postproc_golden.npz): trajectory,
+    initial guesses, footstep plan of one seeded iterate, replicated over a batch with a ragged last tile."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "postproc_golden.npz"))
+    for name in ("hopper", "hyq_gallop_gap"):
+        p = tb.Problem(tb.make_formulation(name).to_spec())
+        B = 35
+        X = np.tile(z[f"{name}_x"], (B, 1))
+        bt = p.batch(B)
+        traj = bt.sample_trajectory(X, float(z["dt"])); ig = bt.initial_guesses(X, z["times"]); plans = bt.footstep_plans(X, float(z["time_horizon"]))
+        for b in (0, 31, 34):
+            for got, ref in ((traj[b], z[f"{name}_trajectory"]), (ig[b], z[f"{name}_initial_guesses"]), (plans[b], z[f"{name}_footstep_plan"])):
+                assert got.shape == ref.shape
+                scale = np.maximum(1.0, np.abs(ref).max(axis=0, keepdims=True))
+                assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref) + 1e-13 * scale), (name, b, np.abs(got - ref).max())

@@ -213,3 +213,16 @@ def test_oracle_footstep_plan_of_the_hopper():
     for row in plan:                                   # positions are those of the trajectory sample at t_global
         k = int(round(row[0] / 0.01))
         assert np.array_equal(row[3:6], tr[k, 20:23])
+
+
+def test_postprocessing_golden_fixtures():
+    """fpowr post-processing outputs of the oracle committed under tests/golden/postproc_golden.npz (scripts/make_golden.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "postproc_golden.npz"))
+    for name in ("hopper", "hyq_gallop_gap"):
+        spec = tb.make_formulation(name).to_spec(); o = oracle_lib.Oracle(spec); p = tb.Problem(spec)
+        x = synthetic_iterates(p, 1, seed=int(z["seed"]))[0]
+        assert np.array_equal(x, z[f"{name}_x"])
+        assert np.allclose(o.trajectory(x, float(z["dt"])), z[f"{name}_trajectory"], rtol=1e-13, atol=1e-13)
+        assert np.allclose(o.initial_guesses(x, z["times"]), z[f"{name}_initial_guesses"], rtol=1e-13, atol=1e-13)
+        plan = o.footstep_plan(x, float(z["time_horizon"]))
+        assert plan.shape == z[f"{name}_footstep_plan"].shape and np.allclose(plan, z[f"{name}_footstep_plan"], rtol=1e-13, atol=1e-13)
