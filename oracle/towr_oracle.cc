@@ -190,10 +190,12 @@ struct CsvGrid {
   std::vector<double> h; int rows = 0, cols = 0;
   const double res = 0.17;        // res_m_p_cell_, :113
   const double eps = 0.17 / 50;   // eps_, :114
-  // static_cast<size_t>(x / res) of a negative x is a huge cell index in practice: "outside the grid"
+  // static_cast<size_t>(x / res), :31-32: the conversion truncates toward zero, so a quotient in (-1, 0) is cell 0 (defined
+  // behaviour, INSIDE the grid); a quotient <= -1 (or NaN) converts to a huge cell index in practice (x86-64: cvttsd2si
+  // of the negative value reinterpreted as unsigned): "outside the grid"
   bool Cell(double x, double y, long long* xc, long long* yc) const {
     double fx = x / res, fy = y / res;
-    if (!(fx >= 0.0) || !(fy >= 0.0)) return false;
+    if (!(fx > -1.0) || !(fy > -1.0)) return false;
     *xc = (long long)fx; *yc = (long long)fy;
     return *xc < cols && *yc < rows;      // isCellValid, :47-49
   }

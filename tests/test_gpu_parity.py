@@ -305,6 +305,9 @@ def test_csv_grid_terrain():
         if name == "ee-motion_0":
             X[0:8, s] = np.arange(1, 9) * 0.17 - 0.001
             X[8:16, s] = np.arange(1, 9) * 0.17 + 0.001
+        if name == "ee-motion_1":                # coordinates in (-res, 0): cell 0 of the reference (size_t truncation), not "outside"
+            X[16:24, s] = -0.05 - 0.01 * np.arange(8)[:, None]
+    grid[0, :] += 0.04; grid[:, 0] += 0.04
     bt = p.batch(B); bt.set_terrains(terr); bt.set_grid_terrain(grid)
     out = bt.eval_host(X)
     oracle_lib.set_grid(grid)

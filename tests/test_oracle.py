@@ -135,7 +135,7 @@ def _csv_grid_reference(grid, x, y):
     """Independent restatement of towr::HeightMapFromCSV (height_map_from_csv.h:29-111) in plain Python."""
     res, eps = 0.17, 0.17 / 50
     rows, cols = grid.shape
-    if x / res < 0 or y / res < 0:
+    if x / res <= -1 or y / res <= -1:          # static_cast<size_t> truncates toward zero: (-1, 0) is cell 0, :31-32
         return 0.0, 0.0, 0.0
     xc, yc = int(x / res), int(y / res)
     if xc >= cols or yc >= rows:
@@ -161,6 +161,9 @@ def test_csv_grid_terrain_of_the_oracle():
     pts = list(rng.uniform(-0.3, 2.6, (300, 2)))
     for k in range(1, 12):                       # points inside the eps bands at the cell edges, both directions
         pts += [(k * res - 0.4 * eps, 0.5), (k * res + 0.4 * eps, 0.5), (0.6, (k % 8 + 1) * res - 0.3 * eps), (0.6, (k % 8 + 1) * res + 0.3 * eps)]
+    pts += [(-0.05, 0.4), (0.4, -0.05), (-0.05, -0.05), (-0.169, 0.2), (-0.17, 0.2), (-0.171, 0.2), (0.2, -0.1701)]   # the (-res, 0) band is cell 0
+    assert grid[:, 0].any() and grid[0, :].any()
+    assert oracle_lib.terrain_point(tb.GRID_CSV, -0.05, 0.4)[0] == grid[2, 0]
     hit = 0
     for x, y in pts:
         got = oracle_lib.terrain_point(tb.GRID_CSV, x, y)

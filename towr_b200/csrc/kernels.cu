@@ -365,11 +365,12 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSa
 struct TerrainPoint { double h, hx, hy, hxx; };
 // HeightMapFromCSV (height_map_from_csv.h:29-111): cell-constant heights, cells of 0.17 m; slope diff/eps on the last
 // eps = res/50 before a rising edge and the first eps after a falling edge, 0 elsewhere; outside the grid everything is 0
-// (a negative coordinate converts to a huge size_t cell index in the reference, i.e. "outside").
+// (static_cast<size_t>(x / res), :31-32, truncates toward zero: a quotient in (-1, 0) is cell 0, inside the grid; a quotient
+// <= -1 or NaN converts to a huge cell index, i.e. "outside").
 __device__ __forceinline__ bool GridCell(const Plan& P, double x, double y, long long* xc, long long* yc) {
   const double res = 0.17;
   const double fx = x / res, fy = y / res;
-  if (!(fx >= 0.0) || !(fy >= 0.0) || !P.grid) return false;
+  if (!(fx > -1.0) || !(fy > -1.0) || !P.grid) return false;
   *xc = (long long)fx; *yc = (long long)fy;
   return *xc < P.grid_cols && *yc < P.grid_rows;
 }
