@@ -14,6 +14,25 @@ from tolerance import check_rows, check_sets
 
 pytestmark = pytest.mark.gpu
 
+# every comparison against the oracle is recorded (worst error / tolerance, fraction of entries that miss the BARE
+# 1e-12 relative / 1e-14 absolute criterion) and written to gpurun_out/parity.json at the end of the module; the copy of
+# the last GPU run of a round is committed as profiles/parity_r<round>.json
+PARITY_LOG = []
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _write_parity_log():
+    yield
+    import json
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "parity.json"), "w") as fh:
+            json.dump({"tolerance": {"rel": 1e-12, "abs": 1e-14, "abs_scaled_by": "largest |ref| of the Jacobian row / constraint set"},
+                       "cases": PARITY_LOG}, fh, indent=1)
+    except OSError:
+        pass
+
 
 def _compare(name, B, terrain=None, terrains=None, costs=None, strict=1e-4, **kw):
     f = tb.make_formulation(name, terrain=terrain, **kw)
@@ -31,6 +50,11 @@ def _compare(name, B, terrain=None, terrains=None, costs=None, strict=1e-4, **kw
     assert ref["rc"] == 0                      # oracle pattern at x == pattern at x0
     bad_j, strict_j, worst_j = check_rows(out["jac"], ref["jac"], p.row_ptr())
     bad_g, strict_g, worst_g = check_sets(out["g"], ref["g"], p.constraint_sets())
+    PARITY_LOG.append({"case": name, "B": B, "n": p.n, "m": p.m, "nnz": p.nnz, "kw": {k: str(v) for k, v in kw.items()},
+                       "terrain": None if terrain is None else int(terrain), "mixed_terrains": terrains is not None,
+                       "jac": {"violations": bad_j, "worst_err_over_tol": worst_j, "strict_miss_fraction": strict_j},
+                       "g": {"violations": bad_g, "worst_err_over_tol": worst_g, "strict_miss_fraction": strict_g},
+                       "strict_miss_limit": strict})
     assert bad_j == 0, (bad_j, worst_j)
     assert bad_g == 0, (bad_g, worst_g)
     assert strict_j < strict and strict_g < strict   # entries missing the bare (unscaled) 1e-12/1e-14 criterion are rare
@@ -58,9 +82,9 @@ def test_anymal_mixed_terrains_config5():
 
 def test_hyq_gallop_gap_durations_config4():
     """Phase durations optimised: PhaseSpline / PhaseDurations Jacobians, TotalDurationConstraint."""
-    # optimised durations enter as T^-2 .. T^-4 (std::pow in the reference, products here: 1 ulp apart) in front of
-    # cancelling sums, inside rows that also hold force-scaled entries (~1e3): more entries need the row scale
-    p, out, ref = _compare("hyq_gallop_gap", 48, strict=1e-2)
+    # optimised durations enter as T^-2 .. T^-4 in front of cancelling sums; the device computes the powers correctly
+    # rounded (Pow3 / Pow4 in kernels.cu) like std::pow, so the bare criterion holds as for the other configs
+    p, out, ref = _compare("hyq_gallop_gap", 48, strict=1e-4)
     (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == "totalduration-2"]
     assert np.array_equal(out["g"][:, r0], ref["g"][:, r0])
 

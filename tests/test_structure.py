@@ -123,6 +123,20 @@ def test_unsupported_and_invalid_specs():
     s = tb.make_formulation("hopper").to_spec(); s.constraints[0] = 99
     with pytest.raises(tb.TowrB200Error):
         tb.Problem(s)
+    # numeric fields that drive loops / allocations: a zeroed or corrupted spec fails with TWB_ERR_INVALID (no hang, no crash)
+    for field, bad in (("duration_base_polynomial", 0.0), ("dt_constraint_dynamic", 0.0), ("dt_constraint_range_of_motion", -0.08),
+                       ("dt_constraint_base_motion", float("nan")), ("ee_polynomials_per_swing_phase", 0),
+                       ("force_polynomials_per_stance_phase", 0), ("dt_constraint_dynamic", 1e-9), ("duration_base_polynomial", float("inf"))):
+        s = tb.make_formulation("hopper").to_spec(); setattr(s, field, bad)
+        with pytest.raises(tb.TowrB200Error) as e:
+            tb.Problem(s)
+        assert e.value.code == capi.ERR_INVALID, field
+    s = tb.make_formulation("hopper").to_spec(); s.phase_durations[0][1] = 0.0
+    with pytest.raises(tb.TowrB200Error):
+        tb.Problem(s)
+    zeroed = capi.Spec()                      # never passed through twb_spec_default
+    with pytest.raises(tb.TowrB200Error):
+        tb.Problem(zeroed)
 
 
 def test_c_abi_exports_every_declared_symbol():

@@ -73,6 +73,10 @@ struct OutRange { int32_t first, count; };
 struct OutList {                        // per alignment class
   OutRange pairs[kMaxClasses];          // whole sectors, two pairs each
   OutRange singles[kMaxClasses];        // single elements (lane = instance)
+  // TMA store path: when the pairs of a class form ONE contiguous run of the row (pair i covers elements run_off + 2i,
+  // run_off + 2i + 1 — the normal case: a CTA owns adjacent CSR rows), the CTA assembles the run in shared memory in
+  // output order and writes it with one cp.async.bulk per instance; -1: not contiguous, 16-byte st.global path
+  int32_t run_off[kMaxClasses];
 };
 // Range-of-motion state block: [0]=1 | R^T (9) | buffers of { D_e (9) | g_e (3) }.  TWB_ROM_ALLFEET = 0: two buffers
 // used by the feet in turn (one CTA barrier and one list per foot); 1: one buffer per foot (one barrier, one list).
@@ -162,6 +166,7 @@ struct Plan {
   int node_rows, dyn_rows, rom_rows;   // state rows of one unit's block: node groups (largest), dynamic samples, range-of-motion samples
   int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz); nc_g = 1 (constraint values go through GT)
   int dyn_list0, rom_list0, node_list0;   // first entry of cta_lists of the dynamic CTAs, (rom CTA, foot) pairs, node CTAs
+  int stage_dyn, stage_rom, stage_node;   // longest contiguous run (in doubles, even) of a dynamic / range-of-motion / node list: staging row of the TMA store path
   int rom_row0[kMaxEE];                   // first constraint row of foot e's range-of-motion set (sample k owns rows rom_row0[e] + 3k ..+2)
   // robot
   double mass, gravity;

@@ -325,6 +325,20 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     if (sp.n_phases[e] < 1 || sp.n_phases[e] > TWB_MAX_PHASES) return fail(TWB_ERR_INVALID, "bad phase count");
   if (sp.n_constraints < 0 || sp.n_constraints > TWB_MAX_CONSTRAINTS || sp.n_costs < 0 || sp.n_costs > TWB_MAX_COSTS)
     return fail(TWB_ERR_INVALID, "bad constraint/cost count");
+  // numeric fields that drive loops and allocations (a zero-initialised or corrupted spec must fail here, not hang,
+  // overflow or silently change m / nnz)
+  auto pos_finite = [](double v) { return std::isfinite(v) && v > 0.0; };
+  if (!pos_finite(sp.duration_base_polynomial) || !pos_finite(sp.dt_constraint_dynamic) || !pos_finite(sp.dt_constraint_range_of_motion) ||
+      !pos_finite(sp.dt_constraint_base_motion))
+    return fail(TWB_ERR_INVALID, "duration_base_polynomial and dt_constraint_* must be finite and > 0");
+  if (sp.ee_polynomials_per_swing_phase < 1 || sp.ee_polynomials_per_swing_phase > 16 || sp.force_polynomials_per_stance_phase < 1 ||
+      sp.force_polynomials_per_stance_phase > 16)
+    return fail(TWB_ERR_INVALID, "polynomials per phase must be in 1..16");
+  for (int e = 0; e < n_ee; ++e)
+    for (int i = 0; i < sp.n_phases[e]; ++i)
+      if (!pos_finite(sp.phase_durations[e][i])) return fail(TWB_ERR_INVALID, "phase durations must be finite and > 0");
+  if (!std::isfinite(sp.force_limit_in_normal_direction) || !std::isfinite(sp.bound_phase_duration_min) || !std::isfinite(sp.bound_phase_duration_max))
+    return fail(TWB_ERR_INVALID, "non-finite parameter");
   optimize_timings = false;
   for (int i = 0; i < sp.n_constraints; ++i) {
     if (sp.constraints[i] == TWB_C_TOTAL_TIME) optimize_timings = true;  // parameters.cc:128-135
@@ -338,6 +352,10 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     if (std::fabs(Te - T) >= 1e-6) return fail(TWB_ERR_INVALID, "feet phase durations do not sum to the same total time");
   }
   if (!(T > 0.0)) return fail(TWB_ERR_INVALID, "total time must be positive");
+  {   // bound the sample / polynomial counts (T / dt) before anything is allocated
+    const double smallest = std::min(std::min(sp.duration_base_polynomial, sp.dt_constraint_dynamic), std::min(sp.dt_constraint_range_of_motion, sp.dt_constraint_base_motion));
+    if (T / smallest > 4096.0) return fail(TWB_ERR_INVALID, "more than 4096 samples or base polynomials (T / dt)");
+  }
   const std::vector<double> base_T = BasePolyDurations(T, sp.duration_base_polynomial);
 
   // ---- variable sets in AddVariableSet order (nlp_formulation.cc:63-93)
@@ -804,9 +822,21 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     // self-check: every element of an output-kernel row is written exactly once
     for (int i = 0; i < L; ++i) if (hits[i] != (elems[i].list >= 0 ? 1 : 0)) return fail(TWB_ERR_UNSUPPORTED, "output lists do not cover every element exactly once");
   }
+  pl.stage_dyn = pl.stage_rom = pl.stage_node = 0;
   auto flush_list = [&](int list) {
     OutList out{};
+    for (int q = 0; q < kMaxClasses; ++q) out.run_off[q] = -1;
     for (int q = 0; q < NC; ++q) {
+      {   // contiguous run of pairs? (sectors are pushed in ascending order)
+        const auto& v = lists[list][q][0];
+        bool run = !v.empty();
+        for (size_t i = 1; i < v.size() && run; ++i) run = v[i].p.off == v[0].p.off + 2 * (int)i;
+        if (run) {
+          out.run_off[q] = v[0].p.off;
+          int& cap = list < n_dyn_ctas ? pl.stage_dyn : list < n_dyn_ctas + n_rom_ctas * rom_lists ? pl.stage_rom : pl.stage_node;
+          cap = std::max(cap, 2 * (int)v.size());
+        }
+      }
       OutRange* dst[2] = {&out.pairs[q], &out.singles[q]};
       for (int w = 0; w < 2; ++w) {
         const auto& v = lists[list][q][w];

@@ -64,6 +64,21 @@ namespace {
 #define TWB_NODE_CTAS 3
 #endif
 #endif
+#ifndef TWB_TMA
+#define TWB_TMA 0        // 1: the Jacobian values of a CTA list leave the SM as cp.async.bulk.global.shared::cta copies of contiguous row segments assembled in shared memory; 0 (ships): 16-byte st.global.cs from the pair loop.  Measured (profiles/README.md, round 2): parity green, but 192 us per step instead of 139 us on config 2 — the extra pass through shared memory costs more than the better DRAM pattern gains
+#endif
+#ifndef TWB_TMA_DYN
+#define TWB_TMA_DYN TWB_TMA   // per-kernel switches of the TMA store path (tuning)
+#endif
+#ifndef TWB_TMA_ROM
+#define TWB_TMA_ROM TWB_TMA
+#endif
+#ifndef TWB_TMA_G
+#define TWB_TMA_G 2      // instances assembled per staging step (2: 16-byte reads of the state rows)
+#endif
+#ifndef TWB_TMA_BUF
+#define TWB_TMA_BUF 1    // staging buffers per warp (ring)
+#endif
 constexpr int kLD = 34;                      // leading dimension of a state block: 32 instances, padded; even keeps rows 16-byte aligned
 
 // output stores: streaming (evict-first) — the values are consumed by the host / a solver, not by these kernels
@@ -111,6 +126,20 @@ __device__ __forceinline__ SampleRegs LoadSample(const SplineSample* __restrict_
   for (int i = 0; i < 6; ++i) { r.xi[2 * i] = (int)(v[i] & 0xFFFFu); r.xi[2 * i + 1] = (int)(v[i] >> 16); }
   return r;
 }
+// std::pow(x, 3) and std::pow(x, 4) of the reference (polynomial.cc:47-61, 236-257; glibc's pow is correctly rounded
+// apart from a handful of hard cases): x*x*x rounds twice and is up to 1 ulp off, which the division by T^3 / T^4 in front
+// of cancelling sums amplifies past 1e-12.  Here: the square with its exact FMA error term, then one rounding of the
+// compensated product — the correctly rounded power (x^2 itself is a single rounding in both).
+__device__ __forceinline__ double Pow3(double x) {
+  const double x2 = x * x, e2 = fma(x, x, -x2);       // x^2 = x2 + e2 exactly
+  const double hi = x2 * x, lo = fma(x2, x, -hi);     // x2 * x = hi + lo exactly
+  return hi + fma(e2, x, lo);
+}
+__device__ __forceinline__ double Pow4(double x) {
+  const double x2 = x * x, e2 = fma(x, x, -x2);
+  const double hi = x2 * x2, lo = fma(x2, x2, -hi);
+  return hi + fma(2.0 * x2, e2, lo);
+}
 // ---- PhaseSpline (phase_spline.cc, phase_durations.cc): polynomial durations are functions of the iterate ----
 // Active polynomial and local time of global time t: PhaseDurations::SetVariables (phase_durations.cc:79-100),
 // NodesVariablesPhaseBased::ConvertPhaseToPolyDurations (nodes_variables_phase_based.cc:78-89),
@@ -145,7 +174,7 @@ __device__ __forceinline__ void EvalSpline(const Plan& P, const SplineSample* __
     const PhaseSplineDef def = P.phase_defs[s.xi[1]];
     const PhaseLoc L = LocatePhasePoly(P, def, s.T, xs);
     const PhasePoly* pp = P.phase_polys + def.poly0 + L.poly;
-    const double T = L.T, T2 = T * T, T3 = T2 * T, t = L.tl, t2 = t * t, t3 = t2 * t;   // std::pow(x, 3) ~ x*x*x (<= 1 ulp)
+    const double T = L.T, T2 = T * T, T3 = Pow3(T), t = L.tl, t2 = t * t, t3 = Pow3(t);   // std::pow(x, 2), std::pow(x, 3)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const double p0 = xs[pp->xi[d]], v0 = xs[pp->xi[3 + d]], p1 = xs[pp->xi[6 + d]], v1 = xs[pp->xi[9 + d]];
@@ -674,6 +703,70 @@ __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __res
     off = noff; d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1;
   }
 }
+
+// ---- TMA store path ---------------------------------------------------------------------------------------------
+// A CTA list whose pairs form one contiguous run of the CSR value row (OutList::run_off) is written per instance as ONE
+// bulk copy shared -> global (SASS UBLKCP): every warp owns 32 / W instances of the tile, assembles the run of kG of them
+// in its staging rows in OUTPUT ORDER (thread = pair: 16-byte shared stores, conflict-free), makes the writes visible to
+// the async proxy and lets lane 0 issue the copies.  The TMA engine drains the staging rows while the warp goes on
+// (next instances, then the evaluation of the next unit); a row is only refilled after its copy has finished reading.
+__device__ __forceinline__ unsigned SmemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void BulkStore(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(SmemAddr(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void BulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void BulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void BulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+struct Stage { double* base; int cap; };   // staging rows of the CTA (after the state blocks): W x kBuf x kG rows of `cap` doubles (cap even)
+
+__device__ __forceinline__ void StorePairsTma(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs, int n_pairs,
+                                              int run_off, double* __restrict__ out, size_t stride, int q, int nc, int n_inst, const Stage st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5, per = 32 / W;
+  const int j_end = min(n_inst, (warp + 1) * per);
+  double* rows = st.base + (size_t)warp * (TWB_TMA_BUF * TWB_TMA_G) * st.cap;
+  const unsigned bytes = (unsigned)n_pairs * 16u;
+  if (lane == 0) BulkWaitRead<0>();   // copies of the previous list (issued before the evaluation of this unit) have long finished reading
+  __syncwarp();
+  int it = 0;
+  if (TWB_TMA_G == 2 && nc == 1) {
+    for (int j = warp * per; j < j_end; j += 2, ++it) {
+      double* b0 = rows + (size_t)(it % TWB_TMA_BUF) * 2 * st.cap; double* b1 = b0 + st.cap;
+      if (it >= TWB_TMA_BUF) { if (lane == 0) BulkWaitRead<TWB_TMA_BUF - 1>(); __syncwarp(); }
+      for (int i = lane; i < n_pairs; i += 32) {
+        int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
+        LoadPair(pairs, coefs, i, n_pairs, &off, &d0, &d1, &c0, &c1);
+        const double2 a = *reinterpret_cast<const double2*>(t + d0 * kLD + j), b = *reinterpret_cast<const double2*>(t + d1 * kLD + j);
+        const int o = off - run_off;
+        *reinterpret_cast<double2*>(b0 + o) = make_double2(a.x * c0, b.x * c1);
+        *reinterpret_cast<double2*>(b1 + o) = make_double2(a.y * c0, b.y * c1);
+      }
+      FenceProxyAsync();
+      __syncwarp();
+      if (lane == 0) {
+        BulkStore(out + (size_t)j * stride + run_off, b0, bytes);
+        if (j + 1 < j_end) BulkStore(out + (size_t)(j + 1) * stride + run_off, b1, bytes);
+        BulkCommit();
+      }
+    }
+    return;
+  }
+  constexpr int kSlots = TWB_TMA_BUF * TWB_TMA_G;
+  for (int j = warp * per; j < j_end; ++j) {
+    if (j % nc != q) continue;
+    double* b0 = rows + (size_t)(it % kSlots) * st.cap;
+    if (it >= kSlots) { if (lane == 0) BulkWaitRead<kSlots - 1>(); __syncwarp(); }
+    ++it;
+    for (int i = lane; i < n_pairs; i += 32) {
+      int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
+      LoadPair(pairs, coefs, i, n_pairs, &off, &d0, &d1, &c0, &c1);
+      *reinterpret_cast<double2*>(b0 + (off - run_off)) = make_double2(t[d0 * kLD + j] * c0, t[d1 * kLD + j] * c1);
+    }
+    FenceProxyAsync();
+    __syncwarp();
+    if (lane == 0) { BulkStore(out + (size_t)j * stride + run_off, b0, bytes); BulkCommit(); }
+  }
+}
 // Entries handled with lane = instance: fetched with one coalesced load (lane = entry), broadcast with shuffles.
 // fn(first, d0, coefficient) is called by every lane of the warp for every entry.
 template <class F>
@@ -699,7 +792,7 @@ __device__ __forceinline__ void StoreValuesTiled(const Plan& P, const double* t,
 }
 // Jacobian values of a whole CTA (after its barrier): every thread takes pairs of the CTA's list; warp 0 writes the
 // single elements (sectors shared with a neighbouring CTA) with lane = instance.
-__device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst) {
+__device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst, const Stage st) {
 #ifdef TWB_EXP_NOSTORE   // timing experiment: compute phase only
   return;
 #endif
@@ -712,6 +805,12 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
     if (threadIdx.x < 32) rs = LoadRange(&list->singles[q]);
     uint2 raw = make_uint2(0u, 0u); double cs = 0.0;
     if (lane < rs.count) { raw = __ldg(reinterpret_cast<const uint2*>(P.pairs + rs.first) + lane); cs = __ldg(reinterpret_cast<const double*>(P.coefs + rs.first + lane)); }
+#if TWB_TMA
+    const int run_off = __ldg(&list->run_off[q]);
+    if (run_off >= 0 && 2 * rp.count <= st.cap && (32 % (blockDim.x >> 5)) == 0)
+      StorePairsTma(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, run_off, jac_tile, (size_t)P.nnz, q, nc, n_inst, st);
+    else
+#endif
     StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, threadIdx.x, blockDim.x);
     if (threadIdx.x < 32 && rs.count > 0) {
       const bool active = lane < n_inst && (lane % nc) == q;
@@ -740,7 +839,7 @@ __device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int l
 // several KB of contiguous CSR values per instance (the samples' rows are adjacent).
 template <int kNEE, bool kPhase>
 __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
-                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
+                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kDynWarps + warp, b0 = tile * 32;
   constexpr int n_rows = 40 + 6 * kNEE;   // local rows: 1 | 3 | 36 | 6 per foot; the 6 constraint values go straight into GT (coalesced)
@@ -755,7 +854,7 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
 #endif
   }
   __syncthreads();
-  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.dyn_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0));
+  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.dyn_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0), st);
 }
 
 // RangeOfMotionConstraint (range_of_motion_constraint.cc:58-109): g_e = R^T (p_e - c); Jacobian state R^T and
@@ -766,7 +865,7 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
 // already evaluates foot e + 1 — one CTA barrier per foot.
 template <int kNEE, bool kPhase>
 __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
-                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile) {
+                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kRomWarps + warp, b0 = tile * 32;
   const bool valid = k < P.n_rom;
@@ -822,19 +921,19 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
     }
 #if !TWB_ROM_ALLFEET
     __syncthreads();   // foot e complete in every block; everybody is done reading buffer (e + 1) & 1 (the list of foot e - 1)
-    if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst);
+    if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst, st);
 #endif
   }
 #if TWB_ROM_ALLFEET
   __syncthreads();
-  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta, jac_tile, n_inst);
+  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta, jac_tile, n_inst, st);
 #endif
 }
 
 // node groups: blockIdx.y = instance tile, warp = one of kNodeWarps consecutive groups
 __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                          int* __restrict__ status, const int* __restrict__ terrain_ids, int default_terrain, int nb,
-                                         unsigned flags, double* node_smem, int cta, int tile) {
+                                         unsigned flags, double* node_smem, int cta, int tile, const Stage st) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = cta * kNodeWarps + warp, b0 = tile * 32, b = b0 + lane;
   double* t = node_smem + (size_t)warp * P.node_rows * kLD;
@@ -879,7 +978,7 @@ __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict
     }
   }
   __syncthreads();
-  if (flags & 2u) StoreCta(P, node_smem, P.cta_lists + P.node_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0));
+  if (flags & 2u) StoreCta(P, node_smem, P.cta_lists + P.node_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0), st);
 }
 
 // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
@@ -917,7 +1016,7 @@ __device__ __forceinline__ PhaseFull EvalPhaseFull(const Plan& P, int def_index,
   const PhaseSplineDef def = P.phase_defs[def_index];
   const PhaseLoc L = LocatePhasePoly(P, def, tg, xs);
   PhaseFull o; o.pp = P.phase_polys + def.poly0 + L.poly; o.n_phases = def.n_phases;
-  const double T = L.T, T2 = T * T, T3 = T2 * T, T4 = T2 * T2, t = L.tl, t2 = t * t, t3 = t2 * t;
+  const double T = L.T, T2 = T * T, T3 = Pow3(T), T4 = Pow4(T), t = L.tl, t2 = t * t, t3 = Pow3(t);
   o.B[0][0] = (2 * t3) / T3 - (3 * t2) / T2 + 1; o.B[0][1] = t - (2 * t2) / T + t3 / T2;
   o.B[1][0] = (3 * t2) / T2 - (2 * t3) / T3;     o.B[1][1] = t3 / T2 - t2 / T;
   const double inner = 1. / (double)o.pp->n_in_phase, prev = (double)o.pp->k_in_phase;
@@ -1194,45 +1293,54 @@ __global__ void __launch_bounds__(kWarps * 32, TWB_CTAS) EvalOut(const Plan P, c
   extern __shared__ __align__(16) double out_smem[];
   const int n_dyn_ctas = (P.n_dyn + kWarps - 1) / kWarps, n_rom_ctas = (P.n_rom + kWarps - 1) / kWarps;
   int cta = blockIdx.x;
-  if (cta < n_dyn_ctas) { DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
+  if (cta < n_dyn_ctas) { DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y, Stage{nullptr, 0}); return; }
   cta -= n_dyn_ctas;
-  if (cta < n_rom_ctas) { RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y); return; }
+  if (cta < n_rom_ctas) { RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, cta, blockIdx.y, Stage{nullptr, 0}); return; }
   cta -= n_rom_ctas;
-  NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, cta, blockIdx.y);
+  NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, cta, blockIdx.y, Stage{nullptr, 0});
 }
 #else
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
-                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
+                                                           double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags,
+                                                           int stage_off, int stage_cap) {
   extern __shared__ __align__(16) double out_smem[];
-  DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+  DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, Stage{out_smem + stage_off, stage_cap});
+#if TWB_TMA
+  if ((threadIdx.x & 31) == 0) BulkWaitAll();   // the staging rows stay allocated until the last copy has left
+#endif
 }
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                            double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
-  RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+  RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, Stage{nullptr, 0});
 }
 __global__ void __launch_bounds__(kNodeWarps * 32, TWB_NODE_CTAS) NodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                            double* __restrict__ jac, int* __restrict__ status,
                                                            const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags) {
   extern __shared__ __align__(16) double out_smem[];
-  NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+  NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x, blockIdx.y, Stage{nullptr, 0});
 }
 #if TWB_ROMNODE   // range-of-motion and node CTAs of a tile in one kernel (kRomWarps == kNodeWarps), in row order
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                                double* __restrict__ jac, int* __restrict__ status,
-                                                               const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags) {
+                                                               const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags,
+                                                               int stage_off, int stage_cap) {
   extern __shared__ __align__(16) double out_smem[];
   static_assert(kRomWarps == kNodeWarps, "TWB_ROMNODE needs equal CTA sizes");
+  const Stage st{out_smem + stage_off, stage_cap};
 #if TWB_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");   // XT complete and visible (programmatic dependency on TransposeIn)
 #endif
   const int n_rom_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps;
-  if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y);
+  if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, st);
 #ifndef TWB_EXP_NONODE   // (timing experiment: node CTAs return at once)
-  else NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x - n_rom_ctas, blockIdx.y);
+  else NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x - n_rom_ctas, blockIdx.y, st);
+#endif
+#if TWB_TMA
+  if ((threadIdx.x & 31) == 0) BulkWaitAll();
 #endif
 }
 #endif
@@ -1256,7 +1364,11 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
 #else
 #if TWB_ROMNODE
   {
-    const size_t smem = (size_t)kRomWarps * std::max(rom_rows, node_rows) * row_bytes;
+    const size_t state_bytes = (size_t)kRomWarps * std::max(rom_rows, node_rows) * row_bytes;
+    const int stage_off = (int)(state_bytes / sizeof(double));
+    int stage_cap = TWB_TMA_ROM ? std::max(P.stage_rom, P.stage_node) : 0;
+    if (state_bytes + (size_t)kRomWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 100 * 1024) stage_cap = 0;   // dense rows (optimised durations): st.global path
+    const size_t smem = state_bytes + (size_t)kRomWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
     if ((e = cudaFuncSetAttribute(RomNodeOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps;
     if (n_ctas > 0) {
@@ -1264,17 +1376,21 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
       cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(n_ctas, tiles); cfg.blockDim = dim3(kRomWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
       cudaLaunchAttribute attr{}; attr.id = cudaLaunchAttributeProgrammaticStreamSerialization; attr.val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = &attr; cfg.numAttrs = 1;
-      if ((e = cudaLaunchKernelEx(&cfg, RomNodeOut<kNEE, kPhase>, P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags)) != cudaSuccess) return e;
+      if ((e = cudaLaunchKernelEx(&cfg, RomNodeOut<kNEE, kPhase>, P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, stage_off, stage_cap)) != cudaSuccess) return e;
 #else
-      RomNodeOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags);
+      RomNodeOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, stage_off, stage_cap);
 #endif
       ++*count; TWB_MARK("RomNodeOut", s);
     }
   }
   if (P.n_dyn > 0) {
-    const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
+    const size_t state_bytes = (size_t)kDynWarps * dyn_rows * row_bytes;
+    const int stage_off = (int)(state_bytes / sizeof(double));
+    int stage_cap = TWB_TMA_DYN ? P.stage_dyn : 0;
+    if (state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 200 * 1024) stage_cap = 0;
+    const size_t smem = state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
     if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
+    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags, stage_off, stage_cap);
     ++*count; TWB_MARK("DynOut", a0);
   }
   return cudaSuccess;
@@ -1286,9 +1402,13 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     ++*count; TWB_MARK("RomOut", s);
   }
   if (P.n_dyn > 0) {
-    const size_t smem = (size_t)kDynWarps * dyn_rows * row_bytes;
+    const size_t state_bytes = (size_t)kDynWarps * dyn_rows * row_bytes;
+    const int stage_off = (int)(state_bytes / sizeof(double));
+    int stage_cap = TWB_TMA_DYN ? P.stage_dyn : 0;
+    if (state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 200 * 1024) stage_cap = 0;
+    const size_t smem = state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
     if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags);
+    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags, stage_off, stage_cap);
     ++*count; TWB_MARK("DynOut", a0);
   }
   if (P.n_groups > 0) {
