@@ -142,6 +142,8 @@ int twb_problem_row_ptr(const twb_problem* p, int* row_ptr);
 /* Bounds (ifopt::Bounds, inf = 1e20) and initial guess. */
 int twb_problem_bounds(const twb_problem* p, double* x_lower, double* x_upper,
                        double* g_lower, double* g_upper);
+/* 1 if the formulation has cost terms (ifopt::Problem::HasCostTerms; params_.costs_ non-empty), else 0 */
+int twb_problem_has_cost(const twb_problem* p);
 int twb_problem_x0(const twb_problem* p, double* x0);
 
 /* Goal-randomised instances of one structure class (BASELINE configs[2]: "randomized goal/initial-guess instances"):

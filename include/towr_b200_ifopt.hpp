@@ -8,15 +8,18 @@
 //     GetVariableSets / GetConstraints / GetCosts (nlp_formulation.cc:63-376),
 //
 // served for batch index `b` of a twb_batch from the result of the last batched evaluation.  ifopt and Eigen are
-// not available in this image, so the ifopt types are restated here in namespace twb_ifopt with the same member
-// names (Eigen::VectorXd -> std::vector<double>, Eigen::SparseMatrix<double, RowMajor> -> a small row-major
-// triplet block with coeffRef); a build that has ifopt only needs `namespace twb_ifopt = ifopt;` plus Eigen::Map
-// in the three places marked "Eigen:".  Nothing here computes: all arithmetic happens in libtowr_b200.so.
+// not available in this image, so ifopt 2.0's classes are restated here in namespace twb_ifopt with the same
+// signatures — Component {GetValues, GetBounds, SetVariables, GetJacobian, GetRows, GetName, Print, SetRows,
+// kSpecifyLater}, Composite, VariableSet, ConstraintSet {LinkWithVariables, GetJacobian final, FillJacobianBlock,
+// InitVariableDependedQuantities}, CostTerm {GetCost} — over two small stand-ins for Eigen::VectorXd and
+// Eigen::SparseMatrix<double, RowMajor>.  Nothing here computes: all arithmetic happens in libtowr_b200.so.
 #ifndef TOWR_B200_IFOPT_HPP_
 #define TOWR_B200_IFOPT_HPP_
 
 #include <algorithm>
 #include <array>
+#include <cassert>
+#include <cstdio>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -26,14 +29,49 @@
 
 #include "towr_b200.h"
 
-namespace twb_ifopt {
+// A build that has ifopt includes its headers first and defines TWB_IFOPT_EXTERNAL to its namespace:
+//     #include <ifopt/problem.h>
+//     #define TWB_IFOPT_EXTERNAL ifopt
+//     #include "towr_b200_ifopt.hpp"
+// The Gpu* classes below then derive from the real ifopt::VariableSet / ConstraintSet / CostTerm.
+// tests/cpp/ifopt_conformance.cc compiles exactly that way against a verbatim restatement of ifopt 2.0's class
+// declarations (component.h, variable_set.h, constraint_set.h, cost_term.h, composite.h) to prove the classes are concrete.
+#ifndef TWB_IFOPT_EXTERNAL
+namespace twb_ifopt {   // mirror of namespace ifopt (ifopt 2.0: component.h, composite.h, variable_set.h, constraint_set.h, cost_term.h, bounds.h)
 
-using VectorXd = std::vector<double>;                       // Eigen: Eigen::VectorXd
-struct Bounds { double lower_, upper_; };                   // ifopt::Bounds
-using VecBound = std::vector<Bounds>;
-static const double inf = 1e20;                             // ifopt::inf
+struct Bounds {                                              // ifopt/bounds.h
+  Bounds(double lower = 0.0, double upper = 0.0) : lower_(lower), upper_(upper) {}
+  double lower_, upper_;
+};
+static const double inf = 1.0e20;
+static const Bounds NoBound = Bounds(-inf, +inf);
+static const Bounds BoundZero = Bounds(0.0, 0.0);
+static const Bounds BoundGreaterZero = Bounds(0.0, +inf);
+static const Bounds BoundSmallerZero = Bounds(-inf, 0.0);
 
-// Eigen: Eigen::SparseMatrix<double, Eigen::RowMajor> restricted to what FillJacobianBlock implementations use
+// Eigen::VectorXd restricted to what this path needs
+class VectorXd {
+ public:
+  VectorXd() = default;
+  explicit VectorXd(int n) : v_(n, 0.0) {}
+  VectorXd(const double* first, const double* last) : v_(first, last) {}
+  VectorXd(std::initializer_list<double> l) : v_(l) {}
+  static VectorXd Zero(int n) { return VectorXd(n); }
+  int size() const { return (int)v_.size(); }
+  int rows() const { return (int)v_.size(); }
+  double& operator()(int i) { return v_[i]; }
+  double operator()(int i) const { return v_[i]; }
+  double& operator[](int i) { return v_[i]; }
+  double operator[](int i) const { return v_[i]; }
+  double* data() { return v_.data(); }
+  const double* data() const { return v_.data(); }
+  std::vector<double>::const_iterator begin() const { return v_.begin(); }
+  std::vector<double>::const_iterator end() const { return v_.end(); }
+ private:
+  std::vector<double> v_;
+};
+
+// Eigen::SparseMatrix<double, Eigen::RowMajor> restricted to what FillJacobianBlock implementations use
 class Jacobian {
  public:
   Jacobian(int rows = 0, int cols = 0) : rows_(rows), cols_(cols) {}
@@ -47,32 +85,136 @@ class Jacobian {
   std::map<std::pair<int, int>, double> v_;
 };
 
-class Component {                                            // ifopt::Component
+class Component {                                            // ifopt/composite.h: class Component
  public:
   using Ptr = std::shared_ptr<Component>;
-  Component(int num_rows, std::string name) : num_rows_(num_rows), name_(std::move(name)) {}
+  using Jacobian = twb_ifopt::Jacobian;
+  using VectorXd = twb_ifopt::VectorXd;
+  using VecBound = std::vector<Bounds>;
+  Component(int num_rows, const std::string& name) : num_rows_(num_rows), name_(name) {}
   virtual ~Component() = default;
   virtual VectorXd GetValues() const = 0;
   virtual VecBound GetBounds() const = 0;
+  virtual void SetVariables(const VectorXd& x) = 0;
+  virtual Jacobian GetJacobian() const = 0;
   int GetRows() const { return num_rows_; }
   std::string GetName() const { return name_; }
+  virtual void Print(double tolerance, int& index_start) const {
+    (void)tolerance;
+    std::printf("%-24s %6d rows  [%d .. %d)\n", name_.c_str(), num_rows_, index_start, index_start + num_rows_);
+    index_start += num_rows_;
+  }
+  void SetRows(int num_rows) { num_rows_ = num_rows; }
+  static const int kSpecifyLater = -1;
  private:
-  int num_rows_;
+  int num_rows_ = kSpecifyLater;
   std::string name_;
 };
-class VariableSet : public Component { public: using Component::Component; };
-class ConstraintSet : public Component {                     // ifopt::ConstraintSet
+
+class Composite : public Component {                         // ifopt/composite.h: class Composite
  public:
-  using Component::Component;
-  virtual void FillJacobianBlock(std::string var_set, Jacobian& jac_block) const = 0;
+  using Ptr = std::shared_ptr<Composite>;
+  using ComponentVec = std::vector<Component::Ptr>;
+  Composite(const std::string& name, bool is_cost) : Component(0, name), is_cost_(is_cost) {}
+  virtual ~Composite() = default;
+  VectorXd GetValues() const override {
+    VectorXd g_all(GetRows());
+    int row = 0;
+    for (const auto& c : components_) {
+      const VectorXd g = c->GetValues();
+      for (int i = 0; i < c->GetRows(); ++i) g_all(row + i) += g(i);
+      if (!is_cost_) row += c->GetRows();
+    }
+    return g_all;
+  }
+  Jacobian GetJacobian() const override { throw std::runtime_error("Composite::GetJacobian: ask the constraint sets"); }
+  VecBound GetBounds() const override {
+    VecBound b;
+    for (const auto& c : components_) { VecBound bc = c->GetBounds(); b.insert(b.end(), bc.begin(), bc.end()); }
+    return b;
+  }
+  void SetVariables(const VectorXd& x) override {
+    int row = 0;
+    for (auto& c : components_) {
+      VectorXd part(x.data() + row, x.data() + row + c->GetRows());
+      c->SetVariables(part);
+      row += c->GetRows();
+    }
+  }
+  void PrintAll() const { int i = 0; for (const auto& c : components_) c->Print(0.001, i); }
+  const Component::Ptr GetComponent(std::string name) const {
+    for (const auto& c : components_) if (c->GetName() == name) return c;
+    throw std::runtime_error("component \"" + name + "\" doesn't exist.");
+  }
+  template <typename T> std::shared_ptr<T> GetComponent(const std::string& name) const {
+    std::shared_ptr<T> t = std::dynamic_pointer_cast<T>(GetComponent(name));
+    if (!t) throw std::runtime_error("Error casting component " + name);
+    return t;
+  }
+  void AddComponent(const Component::Ptr& c) {
+    components_.push_back(c);
+    if (is_cost_) SetRows(1); else SetRows(GetRows() + c->GetRows());
+  }
+  void ClearComponents() { components_.clear(); SetRows(0); }
+  const ComponentVec GetComponents() const { return components_; }
+ private:
+  ComponentVec components_;
+  bool is_cost_;
 };
-class CostTerm : public Component {                          // ifopt::CostTerm
+
+class VariableSet : public Component {                       // ifopt/variable_set.h
  public:
-  using Component::Component;
+  VariableSet(int n_var, const std::string& name) : Component(n_var, name) {}
+  virtual ~VariableSet() = default;
+  Jacobian GetJacobian() const final { throw std::runtime_error("not implemented for variables"); }
+};
+
+class ConstraintSet : public Component {                     // ifopt/constraint_set.h
+ public:
+  using Ptr = std::shared_ptr<ConstraintSet>;
+  using VariablesPtr = Composite::Ptr;
+  ConstraintSet(int n_constraints, const std::string& name) : Component(n_constraints, name) {}
+  virtual ~ConstraintSet() = default;
+  void LinkWithVariables(const VariablesPtr& x) { variables_ = x; InitVariableDependedQuantities(x); }
+  // one block per variable set, side by side (constraint_set.cc: GetJacobian)
+  Jacobian GetJacobian() const final {
+    int n = 0; for (const auto& v : variables_->GetComponents()) n += v->GetRows();
+    Jacobian jacobian(GetRows(), n);
+    int col = 0;
+    for (const auto& v : variables_->GetComponents()) {
+      Jacobian jac(GetRows(), v->GetRows());
+      FillJacobianBlock(v->GetName(), jac);
+      for (const auto& kv : jac.entries()) jacobian.coeffRef(kv.first.first, col + kv.first.second) = kv.second;
+      col += v->GetRows();
+    }
+    return jacobian;
+  }
+  virtual void FillJacobianBlock(std::string var_set, Jacobian& jac_block) const = 0;
+ protected:
+  const VariablesPtr GetVariables() const { return variables_; }
+ private:
+  VariablesPtr variables_;
+  virtual void InitVariableDependedQuantities(const VariablesPtr& x_init) { (void)x_init; }
+  void SetVariables(const VectorXd& x) final { (void)x; assert(false); }
+};
+
+class CostTerm : public ConstraintSet {                      // ifopt/cost_term.h
+ public:
+  CostTerm(const std::string& name) : ConstraintSet(1, name) {}
+  virtual ~CostTerm() = default;
+ private:
   virtual double GetCost() const = 0;
+ public:
+  VectorXd GetValues() const final { VectorXd cost(1); cost(0) = GetCost(); return cost; }
+  VecBound GetBounds() const final { return VecBound(GetRows(), NoBound); }
+  void Print(double tol, int& index) const final { (void)tol; std::printf("%-24s cost %.6g\n", GetName().c_str(), GetCost()); (void)index; }
 };
 
 }  // namespace twb_ifopt
+#define TWB_IFOPT_NS twb_ifopt
+#else
+#define TWB_IFOPT_NS TWB_IFOPT_EXTERNAL
+#endif
 
 namespace towr_b200 {
 
@@ -104,12 +246,18 @@ class BatchedProblem {
   BatchedProblem& operator=(const BatchedProblem&) = delete;
 
   // ifopt::Problem::SetVariables(const double*) for instance b
-  void SetVariables(int b, const double* x) { std::copy(x, x + n_, X.begin() + (size_t)b * n_); }
+  void SetVariables(int b, const double* x) { std::copy(x, x + n_, X.begin() + (size_t)b * n_); dirty_ = true; }
   // one batched evaluation: Problem::EvaluateConstraints + EvalNonzerosOfJacobian + EvaluateCostFunction[Gradient]
   void Evaluate(unsigned flags = TWB_EVAL_ALL) {
     if (!batch_) throw std::runtime_error("BatchedProblem: no device batch");
     Check(twb_batch_eval_host(batch_, X.data(), G.data(), JAC.data(), COST.data(), GRAD.data(), STATUS.data(), flags), "twb_batch_eval_host");
+    if (flags == TWB_EVAL_ALL) dirty_ = false;
   }
+  // The views evaluate lazily: a SetVariables on any view marks the batch dirty, the next Get* of a constraint / cost view
+  // runs ONE batched evaluation for all instances (a lock-step driver sets all iterates first).  Without a device batch
+  // (structure-only use) the host arrays are served as they are.
+  void MarkDirty() { dirty_ = true; }
+  void EnsureEvaluated() { if (dirty_ && batch_) Evaluate(TWB_EVAL_ALL); }
   // ---- solution post-processing of the current X (fpowr) ----
   // fpowr::GetTrajectory(solution, dt) for every instance: [B][n_samples][19 + 13 n_ee]
   std::vector<double> SampleTrajectory(double dt, int* n_samples = nullptr, int* n_values = nullptr) {
@@ -161,47 +309,64 @@ class BatchedProblem {
   twb_problem* prob_ = nullptr;
   twb_batch* batch_ = nullptr;
   int B_, n_ = 0, m_ = 0, nnz_ = 0;
+  bool dirty_ = false;
   std::vector<int> row_ptr_, iRow_, jCol_;
   std::vector<double> xl_, xu_, gl_, gu_;
 };
 
-// "base-lin", "ee-motion_0", "ee-schedule1", ... (NodesVariables / PhaseDurations) of instance b
-class GpuVariableSet : public twb_ifopt::VariableSet {
+namespace ifo = TWB_IFOPT_NS;
+
+// "base-lin", "ee-motion_0", "ee-schedule1", ... (NodesVariables / PhaseDurations, nodes_variables.cc:40-72,
+// phase_durations.cc:68-110) of instance b: a window of row b of X
+class GpuVariableSet : public ifo::VariableSet {
  public:
-  GpuVariableSet(const BatchedProblem* p, int b, const std::string& name, int col0, int n) : VariableSet(n, name), p_(p), b_(b), col0_(col0) {}
-  twb_ifopt::VectorXd GetValues() const override {
+  GpuVariableSet(BatchedProblem* p, int b, const std::string& name, int col0, int n) : VariableSet(n, name), p_(p), b_(b), col0_(col0) {}
+  VectorXd GetValues() const override {
+    VectorXd v(GetRows());
     const double* x = p_->X.data() + (size_t)b_ * p_->GetNumberOfOptimizationVariables() + col0_;
-    return twb_ifopt::VectorXd(x, x + GetRows());
-  }
-  twb_ifopt::VecBound GetBounds() const override {
-    twb_ifopt::VecBound v(GetRows());
-    for (int i = 0; i < GetRows(); ++i) v[i] = {p_->x_lower()[col0_ + i], p_->x_upper()[col0_ + i]};
+    for (int i = 0; i < GetRows(); ++i) v(i) = x[i];
     return v;
+  }
+  VecBound GetBounds() const override {
+    VecBound v;
+    for (int i = 0; i < GetRows(); ++i) v.push_back(ifo::Bounds(p_->x_lower()[col0_ + i], p_->x_upper()[col0_ + i]));
+    return v;
+  }
+  // NodesVariables::SetVariables (nodes_variables.cc:65-72): the values move into the batch's iterate; the next Get* of a
+  // constraint or cost view re-evaluates the batch
+  void SetVariables(const VectorXd& x) override {
+    double* dst = p_->X.data() + (size_t)b_ * p_->GetNumberOfOptimizationVariables() + col0_;
+    for (int i = 0; i < GetRows(); ++i) dst[i] = x(i);
+    p_->MarkDirty();
   }
   int col0() const { return col0_; }
  private:
-  const BatchedProblem* p_; int b_, col0_;
+  BatchedProblem* p_; int b_, col0_;
 };
 
 // "dynamic", "rangeofmotion-0", "terrain-ee-motion_0", ... (towr::DynamicConstraint etc.) of instance b
-class GpuConstraintSet : public twb_ifopt::ConstraintSet {
+class GpuConstraintSet : public ifo::ConstraintSet {
  public:
-  GpuConstraintSet(const BatchedProblem* p, int b, const std::string& name, int row0, int rows,
+  GpuConstraintSet(BatchedProblem* p, int b, const std::string& name, int row0, int rows,
                    std::map<std::string, std::pair<int, int>> var_cols)
       : ConstraintSet(rows, name), p_(p), b_(b), row0_(row0), var_cols_(std::move(var_cols)) {}
-  twb_ifopt::VectorXd GetValues() const override {
+  VectorXd GetValues() const override {
+    p_->EnsureEvaluated();
+    VectorXd v(GetRows());
     const double* g = p_->G.data() + (size_t)b_ * p_->GetNumberOfConstraints() + row0_;
-    return twb_ifopt::VectorXd(g, g + GetRows());
+    for (int i = 0; i < GetRows(); ++i) v(i) = g[i];
+    return v;
   }
-  twb_ifopt::VecBound GetBounds() const override {
-    twb_ifopt::VecBound v(GetRows());
-    for (int i = 0; i < GetRows(); ++i) v[i] = {p_->g_lower()[row0_ + i], p_->g_upper()[row0_ + i]};
+  VecBound GetBounds() const override {
+    VecBound v;
+    for (int i = 0; i < GetRows(); ++i) v.push_back(ifo::Bounds(p_->g_lower()[row0_ + i], p_->g_upper()[row0_ + i]));
     return v;
   }
   // the (rows x n_var_set) block of this set's Jacobian w.r.t. one variable set: a slice of the CSR value array
-  void FillJacobianBlock(std::string var_set, twb_ifopt::Jacobian& jac) const override {
+  void FillJacobianBlock(std::string var_set, Jacobian& jac) const override {
     auto it = var_cols_.find(var_set);
     if (it == var_cols_.end()) return;
+    p_->EnsureEvaluated();
     const int c0 = it->second.first, nc = it->second.second;
     const double* v = p_->JAC.data() + (size_t)b_ * p_->nnz();
     for (int r = 0; r < GetRows(); ++r)
@@ -211,20 +376,30 @@ class GpuConstraintSet : public twb_ifopt::ConstraintSet {
       }
   }
  private:
-  const BatchedProblem* p_; int b_, row0_;
+  // the reference's constraints fetch their variable sets here (e.g. force_constraint.cc:51-60); the views need nothing
+  void InitVariableDependedQuantities(const VariablesPtr& x_init) override { (void)x_init; }
+  BatchedProblem* p_; int b_, row0_;
   std::map<std::string, std::pair<int, int>> var_cols_;
 };
 
-// the summed NodeCost terms of instance b (ifopt sums all cost terms into one row)
-class GpuCostTerm : public twb_ifopt::CostTerm {
+// the summed NodeCost terms of instance b (ifopt sums all cost terms into one row; node_cost.cc:53-76)
+class GpuCostTerm : public ifo::CostTerm {
  public:
-  GpuCostTerm(const BatchedProblem* p, int b) : CostTerm(1, "cost"), p_(p), b_(b) {}
-  double GetCost() const override { return p_->COST[b_]; }
-  twb_ifopt::VectorXd GetValues() const override { return {GetCost()}; }
-  twb_ifopt::VecBound GetBounds() const override { return {{-twb_ifopt::inf, +twb_ifopt::inf}}; }
-  const double* GetGradient() const { return p_->GRAD.data() + (size_t)b_ * p_->GetNumberOfOptimizationVariables(); }
+  GpuCostTerm(BatchedProblem* p, int b, std::map<std::string, std::pair<int, int>> var_cols) : CostTerm("cost"), p_(p), b_(b), var_cols_(std::move(var_cols)) {}
+  double Cost() const { return GetCost(); }
+  // NodeCost::FillJacobianBlock (node_cost.cc:65-76): the gradient entries of one variable set
+  void FillJacobianBlock(std::string var_set, Jacobian& jac) const override {
+    auto it = var_cols_.find(var_set);
+    if (it == var_cols_.end()) return;
+    p_->EnsureEvaluated();
+    const double* gr = GetGradient();
+    for (int c = 0; c < it->second.second; ++c) if (gr[it->second.first + c] != 0.0) jac.coeffRef(0, c) = gr[it->second.first + c];
+  }
+  const double* GetGradient() const { p_->EnsureEvaluated(); return p_->GRAD.data() + (size_t)b_ * p_->GetNumberOfOptimizationVariables(); }
  private:
-  const BatchedProblem* p_; int b_;
+  double GetCost() const override { p_->EnsureEvaluated(); return p_->COST[b_]; }
+  BatchedProblem* p_; int b_;
+  std::map<std::string, std::pair<int, int>> var_cols_;
 };
 
 // towr::NlpFormulation: same public fields; GetVariableSets / GetConstraints / GetCosts return the GPU-backed views
@@ -232,9 +407,9 @@ struct State3 { double p[3] = {0, 0, 0}, v[3] = {0, 0, 0}; };
 struct BaseState { State3 lin, ang; };
 class NlpFormulation {
  public:
-  using VariablePtrVec = std::vector<std::shared_ptr<twb_ifopt::VariableSet>>;
-  using ConstraintPtrVec = std::vector<std::shared_ptr<twb_ifopt::ConstraintSet>>;
-  using CostPtrVec = std::vector<std::shared_ptr<twb_ifopt::CostTerm>>;
+  using VariablePtrVec = std::vector<std::shared_ptr<ifo::VariableSet>>;     // nlp_formulation.h:76-78
+  using ConstraintPtrVec = std::vector<std::shared_ptr<ifo::ConstraintSet>>;
+  using CostPtrVec = std::vector<std::shared_ptr<ifo::CostTerm>>;
 
   explicit NlpFormulation(int robot = TWB_MONOPED, int terrain = TWB_FLAT) { Check(twb_spec_default(&params_, robot), "twb_spec_default"); params_.terrain = terrain; }
 
@@ -258,7 +433,15 @@ class NlpFormulation {
     for (int e = 0; e < s.n_ee; ++e) for (int k = 0; k < 3; ++k) s.initial_ee_W[e][k] = initial_ee_W_[e][k];
     return s;
   }
-  static VariablePtrVec GetVariableSets(const BatchedProblem& p, int b) {
+  static std::map<std::string, std::pair<int, int>> VariableColumns(const BatchedProblem& p) {
+    std::map<std::string, std::pair<int, int>> cols; char name[64]; int a0, na;
+    for (int i = 0; i < twb_layout_num_variable_sets(p.handle()); ++i) {
+      Check(twb_layout_variable_set(p.handle(), i, name, 64, &a0, &na), "twb_layout_variable_set");
+      cols[name] = {a0, na};
+    }
+    return cols;
+  }
+  static VariablePtrVec GetVariableSets(BatchedProblem& p, int b) {
     VariablePtrVec v; char name[64]; int c0, nc;
     for (int i = 0; i < twb_layout_num_variable_sets(p.handle()); ++i) {
       Check(twb_layout_variable_set(p.handle(), i, name, 64, &c0, &nc), "twb_layout_variable_set");
@@ -266,20 +449,74 @@ class NlpFormulation {
     }
     return v;
   }
-  static ConstraintPtrVec GetConstraints(const BatchedProblem& p, int b) {
-    std::map<std::string, std::pair<int, int>> cols; char name[64]; int a0, na;
-    for (int i = 0; i < twb_layout_num_variable_sets(p.handle()); ++i) {
-      Check(twb_layout_variable_set(p.handle(), i, name, 64, &a0, &na), "twb_layout_variable_set");
-      cols[name] = {a0, na};
-    }
-    ConstraintPtrVec v;
+  static ConstraintPtrVec GetConstraints(BatchedProblem& p, int b) {
+    const auto cols = VariableColumns(p);
+    ConstraintPtrVec v; char name[64]; int a0, na;
     for (int i = 0; i < twb_layout_num_constraint_sets(p.handle()); ++i) {
       Check(twb_layout_constraint_set(p.handle(), i, name, 64, &a0, &na), "twb_layout_constraint_set");
       v.push_back(std::make_shared<GpuConstraintSet>(&p, b, name, a0, na, cols));
     }
     return v;
   }
-  static CostPtrVec GetCosts(const BatchedProblem& p, int b) { return {std::make_shared<GpuCostTerm>(&p, b)}; }
+  static CostPtrVec GetCosts(BatchedProblem& p, int b) { return {std::make_shared<GpuCostTerm>(&p, b, VariableColumns(p))}; }
+};
+
+// ifopt::Problem (ifopt/problem.h) for instance b of a batch, assembled the way towr/test/hopper_example.cc:70-75 does
+// (AddVariableSet / AddConstraintSet / AddCostSet of everything the formulation returns) and offering what
+// IpoptAdapter (Ipopt::TNLP) calls.  Every Evaluate* first moves x into the batch (SetVariables) — the batched
+// evaluation behind it runs once per new iterate, for all instances of the batch.
+class GpuProblem {
+ public:
+  using VectorXd = ifo::Component::VectorXd;
+  using VecBound = ifo::Component::VecBound;
+  using Jacobian = ifo::Component::Jacobian;
+  GpuProblem(BatchedProblem& p, int b)
+      : p_(&p), b_(b), variables_(std::make_shared<ifo::Composite>("variable-sets", false)), constraints_("constraint-sets", false), costs_("cost-terms", true) {
+    for (auto& v : NlpFormulation::GetVariableSets(p, b)) AddVariableSet(v);
+    for (auto& c : NlpFormulation::GetConstraints(p, b)) AddConstraintSet(c);
+    for (auto& c : NlpFormulation::GetCosts(p, b)) AddCostSet(c);
+  }
+  void AddVariableSet(std::shared_ptr<ifo::VariableSet> variable_set) { variables_->AddComponent(variable_set); }
+  void AddConstraintSet(std::shared_ptr<ifo::ConstraintSet> constraint_set) { constraint_set->LinkWithVariables(variables_); constraints_.AddComponent(constraint_set); }
+  void AddCostSet(std::shared_ptr<ifo::CostTerm> cost_set) { cost_set->LinkWithVariables(variables_); costs_.AddComponent(cost_set); }
+  void SetVariables(const double* x) { p_->SetVariables(b_, x); }
+  int GetNumberOfOptimizationVariables() const { return variables_->GetRows(); }
+  int GetNumberOfConstraints() const { return constraints_.GetRows(); }
+  bool HasCostTerms() const { return twb_problem_has_cost(p_->handle()) != 0; }
+  VecBound GetBoundsOnOptimizationVariables() const { return variables_->GetBounds(); }
+  VecBound GetBoundsOnConstraints() const { return constraints_.GetBounds(); }
+  VectorXd GetVariableValues() const { return variables_->GetValues(); }
+  double EvaluateCostFunction(const double* x) { SetVariables(x); p_->EnsureEvaluated(); return p_->COST[b_]; }
+  VectorXd EvaluateCostFunctionGradient(const double* x) {
+    SetVariables(x); p_->EnsureEvaluated();
+    VectorXd g(p_->GetNumberOfOptimizationVariables());
+    for (int i = 0; i < g.size(); ++i) g(i) = p_->GRAD[(size_t)b_ * p_->GetNumberOfOptimizationVariables() + i];
+    return g;
+  }
+  VectorXd EvaluateConstraints(const double* x) { SetVariables(x); return constraints_.GetValues(); }
+  // values in the order of the structure IPOPT was given (row-major, ascending column): the CSR value array itself
+  void EvalNonzerosOfJacobian(const double* x, double* values) {
+    SetVariables(x); p_->EnsureEvaluated();
+    std::copy(p_->JAC.begin() + (size_t)b_ * p_->nnz(), p_->JAC.begin() + (size_t)(b_ + 1) * p_->nnz(), values);
+  }
+  // the sparsity structure (Problem::GetJacobianOfConstraints as IpoptAdapter::eval_jac_g reads it)
+  const std::vector<int>& GetJacobianRows() const { return p_->iRow(); }
+  const std::vector<int>& GetJacobianCols() const { return p_->jCol(); }
+  Jacobian GetJacobianOfConstraints() const {
+    p_->EnsureEvaluated();
+    Jacobian jac(p_->GetNumberOfConstraints(), p_->GetNumberOfOptimizationVariables());
+    const double* v = p_->JAC.data() + (size_t)b_ * p_->nnz();
+    for (int k = 0; k < p_->nnz(); ++k) jac.coeffRef(p_->iRow()[k], p_->jCol()[k]) = v[k];
+    return jac;
+  }
+  const ifo::Composite& GetConstraints() const { return constraints_; }
+  const ifo::Composite& GetCosts() const { return costs_; }
+  ifo::Composite::Ptr GetOptVariables() const { return variables_; }
+  void PrintCurrent() const { variables_->PrintAll(); constraints_.PrintAll(); costs_.PrintAll(); }
+ private:
+  BatchedProblem* p_; int b_;
+  ifo::Composite::Ptr variables_;
+  ifo::Composite constraints_, costs_;
 };
 
 }  // namespace towr_b200

@@ -80,6 +80,18 @@ int main(int argc, char** argv) {
     std::vector<double> traj = nlp.SampleTrajectory(0.5, &ns, &nvt);
     REQUIRE(ns == 5 && nvt == 32 && std::fabs(traj[((size_t)b * ns + 2) * nvt + 0] - ig[((size_t)b * 2 + 1) * 49 + 1]) < 1e-13);   // base x at t = 1
     std::printf("footstep_states %d\n", n_states[b]);
+    // ifopt::Problem view of instance b as IpoptAdapter drives it: a new iterate re-evaluates the batch lazily, once
+    GpuProblem ip(nlp, b);
+    std::vector<double> x(nlp.X.begin() + (size_t)b * 339, nlp.X.begin() + (size_t)(b + 1) * 339);
+    for (int i = 0; i < 339; ++i) x[i] += 0.01 * std::sin(1.0 + i);
+    twb_ifopt::VectorXd g1 = ip.EvaluateConstraints(x.data());
+    std::vector<double> vals(nlp.nnz());
+    ip.EvalNonzerosOfJacobian(x.data(), vals.data());
+    nlp.SetVariables(b, x.data()); nlp.Evaluate(TWB_EVAL_ALL);     // the explicit route
+    for (int i = 0; i < 399; ++i) REQUIRE(g1(i) == nlp.G[(size_t)b * 399 + i]);
+    for (int k = 0; k < nlp.nnz(); ++k) REQUIRE(vals[k] == nlp.JAC[(size_t)b * nlp.nnz() + k]);
+    REQUIRE(std::fabs(g1(10 + 3)) > 1e-6);                          // the perturbed iterate violates the dynamics
+    REQUIRE(ip.GetConstraints().GetComponent("dynamic")->GetJacobian().nonZeros() == nlp.row_ptr()[10 + 132] - nlp.row_ptr()[10]);
   }
   std::printf("ok\n");
   return 0;

@@ -37,6 +37,18 @@ def test_cpp_shim_structure_and_block_slicing():
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
 
 
+def test_ifopt_conformance():
+    """The Gpu* views compiled against a verbatim restatement of ifopt 2.0's class declarations (external-ifopt mode of the
+    header): concrete, reference signatures, driven through ifopt's own Composite / ConstraintSet / CostTerm methods."""
+    exe = os.path.join(os.path.dirname(EXE), "ifopt_conformance")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "cpp", "ifopt_conformance.cc"), "-o", exe,
+                           "-L" + libdir, "-ltowr_b200", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_shim_evaluation_matches_python_binding():
     _build()

@@ -330,7 +330,7 @@ def test_csv_grid_terrain():
             X[0:8, s] = np.arange(1, 9) * 0.17 - 0.001
             X[8:16, s] = np.arange(1, 9) * 0.17 + 0.001
         if name == "ee-motion_1":                # coordinates in (-res, 0): cell 0 of the reference (size_t truncation), not "outside"
-            X[16:24, s] = -0.05 - 0.01 * np.arange(8)[:, None]
+            X[16:24, s] = -0.05 - 0.01 * np.arange(8); X[20:28, s + 1] = -0.02 - 0.015 * np.arange(8)
     grid[0, :] += 0.04; grid[:, 0] += 0.04
     bt = p.batch(B); bt.set_terrains(terr); bt.set_grid_terrain(grid)
     out = bt.eval_host(X)

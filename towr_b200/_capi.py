@@ -74,6 +74,7 @@ def _load():
         "twb_problem_row_ptr": (C.c_int, [P, I]),
         "twb_problem_bounds": (C.c_int, [P, D, D, D, D]),
         "twb_problem_x0": (C.c_int, [P, D]),
+        "twb_problem_has_cost": (C.c_int, [P]),
         "twb_problem_goal_instances": (C.c_int, [P, C.c_int, D, D, D, D]),
         "twb_layout_num_variable_sets": (C.c_int, [P]),
         "twb_layout_variable_set": (C.c_int, [P, C.c_int, C.c_char_p, C.c_int, I, I]),

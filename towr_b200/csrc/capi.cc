@@ -124,6 +124,8 @@ int twb_problem_bounds(const twb_problem* p, double* xl, double* xu, double* gl,
   if (gu) std::memcpy(gu, p->f.g_upper.data(), sizeof(double) * p->f.m);
   return TWB_OK;
 }
+int twb_problem_has_cost(const twb_problem* p) { return (p && p->f.has_cost) ? 1 : 0; }
+
 int twb_problem_x0(const twb_problem* p, double* x0) {
   if (!p || !x0) return Fail(TWB_ERR_INVALID, "null argument");
   std::memcpy(x0, p->f.x0.data(), sizeof(double) * p->f.n);

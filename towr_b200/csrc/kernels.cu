@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ G
     if (tid < 64) {                       // the 32 GT rows of this CTA: two 128-byte lines each
       const int r = r0 + (tid >> 1);
       if (r < m) DiscardLine(src + (size_t)r * 32 + (tid & 1) * 16);
-    } else if (XT && tid < 128) {         // XT rows of this tile, 32 per CTA of the tile (CTAs wrap around when m < n)
+    } else if (XT && tid < 128 && b0 + 32 <= nb) {   // XT rows of this tile, 32 per CTA of the tile (CTAs wrap around when m < n); a ragged last tile keeps its lines: its padded lanes are never rewritten
       const double* xt = XT + ((size_t)blockIdx.y * (n + 1)) * 32;
       for (int r = r0 + ((tid - 64) >> 1); r < n; r += gridDim.x * 32) DiscardLine(xt + (size_t)r * 32 + (tid & 1) * 16);
     }
@@ -812,6 +812,7 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
     else
 #endif
     StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, threadIdx.x, blockDim.x);
+#ifndef TWB_EXP_NOSINGLES   // (timing experiment, profiles/README.md round 2: what the single-element stores cost)
     if (threadIdx.x < 32 && rs.count > 0) {
       const bool active = lane < n_inst && (lane % nc) == q;
       double* o = jac_tile + (size_t)lane * P.nnz;
@@ -825,6 +826,7 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
         ForEachEntry(P.pairs + rs.first + 32, P.coefs + rs.first + 32, rs.count - 32, lane,
                      [&](int off, int d, double c) { if (active) StoreOut(o + off, cta_smem[d * kLD + lane] * c); });
     }
+#endif
   }
 }
 // non-finite check of this lane's own column (rows 1 .. n_rows-1); flags instance b
