@@ -52,7 +52,11 @@ enum { TWB_FLAT = 0, TWB_BLOCK = 1, TWB_STAIRS = 2, TWB_GAP = 3, TWB_SLOPE = 4,
        /* towr::HeightMapFromCSV (towr/include/towr/terrain/height_map_from_csv.h:29-111): a cell-constant height grid
         * with one-sided edge slopes; the grid is per-batch data (twb_batch_set_grid_terrain), usable as a per-instance
         * terrain id in twb_batch_set_terrains but not as twb_spec.terrain */
-       TWB_GRID_CSV = 7 };
+       TWB_GRID_CSV = 7,
+       /* towr `Grid` (towr/include/towr/terrain/grid_height_map.h:16-59, what fpowr's footstep_plan_server.cc:155 plans on):
+        * a grid_map elevation layer, bilinear height in float, FLT_MAX outside the map, central-difference slopes with
+        * eps = resolution / 6; per-batch data (twb_batch_set_grid_map), per-instance terrain id like TWB_GRID_CSV */
+       TWB_GRID_MAP = 8 };
 
 /* towr::Parameters::ConstraintName, towr/include/towr/parameters.h:139-147 */
 enum { TWB_C_DYNAMIC = 0, TWB_C_EE_ROM = 1, TWB_C_TOTAL_TIME = 2, TWB_C_TERRAIN = 3,
@@ -179,6 +183,12 @@ int twb_batch_set_terrains(twb_batch* b, const int* terrain_ids);
  * (HeightMapFromCSV::res_m_p_cell_), uploaded to the device.  NULL removes it (every height is then 0). */
 int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, int cols);
 
+/* The elevation layer of TWB_GRID_MAP for this batch: heights[ix * size_y + iy] (float, metres) = layer(ix, iy) of a
+ * grid_map::GridMap with `resolution` metres per cell centred at (pos_x, pos_y); index 0 is the cell with the LARGEST
+ * coordinate (grid_map convention), buffer start index (0, 0).  NULL removes it. */
+int twb_batch_set_grid_map(twb_batch* b, const float* heights, int size_x, int size_y, double resolution,
+                           double pos_x, double pos_y);
+
 #define TWB_EVAL_G 1u     /* constraint values        (Problem::EvaluateConstraints)       */
 #define TWB_EVAL_JAC 2u   /* Jacobian values          (Problem::EvalNonzerosOfJacobian)    */
 #define TWB_EVAL_COST 4u  /* cost + gradient          (EvaluateCostFunction[Gradient])     */
@@ -224,6 +234,29 @@ int twb_batch_initial_guess_host(twb_batch* b, const double* x, const double* ti
 int twb_problem_footstep_plan_dims(const twb_problem* p, int* max_states, int* n_values);
 /* x: host [B][n]; n_states: host [B]; out: host [B][max_states][n_values] (unused states are 0) */
 int twb_batch_footstep_plan_host(twb_batch* b, const double* x, double time_horizon, int* n_states, double* out);
+
+/* fpowr::NearestPlaneLookup::GetNearestPlaneIndex (fpowr/include/fpowr/nearest_plane_lookup.h:62-84) for every foot of every
+ * footstep state of a plan returned by twb_batch_footstep_plan_host: contact_set[b][state][foot] = index of the polygon
+ * nearest to the foot's (x, y) — boost::geometry::distance(point, polygon): 0 inside / on the ring, else the distance to the
+ * nearest ring segment; the first polygon wins ties — or -1 for a foot in the air and for unused states
+ * (footstep_plan_extractor.h:106-116).  Polygons are plain arrays (what PlanarRegionsToPolygons, :24-55, produces from the
+ * PlanarTerrain message): polygon k owns vertices[poly_offsets[k] .. poly_offsets[k+1]-1][2]; like bg::model::polygon's
+ * default (closed) ring, the closing segment exists only if the first vertex is repeated at the end.
+ * plan: host [B][max_states][2 + 4 n_ee]; n_states: host [B]; contact_set: host [B][max_states][n_ee]. */
+int twb_batch_nearest_planes_host(twb_batch* b, const double* plan, const int* n_states, const int* poly_offsets, int n_polys,
+                                  const double* vertices, int* contact_set);
+
+/* ---- the two ifopt components of towr that no Parameters::ConstraintName / CostName reaches ---------------------------
+ * towr::LinearEqualityConstraint (towr/src/linear_constraint.cc:35-73) on variable set `var_set` (index of
+ * twb_layout_variable_set): g[b][rows] = M x_set for every instance (M: host [rows][n_cols], row-major, n_cols = size of
+ * the set); its bounds are -v[i] on both sides and its Jacobian block is M.sparseView(): the non-zeros of M, constant.
+ * x: host [B][n]; g: host [B][rows]. */
+int twb_batch_linear_equality_host(twb_batch* b, const double* x, int var_set, const double* M, int rows, double* g);
+/* towr::SoftConstraint (towr/src/soft_constraint.cc:34-72) around constraint set `constraint_set` (index of
+ * twb_layout_constraint_set): cost[b] = 0.5 (g - b)^T W (g - b) with b = (upper + lower) / 2 of the set's bounds and
+ * grad[b][n] = J^T W (g - b), from the g / Jacobian values of the LAST twb_batch_eval_host(TWB_EVAL_G | TWB_EVAL_JAC) of this
+ * batch (they are still on the device).  weights: host [rows of the set] or NULL (ones, the reference's default). */
+int twb_batch_soft_constraint_host(twb_batch* b, int constraint_set, const double* weights, double* cost, double* grad);
 
 /* number of kernel launches one twb_batch_eval_device(flags) enqueues */
 int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags);

@@ -35,6 +35,7 @@
 #include <array>
 #include <cassert>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -231,6 +232,70 @@ struct CsvGrid {
 };
 CsvGrid g_grid;
 
+// towr `Grid` (towr/include/towr/terrain/grid_height_map.h:16-59, the terrain fpowr instantiates at
+// footstep_plan_server.cc:155): heights come from grid_map::GridMap::atPosition("elevation", p, INTER_LINEAR) in FLOAT,
+// FLT_MAX outside the map (the caught std::out_of_range, :41-45), slopes are central differences of those floats with
+// eps = resolution / 6 (:24, :49-61).  grid_map is an un-vendored ROS dependency (ros-noetic-grid-map 1.6.x); its
+// algorithm is restated from grid_map_core/src/{GridMap.cpp, GridMapMath.cpp}: atPosition -> atPositionLinearInterpolated
+// (bilinear over the four cell centres around p, weights in double, result stored to float) and, when one of the four
+// cells is outside, INTER_NEAREST (getIndex + at), else out_of_range.  Geometry: cell (ix, iy) has its centre at
+// pos + 0.5 * length - 0.5 * res - res * (ix, iy) (index 0 = largest coordinate); buffer start index (0, 0) assumed.
+// Data: row-major [size_x][size_y] floats (layer(ix, iy)).  Parity unpinned (no grid_map source or build in this image).
+struct GridMapTerrain {
+  std::vector<float> h; int sx = 0, sy = 0; double res = 1.0, px = 0.0, py = 0.0;
+  double Lx() const { return sx * res; }
+  double Ly() const { return sy * res; }
+  bool WithinMap(double x, double y) const {   // checkIfPositionWithinMap
+    const double tx = -(x - px - 0.5 * Lx()), ty = -(y - py - 0.5 * Ly());
+    return tx >= 0.0 && ty >= 0.0 && tx < Lx() && ty < Ly();
+  }
+  void IndexOf(double x, double y, int* ix, int* iy) const {   // getIndexFromPosition without the range checks: (int) truncates toward zero
+    const double vx = (x - 0.5 * Lx() - px) / res, vy = (y - 0.5 * Ly() - py) / res;
+    *ix = (int)(-vx); *iy = (int)(-vy);
+  }
+  void CentreOf(int ix, int iy, double* x, double* y) const { *x = px + (0.5 * Lx() - 0.5 * res) + res * (double)(-ix); *y = py + (0.5 * Ly() - 0.5 * res) + res * (double)(-iy); }
+  bool Linear(double x, double y, float* value) const {   // atPositionLinearInterpolated
+    int ix[4], iy[4]; size_t shift[4]; double cx, cy;
+    IndexOf(x, y, &ix[0], &iy[0]);
+    CentreOf(ix[0], iy[0], &cx, &cy);
+    bool dir;
+    if (x >= cx) { ix[1] = ix[0] - 1; iy[1] = iy[0]; dir = true; } else { ix[1] = ix[0] + 1; iy[1] = iy[0]; dir = false; }
+    if (y >= cy) {
+      ix[2] = ix[0]; iy[2] = iy[0] - 1;
+      if (dir) { shift[0] = 0; shift[1] = 1; shift[2] = 2; shift[3] = 3; } else { shift[0] = 1; shift[1] = 0; shift[2] = 3; shift[3] = 2; }
+    } else {
+      ix[2] = ix[0]; iy[2] = iy[0] + 1;
+      if (dir) { shift[0] = 2; shift[1] = 3; shift[2] = 0; shift[3] = 1; } else { shift[0] = 3; shift[1] = 2; shift[2] = 1; shift[3] = 0; }
+    }
+    ix[3] = ix[1]; iy[3] = iy[2];
+    const size_t buffer = (size_t)sx * sy;
+    float f[4];
+    for (int i = 0; i < 4; ++i) {
+      // getLinearIndexFromIndex (column-major Eigen matrix: iy * size_x + ix) in size_t: a negative ix with iy >= 1 wraps into
+      // the previous column like in grid_map; linear indices >= the buffer size are rejected here (grid_map's `>` lets
+      // index == size through, which reads past the buffer: undefined there)
+      const size_t lin = (size_t)((long long)iy[shift[i]] * sx + ix[shift[i]]);
+      if (lin >= buffer) return false;
+      f[i] = h[(lin % (size_t)sx) * sy + lin / (size_t)sx];
+    }
+    CentreOf(ix[shift[0]], iy[shift[0]], &cx, &cy);
+    const double rx = (x - cx) / res, ry = (y - cy) / res, fx = 1.0 - rx, fy = 1.0 - ry;
+    *value = f[0] * fx * fy + f[1] * rx * fy + f[2] * fx * ry + f[3] * rx * ry;
+    return true;
+  }
+  double Height(double x, double y) const {   // grid_height_map.h:29-46
+    float height;
+    if (Linear(x, y, &height)) return height;
+    int ix, iy; IndexOf(x, y, &ix, &iy);
+    if (WithinMap(x, y) && ix >= 0 && iy >= 0 && ix < sx && iy < sy) { height = h[(size_t)ix * sy + iy]; return height; }
+    height = std::numeric_limits<float>::max();
+    return height;
+  }
+  double Hx(double x, double y) const { const double eps = res / 6.0; float r = (float)Height(x + eps, y), l = (float)Height(x - eps, y); return (r - l) / (2 * eps); }   // :48-53
+  double Hy(double x, double y) const { const double eps = res / 6.0; float u = (float)Height(x, y + eps), d = (float)Height(x, y - eps); return (u - d) / (2 * eps); }   // :55-60
+};
+GridMapTerrain g_gridmap;
+
 struct Terrain {
   int id = TWB_FLAT;
   double flat_height = 0.0;
@@ -239,6 +304,7 @@ struct Terrain {
   double Height(double x, double y) const {
     switch (id) {
       case TWB_GRID_CSV: return g_grid.Height(x, y);
+      case TWB_GRID_MAP: return g_gridmap.Height(x, y);
       case TWB_FLAT: return flat_height;
       case TWB_BLOCK: {  // height_map_examples.cc:40-53
         const double block_start = 0.7, length = 3.5, height = 0.5, eps = 0.03; const double slope = height / eps;
@@ -280,6 +346,7 @@ struct Terrain {
   double Hx(double x, double y) const {
     switch (id) {
       case TWB_GRID_CSV: return g_grid.Hx(x, y);
+      case TWB_GRID_MAP: return g_gridmap.Hx(x, y);
       case TWB_BLOCK: { const double block_start = 0.7, height = 0.5, eps = 0.03; const double slope = height / eps;
         double d = 0.0; if (block_start <= x && x <= block_start + eps) d = slope; return d; }  // :55-65
       case TWB_GAP: { GapC g; double d = 0.0; if (g.gap_start <= x && x <= g.gap_end_x) d = 2 * g.a * x + g.b; return d; }  // :100-109
@@ -294,6 +361,7 @@ struct Terrain {
   double Hy(double x, double y) const {
     switch (id) {
       case TWB_GRID_CSV: return g_grid.Hy(x, y);
+      case TWB_GRID_MAP: return g_gridmap.Hy(x, y);
       case TWB_CHIMNEY: { const double x_start = 1.0, length = 1.5, slope = 3.0; const double x_end = x_start + length;
         double d = 0.0; if (x_start <= x && x <= x_end) d = slope; return d; }  // :172-181
       case TWB_CHIMNEY_LR: { const double x_start = 0.5, length = 1.0, slope = 2; const double x_end1 = x_start + length, x_end2 = x_start + 2 * length;
@@ -1498,6 +1566,65 @@ double oracle_terrain_height(int terrain, double x, double y) { Terrain t; t.id 
 // grid of the TWB_GRID_CSV terrain (process-global; set before evaluating)
 void oracle_set_grid(const double* heights, int rows, int cols) {
   g_grid.h.assign(heights, heights + (size_t)rows * cols); g_grid.rows = rows; g_grid.cols = cols;
+}
+void oracle_set_grid_map(const float* heights, int size_x, int size_y, double resolution, double pos_x, double pos_y) {
+  g_gridmap.h.assign(heights, heights + (size_t)size_x * size_y); g_gridmap.sx = size_x; g_gridmap.sy = size_y;
+  g_gridmap.res = resolution; g_gridmap.px = pos_x; g_gridmap.py = pos_y;
+}
+// fpowr::NearestPlaneLookup::GetNearestPlaneIndex (fpowr/include/fpowr/nearest_plane_lookup.h:62-84): boost::geometry::distance
+// (point, polygon), default cartesian strategies, restated (boost is un-vendored): covered_by -> 0 (winding strategy over
+// the ring's segments as given; a `closed` ring has no implicit closing segment), else min over the ring's segments of the
+// projected-point distance (comparable = squared, one sqrt at the end).  min_distance starts at DBL_MAX, strict `<`.
+static double PolygonDistanceRef(const double* v, int n, double px, double py) {
+  if (n <= 0) return std::numeric_limits<double>::max();
+  if (n == 1) return std::sqrt((px - v[0]) * (px - v[0]) + (py - v[1]) * (py - v[1]));
+  int winding = 0; bool touches = false; double best = std::numeric_limits<double>::max();
+  for (int i = 0; i + 1 < n; ++i) {
+    const double ax = v[2 * i], ay = v[2 * i + 1], bx = v[2 * i + 2], by = v[2 * i + 3];
+    const double side = (bx - ax) * (py - ay) - (px - ax) * (by - ay);
+    if (ay <= py) { if (by > py && side > 0) ++winding; } else if (by <= py && side < 0) --winding;
+    const double vx = bx - ax, vy = by - ay, wx = px - ax, wy = py - ay;
+    const double c1 = wx * vx + wy * vy;
+    double d2;
+    if (c1 <= 0) d2 = wx * wx + wy * wy;
+    else {
+      const double c2 = vx * vx + vy * vy;
+      if (c2 <= c1) d2 = (px - bx) * (px - bx) + (py - by) * (py - by);
+      else { const double b = c1 / c2, qx = ax + b * vx, qy = ay + b * vy; d2 = (px - qx) * (px - qx) + (py - qy) * (py - qy); }
+    }
+    if (d2 == 0.0) touches = true;
+    if (d2 < best) best = d2;
+  }
+  if (touches || winding != 0) return 0.0;
+  return std::sqrt(best);
+}
+int oracle_nearest_plane(const int* poly_offsets, int n_polys, const double* verts, double x, double y) {
+  double min_distance = std::numeric_limits<double>::max(); int nearest = -1;
+  for (int i = 0; i < n_polys; ++i) {
+    const double d = PolygonDistanceRef(verts + 2 * (size_t)poly_offsets[i], poly_offsets[i + 1] - poly_offsets[i], x, y);
+    if (d < min_distance) { min_distance = d; nearest = i; }
+  }
+  return nearest;
+}
+// towr::LinearEqualityConstraint::GetValues (linear_constraint.cc:46-51): M * x (Eigen dense row-times-vector: ascending column sum)
+void oracle_linear_equality(const double* M, int rows, int cols, const double* x_set, double* g) {
+  for (int r = 0; r < rows; ++r) { double acc = 0.0; for (int c = 0; c < cols; ++c) acc += M[(size_t)r * cols + c] * x_set[c]; g[r] = acc; }
+}
+// towr::SoftConstraint::GetValues / GetJacobian (soft_constraint.cc:53-72) of rows row0 .. row0+n_rows-1 of an evaluated problem:
+// cost = 0.5 (g-b)^T W (g-b), b = (upper+lower)/2 (:41-46); grad = J^T W (g-b)
+void oracle_soft_constraint(void* h, const double* g, const double* vals, int row0, int n_rows, const double* w, double* cost, double* grad) {
+  auto* p = static_cast<Problem*>(h);
+  std::vector<double> g_lo(p->m), g_up(p->m);
+  p->GBounds(g_lo.data(), g_up.data());
+  double c = 0.0;
+  for (int i = 0; i < p->n; ++i) grad[i] = 0.0;
+  for (int r = 0; r < n_rows; ++r) {
+    const double b = (g_up[row0 + r] + g_lo[row0 + r]) / 2.;
+    const double d = g[row0 + r] - b, wr = w ? w[r] : 1.0;
+    c += d * wr * d;
+    for (int k = p->row_ptr[row0 + r]; k < p->row_ptr[row0 + r + 1]; ++k) grad[p->col_idx[k]] += vals[k] * (wr * d);
+  }
+  *cost = 0.5 * c;
 }
 void oracle_terrain_point(int terrain, double x, double y, double* out3) {
   Terrain t; t.id = terrain; out3[0] = t.Height(x, y); out3[1] = t.DerivOfHeightWrt(0, x, y); out3[2] = t.DerivOfHeightWrt(1, x, y);

@@ -27,7 +27,7 @@ def lib():
         _lib.oracle_create.restype = C.c_void_p
         _lib.oracle_create.argtypes = [C.c_void_p]
         _lib.oracle_destroy.argtypes = [C.c_void_p]
-        for fn in ("oracle_dims", "oracle_structure", "oracle_bounds", "oracle_x0", "oracle_set_terrain", "oracle_set_grid",
+        for fn in ("oracle_dims", "oracle_structure", "oracle_bounds", "oracle_x0", "oracle_set_terrain", "oracle_set_grid", "oracle_set_grid_map", "oracle_linear_equality", "oracle_soft_constraint",
                    "oracle_terrain_point"):
             getattr(_lib, fn).restype = None
         _lib.oracle_eval.restype = C.c_int
@@ -144,6 +144,37 @@ def set_grid(heights):
     """Height grid of the GRID_CSV terrain (process-global in the oracle)."""
     h = np.ascontiguousarray(heights, np.float64)
     lib().oracle_set_grid(_p(h), C.c_int(h.shape[0]), C.c_int(h.shape[1]))
+
+
+def set_grid_map(heights, resolution, position=(0.0, 0.0)):
+    """Elevation layer of the GRID_MAP terrain (process-global in the oracle): heights[ix, iy] float32."""
+    h = np.ascontiguousarray(heights, np.float32)
+    lib().oracle_set_grid_map(_p(h), C.c_int(h.shape[0]), C.c_int(h.shape[1]), C.c_double(resolution), C.c_double(position[0]), C.c_double(position[1]))
+
+
+def nearest_plane(polygons, x, y):
+    """fpowr::NearestPlaneLookup::GetNearestPlaneIndex for one point; polygons: list of (k, 2) arrays."""
+    offs = np.zeros(len(polygons) + 1, np.int32)
+    offs[1:] = np.cumsum([len(q) for q in polygons])
+    verts = np.ascontiguousarray(np.concatenate([np.asarray(q, np.float64).reshape(-1, 2) for q in polygons]))
+    lib().oracle_nearest_plane.restype = C.c_int
+    return lib().oracle_nearest_plane(_p(offs), C.c_int(len(polygons)), _p(verts), C.c_double(x), C.c_double(y))
+
+
+def linear_equality(M, x_set):
+    M = np.ascontiguousarray(M, np.float64); x_set = np.ascontiguousarray(x_set, np.float64)
+    g = np.empty(M.shape[0])
+    lib().oracle_linear_equality(_p(M), C.c_int(M.shape[0]), C.c_int(M.shape[1]), _p(x_set), _p(g))
+    return g
+
+
+def soft_constraint(oracle, g, vals, row0, n_rows, weights=None):
+    """towr::SoftConstraint of rows row0.. of an evaluated Oracle instance: (cost, grad[n])."""
+    cost = C.c_double(); grad = np.empty(oracle.n)
+    w = None if weights is None else np.ascontiguousarray(weights, np.float64)
+    lib().oracle_soft_constraint(oracle._h, _p(np.ascontiguousarray(g)), _p(np.ascontiguousarray(vals)), C.c_int(row0), C.c_int(n_rows), _p(w),
+                                 C.byref(cost), _p(grad))
+    return cost.value, grad
 
 
 def terrain_point(terrain, x, y):

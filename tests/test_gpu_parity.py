@@ -351,6 +351,37 @@ def test_csv_grid_terrain():
     assert check_sets(flat["g"], ref0["g"], p.constraint_sets())[0] == 0
 
 
+def test_grid_map_terrain():
+    """towr `Grid` (grid_height_map.h:16-59: grid_map elevation layer, bilinear float heights, eps = res / 6 slopes) as
+    per-batch terrain data (TWB_GRID_MAP), mixed per instance with analytic terrains; terrain and force rows against the oracle."""
+    rng = np.random.default_rng(23)
+    sx, sy, res, pos = 60, 40, 0.1, (1.0, 0.0)
+    xs = pos[0] + sx * res / 2 - res / 2 - res * np.arange(sx)
+    ys = pos[1] + sy * res / 2 - res / 2 - res * np.arange(sy)
+    H = (0.15 * np.sin(2.0 * xs)[:, None] * np.cos(1.5 * ys)[None, :] + 0.02 * rng.standard_normal((sx, sy))).astype(np.float32)
+    B = 40
+    terr = np.where(np.arange(B) % 4 == 3, tb.SLOPE, tb.GRID_MAP).astype(np.int32)
+    f = tb.make_formulation("anymal_trot_block"); spec = f.to_spec(); p = tb.Problem(spec)
+    X = synthetic_iterates(p, B)
+    bt = p.batch(B); bt.set_terrains(terr); bt.set_grid_map(H, res, pos)
+    out = bt.eval_host(X)
+    oracle_lib.set_grid_map(H, res, pos)
+    ref = oracle_lib.batch_eval(spec, X, terrain_ids=terr)
+    assert ref["rc"] == 0
+    bad_j, strict_j, worst_j = check_rows(out["jac"], ref["jac"], p.row_ptr())
+    bad_g, strict_g, worst_g = check_sets(out["g"], ref["g"], p.constraint_sets())
+    PARITY_LOG.append({"case": "anymal_trot_block+grid_map", "B": B, "jac": {"violations": bad_j, "worst_err_over_tol": worst_j, "strict_miss_fraction": strict_j},
+                       "g": {"violations": bad_g, "worst_err_over_tol": worst_g, "strict_miss_fraction": strict_g}})
+    assert bad_j == 0 and bad_g == 0, (bad_j, bad_g, worst_j, worst_g)
+    assert not out["status"].any()
+    rp = p.row_ptr()
+    (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == "terrain-ee-motion_0"]
+    assert np.abs(out["jac"][:3, rp[r0]:rp[r0 + nr]]).max() > 0.05      # bilinear slopes showed up in the terrain rows
+    flat = p.batch(B); flat.set_terrains(terr)                          # without a layer every grid-map height is FLT_MAX: flagged, not silently flat
+    res0 = flat.eval_host(X)
+    assert (res0["status"][terr == tb.GRID_MAP] & 1).all() or np.abs(res0["g"][terr == tb.GRID_MAP]).max() > 1e30
+
+
 def test_trajectory_sampling_matches_oracle():
     """fpowr::GetTrajectory (footstep_plan_extractor.h:19-53) batched on the device: splines, quaternion, angular
     velocity / acceleration, contact flags — against the oracle, for fixed and for optimised phase durations."""
@@ -403,6 +434,52 @@ def test_footstep_plan_extraction_matches_oracle():
             assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, flags], ref[:, flags])
             assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref) + 1e-13), (name, b, np.abs(got - ref).max())
             assert abs(got[:, 1].sum() - T) < 1e-9                                     # durations tile the horizon
+
+
+def test_linear_equality_and_soft_constraint():
+    """towr::LinearEqualityConstraint and towr::SoftConstraint (the two ifopt components no Parameters enum reaches) on
+    the device against the oracle."""
+    rng = np.random.default_rng(10)
+    spec = tb.make_formulation("anymal_trot_block").to_spec(); p = tb.Problem(spec)
+    B = 45
+    X = synthetic_iterates(p, B)
+    bt = p.batch(B)
+    (_, c0, nc), = [v for v in p.variable_sets() if v[0] == "ee-motion_1"]
+    M = rng.standard_normal((9, nc)); M[rng.random(M.shape) < 0.5] = 0.0
+    g = bt.linear_equality(X, "ee-motion_1", M)
+    for b in range(B):
+        assert np.allclose(g[b], oracle_lib.linear_equality(M, X[b, c0:c0 + nc]), rtol=1e-12, atol=1e-14)
+    out = bt.eval_host(X)
+    o = oracle_lib.Oracle(spec)
+    for name, weights in (("dynamic", None), ("rangeofmotion-2", rng.uniform(0.5, 2.0, 81)), ("terrain-ee-motion_0", None)):
+        (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == name]
+        cost, grad = bt.soft_constraint(name, weights)
+        for b in (0, 7, B - 1):
+            r = o.eval(X[b])
+            c_ref, g_ref = oracle_lib.soft_constraint(o, r["g"], r["jac"], r0, nr, weights)
+            assert np.isclose(cost[b], c_ref, rtol=1e-12), (name, b)
+            assert np.allclose(grad[b], g_ref, rtol=1e-11, atol=1e-12 * np.abs(g_ref).max()), (name, b)
+
+
+def test_footstep_contact_sets_nearest_plane_lookup():
+    """fpowr::ExtractFootstepPlan's contact_set (footstep_plan_extractor.h:106-116): the polygon under every foot in contact
+    (NearestPlaneLookup, nearest_plane_lookup.h:62-84), -1 in the air — device kernel against the oracle's lookup."""
+    from test_oracle import _polys_for_lookup
+    polys = _polys_for_lookup()
+    p = tb.Problem(tb.make_formulation("anymal_trot_block").to_spec())
+    B = 37
+    X = synthetic_iterates(p, B)
+    plans, sets = p.batch(B).footstep_contact_sets(X, 2.0, polys)
+    seen = set()
+    for b in range(B):
+        assert sets[b].shape == (len(plans[b]), 4)
+        for s_i, st in enumerate(plans[b]):
+            for e in range(4):
+                flag, x, y = st[2 + 4 * e], st[3 + 4 * e], st[4 + 4 * e]
+                want = oracle_lib.nearest_plane(polys, x, y) if flag else -1
+                assert sets[b][s_i, e] == want, (b, s_i, e)
+                seen.add(int(want))
+    assert -1 in seen and len(seen) >= 3
 
 
 def test_postprocessing_matches_golden_fixtures():

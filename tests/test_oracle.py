@@ -173,6 +173,101 @@ def test_csv_grid_terrain_of_the_oracle():
     assert hit > 5                               # the edge-slope branches were exercised
 
 
+def test_grid_map_terrain_of_the_oracle():
+    """towr `Grid` (grid_height_map.h) over grid_map's bilinear atPosition: the oracle against an independent numpy
+    statement (continuous cell coordinate, floor, four-cell blend) inside the map, FLT_MAX outside, eps = res / 6 slopes."""
+    rng = np.random.default_rng(11)
+    sx, sy, res, pos = 40, 30, 0.1, (1.0, 0.0)
+    H = (0.2 * rng.standard_normal((sx, sy))).astype(np.float32)
+    oracle_lib.set_grid_map(H, res, pos)
+    Lx, Ly = sx * res, sy * res
+
+    def bilinear(x, y):
+        u = (pos[0] + Lx / 2 - res / 2 - x) / res          # continuous index along x (index 0 = largest coordinate)
+        v = (pos[1] + Ly / 2 - res / 2 - y) / res
+        i0, j0 = int(np.floor(u)), int(np.floor(v))
+        a, b = u - i0, v - j0
+        return ((1 - a) * (1 - b) * H[i0, j0] + a * (1 - b) * H[i0 + 1, j0] + (1 - a) * b * H[i0, j0 + 1] + a * b * H[i0 + 1, j0 + 1])
+
+    for x, y in zip(rng.uniform(-0.8, 2.8, 400), rng.uniform(-1.3, 1.3, 400)):
+        h, hx, hy = oracle_lib.terrain_point(tb.GRID_MAP, x, y)
+        assert abs(h - bilinear(x, y)) <= 3e-7 * max(1.0, abs(h)), (x, y, h, bilinear(x, y))
+        eps = res / 6
+        assert abs(hx - (bilinear(x + eps, y) - bilinear(x - eps, y)) / (2 * eps)) <= 2e-5
+        assert abs(hy - (bilinear(x, y + eps) - bilinear(x, y - eps)) / (2 * eps)) <= 2e-5
+        assert h == float(np.float32(h))                     # heights are floats (grid_height_map.h:38-45)
+    fmax = float(np.finfo(np.float32).max)
+    for x, y in ((1.0, 1.7), (1.0, -1.6), (-1.3, -1.6), (3.3, 1.7)):
+        assert oracle_lib.terrain_point(tb.GRID_MAP, x, y)[0] == fmax      # std::out_of_range -> numeric_limits<float>::max()
+    # grid_map checks the four cells by their LINEAR index only: an x index beyond the map wraps into the neighbouring
+    # column, so a position outside along x (with y inside) still "interpolates" — restated as is
+    assert oracle_lib.terrain_point(tb.GRID_MAP, -1.2, 0.0)[0] != fmax
+    # inside the map but beyond the outermost cell centres at a corner: the linear index of a neighbour is out of range ->
+    # nearest cell (INTER_NEAREST)
+    assert oracle_lib.terrain_point(tb.GRID_MAP, 2.98, 1.48)[0] == float(H[0, 0])
+    assert oracle_lib.terrain_point(tb.GRID_MAP, -0.98, -1.48)[0] == float(H[39, 29])
+
+
+def _polys_for_lookup():
+    sq = lambda x0, y0, w, h: np.array([[x0, y0], [x0, y0 + h], [x0 + w, y0 + h], [x0 + w, y0], [x0, y0]])   # closed, clockwise
+    return [sq(0.0, -0.5, 1.0, 1.0), sq(1.2, -0.5, 0.8, 1.0), np.array([[2.5, 0.0], [3.0, 0.8], [3.5, 0.0], [2.5, 0.0]]), sq(1.2, -0.5, 0.8, 1.0)]
+
+
+def _nearest_plane_reference(polys, x, y):
+    """Independent statement for CLOSED simple polygons: 0 inside (even-odd ray test) or on the boundary, else the
+    smallest vertex / edge distance; first smallest wins."""
+    best, idx = np.inf, -1
+    for k, q in enumerate(polys):
+        inside = False; d = np.inf
+        for (ax, ay), (bx, by) in zip(q[:-1], q[1:]):
+            if (ay > y) != (by > y) and x < ax + (y - ay) * (bx - ax) / (by - ay):
+                inside = not inside
+            t = np.clip(((x - ax) * (bx - ax) + (y - ay) * (by - ay)) / ((bx - ax) ** 2 + (by - ay) ** 2), 0.0, 1.0)
+            d = min(d, np.hypot(x - (ax + t * (bx - ax)), y - (ay + t * (by - ay))))
+        d = 0.0 if inside else d
+        if d < best:
+            best, idx = d, k
+    return idx
+
+
+def test_nearest_plane_lookup_of_the_oracle():
+    polys = _polys_for_lookup()
+    rng = np.random.default_rng(5)
+    pts = list(rng.uniform((-0.5, -1.0), (4.0, 1.2), (500, 2))) + [(0.5, 0.0), (1.1, 0.0), (1.6, 0.2), (3.0, 0.3), (1.1, 0.6), (1.0, 0.0), (5.0, 5.0)]
+    hits = set()
+    for x, y in pts:
+        got = oracle_lib.nearest_plane(polys, x, y)
+        assert got == _nearest_plane_reference(polys, x, y), (x, y)
+        hits.add(got)
+    assert hits == {0, 1, 2}                      # polygon 3 duplicates polygon 1: the first of two equal distances wins (strict <)
+    assert oracle_lib.nearest_plane(polys, 1.0, 0.0) == 0      # on the boundary of polygon 0: distance 0
+
+
+def test_linear_equality_and_soft_constraint_of_the_oracle():
+    """towr::LinearEqualityConstraint (linear_constraint.cc) and towr::SoftConstraint (soft_constraint.cc): the oracle's
+    restatements against numpy (M x; 0.5 (g-b)^T W (g-b) and J^T W (g-b) with the dense Jacobian of the set)."""
+    rng = np.random.default_rng(9)
+    spec = tb.make_formulation("hopper").to_spec()
+    o = oracle_lib.Oracle(spec); p = tb.Problem(spec)
+    x = synthetic_iterates(p, 1)[0]
+    (_, c0, nc), = [v for v in p.variable_sets() if v[0] == "base-lin"]
+    M = rng.standard_normal((7, nc)); M[rng.random(M.shape) < 0.6] = 0.0
+    assert np.allclose(oracle_lib.linear_equality(M, x[c0:c0 + nc]), M @ x[c0:c0 + nc], rtol=1e-13, atol=1e-13)
+    r = o.eval(x)
+    rp, ci = o.structure()
+    _, _, gl, gu = p.bounds()
+    for name in ("dynamic", "rangeofmotion-0", "force-ee-force_0"):
+        (_, r0, nr), = [c for c in p.constraint_sets() if c[0] == name]
+        w = rng.uniform(0.5, 2.0, nr)
+        cost, grad = oracle_lib.soft_constraint(o, r["g"], r["jac"], r0, nr, w)
+        J = np.zeros((nr, p.n))
+        for i in range(nr):
+            J[i, ci[rp[r0 + i]:rp[r0 + i + 1]]] = r["jac"][rp[r0 + i]:rp[r0 + i + 1]]
+        d = r["g"][r0:r0 + nr] - 0.5 * (np.clip(gu[r0:r0 + nr], -1e20, 1e20) + np.clip(gl[r0:r0 + nr], -1e20, 1e20))
+        assert np.isclose(cost, 0.5 * d @ (w * d), rtol=1e-12)
+        assert np.allclose(grad, J.T @ (w * d), rtol=1e-11, atol=1e-9 * np.abs(grad).max())
+
+
 def _quat_from_euler_zyx(roll, pitch, yaw):
     """Independent check: quaternion (w, x, y, z) of R = Rz(yaw) Ry(pitch) Rx(roll)."""
     cr, sr, cp, sp, cy, sy = np.cos(roll / 2), np.sin(roll / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(yaw / 2), np.sin(yaw / 2)

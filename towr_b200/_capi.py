@@ -17,6 +17,7 @@ MONOPED, BIPED, HYQ, ANYMAL, GO1 = range(5)
 # towr::HeightMap::TerrainID (height_map.h:79-86)
 FLAT, BLOCK, STAIRS, GAP, SLOPE, CHIMNEY, CHIMNEY_LR = range(7)
 GRID_CSV = 7   # towr::HeightMapFromCSV; grid data per batch (Batch.set_grid_terrain)
+GRID_MAP = 8   # towr Grid (grid_height_map.h): grid_map elevation layer per batch (Batch.set_grid_map)
 # towr::Parameters::ConstraintName (parameters.h:139-147)
 C_DYNAMIC, C_EE_ROM, C_TOTAL_TIME, C_TERRAIN, C_FORCE, C_SWING, C_BASE_ROM, C_BASE_ACC = range(8)
 # towr::Parameters::CostName
@@ -84,6 +85,7 @@ def _load():
         "twb_batch_destroy": (None, [P]),
         "twb_batch_set_terrains": (C.c_int, [P, I]),
         "twb_batch_set_grid_terrain": (C.c_int, [P, D, C.c_int, C.c_int]),
+        "twb_batch_set_grid_map": (C.c_int, [P, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
         "twb_batch_eval_device": (C.c_int, [P, P, P, P, P, P, P, C.c_uint, P]),
         "twb_batch_eval_host": (C.c_int, [P, P, P, P, P, P, P, C.c_uint]),
         "twb_problem_trajectory_dims": (C.c_int, [P, C.c_double, I, I]),
@@ -91,6 +93,9 @@ def _load():
         "twb_batch_initial_guess_host": (C.c_int, [P, P, P, C.c_int, P]),
         "twb_problem_footstep_plan_dims": (C.c_int, [P, I, I]),
         "twb_batch_footstep_plan_host": (C.c_int, [P, P, C.c_double, P, P]),
+        "twb_batch_nearest_planes_host": (C.c_int, [P, P, P, P, C.c_int, P, P]),
+        "twb_batch_linear_equality_host": (C.c_int, [P, P, C.c_int, P, C.c_int, P]),
+        "twb_batch_soft_constraint_host": (C.c_int, [P, C.c_int, P, P, P]),
         "twb_batch_launches_per_eval": (C.c_int, [P, C.c_uint]),
         "twb_last_error": (C.c_char_p, []),
         "twb_version": (C.c_char_p, []),

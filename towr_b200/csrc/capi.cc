@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,7 @@ struct twb_batch {
   std::vector<void*> owned;       // device allocations of the tables
   int* d_terrain = nullptr;       // per-instance terrain ids (optional)
   double* d_grid = nullptr;       // height grid of TWB_GRID_CSV (optional)
+  float* d_gmap = nullptr;        // elevation layer of TWB_GRID_MAP (optional)
   double* d_XT = nullptr;         // [ld/32][n+1][32] instance-tiled iterates; row n == 0
   double* d_GT = nullptr;         // [ld/32][m][32] instance-tiled constraint values (staging of g)
   // staging for the host-pointer variant
@@ -212,7 +214,7 @@ void twb_batch_destroy(twb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   for (void* p : b->owned) cudaFree(p);
-  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_XT); cudaFree(b->d_GT);
+  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT); cudaFree(b->d_GT);
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
@@ -226,7 +228,7 @@ int twb_batch_set_terrains(twb_batch* b, const int* terrain_ids) {
   cudaSetDevice(b->device);
   if (!terrain_ids) { cudaFree(b->d_terrain); b->d_terrain = nullptr; return TWB_OK; }
   for (int i = 0; i < b->B; ++i)
-    if (terrain_ids[i] < 0 || terrain_ids[i] > TWB_GRID_CSV) return Fail(TWB_ERR_INVALID, "unknown terrain id");
+    if (terrain_ids[i] < 0 || terrain_ids[i] > TWB_GRID_MAP) return Fail(TWB_ERR_INVALID, "unknown terrain id");
   cudaError_t e;
   if (!b->d_terrain && (e = cudaMalloc(&b->d_terrain, sizeof(int) * b->B)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
   if ((e = cudaMemcpy(b->d_terrain, terrain_ids, sizeof(int) * b->B, cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -246,6 +248,23 @@ int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, in
   if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_grid), bytes)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
   if ((e = cudaMemcpy(b->d_grid, heights, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return CudaFail(e, "cudaMemcpy");
   b->plan.grid = b->d_grid; b->plan.grid_rows = rows; b->plan.grid_cols = cols;
+  return TWB_OK;
+}
+
+int twb_batch_set_grid_map(twb_batch* b, const float* heights, int size_x, int size_y, double resolution, double pos_x, double pos_y) {
+  if (!b) return Fail(TWB_ERR_INVALID, "null batch");
+  cudaSetDevice(b->device);
+  cudaFree(b->d_gmap); b->d_gmap = nullptr;
+  b->plan.gmap = nullptr; b->plan.gmap_sx = b->plan.gmap_sy = 0; b->plan.gmap_res = 1.0; b->plan.gmap_px = b->plan.gmap_py = 0.0;
+  if (!heights) return TWB_OK;
+  if (size_x <= 0 || size_y <= 0 || (long long)size_x * size_y > (1ll << 28) || !(resolution > 0.0) || !std::isfinite(resolution) ||
+      !std::isfinite(pos_x) || !std::isfinite(pos_y))
+    return Fail(TWB_ERR_INVALID, "bad grid map geometry");
+  cudaError_t e;
+  const size_t bytes = sizeof(float) * (size_t)size_x * size_y;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_gmap), bytes)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(b->d_gmap, heights, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return CudaFail(e, "cudaMemcpy");
+  b->plan.gmap = b->d_gmap; b->plan.gmap_sx = size_x; b->plan.gmap_sy = size_y; b->plan.gmap_res = resolution; b->plan.gmap_px = pos_x; b->plan.gmap_py = pos_y;
   return TWB_OK;
 }
 
@@ -362,6 +381,98 @@ int twb_batch_footstep_plan_host(twb_batch* b, const double* x, double time_hori
   cleanup();
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "footstep-plan kernel launch");
   if (e != cudaSuccess) return CudaFail(e, "footstep-plan extraction");
+  return TWB_OK;
+}
+
+int twb_batch_nearest_planes_host(twb_batch* b, const double* plan, const int* n_states, const int* poly_offsets, int n_polys,
+                                  const double* vertices, int* contact_set) {
+  if (!b || !plan || !n_states || !poly_offsets || !contact_set || n_polys < 0 || (n_polys > 0 && !vertices)) return Fail(TWB_ERR_INVALID, "null argument");
+  for (int k = 0; k < n_polys; ++k) if (poly_offsets[k + 1] < poly_offsets[k] || poly_offsets[k] < 0) return Fail(TWB_ERR_INVALID, "polygon offsets must ascend");
+  int max_states = 0, V = 0;
+  twb_problem_footstep_plan_dims(b->prob, &max_states, &V);
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  const size_t B = b->B, n_ee = b->prob->f.spec.n_ee, n_vert = n_polys > 0 ? (size_t)poly_offsets[n_polys] : 0;
+  double* d_plan = nullptr; int* d_count = nullptr; int* d_off = nullptr; double* d_vert = nullptr; int* d_out = nullptr;
+  auto cleanup = [&] { cudaFree(d_plan); cudaFree(d_count); cudaFree(d_off); cudaFree(d_vert); cudaFree(d_out); };
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_plan), sizeof(double) * B * max_states * V)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_count), sizeof(int) * B)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_off), sizeof(int) * (n_polys + 1))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_vert), sizeof(double) * 2 * std::max<size_t>(n_vert, 1))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(int) * B * max_states * n_ee)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  cudaStream_t s = b->stream;
+  cudaMemcpyAsync(d_plan, plan, sizeof(double) * B * max_states * V, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_count, n_states, sizeof(int) * B, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_off, poly_offsets, sizeof(int) * (n_polys + 1), cudaMemcpyHostToDevice, s);
+  if (n_vert) cudaMemcpyAsync(d_vert, vertices, sizeof(double) * 2 * n_vert, cudaMemcpyHostToDevice, s);
+  int rc = twb::LaunchNearestPlanes(d_plan, d_count, max_states, (int)n_ee, d_off, n_polys, d_vert, d_out, b->B, s);
+  if (rc == 0) cudaMemcpyAsync(contact_set, d_out, sizeof(int) * B * max_states * n_ee, cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "nearest-plane kernel launch");
+  if (e != cudaSuccess) return CudaFail(e, "nearest-plane lookup");
+  return TWB_OK;
+}
+
+int twb_batch_linear_equality_host(twb_batch* b, const double* x, int var_set, const double* M, int rows, double* g) {
+  if (!b || !x || !M || !g || rows <= 0) return Fail(TWB_ERR_INVALID, "bad argument");
+  const twb::Formulation& f = b->prob->f;
+  if (var_set < 0 || var_set >= (int)f.var_sets.size()) return Fail(TWB_ERR_INVALID, "variable set index out of range");
+  const int col0 = f.var_sets[var_set].start, n_cols = f.var_sets[var_set].count;
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  const size_t B = b->B;
+  double* d_M = nullptr; double* d_g = nullptr;
+  auto cleanup = [&] { cudaFree(d_M); cudaFree(d_g); };
+  if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_M), sizeof(double) * (size_t)rows * n_cols)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_g), sizeof(double) * B * rows)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  cudaStream_t s = b->stream;
+  cudaMemcpyAsync(d_M, M, sizeof(double) * (size_t)rows * n_cols, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(b->d_x, x, sizeof(double) * B * f.n, cudaMemcpyHostToDevice, s);
+  int rc = twb::LaunchLinearEquality(b->plan, b->d_x, b->d_XT, col0, n_cols, d_M, rows, d_g, b->B, s);
+  if (rc == 0) cudaMemcpyAsync(g, d_g, sizeof(double) * B * rows, cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "linear-equality kernel launch");
+  if (e != cudaSuccess) return CudaFail(e, "linear equality constraint");
+  return TWB_OK;
+}
+
+int twb_batch_soft_constraint_host(twb_batch* b, int constraint_set, const double* weights, double* cost, double* grad) {
+  if (!b || !cost || !grad) return Fail(TWB_ERR_INVALID, "null argument");
+  const twb::Formulation& f = b->prob->f;
+  if (constraint_set < 0 || constraint_set >= (int)f.con_sets.size()) return Fail(TWB_ERR_INVALID, "constraint set index out of range");
+  if (!b->d_g || !b->d_jac) return Fail(TWB_ERR_INVALID, "no evaluation on the device yet: call twb_batch_eval_host(TWB_EVAL_G | TWB_EVAL_JAC) first");
+  const int row0 = f.con_sets[constraint_set].start, n_rows = f.con_sets[constraint_set].count;
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  std::vector<double> b_avg(n_rows), w(n_rows, 1.0);
+  for (int i = 0; i < n_rows; ++i) b_avg[i] = (f.g_upper[row0 + i] + f.g_lower[row0 + i]) / 2.;   // soft_constraint.cc:41-46
+  if (weights) w.assign(weights, weights + n_rows);
+  const size_t B = b->B;
+  double *d_b = nullptr, *d_w = nullptr, *d_cost = nullptr, *d_grad = nullptr; int *d_rp = nullptr, *d_ci = nullptr;
+  auto cleanup = [&] { cudaFree(d_b); cudaFree(d_w); cudaFree(d_cost); cudaFree(d_grad); cudaFree(d_rp); cudaFree(d_ci); };
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_b), sizeof(double) * std::max(n_rows, 1))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_w), sizeof(double) * std::max(n_rows, 1))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_cost), sizeof(double) * B)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_grad), sizeof(double) * B * f.n)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_rp), sizeof(int) * (f.m + 1))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&d_ci), sizeof(int) * std::max(f.nnz, 1))) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  cudaStream_t s = b->stream;
+  cudaMemcpyAsync(d_b, b_avg.data(), sizeof(double) * n_rows, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_w, w.data(), sizeof(double) * n_rows, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_rp, f.row_ptr.data(), sizeof(int) * (f.m + 1), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_ci, f.col_idx.data(), sizeof(int) * f.nnz, cudaMemcpyHostToDevice, s);
+  int rc = twb::LaunchSoftConstraint(b->plan, b->d_g, b->d_jac, d_rp, d_ci, row0, n_rows, d_b, d_w, d_cost, d_grad, b->B, s);
+  if (rc == 0) {
+    cudaMemcpyAsync(cost, d_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(grad, d_grad, sizeof(double) * B * f.n, cudaMemcpyDeviceToHost, s);
+  }
+  e = cudaStreamSynchronize(s);   // (pageable vectors b_avg / w stay alive until here)
+  cleanup();
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "soft-constraint kernel launch");
+  if (e != cudaSuccess) return CudaFail(e, "soft constraint");
   return TWB_OK;
 }
 

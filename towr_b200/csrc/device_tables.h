@@ -190,6 +190,10 @@ struct Plan {
   // height grid of the TWB_GRID_CSV terrain (per batch; null: heights 0)
   const double* grid;
   int grid_rows, grid_cols;
+  // elevation layer of the TWB_GRID_MAP terrain (per batch; null: every position is outside the map)
+  const float* gmap;
+  int gmap_sx, gmap_sy;
+  double gmap_res, gmap_px, gmap_py;
   // phase-duration optimisation (all null / 0 otherwise)
   int n_phase_units, n_phase_defs;
   const PhaseSplineDef* phase_defs;   // [2 * n_ee]: ee-motion_e at 2e, ee-force_e at 2e + 1

@@ -417,9 +417,53 @@ __device__ __forceinline__ double GridEdgeSlope(const Plan& P, long long c, long
   }
   return 0.0;
 }
+// towr `Grid` (grid_height_map.h:16-59) over grid_map::GridMap::atPosition(layer, p, INTER_LINEAR) (grid_map_core, restated;
+// un-vendored dependency): bilinear over the four cell centres around p with double weights stored to FLOAT, nearest cell
+// when one of the four is outside, FLT_MAX outside the map; cell (ix, iy) is centred at pos + L/2 - res/2 - res * (ix, iy).
+__device__ __forceinline__ void GridMapCentre(const Plan& P, int ix, int iy, double* x, double* y) {
+  *x = P.gmap_px + (0.5 * (P.gmap_sx * P.gmap_res) - 0.5 * P.gmap_res) + P.gmap_res * (double)(-ix);
+  *y = P.gmap_py + (0.5 * (P.gmap_sy * P.gmap_res) - 0.5 * P.gmap_res) + P.gmap_res * (double)(-iy);
+}
+__device__ __forceinline__ float GridMapHeight(const Plan& P, double x, double y) {
+  const float outside = 3.402823466e+38f;   // std::numeric_limits<float>::max(), grid_height_map.h:43
+  if (!P.gmap) return outside;
+  const double Lx = P.gmap_sx * P.gmap_res, Ly = P.gmap_sy * P.gmap_res;
+  const int ix0 = (int)(-((x - 0.5 * Lx - P.gmap_px) / P.gmap_res)), iy0 = (int)(-((y - 0.5 * Ly - P.gmap_py) / P.gmap_res));
+  double cx, cy; GridMapCentre(P, ix0, iy0, &cx, &cy);
+  const bool dir = x >= cx, up = y >= cy;
+  const int ix1 = dir ? ix0 - 1 : ix0 + 1, iy2 = up ? iy0 - 1 : iy0 + 1;
+  // the four cells in grid_map's order after idxShift: f[0] = cell with the smaller x / y centre ... (GridMap.cpp, atPositionLinearInterpolated)
+  const int cxs[4] = {ix0, ix1, ix0, ix1}, cys[4] = {iy0, iy0, iy2, iy2};
+  int sh[4];
+  if (up) { if (dir) { sh[0] = 0; sh[1] = 1; sh[2] = 2; sh[3] = 3; } else { sh[0] = 1; sh[1] = 0; sh[2] = 3; sh[3] = 2; } }
+  else    { if (dir) { sh[0] = 2; sh[1] = 3; sh[2] = 0; sh[3] = 1; } else { sh[0] = 3; sh[1] = 2; sh[2] = 1; sh[3] = 0; } }
+  const unsigned long long buffer = (unsigned long long)P.gmap_sx * P.gmap_sy;
+  float f[4]; bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned long long lin = (unsigned long long)((long long)cys[sh[i]] * P.gmap_sx + cxs[sh[i]]);   // column-major linear index in size_t, as grid_map
+    if (lin >= buffer) { ok = false; f[i] = 0.0f; }
+    else f[i] = __ldg(P.gmap + (lin % (unsigned long long)P.gmap_sx) * P.gmap_sy + lin / (unsigned long long)P.gmap_sx);
+  }
+  if (ok) {
+    GridMapCentre(P, cxs[sh[0]], cys[sh[0]], &cx, &cy);
+    const double rx = (x - cx) / P.gmap_res, ry = (y - cy) / P.gmap_res, fx = 1.0 - rx, fy = 1.0 - ry;
+    return (float)(f[0] * fx * fy + f[1] * rx * fy + f[2] * fx * ry + f[3] * rx * ry);
+  }
+  const double tx = -(x - P.gmap_px - 0.5 * Lx), ty = -(y - P.gmap_py - 0.5 * Ly);   // checkIfPositionWithinMap + checkIfIndexInRange
+  if (tx >= 0.0 && ty >= 0.0 && tx < Lx && ty < Ly && ix0 >= 0 && iy0 >= 0 && ix0 < P.gmap_sx && iy0 < P.gmap_sy)
+    return __ldg(P.gmap + (size_t)ix0 * P.gmap_sy + iy0);
+  return outside;
+}
 __device__ __forceinline__ TerrainPoint EvalTerrain(const Plan& P, int id, double x, double y) {
   TerrainPoint o{0.0, 0.0, 0.0, 0.0};
   switch (id) {
+    case 8: {  // Grid (grid_map elevation layer), grid_height_map.h:29-60: float heights, central differences with eps = res / 6
+      const double eps = P.gmap_res / 6.0;
+      o.h = (double)GridMapHeight(P, x, y);
+      o.hx = (double)(GridMapHeight(P, x + eps, y) - GridMapHeight(P, x - eps, y)) / (2 * eps);
+      o.hy = (double)(GridMapHeight(P, x, y + eps) - GridMapHeight(P, x, y - eps)) / (2 * eps);
+      break; }
     case 7: {  // Grid (CSV)
       long long xc, yc;
       if (GridCell(P, x, y, &xc, &yc)) {
@@ -1285,6 +1329,61 @@ __global__ void __launch_bounds__(128) FootstepKernel(const double* __restrict__
   n_states[b] = count;
 }
 
+// ---- fpowr::NearestPlaneLookup::GetNearestPlaneIndex (fpowr/include/fpowr/nearest_plane_lookup.h:62-84) ----------------
+// boost::geometry::distance(point, polygon) with the default cartesian strategies, restated (boost is an un-vendored
+// dependency): 0 when the point is inside or on the outer ring (winding number over the ring's segments), else the
+// smallest distance to a segment of the ring, projected-point strategy (distance_projected_point.hpp: c1 = w.v <= 0 ->
+// first end, c2 = v.v <= c1 -> second end, else the foot of the perpendicular), comparable (squared) distances, one sqrt.
+// A ring is the vertex sequence AS GIVEN: bg::model::polygon is `closed` by default, i.e. the closing segment exists
+// only if the caller repeats the first vertex (fpowr appends the message's boundary points as they are).
+__device__ __forceinline__ double PolygonDistance(const double* __restrict__ v, int n, double px, double py) {
+  if (n <= 0) return 1.7976931348623157e308;
+  if (n == 1) { const double dx = px - v[0], dy = py - v[1]; return sqrt(dx * dx + dy * dy); }
+  int winding = 0; bool touches = false;
+  double best = 1.7976931348623157e308;
+  for (int i = 0; i + 1 < n; ++i) {
+    const double ax = __ldg(v + 2 * i), ay = __ldg(v + 2 * i + 1), bx = __ldg(v + 2 * i + 2), by = __ldg(v + 2 * i + 3);
+    // winding: upward / downward crossings of the horizontal ray, side by the sign of the cross product
+    const double side = (bx - ax) * (py - ay) - (px - ax) * (by - ay);
+    if (ay <= py) { if (by > py && side > 0) ++winding; }
+    else if (by <= py && side < 0) --winding;
+    const double vx = bx - ax, vy = by - ay, wx = px - ax, wy = py - ay;
+    const double c1 = wx * vx + wy * vy;
+    double d2;
+    if (c1 <= 0) d2 = wx * wx + wy * wy;
+    else {
+      const double c2 = vx * vx + vy * vy;
+      if (c2 <= c1) { const double ex = px - bx, ey = py - by; d2 = ex * ex + ey * ey; }
+      else { const double b = c1 / c2, qx = ax + b * vx, qy = ay + b * vy, ex = px - qx, ey = py - qy; d2 = ex * ex + ey * ey; }
+    }
+    if (d2 == 0.0) touches = true;
+    if (d2 < best) best = d2;
+  }
+  if (touches || winding != 0) return 0.0;
+  return sqrt(best);
+}
+// thread = (instance, footstep state, foot) of a footstep plan (FootstepKernel's layout): index of the nearest polygon for a
+// foot in contact, -1 for a foot in the air (footstep_plan_extractor.h:106-116) and for unused states
+__global__ void __launch_bounds__(128) NearestPlaneKernel(const double* __restrict__ plan, const int* __restrict__ n_states, int max_states, int n_ee,
+                                                          const int* __restrict__ poly_offset, int n_polys, const double* __restrict__ verts,
+                                                          int* __restrict__ out, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int e = (int)(i % n_ee); const long long bs = i / n_ee; const int st = (int)(bs % max_states); const long long b = bs / max_states;
+  const int V = 2 + 4 * n_ee;
+  const double* rec = plan + (size_t)bs * V + 2 + 4 * e;
+  int idx = -1;
+  if (st < n_states[b] && rec[0] != 0.0) {
+    double min_distance = 1.7976931348623157e308;   // std::numeric_limits<double>::max(), :70
+    for (int k = 0; k < n_polys; ++k) {
+      const int o = __ldg(poly_offset + k), cnt = __ldg(poly_offset + k + 1) - o;
+      const double d = PolygonDistance(verts + 2 * (size_t)o, cnt, rec[1], rec[2]);
+      if (d < min_distance) { min_distance = d; idx = k; }
+    }
+  }
+  out[i] = idx;
+}
+
 #if TWB_FUSED
 // One kernel writes a whole tile of rows: blockIdx.y = instance tile, blockIdx.x walks the tile's CTAs in row
 // order — dynamic samples, range-of-motion samples, node groups.
@@ -1469,6 +1568,61 @@ int LaunchFootstepScan(const double* traj, int n_steps, int n_ee, double dt, dou
                        double* out, int nb, cudaStream_t s) {
   if (nb <= 0) return 0;
   FootstepKernel<<<(nb + 127) / 128, 128, 0, s>>>(traj, n_steps, n_ee, dt, time_horizon, max_states, n_states, out, nb);
+  return (int)cudaGetLastError();
+}
+
+int LaunchNearestPlanes(const double* plan, const int* n_states, int max_states, int n_ee, const int* poly_offset, int n_polys,
+                        const double* verts, int* out, int nb, cudaStream_t s) {
+  const long long total = (long long)nb * max_states * n_ee;
+  if (total <= 0) return 0;
+  NearestPlaneKernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(plan, n_states, max_states, n_ee, poly_offset, n_polys, verts, out, total);
+  return (int)cudaGetLastError();
+}
+
+// ---- the two components outside Parameters::ConstraintName: LinearEqualityConstraint and SoftConstraint -----------------
+// towr::LinearEqualityConstraint::GetValues (linear_constraint.cc:46-51): g = M x_set, thread = (row, instance), lane = instance
+__global__ void __launch_bounds__(128) LinearEqualityKernel(const double* __restrict__ XT, int n, int col0, int n_cols, const double* __restrict__ M,
+                                                            int rows, double* __restrict__ g, int nb) {
+  const int b = blockIdx.y * 32 + (threadIdx.x & 31), r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const ConstCol xs = TiledCol(XT, b, n + 1);
+  double acc = 0.0;
+  for (int c = 0; c < n_cols; ++c) acc += __ldg(M + (size_t)r * n_cols + c) * xs[col0 + c];   // Eigen's dense row-times-vector order
+  if (b < nb) g[(size_t)b * rows + r] = acc;
+}
+// towr::SoftConstraint (soft_constraint.cc:53-72): cost = 0.5 (g - b)^T W (g - b), gradient = J^T W (g - b) of one constraint
+// set (rows row0 .. row0 + n_rows - 1 of g / the CSR); block = instance, the gradient is accumulated in shared memory
+__global__ void __launch_bounds__(128) SoftConstraintKernel(const double* __restrict__ g, const double* __restrict__ jac, const int* __restrict__ row_ptr,
+                                                            const int* __restrict__ col_idx, int n, int m, int nnz, int row0, int n_rows,
+                                                            const double* __restrict__ b_avg, const double* __restrict__ w,
+                                                            double* __restrict__ cost, double* __restrict__ grad, int nb) {
+  extern __shared__ double acc[];   // [n] gradient | [128] partial costs
+  const int b = blockIdx.x;
+  if (b >= nb) return;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  double part = 0.0;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const double d = g[(size_t)b * m + row0 + r] - b_avg[r], wd = w[r] * d;
+    part += d * wd;
+    for (int k = __ldg(row_ptr + row0 + r); k < __ldg(row_ptr + row0 + r + 1); ++k) atomicAdd(acc + __ldg(col_idx + k), jac[(size_t)b * nnz + k] * wd);
+  }
+  acc[n + threadIdx.x] = part;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) grad[(size_t)b * n + i] = acc[i];
+  if (threadIdx.x == 0) { double c = 0.0; for (int i = 0; i < (int)blockDim.x; ++i) c += acc[n + i]; cost[b] = 0.5 * c; }
+}
+int LaunchLinearEquality(const Plan& P, const double* x, double* XT, int col0, int n_cols, const double* M, int rows, double* g, int nb, cudaStream_t s) {
+  if (nb <= 0 || rows <= 0) return 0;
+  const int tiles = (nb + 31) / 32;
+  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb);
+  LinearEqualityKernel<<<dim3((rows + 3) / 4, tiles), 128, 0, s>>>(XT, P.n, col0, n_cols, M, rows, g, nb);
+  return (int)cudaGetLastError();
+}
+int LaunchSoftConstraint(const Plan& P, const double* g, const double* jac, const int* row_ptr, const int* col_idx, int row0, int n_rows,
+                         const double* b_avg, const double* w, double* cost, double* grad, int nb, cudaStream_t s) {
+  if (nb <= 0) return 0;
+  SoftConstraintKernel<<<nb, 128, (P.n + 128) * sizeof(double), s>>>(g, jac, row_ptr, col_idx, P.n, P.m, P.nnz, row0, n_rows, b_avg, w, cost, grad, nb);
   return (int)cudaGetLastError();
 }
 

@@ -28,6 +28,15 @@ int LaunchInitialGuess(const Plan& P, const double* x, double* XT, const SplineS
 // out[b][max_states][2 + 4 n_ee], n_states[b]
 int LaunchFootstepScan(const double* traj, int n_steps, int n_ee, double dt, double time_horizon, int max_states, int* n_states,
                        double* out, int nb, cudaStream_t s);
+// fpowr::NearestPlaneLookup for every (instance, footstep state, foot) of a footstep plan: out[b][state][foot] = index of
+// the nearest polygon (polygon k = vertices poly_offset[k] .. poly_offset[k+1]-1 of verts[][2]) or -1 (foot in the air)
+int LaunchNearestPlanes(const double* plan, const int* n_states, int max_states, int n_ee, const int* poly_offset, int n_polys,
+                        const double* verts, int* out, int nb, cudaStream_t s);
+// towr::LinearEqualityConstraint values g[b][rows] = M x_set (x -> XT first); towr::SoftConstraint cost / gradient of one
+// constraint set from device-resident g / jac
+int LaunchLinearEquality(const Plan& P, const double* x, double* XT, int col0, int n_cols, const double* M, int rows, double* g, int nb, cudaStream_t s);
+int LaunchSoftConstraint(const Plan& P, const double* g, const double* jac, const int* row_ptr, const int* col_idx, int row0, int n_rows,
+                         const double* b_avg, const double* w, double* cost, double* grad, int nb, cudaStream_t s);
 // number of output kernels one evaluation launches for this plan
 int OutKernelsPerEval(const Plan& P);
 int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,

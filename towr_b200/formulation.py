@@ -305,6 +305,49 @@ class Batch:
         assert count.max() <= ms.value
         return [out[b, :count[b]] for b in range(self.B)]
 
+    def footstep_contact_sets(self, x, time_horizon, polygons):
+        """fpowr::ExtractFootstepPlan including the nearest-plane lookup: `polygons` is a list of (k_i, 2) vertex arrays
+        (world x, y of the planar regions' boundaries).  Returns (plans, contact_sets): per instance the footstep states
+        (see footstep_plans) and an (n_states_b, n_ee) int array — polygon index under every foot in contact, -1 in the air."""
+        p = self.problem
+        x = np.ascontiguousarray(x, np.float64)
+        ms, nv = C.c_int(), C.c_int()
+        check(lib.twb_problem_footstep_plan_dims(p._h, C.byref(ms), C.byref(nv)))
+        n_ee = (nv.value - 2) // 4
+        out = np.zeros((self.B, ms.value, nv.value))
+        count = np.empty(self.B, np.int32)
+        check(lib.twb_batch_footstep_plan_host(self._h, x.ctypes.data_as(C.c_void_p), float(time_horizon),
+                                               count.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        offs = np.zeros(len(polygons) + 1, np.int32)
+        offs[1:] = np.cumsum([len(q) for q in polygons])
+        verts = np.ascontiguousarray(np.concatenate([np.asarray(q, np.float64).reshape(-1, 2) for q in polygons]) if polygons else np.zeros((0, 2)))
+        cs = np.empty((self.B, ms.value, n_ee), np.int32)
+        check(lib.twb_batch_nearest_planes_host(self._h, out.ctypes.data_as(C.c_void_p), count.ctypes.data_as(C.c_void_p),
+                                                offs.ctypes.data_as(C.c_void_p), len(polygons), verts.ctypes.data_as(C.c_void_p),
+                                                cs.ctypes.data_as(C.c_void_p)))
+        return [out[b, :count[b]] for b in range(self.B)], [cs[b, :count[b]] for b in range(self.B)]
+
+    def linear_equality(self, x, var_set, M):
+        """towr::LinearEqualityConstraint::GetValues for every instance: (B, rows) = M x_set; var_set is a set name."""
+        p = self.problem
+        names = [n for n, _, _ in p.variable_sets()]
+        x = np.ascontiguousarray(x, np.float64); M = np.ascontiguousarray(M, np.float64)
+        assert x.shape == (self.B, p.n) and M.shape[1] == p.variable_sets()[names.index(var_set)][2]
+        g = np.empty((self.B, M.shape[0]))
+        check(lib.twb_batch_linear_equality_host(self._h, x.ctypes.data_as(C.c_void_p), names.index(var_set), M.ctypes.data_as(C.c_void_p),
+                                                 M.shape[0], g.ctypes.data_as(C.c_void_p)))
+        return g
+
+    def soft_constraint(self, constraint_set, weights=None):
+        """towr::SoftConstraint around a constraint set (by name), from the last eval_host(G | JAC): (cost (B,), grad (B, n))."""
+        p = self.problem
+        names = [n for n, _, _ in p.constraint_sets()]
+        cost = np.empty(self.B); grad = np.empty((self.B, p.n))
+        w = None if weights is None else np.ascontiguousarray(weights, np.float64)
+        check(lib.twb_batch_soft_constraint_host(self._h, names.index(constraint_set), None if w is None else w.ctypes.data_as(C.c_void_p),
+                                                 cost.ctypes.data_as(C.c_void_p), grad.ctypes.data_as(C.c_void_p)))
+        return cost, grad
+
     def set_terrains(self, terrain_ids):
         if terrain_ids is None:
             check(lib.twb_batch_set_terrains(self._h, None))
@@ -321,6 +364,17 @@ class Batch:
         h = np.ascontiguousarray(heights, np.float64)
         assert h.ndim == 2
         check(lib.twb_batch_set_grid_terrain(self._h, h.ctypes.data_as(C.POINTER(C.c_double)), h.shape[0], h.shape[1]))
+
+    def set_grid_map(self, heights, resolution, position=(0.0, 0.0)):
+        """heights[ix, iy] (2-D float32) = the "elevation" layer of a grid_map::GridMap centred at `position` with
+        `resolution` metres per cell (index 0 = largest coordinate), for the GRID_MAP terrain; None removes it."""
+        if heights is None:
+            check(lib.twb_batch_set_grid_map(self._h, None, 0, 0, 1.0, 0.0, 0.0))
+            return
+        h = np.ascontiguousarray(heights, np.float32)
+        assert h.ndim == 2
+        check(lib.twb_batch_set_grid_map(self._h, h.ctypes.data_as(C.POINTER(C.c_float)), h.shape[0], h.shape[1], float(resolution),
+                                         float(position[0]), float(position[1])))
 
     def launches_per_eval(self, flags=capi.EVAL_ALL):
         return lib.twb_batch_launches_per_eval(self._h, flags)
