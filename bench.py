@@ -79,6 +79,47 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_spec_fixture(workload):
+    """twb_spec of a bench workload from tests/golden/bench_specs.json, as a ctypes struct defined by towr_b200/_spec.py loaded
+    BY FILE PATH: neither the towr_b200 package nor libtowr_b200.so is touched (reference arm)."""
+    import importlib.util
+    sp = importlib.util.spec_from_file_location("twb_spec_struct", os.path.join(ROOT, "towr_b200", "_spec.py"))
+    mod = importlib.util.module_from_spec(sp); sp.loader.exec_module(mod)
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_specs.json")))
+    return mod.Spec.from_buffer_copy(bytes.fromhex(fx[workload]))
+
+
+def oracle_iterates(spec, batch, seed=1234):
+    """The iterate distribution of towr_b200.configs.synthetic_iterates_fast (x0 + sigma N(0,1); sigma 0.05 / 0.2 / 10 / 50),
+    built from the ORACLE's x0 and variable-set layout only."""
+    import numpy as np
+    import oracle_lib
+    o = oracle_lib.Oracle(spec)
+    x0 = o.x0()
+    sig = np.zeros(o.n)
+    sets = o.variable_sets()
+    for name, start, count in sets:
+        idx = np.arange(count)
+        if name.startswith("base-"):
+            sig[start:start + count] = np.where((idx % 6) < 3, 0.05, 0.2)
+        elif name.startswith("ee-motion"):
+            sig[start:start + count] = 0.05
+        elif name.startswith("ee-force"):
+            sig[start:start + count] = np.where((idx % 2) == 0, 10.0, 50.0)
+    rng = np.random.default_rng(seed)
+    X = x0 + sig * rng.standard_normal((batch, o.n))
+    for name, start, count in sets:
+        if name.startswith("ee-schedule"):
+            ee = int(name[len("ee-schedule"):])
+            t_total = sum(spec.phase_durations[ee][i] for i in range(spec.n_phases[ee]))
+            d = x0[start:start + count] * rng.uniform(0.9, 1.1, (batch, count))
+            X[:, start:start + count] = d * np.minimum(1.0, 0.98 * t_total / d.sum(axis=-1, keepdims=True))
+        if name == "base-ang":
+            blk = X[:, start:start + count].reshape(batch, -1, 6)
+            blk[:, :, :3] = np.clip(blk[:, :, :3], -1.0, 1.0)
+    return X, o
+
+
 def make_problem():
     import towr_b200 as tb
     spec = tb.make_formulation(WORKLOAD).to_spec()
@@ -155,10 +196,10 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle_lib
-    from towr_b200.configs import synthetic_iterates_fast
-    tb, spec, p = make_problem()
+    spec = load_spec_fixture(WORKLOAD)            # no towr_b200 import, no libtowr_b200.so in this process
     threads = host_threads()
-    X = synthetic_iterates_fast(p, 2048)
+    X, p = oracle_iterates(spec, 2048)
+    assert "towr_b200" not in sys.modules
     # each step: a bounded sample of the workload sized for ~1.5 s of CPU time
     t0 = time.perf_counter(); oracle_lib.batch_eval(spec, X[:max(threads, 8)], threads=threads)
     per_eval = (time.perf_counter() - t0) / max(threads, 8)
@@ -175,7 +216,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD} ({DESCR.get(WORKLOAD, WORKLOAD)}), n={p.n} m={p.m} nnz={p.nnz}",
-                   "note": "reference arm = CPU restatement of towr's evaluation (oracle port; towr itself needs Eigen+ifopt, absent here)"},
+                   "note": "reference arm = CPU restatement of towr's evaluation (oracle port, g++ -O3, OpenMP over instances; towr itself "
+                           "needs Eigen+ifopt, absent here); spec from tests/golden/bench_specs.json, the product library is not loaded"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} instances per step, OpenMP over instances"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,6 +244,63 @@ def bind_to_gpu_numa_node(local):
     except Exception:
         pass
     return 0
+
+
+def run_config5(args, tb, dev, world, rank, local):
+    """BASELINE configs[4], the north-star size: 65 536 Anymal multi-start instances on mixed Slope / Chimney / Gap terrains,
+    split over the ranks with shard_range (STRONG scaling: 65 536 / N instances per GPU).  Device-timed like the headline;
+    after every step the per-instance cost / status are all-gathered over NCCL (outside the timed region)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from towr_b200.configs import synthetic_iterates_fast
+    from towr_b200.sharding import gather_cost_status, shard_range
+    total = 65536
+    lo, hi = shard_range(total, rank, world)
+    nb = hi - lo
+    spec = tb.make_formulation("anymal_trot_mixed").to_spec()
+    p = tb.Problem(spec)
+    batch = p.batch(nb, device=local)
+    batch.set_terrains(np.random.default_rng(7).choice([tb.SLOPE, tb.CHIMNEY, tb.GAP], total).astype(np.int32)[lo:hi])
+    rng_sets = [torch.from_numpy(synthetic_iterates_fast(p, nb, seed=99 + 13 * rank + 1000 * r)).to(dev) for r in range(2)]
+    g = torch.empty((nb, p.m), dtype=torch.float64, device=dev)
+    jac = torch.empty((nb, p.nnz), dtype=torch.float64, device=dev)
+    status = torch.zeros(nb, dtype=torch.int32, device=dev)
+    cost = torch.zeros(nb, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    flags = tb.EVAL_G | tb.EVAL_JAC
+    steps = max(3, min(args.steps, 10))
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize(dev)
+    for i in range(3):
+        batch.eval_device(rng_sets[i % 2], g=g, jac=jac, status=status, flags=flags, stream=stream)
+    barrier()
+    total_ms, gathered, flagged = 0.0, 0, 0
+    for i in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record(stream)
+        batch.eval_device(rng_sets[i % 2], g=g, jac=jac, status=status, flags=flags, stream=stream)
+        b.record(stream)
+        barrier()
+        total_ms += a.elapsed_time(b)
+        cost_all, status_all = gather_cost_status(cost.cpu().numpy(), status.cpu().numpy(), total, device=dev)   # NCCL all_gather (N > 1)
+        gathered, flagged = len(status_all), int((status_all != 0).sum())
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    del batch, g, jac
+    torch.cuda.empty_cache()
+    bytes_per_eval = 8 * (p.n + p.m + p.nnz)
+    achieved_per_gpu = bytes_per_eval * nb / (ms * 1e-3) / 1e9
+    return {"workload": "BASELINE configs[4]: Anymal fly-trot C1 multi-start, terrains drawn from Slope / Chimney / Gap per instance",
+            "instances_total": total, "instances_per_gpu": nb, "scaling": "strong", "steps": steps, "ms_per_step": ms,
+            "value": total / (ms * 1e-3), "unit": UNIT, "roofline_frac_per_gpu": achieved_per_gpu / read_peak()[0],
+            "collective": {"op": "all_gather of per-instance cost (f64) + status (i32) after every step, outside the timed region",
+                           "backend": "nccl" if world > 1 else "none (one rank: local copy)", "gathered_instances": gathered, "flagged": flagged}}
 
 
 def run_cuda(args):
@@ -306,6 +405,23 @@ def run_cuda(args):
     e2e_value = world * B * e2e_steps / float(te.item())
     h2d = B * p.n * 8
     d2h = B * (p.m + p.nnz) * 8 + B * 4
+    # the PCIe ceiling of this box for that step, measured in the same run on the same buffers: a bare pinned D2H copy of
+    # the step's output bytes (all ranks at once, max over ranks) — what the step would cost if the GPU computed in zero time
+    jac_pinned = torch.from_numpy(out["jac"]); g_pinned = torch.from_numpy(out["g"])
+    cs = torch.cuda.Stream(dev)
+    with torch.cuda.stream(cs):
+        jac_pinned.copy_(jac, non_blocking=True); g_pinned.copy_(g, non_blocking=True)
+    cs.synchronize(); sync_all()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        with torch.cuda.stream(cs):
+            jac_pinned.copy_(jac, non_blocking=True); g_pinned.copy_(g, non_blocking=True)
+        cs.synchronize()
+    tc = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    d2h_ceiling_s = float(tc.item())
+    config5 = run_config5(args, tb, dev, world, rank, local) if not os.environ.get("TWB_NO_CONFIG5") else None
 
     if rank == 0:
         import oracle_lib
@@ -345,7 +461,8 @@ def run_cuda(args):
                        "iterates": "x0 + sigma*N(0,1), sigma 0.05 pos / 0.2 vel / 10 N force (SURVEY §8d)"},
             "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_best": per_step[0],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": "static: ncu --set full capture of round 1 (profiles/traffic_bytes_per_launch.json), not measured in this run",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_eval * B, "avg_launch_ms": avg_kernel_ms,
                          "kernel": "whole evaluation: TransposeIn -> RomNodeOut | DynOut (two streams) -> TransposeOut; "
                                    "CUDA events on the launching stream around every step of the timed region",
@@ -354,8 +471,12 @@ def run_cuda(args):
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{cpu_sample} evaluations of instances of the same batch, OpenMP over instances, {cpu_dt:.1f} s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "twb_batch_eval_host (pinned host buffers)",
-                    "host_cpus_bound_per_rank": numa_cpus},
+                    "steps": e2e_steps, "api": "twb_batch_eval_host (pinned host buffers; H2D, kernels and D2H pipelined in chunks of 512 instances)",
+                    "host_cpus_bound_per_rank": numa_cpus,
+                    "ceiling": {"value": world * B / d2h_ceiling_s, "unit": UNIT, "d2h_gbs_per_rank": (d2h - 4 * B) / d2h_ceiling_s / 1e9,
+                                "how": "bare pinned D2H copy of the step's g + jac bytes on every rank at once, max over ranks, same run"},
+                    "frac_of_ceiling": e2e_value / (world * B / d2h_ceiling_s)},
+            "config5": config5,
             "gpu_launches": args.steps * batch.launches_per_eval(flags),
             "clocks": sampler.summary() if sampler else None,
         }
@@ -378,9 +499,14 @@ def main():
     global WORKLOAD
     if args.workload:
         WORKLOAD = args.workload
+    import fcntl
     import __graft_entry__ as ge
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        ge.build(quiet=True)
+    # every rank builds under one file lock: the first one runs make, the others find everything up to date — nobody
+    # imports a half-written library (torchrun starts all ranks at once)
+    with open(os.path.join(ROOT, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        ge.build(quiet=True, import_package=(args.impl != "reference"))
+        fcntl.flock(lock, fcntl.LOCK_UN)
     if args.impl == "reference":
         run_reference(args)
     else:

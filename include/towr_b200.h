@@ -189,6 +189,11 @@ int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, in
 int twb_batch_set_grid_map(twb_batch* b, const float* heights, int size_x, int size_y, double resolution,
                            double pos_x, double pos_y);
 
+/* Batched setup on the device (no host loop): twb_problem_goal_instances for the B instances of the batch.  goals: device
+ * [B][6]; x0 / x_lower / x_upper: device [B][n] (any may be NULL).  The terrain under each goal is the INSTANCE's terrain
+ * (twb_batch_set_terrains, height grids included; else twb_spec.terrain).  The call only enqueues on `stream`. */
+int twb_batch_goal_instances_device(twb_batch* b, const double* goals, double* x0, double* x_lower, double* x_upper, void* stream);
+
 #define TWB_EVAL_G 1u     /* constraint values        (Problem::EvaluateConstraints)       */
 #define TWB_EVAL_JAC 2u   /* Jacobian values          (Problem::EvalNonzerosOfJacobian)    */
 #define TWB_EVAL_COST 4u  /* cost + gradient          (EvaluateCostFunction[Gradient])     */

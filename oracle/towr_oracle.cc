@@ -48,8 +48,28 @@
 #endif
 
 #include "../include/towr_b200.h"  // twb_spec layout + enums only (plain C data)
+typedef double twb_f64;   // IEEE double in every build (see below)
+
+// Extended-precision build (oracle/Makefile: libtowr_oracle_ld.so, -DTWB_ORACLE_LONG_DOUBLE): every `double` below this
+// line becomes the x87 80-bit long double (64-bit mantissa), math calls resolve to the std:: long double overloads, and the
+// extern "C" entry points take numpy.longdouble arrays.  Used by tests/test_oracle.py only, to differentiate g numerically
+// at ~1e-12 accuracy (Richardson-extrapolated central differences) and pin the analytic Jacobian of the double build to
+// <= 1e-10 — four orders tighter than a double-precision finite difference can.  twb_spec (above) stays plain double.
+#ifdef TWB_ORACLE_LONG_DOUBLE
+typedef long double twb_ld;
+#define double twb_ld
+#endif
+// the time grids decide the STRUCTURE (sample counts, polynomial counts): their arithmetic stays IEEE double in both builds
 
 namespace {
+#ifdef TWB_ORACLE_LONG_DOUBLE   // unqualified calls below must not fall back to the C library's double versions
+inline double sin(double x) { return std::sin(x); }
+inline double cos(double x) { return std::cos(x); }
+inline double sqrt(double x) { return std::sqrt(x); }
+inline double fabs(double x) { return std::fabs(x); }
+inline double floor(double x) { return std::floor(x); }
+inline double pow(double x, double y) { return std::pow(x, y); }
+#endif
 
 constexpr double kInf = 1e20;  // ifopt::inf
 struct Bound { double lo, up; };
@@ -1029,8 +1049,8 @@ struct CSet {
 };
 
 std::vector<double> MakeDts(double T, double dt) {  // time_discretization_constraint.cc:37-51
-  double t = 0.0; std::vector<double> dts = {t};
-  for (int i = 0; i < floor(T / dt); ++i) { t += dt; dts.push_back(t); }
+  twb_f64 t = 0.0; const twb_f64 T64 = (twb_f64)T, dt64 = (twb_f64)dt; std::vector<double> dts = {t};
+  for (int i = 0; i < std::floor(T64 / dt64); ++i) { t += dt64; dts.push_back(t); }
   dts.push_back(T);
   return dts;
 }
@@ -1349,12 +1369,12 @@ struct Problem {
   std::vector<int> row_ptr, col_idx;           // structure from the first Jacobian
 
   static std::vector<double> BasePolyDurations(double T, double dt) {  // parameters.cc:82-98
-    std::vector<double> v; double t_left = T; double eps = 1e-10;
-    while (t_left > eps) { double d = t_left > dt ? dt : t_left; v.push_back(d); t_left -= dt; }
+    std::vector<double> v; twb_f64 t_left = (twb_f64)T; const twb_f64 eps = 1e-10, dt64 = (twb_f64)dt;
+    while (t_left > eps) { twb_f64 d = t_left > dt64 ? dt64 : t_left; v.push_back(d); t_left -= dt64; }
     return v;
   }
   double TotalTime() const {  // parameters.cc:112-126
-    double T = 0.0;
+    twb_f64 T = 0.0;
     if (spec.n_ee > 0) { T = 0.0; for (int i = 0; i < spec.n_phases[0]; ++i) T += spec.phase_durations[0][i]; }
     return T;
   }
@@ -1369,7 +1389,7 @@ struct Problem {
     model.Init(robot);
     const int n_ee = spec.n_ee;
     const double T = TotalTime();
-    auto v3 = [](const double* p) { return V3{p[0], p[1], p[2]}; };
+    auto v3 = [](const auto* p) { return V3{p[0], p[1], p[2]}; };
     auto dims = [](const int* f) { std::vector<int> d; for (int i = 0; i < 3; ++i) if (f[i]) d.push_back(i); return d; };
     std::vector<double> base_T = BasePolyDurations(T, spec.duration_base_polynomial);
 

@@ -436,6 +436,37 @@ def test_footstep_plan_extraction_matches_oracle():
             assert abs(got[:, 1].sum() - T) < 1e-9                                     # durations tile the horizon
 
 
+def test_goal_instances_on_the_device():
+    """Batched setup: x0 / variable bounds of goal-randomised instances from a kernel, against the host
+    builder (twb_problem_goal_instances, itself bit-equal to the oracle in tests/test_structure.py) — every robot class,
+    optimised durations included; then with a height grid as the instances' terrain, which only the device path serves."""
+    import torch
+    rng = np.random.default_rng(31)
+    for name in ("hopper", "anymal_trot_block", "biped_walk_stairs", "hyq_gallop_gap", "anymal_trot_block_base_rom"):
+        p = tb.Problem(tb.make_formulation(name).to_spec())
+        B = 70
+        goals = np.column_stack([rng.uniform(0.3, 2.5, B), rng.uniform(-0.4, 0.4, B), np.full(B, 0.5), np.zeros(B), np.zeros(B), rng.uniform(-0.5, 0.5, B)])
+        x0h, xlh, xuh = p.goal_instances(goals)
+        bt = p.batch(B)
+        x0, lo, up = bt.goal_instances_device(torch.from_numpy(goals).cuda())
+        assert np.allclose(x0.cpu().numpy(), x0h, rtol=1e-14, atol=1e-15), name    # sincos(yaw) may differ from the host's libm in the last place
+        assert np.allclose(lo.cpu().numpy(), xlh, rtol=1e-14, atol=0) and np.allclose(up.cpu().numpy(), xuh, rtol=1e-14, atol=0), name
+    # the CSV height grid under the goals: final base z and footholds follow the grid
+    p = tb.Problem(tb.make_formulation("anymal_trot_block").to_spec())
+    B = 33
+    grid = rng.integers(0, 4, (12, 20)) * 0.04
+    bt = p.batch(B); bt.set_terrains(np.full(B, tb.GRID_CSV, np.int32)); bt.set_grid_terrain(grid)
+    goals = np.column_stack([rng.uniform(0.5, 2.5, B), rng.uniform(0.3, 1.0, B), np.full(B, 0.5), np.zeros(B), np.zeros(B), np.zeros(B)])
+    x0, _, _ = bt.goal_instances_device(torch.from_numpy(goals).cuda(), want_bounds=False)
+    x0 = x0.cpu().numpy()
+    oracle_lib.set_grid(grid)
+    (_, s_lin, n_lin), = [v for v in p.variable_sets() if v[0] == "base-lin"]
+    nominal_z = tb.robot_info(tb.ANYMAL)["nominal_stance"][0][2]
+    for b in range(B):
+        h = oracle_lib.terrain_point(tb.GRID_CSV, goals[b, 0], goals[b, 1])[0]
+        assert abs(x0[b, s_lin + n_lin - 6 + 2] - (h - nominal_z)) < 1e-14          # last base-lin node, z
+
+
 def test_linear_equality_and_soft_constraint():
     """towr::LinearEqualityConstraint and towr::SoftConstraint (the two ifopt components no Parameters enum reaches) on
     the device against the oracle."""

@@ -190,6 +190,15 @@ def test_goal_randomised_instances_match_oracle():
     assert np.array_equal(x0[0], p.GetVariableValues()) and np.array_equal(xl[0], p.bounds()[0])
 
 
+def test_bench_spec_fixture_is_current():
+    """tests/golden/bench_specs.json (what bench.py's reference arm evaluates without loading the product library) equals
+    the recipes of towr_b200.configs."""
+    import json
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_specs.json")))
+    for name, hexbytes in fx.items():
+        assert bytes(tb.make_formulation(name).to_spec()).hex() == hexbytes, name
+
+
 def test_trajectory_dims_match_oracle():
     for name, dt in (("hopper", 0.05), ("anymal_trot_block", 0.01), ("hyq_gallop_gap", 0.1)):
         spec = tb.make_formulation(name).to_spec(); p = tb.Problem(spec)

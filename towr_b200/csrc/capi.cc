@@ -77,6 +77,9 @@ struct twb_batch {
   double *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_cost = nullptr, *d_grad = nullptr;
   int* d_status = nullptr;
   cudaStream_t stream = nullptr, aux0 = nullptr, aux1 = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-pointer evaluation
+  std::vector<cudaEvent_t> ev_chunk;              // per chunk: H2D done, kernels done
+  int e2e_chunk = 512;                            // instances per chunk of twb_batch_eval_host (TWB_E2E_CHUNK)
   std::vector<cudaEvent_t> ev;    // fork/join events of the two-stream pipeline
   int launches_last = 0;
 };
@@ -182,10 +185,11 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   }
   TWB_UP(samples) TWB_UP(dyn) TWB_UP(rom) TWB_UP(groups) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc)
   TWB_UP(base_motion) TWB_UP(cost) TWB_UP(pairs) TWB_UP(coefs) TWB_UP(cta_lists) TWB_UP(dyn_ang_basis)
-  TWB_UP(phase_defs) TWB_UP(phase_polys) TWB_UP(phase_units) TWB_UP(slot_of)
+  TWB_UP(phase_defs) TWB_UP(phase_polys) TWB_UP(phase_units) TWB_UP(slot_of) TWB_UP(goal_vars)
 #undef TWB_UP
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
+  if (const char* v = std::getenv("TWB_E2E_CHUNK")) b->e2e_chunk = std::max(32, std::atoi(v));
   b->ld = ((size_t)batch_size + 31) & ~(size_t)31;
   const size_t xt_bytes = (size_t)(b->plan.n + 1) * b->ld * sizeof(double);
   if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_XT), xt_bytes)) != cudaSuccess ||
@@ -218,6 +222,9 @@ void twb_batch_destroy(twb_batch* b) {
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
+  if (b->s_in) cudaStreamDestroy(b->s_in);
+  if (b->s_out) cudaStreamDestroy(b->s_out);
+  for (auto ev : b->ev_chunk) cudaEventDestroy(ev);
   cudaFree(b->d_x); cudaFree(b->d_g); cudaFree(b->d_jac); cudaFree(b->d_cost); cudaFree(b->d_grad); cudaFree(b->d_status);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -265,6 +272,16 @@ int twb_batch_set_grid_map(twb_batch* b, const float* heights, int size_x, int s
   if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_gmap), bytes)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
   if ((e = cudaMemcpy(b->d_gmap, heights, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return CudaFail(e, "cudaMemcpy");
   b->plan.gmap = b->d_gmap; b->plan.gmap_sx = size_x; b->plan.gmap_sy = size_y; b->plan.gmap_res = resolution; b->plan.gmap_px = pos_x; b->plan.gmap_py = pos_y;
+  return TWB_OK;
+}
+
+int twb_batch_goal_instances_device(twb_batch* b, const double* goals, double* x0, double* x_lower, double* x_upper, void* stream) {
+  if (!b || !goals) return Fail(TWB_ERR_INVALID, "null argument");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  const twb::Formulation& f = b->prob->f;
+  int rc = twb::LaunchGoalInstances(b->plan, f.tables.goal_setup, goals, b->d_terrain, f.spec.terrain, x0, x_lower, x_upper, b->B, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "goal-instance kernel launch");
   return TWB_OK;
 }
 
@@ -523,17 +540,43 @@ int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac, d
   if (flags & TWB_EVAL_JAC) TWB_ENSURE(b->d_jac, B * f.nnz, double)
   if (has_cost) { TWB_ENSURE(b->d_cost, B, double) TWB_ENSURE(b->d_grad, B * f.n, double) }
 #undef TWB_ENSURE
+  // Pipelined in chunks of whole instance tiles: the H2D copy of chunk c+1 (copy-in stream), the kernels of chunk c
+  // (b->stream + the two auxiliary streams) and the D2H copies of chunk c-1 (copy-out stream) overlap, so the call costs
+  // what the larger of the two PCIe directions costs (the D2H of g + jac: 524 MB on config 2) plus one chunk of latency.
+  const size_t chunk = ((size_t)std::max(32, b->e2e_chunk) + 31) & ~(size_t)31;
+  const size_t n_chunks = (B + chunk - 1) / chunk;
+  if (!b->s_in && ((e = cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+                   (e = cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking)) != cudaSuccess)) return CudaFail(e, "cudaStreamCreate");
+  while (b->ev_chunk.size() < 2 * n_chunks) {
+    cudaEvent_t ev; if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return CudaFail(e, "cudaEventCreate");
+    b->ev_chunk.push_back(ev);
+  }
   cudaStream_t s = b->stream;
-  if ((e = cudaMemcpyAsync(b->d_x, x, sizeof(double) * B * f.n, cudaMemcpyHostToDevice, s)) != cudaSuccess)
-    return CudaFail(e, "H2D copy");
-  int rc = twb_batch_eval_device(b, b->d_x, b->d_g, b->d_jac, has_cost ? b->d_cost : nullptr,
-                                 has_cost ? b->d_grad : nullptr, b->d_status, flags, s);
-  if (rc != TWB_OK) return rc;
-  if ((flags & TWB_EVAL_G) && g) cudaMemcpyAsync(g, b->d_g, sizeof(double) * B * f.m, cudaMemcpyDeviceToHost, s);
-  if ((flags & TWB_EVAL_JAC) && jac) cudaMemcpyAsync(jac, b->d_jac, sizeof(double) * B * f.nnz, cudaMemcpyDeviceToHost, s);
-  if (has_cost && cost) cudaMemcpyAsync(cost, b->d_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, s);
-  if (has_cost && grad) cudaMemcpyAsync(grad, b->d_grad, sizeof(double) * B * f.n, cudaMemcpyDeviceToHost, s);
-  if (status) cudaMemcpyAsync(status, b->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, s);
+  unsigned kflags = flags & (TWB_EVAL_G | TWB_EVAL_JAC);
+  if (has_cost) kflags |= TWB_EVAL_COST;
+  int launches = 0;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t off = c * chunk, nb = std::min(chunk, B - off), tile0 = off / 32;
+    if ((e = cudaMemcpyAsync(b->d_x + off * f.n, x + off * f.n, sizeof(double) * nb * f.n, cudaMemcpyHostToDevice, b->s_in)) != cudaSuccess)
+      return CudaFail(e, "H2D copy");
+    cudaEventRecord(b->ev_chunk[2 * c], b->s_in);
+    cudaStreamWaitEvent(s, b->ev_chunk[2 * c], 0);
+    int rc = twb::LaunchEval(b->plan, b->d_x + off * f.n, b->d_XT + tile0 * (size_t)(f.n + 1) * 32, b->d_GT + tile0 * (size_t)std::max(f.m, 1) * 32,
+                             (flags & TWB_EVAL_G) ? b->d_g + off * f.m : nullptr, (flags & TWB_EVAL_JAC) ? b->d_jac + off * f.nnz : nullptr,
+                             has_cost ? b->d_cost + off : nullptr, has_cost ? b->d_grad + off * f.n : nullptr, b->d_status + off,
+                             b->d_terrain ? b->d_terrain + off : nullptr, f.spec.terrain, (int)nb, kflags, s, b->aux0, b->aux1, b->ev.data(), &launches);
+    if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
+    cudaEventRecord(b->ev_chunk[2 * c + 1], s);
+    cudaStreamWaitEvent(b->s_out, b->ev_chunk[2 * c + 1], 0);
+    cudaStream_t o = b->s_out;
+    if ((flags & TWB_EVAL_G) && g) cudaMemcpyAsync(g + off * f.m, b->d_g + off * f.m, sizeof(double) * nb * f.m, cudaMemcpyDeviceToHost, o);
+    if ((flags & TWB_EVAL_JAC) && jac) cudaMemcpyAsync(jac + off * f.nnz, b->d_jac + off * f.nnz, sizeof(double) * nb * f.nnz, cudaMemcpyDeviceToHost, o);
+    if (has_cost && cost) cudaMemcpyAsync(cost + off, b->d_cost + off, sizeof(double) * nb, cudaMemcpyDeviceToHost, o);
+    if (has_cost && grad) cudaMemcpyAsync(grad + off * f.n, b->d_grad + off * f.n, sizeof(double) * nb * f.n, cudaMemcpyDeviceToHost, o);
+    if (status) cudaMemcpyAsync(status + off, b->d_status + off, sizeof(int) * nb, cudaMemcpyDeviceToHost, o);
+  }
+  b->launches_last = launches;
+  if ((e = cudaStreamSynchronize(b->s_out)) != cudaSuccess) return CudaFail(e, "evaluation");
   if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return CudaFail(e, "evaluation");
   if (!has_cost && (flags & TWB_EVAL_COST)) {  // Problem::EvaluateCostFunction without cost terms: 0
     if (cost) for (size_t i = 0; i < B; ++i) cost[i] = 0.0;

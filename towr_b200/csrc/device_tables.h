@@ -160,6 +160,27 @@ struct CostEntry {
   double weight;
 };
 
+// ---- batched setup: NlpFormulation::GetVariableSets' initial guess and variable bounds (nlp_formulation.cc:95-181) as a
+// per-variable recipe, so that goal-randomised instances of one structure class are set up by a kernel:
+//   position variable: x0 = a[dim] + frac * (b[dim] - a[dim])   (NodesVariables::SetByLinearInterpolation, nodes_variables.cc:126-150;
+//                      frac = node / (n_nodes - 1) of the LAST node the variable belongs to)
+//   velocity variable: x0 = (b[dim] - a[dim]) / T
+// with (a, b) = (initial, final) of the variable's set: base-lin (final z = terrain height - nominal z), base-ang, ee-motion_e
+// (final = goal base + yaw-rotated nominal stance, z on the terrain), ee-force_e (a = b = (0, 0, m g / n_ee)); ee-schedule
+// variables are constants.  Bounds: free, a constant on both sides, the goal's own base position / angle, or a constant pair.
+enum GoalBound : int8_t { kBoundFree = 0, kBoundConst = 1, kBoundGoalLin = 2, kBoundGoalAng = 3, kBoundPair = 4 };
+enum GoalKind : int8_t { kGoalLin = 0, kGoalAng = 1, kGoalMotion = 2, kGoalForce = 3, kGoalConst = 4 };
+struct GoalVar {
+  int8_t kind, ee, deriv, dim;   // GoalKind, foot (motion / force), 0 position / 1 velocity, dimension
+  int8_t bound, pad[3];          // GoalBound
+  double frac;                   // node fraction (positions); constant x0 (kGoalConst)
+  double c0, c1;                 // bound constants
+};
+struct GoalSetup {                // goal-independent inputs of the recipe (twb_spec + robot)
+  double initial_lin[3], initial_ang[3], initial_ee[kMaxEE][3], nominal[kMaxEE][3];
+  double t_total, f_stance_z;
+};
+
 struct Plan {
   int n, m, nnz, n_ee;
   int n_dyn, n_rom, n_groups, n_cost;
@@ -194,6 +215,7 @@ struct Plan {
   const float* gmap;
   int gmap_sx, gmap_sy;
   double gmap_res, gmap_px, gmap_py;
+  const GoalVar* goal_vars;             // [n] recipe of x0 / bounds per variable
   // phase-duration optimisation (all null / 0 otherwise)
   int n_phase_units, n_phase_defs;
   const PhaseSplineDef* phase_defs;   // [2 * n_ee]: ee-motion_e at 2e, ee-force_e at 2e + 1

@@ -383,6 +383,50 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   InitialGuessAndBounds(sp, rb, T, optimize_timings, &sets, &x0, &x_lower, &x_upper);
   holder = std::make_shared<SetsHolder>(); holder->sets = sets; holder->robot = rb; holder->T = T; holder->base_T = base_T;
 
+  // ---- the same initial guess / bounds as a per-variable recipe for the device (GoalInstanceKernel): mirrors
+  // InitialGuessAndBounds above line by line; tests compare the kernel with Formulation::GoalInstance
+  {
+    tables = HostTables{};
+    std::vector<GoalVar>& gv = tables.goal_vars; gv.assign(n, GoalVar{});
+    auto fill_set = [&](const NodeSet& ns, int kind, int ee) {
+      for (int node = 0; node < ns.n_nodes; ++node)
+        for (int k = 0; k < 6; ++k) {
+          const int v = ns.var[node][k];
+          if (v < 0) continue;
+          GoalVar& g = gv[ns.offset + v];
+          g.kind = (int8_t)kind; g.ee = (int8_t)ee; g.deriv = (int8_t)(k / 3); g.dim = (int8_t)(k % 3);
+          g.frac = node / static_cast<double>(ns.n_nodes - 1);   // the later node of a shared variable wins, like the reference's loop
+          g.bound = kBoundFree;
+        }
+    };
+    auto fix = [&](const NodeSet& ns, int node, int deriv, int dim, int8_t mode, double c) {
+      const int v = ns.Var(node, deriv, dim);
+      if (v >= 0) { gv[ns.offset + v].bound = mode; gv[ns.offset + v].c0 = c; gv[ns.offset + v].c1 = c; }
+    };
+    fill_set(lin, kGoalLin, 0); fill_set(ang, kGoalAng, 0);
+    for (int e = 0; e < n_ee; ++e) { fill_set(motion(e), kGoalMotion, e); fill_set(force(e), kGoalForce, e); }
+    const int last = lin.n_nodes - 1;
+    for (int d = 0; d < 3; ++d) {
+      fix(lin, 0, kPos, d, kBoundConst, sp.initial_base_lin_pos[d]); fix(lin, 0, kVel, d, kBoundConst, sp.initial_base_lin_vel[d]);
+      fix(ang, 0, kPos, d, kBoundConst, sp.initial_base_ang_pos[d]); fix(ang, 0, kVel, d, kBoundConst, sp.initial_base_ang_vel[d]);
+      if (sp.bounds_final_lin_pos[d]) fix(lin, last, kPos, d, kBoundGoalLin, 0.0);
+      if (sp.bounds_final_lin_vel[d]) fix(lin, last, kVel, d, kBoundConst, sp.final_base_lin_vel[d]);
+      if (sp.bounds_final_ang_pos[d]) fix(ang, last, kPos, d, kBoundGoalAng, 0.0);
+      if (sp.bounds_final_ang_vel[d]) fix(ang, last, kVel, d, kBoundConst, sp.final_base_ang_vel[d]);
+      for (int e = 0; e < n_ee; ++e) fix(motion(e), 0, kPos, d, kBoundConst, sp.initial_ee_W[e][d]);
+    }
+    if (optimize_timings)
+      for (int e = 0; e < n_ee; ++e)
+        for (int i = 0; i + 1 < sp.n_phases[e]; ++i) {
+          GoalVar& g = gv[sched0[e] + i];
+          g.kind = kGoalConst; g.frac = sp.phase_durations[e][i]; g.bound = kBoundPair; g.c0 = sp.bound_phase_duration_min; g.c1 = sp.bound_phase_duration_max;
+        }
+    GoalSetup& gs = tables.goal_setup; gs = GoalSetup{};
+    for (int d = 0; d < 3; ++d) { gs.initial_lin[d] = sp.initial_base_lin_pos[d]; gs.initial_ang[d] = sp.initial_base_ang_pos[d]; }
+    for (int e = 0; e < n_ee; ++e) for (int d = 0; d < 3; ++d) { gs.initial_ee[e][d] = sp.initial_ee_W[e][d]; gs.nominal[e][d] = rb.nominal[e][d]; }
+    gs.t_total = T; gs.f_stance_z = rb.mass * 9.80665 / n_ee;
+  }
+
   // ---- splines (spline_holder.cc:35-61, fixed durations)
   auto poly_durations = [&](const NodeSet& s, int e) {  // nodes_variables_phase_based.cc:78-89
     std::vector<double> d;
@@ -394,7 +438,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   for (int e = 0; e < n_ee; ++e) { sp_motion.push_back({&motion(e), poly_durations(motion(e), e)}); sp_force.push_back({&force(e), poly_durations(force(e), e)}); }
 
   // ---- units and their Jacobian entries
-  HostTables& tb = tables; tb = HostTables{};
+  HostTables& tb = tables;
   // foot splines: fixed-duration samples, or a reference to the PhaseSpline when the durations are optimised
   auto foot_sample = [&](int e, int kind, double t) {   // kind 0: ee-motion, 1: ee-force
     if (!optimize_timings) return MakeSample(kind == 0 ? sp_motion[e] : sp_force[e], t, zero_slot);

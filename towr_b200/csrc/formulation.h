@@ -53,6 +53,8 @@ struct HostTables {
   std::vector<PhasePoly> phase_polys;
   std::vector<PhaseUnit> phase_units;
   std::vector<int32_t> slot_of;
+  std::vector<GoalVar> goal_vars;
+  GoalSetup goal_setup{};
 };
 
 class Formulation {

@@ -1027,15 +1027,15 @@ __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict
   if (flags & 2u) StoreCta(P, node_smem, P.cta_lists + P.node_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0), st);
 }
 
-// NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the
-// dense gradient row (node_cost.cc:65-76), both in the reference's order.  One thread per instance.
+// NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the dense gradient row
+// (node_cost.cc:65-76), both in the reference's order.  lane = instance (coalesced reads of XT); the gradient row is
+// zeroed by a memset (coalesced) before this kernel, which then only touches the columns that carry a cost term.
 __global__ void __launch_bounds__(128) CostKernel(const Plan P, const double* __restrict__ XT, double* __restrict__ cost,
                                                   double* __restrict__ grad, int nb) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   const ConstCol xs = TiledCol(XT, b, P.n + 1);
   double* gr = grad ? grad + (size_t)b * P.n : nullptr;
-  if (gr) for (int i = 0; i < P.n; ++i) gr[i] = 0.0;
   double total_cost = 0.0, term = 0.0;
   for (int i = 0; i < P.n_cost; ++i) {
     const CostEntry ce = P.cost[i];
@@ -1626,6 +1626,62 @@ int LaunchSoftConstraint(const Plan& P, const double* g, const double* jac, cons
   return (int)cudaGetLastError();
 }
 
+// ---- batched setup: x0 and variable bounds of goal-randomised instances, block = instance ------------------
+// NlpFormulation::GetVariableSets (nlp_formulation.cc:95-181) through the per-variable recipe Plan::goal_vars; the terrain
+// under the goal is the instance's own (per-instance id, height grids included — which the host path cannot serve).
+__global__ void __launch_bounds__(128) GoalInstanceKernel(const Plan P, const GoalSetup S, const double* __restrict__ goals, const int* __restrict__ terrain_ids,
+                                                          int default_terrain, double* __restrict__ x0, double* __restrict__ lo, double* __restrict__ up, int nb) {
+  __shared__ double a_[2 + 2 * kMaxEE][3], b_[2 + 2 * kMaxEE][3];   // (initial, final) per set: lin, ang, motion_e.., force_e..
+  const int b = blockIdx.x;
+  if (b >= nb) return;
+  const double* gp = goals + 6 * (size_t)b;
+  const int terrain = terrain_ids ? __ldg(terrain_ids + b) : default_terrain;
+  if (threadIdx.x == 0) {
+    const double fx = gp[0], fy = gp[1];
+    const double fz = EvalTerrain(P, terrain, fx, fy).h - S.nominal[0][2];
+    const double fin[3] = {fx, fy, fz};
+    for (int d = 0; d < 3; ++d) { a_[0][d] = S.initial_lin[d]; b_[0][d] = fin[d]; a_[1][d] = S.initial_ang[d]; b_[1][d] = gp[3 + d]; }
+  } else if ((int)threadIdx.x <= P.n_ee) {
+    const int e = threadIdx.x - 1;
+    double sz, cz; sincos(gp[5], &sz, &cz);   // yaw-only rotation of the nominal stance (EulerConverter::GetRotationMatrixBaseToWorld with x = y = 0)
+    const double* nom = S.nominal[e];
+    const double R[3][3] = {{cz, -sz, 0.0}, {sz, cz, 0.0}, {-0.0, 0.0, 1.0}};
+    double w[3];
+    for (int i = 0; i < 3; ++i) w[i] = gp[i] + (R[i][0] * nom[0] + R[i][1] * nom[1] + R[i][2] * nom[2]);
+    const double goal[3] = {w[0], w[1], EvalTerrain(P, terrain, w[0], w[1]).h};
+    for (int d = 0; d < 3; ++d) {
+      a_[2 + e][d] = S.initial_ee[e][d]; b_[2 + e][d] = goal[d];
+      a_[2 + kMaxEE + e][d] = b_[2 + kMaxEE + e][d] = (d == 2) ? S.f_stance_z : 0.0;
+    }
+  }
+  __syncthreads();
+  const double inf = 1e20;
+  for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+    const GoalVar v = P.goal_vars[i];
+    double x, l = -inf, u = inf;
+    if (v.kind == kGoalConst) x = v.frac;
+    else {
+      const int set = v.kind == kGoalLin ? 0 : v.kind == kGoalAng ? 1 : v.kind == kGoalMotion ? 2 + v.ee : 2 + kMaxEE + v.ee;
+      const double a = a_[set][v.dim], dp = b_[set][v.dim] - a;
+      x = v.deriv == 0 ? a + v.frac * dp : dp / S.t_total;
+    }
+    if (v.bound == kBoundConst) l = u = v.c0;
+    else if (v.bound == kBoundGoalLin) l = u = gp[v.dim];
+    else if (v.bound == kBoundGoalAng) l = u = gp[3 + v.dim];
+    else if (v.bound == kBoundPair) { l = v.c0; u = v.c1; }
+    const size_t o = (size_t)b * P.n + i;
+    if (x0) x0[o] = x;
+    if (lo) lo[o] = l;
+    if (up) up[o] = u;
+  }
+}
+int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, const int* terrain_ids, int default_terrain, double* x0, double* lo,
+                        double* up, int nb, cudaStream_t s) {
+  if (nb <= 0) return 0;
+  GoalInstanceKernel<<<nb, 128, 0, s>>>(P, S, goals, terrain_ids, default_terrain, x0, lo, up, nb);
+  return (int)cudaGetLastError();
+}
+
 int OutKernelsPerEval(const Plan& P) {
 #if TWB_FUSED
   return (P.n_dyn + P.n_rom + P.n_groups) > 0;
@@ -1668,7 +1724,10 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
     }
     if (e != cudaSuccess) return (int)e;
   }
-  if (want_cost) { CostKernel<<<(nb + 127) / 128, 128, 0, aux1>>>(P, XT, cost, grad, nb); ++count; TWB_MARK("CostKernel", aux1); }
+  if (want_cost) {
+    if (grad) cudaMemsetAsync(grad, 0, sizeof(double) * (size_t)nb * P.n, aux1);
+    CostKernel<<<(nb + 127) / 128, 128, 0, aux1>>>(P, XT, cost, grad, nb); ++count; TWB_MARK("CostKernel", aux1);
+  }
   if (fork) {
     cudaEventRecord(ev[1], aux0); cudaEventRecord(ev[2], aux1);
     cudaStreamWaitEvent(s, ev[1], 0); cudaStreamWaitEvent(s, ev[2], 0);

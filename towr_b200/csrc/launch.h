@@ -37,6 +37,9 @@ int LaunchNearestPlanes(const double* plan, const int* n_states, int max_states,
 int LaunchLinearEquality(const Plan& P, const double* x, double* XT, int col0, int n_cols, const double* M, int rows, double* g, int nb, cudaStream_t s);
 int LaunchSoftConstraint(const Plan& P, const double* g, const double* jac, const int* row_ptr, const int* col_idx, int row0, int n_rows,
                          const double* b_avg, const double* w, double* cost, double* grad, int nb, cudaStream_t s);
+// x0 / variable bounds of `nb` goal-randomised instances (goals[b][6] = final base position, final base Euler angles)
+int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, const int* terrain_ids, int default_terrain, double* x0, double* lo,
+                        double* up, int nb, cudaStream_t s);
 // number of output kernels one evaluation launches for this plan
 int OutKernelsPerEval(const Plan& P);
 int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,

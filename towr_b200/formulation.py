@@ -400,6 +400,22 @@ class Batch:
         check(lib.twb_batch_eval_host(self._h, ptr(x), ptr(g), ptr(jac), ptr(cost), ptr(grad), ptr(status), flags))
         return dict(g=g, jac=jac, cost=cost, grad=grad, status=status)
 
+    def goal_instances_device(self, goals, want_bounds=True, stream=None):
+        """Batched setup on the device: goals (B, 6) torch CUDA float64 = final base position + final base Euler angles of
+        every instance.  Returns (x0, x_lower, x_upper) CUDA tensors of shape (B, n) (bounds None if not wanted).  The terrain
+        under each goal is the instance's own (set_terrains / grids)."""
+        import torch
+        p = self.problem
+        assert goals.is_cuda and goals.dtype == torch.float64 and goals.is_contiguous() and tuple(goals.shape) == (self.B, 6)
+        if stream is None:
+            stream = torch.cuda.current_stream(goals.device)
+        x0 = torch.empty((self.B, p.n), dtype=torch.float64, device=goals.device)
+        lo = torch.empty_like(x0) if want_bounds else None
+        up = torch.empty_like(x0) if want_bounds else None
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        check(lib.twb_batch_goal_instances_device(self._h, ptr(goals), ptr(x0), ptr(lo), ptr(up), C.c_void_p(stream.cuda_stream)))
+        return x0, lo, up
+
     def eval_device(self, x, g=None, jac=None, cost=None, grad=None, status=None,
                     flags=capi.EVAL_G | capi.EVAL_JAC, stream=None):
         """Device-pointer variant. Arguments are torch CUDA float64 tensors (or None);
