@@ -461,7 +461,7 @@ def run_cuda(args):
                        "iterates": "x0 + sigma*N(0,1), sigma 0.05 pos / 0.2 vel / 10 N force (SURVEY §8d)"},
             "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_best": per_step[0],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "static: ncu --set full capture of round 1 (profiles/traffic_bytes_per_launch.json), not measured in this run",
+                         "traffic": traffic, "traffic_source": "static: ncu --set full capture committed under profiles/ (traffic_bytes_per_launch.json, taken with the same command in a separate profiler run), not measured in this run",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_eval * B, "avg_launch_ms": avg_kernel_ms,
                          "kernel": "whole evaluation: TransposeIn -> RomNodeOut | DynOut (two streams) -> TransposeOut; "

@@ -205,7 +205,10 @@ int twb_batch_goal_instances_device(twb_batch* b, const double* goals, double* x
  *   jac  [B][nnz]  out (CSR value order of twb_problem_structure)
  *   cost [B]       out, grad [B][n] out (only written when the problem has cost terms)
  *   status [B]     out, bit0: non-finite value produced, bit1: sum of phase durations >= T
- * `stream` is a cudaStream_t (NULL = default stream); the call only enqueues. */
+ * `stream` is a cudaStream_t (NULL = default stream); the call only enqueues.
+ * jac must be 16-byte aligned (cudaMalloc'ed arrays are; an odd-offset view of one is not): TWB_ERR_INVALID otherwise.
+ * A batch serves ONE evaluation / post-processing call at a time: its staging matrices and fork / join events are shared,
+ * so a second call on another stream must be ordered after the first by the caller. */
 int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
                           double* cost, double* grad, int* status,
                           unsigned flags, void* stream);

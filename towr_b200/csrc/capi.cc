@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,7 +83,25 @@ struct twb_batch {
   int e2e_chunk = 512;                            // instances per chunk of twb_batch_eval_host (TWB_E2E_CHUNK)
   std::vector<cudaEvent_t> ev;    // fork/join events of the two-stream pipeline
   int launches_last = 0;
+  std::vector<std::pair<void*, size_t>> scratch;   // device scratch of the post-processing calls, grown on demand, freed with the batch
 };
+
+namespace {
+// slot `slot` of the batch's scratch pool with at least `bytes` bytes (the post-processing entry points synchronise before
+// they return and a batch has one caller at a time, so the slots are free again at the next call)
+cudaError_t ScratchAlloc(twb_batch* b, int slot, void** p, size_t bytes) {
+  if ((int)b->scratch.size() <= slot) b->scratch.resize(slot + 1, {nullptr, 0});
+  auto& s = b->scratch[slot];
+  if (s.second < bytes || !s.first) {
+    cudaFree(s.first); s = {nullptr, 0};
+    cudaError_t e = cudaMalloc(&s.first, std::max<size_t>(bytes, 256));
+    if (e != cudaSuccess) { s.first = nullptr; return e; }
+    s.second = std::max<size_t>(bytes, 256);
+  }
+  *p = s.first;
+  return cudaSuccess;
+}
+}  // namespace
 
 extern "C" {
 
@@ -185,7 +204,7 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   }
   TWB_UP(samples) TWB_UP(dyn) TWB_UP(rom) TWB_UP(groups) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc)
   TWB_UP(base_motion) TWB_UP(cost) TWB_UP(pairs) TWB_UP(coefs) TWB_UP(cta_lists) TWB_UP(dyn_ang_basis)
-  TWB_UP(phase_defs) TWB_UP(phase_polys) TWB_UP(phase_units) TWB_UP(slot_of) TWB_UP(goal_vars)
+  TWB_UP(phase_defs) TWB_UP(phase_polys) TWB_UP(phase_units) TWB_UP(slot_of) TWB_UP(goal_vars) TWB_UP(const_runs) TWB_UP(const_vals)
 #undef TWB_UP
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
@@ -218,6 +237,7 @@ void twb_batch_destroy(twb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   for (void* p : b->owned) cudaFree(p);
+  for (auto& sc : b->scratch) cudaFree(sc.first);
   cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT); cudaFree(b->d_GT);
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
@@ -306,11 +326,11 @@ int twb_batch_sample_trajectory_host(twb_batch* b, const double* x, double dt, d
   if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
   const size_t B = b->B, K = 19 + 13 * (size_t)f.spec.n_ee, n_steps = times.size();
   twb::SplineSample* d_samples = nullptr; int* d_contact = nullptr; double* d_out = nullptr;
-  auto cleanup = [&] { cudaFree(d_samples); cudaFree(d_contact); cudaFree(d_out); };
+  auto cleanup = [] {};   // scratch buffers stay with the batch (twb_batch::scratch) and are reused by the next call
   if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_contact), sizeof(int) * contact.size())) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(double) * B * n_steps * K)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  if ((e = ScratchAlloc(b, 0, reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
+      (e = ScratchAlloc(b, 1, reinterpret_cast<void**>(&d_contact), sizeof(int) * contact.size())) != cudaSuccess ||
+      (e = ScratchAlloc(b, 2, reinterpret_cast<void**>(&d_out), sizeof(double) * B * n_steps * K)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
   cudaStream_t s = b->stream;
   cudaMemcpyAsync(d_samples, samples.data(), sizeof(twb::SplineSample) * samples.size(), cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_contact, contact.data(), sizeof(int) * contact.size(), cudaMemcpyHostToDevice, s);
@@ -335,11 +355,11 @@ int twb_batch_initial_guess_host(twb_batch* b, const double* x, const double* ti
   if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
   const size_t B = b->B;
   twb::SplineSample* d_samples = nullptr; double* d_times = nullptr; double* d_out = nullptr;
-  auto cleanup = [&] { cudaFree(d_samples); cudaFree(d_times); cudaFree(d_out); };
+  auto cleanup = [] {};   // scratch buffers stay with the batch (twb_batch::scratch) and are reused by the next call
   if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_times), sizeof(double) * n_times)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(double) * B * n_times * 49)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  if ((e = ScratchAlloc(b, 0, reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
+      (e = ScratchAlloc(b, 1, reinterpret_cast<void**>(&d_times), sizeof(double) * n_times)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 2, reinterpret_cast<void**>(&d_out), sizeof(double) * B * n_times * 49)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
   cudaStream_t s = b->stream;
   cudaMemcpyAsync(d_samples, samples.data(), sizeof(twb::SplineSample) * samples.size(), cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_times, times, sizeof(double) * n_times, cudaMemcpyHostToDevice, s);
@@ -376,13 +396,13 @@ int twb_batch_footstep_plan_host(twb_batch* b, const double* x, double time_hori
   if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
   const size_t B = b->B, K = 19 + 13 * (size_t)f.spec.n_ee, n_steps = times.size();
   twb::SplineSample* d_samples = nullptr; int* d_contact = nullptr; double* d_traj = nullptr; double* d_out = nullptr; int* d_count = nullptr;
-  auto cleanup = [&] { cudaFree(d_samples); cudaFree(d_contact); cudaFree(d_traj); cudaFree(d_out); cudaFree(d_count); };
+  auto cleanup = [] {};   // scratch buffers stay with the batch (twb_batch::scratch) and are reused by the next call
   if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_contact), sizeof(int) * contact.size())) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_traj), sizeof(double) * B * n_steps * K)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(double) * B * max_states * V)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_count), sizeof(int) * B)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  if ((e = ScratchAlloc(b, 0, reinterpret_cast<void**>(&d_samples), sizeof(twb::SplineSample) * samples.size())) != cudaSuccess ||
+      (e = ScratchAlloc(b, 1, reinterpret_cast<void**>(&d_contact), sizeof(int) * contact.size())) != cudaSuccess ||
+      (e = ScratchAlloc(b, 2, reinterpret_cast<void**>(&d_traj), sizeof(double) * B * n_steps * K)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 3, reinterpret_cast<void**>(&d_out), sizeof(double) * B * max_states * V)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 4, reinterpret_cast<void**>(&d_count), sizeof(int) * B)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
   cudaStream_t s = b->stream;
   cudaMemcpyAsync(d_samples, samples.data(), sizeof(twb::SplineSample) * samples.size(), cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_contact, contact.data(), sizeof(int) * contact.size(), cudaMemcpyHostToDevice, s);
@@ -411,12 +431,12 @@ int twb_batch_nearest_planes_host(twb_batch* b, const double* plan, const int* n
   if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
   const size_t B = b->B, n_ee = b->prob->f.spec.n_ee, n_vert = n_polys > 0 ? (size_t)poly_offsets[n_polys] : 0;
   double* d_plan = nullptr; int* d_count = nullptr; int* d_off = nullptr; double* d_vert = nullptr; int* d_out = nullptr;
-  auto cleanup = [&] { cudaFree(d_plan); cudaFree(d_count); cudaFree(d_off); cudaFree(d_vert); cudaFree(d_out); };
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_plan), sizeof(double) * B * max_states * V)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_count), sizeof(int) * B)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_off), sizeof(int) * (n_polys + 1))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_vert), sizeof(double) * 2 * std::max<size_t>(n_vert, 1))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_out), sizeof(int) * B * max_states * n_ee)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  auto cleanup = [] {};   // scratch buffers stay with the batch (twb_batch::scratch) and are reused by the next call
+  if ((e = ScratchAlloc(b, 0, reinterpret_cast<void**>(&d_plan), sizeof(double) * B * max_states * V)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 1, reinterpret_cast<void**>(&d_count), sizeof(int) * B)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 2, reinterpret_cast<void**>(&d_off), sizeof(int) * (n_polys + 1))) != cudaSuccess ||
+      (e = ScratchAlloc(b, 3, reinterpret_cast<void**>(&d_vert), sizeof(double) * 2 * std::max<size_t>(n_vert, 1))) != cudaSuccess ||
+      (e = ScratchAlloc(b, 4, reinterpret_cast<void**>(&d_out), sizeof(int) * B * max_states * n_ee)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
   cudaStream_t s = b->stream;
   cudaMemcpyAsync(d_plan, plan, sizeof(double) * B * max_states * V, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_count, n_states, sizeof(int) * B, cudaMemcpyHostToDevice, s);
@@ -440,10 +460,10 @@ int twb_batch_linear_equality_host(twb_batch* b, const double* x, int var_set, c
   if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
   const size_t B = b->B;
   double* d_M = nullptr; double* d_g = nullptr;
-  auto cleanup = [&] { cudaFree(d_M); cudaFree(d_g); };
+  auto cleanup = [] {};   // scratch buffers stay with the batch (twb_batch::scratch) and are reused by the next call
   if (!b->d_x && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_x), sizeof(double) * B * f.n)) != cudaSuccess) return CudaFail(e, "cudaMalloc");
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_M), sizeof(double) * (size_t)rows * n_cols)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_g), sizeof(double) * B * rows)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  if ((e = ScratchAlloc(b, 0, reinterpret_cast<void**>(&d_M), sizeof(double) * (size_t)rows * n_cols)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 1, reinterpret_cast<void**>(&d_g), sizeof(double) * B * rows)) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
   cudaStream_t s = b->stream;
   cudaMemcpyAsync(d_M, M, sizeof(double) * (size_t)rows * n_cols, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(b->d_x, x, sizeof(double) * B * f.n, cudaMemcpyHostToDevice, s);
@@ -469,13 +489,13 @@ int twb_batch_soft_constraint_host(twb_batch* b, int constraint_set, const doubl
   if (weights) w.assign(weights, weights + n_rows);
   const size_t B = b->B;
   double *d_b = nullptr, *d_w = nullptr, *d_cost = nullptr, *d_grad = nullptr; int *d_rp = nullptr, *d_ci = nullptr;
-  auto cleanup = [&] { cudaFree(d_b); cudaFree(d_w); cudaFree(d_cost); cudaFree(d_grad); cudaFree(d_rp); cudaFree(d_ci); };
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&d_b), sizeof(double) * std::max(n_rows, 1))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_w), sizeof(double) * std::max(n_rows, 1))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_cost), sizeof(double) * B)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_grad), sizeof(double) * B * f.n)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_rp), sizeof(int) * (f.m + 1))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&d_ci), sizeof(int) * std::max(f.nnz, 1))) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
+  auto cleanup = [] {};   // scratch buffers stay with the batch (twb_batch::scratch) and are reused by the next call
+  if ((e = ScratchAlloc(b, 0, reinterpret_cast<void**>(&d_b), sizeof(double) * std::max(n_rows, 1))) != cudaSuccess ||
+      (e = ScratchAlloc(b, 1, reinterpret_cast<void**>(&d_w), sizeof(double) * std::max(n_rows, 1))) != cudaSuccess ||
+      (e = ScratchAlloc(b, 2, reinterpret_cast<void**>(&d_cost), sizeof(double) * B)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 3, reinterpret_cast<void**>(&d_grad), sizeof(double) * B * f.n)) != cudaSuccess ||
+      (e = ScratchAlloc(b, 4, reinterpret_cast<void**>(&d_rp), sizeof(int) * (f.m + 1))) != cudaSuccess ||
+      (e = ScratchAlloc(b, 5, reinterpret_cast<void**>(&d_ci), sizeof(int) * std::max(f.nnz, 1))) != cudaSuccess) { cleanup(); return CudaFail(e, "cudaMalloc"); }
   cudaStream_t s = b->stream;
   cudaMemcpyAsync(d_b, b_avg.data(), sizeof(double) * n_rows, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_w, w.data(), sizeof(double) * n_rows, cudaMemcpyHostToDevice, s);
@@ -510,6 +530,8 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   if (!b || !x) return Fail(TWB_ERR_INVALID, "null argument");
   if ((flags & TWB_EVAL_G) && !g) return Fail(TWB_ERR_INVALID, "g requested but NULL");
   if ((flags & TWB_EVAL_JAC) && !jac) return Fail(TWB_ERR_INVALID, "jac requested but NULL");
+  if ((flags & TWB_EVAL_JAC) && (reinterpret_cast<uintptr_t>(jac) % 16) != 0)
+    return Fail(TWB_ERR_INVALID, "jac must be 16-byte aligned (the kernels write it with 16-byte stores and TMA bulk copies)");
   cudaError_t e = cudaSetDevice(b->device);
   if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
   const twb::Formulation& f = b->prob->f;

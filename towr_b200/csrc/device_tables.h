@@ -70,6 +70,12 @@ constexpr int kMaxClasses = 4;
 struct OutPair { int32_t off; uint16_t d0, d1; };       // pair: element index of the first half; single / value entry: element index / g row, d0 = state row
 struct alignas(16) OutCoef { double c0, c1; };
 struct OutRange { int32_t first, count; };
+// A run of iterate-independent Jacobian values (state row 0 = the constant 1 on every element: spline-acc and swing rows
+// with fixed durations, ...), whole sectors, at least kConstRunMin elements: not part of any CTA list — a "constant CTA"
+// loads the run's values (the same for every instance) into shared memory with one TMA bulk copy and writes them to the
+// 32 instances of its tile with one cp.async.bulk per instance (SASS UBLKCP.S.G / UBLKCP.G.S), no LSU work at all.
+struct ConstRun { int32_t off, len, src, pad; };   // element offset in the instance's CSR row, elements (multiple of 4), first value in Plan::const_vals
+constexpr int kConstRunMin = 128, kConstRunMax = 2048;   // elements per run piece (1 KB .. 16 KB)
 struct OutList {                        // per alignment class
   OutRange pairs[kMaxClasses];          // whole sectors, two pairs each
   OutRange singles[kMaxClasses];        // single elements (lane = instance)
@@ -216,6 +222,9 @@ struct Plan {
   int gmap_sx, gmap_sy;
   double gmap_res, gmap_px, gmap_py;
   const GoalVar* goal_vars;             // [n] recipe of x0 / bounds per variable
+  int n_const_runs;                     // constant runs (TMA-written; fixed durations, row length a multiple of 4)
+  const ConstRun* const_runs;
+  const double* const_vals;
   // phase-duration optimisation (all null / 0 otherwise)
   int n_phase_units, n_phase_defs;
   const PhaseSplineDef* phase_defs;   // [2 * n_ee]: ee-motion_e at 2e, ee-force_e at 2e + 1

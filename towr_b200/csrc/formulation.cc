@@ -847,6 +847,32 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   std::vector<std::array<std::array<std::vector<Entry>, 2>, kMaxClasses>> lists(n_lists);
   const int NC = (nnz % 4 == 0) ? 1 : (nnz % 2 == 0) ? 2 : 4;
   pl.nc_jac = NC; pl.nc_g = 1;
+  // ---- constant runs (device_tables.h: ConstRun): whole sectors whose elements all multiply the constant-1 state row.
+  // Only with one alignment class (every instance's row starts on a sector) and without PhaseJac overwrites.
+  std::vector<char> is_const_run(nnz, 0);
+  if (NC == 1 && !optimize_timings && TWB_ROMNODE && !TWB_FUSED && EnvInt("TWB_CONST_TMA", 1, 0, 1)) {   // (the constant CTAs live in RomNodeOut's grid)
+    auto constant = [&](int i) {
+      if (elems[i].list < 0) return false;
+      const int kind_rows = elems[i].list < n_dyn_ctas ? pl.dyn_rows : elems[i].list < n_dyn_ctas + n_rom_ctas * rom_lists ? pl.rom_rows : pl.node_rows;
+      return elems[i].d % kind_rows == 0;   // row 0 of a warp's state block
+    };
+    int i = 0;
+    while (i + 3 < nnz) {
+      if (i % 4 != 0 || !(constant(i) && constant(i + 1) && constant(i + 2) && constant(i + 3))) { i += (i % 4) ? (4 - i % 4) : 4; continue; }
+      int j = i;
+      while (j + 3 < nnz && constant(j) && constant(j + 1) && constant(j + 2) && constant(j + 3)) j += 4;
+      if (j - i >= kConstRunMin) {
+        for (int a = i; a < j; a += kConstRunMax) {
+          const int len = std::min(kConstRunMax, j - a);
+          if (len < 4) break;
+          tb.const_runs.push_back(ConstRun{a, len, (int32_t)tb.const_vals.size(), 0});
+          for (int k = a; k < a + len; ++k) { tb.const_vals.push_back(elems[k].c); is_const_run[k] = 1; elems[k].list = -2; }
+        }
+      }
+      i = j;
+    }
+  }
+  pl.n_const_runs = (int)tb.const_runs.size();
   for (int q = 0; q < NC; ++q) {
     const int L = nnz, c = (int)(((long long)q * L) % 4);   // position of the row's first element inside its sector
     std::vector<int> hits(L, 0);
@@ -865,6 +891,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     }
     // self-check: every element of an output-kernel row is written exactly once
     for (int i = 0; i < L; ++i) if (hits[i] != (elems[i].list >= 0 ? 1 : 0)) return fail(TWB_ERR_UNSUPPORTED, "output lists do not cover every element exactly once");
+    for (int i = 0; i < L; ++i) if (is_const_run[i] && hits[i] != 0) return fail(TWB_ERR_UNSUPPORTED, "constant run also written by a list");
   }
   pl.stage_dyn = pl.stage_rom = pl.stage_node = 0;
   auto flush_list = [&](int list) {

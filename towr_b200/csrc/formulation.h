@@ -54,6 +54,8 @@ struct HostTables {
   std::vector<PhaseUnit> phase_units;
   std::vector<int32_t> slot_of;
   std::vector<GoalVar> goal_vars;
+  std::vector<ConstRun> const_runs;
+  std::vector<double> const_vals;
   GoalSetup goal_setup{};
 };
 

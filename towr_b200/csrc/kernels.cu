@@ -834,6 +834,33 @@ __device__ __forceinline__ void StoreValuesTiled(const Plan& P, const double* t,
   ForEachEntry(P.pairs + r.first, P.coefs + r.first, r.count, lane,
                [&](int g_row, int d, double c) { gt_tile[(size_t)g_row * 32 + lane] = t[d * kLD + lane] * c; });
 }
+// Row lengths that are not a multiple of 4 doubles (odd nnz: Biped) give up to four alignment classes, each with its own
+// pair list for the instances j = q (mod nc).  Walking the lists one class after the other leaves most threads idle in the
+// last round of every class (a list is ~1.3 pairs per thread long); here the lists of all classes form ONE item space —
+// item = (class, pair), its 32 / nc instances — so the threads of the CTA stay evenly busy (config 3: 0.42 -> see profiles).
+__device__ __forceinline__ void StorePairsClasses(const Plan& P, const double* t, const OutList* list, double* __restrict__ out, size_t stride, int nc,
+                                                  int tid, int n_threads) {
+  int first[kMaxClasses], end[kMaxClasses + 1];
+  end[0] = 0;
+  for (int q = 0; q < kMaxClasses; ++q) {
+    OutRange r{0, 0};
+    if (q < nc) r = LoadRange(&list->pairs[q]);
+    first[q] = r.first; end[q + 1] = end[q] + r.count;
+  }
+  const int n_items = end[nc];
+  for (int i = tid; i < n_items; i += n_threads) {
+    int q = 0;
+    while (q + 1 < nc && i >= end[q + 1]) ++q;
+    const int k = first[q] + (i - end[q]);
+    int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
+    LoadPair(P.pairs, P.coefs, k, k + 1, &off, &d0, &d1, &c0, &c1);
+    double* o = out + off + (size_t)q * stride;
+    const double* r0 = t + d0 * kLD + q; const double* r1 = t + d1 * kLD + q;
+    const size_t step = (size_t)nc * stride;
+#pragma unroll 8
+    for (int j = 0; j < 32; j += nc) { StoreOut2(o, r0[j] * c0, r1[j] * c1); o += step; }
+  }
+}
 // Jacobian values of a whole CTA (after its barrier): every thread takes pairs of the CTA's list; warp 0 writes the
 // single elements (sectors shared with a neighbouring CTA) with lane = instance.
 __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst, const Stage st) {
@@ -841,8 +868,10 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
   return;
 #endif
   const int nc = P.nc_jac, lane = threadIdx.x & 31;
+  const bool merged = !TWB_TMA && nc > 1 && n_inst == 32;
+  if (merged) StorePairsClasses(P, cta_smem, list, jac_tile, (size_t)P.nnz, nc, threadIdx.x, blockDim.x);
   for (int q = 0; q < nc; ++q) {
-    const OutRange rp = LoadRange(&list->pairs[q]);
+    const OutRange rp = merged ? OutRange{0, 0} : LoadRange(&list->pairs[q]);
     // warp 0 also owns the single elements: their range (and, below, their first 32 entries) is fetched BEFORE the pair
     // loop, so that the two dependent loads are in flight under the warp's pair stores instead of after them
     OutRange rs{0, 0};
@@ -1384,6 +1413,33 @@ __global__ void __launch_bounds__(128) NearestPlaneKernel(const double* __restri
   out[i] = idx;
 }
 
+// ---- constant runs (device_tables.h: ConstRun): the TMA engine copies iterate-independent stretches of the CSR value rows ----
+// CTA = (run, tile): one bulk copy global -> shared of the run's values (mbarrier, complete_tx), then one bulk copy
+// shared -> global per instance of the tile.  No register or LSU traffic for these bytes (6 % of config 2's Jacobian).
+__device__ __forceinline__ void ConstRunBody(const Plan& P, double* __restrict__ jac, int nb, double* smem, int run, int tile) {
+  __shared__ __align__(8) unsigned long long mbar;
+  const ConstRun r = P.const_runs[run];
+  const unsigned bytes = (unsigned)r.len * 8u;
+  const int b0 = tile * 32;
+  if (threadIdx.x == 0) {
+    const unsigned mb = SmemAddr(&mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(SmemAddr(smem)), "l"(P.const_vals + r.src), "r"(bytes), "r"(mb) : "memory");
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+  }
+  __syncthreads();   // the values are in shared memory (written by the async proxy, observed through the mbarrier by thread 0)
+  if (threadIdx.x < 32 && b0 + (int)threadIdx.x < nb) {
+    BulkStore(jac + (size_t)(b0 + threadIdx.x) * P.nnz + r.off, smem, bytes);
+    BulkCommit();
+    BulkWaitAll();
+  }
+}
+
 #if TWB_FUSED
 // One kernel writes a whole tile of rows: blockIdx.y = instance tile, blockIdx.x walks the tile's CTAs in row
 // order — dynamic samples, range-of-motion samples, node groups.
@@ -1436,6 +1492,11 @@ __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const
   asm volatile("griddepcontrol.wait;" ::: "memory");   // XT complete and visible (programmatic dependency on TransposeIn)
 #endif
   const int n_rom_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps;
+  const int n_node_ctas = (P.n_groups + kNodeWarps - 1) / kNodeWarps;
+  if ((int)blockIdx.x >= n_rom_ctas + n_node_ctas) {   // constant runs: TMA only
+    if (flags & 2u) ConstRunBody(P, jac, nb, out_smem, blockIdx.x - n_rom_ctas - n_node_ctas, blockIdx.y);
+    return;
+  }
   if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, st);
 #ifndef TWB_EXP_NONODE   // (timing experiment: node CTAs return at once)
   else NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x - n_rom_ctas, blockIdx.y, st);
@@ -1469,9 +1530,10 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     const int stage_off = (int)(state_bytes / sizeof(double));
     int stage_cap = TWB_TMA_ROM ? std::max(P.stage_rom, P.stage_node) : 0;
     if (state_bytes + (size_t)kRomWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 100 * 1024) stage_cap = 0;   // dense rows (optimised durations): st.global path
-    const size_t smem = state_bytes + (size_t)kRomWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
+    const size_t smem = std::max(state_bytes + (size_t)kRomWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double),
+                                 P.n_const_runs > 0 ? (size_t)kConstRunMax * sizeof(double) : (size_t)0);
     if ((e = cudaFuncSetAttribute(RomNodeOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps;
+    const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps + P.n_const_runs;
     if (n_ctas > 0) {
 #if TWB_PDL
       cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(n_ctas, tiles); cfg.blockDim = dim3(kRomWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;

@@ -424,6 +424,10 @@ class Batch:
         if stream is None:
             stream = torch.cuda.current_stream(x.device)
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+        p = self.problem
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.B * p.n
+        for t, dt, count in ((g, torch.float64, self.B * p.m), (jac, torch.float64, self.B * p.nnz), (cost, torch.float64, self.B),
+                             (grad, torch.float64, self.B * p.n), (status, torch.int32, self.B)):
+            assert t is None or (t.is_cuda and t.dtype == dt and t.is_contiguous() and t.numel() == count), "bad output tensor"
         check(lib.twb_batch_eval_device(self._h, ptr(x), ptr(g), ptr(jac), ptr(cost), ptr(grad), ptr(status),
                                         flags, C.c_void_p(stream.cuda_stream)))
