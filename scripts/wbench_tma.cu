@@ -194,6 +194,51 @@ __global__ void FillTmaGroup(double* out, const PairDesc* __restrict__ descs, in
   if (threadIdx.x == 0) BulkWaitRead<0>();
 }
 
+// 256-bit stores (sm_100: st.global.v4.f64, SASS STG.E.256): thread = whole 32-byte sector (two consecutive pairs of the
+// list), a warp instruction covers 1 KB of one instance's row
+__global__ void FillContigV4(double* out, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += step) asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out + 4 * i), "d"(1.0), "d"(2.0), "d"(3.0), "d"(4.0) : "memory");
+}
+__global__ void FillContigV2(double* out, size_t n2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n2; i += step) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(out + 2 * i), "d"(1.0), "d"(2.0) : "memory");
+}
+template <int kCs>
+__global__ void FillStgV4(double* out, const PairDesc* __restrict__ descs, int row_len, int seg, int seg_lo, int seg_hi, int rows) {
+  extern __shared__ __align__(128) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = seg_lo + blockIdx.x;
+  if (s >= seg_hi) return;
+  double* t = sm;
+  for (int r = warp; r < rows; r += (blockDim.x >> 5)) t[r * 34 + lane] = r + lane;
+  __syncthreads();
+  double* base = out + (size_t)blockIdx.y * 32 * row_len;
+  const int sectors = seg / 4;                     // (the benchmark's segments start on sectors when seg % 4 == 0; else the tail pair is skipped)
+  const PairDesc* dl = descs + (size_t)s * (seg / 2);
+  const int n_items = sectors * 4;                 // (sector, quarter of the tile's instances)
+  for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+    const int q = it / sectors, k = it - q * sectors;
+    const PairDesc p0 = dl[2 * k], p1 = dl[2 * k + 1];
+    double* o = base + p0.off + (size_t)(8 * q) * row_len;
+    const double* r0 = t + p0.d0 * 34 + 8 * q; const double* r1 = t + p0.d1 * 34 + 8 * q;
+    const double* r2 = t + p1.d0 * 34 + 8 * q; const double* r3 = t + p1.d1 * 34 + 8 * q;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
+      const double2 c = *reinterpret_cast<const double2*>(r2 + j), d = *reinterpret_cast<const double2*>(r3 + j);
+      if (kCs) asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o), "d"(a.x * p0.c0), "d"(b.x * p0.c1), "d"(c.x * p1.c0), "d"(d.x * p1.c1) : "memory");
+      else asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o), "d"(a.x * p0.c0), "d"(b.x * p0.c1), "d"(c.x * p1.c0), "d"(d.x * p1.c1) : "memory");
+      o += row_len;
+      if (kCs) asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o), "d"(a.y * p0.c0), "d"(b.y * p0.c1), "d"(c.y * p1.c0), "d"(d.y * p1.c1) : "memory");
+      else asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o), "d"(a.y * p0.c0), "d"(b.y * p0.c1), "d"(c.y * p1.c0), "d"(d.y * p1.c1) : "memory");
+      o += row_len;
+    }
+  }
+}
+
 template <class F>
 float TimeIt(F f, int reps = 10) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -211,7 +256,9 @@ int main(int argc, char** argv) {
   const int tiles = B / 32, rows = 34 * 4, W = 4;
   const bool realistic = argc > 2 ? atoi(argv[2]) != 0 : true;
   ({ float ms = TimeIt([&] { cudaMemsetAsync(out, 0, n * 8); }); printf("cudaMemset: %.1f us  %.0f GB/s\n", ms * 1e3, n * 8 / 1e9 / ms * 1e3); });
-  for (int seg : {88, 176, 338, 730, 1368}) {
+  ({ float ms = TimeIt([&] { FillContigV2<<<148 * 8, 256>>>(out, n / 2); }); printf("contiguous fill st.cs.v2.f64: %.1f us  %.0f GB/s\n", ms * 1e3, n * 8 / 1e9 / ms * 1e3); });
+  ({ float ms = TimeIt([&] { FillContigV4<<<148 * 8, 256>>>(out, n / 4); }); printf("contiguous fill st.v4.f64 (256-bit): %.1f us  %.0f GB/s\n", ms * 1e3, n * 8 / 1e9 / ms * 1e3); });
+  for (int seg : {88, 176, 336, 728, 1368}) {
     const int n_seg = row_len / seg, pairs = seg / 2;
     std::vector<PairDesc> h((size_t)n_seg * pairs);
     for (int sgm = 0; sgm < n_seg; ++sgm) for (int i = 0; i < pairs; ++i)
@@ -233,6 +280,12 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(FillStg, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         float ms = TimeIt([&] { FillStg<<<grid, W * 32, state_bytes>>>(out, d, row_len, seg, rg.lo, rg.hi, rows); });
         printf("  stg %.0f", gb / ms * 1e3);
+        CK(cudaFuncSetAttribute(FillStgV4<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(FillStgV4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ms = TimeIt([&] { FillStgV4<0><<<grid, W * 32, state_bytes>>>(out, d, row_len, seg, rg.lo, rg.hi, rows); });
+        printf("  stg256 %.0f", gb / ms * 1e3);
+        ms = TimeIt([&] { FillStgV4<1><<<grid, W * 32, state_bytes>>>(out, d, row_len, seg, rg.lo, rg.hi, rows); });
+        printf("  stg256.cs %.0f", gb / ms * 1e3);
       }
 #define RUN(MODE, G, NB, HINT, label)                                                                                         \
   {                                                                                                                          \

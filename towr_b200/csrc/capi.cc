@@ -83,6 +83,8 @@ struct twb_batch {
   int e2e_chunk = 512;                            // instances per chunk of twb_batch_eval_host (TWB_E2E_CHUNK)
   std::vector<cudaEvent_t> ev;    // fork/join events of the two-stream pipeline
   int launches_last = 0;
+  cudaAccessPolicyWindow l2_window{};            // XT + GT persisting in the L2 (experiment, TWB_L2_PERSIST=1)
+  bool use_l2_window = false;
   std::vector<std::pair<void*, size_t>> scratch;   // device scratch of the post-processing calls, grown on demand, freed with the batch
 };
 
@@ -211,11 +213,29 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   if (const char* v = std::getenv("TWB_E2E_CHUNK")) b->e2e_chunk = std::max(32, std::atoi(v));
   b->ld = ((size_t)batch_size + 31) & ~(size_t)31;
   const size_t xt_bytes = (size_t)(b->plan.n + 1) * b->ld * sizeof(double);
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_XT), xt_bytes)) != cudaSuccess ||
-      (e = cudaMemset(b->d_XT, 0, xt_bytes)) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&b->d_GT), (size_t)std::max(b->plan.m, 1) * b->ld * sizeof(double))) != cudaSuccess) {
+  // XT and GT live in ONE allocation, so that one L2 access-policy window can cover both staging matrices (TWB_L2_PERSIST=1;
+  // measured, profiles/README.md experiment 39: marking them persisting makes the step SLOWER, 175 instead of 139 us — off)
+  const size_t xt_padded = (xt_bytes + 255) & ~(size_t)255, gt_bytes = (size_t)std::max(b->plan.m, 1) * b->ld * sizeof(double);
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_XT), xt_padded + gt_bytes)) != cudaSuccess ||
+      (e = cudaMemset(b->d_XT, 0, xt_bytes)) != cudaSuccess) {
     twb_batch_destroy(b);
     return CudaFail(e, "state allocation");
+  }
+  b->d_GT = reinterpret_cast<double*>(reinterpret_cast<char*>(b->d_XT) + xt_padded);
+  {
+    const char* v = std::getenv("TWB_L2_PERSIST");
+    cudaDeviceProp prop{};
+    if (v && std::atoi(v) != 0 && cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+      const size_t want = xt_padded + gt_bytes, cap = (size_t)prop.persistingL2CacheMaxSize;
+      size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+      if (cur < std::min(want, cap)) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, cap));
+      b->l2_window.base_ptr = b->d_XT;
+      b->l2_window.num_bytes = std::min(want, (size_t)prop.accessPolicyMaxWindowSize);
+      b->l2_window.hitRatio = want <= cap ? 1.0f : (float)((double)cap / (double)want);
+      b->l2_window.hitProp = cudaAccessPropertyPersisting;
+      b->l2_window.missProp = cudaAccessPropertyNormal;
+      b->use_l2_window = true;
+    }
   }
   if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&b->aux0, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -236,9 +256,10 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
 void twb_batch_destroy(twb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  if (b->use_l2_window) cudaCtxResetPersistingL2Cache();   // lines of XT / GT must not stay pinned in the L2 after the batch is gone
   for (void* p : b->owned) cudaFree(p);
   for (auto& sc : b->scratch) cudaFree(sc.first);
-  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT); cudaFree(b->d_GT);
+  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT);   // (d_GT is part of d_XT's allocation)
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
@@ -538,6 +559,7 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   unsigned kflags = flags & (TWB_EVAL_G | TWB_EVAL_JAC);
   if (f.has_cost && (flags & TWB_EVAL_COST)) kflags |= TWB_EVAL_COST;
   int launches = 0;
+  twb::SetL2Window(b->use_l2_window ? &b->l2_window : nullptr);
   int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
                            kflags, static_cast<cudaStream_t>(stream), b->aux0, b->aux1, b->ev.data(), &launches);
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
@@ -577,6 +599,7 @@ int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac, d
   unsigned kflags = flags & (TWB_EVAL_G | TWB_EVAL_JAC);
   if (has_cost) kflags |= TWB_EVAL_COST;
   int launches = 0;
+  twb::SetL2Window(b->use_l2_window ? &b->l2_window : nullptr);
   for (size_t c = 0; c < n_chunks; ++c) {
     const size_t off = c * chunk, nb = std::min(chunk, B - off), tile0 = off / 32;
     if ((e = cudaMemcpyAsync(b->d_x + off * f.n, x + off * f.n, sizeof(double) * nb * f.n, cudaMemcpyHostToDevice, b->s_in)) != cudaSuccess)

@@ -38,6 +38,11 @@
 namespace twb {
 void (*g_after_launch)(const char* label, cudaStream_t stream) = nullptr;   // profiling hook (capi.cc, TWB_PROFILE=1)
 #define TWB_MARK(label, stream) do { if (g_after_launch) g_after_launch(label, stream); } while (0)
+// L2 access-policy window of the evaluation kernels (capi.cc sets it per call): the two staging matrices XT / GT are marked
+// persisting, so that the 524 MB of streaming output per step cannot push them out of the L2 before their readers run
+// (ncu, round 2: 38 MB of XT were re-fetched from HBM by the output kernels and all 29 MB of GT by TransposeOut).
+thread_local const cudaAccessPolicyWindow* t_l2_window = nullptr;
+void SetL2Window(const cudaAccessPolicyWindow* w) { t_l2_window = w; }
 namespace {
 
 #ifndef TWB_TOUT_LD
@@ -67,6 +72,21 @@ namespace {
 #ifndef TWB_TMA
 #define TWB_TMA 0        // 1: the Jacobian values of a CTA list leave the SM as cp.async.bulk.global.shared::cta copies of contiguous row segments assembled in shared memory; 0 (ships): 16-byte st.global.cs from the pair loop.  Measured (profiles/README.md, round 2): parity green, but 192 us per step instead of 139 us on config 2 — the extra pass through shared memory costs more than the better DRAM pattern gains
 #endif
+#ifndef TWB_CONST_WAIT_ALL
+#define TWB_CONST_WAIT_ALL 0
+#endif
+#ifndef TWB_ST_HINT
+#define TWB_ST_HINT 0    // cache operator of the Jacobian-value stores: 0 .cs (evict-first), 1 default (.wb), 2 .wt
+#endif
+#ifndef TWB_XT_EVICT_LAST
+#define TWB_XT_EVICT_LAST 0   // 1: TransposeIn writes XT with an L2 evict_last policy (experiment)
+#endif
+#ifndef TWB_ST256
+#define TWB_ST256 0     // 1: thread = whole sector (two consecutive pairs of the list), 256-bit stores, items of 8 instances
+#endif
+#ifndef TWB_MERGE_CLASSES
+#define TWB_MERGE_CLASSES 0   // 1: the pair lists of all alignment classes (odd row length) as one item space (StorePairsClasses); measured slower on config 3 (126 vs 113 us)
+#endif
 #ifndef TWB_TMA_DYN
 #define TWB_TMA_DYN TWB_TMA   // per-kernel switches of the TMA store path (tuning)
 #endif
@@ -84,9 +104,19 @@ constexpr int kLD = 34;                      // leading dimension of a state blo
 // output stores: streaming (evict-first) — the values are consumed by the host / a solver, not by these kernels
 __device__ __forceinline__ void StoreOut(double* p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void StoreOut2(double* p, double a, double b) {
+#if TWB_ST_HINT == 1
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+#elif TWB_ST_HINT == 2
+  asm volatile("st.global.wt.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+#else
   asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+#endif
 }
 
+// 256-bit store (sm_100: SASS STG.E.256): a thread writes a whole 32-byte sector
+__device__ __forceinline__ void StoreOut4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 // column `b` of a row-major [rows][ld] matrix: element r lives at p[r * ld]
 struct Col {
   double* p;
@@ -635,7 +665,15 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
 #pragma unroll
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int i = i0 + r, b = b0 + threadIdx.x;
+#if TWB_XT_EVICT_LAST
+    if (b < nb && i < n) {
+      unsigned long long pol;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(dst + (size_t)i * 32 + threadIdx.x), "d"(tile[threadIdx.x][r]), "l"(pol) : "memory");
+    }
+#else
     if (b < nb && i < n) dst[(size_t)i * 32 + threadIdx.x] = tile[threadIdx.x][r];
+#endif
   }
 }
 
@@ -698,6 +736,31 @@ __device__ __forceinline__ void LoadPair(const OutPair* __restrict__ pairs, cons
 __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
                                            int n_pairs, double* __restrict__ out, size_t stride, int j0, int jstep, int n_inst,
                                            int tid, int n_threads) {
+#if TWB_ST256
+  if (n_inst == 32 && jstep == 1 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 && (stride & 3) == 0) {
+    // thread = whole 32-byte sector (the list holds two consecutive pairs per sector), item = (sector, quarter of the tile's
+    // instances): one 256-bit store per instance, a warp instruction covers 1 KB of the instance's row
+    const int n_sec = n_pairs >> 1, n_items = 4 * n_sec;
+    for (int i = tid; i < n_items; i += n_threads) {
+      const int qd = i / n_sec, k = i - qd * n_sec;
+      int off = 0, d0 = 0, d1 = 0, off2 = 0, d2 = 0, d3 = 0; double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+      LoadPair(pairs, coefs, 2 * k, n_pairs, &off, &d0, &d1, &c0, &c1);
+      LoadPair(pairs, coefs, 2 * k + 1, n_pairs, &off2, &d2, &d3, &c2, &c3);
+      const int jb = 8 * qd;
+      double* o = out + off + (size_t)jb * stride;
+      const double* r0 = t + d0 * kLD + jb; const double* r1 = t + d1 * kLD + jb;
+      const double* r2 = t + d2 * kLD + jb; const double* r3 = t + d3 * kLD + jb;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
+        const double2 c = *reinterpret_cast<const double2*>(r2 + j), d = *reinterpret_cast<const double2*>(r3 + j);
+        StoreOut4(o, a.x * c0, b.x * c1, c.x * c2, d.x * c3); o += stride;
+        StoreOut4(o, a.y * c0, b.y * c1, c.y * c2, d.y * c3); o += stride;
+      }
+    }
+    return;
+  }
+#endif
   if (n_inst == 32 && jstep == 1) {
     // Work items are (pair, half of the tile's instances): twice as many items as pairs keep the threads of a CTA
     // evenly busy when a list is only 1 - 2 pairs per thread long.  Items 0 .. n_pairs-1 are the first 16 instances,
@@ -834,11 +897,12 @@ __device__ __forceinline__ void StoreValuesTiled(const Plan& P, const double* t,
   ForEachEntry(P.pairs + r.first, P.coefs + r.first, r.count, lane,
                [&](int g_row, int d, double c) { gt_tile[(size_t)g_row * 32 + lane] = t[d * kLD + lane] * c; });
 }
+#if TWB_MERGE_CLASSES
 // Row lengths that are not a multiple of 4 doubles (odd nnz: Biped) give up to four alignment classes, each with its own
 // pair list for the instances j = q (mod nc).  Walking the lists one class after the other leaves most threads idle in the
 // last round of every class (a list is ~1.3 pairs per thread long); here the lists of all classes form ONE item space —
 // item = (class, pair), its 32 / nc instances — so the threads of the CTA stay evenly busy (config 3: 0.42 -> see profiles).
-__device__ __forceinline__ void StorePairsClasses(const Plan& P, const double* t, const OutList* list, double* __restrict__ out, size_t stride, int nc,
+__device__ __noinline__ void StorePairsClasses(const Plan& P, const double* t, const OutList* list, double* __restrict__ out, size_t stride, int nc,
                                                   int tid, int n_threads) {
   int first[kMaxClasses], end[kMaxClasses + 1];
   end[0] = 0;
@@ -861,6 +925,7 @@ __device__ __forceinline__ void StorePairsClasses(const Plan& P, const double* t
     for (int j = 0; j < 32; j += nc) { StoreOut2(o, r0[j] * c0, r1[j] * c1); o += step; }
   }
 }
+#endif
 // Jacobian values of a whole CTA (after its barrier): every thread takes pairs of the CTA's list; warp 0 writes the
 // single elements (sectors shared with a neighbouring CTA) with lane = instance.
 __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst, const Stage st) {
@@ -868,8 +933,12 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
   return;
 #endif
   const int nc = P.nc_jac, lane = threadIdx.x & 31;
+#if TWB_MERGE_CLASSES
   const bool merged = !TWB_TMA && nc > 1 && n_inst == 32;
   if (merged) StorePairsClasses(P, cta_smem, list, jac_tile, (size_t)P.nnz, nc, threadIdx.x, blockDim.x);
+#else
+  const bool merged = false;
+#endif
   for (int q = 0; q < nc; ++q) {
     const OutRange rp = merged ? OutRange{0, 0} : LoadRange(&list->pairs[q]);
     // warp 0 also owns the single elements: their range (and, below, their first 32 entries) is fetched BEFORE the pair
@@ -1416,9 +1485,9 @@ __global__ void __launch_bounds__(128) NearestPlaneKernel(const double* __restri
 // ---- constant runs (device_tables.h: ConstRun): the TMA engine copies iterate-independent stretches of the CSR value rows ----
 // CTA = (run, tile): one bulk copy global -> shared of the run's values (mbarrier, complete_tx), then one bulk copy
 // shared -> global per instance of the tile.  No register or LSU traffic for these bytes (6 % of config 2's Jacobian).
-__device__ __forceinline__ void ConstRunBody(const Plan& P, double* __restrict__ jac, int nb, double* smem, int run, int tile) {
+__device__ __noinline__ void ConstRunBody(const ConstRun* __restrict__ runs, const double* __restrict__ vals, int nnz, double* __restrict__ jac, int nb, double* smem, int run, int tile) {
   __shared__ __align__(8) unsigned long long mbar;
-  const ConstRun r = P.const_runs[run];
+  const ConstRun r = runs[run];
   const unsigned bytes = (unsigned)r.len * 8u;
   const int b0 = tile * 32;
   if (threadIdx.x == 0) {
@@ -1427,16 +1496,25 @@ __device__ __forceinline__ void ConstRunBody(const Plan& P, double* __restrict__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(SmemAddr(smem)), "l"(P.const_vals + r.src), "r"(bytes), "r"(mb) : "memory");
+                 ::"r"(SmemAddr(smem)), "l"(vals + r.src), "r"(bytes), "r"(mb) : "memory");
     unsigned done = 0;
     while (!done)
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
   }
   __syncthreads();   // the values are in shared memory (written by the async proxy, observed through the mbarrier by thread 0)
   if (threadIdx.x < 32 && b0 + (int)threadIdx.x < nb) {
-    BulkStore(jac + (size_t)(b0 + threadIdx.x) * P.nnz + r.off, smem, bytes);
+    // evict-first like the st.global.cs of the pair loop: the values are consumed by the host / a solver, they must not push
+    // XT, GT and the lists out of the L2
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(jac + (size_t)(b0 + threadIdx.x) * nnz + r.off), "r"(SmemAddr(smem)), "r"(bytes), "l"(pol) : "memory");
     BulkCommit();
+#if TWB_CONST_WAIT_ALL
     BulkWaitAll();
+#else
+    BulkWaitRead<0>();   // the CTA may retire once the engine has read the staging row (the writes complete before the grid does)
+#endif
   }
 }
 
@@ -1494,7 +1572,7 @@ __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const
   const int n_rom_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps;
   const int n_node_ctas = (P.n_groups + kNodeWarps - 1) / kNodeWarps;
   if ((int)blockIdx.x >= n_rom_ctas + n_node_ctas) {   // constant runs: TMA only
-    if (flags & 2u) ConstRunBody(P, jac, nb, out_smem, blockIdx.x - n_rom_ctas - n_node_ctas, blockIdx.y);
+    if (flags & 2u) ConstRunBody(P.const_runs, P.const_vals, P.nnz, jac, nb, out_smem, blockIdx.x - n_rom_ctas - n_node_ctas, blockIdx.y);
     return;
   }
   if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, st);
@@ -1507,6 +1585,17 @@ __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const
 }
 #endif
 #endif
+
+// kernel launch with the optional attributes of this pipeline: programmatic dependent launch, L2 access-policy window
+template <class... KArgs, class... Args>
+cudaError_t LaunchK(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2]; unsigned na = 0;
+  if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  if (t_l2_window) { attr[na].id = cudaLaunchAttributeAccessPolicyWindow; attr[na].val.accessPolicyWindow = *t_l2_window; ++na; }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // s: caller's stream (after TransposeIn); a0, a1: auxiliary streams already waiting on the transposition
 template <int kNEE, bool kPhase>
@@ -1535,14 +1624,8 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     if ((e = cudaFuncSetAttribute(RomNodeOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps + P.n_const_runs;
     if (n_ctas > 0) {
-#if TWB_PDL
-      cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(n_ctas, tiles); cfg.blockDim = dim3(kRomWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-      cudaLaunchAttribute attr{}; attr.id = cudaLaunchAttributeProgrammaticStreamSerialization; attr.val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = &attr; cfg.numAttrs = 1;
-      if ((e = cudaLaunchKernelEx(&cfg, RomNodeOut<kNEE, kPhase>, P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, stage_off, stage_cap)) != cudaSuccess) return e;
-#else
-      RomNodeOut<kNEE, kPhase><<<dim3(n_ctas, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, stage_off, stage_cap);
-#endif
+      if ((e = LaunchK(RomNodeOut<kNEE, kPhase>, dim3(n_ctas, tiles), dim3(kRomWarps * 32), smem, s, TWB_PDL != 0, P, XT, GT, jac, status, terrain_ids,
+                       default_terrain, nb, flags, stage_off, stage_cap)) != cudaSuccess) return e;
       ++*count; TWB_MARK("RomNodeOut", s);
     }
   }
@@ -1553,7 +1636,8 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     if (state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 200 * 1024) stage_cap = 0;
     const size_t smem = state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
     if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags, stage_off, stage_cap);
+    if ((e = LaunchK(DynOut<kNEE, kPhase>, dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), dim3(kDynWarps * 32), smem, a0, false, P, XT, GT, jac, status, nb, flags,
+                     stage_off, stage_cap)) != cudaSuccess) return e;
     ++*count; TWB_MARK("DynOut", a0);
   }
   return cudaSuccess;
@@ -1769,7 +1853,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
   const unsigned out_flags = flags & 3u;
   const bool want_cost = (flags & 4u) && P.n_cost > 0;
   TWB_MARK("begin", s);
-  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, status, P.n, nb); ++count; TWB_MARK("TransposeIn", s);
+  LaunchK(TransposeIn, dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s, false, x, XT, status, P.n, nb); ++count; TWB_MARK("TransposeIn", s);
   const bool fork = !serial && (want_cost || (!TWB_FUSED && out_flags));
   if (fork) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
@@ -1803,7 +1887,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
     }
     ++count; TWB_MARK("PhaseJac", s);
   }
-  if (out_flags & 1u) { TransposeOut<<<dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s>>>(GT, g, P.m, nb, XT, P.n); ++count; TWB_MARK("TransposeOut", s); }
+  if (out_flags & 1u) { LaunchK(TransposeOut, dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s, false, (const double*)GT, g, P.m, nb, XT, P.n); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
   return (int)cudaGetLastError();
 }

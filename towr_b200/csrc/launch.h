@@ -40,6 +40,8 @@ int LaunchSoftConstraint(const Plan& P, const double* g, const double* jac, cons
 // x0 / variable bounds of `nb` goal-randomised instances (goals[b][6] = final base position, final base Euler angles)
 int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, const int* terrain_ids, int default_terrain, double* x0, double* lo,
                         double* up, int nb, cudaStream_t s);
+// L2 access-policy window applied to the evaluation kernels launched by this thread (null: none)
+void SetL2Window(const cudaAccessPolicyWindow* w);
 // number of output kernels one evaluation launches for this plan
 int OutKernelsPerEval(const Plan& P);
 int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,
