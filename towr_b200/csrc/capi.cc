@@ -206,7 +206,7 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   }
   TWB_UP(samples) TWB_UP(dyn) TWB_UP(rom) TWB_UP(groups) TWB_UP(terr) TWB_UP(force) TWB_UP(swing) TWB_UP(acc)
   TWB_UP(base_motion) TWB_UP(cost) TWB_UP(pairs) TWB_UP(coefs) TWB_UP(cta_lists) TWB_UP(dyn_ang_basis)
-  TWB_UP(phase_defs) TWB_UP(phase_polys) TWB_UP(phase_units) TWB_UP(slot_of) TWB_UP(goal_vars) TWB_UP(const_runs) TWB_UP(const_vals)
+  TWB_UP(phase_defs) TWB_UP(phase_polys) TWB_UP(phase_units) TWB_UP(exts) TWB_UP(goal_vars) TWB_UP(const_runs) TWB_UP(const_vals)
 #undef TWB_UP
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
@@ -539,7 +539,7 @@ int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   const twb::Plan& p = b->plan;
   const bool want_cost = b->prob->f.has_cost && (flags & TWB_EVAL_COST);
   int n = 1;   // TransposeIn
-  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += twb::OutKernelsPerEval(p);   // DynOut + RomNodeOut (or RomOut, NodeOut)
+  if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += twb::OutKernelsPerEval(p, flags);   // DynOut [+ DynTailOut] + RomNodeOut (or RomOut, NodeOut)
   if ((flags & (TWB_EVAL_G | TWB_EVAL_JAC)) && p.n_phase_units > 0) n += 1;   // PhaseJac
   if (flags & TWB_EVAL_G) n += 1;   // TransposeOut
   if (want_cost) n += 1;

@@ -39,16 +39,15 @@ struct PhaseSplineDef {
   int32_t sched0, n_phases;   // x index of the foot's first duration variable; number of phases (variables: n_phases - 1)
   double t_total;
 };
-// Work item of the PhaseJac kernel: the Jacobian entries of one constraint sample w.r.t. the ee-motion /
-// ee-force node variables (active polynomial only — everything else stays at the zero the output kernels
-// wrote) and w.r.t. the phase durations.
-enum PhaseUnitKind : int32_t { kPhaseDyn = 0, kPhaseRom = 1, kPhaseTotal = 2 };
+// Work item of the PhaseJac kernel: the TotalDurationConstraint rows (total_duration_constraint.cc:36-72) — value, the
+// constant Jacobian entries and status bit 1.  (The PhaseSpline entries of the dynamic and range-of-motion rows are
+// "phase elements" of the output lists, see PhaseExt below.)
+enum PhaseUnitKind : int32_t { kPhaseTotal = 2 };
 struct PhaseUnit {
   int32_t kind;
-  int32_t row0;               // dynamic: first of the sample's 6 rows; total duration: unused
-  int32_t sample_lin, sample_ang;   // fixed-duration samples of the base splines (Plan::samples)
-  int32_t rows[kMaxEE];       // range of motion: first of the foot's 3 rows; total duration: the foot's row
-  double t;                   // global sample time
+  int32_t pad;
+  int32_t rows[kMaxEE];       // the foot's constraint row
+  int32_t slot0[kMaxEE];      // CSR slot of the row's first entry (its entries are the foot's duration columns, ascending)
 };
 
 // ---- output lists -------------------------------------------------------------
@@ -67,6 +66,35 @@ struct PhaseUnit {
 // list exists per alignment class q = instance mod n_classes (n_classes = 1 when the row length is a multiple of 4).
 // The constraint values of a unit go, lane = instance, into the instance-tiled staging matrix GT.
 constexpr int kMaxClasses = 4;
+// ---- phase elements (optimised phase durations) ----------------------------------------------------------------------
+// With PhaseSplines a constraint sample's row is structurally dense in ALL node variables of the foot's set
+// (phase_spline.cc:45-51) and in the foot's duration variables, but which of those entries are non-zero depends on the
+// polynomial the sample falls into — on the iterate.  Such an element is written by the same CTA-wide pair loop as every
+// other element (coalesced, whole sectors).  The compute phase leaves, for every PhaseSpline of the sample, an "info block"
+// of kInfoRows state rows:
+//   +0   32-bit integers: [0..31] active polynomial P per instance | [32], [33] min / max of P over the tile
+//        | [34..65] current phase per instance | [66], [67] its min / max
+//   +1   Z, a row of zeros
+//   +2.. WINDOW form (P differs by at most 2 over the tile — the normal case): the weight of node pmin + s, s = 0..3, for
+//        node derivative 0 / 1 in row +2 + 2 s + deriv:  B[0][deriv] where P == node, B[1][deriv] where P == node - 1, else 0
+//        (NodeSpline::FillJacobianWrtNodes, node_spline.cc:85-112).  An element of node a then is, for EVERY instance of the
+//        tile, out = (state[d] * c) * state[w], w = the row of node a (a shared stance position: the sum of the rows of a and
+//        a + 1), or zero when a is outside the window — no per-instance selection in the store loop.
+//        TABLE form (wider spread): Z B1[0] B0[0] Z B1[1] B0[1] Z B1[0] B0[0]+B1[0] B0[0] Z from +1 on, walked per instance
+//        with the clamped index P - a + 2.
+// Duration columns (PhaseDurations::GetJacobianOfPos, phase_durations.cc:122-154): column ph is U (state rows d ..) where
+// ph < current phase, V where ph == current phase, else 0.  Rows: U | X.  Window form (current phase differs by less than
+// `dwin` over the tile): X holds the finished columns cmin, cmin + 1, .. (row d + v_off (1 + ph - cmin)); columns before cmin
+// are U, columns after cmax zero, for every instance.  Otherwise X starts with V and the store loop selects per instance.
+// One 32-bit word per element, parallel to the pair / single entries: kind (bits 0-1), deriv (bit 2), shared (bit 3),
+// a or ph (bits 8-15), first row of the info block in the CTA's shared memory (bits 16-31).
+enum PhaseElemKind : uint32_t { kElemPlain = 0, kElemNode = 1, kElemDuration = 2 };
+struct PhaseExt { uint32_t e0, e1; };
+constexpr int kInfoRows = 12;
+constexpr int kDynDurWin = 3, kRomDurWin = 2;   // duration columns finished per instance (window form) in DynTailOut / RomBody
+// state rows of one foot in the DynTailOut kernel: 0: 1 | 1..3: f_e | 4..6: c - p_e | 7..18: info block of ee-motion_e |
+// 19..30: info block of ee-force_e | 31..36: U | 37..54: X   (duration columns of the sample's 6 rows)
+constexpr int kTailRows = 7 + 2 * kInfoRows + 6 + 6 * kDynDurWin;
 struct OutPair { int32_t off; uint16_t d0, d1; };       // pair: element index of the first half; single / value entry: element index / g row, d0 = state row
 struct alignas(16) OutCoef { double c0, c1; };
 struct OutRange { int32_t first, count; };
@@ -79,6 +107,7 @@ constexpr int kConstRunMin = 128, kConstRunMax = 2048;   // elements per run pie
 struct OutList {                        // per alignment class
   OutRange pairs[kMaxClasses];          // whole sectors, two pairs each
   OutRange singles[kMaxClasses];        // single elements (lane = instance)
+  OutRange phase[kMaxClasses];          // whole sectors that hold at least one phase element (same layout as `pairs`, with Plan::exts)
   // TMA store path: when the pairs of a class form ONE contiguous run of the row (pair i covers elements run_off + 2i,
   // run_off + 2i + 1 — the normal case: a CTA owns adjacent CSR rows), the CTA assembles the run in shared memory in
   // output order and writes it with one cp.async.bulk per instance; -1: not contiguous, 16-byte st.global path
@@ -89,8 +118,12 @@ struct OutList {                        // per alignment class
 #ifndef TWB_ROM_ALLFEET
 #define TWB_ROM_ALLFEET 0
 #endif
-#define RomBuffer(e) (TWB_ROM_ALLFEET ? 12 * (e) : 12 * ((e) & 1))            /* first row of foot e's buffer, relative to row 10 */
-#define RomBlockRows(n_ee) (10 + 12 * (TWB_ROM_ALLFEET ? (n_ee) : 2))
+// With optimised phase durations a foot's buffer is D_e (9) | info block of its PhaseSpline (kInfoRows) | U (3) | X (3 kRomDurWin).
+#define RomBufRows(phase) ((phase) ? 9 + kInfoRows + 3 + 3 * kRomDurWin : 12)
+#define RomBufferP(e, phase) (TWB_ROM_ALLFEET ? RomBufRows(phase) * (e) : RomBufRows(phase) * ((e) & 1))   /* first row of foot e's buffer, relative to row 10 */
+#define RomBlockRowsP(n_ee, phase) (10 + RomBufRows(phase) * (TWB_ROM_ALLFEET ? (n_ee) : 2))
+#define RomBuffer(e) RomBufferP(e, false)
+#define RomBlockRows(n_ee) RomBlockRowsP(n_ee, false)
 #define RomListsPerCta(n_ee) (TWB_ROM_ALLFEET ? 1 : (n_ee))
 
 // warps per CTA of the output kernels = consecutive units whose output ranges are chained through carry rows.
@@ -193,6 +226,7 @@ struct Plan {
   int node_rows, dyn_rows, rom_rows;   // state rows of one unit's block: node groups (largest), dynamic samples, range-of-motion samples
   int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz); nc_g = 1 (constraint values go through GT)
   int dyn_list0, rom_list0, node_list0;   // first entry of cta_lists of the dynamic CTAs, (rom CTA, foot) pairs, node CTAs
+  int tail_list0;                         // optimised durations: list of dynamic sample k's PhaseSpline columns (DynTailOut) = tail_list0 + k
   int stage_dyn, stage_rom, stage_node;   // longest contiguous run (in doubles, even) of a dynamic / range-of-motion / node list: staging row of the TMA store path
   int rom_row0[kMaxEE];                   // first constraint row of foot e's range-of-motion set (sample k owns rows rom_row0[e] + 3k ..+2)
   // robot
@@ -214,6 +248,7 @@ struct Plan {
   const OutPair* pairs;
   const OutCoef* coefs;
   const OutList* cta_lists;
+  const PhaseExt* exts;                 // parallel to pairs / coefs (optimised durations only, else null)
   // height grid of the TWB_GRID_CSV terrain (per batch; null: heights 0)
   const double* grid;
   int grid_rows, grid_cols;
@@ -230,7 +265,6 @@ struct Plan {
   const PhaseSplineDef* phase_defs;   // [2 * n_ee]: ee-motion_e at 2e, ee-force_e at 2e + 1
   const PhasePoly* phase_polys;
   const PhaseUnit* phase_units;
-  const int32_t* slot_of;             // [m][n]: CSR slot of (row, column) or -1
 };
 
 }  // namespace twb

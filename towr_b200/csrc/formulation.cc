@@ -181,7 +181,13 @@ int EnvInt(const char* name, int def, int lo, int hi) {
   return std::max(lo, std::min(hi, std::atoi(v)));
 }
 
-struct Emit { int row, col; uint32_t a; double c0; };   // a: local state row of the owning unit (0 = the constant 1)
+// a: local state row of the owning unit (0 = the constant 1); ext: phase-element word (device_tables.h: PhaseExt) with the
+// info row local to the unit as well; tail >= 0: element of dynamic sample `tail` written by the DynTailOut kernel (a and
+// the info row are then rows of that kernel's CTA)
+struct Emit { int row, col; uint32_t a; double c0; uint32_t ext = 0; int tail = -1; };
+uint32_t PackExt(uint32_t kind, int deriv, bool shared, int a_or_ph, uint32_t info_row) {
+  return kind | ((uint32_t)deriv << 2) | ((uint32_t)(shared ? 1 : 0) << 3) | ((uint32_t)a_or_ph << 8) | (info_row << 16);
+}
 
 // Who computes a constraint row: a dynamic sample, a range-of-motion sample (all feet) or a node unit.
 enum OwnerKind { kOwnDyn, kOwnRom, kOwnNode, kOwnPhase };   // kOwnPhase: rows written by the PhaseJac kernel (total duration)
@@ -463,17 +469,33 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
         tb.phase_defs.push_back(def);
       }
   }
-  // PhaseSpline pattern (phase_spline.cc:45-51): every variable of the set is structurally non-zero in the row of its dimension
+  // PhaseSpline pattern (phase_spline.cc:45-51): every variable of the set is structurally non-zero in the row of its dimension.
+  // Per variable: column, dimension, node derivative, first node holding it and whether the next node shares it (stance
+  // position of a phase-based ee-motion set) — what decides, per instance, which Hermite basis value multiplies it.
+  struct VarInfo { int col = -1, dim = -1, deriv = -1, a = -1, count = 0; bool ok = true; };
   auto all_vars = [&](const NodeSet& ns) {
-    std::vector<std::pair<int, int>> v(ns.n_vars, {-1, -1});   // (column, dim)
-    for (int nd = 0; nd < ns.n_nodes; ++nd) for (int k = 0; k < 6; ++k) { int var = ns.var[nd][k]; if (var >= 0) v[var] = {ns.offset + var, k % 3}; }
+    std::vector<VarInfo> v(ns.n_vars);
+    for (int nd = 0; nd < ns.n_nodes; ++nd) for (int k = 0; k < 6; ++k) {
+      const int var = ns.var[nd][k];
+      if (var < 0) continue;
+      VarInfo& vi = v[var];
+      if (vi.count == 0) { vi.col = ns.offset + var; vi.dim = k % 3; vi.deriv = k / 3; vi.a = nd; vi.count = 1; }
+      else { if (vi.dim != k % 3 || vi.deriv != k / 3 || nd != vi.a + vi.count || vi.count >= 2) vi.ok = false; vi.count++; }
+    }
     return v;
   };
+  if (optimize_timings)
+    for (int e = 0; e < n_ee; ++e) for (int kind = 0; kind < 2; ++kind) {
+      const NodeSet& ns = kind == 0 ? motion(e) : force(e);
+      if (ns.n_nodes > 255) return fail(TWB_ERR_UNSUPPORTED, "more than 255 nodes in a phase-based set");
+      for (auto& vi : all_vars(ns)) if (!vi.ok || vi.count < 1 || (vi.count == 2 && vi.deriv != kPos)) return fail(TWB_ERR_UNSUPPORTED, "node variable shared by more than two adjacent nodes");
+    }
   Plan& pl = tb.plan;
   const uint32_t S_ONE = 0;      // local row 0 of every unit's state block is the constant 1
 
   std::vector<Emit> em;
   auto emit1 = [&](int row, int col, uint32_t a, double c) { em.push_back({row, col, a, c}); };
+  auto emit_phase = [&](int row, int col, uint32_t a, double c, uint32_t ext, int tail) { Emit e{row, col, a, c}; e.ext = ext; e.tail = tail; em.push_back(e); };
   std::vector<RowOwner> owner;         // per constraint row
   std::vector<NodeUnitRef> node_units; // node-wise units in row order
   int set_counter = 0;
@@ -518,10 +540,6 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           tb.samples.push_back(MakeSample(sp_ang, t, zero_slot));
           for (int e = 0; e < n_ee; ++e) tb.samples.push_back(foot_sample(e, 0, t));
           for (int e = 0; e < n_ee; ++e) tb.samples.push_back(foot_sample(e, 1, t));
-          if (optimize_timings) {
-            PhaseUnit pu{}; pu.kind = kPhaseDyn; pu.row0 = row; pu.sample_lin = du.sample0; pu.sample_ang = du.sample0 + 1; pu.t = t;
-            tb.phase_units.push_back(pu);
-          }
           int p; double tl;
           // base-lin: angular rows = -sum_e [f_e]x dc ; linear rows = m * d(acc)
           Locate(sp_lin, t, &p, &tl);
@@ -546,14 +564,25 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             for (int q = 0; q < 4; ++q) tb.dyn_ang_basis.push_back(ba[3 * q].val);
           }
           for (int e = 0; e < n_ee && optimize_timings; ++e) {
-            // structural entries only (value 0 from the output kernel); the PhaseJac kernel overwrites the active ones
-            for (auto& cv : all_vars(motion(e))) for (int i = 0; i < 3; ++i) if (i != cv.second) emit1(row + i, cv.first, S_ONE, 0.0);
-            for (auto& cv : all_vars(force(e))) {
-              for (int i = 0; i < 3; ++i) if (i != cv.second) emit1(row + i, cv.first, S_ONE, 0.0);
-              emit1(row + 3 + cv.second, cv.first, S_ONE, 0.0);
+            // PhaseSpline columns (dynamic_constraint.cc:91-113, single_rigid_body_dynamics.cc:167-192): phase elements written by
+            // the DynTailOut kernel, CTA = sample, warp = foot; rows of the foot's state block (kTailRows):
+            // 0: 1 | 1..3: f_e | 4..6: c - p_e | 7..18: info block of ee-motion | 19..30: info block of ee-force | 31..36: U | 37..: X
+            const uint32_t tb0 = (uint32_t)e * kTailRows, F = tb0 + 1, Rr = tb0 + 4, info_mo = tb0 + 7, info_fo = tb0 + 7 + kInfoRows, cur = info_mo, U0 = tb0 + 7 + 2 * kInfoRows;
+            for (auto& vi : all_vars(motion(e)))   // angular rows: [f_e]x d(p_e)
+              for (int i = 0; i < 3; ++i) if (i != vi.dim) {
+                int comp; double sg; CrossEntry(i, vi.dim, &comp, &sg);
+                emit_phase(row + i, vi.col, F + comp, sg, PackExt(kElemNode, vi.deriv, vi.count == 2, vi.a, info_mo), k);
+              }
+            for (auto& vi : all_vars(force(e))) {   // angular rows: [c - p_e]x d(f_e); linear rows: -d(f_e)
+              for (int i = 0; i < 3; ++i) if (i != vi.dim) {
+                int comp; double sg; CrossEntry(i, vi.dim, &comp, &sg);
+                emit_phase(row + i, vi.col, Rr + comp, sg, PackExt(kElemNode, vi.deriv, vi.count == 2, vi.a, info_fo), k);
+              }
+              emit_phase(row + 3 + vi.dim, vi.col, tb0, -1.0, PackExt(kElemNode, vi.deriv, vi.count == 2, vi.a, info_fo), k);
             }
             // ee-schedule: JacWrtForce + JacWrtEEPos of the dense 3 x (P-1) duration Jacobians (dynamic_constraint.cc:106-112)
-            for (int ph = 0; ph + 1 < sp.n_phases[e]; ++ph) for (int r = 0; r < 6; ++r) emit1(row + r, sched0[e] + ph, S_ONE, 0.0);
+            for (int ph = 0; ph + 1 < sp.n_phases[e]; ++ph)
+              for (int r = 0; r < 6; ++r) emit_phase(row + r, sched0[e] + ph, U0 + r, 1.0, PackExt(kElemDuration, 0, false, ph, cur), k);
           }
           for (int e = 0; e < n_ee && !optimize_timings; ++e) {
             // ee-motion: angular rows = [f_e]x dp_e
@@ -588,18 +617,14 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           tb.samples.push_back(MakeSample(sp_lin, ts[k], zero_slot));
           tb.samples.push_back(MakeSample(sp_ang, ts[k], zero_slot));
           for (int e = 0; e < n_ee; ++e) tb.samples.push_back(foot_sample(e, 0, ts[k]));
-          if (optimize_timings) {
-            PhaseUnit pu{}; pu.kind = kPhaseRom; pu.sample_lin = ru.sample0; pu.sample_ang = ru.sample0 + 1; pu.t = ts[k];
-            tb.phase_units.push_back(pu);   // rows[] filled below
-          }
         }
-        const size_t first_rom_phase_unit = tb.phase_units.size() - (optimize_timings ? (size_t)pl.n_rom : 0);
         for (int e = 0; e < n_ee; ++e) {
           int r0 = add_set("rangeofmotion-" + std::to_string(e), pl.n_rom * 3);
           pl.rom_row0[e] = r0;
           for (int k = 0; k < pl.n_rom; ++k) {
             const double t = ts[k]; const int row = r0 + 3 * k;
-            const uint32_t sb = 1, sd = 10 + RomBuffer(e), G0 = 19 + RomBuffer(e);
+            // (with optimised durations the foot's values exist in registers only: G0 is a placeholder)
+            const uint32_t sb = 1, sd = 10 + RomBufferP(e, optimize_timings), G0 = optimize_timings ? sd : 19 + RomBufferP(e, optimize_timings);
             for (int d = 0; d < 3; ++d) {
               bound(row + d, (0.0 + rb.nominal[e][d]) - rb.max_dev[d], (0.0 + rb.nominal[e][d]) + rb.max_dev[d]);
               own(row + d, kOwnRom, k * n_ee + e, G0 + d);
@@ -611,9 +636,13 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
             for (auto& b : Basis(sp_ang, p, tl, kPos)) for (int i = 0; i < 3; ++i)
               if (!(i == 0 && b.dim == 0)) emit1(row + i, ang.offset + b.var, sd + i * 3 + b.dim, b.val);
             if (optimize_timings) {
-              tb.phase_units[first_rom_phase_unit + k].rows[e] = row;
-              for (auto& cv : all_vars(motion(e))) for (int i = 0; i < 3; ++i) emit1(row + i, cv.first, S_ONE, 0.0);
-              for (int ph = 0; ph + 1 < sp.n_phases[e]; ++ph) for (int i = 0; i < 3; ++i) emit1(row + i, sched0[e] + ph, S_ONE, 0.0);
+              // PhaseSpline columns (range_of_motion_constraint.cc:83-109): phase elements of the foot's own list; the foot's
+              // buffer continues with the info block (sd + 9 .. sd + 20) | sd + 21..23: U | sd + 24..: X
+              const uint32_t info = sd + 9, cur = info, U0 = sd + 9 + kInfoRows;
+              for (auto& vi : all_vars(motion(e)))   // R^T d(p_e)
+                for (int i = 0; i < 3; ++i) emit_phase(row + i, vi.col, sb + i * 3 + vi.dim, 1.0, PackExt(kElemNode, vi.deriv, vi.count == 2, vi.a, info), -1);
+              for (int ph = 0; ph + 1 < sp.n_phases[e]; ++ph)
+                for (int i = 0; i < 3; ++i) emit_phase(row + i, sched0[e] + ph, U0 + i, 1.0, PackExt(kElemDuration, 0, false, ph, cur), -1);
               continue;
             }
             Locate(sp_motion[e], t, &p, &tl);  // R^T dp_e
@@ -773,6 +802,8 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   for (int s = 0; s < nnz; ++s) { row_ptr[em[s].row + 1]++; col_idx[s] = em[s].col; }
   for (int r = 0; r < m; ++r) row_ptr[r + 1] += row_ptr[r];
 
+  for (auto& pu : tb.phase_units) for (int e = 0; e < n_ee; ++e) pu.slot0[e] = row_ptr[pu.rows[e]];
+
   // ---- node groups: consecutive units of one kind and one constraint set share a warp's state block
   struct GroupBuild { int kind, first, count; std::vector<int> unit_ids; };
   std::vector<GroupBuild> groups;
@@ -814,8 +845,10 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   const int n_dyn_ctas = (pl.n_dyn + kDynWarps - 1) / kDynWarps, n_rom_ctas = (pl.n_rom + kRomWarps - 1) / kRomWarps;
   const int n_node_ctas = ((int)groups.size() + kNodeWarps - 1) / kNodeWarps;
   const int rom_lists = RomListsPerCta(n_ee);
-  const int n_lists = n_dyn_ctas + n_rom_ctas * rom_lists + n_node_ctas;   // dynamic CTAs | (rom CTA[, foot]) | node CTAs
-  pl.dyn_rows = 40 + 6 * n_ee; pl.rom_rows = RomBlockRows(n_ee);
+  const int tail_list0 = n_dyn_ctas + n_rom_ctas * rom_lists + n_node_ctas;
+  const int n_lists = tail_list0 + (optimize_timings ? pl.n_dyn : 0);   // dynamic CTAs | (rom CTA[, foot]) | node CTAs | PhaseSpline columns of dynamic sample k
+  pl.tail_list0 = tail_list0;
+  pl.dyn_rows = 40 + 6 * n_ee; pl.rom_rows = RomBlockRowsP(n_ee, optimize_timings);
   std::vector<int> list_of(n_blocks, -1), row_base(n_blocks, 0);   // list a block's elements belong to; first row of the block inside its CTA
   for (int k = 0; k < pl.n_dyn; ++k) { list_of[k] = k / kDynWarps; row_base[k] = (k % kDynWarps) * pl.dyn_rows; }
   for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) {
@@ -826,9 +859,9 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     const int b = pl.n_dyn + n_rom_blocks + gi;
     list_of[b] = n_dyn_ctas + n_rom_ctas * rom_lists + gi / kNodeWarps; row_base[b] = (gi % kNodeWarps) * pl.node_rows;
   }
-  struct Elem { int list; uint16_t d; double c; };
+  struct Elem { int list; uint16_t d; double c; uint32_t ext; };
   std::vector<Elem> elems(nnz);
-  struct Entry { OutPair p; OutCoef c; };
+  struct Entry { OutPair p; OutCoef c; PhaseExt x{0, 0}; };
   std::vector<std::vector<Entry>> values(n_blocks);   // constraint values of a block: (g row, local state row, 1)
   for (int r = 0; r < m; ++r) {
     const RowOwner& o = owner[r];
@@ -839,12 +872,15 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     if (blk >= 0 && o.g_local != kDirectValue) values[blk].push_back({OutPair{r, (uint16_t)g_row, 0}, OutCoef{1.0, 0.0}});
     for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) {
       uint32_t a = em[s].a;
+      if (em[s].tail >= 0) { elems[s] = Elem{tail_list0 + em[s].tail, (uint16_t)a, em[s].c0, em[s].ext}; continue; }   // rows of the tail kernel's CTA
       if (o.kind == kOwnNode && a != S_ONE) a = state0 + (a - 1);
-      elems[s] = blk >= 0 ? Elem{list_of[blk], (uint16_t)(row_base[blk] + a), em[s].c0} : Elem{-1, 0, 0.0};
+      uint32_t ext = em[s].ext;
+      if (blk >= 0 && (ext & 3u)) ext += (uint32_t)row_base[blk] << 16;   // info row: unit-local -> row of the CTA's shared memory
+      elems[s] = blk >= 0 ? Elem{list_of[blk], (uint16_t)(row_base[blk] + a), em[s].c0, ext} : Elem{-1, 0, 0.0, 0};
     }
   }
-  // lists[list][class][0: pairs, 1: singles]
-  std::vector<std::array<std::array<std::vector<Entry>, 2>, kMaxClasses>> lists(n_lists);
+  // lists[list][class][0: pairs, 1: singles, 2: pairs of sectors with a phase element]
+  std::vector<std::array<std::array<std::vector<Entry>, 3>, kMaxClasses>> lists(n_lists);
   const int NC = (nnz % 4 == 0) ? 1 : (nnz % 2 == 0) ? 2 : 4;
   pl.nc_jac = NC; pl.nc_g = 1;
   // ---- constant runs (device_tables.h: ConstRun): whole sectors whose elements all multiply the constant-1 state row.
@@ -882,11 +918,12 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
       bool full = (4 * S - c >= 0) && (4 * S + 3 - c <= L - 1) && writer >= 0;
       for (int i = first; i <= last && full; ++i) if (elems[i].list != writer) full = false;
       if (!full) {
-        for (int i = first; i <= last; ++i) if (elems[i].list >= 0) { lists[elems[i].list][q][1].push_back({OutPair{i, elems[i].d, 0}, OutCoef{elems[i].c, 0.0}}); hits[i]++; }
+        for (int i = first; i <= last; ++i) if (elems[i].list >= 0) { lists[elems[i].list][q][1].push_back({OutPair{i, elems[i].d, 0}, OutCoef{elems[i].c, 0.0}, PhaseExt{elems[i].ext, 0}}); hits[i]++; }
         continue;
       }
-      lists[writer][q][0].push_back({OutPair{first, elems[first].d, elems[first + 1].d}, OutCoef{elems[first].c, elems[first + 1].c}});
-      lists[writer][q][0].push_back({OutPair{first + 2, elems[first + 2].d, elems[first + 3].d}, OutCoef{elems[first + 2].c, elems[first + 3].c}});
+      const int cat = ((elems[first].ext | elems[first + 1].ext | elems[first + 2].ext | elems[first + 3].ext) & 3u) ? 2 : 0;
+      lists[writer][q][cat].push_back({OutPair{first, elems[first].d, elems[first + 1].d}, OutCoef{elems[first].c, elems[first + 1].c}, PhaseExt{elems[first].ext, elems[first + 1].ext}});
+      lists[writer][q][cat].push_back({OutPair{first + 2, elems[first + 2].d, elems[first + 3].d}, OutCoef{elems[first + 2].c, elems[first + 3].c}, PhaseExt{elems[first + 2].ext, elems[first + 3].ext}});
       for (int i = first; i <= last; ++i) hits[i]++;
     }
     // self-check: every element of an output-kernel row is written exactly once
@@ -908,18 +945,18 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
           cap = std::max(cap, 2 * (int)v.size());
         }
       }
-      OutRange* dst[2] = {&out.pairs[q], &out.singles[q]};
-      for (int w = 0; w < 2; ++w) {
+      OutRange* dst[3] = {&out.pairs[q], &out.singles[q], &out.phase[q]};
+      for (int w = 0; w < 3; ++w) {
         const auto& v = lists[list][q][w];
         dst[w]->first = (int32_t)tb.pairs.size(); dst[w]->count = (int32_t)v.size();
-        for (const Entry& en : v) { tb.pairs.push_back(en.p); tb.coefs.push_back(en.c); }
+        for (const Entry& en : v) { tb.pairs.push_back(en.p); tb.coefs.push_back(en.c); if (optimize_timings) tb.exts.push_back(en.x); }
       }
     }
     return out;
   };
   auto flush_values = [&](int block) {
     OutRange r{(int32_t)tb.pairs.size(), (int32_t)values[block].size()};
-    for (const Entry& en : values[block]) { tb.pairs.push_back(en.p); tb.coefs.push_back(en.c); }
+    for (const Entry& en : values[block]) { tb.pairs.push_back(en.p); tb.coefs.push_back(en.c); if (optimize_timings) tb.exts.push_back(en.x); }
     return r;
   };
   for (int i = 0; i < n_lists; ++i) tb.cta_lists.push_back(flush_list(i));
@@ -955,10 +992,6 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
     has_cost = true;
   }
 
-  if (optimize_timings) {   // (row, column) -> CSR slot, for the PhaseJac kernel
-    tb.slot_of.assign((size_t)m * n, -1);
-    for (int r = 0; r < m; ++r) for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) tb.slot_of[(size_t)r * n + col_idx[s]] = s;
-  }
   pl.n_phase_units = (int)tb.phase_units.size(); pl.n_phase_defs = (int)tb.phase_defs.size();
   // ---- plan scalars
   pl.n = n; pl.m = m; pl.nnz = nnz; pl.n_ee = n_ee;

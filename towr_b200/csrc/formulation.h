@@ -52,7 +52,7 @@ struct HostTables {
   std::vector<PhaseSplineDef> phase_defs;
   std::vector<PhasePoly> phase_polys;
   std::vector<PhaseUnit> phase_units;
-  std::vector<int32_t> slot_of;
+  std::vector<PhaseExt> exts;
   std::vector<GoalVar> goal_vars;
   std::vector<ConstRun> const_runs;
   std::vector<double> const_vals;

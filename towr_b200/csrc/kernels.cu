@@ -640,6 +640,111 @@ __device__ __forceinline__ void BaseMotionUnitEval(const Plan& P, const BaseMoti
   for (int d = 0; d < 3; ++d) { gk[d] = ang[d]; gk[3 + d] = lin[d]; }
 }
 
+// ---- PhaseSplines: what the Jacobian needs beyond the value (optimised phase durations only) ------------------
+// Everything a PhaseSpline contributes at one sample: value, velocity, the four Hermite basis values of the active
+// polynomial (polynomial.cc:106-234), d(pos)/d(phase duration) (polynomial.cc:236-257, phase_spline.cc:77-93) and
+// the phase the sample falls into (phase_durations.cc:122-154).
+struct PhaseFull {
+  const PhasePoly* pp;
+  double B[2][2];          // [side][node derivative]: d(pos)/d(node value)
+  double pos[3], vel[3], dxdT[3];
+  int cur, n_phases;       // current phase, number of phases
+  int poly;                // active polynomial
+};
+__device__ __forceinline__ PhaseFull EvalPhaseFull(const Plan& P, int def_index, double tg, const ConstCol xs) {
+  const PhaseSplineDef def = P.phase_defs[def_index];
+  const PhaseLoc L = LocatePhasePoly(P, def, tg, xs);
+  PhaseFull o; o.pp = P.phase_polys + def.poly0 + L.poly; o.n_phases = def.n_phases; o.poly = L.poly;
+  const double T = L.T, T2 = T * T, T3 = Pow3(T), T4 = Pow4(T), t = L.tl, t2 = t * t, t3 = Pow3(t);
+  o.B[0][0] = (2 * t3) / T3 - (3 * t2) / T2 + 1; o.B[0][1] = t - (2 * t2) / T + t3 / T2;
+  o.B[1][0] = (3 * t2) / T2 - (2 * t3) / T3;     o.B[1][1] = t3 / T2 - t2 / T;
+  const double inner = 1. / (double)o.pp->n_in_phase, prev = (double)o.pp->k_in_phase;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double x0 = xs[o.pp->xi[d]], v0 = xs[o.pp->xi[3 + d]], x1 = xs[o.pp->xi[6 + d]], v1 = xs[o.pp->xi[9 + d]];
+    const double C = -(3 * (x0 - x1) + T * (2 * v0 + v1)) / T2;
+    const double D = (2 * (x0 - x1) + T * (v0 + v1)) / T3;
+    o.pos[d] = ((x0 + t * v0) + t2 * C) + t3 * D;
+    o.vel[d] = (v0 + (2 * t) * C) + (3 * t2) * D;
+    const double dT = (t3 * (v0 + v1)) / T3 - (t2 * (2 * v0 + v1)) / T2 - (3 * t3 * (2 * x0 - 2 * x1 + T * v0 + T * v1)) / T4 +
+                      (2 * t2 * (3 * x0 - 3 * x1 + 2 * T * v0 + T * v1)) / T3;
+    o.dxdT[d] = inner * (dT - prev * o.vel[d]);
+  }
+  // Spline::GetSegmentID over the PHASE durations
+  const double eps = 1e-10;
+  double acc = 0.0; o.cur = def.n_phases - 1; bool found = false;
+  for (int ph = 0; ph < def.n_phases; ++ph) {
+    acc += (ph == def.n_phases - 1) ? L.last : xs[def.sched0 + ph];
+    if (!found && acc >= tg - eps) { found = true; o.cur = ph; }
+  }
+  return o;
+}
+// column `ph` of PhaseDurations::GetJacobianOfPos (phase_durations.cc:122-154)
+__device__ __forceinline__ void DurationColumn(const PhaseFull& f, int ph, double col[3]) {
+  const bool in_last = f.cur == f.n_phases - 1;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double v = 0.0;
+    if (!in_last && ph == f.cur) v = f.dxdT[d];
+    else if (ph < f.cur) { v = -1 * f.vel[d]; if (in_last) v = v - f.dxdT[d]; }
+    col[d] = v;
+  }
+}
+// The two non-zero shapes of a duration column (DurationColumn above): U for the columns of earlier phases (ph < cur),
+// V for the column of the current phase (zero when the sample lies in the last phase)
+__device__ __forceinline__ void DurationVectors(const PhaseFull& f, double U[3], double V[3]) {
+  if (f.cur >= 1) DurationColumn(f, f.cur - 1, U); else { U[0] = U[1] = U[2] = 0.0; }
+  DurationColumn(f, f.cur, V);
+}
+// info block of a PhaseSpline at one sample (device_tables.h: PhaseExt), rows `info`..`info + kInfoRows - 1` of the warp's
+// state block `t`; called by all 32 lanes (lane = instance)
+__device__ __forceinline__ void StorePhaseInfo(const PhaseFull& f, double* t, int info, int lane) {
+  int* pi = reinterpret_cast<int*>(t + info * kLD);
+  pi[lane] = f.poly;
+  const int pmin = __reduce_min_sync(0xffffffffu, f.poly), pmax = __reduce_max_sync(0xffffffffu, f.poly);
+  if (lane == 0) { pi[32] = pmin; pi[33] = pmax; }
+  double* r = t + (info + 1) * kLD + lane;
+  const double b00 = f.B[0][0], b01 = f.B[0][1], b10 = f.B[1][0], b11 = f.B[1][1];
+  if (pmax - pmin <= 2) {   // window form: weights of the nodes pmin .. pmin + 3
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r[k * kLD] = 0.0;
+    double* w = r + (1 + 2 * (f.poly - pmin)) * kLD;   // this instance's polynomial joins the nodes P (side 0) and P + 1 (side 1)
+    w[0] = b00; w[kLD] = b01; w[2 * kLD] = b10; w[3 * kLD] = b11;
+  } else {                  // table form
+    r[0] = 0.0; r[kLD] = b10; r[2 * kLD] = b00; r[3 * kLD] = 0.0; r[4 * kLD] = b11; r[5 * kLD] = b01; r[6 * kLD] = 0.0;
+    r[7 * kLD] = b10; r[8 * kLD] = b00 + b10; r[9 * kLD] = b00; r[10 * kLD] = 0.0;
+  }
+}
+// Current phase of the foot (the same for its ee-motion and ee-force splines: integers 34.. of the ee-motion info block's
+// first row) and the duration columns of `kRows` constraint rows: U (columns of earlier phases) into rows u0 .., then X —
+// window form (the current phase differs by less than kWin over the tile): the finished columns cmin, cmin + 1, ..; else V.
+template <int kRows, int kWin>
+__device__ __forceinline__ void StorePhaseDurations(int cur, const double* U, const double* V, double* t, int info, int u0, int lane) {
+  int* pi = reinterpret_cast<int*>(t + info * kLD);
+  pi[34 + lane] = cur;
+  const int cmin = __reduce_min_sync(0xffffffffu, cur), cmax = __reduce_max_sync(0xffffffffu, cur);
+  if (lane == 0) { pi[66] = cmin; pi[67] = cmax; }
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) t[(u0 + r) * kLD + lane] = U[r];
+  if (cmax - cmin < kWin) {
+#pragma unroll
+    for (int w = 0; w < kWin; ++w) {
+      const int ph = cmin + w;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) t[(u0 + kRows * (1 + w) + r) * kLD + lane] = ph < cur ? U[r] : ph == cur ? V[r] : 0.0;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) t[(u0 + kRows + r) * kLD + lane] = V[r];
+  }
+}
+// C = Cross(v) of single_rigid_body_dynamics.cc:46-57
+__device__ __forceinline__ void CrossMatrix(const double v[3], double C[3][3]) {
+  C[0][0] = 0.0;   C[0][1] = -v[2]; C[0][2] = v[1];
+  C[1][0] = v[2];  C[1][1] = 0.0;   C[1][2] = -v[0];
+  C[2][0] = -v[1]; C[2][1] = v[0];  C[2][2] = 0.0;
+}
+
 // ---- kernels ---------------------------------------------------------------------
 // instance b of the tiled iterate matrix with `rows` rows: element r lives at base[((b/32)*rows + r)*32 + b%32]
 __device__ __forceinline__ ConstCol TiledCol(const double* base, int b, int rows) {
@@ -874,6 +979,105 @@ __device__ __forceinline__ void StorePairsTma(const double* t, const OutPair* __
     if (lane == 0) { BulkStore(out + (size_t)j * stride + run_off, b0, bytes); BulkCommit(); }
   }
 }
+// ---- phase elements (device_tables.h: PhaseExt) --------------------------------------------------------------------
+// per-instance value of one element whose info block is in TABLE form / whose duration columns are not finished:
+// `x` is the element's PhaseExt word, d / c its state row and coefficient
+__device__ __forceinline__ double PhaseVal(const double* t, int j, unsigned x, int d, double c, int v_off) {
+  const int a = (int)((x >> 8) & 0xFFu), info = (int)(x >> 16);
+  const int* pi = reinterpret_cast<const int*>(t + info * kLD);
+  if ((x & 3u) == kElemNode) {   // NodeSpline::FillJacobianWrtNodes (node_spline.cc:85-112) for the instance's active polynomial
+    const int shared = (int)((x >> 3) & 1u);
+    const int tbl = info + (shared ? 7 : 1 + 3 * (int)((x >> 2) & 1u));
+    const int idx = min(max(pi[j] - a + 2, 0), 3 + shared);
+    return (t[d * kLD + j] * c) * t[(tbl + idx) * kLD + j];
+  }
+  const int dl = pi[34 + j] - a;   // PhaseDurations::GetJacobianOfPos (phase_durations.cc:122-154): a = the column's phase
+  return dl < 0 ? 0.0 : t[(dl > 0 ? d : d + v_off) * kLD + j];
+}
+// What an element is for the instances of this tile: out = (state[d] * c) * (state[w1] [+ state[w2]]) with rows that are the
+// same for every instance (w1 = row 0, the constant 1, for an ordinary element; zero elements become row `zrow` times 0), or
+// `slow`: the per-instance selection of PhaseVal.
+struct ElemForm { int d, w1, w2; double c; bool slow; };
+__device__ __forceinline__ ElemForm Classify(const double* t, unsigned x, int d, double c, int v_off, int dwin, int zrow) {
+  ElemForm f{d, 0, -1, c, false};
+  const unsigned kind = x & 3u;
+  if (kind == kElemPlain) return f;
+  const int a = (int)((x >> 8) & 0xFFu), info = (int)(x >> 16);
+  const int* pi = reinterpret_cast<const int*>(t + info * kLD);
+  if (kind == kElemNode) {
+    const int2 mm = *reinterpret_cast<const int2*>(pi + 32);
+    const int shared = (int)((x >> 3) & 1u);
+    if (mm.y < a - 1 || mm.x > a + shared) { f.d = zrow; f.c = 0.0; return f; }   // no instance's polynomial touches the node(s)
+    if (mm.y - mm.x > 2) { f.slow = true; return f; }
+    const int s1 = a - mm.x, deriv = (int)((x >> 2) & 1u);
+    const bool in1 = s1 >= 0 && s1 <= 3, in2 = shared && s1 + 1 >= 0 && s1 + 1 <= 3;
+    if (in1) { f.w1 = info + 2 + 2 * s1 + deriv; if (in2) f.w2 = info + 2 + 2 * (s1 + 1); }
+    else if (in2) f.w1 = info + 2 + 2 * (s1 + 1);
+    else { f.d = zrow; f.c = 0.0; }
+    return f;
+  }
+  const int2 mm = *reinterpret_cast<const int2*>(pi + 66);
+  if (a > mm.y) { f.d = zrow; f.c = 0.0; }
+  else if (a < mm.x) { }                                     // a column of an earlier phase for every instance: U
+  else if (mm.y - mm.x < dwin) f.d = d + v_off * (1 + a - mm.x);   // finished column
+  else f.slow = true;
+  return f;
+}
+__device__ __forceinline__ double FormVal(const double* t, int j, const ElemForm& f, unsigned x, int d, double c, int v_off) {
+  if (f.slow) return PhaseVal(t, j, x, d, c, v_off);
+  const double w = f.w2 >= 0 ? t[f.w1 * kLD + j] + t[f.w2 * kLD + j] : t[f.w1 * kLD + j];
+  return (t[f.d * kLD + j] * f.c) * w;
+}
+// the pair loop for sectors that hold phase elements: item = (pair, half of the tile's instances) as in StorePairs
+__device__ __forceinline__ void StorePhasePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
+                                                const PhaseExt* __restrict__ exts, int n_pairs, double* __restrict__ out, size_t stride,
+                                                int q, int nc, int n_inst, int v_off, int dwin, int zrow, int tid, int n_threads) {
+  const int n_items = 2 * n_pairs;
+  for (int i = tid; i < n_items; i += n_threads) {
+    const int k = i < n_pairs ? i : i - n_pairs, jb = i < n_pairs ? 0 : 16;
+    int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
+    LoadPair(pairs, coefs, k, n_pairs, &off, &d0, &d1, &c0, &c1);
+    const uint2 x = __ldg(reinterpret_cast<const uint2*>(exts) + k);
+    double* o = out + off + (size_t)jb * stride;
+    const ElemForm f0 = Classify(t, x.x, d0, c0, v_off, dwin, zrow), f1 = Classify(t, x.y, d1, c1, v_off, dwin, zrow);
+    if (n_inst == 32 && nc == 1 && !f0.slow && !f1.slow) {
+      const double* r0 = t + f0.d * kLD + jb; const double* r1 = t + f1.d * kLD + jb;
+      if ((f0.w1 | f1.w1) == 0) {   // both elements are ordinary for this tile: the pair loop of StorePairs
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
+          StoreOut2(o, a.x * f0.c, b.x * f1.c); o += stride;
+          StoreOut2(o, a.y * f0.c, b.y * f1.c); o += stride;
+        }
+      } else if ((f0.w2 & f1.w2) < 0) {   // a weight row each (row 0 = 1 for an ordinary element)
+        const double* w0 = t + f0.w1 * kLD + jb; const double* w1 = t + f1.w1 * kLD + jb;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
+          const double2 u = *reinterpret_cast<const double2*>(w0 + j), v = *reinterpret_cast<const double2*>(w1 + j);
+          StoreOut2(o, (a.x * f0.c) * u.x, (b.x * f1.c) * v.x); o += stride;
+          StoreOut2(o, (a.y * f0.c) * u.y, (b.y * f1.c) * v.y); o += stride;
+        }
+      } else {                            // shared stance positions: the sum of two weight rows (the zero row where there is none)
+        const double* w0 = t + f0.w1 * kLD + jb; const double* w1 = t + f1.w1 * kLD + jb;
+        const double* y0 = t + (f0.w2 >= 0 ? f0.w2 : zrow) * kLD + jb; const double* y1 = t + (f1.w2 >= 0 ? f1.w2 : zrow) * kLD + jb;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
+          const double2 u = *reinterpret_cast<const double2*>(w0 + j), v = *reinterpret_cast<const double2*>(w1 + j);
+          const double2 p = *reinterpret_cast<const double2*>(y0 + j), r = *reinterpret_cast<const double2*>(y1 + j);
+          StoreOut2(o, (a.x * f0.c) * (u.x + p.x), (b.x * f1.c) * (v.x + r.x)); o += stride;
+          StoreOut2(o, (a.y * f0.c) * (u.y + p.y), (b.y * f1.c) * (v.y + r.y)); o += stride;
+        }
+      }
+    } else if (n_inst == 32 && nc == 1) {
+#pragma unroll 4
+      for (int j = jb; j < jb + 16; ++j) { StoreOut2(o, FormVal(t, j, f0, x.x, d0, c0, v_off), FormVal(t, j, f1, x.y, d1, c1, v_off)); o += stride; }
+    } else {
+      for (int j = jb; j < jb + 16; ++j) { if (j < n_inst && (j % nc) == q) StoreOut2(o, FormVal(t, j, f0, x.x, d0, c0, v_off), FormVal(t, j, f1, x.y, d1, c1, v_off)); o += stride; }
+    }
+  }
+}
 // Entries handled with lane = instance: fetched with one coalesced load (lane = entry), broadcast with shuffles.
 // fn(first, d0, coefficient) is called by every lane of the warp for every entry.
 template <class F>
@@ -928,7 +1132,9 @@ __device__ __noinline__ void StorePairsClasses(const Plan& P, const double* t, c
 #endif
 // Jacobian values of a whole CTA (after its barrier): every thread takes pairs of the CTA's list; warp 0 writes the
 // single elements (sectors shared with a neighbouring CTA) with lane = instance.
-__device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst, const Stage st) {
+template <bool kPhase = false>
+__device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst, const Stage st,
+                                         int v_off = 0, int dwin = 0, int zrow = 0) {
 #ifdef TWB_EXP_NOSTORE   // timing experiment: compute phase only
   return;
 #endif
@@ -945,8 +1151,11 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
     // loop, so that the two dependent loads are in flight under the warp's pair stores instead of after them
     OutRange rs{0, 0};
     if (threadIdx.x < 32) rs = LoadRange(&list->singles[q]);
-    uint2 raw = make_uint2(0u, 0u); double cs = 0.0;
-    if (lane < rs.count) { raw = __ldg(reinterpret_cast<const uint2*>(P.pairs + rs.first) + lane); cs = __ldg(reinterpret_cast<const double*>(P.coefs + rs.first + lane)); }
+    uint2 raw = make_uint2(0u, 0u); double cs = 0.0; unsigned xs = 0u;
+    if (lane < rs.count) {
+      raw = __ldg(reinterpret_cast<const uint2*>(P.pairs + rs.first) + lane); cs = __ldg(reinterpret_cast<const double*>(P.coefs + rs.first + lane));
+      if (kPhase) xs = __ldg(reinterpret_cast<const unsigned*>(P.exts + rs.first + lane));
+    }
 #if TWB_TMA
     const int run_off = __ldg(&list->run_off[q]);
     if (run_off >= 0 && 2 * rp.count <= st.cap && (32 % (blockDim.x >> 5)) == 0)
@@ -954,6 +1163,11 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
     else
 #endif
     StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, threadIdx.x, blockDim.x);
+    if (kPhase) {
+      const OutRange rq = LoadRange(&list->phase[q]);
+      StorePhasePairs(cta_smem, P.pairs + rq.first, P.coefs + rq.first, P.exts + rq.first, rq.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, v_off, dwin, zrow,
+                      threadIdx.x, blockDim.x);
+    }
 #ifndef TWB_EXP_NOSINGLES   // (timing experiment, profiles/README.md round 2: what the single-element stores cost)
     if (threadIdx.x < 32 && rs.count > 0) {
       const bool active = lane < n_inst && (lane % nc) == q;
@@ -962,11 +1176,23 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
       for (int sidx = 0; sidx < cnt; ++sidx) {
         const int off = __shfl_sync(0xffffffffu, (int)raw.x, sidx), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), sidx);
         const double c = __shfl_sync(0xffffffffu, cs, sidx);
-        if (active) StoreOut(o + off, cta_smem[d * kLD + lane] * c);
+        const unsigned x = kPhase ? __shfl_sync(0xffffffffu, xs, sidx) : 0u;
+        if (active) StoreOut(o + off, kPhase ? FormVal(cta_smem, lane, Classify(cta_smem, x, d, c, v_off, dwin, zrow), x, d, c, v_off) : cta_smem[d * kLD + lane] * c);
       }
-      if (rs.count > 32)
-        ForEachEntry(P.pairs + rs.first + 32, P.coefs + rs.first + 32, rs.count - 32, lane,
-                     [&](int off, int d, double c) { if (active) StoreOut(o + off, cta_smem[d * kLD + lane] * c); });
+      for (int base = 32; base < rs.count; base += 32) {   // (rare) more than 32 single elements
+        raw = make_uint2(0u, 0u); cs = 0.0; xs = 0u;
+        if (base + lane < rs.count) {
+          raw = __ldg(reinterpret_cast<const uint2*>(P.pairs + rs.first + base) + lane); cs = __ldg(reinterpret_cast<const double*>(P.coefs + rs.first + base + lane));
+          if (kPhase) xs = __ldg(reinterpret_cast<const unsigned*>(P.exts + rs.first + base + lane));
+        }
+        const int more = min(32, rs.count - base);
+        for (int sidx = 0; sidx < more; ++sidx) {
+          const int off = __shfl_sync(0xffffffffu, (int)raw.x, sidx), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), sidx);
+          const double c = __shfl_sync(0xffffffffu, cs, sidx);
+          const unsigned x = kPhase ? __shfl_sync(0xffffffffu, xs, sidx) : 0u;
+          if (active) StoreOut(o + off, kPhase ? FormVal(cta_smem, lane, Classify(cta_smem, x, d, c, v_off, dwin, zrow), x, d, c, v_off) : cta_smem[d * kLD + lane] * c);
+        }
+      }
     }
 #endif
   }
@@ -1013,12 +1239,14 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kRomWarps + warp, b0 = tile * 32;
   const bool valid = k < P.n_rom;
-  constexpr int block_rows = RomBlockRows(kNEE);
+  constexpr int block_rows = RomBlockRowsP(kNEE, kPhase);
   double* t = out_smem + (size_t)warp * block_rows * kLD;
   const RomUnit* u = P.rom + (valid ? k : 0);
   const SplineSample* __restrict__ sp = P.samples + __ldg(&u->sample0);
   const ConstCol xs = TiledCol(XT, b0 + lane, P.n + 1);
-  const Col Sk{t + kLD + lane, kLD};   // local state rows 1..: R^T (0..8) | buffer 0: D_e (9..17), g_e (18..20) | buffer 1: (21..29), (30..32)
+  // local state rows 1..: R^T (0..8) | buffer 0: D_e (9..17), g_e (18..20) | buffer 1: (21..29), (30..32); with optimised durations a
+  // buffer is D_e (9) | the PhaseSpline's info block (kInfoRows) | U (3) | X (3 kRomDurWin)   (g_e lives in registers only)
+  const Col Sk{t + kLD + lane, kLD};
   const int n_inst = min(32, nb - b0);
   double* jac_tile = jac + (size_t)b0 * P.nnz;
   t[lane] = 1.0;
@@ -1036,22 +1264,35 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
 #endif
 #pragma unroll 1
   for (int e = 0; e < kNEE; ++e) {
-    const int buf = RomBuffer(e);
+    const int buf = RomBufferP(e, kPhase);
 #ifndef TWB_EXP_NOCOMPUTE
     double pe[3];
-    EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
+    if (kPhase) {   // range_of_motion_constraint.cc:83-109 with the PhaseSpline of foot e: value, active polynomial, duration columns
+      const PhaseFull mo = EvalPhaseFull(P, 2 * e, __ldg(&sp[2 + e].T), xs);
+      pe[0] = mo.pos[0]; pe[1] = mo.pos[1]; pe[2] = mo.pos[2];
+      StorePhaseInfo(mo, t, 19 + buf, lane);
+      double U[3], V[3], RU[3], RV[3]; DurationVectors(mo, U, V);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        RU[i] = (R[0][i] * U[0] + R[1][i] * U[1]) + R[2][i] * U[2];
+        RV[i] = (R[0][i] * V[0] + R[1][i] * V[1]) + R[2][i] * V[2];
+      }
+      StorePhaseDurations<3, kRomDurWin>(mo.cur, RU, RV, t, 19 + buf, 19 + kInfoRows + buf, lane);
+    } else {
+      EvalSpline<0, false>(P, sp + 2 + e, xs, pe, unused, unused);
+    }
     const double r[3] = {pe[0] - c[0], pe[1] - c[1], pe[2] - c[2]};
     double D[3][3]; RotVecDerivative<true>(dR, r, D);
     double ge[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { ge[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2]; Sk[18 + buf + i] = ge[i]; }
+    for (int i = 0; i < 3; ++i) { ge[i] = R[0][i] * r[0] + R[1][i] * r[1] + R[2][i] * r[2]; if (!kPhase) Sk[18 + buf + i] = ge[i]; }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int d = 0; d < 3; ++d) Sk[9 + buf + i * 3 + d] = D[i][d];
     if (valid) {
       if (e == 0) FlagNonFinite(t, 10, lane, status, b0 + lane, nb);
-      FlagNonFinite(t, 22 + buf, lane, status, b0 + lane, nb, 10 + buf);
+      FlagNonFinite(t, (kPhase ? 19 : 22) + buf, lane, status, b0 + lane, nb, 10 + buf);
     }
 #endif
     if (valid && (flags & 1u)) {   // rows rom_row0[e] + 3k .. + 2 (range_of_motion_constraint.cc:58-66), lane = instance into GT
@@ -1065,12 +1306,12 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
     }
 #if !TWB_ROM_ALLFEET
     __syncthreads();   // foot e complete in every block; everybody is done reading buffer (e + 1) & 1 (the list of foot e - 1)
-    if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst, st);
+    if (flags & 2u) StoreCta<kPhase>(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst, st, 3, kRomDurWin, 20 + buf);
 #endif
   }
 #if TWB_ROM_ALLFEET
   __syncthreads();
-  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.rom_list0 + cta, jac_tile, n_inst, st);
+  if (flags & 2u) StoreCta<kPhase>(P, out_smem, P.cta_lists + P.rom_list0 + cta, jac_tile, n_inst, st, 3, kRomDurWin, 20);
 #endif
 }
 
@@ -1146,149 +1387,72 @@ __global__ void __launch_bounds__(128) CostKernel(const Plan P, const double* __
   if (cost) cost[b] = total_cost;
 }
 
-// ---- PhaseJac: Jacobian entries that exist only with optimised phase durations -----------------------------
-// Everything a PhaseSpline contributes at one sample: value, velocity, the four Hermite basis values of the active
-// polynomial (polynomial.cc:106-234), d(pos)/d(phase duration) (polynomial.cc:236-257, phase_spline.cc:77-93) and
-// the phase the sample falls into (phase_durations.cc:122-154).
-struct PhaseFull {
-  const PhasePoly* pp;
-  double B[2][2];          // [side][node derivative]: d(pos)/d(node value)
-  double pos[3], vel[3], dxdT[3];
-  int cur, n_phases;       // current phase, number of phases
-};
-__device__ __forceinline__ PhaseFull EvalPhaseFull(const Plan& P, int def_index, double tg, const ConstCol xs) {
-  const PhaseSplineDef def = P.phase_defs[def_index];
-  const PhaseLoc L = LocatePhasePoly(P, def, tg, xs);
-  PhaseFull o; o.pp = P.phase_polys + def.poly0 + L.poly; o.n_phases = def.n_phases;
-  const double T = L.T, T2 = T * T, T3 = Pow3(T), T4 = Pow4(T), t = L.tl, t2 = t * t, t3 = Pow3(t);
-  o.B[0][0] = (2 * t3) / T3 - (3 * t2) / T2 + 1; o.B[0][1] = t - (2 * t2) / T + t3 / T2;
-  o.B[1][0] = (3 * t2) / T2 - (2 * t3) / T3;     o.B[1][1] = t3 / T2 - t2 / T;
-  const double inner = 1. / (double)o.pp->n_in_phase, prev = (double)o.pp->k_in_phase;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const double x0 = xs[o.pp->xi[d]], v0 = xs[o.pp->xi[3 + d]], x1 = xs[o.pp->xi[6 + d]], v1 = xs[o.pp->xi[9 + d]];
-    const double C = -(3 * (x0 - x1) + T * (2 * v0 + v1)) / T2;
-    const double D = (2 * (x0 - x1) + T * (v0 + v1)) / T3;
-    o.pos[d] = ((x0 + t * v0) + t2 * C) + t3 * D;
-    o.vel[d] = (v0 + (2 * t) * C) + (3 * t2) * D;
-    const double dT = (t3 * (v0 + v1)) / T3 - (t2 * (2 * v0 + v1)) / T2 - (3 * t3 * (2 * x0 - 2 * x1 + T * v0 + T * v1)) / T4 +
-                      (2 * t2 * (3 * x0 - 3 * x1 + 2 * T * v0 + T * v1)) / T3;
-    o.dxdT[d] = inner * (dT - prev * o.vel[d]);
-  }
-  // Spline::GetSegmentID over the PHASE durations
-  const double eps = 1e-10;
-  double acc = 0.0; o.cur = def.n_phases - 1; bool found = false;
-  for (int ph = 0; ph < def.n_phases; ++ph) {
-    acc += (ph == def.n_phases - 1) ? L.last : xs[def.sched0 + ph];
-    if (!found && acc >= tg - eps) { found = true; o.cur = ph; }
-  }
-  return o;
-}
-// column `ph` of PhaseDurations::GetJacobianOfPos (phase_durations.cc:122-154)
-__device__ __forceinline__ void DurationColumn(const PhaseFull& f, int ph, double col[3]) {
-  const bool in_last = f.cur == f.n_phases - 1;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    double v = 0.0;
-    if (!in_last && ph == f.cur) v = f.dxdT[d];
-    else if (ph < f.cur) { v = -1 * f.vel[d]; if (in_last) v = v - f.dxdT[d]; }
-    col[d] = v;
-  }
-}
-// C = Cross(v) of single_rigid_body_dynamics.cc:46-57
-__device__ __forceinline__ void CrossMatrix(const double v[3], double C[3][3]) {
-  C[0][0] = 0.0;   C[0][1] = -v[2]; C[0][2] = v[1];
-  C[1][0] = v[2];  C[1][1] = 0.0;   C[1][2] = -v[0];
-  C[2][0] = -v[1]; C[2][1] = v[0];  C[2][2] = 0.0;
-}
-// The node variables of the active polynomial: up to 12 (column, dim, weight) entries; a stance position shared
-// by both boundary nodes gets the sum of both basis values (NodeSpline::FillJacobianWrtNodes, node_spline.cc:85-112).
-template <class F>
-__device__ __forceinline__ void ForEachActiveNodeVar(const PhaseFull& f, int zero_slot, F&& fn) {
-#pragma unroll
-  for (int deriv = 0; deriv < 2; ++deriv)
-#pragma unroll
-    for (int dim = 0; dim < 3; ++dim) {
-      const int c0 = f.pp->xi[deriv * 3 + dim], c1 = f.pp->xi[6 + deriv * 3 + dim];
-      if (c0 == c1) { if (c0 != zero_slot) fn(c0, dim, f.B[0][deriv] + f.B[1][deriv]); }
-      else { if (c0 != zero_slot) fn(c0, dim, f.B[0][deriv]); if (c1 != zero_slot) fn(c1, dim, f.B[1][deriv]); }
-    }
-}
-// warp = one phase unit (a dynamic sample, a range-of-motion sample, or the total-duration rows) x one tile of 32
-// instances; lane = instance writes its own entries with 8-byte stores (a few dozen per sample; the bulk of these
-// rows — structural zeros — was written, coalesced, by the output kernels).
+// ---- PhaseSpline columns of the dynamic constraint (optimised phase durations) --------------------------------
+// dynamic_constraint.cc:91-113 with single_rigid_body_dynamics.cc:167-192: with PhaseSplines every dynamic row is
+// structurally dense in all ee-motion / ee-force node variables and in the feet's duration variables (324 of the 348 entries
+// of an angular row of config 4).  CTA = (dynamic sample, tile of 32 instances), warp = foot: lane = instance evaluates the
+// foot's two PhaseSplines with everything their Jacobian needs (active polynomial, Hermite basis values, duration columns)
+// into the foot's state block (device_tables.h: kTailRows); then all threads of the CTA walk the sample's list of phase
+// elements — the same coalesced whole-sector pair loop as every other Jacobian value.  (Until round 2 these entries were
+// scattered by lane = instance 8-byte stores over rows of zeros: 1.0 of config 4's 1.26 ms.)
 template <int kNEE>
-__global__ void __launch_bounds__(128) PhaseJac(const Plan P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
-                                                int* __restrict__ status, int nb, unsigned flags) {
-  const int lane = threadIdx.x & 31, ui = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (ui >= P.n_phase_units) return;
-  const int b = blockIdx.y * 32 + lane;
-  const bool live = b < nb, want_jac = (flags & 2u) != 0;
+__global__ void __launch_bounds__(kNEE * 32) DynTailOut(const Plan P, const double* __restrict__ XT, double* __restrict__ jac, int nb) {
+  extern __shared__ __align__(16) double out_smem[];
+  const int lane = threadIdx.x & 31, e = threadIdx.x >> 5, k = blockIdx.x, b0 = blockIdx.y * 32;
+  double* t = out_smem + (size_t)e * kTailRows * kLD;
+  const SplineSample* __restrict__ sp = P.samples + __ldg(&P.dyn[k].sample0);
+  const ConstCol xs = TiledCol(XT, b0 + lane, P.n + 1);
+#ifndef TWB_EXP_NOCOMPUTE
+  double c[3], unused[3];
+  EvalSpline<0>(P, sp, xs, c, unused, unused);
+  const double tg = __ldg(&sp[2 + e].T);   // phase samples carry the global time
+  const PhaseFull mo = EvalPhaseFull(P, 2 * e, tg, xs), fo = EvalPhaseFull(P, 2 * e + 1, tg, xs);
+  const double r[3] = {c[0] - mo.pos[0], c[1] - mo.pos[1], c[2] - mo.pos[2]};
+  t[lane] = 1.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { t[(1 + d) * kLD + lane] = fo.pos[d]; t[(4 + d) * kLD + lane] = r[d]; }
+  StorePhaseInfo(mo, t, 7, lane);
+  StorePhaseInfo(fo, t, 7 + kInfoRows, lane);
+  double Cf[3][3], Cr[3][3];
+  CrossMatrix(fo.pos, Cf); CrossMatrix(r, Cr);
+  double jfU[3], jfV[3], jmU[3], jmV[3];
+  DurationVectors(fo, jfU, jfV); DurationVectors(mo, jmU, jmV);
+  double U[6], V[6];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {   // JacWrtForce + JacWrtEEPos of the duration columns (dynamic_constraint.cc:106-112)
+    const int d1 = (i == 0) ? 1 : 0, d2 = (i == 2) ? 1 : 2;
+    U[i] = (Cr[i][d1] * jfU[d1] + Cr[i][d2] * jfU[d2]) + (Cf[i][d1] * jmU[d1] + Cf[i][d2] * jmU[d2]);
+    U[3 + i] = -jfU[i];
+    V[i] = (Cr[i][d1] * jfV[d1] + Cr[i][d2] * jfV[d2]) + (Cf[i][d1] * jmV[d1] + Cf[i][d2] * jmV[d2]);
+    V[3 + i] = -jfV[i];
+  }
+  StorePhaseDurations<6, kDynDurWin>(mo.cur, U, V, t, 7, 7 + 2 * kInfoRows, lane);
+#endif
+  __syncthreads();
+  StoreCta<true>(P, out_smem, P.cta_lists + P.tail_list0 + k, jac + (size_t)b0 * P.nnz, min(32, nb - b0), Stage{nullptr, 0}, 6, kDynDurWin, 8);
+}
+
+// TotalDurationConstraint (total_duration_constraint.cc:36-72; the only rows no output kernel owns): value = sum of the foot's
+// optimised durations, Jacobian = 1 in each of their columns, status bit 1 when the sum leaves nothing for the last phase
+// (phase_durations.cc:92).  warp = tile of 32 instances, lane = instance; 8 entries per foot at the very end of the CSR row.
+template <int kNEE>
+__global__ void __launch_bounds__(32) PhaseJac(const Plan P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
+                                               int* __restrict__ status, int nb, unsigned flags) {
+  const int lane = threadIdx.x, b = blockIdx.x * 32 + lane;
+  const bool live = b < nb;
   const ConstCol xs = TiledCol(XT, b, P.n + 1);
-  const PhaseUnit* u = P.phase_units + ui;
-  const int kind = __ldg(&u->kind);
-  double* J = jac + (size_t)b * P.nnz;
-  auto put = [&](int row, int col, double v) {
-    const int slot = __ldg(P.slot_of + (size_t)row * P.n + col);
-    if (live && slot >= 0) StoreOut(J + slot, v);
-  };
-  double unused[3];
-  if (kind == kPhaseTotal) {   // TotalDurationConstraint, total_duration_constraint.cc:48-72
+  for (int ui = 0; ui < P.n_phase_units; ++ui) {
+    const PhaseUnit* u = P.phase_units + ui;
     for (int e = 0; e < kNEE; ++e) {
       const PhaseSplineDef def = P.phase_defs[2 * e];
-      const int row = __ldg(&u->rows[e]);
+      const int row = __ldg(&u->rows[e]), slot0 = __ldg(&u->slot0[e]);
       double sum = 0.0;
-      for (int i = 0; i + 1 < def.n_phases; ++i) { sum += xs[def.sched0 + i]; if (want_jac) put(row, def.sched0 + i, 1.0); }
-      if (flags & 1u) GT[((size_t)blockIdx.y * P.m + row) * 32 + lane] = sum;
+      for (int i = 0; i + 1 < def.n_phases; ++i) {
+        sum += xs[def.sched0 + i];
+        if (live && (flags & 2u)) StoreOut(jac + (size_t)b * P.nnz + slot0 + i, 1.0);
+      }
+      if (flags & 1u) GT[((size_t)blockIdx.x * P.m + row) * 32 + lane] = sum;
       if (live && status && !(def.t_total - sum > 0.0)) atomicOr(status + b, 2);
-    }
-    return;
-  }
-  if (!want_jac) return;
-  const double tg = u->t;
-  double c[3];
-  EvalSpline<0>(P, P.samples + __ldg(&u->sample_lin), xs, c, unused, unused);
-  if (kind == kPhaseDyn) {   // dynamic_constraint.cc:91-113 with single_rigid_body_dynamics.cc:167-192
-    const int row0 = __ldg(&u->row0);
-    for (int e = 0; e < kNEE; ++e) {
-      const PhaseFull mo = EvalPhaseFull(P, 2 * e, tg, xs), fo = EvalPhaseFull(P, 2 * e + 1, tg, xs);
-      const double r[3] = {c[0] - mo.pos[0], c[1] - mo.pos[1], c[2] - mo.pos[2]};
-      double Cf[3][3], Cr[3][3];
-      CrossMatrix(fo.pos, Cf); CrossMatrix(r, Cr);
-      ForEachActiveNodeVar(mo, P.n, [&](int col, int dim, double w) {
-        for (int i = 0; i < 3; ++i) if (i != dim) put(row0 + i, col, Cf[i][dim] * w);
-      });
-      ForEachActiveNodeVar(fo, P.n, [&](int col, int dim, double w) {
-        for (int i = 0; i < 3; ++i) if (i != dim) put(row0 + i, col, Cr[i][dim] * w);
-        put(row0 + 3 + dim, col, -w);
-      });
-      const int sched0 = P.phase_defs[2 * e].sched0;
-      for (int ph = 0; ph + 1 < mo.n_phases; ++ph) {
-        double jf[3], jm[3];
-        DurationColumn(fo, ph, jf); DurationColumn(mo, ph, jm);
-        for (int i = 0; i < 3; ++i) {
-          const int d1 = (i == 0) ? 1 : 0, d2 = (i == 2) ? 1 : 2;
-          put(row0 + i, sched0 + ph, (Cr[i][d1] * jf[d1] + Cr[i][d2] * jf[d2]) + (Cf[i][d1] * jm[d1] + Cf[i][d2] * jm[d2]));
-          put(row0 + 3 + i, sched0 + ph, -jf[i]);
-        }
-      }
-    }
-  } else {   // range_of_motion_constraint.cc:83-109
-    double th[3];
-    EvalSpline<0>(P, P.samples + __ldg(&u->sample_ang), xs, th, unused, unused);
-    const Trig tr = MakeTrig(th);
-    double R[3][3]; RotationMatrix(tr, R);
-    for (int e = 0; e < kNEE; ++e) {
-      const int row0 = __ldg(&u->rows[e]);
-      const PhaseFull mo = EvalPhaseFull(P, 2 * e, tg, xs);
-      ForEachActiveNodeVar(mo, P.n, [&](int col, int dim, double w) {
-        for (int i = 0; i < 3; ++i) put(row0 + i, col, R[dim][i] * w);
-      });
-      const int sched0 = P.phase_defs[2 * e].sched0;
-      for (int ph = 0; ph + 1 < mo.n_phases; ++ph) {
-        double jm[3]; DurationColumn(mo, ph, jm);
-        for (int i = 0; i < 3; ++i) put(row0 + i, sched0 + ph, (R[0][i] * jm[0] + R[1][i] * jm[1]) + R[2][i] * jm[2]);
-      }
     }
   }
 }
@@ -1602,11 +1766,12 @@ template <int kNEE, bool kPhase>
 cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, int* status, const int* terrain_ids, int default_terrain,
                       int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
   const size_t row_bytes = (size_t)kLD * sizeof(double);
-  const int dyn_rows = 40 + 6 * kNEE, rom_rows = RomBlockRows(kNEE), node_rows = P.node_rows;
+  const int dyn_rows = 40 + 6 * kNEE, rom_rows = RomBlockRowsP(kNEE, kPhase), node_rows = P.node_rows;
   cudaError_t e = cudaSuccess;
 #if TWB_FUSED
   const int n_ctas = (P.n_dyn + kWarps - 1) / kWarps + (P.n_rom + kWarps - 1) / kWarps + (P.n_groups + kWarps - 1) / kWarps;
   if (n_ctas == 0) return cudaSuccess;
+  if (kPhase) return cudaErrorNotSupported;   // the fused experiment does not carry the PhaseSpline columns
   const int rows = std::max(std::max(P.n_dyn > 0 ? dyn_rows : 0, P.n_rom > 0 ? rom_rows : 0), P.n_groups > 0 ? node_rows : 0);
   const size_t smem = (size_t)kWarps * rows * row_bytes;
   if ((e = cudaFuncSetAttribute(EvalOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -1639,6 +1804,11 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     if ((e = LaunchK(DynOut<kNEE, kPhase>, dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), dim3(kDynWarps * 32), smem, a0, false, P, XT, GT, jac, status, nb, flags,
                      stage_off, stage_cap)) != cudaSuccess) return e;
     ++*count; TWB_MARK("DynOut", a0);
+    if (kPhase && (flags & 2u)) {   // PhaseSpline columns of the dynamic rows, beside the two output kernels
+      if ((e = cudaFuncSetAttribute(DynTailOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kNEE * kTailRows * row_bytes))) != cudaSuccess) return e;
+      DynTailOut<kNEE><<<dim3(P.n_dyn, tiles), kNEE * 32, (size_t)kNEE * kTailRows * row_bytes, a1>>>(P, XT, jac, nb);
+      ++*count; TWB_MARK("DynTailOut", a1);
+    }
   }
   return cudaSuccess;
 #endif
@@ -1657,6 +1827,11 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags, stage_off, stage_cap);
     ++*count; TWB_MARK("DynOut", a0);
+    if (kPhase && (flags & 2u)) {
+      if ((e = cudaFuncSetAttribute(DynTailOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kNEE * kTailRows * row_bytes))) != cudaSuccess) return e;
+      DynTailOut<kNEE><<<dim3(P.n_dyn, tiles), kNEE * 32, (size_t)kNEE * kTailRows * row_bytes, a0>>>(P, XT, jac, nb);
+      ++*count; TWB_MARK("DynTailOut", a0);
+    }
   }
   if (P.n_groups > 0) {
     const size_t smem = (size_t)kNodeWarps * node_rows * row_bytes;
@@ -1828,13 +2003,14 @@ int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, 
   return (int)cudaGetLastError();
 }
 
-int OutKernelsPerEval(const Plan& P) {
+int OutKernelsPerEval(const Plan& P, unsigned flags) {
+  const int dyn = (P.n_dyn > 0) * ((P.n_phase_defs > 0 && (flags & 2u)) ? 2 : 1);   // DynOut [+ DynTailOut]
 #if TWB_FUSED
-  return (P.n_dyn + P.n_rom + P.n_groups) > 0;
+  (void)dyn; return (P.n_dyn + P.n_rom + P.n_groups) > 0;
 #elif TWB_ROMNODE
-  return (P.n_dyn > 0) + ((P.n_rom + P.n_groups) > 0);
+  return dyn + ((P.n_rom + P.n_groups) > 0);
 #else
-  return (P.n_dyn > 0) + (P.n_rom > 0) + (P.n_groups > 0);
+  return dyn + (P.n_rom > 0) + (P.n_groups > 0);
 #endif
 }
 
@@ -1878,12 +2054,11 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
     cudaEventRecord(ev[1], aux0); cudaEventRecord(ev[2], aux1);
     cudaStreamWaitEvent(s, ev[1], 0); cudaStreamWaitEvent(s, ev[2], 0);
   }
-  if (out_flags && P.n_phase_units > 0) {   // after every output kernel: overwrites zeros they wrote
-    const dim3 grid((P.n_phase_units + 3) / 4, tiles);
+  if (out_flags && P.n_phase_units > 0) {   // TotalDurationConstraint rows
     switch (P.n_ee) {
-      case 1: PhaseJac<1><<<grid, 128, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
-      case 2: PhaseJac<2><<<grid, 128, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
-      default: PhaseJac<4><<<grid, 128, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      case 1: PhaseJac<1><<<tiles, 32, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      case 2: PhaseJac<2><<<tiles, 32, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      default: PhaseJac<4><<<tiles, 32, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
     }
     ++count; TWB_MARK("PhaseJac", s);
   }
