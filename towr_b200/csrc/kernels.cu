@@ -174,22 +174,32 @@ __device__ __forceinline__ double Pow4(double x) {
 // Active polynomial and local time of global time t: PhaseDurations::SetVariables (phase_durations.cc:79-100),
 // NodesVariablesPhaseBased::ConvertPhaseToPolyDurations (nodes_variables_phase_based.cc:78-89),
 // Spline::GetSegmentID / GetLocalTime (spline.cc:48-78) — same operations in the same order, per instance.
-struct PhaseLoc { int poly; double tl, T, last; };
+// One pass over the foot's phases (their polynomials are consecutive in Plan::phase_polys, every phase has at least one):
+// the sum of the optimised durations and the last phase's duration (phase_durations.cc:92-98), the phase the time falls
+// into (GetSegmentID over the phase durations), and the polynomial / local time (GetSegmentID / GetLocalTime over the
+// polynomial durations phase / n) — every accumulation in the reference's order.  d / n is a plain copy for n = 1 and an
+// exact scaling for n = 2 (both are the correctly rounded quotient); other n divide.
+struct PhaseLoc { int poly, cur; double tl, T, last; };
 __device__ __forceinline__ PhaseLoc LocatePhasePoly(const Plan& P, const PhaseSplineDef& def, double t, const ConstCol xs) {
-  double sum = 0.0;
-  for (int i = 0; i + 1 < def.n_phases; ++i) sum += xs[def.sched0 + i];
-  PhaseLoc o; o.last = def.t_total - sum; o.poly = def.n_polys - 1; o.tl = t; o.T = 0.0;
-  const double eps = 1e-10;
-  double acc = 0.0, tl_run = t; bool found = false;
-  for (int p = 0; p < def.n_polys; ++p) {
-    const PhasePoly* pp = P.phase_polys + def.poly0 + p;
-    const int ph = pp->phase;
-    const double d = (ph == def.n_phases - 1) ? o.last : xs[def.sched0 + ph];
-    const double Tp = d / (double)pp->n_in_phase;
-    acc += Tp;
-    if (!found) {
-      if (acc >= t - eps || p == def.n_polys - 1) { found = true; o.poly = p; o.T = Tp; o.tl = tl_run; }
-      tl_run -= Tp;
+  PhaseLoc o; o.poly = def.n_polys - 1; o.cur = def.n_phases - 1; o.tl = t; o.T = 0.0; o.last = def.t_total;
+  const double eps = 1e-10, thr = t - eps;
+  double sum = 0.0, acc = 0.0, acc_ph = 0.0, tl_run = t; bool found = false, found_ph = false;
+  const PhasePoly* pp = P.phase_polys + def.poly0;
+  int p = 0;
+  for (int ph = 0; ph < def.n_phases; ++ph) {
+    double d;
+    if (ph == def.n_phases - 1) { d = def.t_total - sum; o.last = d; }
+    else { d = xs[def.sched0 + ph]; sum += d; }
+    acc_ph += d;
+    if (!found_ph && acc_ph >= thr) { found_ph = true; o.cur = ph; }
+    const int n = pp[p].n_in_phase;
+    const double Tp = n == 1 ? d : n == 2 ? d * 0.5 : d / (double)n;
+    for (int k = 0; k < n; ++k, ++p) {
+      acc += Tp;
+      if (!found) {
+        if (acc >= thr || p == def.n_polys - 1) { found = true; o.poly = p; o.T = Tp; o.tl = tl_run; }
+        tl_run -= Tp;
+      }
     }
   }
   return o;
@@ -205,11 +215,12 @@ __device__ __forceinline__ void EvalSpline(const Plan& P, const SplineSample* __
     const PhaseLoc L = LocatePhasePoly(P, def, s.T, xs);
     const PhasePoly* pp = P.phase_polys + def.poly0 + L.poly;
     const double T = L.T, T2 = T * T, T3 = Pow3(T), t = L.tl, t2 = t * t, t3 = Pow3(t);   // std::pow(x, 2), std::pow(x, 3)
+    const double rT2 = 1.0 / T2, rT3 = 1.0 / T3;   // the quotients below: exact (Markstein) divisions seeded with these
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const double p0 = xs[pp->xi[d]], v0 = xs[pp->xi[3 + d]], p1 = xs[pp->xi[6 + d]], v1 = xs[pp->xi[9 + d]];
-      const double C = -(3 * (p0 - p1) + T * (2 * v0 + v1)) / T2;
-      const double D = (2 * (p0 - p1) + T * (v0 + v1)) / T3;
+      const double C = DivExact(-(3 * (p0 - p1) + T * (2 * v0 + v1)), T2, rT2);
+      const double D = DivExact(2 * (p0 - p1) + T * (v0 + v1), T3, rT3);
       pos[d] = ((p0 + t * v0) + t2 * C) + t3 * D;
       if (kWant == 2) vel[d] = (v0 + (2 * t) * C) + (3 * t2) * D;
       if (kWant >= 1) acc[d] = 2 * C + (6 * t) * D;
@@ -656,27 +667,25 @@ __device__ __forceinline__ PhaseFull EvalPhaseFull(const Plan& P, int def_index,
   const PhaseLoc L = LocatePhasePoly(P, def, tg, xs);
   PhaseFull o; o.pp = P.phase_polys + def.poly0 + L.poly; o.n_phases = def.n_phases; o.poly = L.poly;
   const double T = L.T, T2 = T * T, T3 = Pow3(T), T4 = Pow4(T), t = L.tl, t2 = t * t, t3 = Pow3(t);
-  o.B[0][0] = (2 * t3) / T3 - (3 * t2) / T2 + 1; o.B[0][1] = t - (2 * t2) / T + t3 / T2;
-  o.B[1][0] = (3 * t2) / T2 - (2 * t3) / T3;     o.B[1][1] = t3 / T2 - t2 / T;
+  // every x / T^k below is the correctly rounded quotient: DivExact seeded with the correctly rounded reciprocal
+  const double rT = 1.0 / T, rT2 = 1.0 / T2, rT3 = 1.0 / T3, rT4 = 1.0 / T4;
+  const double q23 = DivExact(2 * t3, T3, rT3), q32 = DivExact(3 * t2, T2, rT2), q32b = DivExact(t3, T2, rT2);
+  o.B[0][0] = q23 - q32 + 1; o.B[0][1] = t - DivExact(2 * t2, T, rT) + q32b;
+  o.B[1][0] = q32 - q23;     o.B[1][1] = q32b - DivExact(t2, T, rT);
   const double inner = 1. / (double)o.pp->n_in_phase, prev = (double)o.pp->k_in_phase;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double x0 = xs[o.pp->xi[d]], v0 = xs[o.pp->xi[3 + d]], x1 = xs[o.pp->xi[6 + d]], v1 = xs[o.pp->xi[9 + d]];
-    const double C = -(3 * (x0 - x1) + T * (2 * v0 + v1)) / T2;
-    const double D = (2 * (x0 - x1) + T * (v0 + v1)) / T3;
+    const double C = DivExact(-(3 * (x0 - x1) + T * (2 * v0 + v1)), T2, rT2);
+    const double D = DivExact(2 * (x0 - x1) + T * (v0 + v1), T3, rT3);
     o.pos[d] = ((x0 + t * v0) + t2 * C) + t3 * D;
     o.vel[d] = (v0 + (2 * t) * C) + (3 * t2) * D;
-    const double dT = (t3 * (v0 + v1)) / T3 - (t2 * (2 * v0 + v1)) / T2 - (3 * t3 * (2 * x0 - 2 * x1 + T * v0 + T * v1)) / T4 +
-                      (2 * t2 * (3 * x0 - 3 * x1 + 2 * T * v0 + T * v1)) / T3;
+    const double dT = DivExact(t3 * (v0 + v1), T3, rT3) - DivExact(t2 * (2 * v0 + v1), T2, rT2) -
+                      DivExact(3 * t3 * (2 * x0 - 2 * x1 + T * v0 + T * v1), T4, rT4) +
+                      DivExact(2 * t2 * (3 * x0 - 3 * x1 + 2 * T * v0 + T * v1), T3, rT3);
     o.dxdT[d] = inner * (dT - prev * o.vel[d]);
   }
-  // Spline::GetSegmentID over the PHASE durations
-  const double eps = 1e-10;
-  double acc = 0.0; o.cur = def.n_phases - 1; bool found = false;
-  for (int ph = 0; ph < def.n_phases; ++ph) {
-    acc += (ph == def.n_phases - 1) ? L.last : xs[def.sched0 + ph];
-    if (!found && acc >= tg - eps) { found = true; o.cur = ph; }
-  }
+  o.cur = L.cur;   // Spline::GetSegmentID over the PHASE durations
   return o;
 }
 // column `ph` of PhaseDurations::GetJacobianOfPos (phase_durations.cc:122-154)
@@ -1033,11 +1042,22 @@ __device__ __forceinline__ void StorePhasePairs(const double* t, const OutPair* 
                                                 const PhaseExt* __restrict__ exts, int n_pairs, double* __restrict__ out, size_t stride,
                                                 int q, int nc, int n_inst, int v_off, int dwin, int zrow, int tid, int n_threads) {
   const int n_items = 2 * n_pairs;
+  if (tid >= n_items) return;
+  int noff = 0, nd0 = 0, nd1 = 0; double nc0 = 0.0, nc1 = 0.0; uint2 nx = make_uint2(0u, 0u);
+  {
+    const int k = tid < n_pairs ? tid : tid - n_pairs;
+    LoadPair(pairs, coefs, k, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
+    nx = __ldg(reinterpret_cast<const uint2*>(exts) + k);
+  }
   for (int i = tid; i < n_items; i += n_threads) {
-    const int k = i < n_pairs ? i : i - n_pairs, jb = i < n_pairs ? 0 : 16;
-    int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
-    LoadPair(pairs, coefs, k, n_pairs, &off, &d0, &d1, &c0, &c1);
-    const uint2 x = __ldg(reinterpret_cast<const uint2*>(exts) + k);
+    const int jb = i < n_pairs ? 0 : 16;
+    const int off = noff, d0 = nd0, d1 = nd1; const double c0 = nc0, c1 = nc1; const uint2 x = nx;
+    const int ni = i + n_threads;   // the next entry of this thread is fetched under the stores of the current one
+    if (ni < n_items) {
+      const int k = ni < n_pairs ? ni : ni - n_pairs;
+      LoadPair(pairs, coefs, k, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
+      nx = __ldg(reinterpret_cast<const uint2*>(exts) + k);
+    }
     double* o = out + off + (size_t)jb * stride;
     const ElemForm f0 = Classify(t, x.x, d0, c0, v_off, dwin, zrow), f1 = Classify(t, x.y, d1, c1, v_off, dwin, zrow);
     if (n_inst == 32 && nc == 1 && !f0.slow && !f1.slow) {
