@@ -89,6 +89,32 @@ def test_hyq_gallop_gap_durations_config4():
     assert np.array_equal(out["g"][:, r0], ref["g"][:, r0])
 
 
+def test_durations_spread_widely_over_a_tile():
+    """The instances of one tile of 32 fall into polynomials / phases far apart (durations x U[0.35, 1.65]): the phase
+    elements then take the table form and the per-instance duration columns instead of the window form (device_tables.h)."""
+    from towr_b200.configs import _renormalise
+    for name, B in (("hyq_gallop_gap", 64), ("biped_walk_stairs", 37)):
+        f = tb.make_formulation(name)
+        f.params_.OptimizePhaseDurations()
+        spec = f.to_spec(); p = tb.Problem(spec)
+        X = synthetic_iterates(p, B)
+        x0 = p.GetVariableValues()
+        rng = np.random.default_rng(99)
+        for sname, start, count in p.variable_sets():
+            if sname.startswith("ee-schedule"):
+                X[:, start:start + count] = _renormalise(p, sname, x0[start:start + count] * rng.uniform(0.35, 1.65, (B, count)))
+        out = p.batch(B).eval_host(X)
+        ref = oracle_lib.batch_eval(spec, X)
+        assert ref["rc"] == 0
+        bad_j, strict_j, worst_j = check_rows(out["jac"], ref["jac"], p.row_ptr())
+        bad_g, strict_g, worst_g = check_sets(out["g"], ref["g"], p.constraint_sets())
+        PARITY_LOG.append({"case": name + " (durations x U[0.35, 1.65])", "B": B, "n": p.n, "m": p.m, "nnz": p.nnz,
+                           "jac": {"violations": bad_j, "worst_err_over_tol": worst_j, "strict_miss_fraction": strict_j},
+                           "g": {"violations": bad_g, "worst_err_over_tol": worst_g, "strict_miss_fraction": strict_g}})
+        assert bad_j == 0 and bad_g == 0, (name, bad_j, worst_j, bad_g, worst_g)
+        assert not out["status"].any()
+
+
 def test_durations_other_robots_and_terrains():
     f = tb.make_formulation("hopper"); f.params_.OptimizePhaseDurations()
     spec = f.to_spec(); p = tb.Problem(spec)

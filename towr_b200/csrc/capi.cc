@@ -74,6 +74,7 @@ struct twb_batch {
   float* d_gmap = nullptr;        // elevation layer of TWB_GRID_MAP (optional)
   double* d_XT = nullptr;         // [ld/32][n+1][32] instance-tiled iterates; row n == 0
   double* d_GT = nullptr;         // [ld/32][m][32] instance-tiled constraint values (staging of g)
+  double* d_FS = nullptr;         // [ld/32][n_dyn][6 n_ee][32] feet positions / forces per dynamic sample (optimised durations only)
   // staging for the host-pointer variant
   double *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_cost = nullptr, *d_grad = nullptr;
   int* d_status = nullptr;
@@ -222,6 +223,11 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
     return CudaFail(e, "state allocation");
   }
   b->d_GT = reinterpret_cast<double*>(reinterpret_cast<char*>(b->d_XT) + xt_padded);
+  if (b->plan.n_phase_defs > 0 && b->plan.n_dyn > 0 &&
+      (e = cudaMalloc(reinterpret_cast<void**>(&b->d_FS), (size_t)b->plan.n_dyn * 6 * b->plan.n_ee * b->ld * sizeof(double))) != cudaSuccess) {
+    twb_batch_destroy(b);
+    return CudaFail(e, "state allocation");
+  }
   {
     const char* v = std::getenv("TWB_L2_PERSIST");
     cudaDeviceProp prop{};
@@ -259,7 +265,7 @@ void twb_batch_destroy(twb_batch* b) {
   if (b->use_l2_window) cudaCtxResetPersistingL2Cache();   // lines of XT / GT must not stay pinned in the L2 after the batch is gone
   for (void* p : b->owned) cudaFree(p);
   for (auto& sc : b->scratch) cudaFree(sc.first);
-  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT);   // (d_GT is part of d_XT's allocation)
+  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT); cudaFree(b->d_FS);   // (d_GT is part of d_XT's allocation)
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
@@ -560,7 +566,7 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   if (f.has_cost && (flags & TWB_EVAL_COST)) kflags |= TWB_EVAL_COST;
   int launches = 0;
   twb::SetL2Window(b->use_l2_window ? &b->l2_window : nullptr);
-  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
+  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, b->d_FS, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
                            kflags, static_cast<cudaStream_t>(stream), b->aux0, b->aux1, b->ev.data(), &launches);
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
   b->launches_last = launches;
@@ -607,6 +613,7 @@ int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac, d
     cudaEventRecord(b->ev_chunk[2 * c], b->s_in);
     cudaStreamWaitEvent(s, b->ev_chunk[2 * c], 0);
     int rc = twb::LaunchEval(b->plan, b->d_x + off * f.n, b->d_XT + tile0 * (size_t)(f.n + 1) * 32, b->d_GT + tile0 * (size_t)std::max(f.m, 1) * 32,
+                             b->d_FS ? b->d_FS + tile0 * (size_t)b->plan.n_dyn * 6 * b->plan.n_ee * 32 : nullptr,
                              (flags & TWB_EVAL_G) ? b->d_g + off * f.m : nullptr, (flags & TWB_EVAL_JAC) ? b->d_jac + off * f.nnz : nullptr,
                              has_cost ? b->d_cost + off : nullptr, has_cost ? b->d_grad + off * f.n : nullptr, b->d_status + off,
                              b->d_terrain ? b->d_terrain + off : nullptr, f.spec.terrain, (int)nb, kflags, s, b->aux0, b->aux1, b->ev.data(), &launches);

@@ -91,7 +91,13 @@ constexpr int kMaxClasses = 4;
 enum PhaseElemKind : uint32_t { kElemPlain = 0, kElemNode = 1, kElemDuration = 2 };
 struct PhaseExt { uint32_t e0, e1; };
 constexpr int kInfoRows = 12;
-constexpr int kDynDurWin = 3, kRomDurWin = 2;   // duration columns finished per instance (window form) in DynTailOut / RomBody
+#ifndef TWB_DYN_DURWIN
+#define TWB_DYN_DURWIN 2
+#endif
+#ifndef TWB_ROM_DURWIN
+#define TWB_ROM_DURWIN 2
+#endif
+constexpr int kDynDurWin = TWB_DYN_DURWIN, kRomDurWin = TWB_ROM_DURWIN;   // duration columns finished per instance (window form) in DynTailOut / RomBody
 // state rows of one foot in the DynTailOut kernel: 0: 1 | 1..3: f_e | 4..6: c - p_e | 7..18: info block of ee-motion_e |
 // 19..30: info block of ee-force_e | 31..36: U | 37..54: X   (duration columns of the sample's 6 rows)
 constexpr int kTailRows = 7 + 2 * kInfoRows + 6 + 6 * kDynDurWin;

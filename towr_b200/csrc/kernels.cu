@@ -308,9 +308,11 @@ __device__ __forceinline__ void CrossMul(const double w[3], const double A[3][3]
 //   sum of forces, per-foot force and lever arm for the other blocks (:103-121, :167-192).
 // Sk: local state rows 1.. (Sk[0..2] sum f, Sk[3..38] base-ang block, Sk[39 + 6e ..] f_e, c - p_e);
 // gk: the 6 constraint values
+// feet: with optimised durations and a Jacobian evaluation the DynTailOut kernel has already evaluated the feet's PhaseSplines
+// of this sample; their values come from its scratch rows (6 per foot: p_e, f_e; lane = instance) instead of a second evaluation
 template <int kNEE, bool kPhase>
 __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSample* __restrict__ sp, const ConstCol xs,
-                                            const Col Sk, const Col gk) {
+                                            const Col Sk, const Col gk, const double* __restrict__ feet) {
   double c[3], cdd[3], th[3], thd[3], thdd[3], unused[3];
   EvalSpline<1>(P, sp + 0, xs, c, unused, cdd);
   EvalSpline<2>(P, sp + 1, xs, th, thd, thdd);
@@ -320,8 +322,13 @@ __device__ __forceinline__ void DynamicUnit(const Plan& P, int k, const SplineSa
 #pragma unroll
   for (int e = 0; e < kNEE; ++e) {
     double pe[3], f[3];
-    EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
-    EvalSpline<0, kPhase>(P, sp + 2 + kNEE + e, xs, f, unused, unused);
+    if (kPhase && feet) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { pe[d] = __ldcg(feet + (e * 6 + d) * 32); f[d] = __ldcg(feet + (e * 6 + 3 + d) * 32); }
+    } else {
+      EvalSpline<0, kPhase>(P, sp + 2 + e, xs, pe, unused, unused);
+      EvalSpline<0, kPhase>(P, sp + 2 + kNEE + e, xs, f, unused, unused);
+    }
     const double r[3] = {c[0] - pe[0], c[1] - pe[1], c[2] - pe[2]};
     tau[0] += f[1] * r[2] - f[2] * r[1];
     tau[1] += f[2] * r[0] - f[0] * r[2];
@@ -1062,7 +1069,10 @@ __device__ __forceinline__ void StorePhasePairs(const double* t, const OutPair* 
     const ElemForm f0 = Classify(t, x.x, d0, c0, v_off, dwin, zrow), f1 = Classify(t, x.y, d1, c1, v_off, dwin, zrow);
     if (n_inst == 32 && nc == 1 && !f0.slow && !f1.slow) {
       const double* r0 = t + f0.d * kLD + jb; const double* r1 = t + f1.d * kLD + jb;
-      if ((f0.w1 | f1.w1) == 0) {   // both elements are ordinary for this tile: the pair loop of StorePairs
+      if ((f0.w1 | f1.w1) == 0 && f0.c == 0.0 && f1.c == 0.0) {   // zero for every instance of the tile (most phase elements)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { StoreOut2(o, 0.0, 0.0); o += stride; }
+      } else if ((f0.w1 | f1.w1) == 0) {   // both elements are ordinary for this tile: the pair loop of StorePairs
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           const double2 a = *reinterpret_cast<const double2*>(r0 + j), b = *reinterpret_cast<const double2*>(r1 + j);
@@ -1229,7 +1239,8 @@ __device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int l
 // several KB of contiguous CSR values per instance (the samples' rows are adjacent).
 template <int kNEE, bool kPhase>
 __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
-                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st) {
+                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st,
+                                        const double* __restrict__ FS = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kDynWarps + warp, b0 = tile * 32;
   constexpr int n_rows = 40 + 6 * kNEE;   // local rows: 1 | 3 | 36 | 6 per foot; the 6 constraint values go straight into GT (coalesced)
@@ -1239,7 +1250,8 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
     t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE   // (timing experiment: store phase only)
     DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD},
-                              Col{GT + ((size_t)b0 * P.m + (size_t)__ldg(&u->g_row0) * 32) + lane, 32});
+                              Col{GT + ((size_t)b0 * P.m + (size_t)__ldg(&u->g_row0) * 32) + lane, 32},
+                              FS ? FS + (((size_t)tile * P.n_dyn + k) * (6 * kNEE)) * 32 + lane : nullptr);
     FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
 #endif
   }
@@ -1415,8 +1427,12 @@ __global__ void __launch_bounds__(128) CostKernel(const Plan P, const double* __
 // into the foot's state block (device_tables.h: kTailRows); then all threads of the CTA walk the sample's list of phase
 // elements — the same coalesced whole-sector pair loop as every other Jacobian value.  (Until round 2 these entries were
 // scattered by lane = instance 8-byte stores over rows of zeros: 1.0 of config 4's 1.26 ms.)
+#ifndef TWB_TAIL_CTAS
+#define TWB_TAIL_CTAS 4   // resident CTAs per SM the DynTailOut kernel is compiled for (128 registers; 49 state rows per foot = 53 KB per CTA)
+#endif
 template <int kNEE>
-__global__ void __launch_bounds__(kNEE * 32) DynTailOut(const Plan P, const double* __restrict__ XT, double* __restrict__ jac, int nb) {
+__global__ void __launch_bounds__(kNEE * 32, TWB_TAIL_CTAS) DynTailOut(const Plan P, const double* __restrict__ XT, double* __restrict__ jac, int nb,
+                                                        double* __restrict__ FS) {
   extern __shared__ __align__(16) double out_smem[];
   const int lane = threadIdx.x & 31, e = threadIdx.x >> 5, k = blockIdx.x, b0 = blockIdx.y * 32;
   double* t = out_smem + (size_t)e * kTailRows * kLD;
@@ -1431,6 +1447,11 @@ __global__ void __launch_bounds__(kNEE * 32) DynTailOut(const Plan P, const doub
   t[lane] = 1.0;
 #pragma unroll
   for (int d = 0; d < 3; ++d) { t[(1 + d) * kLD + lane] = fo.pos[d]; t[(4 + d) * kLD + lane] = r[d]; }
+  if (FS) {   // p_e, f_e of this sample for the DynOut kernel that follows on the same stream
+    double* fs = FS + (((size_t)blockIdx.y * P.n_dyn + k) * (6 * kNEE) + 6 * e) * 32 + lane;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { __stcg(fs + d * 32, mo.pos[d]); __stcg(fs + (3 + d) * 32, fo.pos[d]); }
+  }
   StorePhaseInfo(mo, t, 7, lane);
   StorePhaseInfo(fo, t, 7 + kInfoRows, lane);
   double Cf[3][3], Cr[3][3];
@@ -1722,9 +1743,9 @@ __global__ void __launch_bounds__(kWarps * 32, TWB_CTAS) EvalOut(const Plan P, c
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                            double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags,
-                                                           int stage_off, int stage_cap) {
+                                                           int stage_off, int stage_cap, const double* __restrict__ FS) {
   extern __shared__ __align__(16) double out_smem[];
-  DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, Stage{out_smem + stage_off, stage_cap});
+  DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, Stage{out_smem + stage_off, stage_cap}, FS);
 #if TWB_TMA
   if ((threadIdx.x & 31) == 0) BulkWaitAll();   // the staging rows stay allocated until the last copy has left
 #endif
@@ -1783,11 +1804,36 @@ cudaError_t LaunchK(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem
 
 // s: caller's stream (after TransposeIn); a0, a1: auxiliary streams already waiting on the transposition
 template <int kNEE, bool kPhase>
-cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, int* status, const int* terrain_ids, int default_terrain,
+cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* FS, double* jac, int* status, const int* terrain_ids, int default_terrain,
                       int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
   const size_t row_bytes = (size_t)kLD * sizeof(double);
   const int dyn_rows = 40 + 6 * kNEE, rom_rows = RomBlockRowsP(kNEE, kPhase), node_rows = P.node_rows;
   cudaError_t e = cudaSuccess;
+#if !TWB_FUSED
+  // the dynamic rows on stream a0: with optimised durations and a Jacobian evaluation first DynTailOut (the PhaseSpline columns; it
+  // leaves the feet's positions and forces in FS), then DynOut (base columns and the constraint values)
+  auto launch_dyn = [&]() -> cudaError_t {
+    if (P.n_dyn <= 0) return cudaSuccess;
+    cudaError_t err;
+    const bool tail = kPhase && (flags & 2u);
+    if (tail) {
+      const size_t tail_smem = (size_t)kNEE * kTailRows * row_bytes;
+      if ((err = cudaFuncSetAttribute(DynTailOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem)) != cudaSuccess) return err;
+      DynTailOut<kNEE><<<dim3(P.n_dyn, tiles), kNEE * 32, tail_smem, a0>>>(P, XT, jac, nb, FS);
+      ++*count; TWB_MARK("DynTailOut", a0);
+    }
+    const size_t state_bytes = (size_t)kDynWarps * dyn_rows * row_bytes;
+    const int stage_off = (int)(state_bytes / sizeof(double));
+    int stage_cap = TWB_TMA_DYN ? P.stage_dyn : 0;
+    if (state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 200 * 1024) stage_cap = 0;
+    const size_t smem = state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
+    if ((err = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    if ((err = LaunchK(DynOut<kNEE, kPhase>, dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), dim3(kDynWarps * 32), smem, a0, false, P, XT, GT, jac, status, nb, flags,
+                       stage_off, stage_cap, (const double*)(tail ? FS : nullptr))) != cudaSuccess) return err;
+    ++*count; TWB_MARK("DynOut", a0);
+    return cudaSuccess;
+  };
+#endif
 #if TWB_FUSED
   const int n_ctas = (P.n_dyn + kWarps - 1) / kWarps + (P.n_rom + kWarps - 1) / kWarps + (P.n_groups + kWarps - 1) / kWarps;
   if (n_ctas == 0) return cudaSuccess;
@@ -1814,22 +1860,7 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
       ++*count; TWB_MARK("RomNodeOut", s);
     }
   }
-  if (P.n_dyn > 0) {
-    const size_t state_bytes = (size_t)kDynWarps * dyn_rows * row_bytes;
-    const int stage_off = (int)(state_bytes / sizeof(double));
-    int stage_cap = TWB_TMA_DYN ? P.stage_dyn : 0;
-    if (state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 200 * 1024) stage_cap = 0;
-    const size_t smem = state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
-    if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    if ((e = LaunchK(DynOut<kNEE, kPhase>, dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), dim3(kDynWarps * 32), smem, a0, false, P, XT, GT, jac, status, nb, flags,
-                     stage_off, stage_cap)) != cudaSuccess) return e;
-    ++*count; TWB_MARK("DynOut", a0);
-    if (kPhase && (flags & 2u)) {   // PhaseSpline columns of the dynamic rows, beside the two output kernels
-      if ((e = cudaFuncSetAttribute(DynTailOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kNEE * kTailRows * row_bytes))) != cudaSuccess) return e;
-      DynTailOut<kNEE><<<dim3(P.n_dyn, tiles), kNEE * 32, (size_t)kNEE * kTailRows * row_bytes, a1>>>(P, XT, jac, nb);
-      ++*count; TWB_MARK("DynTailOut", a1);
-    }
-  }
+  if ((e = launch_dyn()) != cudaSuccess) return e;
   return cudaSuccess;
 #endif
   if (P.n_rom > 0) {
@@ -1838,21 +1869,7 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* jac, 
     RomOut<kNEE, kPhase><<<dim3((P.n_rom + kRomWarps - 1) / kRomWarps, tiles), kRomWarps * 32, smem, s>>>(P, XT, GT, jac, status, nb, flags);
     ++*count; TWB_MARK("RomOut", s);
   }
-  if (P.n_dyn > 0) {
-    const size_t state_bytes = (size_t)kDynWarps * dyn_rows * row_bytes;
-    const int stage_off = (int)(state_bytes / sizeof(double));
-    int stage_cap = TWB_TMA_DYN ? P.stage_dyn : 0;
-    if (state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double) > 200 * 1024) stage_cap = 0;
-    const size_t smem = state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
-    if ((e = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    DynOut<kNEE, kPhase><<<dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), kDynWarps * 32, smem, a0>>>(P, XT, GT, jac, status, nb, flags, stage_off, stage_cap);
-    ++*count; TWB_MARK("DynOut", a0);
-    if (kPhase && (flags & 2u)) {
-      if ((e = cudaFuncSetAttribute(DynTailOut<kNEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kNEE * kTailRows * row_bytes))) != cudaSuccess) return e;
-      DynTailOut<kNEE><<<dim3(P.n_dyn, tiles), kNEE * 32, (size_t)kNEE * kTailRows * row_bytes, a0>>>(P, XT, jac, nb);
-      ++*count; TWB_MARK("DynTailOut", a0);
-    }
-  }
+  if ((e = launch_dyn()) != cudaSuccess) return e;
   if (P.n_groups > 0) {
     const size_t smem = (size_t)kNodeWarps * node_rows * row_bytes;
     if ((e = cudaFuncSetAttribute(NodeOut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -2038,7 +2055,7 @@ int OutKernelsPerEval(const Plan& P, unsigned flags) {
 // instance of x / g / jac).  Streams: `s` carries TransposeIn -> [out kernels] -> TransposeOut; with separate
 // out kernels DynOut / NodeOut (and the CostKernel) run beside RomOut on aux0 / aux1 after the transposition
 // (ev[0]) and are joined back into `s` (ev[1], ev[2]) before TransposeOut.
-int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g, double* jac, double* cost, double* grad,
+int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* FS, double* g, double* jac, double* cost, double* grad,
                int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
                cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches) {
   if (nb <= 0) return 0;
@@ -2056,12 +2073,12 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* g
   if (out_flags) {
     const bool phase = P.n_phase_defs > 0;
     switch (P.n_ee) {
-      case 1: e = phase ? LaunchOut<1, true>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
-                       : LaunchOut<1, false>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
-      case 2: e = phase ? LaunchOut<2, true>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
-                       : LaunchOut<2, false>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
-      case 4: e = phase ? LaunchOut<4, true>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
-                       : LaunchOut<4, false>(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 1: e = phase ? LaunchOut<1, true>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<1, false>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 2: e = phase ? LaunchOut<2, true>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<2, false>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 4: e = phase ? LaunchOut<4, true>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<4, false>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
       default: return (int)cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return (int)e;
