@@ -212,7 +212,9 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
   if (const char* v = std::getenv("TWB_E2E_CHUNK")) b->e2e_chunk = std::max(32, std::atoi(v));
-  b->ld = ((size_t)batch_size + 31) & ~(size_t)31;
+  // whole groups of nc interleaved tiles (kernels.cu: TileInstance); nc = 1 unless the Jacobian row length is not a multiple of 4
+  const size_t group = 32 * (size_t)std::max(b->plan.nc_jac, 1);
+  b->ld = ((size_t)batch_size + group - 1) / group * group;
   const size_t xt_bytes = (size_t)(b->plan.n + 1) * b->ld * sizeof(double);
   // XT and GT live in ONE allocation, so that one L2 access-policy window can cover both staging matrices (TWB_L2_PERSIST=1;
   // measured, profiles/README.md experiment 39: marking them persisting makes the step SLOWER, 175 instead of 139 us — off)
@@ -593,7 +595,8 @@ int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac, d
   // Pipelined in chunks of whole instance tiles: the H2D copy of chunk c+1 (copy-in stream), the kernels of chunk c
   // (b->stream + the two auxiliary streams) and the D2H copies of chunk c-1 (copy-out stream) overlap, so the call costs
   // what the larger of the two PCIe directions costs (the D2H of g + jac: 524 MB on config 2) plus one chunk of latency.
-  const size_t chunk = ((size_t)std::max(32, b->e2e_chunk) + 31) & ~(size_t)31;
+  const size_t group = 32 * (size_t)std::max(b->plan.nc_jac, 1);   // chunks hold whole groups of interleaved tiles
+  const size_t chunk = ((size_t)std::max(32, b->e2e_chunk) + group - 1) / group * group;
   const size_t n_chunks = (B + chunk - 1) / chunk;
   if (!b->s_in && ((e = cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
                    (e = cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking)) != cudaSuccess)) return CudaFail(e, "cudaStreamCreate");

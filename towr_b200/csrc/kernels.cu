@@ -84,9 +84,6 @@ namespace {
 #ifndef TWB_ST256
 #define TWB_ST256 0     // 1: thread = whole sector (two consecutive pairs of the list), 256-bit stores, items of 8 instances
 #endif
-#ifndef TWB_MERGE_CLASSES
-#define TWB_MERGE_CLASSES 0   // 1: the pair lists of all alignment classes (odd row length) as one item space (StorePairsClasses); measured slower on config 3 (126 vs 113 us)
-#endif
 #ifndef TWB_TMA_DYN
 #define TWB_TMA_DYN TWB_TMA   // per-kernel switches of the TMA store path (tuning)
 #endif
@@ -762,30 +759,49 @@ __device__ __forceinline__ void CrossMatrix(const double v[3], double C[3][3]) {
 }
 
 // ---- kernels ---------------------------------------------------------------------
-// instance b of the tiled iterate matrix with `rows` rows: element r lives at base[((b/32)*rows + r)*32 + b%32]
-__device__ __forceinline__ ConstCol TiledCol(const double* base, int b, int rows) {
-  return ConstCol{base + ((size_t)(b >> 5) * rows) * 32 + (b & 31)};
+// ---- instances <-> (tile, lane) ----------------------------------------------------------------------------------------
+// A tile is the set of 32 instances one warp serves (lane = instance).  When the Jacobian-value row length is not a multiple
+// of 4 doubles, the rows of consecutive instances start at different offsets inside their 32-byte sectors: nc = 2 or 4
+// alignment classes, instance b belongs to class b mod nc.  The tiles are then INTERLEAVED: tile nc G + q holds the
+// instances 32 nc G + nc lane + q, i.e. 32 instances of ONE class, so that a whole tile is written from one pair list
+// (one sector layout) with the same store loop as an aligned problem — the instance stride is nc rows.  nc = 1: tile t =
+// instances 32 t .. 32 t + 31.  XT, GT and the scratch matrices are indexed by (tile, lane).
+__device__ __forceinline__ int TileInstance(int nc, int tile, int lane) {
+  return nc == 1 ? tile * 32 + lane : (tile / nc) * (32 * nc) + lane * nc + tile % nc;
+}
+__device__ __forceinline__ int TileCount(int nc, int tile, int nb) {   // valid lanes of the tile (a prefix)
+  const int first = TileInstance(nc, tile, 0);
+  return first >= nb ? 0 : min(32, (nb - first + nc - 1) / nc);
+}
+// column (tile, lane) of a tiled matrix with `rows` rows: element r lives at base[(tile * rows + r) * 32 + lane]
+__device__ __forceinline__ ConstCol TileCol(const double* base, int tile, int lane, int rows) {
+  return ConstCol{base + ((size_t)tile * rows) * 32 + lane};
+}
+// the same for instance b (kernels that are not organised by tiles)
+__device__ __forceinline__ ConstCol TiledCol(const double* base, int b, int rows, int nc) {
+  const int grp = b / (32 * nc), rem = b - grp * (32 * nc);
+  return TileCol(base, grp * nc + rem % nc, rem / nc, rows);
 }
 
 // x[b][i] -> XT[b/32][i][b%32]: 32x32 tiles through shared memory, coalesced on both sides; clears status
 __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x, double* __restrict__ XT,
-                                                   int* __restrict__ status, int n, int nb) {
+                                                   int* __restrict__ status, int n, int nb, int nc) {
   __shared__ double tile[32][33];
 #if TWB_PDL
   asm volatile("griddepcontrol.launch_dependents;");   // the dependent output kernel may become resident while this grid drains
 #endif
-  const int i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
-  if (status && blockIdx.x == 0 && threadIdx.y == 0 && b0 + threadIdx.x < nb) status[b0 + threadIdx.x] = 0;
+  const int i0 = blockIdx.x * 32;
+  if (status && blockIdx.x == 0 && threadIdx.y == 0 && TileInstance(nc, blockIdx.y, threadIdx.x) < nb) status[TileInstance(nc, blockIdx.y, threadIdx.x)] = 0;
 #pragma unroll
   for (int r = threadIdx.y; r < 32; r += 8) {
-    const int b = b0 + r, i = i0 + threadIdx.x;
+    const int b = TileInstance(nc, blockIdx.y, r), i = i0 + threadIdx.x;
     if (b < nb && i < n) tile[r][threadIdx.x] = __ldcs(x + (size_t)b * n + i);
   }
   __syncthreads();
   double* dst = XT + ((size_t)blockIdx.y * (n + 1)) * 32;
 #pragma unroll
   for (int r = threadIdx.y; r < 32; r += 8) {
-    const int i = i0 + r, b = b0 + threadIdx.x;
+    const int i = i0 + r, b = TileInstance(nc, blockIdx.y, threadIdx.x);
 #if TWB_XT_EVICT_LAST
     if (b < nb && i < n) {
       unsigned long long pol;
@@ -804,9 +820,9 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
 // on config 2, 9 % of the step's DRAM writes).  Both matrices are rewritten by the next evaluation before they are read.
 __device__ __forceinline__ void DiscardLine(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ GT, double* __restrict__ g, int m, int nb,
-                                                    const double* __restrict__ XT, int n) {
+                                                    const double* __restrict__ XT, int n, int nc) {
   __shared__ double tile[32][33];
-  const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int r0 = blockIdx.x * 32;
   const double* src = GT + ((size_t)blockIdx.y * m) * 32;
 #pragma unroll
   for (int q = threadIdx.y; q < 32; q += 8) {
@@ -828,7 +844,7 @@ __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ G
     if (tid < 64) {                       // the 32 GT rows of this CTA: two 128-byte lines each
       const int r = r0 + (tid >> 1);
       if (r < m) DiscardLine(src + (size_t)r * 32 + (tid & 1) * 16);
-    } else if (XT && tid < 128 && b0 + 32 <= nb) {   // XT rows of this tile, 32 per CTA of the tile (CTAs wrap around when m < n); a ragged last tile keeps its lines: its padded lanes are never rewritten
+    } else if (XT && tid < 128 && TileCount(nc, blockIdx.y, nb) == 32) {   // XT rows of this tile, 32 per CTA of the tile (CTAs wrap around when m < n); a ragged last tile keeps its lines: its padded lanes are never rewritten
       const double* xt = XT + ((size_t)blockIdx.y * (n + 1)) * 32;
       for (int r = r0 + ((tid - 64) >> 1); r < n; r += gridDim.x * 32) DiscardLine(xt + (size_t)r * 32 + (tid & 1) * 16);
     }
@@ -836,15 +852,15 @@ __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ G
 #endif
 #pragma unroll
   for (int q = threadIdx.y; q < 32; q += 8) {
-    const int b = b0 + q, r = r0 + threadIdx.x;
+    const int b = TileInstance(nc, blockIdx.y, q), r = r0 + threadIdx.x;
     if (b < nb && r < m) StoreOut(g + (size_t)b * m + r, tile[threadIdx.x][q]);
   }
 }
 
 // ---- CTA-collective output: threads switch from "instance" to "pair of output elements" ----------------------
-// out[j][off + h] = t[d_h][j] * c_h for the instances j = j0, j0 + jstep, .. < n_inst of the tile; `t` is the CTA's
-// shared memory (all state blocks), `out` points at element 0 of the tile's first instance, `stride` is the row length
-// (nnz).  The list holds whole 32-byte sectors (two consecutive pairs = two adjacent lanes); thread `tid` of
+// out[j][off + h] = t[d_h][j] * c_h for the lanes j < n_inst of the tile; `t` is the CTA's shared memory (all state
+// blocks), `out` points at element 0 of the tile's first instance, `stride` is the distance between the rows of consecutive
+// lanes (nc rows of nnz elements).  The list holds whole 32-byte sectors (two consecutive pairs = two adjacent lanes); thread `tid` of
 // `n_threads` takes the pairs tid, tid + n_threads, ..
 __device__ __forceinline__ void LoadPair(const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs, int i, int n,
                                          int* off, int* d0, int* d1, double* c0, double* c1) {
@@ -855,10 +871,10 @@ __device__ __forceinline__ void LoadPair(const OutPair* __restrict__ pairs, cons
   }
 }
 __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
-                                           int n_pairs, double* __restrict__ out, size_t stride, int j0, int jstep, int n_inst,
+                                           int n_pairs, double* __restrict__ out, size_t stride, int n_inst,
                                            int tid, int n_threads) {
 #if TWB_ST256
-  if (n_inst == 32 && jstep == 1 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 && (stride & 3) == 0) {
+  if (n_inst == 32 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 && (stride & 3) == 0) {
     // thread = whole 32-byte sector (the list holds two consecutive pairs per sector), item = (sector, quarter of the tile's
     // instances): one 256-bit store per instance, a warp instruction covers 1 KB of the instance's row
     const int n_sec = n_pairs >> 1, n_items = 4 * n_sec;
@@ -882,7 +898,7 @@ __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __res
     return;
   }
 #endif
-  if (n_inst == 32 && jstep == 1) {
+  if (n_inst == 32) {
     // Work items are (pair, half of the tile's instances): twice as many items as pairs keep the threads of a CTA
     // evenly busy when a list is only 1 - 2 pairs per thread long.  Items 0 .. n_pairs-1 are the first 16 instances,
     // n_pairs .. 2 n_pairs-1 the last 16, so consecutive threads still hold consecutive pairs (whole sectors).
@@ -916,18 +932,8 @@ __device__ __forceinline__ void StorePairs(const double* t, const OutPair* __res
     LoadPair(pairs, coefs, i + n_threads, n_pairs, &noff, &nd0, &nd1, &nc0, &nc1);
     double* o = out + off;
     const double* r0 = t + d0 * kLD; const double* r1 = t + d1 * kLD;
-    if (n_inst == 32 && jstep == 2) {   // rows of two alignment classes: every other instance
-      o += (size_t)j0 * stride;
-#pragma unroll 8
-      for (int j = 0; j < 32; j += 2) { StoreOut2(o, r0[j0 + j] * c0, r1[j0 + j] * c1); o += 2 * stride; }
-    } else if (n_inst == 32 && jstep == 4) {   // four alignment classes: every fourth instance
-      o += (size_t)j0 * stride;
-#pragma unroll 8
-      for (int j = 0; j < 32; j += 4) { StoreOut2(o, r0[j0 + j] * c0, r1[j0 + j] * c1); o += 4 * stride; }
-    } else {
 #pragma unroll 4
-      for (int j = j0; j < n_inst; j += jstep) StoreOut2(o + j * stride, r0[j] * c0, r1[j] * c1);
-    }
+    for (int j = 0; j < n_inst; ++j) StoreOut2(o + j * stride, r0[j] * c0, r1[j] * c1);   // ragged last tile
     off = noff; d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1;
   }
 }
@@ -1047,7 +1053,7 @@ __device__ __forceinline__ double FormVal(const double* t, int j, const ElemForm
 // the pair loop for sectors that hold phase elements: item = (pair, half of the tile's instances) as in StorePairs
 __device__ __forceinline__ void StorePhasePairs(const double* t, const OutPair* __restrict__ pairs, const OutCoef* __restrict__ coefs,
                                                 const PhaseExt* __restrict__ exts, int n_pairs, double* __restrict__ out, size_t stride,
-                                                int q, int nc, int n_inst, int v_off, int dwin, int zrow, int tid, int n_threads) {
+                                                int n_inst, int v_off, int dwin, int zrow, int tid, int n_threads) {
   const int n_items = 2 * n_pairs;
   if (tid >= n_items) return;
   int noff = 0, nd0 = 0, nd1 = 0; double nc0 = 0.0, nc1 = 0.0; uint2 nx = make_uint2(0u, 0u);
@@ -1067,7 +1073,7 @@ __device__ __forceinline__ void StorePhasePairs(const double* t, const OutPair* 
     }
     double* o = out + off + (size_t)jb * stride;
     const ElemForm f0 = Classify(t, x.x, d0, c0, v_off, dwin, zrow), f1 = Classify(t, x.y, d1, c1, v_off, dwin, zrow);
-    if (n_inst == 32 && nc == 1 && !f0.slow && !f1.slow) {
+    if (n_inst == 32 && !f0.slow && !f1.slow) {
       const double* r0 = t + f0.d * kLD + jb; const double* r1 = t + f1.d * kLD + jb;
       if ((f0.w1 | f1.w1) == 0 && f0.c == 0.0 && f1.c == 0.0) {   // zero for every instance of the tile (most phase elements)
 #pragma unroll
@@ -1100,11 +1106,11 @@ __device__ __forceinline__ void StorePhasePairs(const double* t, const OutPair* 
           StoreOut2(o, (a.y * f0.c) * (u.y + p.y), (b.y * f1.c) * (v.y + r.y)); o += stride;
         }
       }
-    } else if (n_inst == 32 && nc == 1) {
+    } else if (n_inst == 32) {
 #pragma unroll 4
       for (int j = jb; j < jb + 16; ++j) { StoreOut2(o, FormVal(t, j, f0, x.x, d0, c0, v_off), FormVal(t, j, f1, x.y, d1, c1, v_off)); o += stride; }
     } else {
-      for (int j = jb; j < jb + 16; ++j) { if (j < n_inst && (j % nc) == q) StoreOut2(o, FormVal(t, j, f0, x.x, d0, c0, v_off), FormVal(t, j, f1, x.y, d1, c1, v_off)); o += stride; }
+      for (int j = jb; j < jb + 16; ++j) { if (j < n_inst) StoreOut2(o, FormVal(t, j, f0, x.x, d0, c0, v_off), FormVal(t, j, f1, x.y, d1, c1, v_off)); o += stride; }
     }
   }
 }
@@ -1131,52 +1137,21 @@ __device__ __forceinline__ void StoreValuesTiled(const Plan& P, const double* t,
   ForEachEntry(P.pairs + r.first, P.coefs + r.first, r.count, lane,
                [&](int g_row, int d, double c) { gt_tile[(size_t)g_row * 32 + lane] = t[d * kLD + lane] * c; });
 }
-#if TWB_MERGE_CLASSES
-// Row lengths that are not a multiple of 4 doubles (odd nnz: Biped) give up to four alignment classes, each with its own
-// pair list for the instances j = q (mod nc).  Walking the lists one class after the other leaves most threads idle in the
-// last round of every class (a list is ~1.3 pairs per thread long); here the lists of all classes form ONE item space —
-// item = (class, pair), its 32 / nc instances — so the threads of the CTA stay evenly busy (config 3: 0.42 -> see profiles).
-__device__ __noinline__ void StorePairsClasses(const Plan& P, const double* t, const OutList* list, double* __restrict__ out, size_t stride, int nc,
-                                                  int tid, int n_threads) {
-  int first[kMaxClasses], end[kMaxClasses + 1];
-  end[0] = 0;
-  for (int q = 0; q < kMaxClasses; ++q) {
-    OutRange r{0, 0};
-    if (q < nc) r = LoadRange(&list->pairs[q]);
-    first[q] = r.first; end[q + 1] = end[q] + r.count;
-  }
-  const int n_items = end[nc];
-  for (int i = tid; i < n_items; i += n_threads) {
-    int q = 0;
-    while (q + 1 < nc && i >= end[q + 1]) ++q;
-    const int k = first[q] + (i - end[q]);
-    int off = 0, d0 = 0, d1 = 0; double c0 = 0.0, c1 = 0.0;
-    LoadPair(P.pairs, P.coefs, k, k + 1, &off, &d0, &d1, &c0, &c1);
-    double* o = out + off + (size_t)q * stride;
-    const double* r0 = t + d0 * kLD + q; const double* r1 = t + d1 * kLD + q;
-    const size_t step = (size_t)nc * stride;
-#pragma unroll 8
-    for (int j = 0; j < 32; j += nc) { StoreOut2(o, r0[j] * c0, r1[j] * c1); o += step; }
-  }
-}
-#endif
 // Jacobian values of a whole CTA (after its barrier): every thread takes pairs of the CTA's list; warp 0 writes the
 // single elements (sectors shared with a neighbouring CTA) with lane = instance.
 template <bool kPhase = false>
-__device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac_tile, int n_inst, const Stage st,
+__device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, const OutList* list, double* __restrict__ jac, int tile, int nb, const Stage st,
                                          int v_off = 0, int dwin = 0, int zrow = 0) {
 #ifdef TWB_EXP_NOSTORE   // timing experiment: compute phase only
   return;
 #endif
   const int nc = P.nc_jac, lane = threadIdx.x & 31;
-#if TWB_MERGE_CLASSES
-  const bool merged = !TWB_TMA && nc > 1 && n_inst == 32;
-  if (merged) StorePairsClasses(P, cta_smem, list, jac_tile, (size_t)P.nnz, nc, threadIdx.x, blockDim.x);
-#else
-  const bool merged = false;
-#endif
-  for (int q = 0; q < nc; ++q) {
-    const OutRange rp = merged ? OutRange{0, 0} : LoadRange(&list->pairs[q]);
+  // all instances of the tile belong to alignment class q (interleaved tiles); consecutive lanes are nc rows apart
+  const int q = tile % nc, n_inst = TileCount(nc, tile, nb);
+  const size_t stride = (size_t)nc * P.nnz;
+  double* __restrict__ jac_tile = jac + (size_t)TileInstance(nc, tile, 0) * P.nnz;
+  {
+    const OutRange rp = LoadRange(&list->pairs[q]);
     // warp 0 also owns the single elements: their range (and, below, their first 32 entries) is fetched BEFORE the pair
     // loop, so that the two dependent loads are in flight under the warp's pair stores instead of after them
     OutRange rs{0, 0};
@@ -1189,19 +1164,19 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
 #if TWB_TMA
     const int run_off = __ldg(&list->run_off[q]);
     if (run_off >= 0 && 2 * rp.count <= st.cap && (32 % (blockDim.x >> 5)) == 0)
-      StorePairsTma(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, run_off, jac_tile, (size_t)P.nnz, q, nc, n_inst, st);
+      StorePairsTma(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, run_off, jac_tile, stride, 0, 1, n_inst, st);
     else
 #endif
-    StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, threadIdx.x, blockDim.x);
+    StorePairs(cta_smem, P.pairs + rp.first, P.coefs + rp.first, rp.count, jac_tile, stride, n_inst, threadIdx.x, blockDim.x);
     if (kPhase) {
       const OutRange rq = LoadRange(&list->phase[q]);
-      StorePhasePairs(cta_smem, P.pairs + rq.first, P.coefs + rq.first, P.exts + rq.first, rq.count, jac_tile, (size_t)P.nnz, q, nc, n_inst, v_off, dwin, zrow,
+      StorePhasePairs(cta_smem, P.pairs + rq.first, P.coefs + rq.first, P.exts + rq.first, rq.count, jac_tile, stride, n_inst, v_off, dwin, zrow,
                       threadIdx.x, blockDim.x);
     }
 #ifndef TWB_EXP_NOSINGLES   // (timing experiment, profiles/README.md round 2: what the single-element stores cost)
     if (threadIdx.x < 32 && rs.count > 0) {
-      const bool active = lane < n_inst && (lane % nc) == q;
-      double* o = jac_tile + (size_t)lane * P.nnz;
+      const bool active = lane < n_inst;
+      double* o = jac_tile + (size_t)lane * stride;
       const int cnt = min(32, rs.count);
       for (int sidx = 0; sidx < cnt; ++sidx) {
         const int off = __shfl_sync(0xffffffffu, (int)raw.x, sidx), d = __shfl_sync(0xffffffffu, (int)(raw.y & 0xFFFFu), sidx);
@@ -1242,21 +1217,21 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st,
                                         const double* __restrict__ FS = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = cta * kDynWarps + warp, b0 = tile * 32;
+  const int k = cta * kDynWarps + warp, b = TileInstance(P.nc_jac, tile, lane);
   constexpr int n_rows = 40 + 6 * kNEE;   // local rows: 1 | 3 | 36 | 6 per foot; the 6 constraint values go straight into GT (coalesced)
   double* t = out_smem + (size_t)warp * n_rows * kLD;
   if (k < P.n_dyn) {
     const DynUnit* u = P.dyn + k;
     t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE   // (timing experiment: store phase only)
-    DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TiledCol(XT, b0 + lane, P.n + 1), Col{t + kLD + lane, kLD},
-                              Col{GT + ((size_t)b0 * P.m + (size_t)__ldg(&u->g_row0) * 32) + lane, 32},
+    DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TileCol(XT, tile, lane, P.n + 1), Col{t + kLD + lane, kLD},
+                              Col{GT + (((size_t)tile * P.m + (size_t)__ldg(&u->g_row0)) * 32) + lane, 32},
                               FS ? FS + (((size_t)tile * P.n_dyn + k) * (6 * kNEE)) * 32 + lane : nullptr);
-    FlagNonFinite(t, n_rows, lane, status, b0 + lane, nb);
+    FlagNonFinite(t, n_rows, lane, status, b, nb);
 #endif
   }
   __syncthreads();
-  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.dyn_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0), st);
+  if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.dyn_list0 + cta, jac, tile, nb, st);
 }
 
 // RangeOfMotionConstraint (range_of_motion_constraint.cc:58-109): g_e = R^T (p_e - c); Jacobian state R^T and
@@ -1269,18 +1244,16 @@ template <int kNEE, bool kPhase>
 __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = cta * kRomWarps + warp, b0 = tile * 32;
+  const int k = cta * kRomWarps + warp, b = TileInstance(P.nc_jac, tile, lane);
   const bool valid = k < P.n_rom;
   constexpr int block_rows = RomBlockRowsP(kNEE, kPhase);
   double* t = out_smem + (size_t)warp * block_rows * kLD;
   const RomUnit* u = P.rom + (valid ? k : 0);
   const SplineSample* __restrict__ sp = P.samples + __ldg(&u->sample0);
-  const ConstCol xs = TiledCol(XT, b0 + lane, P.n + 1);
+  const ConstCol xs = TileCol(XT, tile, lane, P.n + 1);
   // local state rows 1..: R^T (0..8) | buffer 0: D_e (9..17), g_e (18..20) | buffer 1: (21..29), (30..32); with optimised durations a
   // buffer is D_e (9) | the PhaseSpline's info block (kInfoRows) | U (3) | X (3 kRomDurWin)   (g_e lives in registers only)
   const Col Sk{t + kLD + lane, kLD};
-  const int n_inst = min(32, nb - b0);
-  double* jac_tile = jac + (size_t)b0 * P.nnz;
   t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE
   double c[3], th[3], unused[3];
@@ -1323,12 +1296,12 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
 #pragma unroll
       for (int d = 0; d < 3; ++d) Sk[9 + buf + i * 3 + d] = D[i][d];
     if (valid) {
-      if (e == 0) FlagNonFinite(t, 10, lane, status, b0 + lane, nb);
-      FlagNonFinite(t, (kPhase ? 19 : 22) + buf, lane, status, b0 + lane, nb, 10 + buf);
+      if (e == 0) FlagNonFinite(t, 10, lane, status, b, nb);
+      FlagNonFinite(t, (kPhase ? 19 : 22) + buf, lane, status, b, nb, 10 + buf);
     }
 #endif
     if (valid && (flags & 1u)) {   // rows rom_row0[e] + 3k .. + 2 (range_of_motion_constraint.cc:58-66), lane = instance into GT
-      double* gt = GT + ((size_t)b0 * P.m + (size_t)(P.rom_row0[e] + 3 * k) * 32) + lane;
+      double* gt = GT + (((size_t)tile * P.m + (size_t)(P.rom_row0[e] + 3 * k)) * 32) + lane;
 #ifndef TWB_EXP_NOCOMPUTE
 #pragma unroll
       for (int i = 0; i < 3; ++i) gt[i * 32] = ge[i];
@@ -1338,12 +1311,12 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
     }
 #if !TWB_ROM_ALLFEET
     __syncthreads();   // foot e complete in every block; everybody is done reading buffer (e + 1) & 1 (the list of foot e - 1)
-    if (flags & 2u) StoreCta<kPhase>(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac_tile, n_inst, st, 3, kRomDurWin, 20 + buf);
+    if (flags & 2u) StoreCta<kPhase>(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac, tile, nb, st, 3, kRomDurWin, 20 + buf);
 #endif
   }
 #if TWB_ROM_ALLFEET
   __syncthreads();
-  if (flags & 2u) StoreCta<kPhase>(P, out_smem, P.cta_lists + P.rom_list0 + cta, jac_tile, n_inst, st, 3, kRomDurWin, 20);
+  if (flags & 2u) StoreCta<kPhase>(P, out_smem, P.cta_lists + P.rom_list0 + cta, jac, tile, nb, st, 3, kRomDurWin, 20);
 #endif
 }
 
@@ -1352,10 +1325,10 @@ __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict
                                          int* __restrict__ status, const int* __restrict__ terrain_ids, int default_terrain, int nb,
                                          unsigned flags, double* node_smem, int cta, int tile, const Stage st) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gi = cta * kNodeWarps + warp, b0 = tile * 32, b = b0 + lane;
+  const int gi = cta * kNodeWarps + warp, b = TileInstance(P.nc_jac, tile, lane);
   double* t = node_smem + (size_t)warp * P.node_rows * kLD;
   if (gi < P.n_groups) {
-    const ConstCol xs = TiledCol(XT, b, P.n + 1);
+    const ConstCol xs = TileCol(XT, tile, lane, P.n + 1);
     const NodeGroup* grp = P.groups + gi;
     const int kind = __ldg(&grp->kind), first = __ldg(&grp->first), count = __ldg(&grp->count);
     t[lane] = 1.0;
@@ -1387,15 +1360,15 @@ __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict
       const int g_row0 = __ldg(&grp->g_row0);
       if (g_row0 >= 0) {
         const int d0 = __ldg(&grp->g_d0), gn = __ldg(&grp->g_n);
-        double* gt = GT + ((size_t)b0 * P.m + (size_t)g_row0 * 32) + lane;
+        double* gt = GT + (((size_t)tile * P.m + (size_t)g_row0) * 32) + lane;
         for (int i = 0; i < gn; ++i) gt[(size_t)i * 32] = t[(d0 + i) * kLD + lane];
       } else {
-        StoreValuesTiled(P, t, &grp->values, GT + (size_t)b0 * P.m, lane);
+        StoreValuesTiled(P, t, &grp->values, GT + (size_t)tile * P.m * 32, lane);
       }
     }
   }
   __syncthreads();
-  if (flags & 2u) StoreCta(P, node_smem, P.cta_lists + P.node_list0 + cta, jac + (size_t)b0 * P.nnz, min(32, nb - b0), st);
+  if (flags & 2u) StoreCta(P, node_smem, P.cta_lists + P.node_list0 + cta, jac, tile, nb, st);
 }
 
 // NodeCost::GetCost summed over terms (node_cost.cc:53-63; Composite::GetValues for costs) and the dense gradient row
@@ -1405,7 +1378,7 @@ __global__ void __launch_bounds__(128) CostKernel(const Plan P, const double* __
                                                   double* __restrict__ grad, int nb) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const ConstCol xs = TiledCol(XT, b, P.n + 1, P.nc_jac);
   double* gr = grad ? grad + (size_t)b * P.n : nullptr;
   double total_cost = 0.0, term = 0.0;
   for (int i = 0; i < P.n_cost; ++i) {
@@ -1434,10 +1407,10 @@ template <int kNEE>
 __global__ void __launch_bounds__(kNEE * 32, TWB_TAIL_CTAS) DynTailOut(const Plan P, const double* __restrict__ XT, double* __restrict__ jac, int nb,
                                                         double* __restrict__ FS) {
   extern __shared__ __align__(16) double out_smem[];
-  const int lane = threadIdx.x & 31, e = threadIdx.x >> 5, k = blockIdx.x, b0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, e = threadIdx.x >> 5, k = blockIdx.x;
   double* t = out_smem + (size_t)e * kTailRows * kLD;
   const SplineSample* __restrict__ sp = P.samples + __ldg(&P.dyn[k].sample0);
-  const ConstCol xs = TiledCol(XT, b0 + lane, P.n + 1);
+  const ConstCol xs = TileCol(XT, blockIdx.y, lane, P.n + 1);
 #ifndef TWB_EXP_NOCOMPUTE
   double c[3], unused[3];
   EvalSpline<0>(P, sp, xs, c, unused, unused);
@@ -1470,7 +1443,7 @@ __global__ void __launch_bounds__(kNEE * 32, TWB_TAIL_CTAS) DynTailOut(const Pla
   StorePhaseDurations<6, kDynDurWin>(mo.cur, U, V, t, 7, 7 + 2 * kInfoRows, lane);
 #endif
   __syncthreads();
-  StoreCta<true>(P, out_smem, P.cta_lists + P.tail_list0 + k, jac + (size_t)b0 * P.nnz, min(32, nb - b0), Stage{nullptr, 0}, 6, kDynDurWin, 8);
+  StoreCta<true>(P, out_smem, P.cta_lists + P.tail_list0 + k, jac, blockIdx.y, nb, Stage{nullptr, 0}, 6, kDynDurWin, 8);
 }
 
 // TotalDurationConstraint (total_duration_constraint.cc:36-72; the only rows no output kernel owns): value = sum of the foot's
@@ -1479,9 +1452,9 @@ __global__ void __launch_bounds__(kNEE * 32, TWB_TAIL_CTAS) DynTailOut(const Pla
 template <int kNEE>
 __global__ void __launch_bounds__(32) PhaseJac(const Plan P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                                int* __restrict__ status, int nb, unsigned flags) {
-  const int lane = threadIdx.x, b = blockIdx.x * 32 + lane;
+  const int lane = threadIdx.x, b = TileInstance(P.nc_jac, blockIdx.x, lane);
   const bool live = b < nb;
-  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const ConstCol xs = TileCol(XT, blockIdx.x, lane, P.n + 1);
   for (int ui = 0; ui < P.n_phase_units; ++ui) {
     const PhaseUnit* u = P.phase_units + ui;
     for (int e = 0; e < kNEE; ++e) {
@@ -1519,9 +1492,9 @@ __device__ __forceinline__ void QuaternionFromMatrix(const double m[3][3], doubl
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(128) TrajectoryKernel(const Plan P, const double* __restrict__ XT, const SplineSample* __restrict__ samples,
                                                         const int* __restrict__ contact, int n_steps, double* __restrict__ out, int nb) {
-  const int lane = threadIdx.x & 31, ti = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y * 32 + lane;
+  const int lane = threadIdx.x & 31, ti = blockIdx.x * 4 + (threadIdx.x >> 5), b = TileInstance(P.nc_jac, blockIdx.y, lane);
   if (ti >= n_steps) return;
-  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const ConstCol xs = TileCol(XT, blockIdx.y, lane, P.n + 1);
   const SplineSample* sp = samples + (size_t)ti * (2 + 2 * kNEE);
   constexpr int K = 19 + 13 * kNEE;
   double o[K];
@@ -1576,9 +1549,9 @@ __global__ void __launch_bounds__(128) TrajectoryKernel(const Plan P, const doub
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(128) InitialGuessKernel(const Plan P, const double* __restrict__ XT, const SplineSample* __restrict__ samples,
                                                           const double* __restrict__ times, int n_times, double* __restrict__ out, int nb) {
-  const int lane = threadIdx.x & 31, ti = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y * 32 + lane;
+  const int lane = threadIdx.x & 31, ti = blockIdx.x * 4 + (threadIdx.x >> 5), b = TileInstance(P.nc_jac, blockIdx.y, lane);
   if (ti >= n_times) return;
-  const ConstCol xs = TiledCol(XT, b, P.n + 1);
+  const ConstCol xs = TileCol(XT, blockIdx.y, lane, P.n + 1);
   const SplineSample* sp = samples + (size_t)ti * (2 + 2 * kNEE);
   double o[49];
 #pragma unroll
@@ -1791,6 +1764,9 @@ __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const
 #endif
 #endif
 
+// number of tiles that cover nb instances (whole groups of nc interleaved tiles)
+inline int TileTotal(int nc, int nb) { return nc * ((nb + 32 * nc - 1) / (32 * nc)); }
+
 // kernel launch with the optional attributes of this pipeline: programmatic dependent launch, L2 access-policy window
 template <class... KArgs, class... Args>
 cudaError_t LaunchK(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
@@ -1887,8 +1863,8 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* FS, d
 int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSample* samples, const int* contact, int n_steps,
                      double* out, int nb, cudaStream_t s) {
   if (nb <= 0 || n_steps <= 0) return 0;
-  const int tiles = (nb + 31) / 32;
-  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb);
+  const int tiles = TileTotal(P.nc_jac, nb);
+  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
   const dim3 grid((n_steps + 3) / 4, tiles);
   const bool phase = P.n_phase_defs > 0;
 #define TWB_TRAJ(NEE) (phase ? TrajectoryKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, contact, n_steps, out, nb) \
@@ -1906,8 +1882,8 @@ int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSam
 int LaunchInitialGuess(const Plan& P, const double* x, double* XT, const SplineSample* samples, const double* times, int n_times,
                        double* out, int nb, cudaStream_t s) {
   if (nb <= 0 || n_times <= 0) return 0;
-  const int tiles = (nb + 31) / 32;
-  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb);
+  const int tiles = TileTotal(P.nc_jac, nb);
+  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
   const dim3 grid((n_times + 3) / 4, tiles);
   const bool phase = P.n_phase_defs > 0;
 #define TWB_IG(NEE) (phase ? InitialGuessKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, times, n_times, out, nb) \
@@ -1940,10 +1916,10 @@ int LaunchNearestPlanes(const double* plan, const int* n_states, int max_states,
 // ---- the two components outside Parameters::ConstraintName: LinearEqualityConstraint and SoftConstraint -----------------
 // towr::LinearEqualityConstraint::GetValues (linear_constraint.cc:46-51): g = M x_set, thread = (row, instance), lane = instance
 __global__ void __launch_bounds__(128) LinearEqualityKernel(const double* __restrict__ XT, int n, int col0, int n_cols, const double* __restrict__ M,
-                                                            int rows, double* __restrict__ g, int nb) {
-  const int b = blockIdx.y * 32 + (threadIdx.x & 31), r = blockIdx.x * 4 + (threadIdx.x >> 5);
+                                                            int rows, double* __restrict__ g, int nb, int nc) {
+  const int b = TileInstance(nc, blockIdx.y, threadIdx.x & 31), r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
-  const ConstCol xs = TiledCol(XT, b, n + 1);
+  const ConstCol xs = TileCol(XT, blockIdx.y, threadIdx.x & 31, n + 1);
   double acc = 0.0;
   for (int c = 0; c < n_cols; ++c) acc += __ldg(M + (size_t)r * n_cols + c) * xs[col0 + c];   // Eigen's dense row-times-vector order
   if (b < nb) g[(size_t)b * rows + r] = acc;
@@ -1972,9 +1948,9 @@ __global__ void __launch_bounds__(128) SoftConstraintKernel(const double* __rest
 }
 int LaunchLinearEquality(const Plan& P, const double* x, double* XT, int col0, int n_cols, const double* M, int rows, double* g, int nb, cudaStream_t s) {
   if (nb <= 0 || rows <= 0) return 0;
-  const int tiles = (nb + 31) / 32;
-  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb);
-  LinearEqualityKernel<<<dim3((rows + 3) / 4, tiles), 128, 0, s>>>(XT, P.n, col0, n_cols, M, rows, g, nb);
+  const int tiles = TileTotal(P.nc_jac, nb);
+  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
+  LinearEqualityKernel<<<dim3((rows + 3) / 4, tiles), 128, 0, s>>>(XT, P.n, col0, n_cols, M, rows, g, nb, P.nc_jac);
   return (int)cudaGetLastError();
 }
 int LaunchSoftConstraint(const Plan& P, const double* g, const double* jac, const int* row_ptr, const int* col_idx, int row0, int n_rows,
@@ -2062,11 +2038,11 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
   int count = 0;
   const bool serial = (g_after_launch != nullptr);
   if (serial) aux0 = aux1 = s;
-  const int tiles = (nb + 31) / 32;
+  const int tiles = TileTotal(P.nc_jac, nb);
   const unsigned out_flags = flags & 3u;
   const bool want_cost = (flags & 4u) && P.n_cost > 0;
   TWB_MARK("begin", s);
-  LaunchK(TransposeIn, dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s, false, x, XT, status, P.n, nb); ++count; TWB_MARK("TransposeIn", s);
+  LaunchK(TransposeIn, dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s, false, x, XT, status, P.n, nb, P.nc_jac); ++count; TWB_MARK("TransposeIn", s);
   const bool fork = !serial && (want_cost || (!TWB_FUSED && out_flags));
   if (fork) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
@@ -2099,7 +2075,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
     }
     ++count; TWB_MARK("PhaseJac", s);
   }
-  if (out_flags & 1u) { LaunchK(TransposeOut, dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s, false, (const double*)GT, g, P.m, nb, XT, P.n); ++count; TWB_MARK("TransposeOut", s); }
+  if (out_flags & 1u) { LaunchK(TransposeOut, dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s, false, (const double*)GT, g, P.m, nb, XT, P.n, P.nc_jac); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
   return (int)cudaGetLastError();
 }
