@@ -74,6 +74,7 @@ struct twb_batch {
   float* d_gmap = nullptr;        // elevation layer of TWB_GRID_MAP (optional)
   double* d_XT = nullptr;         // [ld/32][n+1][32] instance-tiled iterates; row n == 0
   double* d_GT = nullptr;         // [ld/32][m][32] instance-tiled constraint values (staging of g)
+  int* d_TD = nullptr;            // [ld/32] per-tile completion counters of the output kernels (zero between evaluations)
   double* d_FS = nullptr;         // [ld/32][n_dyn][6 n_ee][32] feet positions / forces per dynamic sample (optimised durations only)
   // staging for the host-pointer variant
   double *d_x = nullptr, *d_g = nullptr, *d_jac = nullptr, *d_cost = nullptr, *d_grad = nullptr;
@@ -87,9 +88,21 @@ struct twb_batch {
   cudaAccessPolicyWindow l2_window{};            // XT + GT persisting in the L2 (experiment, TWB_L2_PERSIST=1)
   bool use_l2_window = false;
   std::vector<std::pair<void*, size_t>> scratch;   // device scratch of the post-processing calls, grown on demand, freed with the batch
+  // CUDA graphs of twb_batch_eval_device: one evaluation is 4 - 6 kernels on three streams joined by events; replayed as a
+  // graph, the dependencies are resolved on the device instead of through cross-stream event waits.  One instantiated graph
+  // per distinct argument set (a solver loop alternates between a few buffers), least recently used replaced.
+  struct EvalGraph { const void* x; void *g, *jac, *cost, *grad, *status; unsigned flags; cudaGraphExec_t exec; int launches; unsigned long long used; };
+  std::vector<EvalGraph> graphs;
+  unsigned long long graph_clock = 0;
+  int use_graphs = 1;             // TWB_GRAPH=0 disables; set to 0 when a capture fails
 };
 
 namespace {
+// cached graphs hold the batch's plan and buffers by value: dropped whenever those change
+void DropGraphs(twb_batch* b) {
+  for (auto& gr : b->graphs) cudaGraphExecDestroy(gr.exec);
+  b->graphs.clear();
+}
 // slot `slot` of the batch's scratch pool with at least `bytes` bytes (the post-processing entry points synchronise before
 // they return and a batch has one caller at a time, so the slots are free again at the next call)
 cudaError_t ScratchAlloc(twb_batch* b, int slot, void** p, size_t bytes) {
@@ -212,6 +225,7 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   if (std::getenv("TWB_PROFILE") && !g_prof_on) { g_prof_on = true; twb::g_after_launch = ProfHook; std::atexit(ProfReport); }
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
   if (const char* v = std::getenv("TWB_E2E_CHUNK")) b->e2e_chunk = std::max(32, std::atoi(v));
+  if (const char* v = std::getenv("TWB_GRAPH")) b->use_graphs = std::atoi(v) != 0;
   // whole groups of nc interleaved tiles (kernels.cu: TileInstance); nc = 1 unless the Jacobian row length is not a multiple of 4
   const size_t group = 32 * (size_t)std::max(b->plan.nc_jac, 1);
   b->ld = ((size_t)batch_size + group - 1) / group * group;
@@ -225,6 +239,11 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
     return CudaFail(e, "state allocation");
   }
   b->d_GT = reinterpret_cast<double*>(reinterpret_cast<char*>(b->d_XT) + xt_padded);
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&b->d_TD), sizeof(int) * (b->ld / 32))) != cudaSuccess ||
+      (e = cudaMemset(b->d_TD, 0, sizeof(int) * (b->ld / 32))) != cudaSuccess) {
+    twb_batch_destroy(b);
+    return CudaFail(e, "state allocation");
+  }
   if (b->plan.n_phase_defs > 0 && b->plan.n_dyn > 0 &&
       (e = cudaMalloc(reinterpret_cast<void**>(&b->d_FS), (size_t)b->plan.n_dyn * 6 * b->plan.n_ee * b->ld * sizeof(double))) != cudaSuccess) {
     twb_batch_destroy(b);
@@ -264,10 +283,11 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
 void twb_batch_destroy(twb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  DropGraphs(b);
   if (b->use_l2_window) cudaCtxResetPersistingL2Cache();   // lines of XT / GT must not stay pinned in the L2 after the batch is gone
   for (void* p : b->owned) cudaFree(p);
   for (auto& sc : b->scratch) cudaFree(sc.first);
-  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT); cudaFree(b->d_FS);   // (d_GT is part of d_XT's allocation)
+  cudaFree(b->d_terrain); cudaFree(b->d_grid); cudaFree(b->d_gmap); cudaFree(b->d_XT); cudaFree(b->d_FS); cudaFree(b->d_TD);   // (d_GT is part of d_XT's allocation)
   for (auto ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->aux0) cudaStreamDestroy(b->aux0);
   if (b->aux1) cudaStreamDestroy(b->aux1);
@@ -282,6 +302,7 @@ void twb_batch_destroy(twb_batch* b) {
 int twb_batch_set_terrains(twb_batch* b, const int* terrain_ids) {
   if (!b) return Fail(TWB_ERR_INVALID, "null batch");
   cudaSetDevice(b->device);
+  DropGraphs(b);
   if (!terrain_ids) { cudaFree(b->d_terrain); b->d_terrain = nullptr; return TWB_OK; }
   for (int i = 0; i < b->B; ++i)
     if (terrain_ids[i] < 0 || terrain_ids[i] > TWB_GRID_MAP) return Fail(TWB_ERR_INVALID, "unknown terrain id");
@@ -295,6 +316,7 @@ int twb_batch_set_terrains(twb_batch* b, const int* terrain_ids) {
 int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, int cols) {
   if (!b) return Fail(TWB_ERR_INVALID, "null batch");
   cudaSetDevice(b->device);
+  DropGraphs(b);
   cudaFree(b->d_grid); b->d_grid = nullptr;
   b->plan.grid = nullptr; b->plan.grid_rows = b->plan.grid_cols = 0;
   if (!heights) return TWB_OK;
@@ -310,6 +332,7 @@ int twb_batch_set_grid_terrain(twb_batch* b, const double* heights, int rows, in
 int twb_batch_set_grid_map(twb_batch* b, const float* heights, int size_x, int size_y, double resolution, double pos_x, double pos_y) {
   if (!b) return Fail(TWB_ERR_INVALID, "null batch");
   cudaSetDevice(b->device);
+  DropGraphs(b);
   cudaFree(b->d_gmap); b->d_gmap = nullptr;
   b->plan.gmap = nullptr; b->plan.gmap_sx = b->plan.gmap_sy = 0; b->plan.gmap_res = 1.0; b->plan.gmap_px = b->plan.gmap_py = 0.0;
   if (!heights) return TWB_OK;
@@ -549,7 +572,7 @@ int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   int n = 1;   // TransposeIn
   if (flags & (TWB_EVAL_G | TWB_EVAL_JAC)) n += twb::OutKernelsPerEval(p, flags);   // DynOut [+ DynTailOut] + RomNodeOut (or RomOut, NodeOut)
   if ((flags & (TWB_EVAL_G | TWB_EVAL_JAC)) && p.n_phase_units > 0) n += 1;   // PhaseJac
-  if (flags & TWB_EVAL_G) n += 1;   // TransposeOut
+  if (flags & TWB_EVAL_G) n += twb::TransposeOutPerEval(p);   // TransposeOut (not with fixed durations: the values are written directly)
   if (want_cost) n += 1;
   return n;
 }
@@ -568,7 +591,41 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   if (f.has_cost && (flags & TWB_EVAL_COST)) kflags |= TWB_EVAL_COST;
   int launches = 0;
   twb::SetL2Window(b->use_l2_window ? &b->l2_window : nullptr);
-  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, b->d_FS, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
+  if (b->use_graphs && !g_prof_on) {
+    // replay (or first capture on the batch's own stream) the evaluation of this argument set as a CUDA graph
+    twb_batch::EvalGraph* hit = nullptr;
+    for (auto& gr : b->graphs)
+      if (gr.x == x && gr.g == g && gr.jac == jac && gr.cost == cost && gr.grad == grad && gr.status == status && gr.flags == kflags) { hit = &gr; break; }
+    if (!hit) {
+      cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+      bool ok = cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      if (ok) {
+        const int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, b->d_FS, b->d_TD, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
+                                       kflags, b->stream, b->aux0, b->aux1, b->ev.data(), &launches);
+        ok = cudaStreamEndCapture(b->stream, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+      }
+      ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) { cudaGetLastError(); b->use_graphs = 0; launches = 0; }   // plain launches from now on
+      else {
+        if (b->graphs.size() >= 16) {   // replace the least recently used
+          size_t lru = 0;
+          for (size_t i = 1; i < b->graphs.size(); ++i) if (b->graphs[i].used < b->graphs[lru].used) lru = i;
+          cudaGraphExecDestroy(b->graphs[lru].exec);
+          b->graphs.erase(b->graphs.begin() + lru);
+        }
+        b->graphs.push_back({x, g, jac, cost, grad, status, kflags, exec, launches, 0});
+        hit = &b->graphs.back();
+      }
+    }
+    if (hit) {
+      hit->used = ++b->graph_clock;
+      if ((e = cudaGraphLaunch(hit->exec, static_cast<cudaStream_t>(stream))) != cudaSuccess) return CudaFail(e, "cudaGraphLaunch");
+      b->launches_last = hit->launches;
+      return TWB_OK;
+    }
+  }
+  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, b->d_FS, b->d_TD, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
                            kflags, static_cast<cudaStream_t>(stream), b->aux0, b->aux1, b->ev.data(), &launches);
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
   b->launches_last = launches;
@@ -616,7 +673,7 @@ int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac, d
     cudaEventRecord(b->ev_chunk[2 * c], b->s_in);
     cudaStreamWaitEvent(s, b->ev_chunk[2 * c], 0);
     int rc = twb::LaunchEval(b->plan, b->d_x + off * f.n, b->d_XT + tile0 * (size_t)(f.n + 1) * 32, b->d_GT + tile0 * (size_t)std::max(f.m, 1) * 32,
-                             b->d_FS ? b->d_FS + tile0 * (size_t)b->plan.n_dyn * 6 * b->plan.n_ee * 32 : nullptr,
+                             b->d_FS ? b->d_FS + tile0 * (size_t)b->plan.n_dyn * 6 * b->plan.n_ee * 32 : nullptr, b->d_TD + tile0,
                              (flags & TWB_EVAL_G) ? b->d_g + off * f.m : nullptr, (flags & TWB_EVAL_JAC) ? b->d_jac + off * f.nnz : nullptr,
                              has_cost ? b->d_cost + off : nullptr, has_cost ? b->d_grad + off * f.n : nullptr, b->d_status + off,
                              b->d_terrain ? b->d_terrain + off : nullptr, f.spec.terrain, (int)nb, kflags, s, b->aux0, b->aux1, b->ev.data(), &launches);

@@ -132,6 +132,15 @@ struct OutList {                        // per alignment class
 #define RomBlockRows(n_ee) RomBlockRowsP(n_ee, false)
 #define RomListsPerCta(n_ee) (TWB_ROM_ALLFEET ? 1 : (n_ee))
 
+// TWB_GDIRECT = 1 (fixed durations): the constraint values leave the output kernels straight into g[B][m] — after the CTA
+// barrier all threads write the CTA's consecutive rows (24 per dynamic CTA, 12 per range-of-motion CTA and foot) with
+// consecutive threads = consecutive rows of one instance; no GT staging matrix, no TransposeOut kernel.  The dynamic unit then
+// keeps its 6 values in 6 more state rows.  0: values staged instance-tiled in GT, transposed by TransposeOut.
+#ifndef TWB_GDIRECT
+#define TWB_GDIRECT 1
+#endif
+#define DynBlockRows(n_ee) (40 + 6 * (n_ee) + (TWB_GDIRECT ? 6 : 0))   /* 1 | 3 | 36 | 6 per foot [| 6 values] */
+
 // warps per CTA of the output kernels = consecutive units whose output ranges are chained through carry rows.
 // TWB_FUSED = 1: one kernel (EvalOut) serves all three unit kinds with CTAs of TWB_WARPS warps.
 #ifndef TWB_FUSED

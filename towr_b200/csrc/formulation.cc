@@ -848,7 +848,7 @@ int Formulation::Build(const twb_spec& sp, std::string* err) {
   const int tail_list0 = n_dyn_ctas + n_rom_ctas * rom_lists + n_node_ctas;
   const int n_lists = tail_list0 + (optimize_timings ? pl.n_dyn : 0);   // dynamic CTAs | (rom CTA[, foot]) | node CTAs | PhaseSpline columns of dynamic sample k
   pl.tail_list0 = tail_list0;
-  pl.dyn_rows = 40 + 6 * n_ee; pl.rom_rows = RomBlockRowsP(n_ee, optimize_timings);
+  pl.dyn_rows = DynBlockRows(n_ee); pl.rom_rows = RomBlockRowsP(n_ee, optimize_timings);
   std::vector<int> list_of(n_blocks, -1), row_base(n_blocks, 0);   // list a block's elements belong to; first row of the block inside its CTA
   for (int k = 0; k < pl.n_dyn; ++k) { list_of[k] = k / kDynWarps; row_base[k] = (k % kDynWarps) * pl.dyn_rows; }
   for (int k = 0; k < pl.n_rom; ++k) for (int e = 0; e < n_ee; ++e) {

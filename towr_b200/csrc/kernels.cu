@@ -819,6 +819,28 @@ __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x,
 // are still dirty in the L2; `discard.global.L2` drops the lines instead of writing them back to HBM (50 MB per step
 // on config 2, 9 % of the step's DRAM writes).  Both matrices are rewritten by the next evaluation before they are read.
 __device__ __forceinline__ void DiscardLine(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
+// Experiment (TWB_XT_DROP=1): without TransposeOut (direct constraint values) the LAST output CTA of a tile drops the tile's XT lines: every output CTA
+// counts itself on the tile's counter when it is done; the one that completes the count discards rows 0 .. n-1 (row n is the
+// permanent zero row; a ragged tile keeps its lines: its padded lanes are never rewritten) and resets the counter.
+// Measured (config 2, one box): 137.3 us per step with the counters against 132.1 us without — the atomics and the extra CTA
+// barriers cost more than the 21 MB of XT write-back they save.  Off.
+#ifndef TWB_XT_DROP
+#define TWB_XT_DROP 0
+#endif
+__device__ __forceinline__ void TileDone(int* __restrict__ tile_done, int total, const double* __restrict__ XT, int n, int nc, int tile, int nb) {
+#if TWB_XT_DROP
+  if (!tile_done) return;
+  __shared__ int last;
+  __syncthreads();   // every thread of the CTA is past its reads of XT
+  if (threadIdx.x == 0) last = (atomicAdd(tile_done + tile, 1) == total - 1);
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) tile_done[tile] = 0;
+  if (TileCount(nc, tile, nb) != 32) return;
+  const double* xt = XT + ((size_t)tile * (n + 1)) * 32;
+  for (int l = threadIdx.x; l < 2 * n; l += blockDim.x) DiscardLine(xt + (size_t)l * 16);
+#endif
+}
 __global__ void __launch_bounds__(256) TransposeOut(const double* __restrict__ GT, double* __restrict__ g, int m, int nb,
                                                     const double* __restrict__ XT, int n, int nc) {
   __shared__ double tile[32][33];
@@ -1202,6 +1224,33 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
 #endif
   }
 }
+// ---- constraint values straight into g[B][m] (TWB_GDIRECT) ----------------------------------------------------------------
+#ifndef TWB_G_ST
+#define TWB_G_ST 1   // cache operator of the direct constraint-value stores: 0 .cs (evict-first), 1 default (ships: 132.0 vs 134.5 us per step on config 2 — rows shared by two CTAs merge in the L2)
+#endif
+__device__ __forceinline__ void StoreG(double* p, double v) {
+#if TWB_G_ST == 1
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
+// The `n_units` consecutive units of a CTA own kPer consecutive constraint rows each, starting at row `row0`; unit w keeps its
+// values in the state rows w * block_rows + d0 .. of the CTA's shared memory `t`.  All threads: consecutive threads write
+// consecutive rows of one instance (kPer * n_units * 8 contiguous bytes per instance), after the CTA barrier.
+template <int kPer>
+__device__ __forceinline__ void StoreValuesDirect(const Plan& P, const double* t, double* __restrict__ g, int tile, int nb, int row0, int n_units,
+                                                  int block_rows, int d0) {
+  // thread = (row r of the CTA's run, instance j0), then every `per`-th instance: the index arithmetic happens once per thread
+  const int nc = P.nc_jac, n_inst = TileCount(nc, tile, nb), N = kPer * n_units, per = (int)blockDim.x / N;
+  const int j0 = (int)threadIdx.x / N, r = (int)threadIdx.x - j0 * N;
+  if (j0 >= per) return;
+  const int w = r / kPer, i = r - w * kPer;
+  const double* src = t + (w * block_rows + d0 + i) * kLD;
+  double* dst = g + (size_t)TileInstance(nc, tile, j0) * P.m + row0 + r;
+  const size_t step = (size_t)per * nc * P.m;
+  for (int j = j0; j < n_inst; j += per, dst += step) StoreG(dst, src[j]);
+}
 // non-finite check of this lane's own column (rows 1 .. n_rows-1); flags instance b
 __device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int lane, int* __restrict__ status, int b, int nb, int first_row = 1) {
   if (!status) return;
@@ -1215,22 +1264,26 @@ __device__ __forceinline__ void FlagNonFinite(const double* t, int n_rows, int l
 template <int kNEE, bool kPhase>
 __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                         int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st,
-                                        const double* __restrict__ FS = nullptr) {
+                                        const double* __restrict__ FS = nullptr, double* __restrict__ g = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kDynWarps + warp, b = TileInstance(P.nc_jac, tile, lane);
-  constexpr int n_rows = 40 + 6 * kNEE;   // local rows: 1 | 3 | 36 | 6 per foot; the 6 constraint values go straight into GT (coalesced)
+  // local rows: 1 | 3 | 36 | 6 per foot [| the 6 constraint values (TWB_GDIRECT); else they go straight into GT, coalesced]
+  constexpr int n_rows = DynBlockRows(kNEE), g_d0 = n_rows - 6;
+  const bool g_direct = TWB_GDIRECT && g != nullptr;
   double* t = out_smem + (size_t)warp * n_rows * kLD;
   if (k < P.n_dyn) {
     const DynUnit* u = P.dyn + k;
     t[lane] = 1.0;
 #ifndef TWB_EXP_NOCOMPUTE   // (timing experiment: store phase only)
     DynamicUnit<kNEE, kPhase>(P, k, P.samples + __ldg(&u->sample0), TileCol(XT, tile, lane, P.n + 1), Col{t + kLD + lane, kLD},
-                              Col{GT + (((size_t)tile * P.m + (size_t)__ldg(&u->g_row0)) * 32) + lane, 32},
+                              g_direct ? Col{t + g_d0 * kLD + lane, kLD} : Col{GT + (((size_t)tile * P.m + (size_t)__ldg(&u->g_row0)) * 32) + lane, 32},
                               FS ? FS + (((size_t)tile * P.n_dyn + k) * (6 * kNEE)) * 32 + lane : nullptr);
     FlagNonFinite(t, n_rows, lane, status, b, nb);
 #endif
   }
   __syncthreads();
+  if (g_direct && (flags & 1u) && cta * kDynWarps < P.n_dyn)
+    StoreValuesDirect<6>(P, out_smem, g, tile, nb, __ldg(&P.dyn[cta * kDynWarps].g_row0), min(kDynWarps, P.n_dyn - cta * kDynWarps), n_rows, g_d0);
   if (flags & 2u) StoreCta(P, out_smem, P.cta_lists + P.dyn_list0 + cta, jac, tile, nb, st);
 }
 
@@ -1242,7 +1295,9 @@ __device__ __forceinline__ void DynBody(const Plan& P, const double* __restrict_
 // already evaluates foot e + 1 — one CTA barrier per foot.
 template <int kNEE, bool kPhase>
 __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
-                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st) {
+                                        int* __restrict__ status, int nb, unsigned flags, double* out_smem, int cta, int tile, const Stage st,
+                                        double* __restrict__ g = nullptr) {
+  const bool g_direct = TWB_GDIRECT && !kPhase && g != nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = cta * kRomWarps + warp, b = TileInstance(P.nc_jac, tile, lane);
   const bool valid = k < P.n_rom;
@@ -1300,7 +1355,7 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
       FlagNonFinite(t, (kPhase ? 19 : 22) + buf, lane, status, b, nb, 10 + buf);
     }
 #endif
-    if (valid && (flags & 1u)) {   // rows rom_row0[e] + 3k .. + 2 (range_of_motion_constraint.cc:58-66), lane = instance into GT
+    if (valid && (flags & 1u) && !g_direct) {   // rows rom_row0[e] + 3k .. + 2 (range_of_motion_constraint.cc:58-66), lane = instance into GT
       double* gt = GT + (((size_t)tile * P.m + (size_t)(P.rom_row0[e] + 3 * k)) * 32) + lane;
 #ifndef TWB_EXP_NOCOMPUTE
 #pragma unroll
@@ -1311,6 +1366,8 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
     }
 #if !TWB_ROM_ALLFEET
     __syncthreads();   // foot e complete in every block; everybody is done reading buffer (e + 1) & 1 (the list of foot e - 1)
+    if (g_direct && (flags & 1u))   // the foot's rows of the CTA's samples are adjacent: 3 kRomWarps consecutive values per instance
+      StoreValuesDirect<3>(P, out_smem, g, tile, nb, P.rom_row0[e] + 3 * cta * kRomWarps, min(kRomWarps, P.n_rom - cta * kRomWarps), block_rows, 19 + buf);
     if (flags & 2u) StoreCta<kPhase>(P, out_smem, P.cta_lists + P.rom_list0 + cta * kNEE + e, jac, tile, nb, st, 3, kRomDurWin, 20 + buf);
 #endif
   }
@@ -1323,8 +1380,9 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
 // node groups: blockIdx.y = instance tile, warp = one of kNodeWarps consecutive groups
 __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
                                          int* __restrict__ status, const int* __restrict__ terrain_ids, int default_terrain, int nb,
-                                         unsigned flags, double* node_smem, int cta, int tile, const Stage st) {
+                                         unsigned flags, double* node_smem, int cta, int tile, const Stage st, double* __restrict__ g = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool g_direct = TWB_GDIRECT && g != nullptr;
   const int gi = cta * kNodeWarps + warp, b = TileInstance(P.nc_jac, tile, lane);
   double* t = node_smem + (size_t)warp * P.node_rows * kLD;
   if (gi < P.n_groups) {
@@ -1356,7 +1414,29 @@ __device__ __forceinline__ void NodeBody(const Plan& P, const double* __restrict
     }
     FlagNonFinite(t, n_rows, lane, status, b, nb);
 #endif
-    if (flags & 1u) {
+    if ((flags & 1u) && g_direct) {   // the group's consecutive rows, this warp's own state: lanes = (instance, row) pairs
+      const int g_row0 = __ldg(&grp->g_row0), nc = P.nc_jac, n_inst = TileCount(nc, tile, nb);
+      __syncwarp();
+      if (g_row0 >= 0) {
+        const int d0 = __ldg(&grp->g_d0), gn = __ldg(&grp->g_n);
+        if (gn <= 32) {   // lane = (row i, instance j0), then every `per`-th instance
+          const int per = 32 / gn, j0 = lane / gn, i = lane - j0 * gn;
+          if (j0 < per) {
+            const double* src = t + (d0 + i) * kLD;
+            double* dst = g + (size_t)TileInstance(nc, tile, j0) * P.m + g_row0 + i;
+            const size_t step = (size_t)per * nc * P.m;
+            for (int j = j0; j < n_inst; j += per, dst += step) StoreG(dst, src[j]);
+          }
+        } else {
+          for (int j = 0; j < n_inst; ++j)
+            for (int i = lane; i < gn; i += 32) StoreG(g + (size_t)TileInstance(nc, tile, j) * P.m + g_row0 + i, t[(d0 + i) * kLD + j]);
+        }
+      } else {
+        const OutRange r = LoadRange(&grp->values);
+        ForEachEntry(P.pairs + r.first, P.coefs + r.first, r.count, lane,
+                     [&](int g_row, int d, double c) { if (b < nb) StoreG(g + (size_t)b * P.m + g_row, t[d * kLD + lane] * c); });
+      }
+    } else if (flags & 1u) {
       const int g_row0 = __ldg(&grp->g_row0);
       if (g_row0 >= 0) {
         const int d0 = __ldg(&grp->g_d0), gn = __ldg(&grp->g_n);
@@ -1716,9 +1796,11 @@ __global__ void __launch_bounds__(kWarps * 32, TWB_CTAS) EvalOut(const Plan P, c
 template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kDynWarps * 32, TWB_DYN_CTAS) DynOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                            double* __restrict__ jac, int* __restrict__ status, int nb, unsigned flags,
-                                                           int stage_off, int stage_cap, const double* __restrict__ FS) {
+                                                           int stage_off, int stage_cap, const double* __restrict__ FS, double* __restrict__ g,
+                                                           int* __restrict__ tile_done, int done_total) {
   extern __shared__ __align__(16) double out_smem[];
-  DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, Stage{out_smem + stage_off, stage_cap}, FS);
+  DynBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, Stage{out_smem + stage_off, stage_cap}, FS, g);
+  TileDone(tile_done, done_total, XT, P.n, P.nc_jac, blockIdx.y, nb);
 #if TWB_TMA
   if ((threadIdx.x & 31) == 0) BulkWaitAll();   // the staging rows stay allocated until the last copy has left
 #endif
@@ -1740,7 +1822,8 @@ template <int kNEE, bool kPhase>
 __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const Plan P, const double* __restrict__ XT, double* __restrict__ GT,
                                                                double* __restrict__ jac, int* __restrict__ status,
                                                                const int* __restrict__ terrain_ids, int default_terrain, int nb, unsigned flags,
-                                                               int stage_off, int stage_cap) {
+                                                               int stage_off, int stage_cap, double* __restrict__ g,
+                                                               int* __restrict__ tile_done, int done_total) {
   extern __shared__ __align__(16) double out_smem[];
   static_assert(kRomWarps == kNodeWarps, "TWB_ROMNODE needs equal CTA sizes");
   const Stage st{out_smem + stage_off, stage_cap};
@@ -1751,15 +1834,17 @@ __global__ void __launch_bounds__(kRomWarps * 32, TWB_ROM_CTAS) RomNodeOut(const
   const int n_node_ctas = (P.n_groups + kNodeWarps - 1) / kNodeWarps;
   if ((int)blockIdx.x >= n_rom_ctas + n_node_ctas) {   // constant runs: TMA only
     if (flags & 2u) ConstRunBody(P.const_runs, P.const_vals, P.nnz, jac, nb, out_smem, blockIdx.x - n_rom_ctas - n_node_ctas, blockIdx.y);
+    TileDone(tile_done, done_total, XT, P.n, P.nc_jac, blockIdx.y, nb);
     return;
   }
-  if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, st);
+  if ((int)blockIdx.x < n_rom_ctas) RomBody<kNEE, kPhase>(P, XT, GT, jac, status, nb, flags, out_smem, blockIdx.x, blockIdx.y, st, g);
 #ifndef TWB_EXP_NONODE   // (timing experiment: node CTAs return at once)
-  else NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x - n_rom_ctas, blockIdx.y, st);
+  else NodeBody(P, XT, GT, jac, status, terrain_ids, default_terrain, nb, flags, out_smem, blockIdx.x - n_rom_ctas, blockIdx.y, st, g);
 #endif
 #if TWB_TMA
   if ((threadIdx.x & 31) == 0) BulkWaitAll();
 #endif
+  TileDone(tile_done, done_total, XT, P.n, P.nc_jac, blockIdx.y, nb);
 }
 #endif
 #endif
@@ -1780,11 +1865,15 @@ cudaError_t LaunchK(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem
 
 // s: caller's stream (after TransposeIn); a0, a1: auxiliary streams already waiting on the transposition
 template <int kNEE, bool kPhase>
-cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* FS, double* jac, int* status, const int* terrain_ids, int default_terrain,
+cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* FS, double* g_direct, int* tile_done_in, double* jac, int* status, const int* terrain_ids, int default_terrain,
                       int nb, unsigned flags, int tiles, cudaStream_t s, cudaStream_t a0, cudaStream_t a1, int* count) {
   const size_t row_bytes = (size_t)kLD * sizeof(double);
-  const int dyn_rows = 40 + 6 * kNEE, rom_rows = RomBlockRowsP(kNEE, kPhase), node_rows = P.node_rows;
+  const int dyn_rows = DynBlockRows(kNEE), rom_rows = RomBlockRowsP(kNEE, kPhase), node_rows = P.node_rows;
   cudaError_t e = cudaSuccess;
+  // CTAs per tile of the two output kernels (the count that completes a tile's counter, TileDone)
+  const int done_total = (P.n_dyn > 0 ? (P.n_dyn + kDynWarps - 1) / kDynWarps : 0) +
+                         (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps + P.n_const_runs;
+  int* tile_done = (TWB_ROMNODE && !TWB_FUSED) ? tile_done_in : nullptr;
 #if !TWB_FUSED
   // the dynamic rows on stream a0: with optimised durations and a Jacobian evaluation first DynTailOut (the PhaseSpline columns; it
   // leaves the feet's positions and forces in FS), then DynOut (base columns and the constraint values)
@@ -1805,7 +1894,7 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* FS, d
     const size_t smem = state_bytes + (size_t)kDynWarps * (TWB_TMA_BUF * TWB_TMA_G) * stage_cap * sizeof(double);
     if ((err = cudaFuncSetAttribute(DynOut<kNEE, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
     if ((err = LaunchK(DynOut<kNEE, kPhase>, dim3((P.n_dyn + kDynWarps - 1) / kDynWarps, tiles), dim3(kDynWarps * 32), smem, a0, false, P, XT, GT, jac, status, nb, flags,
-                       stage_off, stage_cap, (const double*)(tail ? FS : nullptr))) != cudaSuccess) return err;
+                       stage_off, stage_cap, (const double*)(tail ? FS : nullptr), g_direct, tile_done, done_total)) != cudaSuccess) return err;
     ++*count; TWB_MARK("DynOut", a0);
     return cudaSuccess;
   };
@@ -1832,7 +1921,7 @@ cudaError_t LaunchOut(const Plan& P, const double* XT, double* GT, double* FS, d
     const int n_ctas = (P.n_rom + kRomWarps - 1) / kRomWarps + (P.n_groups + kNodeWarps - 1) / kNodeWarps + P.n_const_runs;
     if (n_ctas > 0) {
       if ((e = LaunchK(RomNodeOut<kNEE, kPhase>, dim3(n_ctas, tiles), dim3(kRomWarps * 32), smem, s, TWB_PDL != 0, P, XT, GT, jac, status, terrain_ids,
-                       default_terrain, nb, flags, stage_off, stage_cap)) != cudaSuccess) return e;
+                       default_terrain, nb, flags, stage_off, stage_cap, g_direct, tile_done, done_total)) != cudaSuccess) return e;
       ++*count; TWB_MARK("RomNodeOut", s);
     }
   }
@@ -2016,6 +2105,8 @@ int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, 
   return (int)cudaGetLastError();
 }
 
+// 1 when the constraint values go through GT and the TransposeOut kernel (optimised durations, experimental variants), else 0
+int TransposeOutPerEval(const Plan& P) { return (TWB_GDIRECT && TWB_ROMNODE && !TWB_FUSED && P.n_phase_defs == 0) ? 0 : 1; }
 int OutKernelsPerEval(const Plan& P, unsigned flags) {
   const int dyn = (P.n_dyn > 0) * ((P.n_phase_defs > 0 && (flags & 2u)) ? 2 : 1);   // DynOut [+ DynTailOut]
 #if TWB_FUSED
@@ -2031,7 +2122,7 @@ int OutKernelsPerEval(const Plan& P, unsigned flags) {
 // instance of x / g / jac).  Streams: `s` carries TransposeIn -> [out kernels] -> TransposeOut; with separate
 // out kernels DynOut / NodeOut (and the CostKernel) run beside RomOut on aux0 / aux1 after the transposition
 // (ev[0]) and are joined back into `s` (ev[1], ev[2]) before TransposeOut.
-int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* FS, double* g, double* jac, double* cost, double* grad,
+int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* FS, int* TD, double* g, double* jac, double* cost, double* grad,
                int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
                cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches) {
   if (nb <= 0) return 0;
@@ -2046,15 +2137,18 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
   const bool fork = !serial && (want_cost || (!TWB_FUSED && out_flags));
   if (fork) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
+  // fixed durations: the output kernels write the constraint values straight into g (no GT, no TransposeOut)
+  const bool direct = TWB_GDIRECT && TWB_ROMNODE && !TWB_FUSED && P.n_phase_defs == 0;
+  double* g_direct = (direct && (out_flags & 1u)) ? g : nullptr;
   if (out_flags) {
     const bool phase = P.n_phase_defs > 0;
     switch (P.n_ee) {
-      case 1: e = phase ? LaunchOut<1, true>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
-                       : LaunchOut<1, false>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
-      case 2: e = phase ? LaunchOut<2, true>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
-                       : LaunchOut<2, false>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
-      case 4: e = phase ? LaunchOut<4, true>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
-                       : LaunchOut<4, false>(P, XT, GT, FS, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 1: e = phase ? LaunchOut<1, true>(P, XT, GT, FS, g_direct, direct ? TD : nullptr, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<1, false>(P, XT, GT, FS, g_direct, direct ? TD : nullptr, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 2: e = phase ? LaunchOut<2, true>(P, XT, GT, FS, g_direct, direct ? TD : nullptr, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<2, false>(P, XT, GT, FS, g_direct, direct ? TD : nullptr, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
+      case 4: e = phase ? LaunchOut<4, true>(P, XT, GT, FS, g_direct, direct ? TD : nullptr, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count)
+                       : LaunchOut<4, false>(P, XT, GT, FS, g_direct, direct ? TD : nullptr, jac, status, terrain_ids, default_terrain, nb, out_flags, tiles, s, aux0, aux1, &count); break;
       default: return (int)cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return (int)e;
@@ -2075,7 +2169,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
     }
     ++count; TWB_MARK("PhaseJac", s);
   }
-  if (out_flags & 1u) { LaunchK(TransposeOut, dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s, false, (const double*)GT, g, P.m, nb, XT, P.n, P.nc_jac); ++count; TWB_MARK("TransposeOut", s); }
+  if ((out_flags & 1u) && !direct) { LaunchK(TransposeOut, dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s, false, (const double*)GT, g, P.m, nb, XT, P.n, P.nc_jac); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
   return (int)cudaGetLastError();
 }

@@ -44,8 +44,10 @@ int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, 
 void SetL2Window(const cudaAccessPolicyWindow* w);
 // number of output kernels one evaluation launches for this plan
 int OutKernelsPerEval(const Plan& P, unsigned flags);
+int TransposeOutPerEval(const Plan& P);
 // FS: scratch of the feet's positions / forces per dynamic sample, [tiles][n_dyn][6 n_ee][32] (optimised durations only, else null)
-int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* FS, double* g, double* jac, double* cost, double* grad,
+// TD: one zero-initialised counter per tile (the output CTAs count themselves; the last one of a tile drops the tile's XT lines)
+int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* FS, int* TD, double* g, double* jac, double* cost, double* grad,
                int* status, const int* terrain_ids, int default_terrain, int nb, unsigned flags, cudaStream_t s,
                cudaStream_t aux0, cudaStream_t aux1, cudaEvent_t* ev, int* launches);
 
