@@ -412,12 +412,15 @@ def run_cuda(args):
     with torch.cuda.stream(cs):
         jac_pinned.copy_(jac, non_blocking=True); g_pinned.copy_(g, non_blocking=True)
     cs.synchronize(); sync_all()
-    t0 = time.perf_counter()
-    for _ in range(3):
+    best = float("inf")
+    for _ in range(5):   # the best of five: a ceiling must not be lowered by a disturbed repetition
+        sync_all()
+        t0 = time.perf_counter()
         with torch.cuda.stream(cs):
             jac_pinned.copy_(jac, non_blocking=True); g_pinned.copy_(g, non_blocking=True)
         cs.synchronize()
-    tc = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+        best = min(best, time.perf_counter() - t0)
+    tc = torch.tensor([best], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tc, op=dist.ReduceOp.MAX)
     d2h_ceiling_s = float(tc.item())
@@ -464,7 +467,8 @@ def run_cuda(args):
                          "traffic": traffic, "traffic_source": "static: ncu --set full capture committed under profiles/ (traffic_bytes_per_launch.json, taken with the same command in a separate profiler run), not measured in this run",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_eval * B, "avg_launch_ms": avg_kernel_ms,
-                         "kernel": "whole evaluation: TransposeIn -> RomNodeOut | DynOut (two streams) -> TransposeOut; "
+                         "kernel": "whole evaluation, replayed as one CUDA graph: TransposeIn -> RomNodeOut | DynOut (two branches; the "
+                                   "constraint values are written by the output CTAs themselves, no TransposeOut with fixed durations); "
                                    "CUDA events on the launching stream around every step of the timed region",
                          "dominant_kernel": dominant},
             "kernels": kernels,

@@ -783,34 +783,48 @@ __device__ __forceinline__ ConstCol TiledCol(const double* base, int b, int rows
   return TileCol(base, grp * nc + rem % nc, rem / nc, rows);
 }
 
-// x[b][i] -> XT[b/32][i][b%32]: 32x32 tiles through shared memory, coalesced on both sides; clears status
+// x[b][i] -> XT[tile][i][lane]: 32x32 tiles through shared memory, coalesced on both sides; clears status.  A CTA moves
+// kTinTiles consecutive column tiles: all their loads are issued before the barrier (more bytes in flight per thread, fewer
+// waves of CTAs for this short, latency-bound kernel that everything else waits for).
+#ifndef TWB_TIN_TILES
+#define TWB_TIN_TILES 1
+#endif
+constexpr int kTinTiles = TWB_TIN_TILES;
 __global__ void __launch_bounds__(256) TransposeIn(const double* __restrict__ x, double* __restrict__ XT,
                                                    int* __restrict__ status, int n, int nb, int nc) {
-  __shared__ double tile[32][33];
+  __shared__ double tile[kTinTiles][32][33];
 #if TWB_PDL
   asm volatile("griddepcontrol.launch_dependents;");   // the dependent output kernel may become resident while this grid drains
 #endif
-  const int i0 = blockIdx.x * 32;
   if (status && blockIdx.x == 0 && threadIdx.y == 0 && TileInstance(nc, blockIdx.y, threadIdx.x) < nb) status[TileInstance(nc, blockIdx.y, threadIdx.x)] = 0;
 #pragma unroll
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int b = TileInstance(nc, blockIdx.y, r), i = i0 + threadIdx.x;
-    if (b < nb && i < n) tile[r][threadIdx.x] = __ldcs(x + (size_t)b * n + i);
+  for (int c = 0; c < kTinTiles; ++c) {
+    const int i0 = (blockIdx.x * kTinTiles + c) * 32;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int b = TileInstance(nc, blockIdx.y, r), i = i0 + threadIdx.x;
+      if (b < nb && i < n) tile[c][r][threadIdx.x] = __ldcs(x + (size_t)b * n + i);
+    }
   }
   __syncthreads();
   double* dst = XT + ((size_t)blockIdx.y * (n + 1)) * 32;
+  const int b = TileInstance(nc, blockIdx.y, threadIdx.x);
 #pragma unroll
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int i = i0 + r, b = TileInstance(nc, blockIdx.y, threadIdx.x);
+  for (int c = 0; c < kTinTiles; ++c) {
+    const int i0 = (blockIdx.x * kTinTiles + c) * 32;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int i = i0 + r;
 #if TWB_XT_EVICT_LAST
-    if (b < nb && i < n) {
-      unsigned long long pol;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-      asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(dst + (size_t)i * 32 + threadIdx.x), "d"(tile[threadIdx.x][r]), "l"(pol) : "memory");
-    }
+      if (b < nb && i < n) {
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(dst + (size_t)i * 32 + threadIdx.x), "d"(tile[c][threadIdx.x][r]), "l"(pol) : "memory");
+      }
 #else
-    if (b < nb && i < n) dst[(size_t)i * 32 + threadIdx.x] = tile[threadIdx.x][r];
+      if (b < nb && i < n) dst[(size_t)i * 32 + threadIdx.x] = tile[c][threadIdx.x][r];
 #endif
+    }
   }
 }
 
@@ -1953,7 +1967,7 @@ int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSam
                      double* out, int nb, cudaStream_t s) {
   if (nb <= 0 || n_steps <= 0) return 0;
   const int tiles = TileTotal(P.nc_jac, nb);
-  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
+  TransposeIn<<<dim3((P.n + 32 * kTinTiles - 1) / (32 * kTinTiles), tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
   const dim3 grid((n_steps + 3) / 4, tiles);
   const bool phase = P.n_phase_defs > 0;
 #define TWB_TRAJ(NEE) (phase ? TrajectoryKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, contact, n_steps, out, nb) \
@@ -1972,7 +1986,7 @@ int LaunchInitialGuess(const Plan& P, const double* x, double* XT, const SplineS
                        double* out, int nb, cudaStream_t s) {
   if (nb <= 0 || n_times <= 0) return 0;
   const int tiles = TileTotal(P.nc_jac, nb);
-  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
+  TransposeIn<<<dim3((P.n + 32 * kTinTiles - 1) / (32 * kTinTiles), tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
   const dim3 grid((n_times + 3) / 4, tiles);
   const bool phase = P.n_phase_defs > 0;
 #define TWB_IG(NEE) (phase ? InitialGuessKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, times, n_times, out, nb) \
@@ -2038,7 +2052,7 @@ __global__ void __launch_bounds__(128) SoftConstraintKernel(const double* __rest
 int LaunchLinearEquality(const Plan& P, const double* x, double* XT, int col0, int n_cols, const double* M, int rows, double* g, int nb, cudaStream_t s) {
   if (nb <= 0 || rows <= 0) return 0;
   const int tiles = TileTotal(P.nc_jac, nb);
-  TransposeIn<<<dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
+  TransposeIn<<<dim3((P.n + 32 * kTinTiles - 1) / (32 * kTinTiles), tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
   LinearEqualityKernel<<<dim3((rows + 3) / 4, tiles), 128, 0, s>>>(XT, P.n, col0, n_cols, M, rows, g, nb, P.nc_jac);
   return (int)cudaGetLastError();
 }
@@ -2133,7 +2147,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
   const unsigned out_flags = flags & 3u;
   const bool want_cost = (flags & 4u) && P.n_cost > 0;
   TWB_MARK("begin", s);
-  LaunchK(TransposeIn, dim3((P.n + 31) / 32, tiles), dim3(32, 8), 0, s, false, x, XT, status, P.n, nb, P.nc_jac); ++count; TWB_MARK("TransposeIn", s);
+  LaunchK(TransposeIn, dim3((P.n + 32 * kTinTiles - 1) / (32 * kTinTiles), tiles), dim3(32, 8), 0, s, false, x, XT, status, P.n, nb, P.nc_jac); ++count; TWB_MARK("TransposeIn", s);
   const bool fork = !serial && (want_cost || (!TWB_FUSED && out_flags));
   if (fork) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
