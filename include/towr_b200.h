@@ -208,7 +208,9 @@ int twb_batch_goal_instances_device(twb_batch* b, const double* goals, double* x
  * `stream` is a cudaStream_t (NULL = default stream); the call only enqueues.
  * jac must be 16-byte aligned (cudaMalloc'ed arrays are; an odd-offset view of one is not): TWB_ERR_INVALID otherwise.
  * A batch serves ONE evaluation / post-processing call at a time: its staging matrices and fork / join events are shared,
- * so a second call on another stream must be ordered after the first by the caller. */
+ * so a second call on another stream must be ordered after the first by the caller.
+ * The kernels of an evaluation are captured once per argument set (pointers + flags) and replayed as a CUDA graph launched
+ * into `stream` (up to 16 sets cached per batch; environment TWB_GRAPH=0: plain launches). */
 int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
                           double* cost, double* grad, int* status,
                           unsigned flags, void* stream);
