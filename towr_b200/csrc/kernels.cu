@@ -770,6 +770,7 @@ __device__ __forceinline__ int TileInstance(int nc, int tile, int lane) {
   return nc == 1 ? tile * 32 + lane : (tile / nc) * (32 * nc) + lane * nc + tile % nc;
 }
 __device__ __forceinline__ int TileCount(int nc, int tile, int nb) {   // valid lanes of the tile (a prefix)
+  if (nc == 1) return max(0, min(32, nb - tile * 32));
   const int first = TileInstance(nc, tile, 0);
   return first >= nb ? 0 : min(32, (nb - first + nc - 1) / nc);
 }
@@ -1365,8 +1366,21 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
 #pragma unroll
       for (int d = 0; d < 3; ++d) Sk[9 + buf + i * 3 + d] = D[i][d];
     if (valid) {
-      if (e == 0) FlagNonFinite(t, 10, lane, status, b, nb);
-      FlagNonFinite(t, (kPhase ? 19 : 22) + buf, lane, status, b, nb, 10 + buf);
+      // non-finite check of this lane's R^T (first foot), D_e and g_e, from the registers
+      double chk = 0.0;
+      if (e == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) chk = fma(R[i][d], 0.0, chk);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        chk = fma(ge[i], 0.0, chk);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) chk = fma(D[i][d], 0.0, chk);
+      }
+      if (status && chk != chk && b < nb) atomicOr(status + b, 1);
     }
 #endif
     if (valid && (flags & 1u) && !g_direct) {   // rows rom_row0[e] + 3k .. + 2 (range_of_motion_constraint.cc:58-66), lane = instance into GT
@@ -1771,7 +1785,7 @@ __device__ __noinline__ void ConstRunBody(const ConstRun* __restrict__ runs, con
                  ::"r"(SmemAddr(smem)), "l"(vals + r.src), "r"(bytes), "r"(mb) : "memory");
     unsigned done = 0;
     while (!done)
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0, %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb), "r"(2000u) : "memory");   // (suspend-time hint: the thread sleeps in the wait instead of spinning)
   }
   __syncthreads();   // the values are in shared memory (written by the async proxy, observed through the mbarrier by thread 0)
   if (threadIdx.x < 32 && b0 + (int)threadIdx.x < nb) {
