@@ -92,8 +92,11 @@ def load_spec_fixture(workload):
 def oracle_iterates(spec, batch, seed=1234):
     """The iterate distribution of towr_b200.configs.synthetic_iterates_fast (x0 + sigma N(0,1); sigma 0.05 / 0.2 / 10 / 50),
     built from the ORACLE's x0 and variable-set layout only."""
+    import importlib.util
     import numpy as np
     import oracle_lib
+    sp_ = importlib.util.spec_from_file_location("twb_spec_struct", os.path.join(ROOT, "towr_b200", "_spec.py"))
+    mod = importlib.util.module_from_spec(sp_); sp_.loader.exec_module(mod)
     o = oracle_lib.Oracle(spec)
     x0 = o.x0()
     sig = np.zeros(o.n)
@@ -103,7 +106,7 @@ def oracle_iterates(spec, batch, seed=1234):
         if name.startswith("base-"):
             sig[start:start + count] = np.where((idx % 6) < 3, 0.05, 0.2)
         elif name.startswith("ee-motion"):
-            sig[start:start + count] = 0.05
+            sig[start:start + count] = np.where(np.array(mod.motion_velocity_mask(spec, int(name[len("ee-motion_"):]))), 0.2, 0.05)
         elif name.startswith("ee-force"):
             sig[start:start + count] = np.where((idx % 2) == 0, 10.0, 50.0)
     rng = np.random.default_rng(seed)

@@ -46,3 +46,32 @@ class Spec(C.Structure):
     ]
 
 
+
+
+def motion_velocity_mask(spec, ee):
+    """True for the velocity variables of the phase-based set ee-motion_<ee>, in variable order
+    (nodes_variables_phase_based.cc:190-253: a swing node holds px, vx, py, vy, pz; the two nodes of a stance phase share
+    px, py, pz and have no velocity variables).  Pure Python on the spec: bench.py's reference arm uses it without the library."""
+    polys = []                      # True: polynomial of a constant (stance) phase
+    const = bool(spec.in_contact_at_start[ee])
+    for _ in range(spec.n_phases[ee]):
+        polys += [True] if const else [False] * spec.ee_polynomials_per_swing_phase
+        const = not const
+    n_nodes = len(polys) + 1
+
+    def const_node(i):
+        if i == 0:
+            return polys[0]
+        if i == n_nodes - 1:
+            return polys[-1]
+        return polys[i - 1] or polys[i]
+
+    mask, nd = [], 0
+    while nd < n_nodes:
+        if const_node(nd):
+            mask += [False, False, False]
+            nd += 2
+        else:
+            mask += [False, True, False, True, False]
+            nd += 1
+    return mask

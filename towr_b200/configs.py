@@ -5,6 +5,7 @@ plus the synthetic-iterate generator shared by tests and bench.py
 import numpy as np
 
 from . import _capi as capi
+from ._spec import motion_velocity_mask
 from .formulation import GaitGenerator, NlpFormulation, robot_info
 
 
@@ -76,7 +77,9 @@ def variable_sigma(problem):
         if name.startswith("base-"):
             s = np.where((idx % 6) < 3, 0.05, 0.2)
         elif name.startswith("ee-motion"):
-            s = np.full(count, 0.05)     # positions and (few) velocities alike: keeps feet near the plan
+            vel = np.array(motion_velocity_mask(spec, int(name[len("ee-motion_"):])))
+            assert vel.size == count
+            s = np.where(vel, 0.2, 0.05)
         elif name.startswith("ee-force"):
             s = np.where((idx % 2) == 0, 10.0, 50.0)
         else:                            # ee-schedule durations are perturbed multiplicatively by the caller
