@@ -95,9 +95,20 @@ struct twb_batch {
   std::vector<EvalGraph> graphs;
   unsigned long long graph_clock = 0;
   int use_graphs = 1;             // TWB_GRAPH=0 disables; set to 0 when a capture fails
+  // twb_batch_eval_device walks batches of 1.5 .. 3.5 x this many instances in chunks (one after the other on the same streams).
+  // Measured (profiles/README.md, experiment 55; fixed durations): 8192 instances in one go cost 145.8 us per 4096 — the
+  // pipeline's weakest size — against 137 us in two chunks; 16 384 and more are as fast (or faster) in one go.  0: never.
+  size_t eval_chunk = 4096;
 };
 
 namespace {
+// instances per chunk of twb_batch_eval_device (twb_batch::eval_chunk): the whole batch unless it is 1.5 .. 3.5 chunks long
+size_t EvalChunk(const twb_batch* b) {
+  const size_t B = (size_t)b->B, group = 32 * (size_t)std::max(b->plan.nc_jac, 1);
+  if (!b->eval_chunk || g_prof_on || b->plan.n_phase_defs > 0) return B;
+  const size_t chunk = (b->eval_chunk + group - 1) / group * group;
+  return (2 * B >= 3 * chunk && 2 * B <= 7 * chunk) ? chunk : B;
+}
 // cached graphs hold the batch's plan and buffers by value: dropped whenever those change
 void DropGraphs(twb_batch* b) {
   for (auto& gr : b->graphs) cudaGraphExecDestroy(gr.exec);
@@ -226,6 +237,7 @@ int twb_batch_create(const twb_problem* p, int batch_size, int device, twb_batch
   if (g_prof_on) std::fprintf(stderr, "[twb profile] n=%d m=%d nnz=%d\n", b->plan.n, b->plan.m, b->plan.nnz);
   if (const char* v = std::getenv("TWB_E2E_CHUNK")) b->e2e_chunk = std::max(32, std::atoi(v));
   if (const char* v = std::getenv("TWB_GRAPH")) b->use_graphs = std::atoi(v) != 0;
+  if (const char* v = std::getenv("TWB_EVAL_CHUNK")) b->eval_chunk = (size_t)std::max(0, std::atoi(v));
   // whole groups of nc interleaved tiles (kernels.cu: TileInstance); nc = 1 unless the Jacobian row length is not a multiple of 4
   const size_t group = 32 * (size_t)std::max(b->plan.nc_jac, 1);
   b->ld = ((size_t)batch_size + group - 1) / group * group;
@@ -574,6 +586,10 @@ int twb_batch_launches_per_eval(const twb_batch* b, unsigned flags) {
   if ((flags & (TWB_EVAL_G | TWB_EVAL_JAC)) && p.n_phase_units > 0) n += 1;   // PhaseJac
   if (flags & TWB_EVAL_G) n += twb::TransposeOutPerEval(p);   // TransposeOut (not with fixed durations: the values are written directly)
   if (want_cost) n += 1;
+  {   // large batches are evaluated chunk after chunk (twb_batch::eval_chunk)
+    const size_t B = (size_t)b->B, chunk = EvalChunk(b);
+    n *= (int)((B + chunk - 1) / chunk);
+  }
   return n;
 }
 
@@ -591,6 +607,22 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   if (f.has_cost && (flags & TWB_EVAL_COST)) kflags |= TWB_EVAL_COST;
   int launches = 0;
   twb::SetL2Window(b->use_l2_window ? &b->l2_window : nullptr);
+  // the whole batch, or chunk after chunk (twb_batch::eval_chunk), enqueued on s0 and the batch's two auxiliary streams
+  auto enqueue = [&](cudaStream_t s0) -> int {
+    const size_t B = (size_t)b->B;
+    const size_t chunk = EvalChunk(b);
+    const size_t n = f.n, m = f.m;
+    for (size_t off = 0; off < B; off += chunk) {
+      const size_t nb = std::min(chunk, B - off), t0 = off / 32;
+      const int rc = twb::LaunchEval(b->plan, x + off * n, b->d_XT + t0 * (n + 1) * 32, b->d_GT + t0 * (size_t)std::max(f.m, 1) * 32,
+                                     b->d_FS ? b->d_FS + t0 * (size_t)b->plan.n_dyn * 6 * b->plan.n_ee * 32 : nullptr, b->d_TD + t0,
+                                     g ? g + off * m : nullptr, jac ? jac + off * (size_t)f.nnz : nullptr, cost ? cost + off : nullptr,
+                                     grad ? grad + off * n : nullptr, status ? status + off : nullptr,
+                                     b->d_terrain ? b->d_terrain + off : nullptr, f.spec.terrain, (int)nb, kflags, s0, b->aux0, b->aux1, b->ev.data(), &launches);
+      if (rc != 0) return rc;
+    }
+    return 0;
+  };
   if (b->use_graphs && !g_prof_on) {
     // replay (or first capture on the batch's own stream) the evaluation of this argument set as a CUDA graph
     twb_batch::EvalGraph* hit = nullptr;
@@ -600,8 +632,7 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
       cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
       bool ok = cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
       if (ok) {
-        const int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, b->d_FS, b->d_TD, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
-                                       kflags, b->stream, b->aux0, b->aux1, b->ev.data(), &launches);
+        const int rc = enqueue(b->stream);
         ok = cudaStreamEndCapture(b->stream, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
       }
       ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
@@ -625,8 +656,7 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
       return TWB_OK;
     }
   }
-  int rc = twb::LaunchEval(b->plan, x, b->d_XT, b->d_GT, b->d_FS, b->d_TD, g, jac, cost, grad, status, b->d_terrain, f.spec.terrain, b->B,
-                           kflags, static_cast<cudaStream_t>(stream), b->aux0, b->aux1, b->ev.data(), &launches);
+  int rc = enqueue(static_cast<cudaStream_t>(stream));
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
   b->launches_last = launches;
   return TWB_OK;
