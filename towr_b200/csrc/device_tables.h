@@ -150,6 +150,7 @@ struct OutList {                        // per alignment class
 #ifndef TWB_WARPS
 #define TWB_WARPS 5
 #endif
+#define TWB_ROMNODE 0
 constexpr int kWarps = TWB_WARPS;
 constexpr int kDynWarps = kWarps, kRomWarps = kWarps, kNodeWarps = kWarps;
 #else
