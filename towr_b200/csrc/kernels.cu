@@ -443,7 +443,7 @@ struct TerrainPoint { double h, hx, hy, hxx; };
 // <= -1 or NaN converts to a huge cell index, i.e. "outside").
 // the height grids of a batch, by value: the grid terrains are evaluated out of line (EvalGridTerrain), so that their code —
 // five bilinear look-ups per point for the grid_map layer — exists once per kernel instead of once per inlined call site
-// (RomNodeOut shrank from 12 952 to SASS instructions; its instruction-cache misses were 9 % of the stall samples)
+// (RomNodeOut shrank from 12 952 to 8 456 SASS instructions; the step time did not change)
 struct GridArgs {
   const double* grid; int grid_rows, grid_cols;
   const float* gmap; int gmap_sx, gmap_sy; double gmap_res, gmap_px, gmap_py;
