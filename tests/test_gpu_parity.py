@@ -201,6 +201,50 @@ def test_device_pointer_variant_matches_host_variant():
     assert np.array_equal(g.cpu().numpy(), host["g"]) and np.array_equal(jac.cpu().numpy(), host["jac"])
 
 
+def test_device_variant_graph_cache_and_chunks():
+    """twb_batch_eval_device replays a CUDA graph per argument set (16 cached, least recently used replaced, dropped when the
+    terrains change) and walks batches of 1.5 - 3.5 x 4096 instances in chunks: 20 argument sets in rotation, a terrain change
+    in between, the legacy default stream, a 6144-instance batch — every result equals the host-pointer variant's bit for bit."""
+    import torch
+    f = tb.make_formulation("anymal_trot_block"); p = tb.Problem(f.to_spec())
+    B = 70
+    bt = p.batch(B)
+    Xs = [synthetic_iterates_fast(p, B, seed=500 + i) for i in range(20)]
+    want = [bt.eval_host(X) for X in Xs]
+    xd = [torch.from_numpy(X).cuda() for X in Xs]
+    outs = [(torch.empty((B, p.m), dtype=torch.float64, device="cuda"), torch.empty((B, p.nnz), dtype=torch.float64, device="cuda"),
+             torch.empty(B, dtype=torch.int32, device="cuda")) for _ in range(3)]
+    for rounds in range(2):                      # second round: sets 0 .. 3 were evicted from the cache and are captured again
+        for i in range(20):
+            g, jac, st = outs[i % 3]
+            bt.eval_device(xd[i], g=g, jac=jac, status=st)          # current (legacy default) stream
+            torch.cuda.synchronize()
+            assert np.array_equal(g.cpu().numpy(), want[i]["g"]) and np.array_equal(jac.cpu().numpy(), want[i]["jac"])
+    terr = np.full(B, tb.SLOPE, dtype=np.int32); terr[::3] = tb.GAP
+    bt.set_terrains(terr)                        # cached graphs hold the old terrain pointer: must be dropped
+    ref = bt.eval_host(Xs[0])
+    g, jac, st = outs[0]
+    bt.eval_device(xd[0], g=g, jac=jac, status=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(jac.cpu().numpy(), ref["jac"]) and not np.array_equal(ref["jac"], want[0]["jac"])
+    g_only = torch.zeros_like(g)
+    bt.eval_device(xd[0], g=g_only, status=st, flags=capi.EVAL_G)   # same pointers, other flags: another graph
+    torch.cuda.synchronize()
+    assert np.array_equal(g_only.cpu().numpy(), ref["g"])
+    # chunked evaluation: 6144 instances = 1.5 chunks
+    B2 = 6144
+    X2 = synthetic_iterates_fast(p, B2, seed=9)
+    b2 = p.batch(B2)
+    h2 = b2.eval_host(X2)
+    x2 = torch.from_numpy(X2).cuda()
+    g2 = torch.empty((B2, p.m), dtype=torch.float64, device="cuda"); j2 = torch.empty((B2, p.nnz), dtype=torch.float64, device="cuda")
+    s2 = torch.empty(B2, dtype=torch.int32, device="cuda")
+    b2.eval_device(x2, g=g2, jac=j2, status=s2)
+    torch.cuda.synchronize()
+    assert np.array_equal(g2.cpu().numpy(), h2["g"]) and np.array_equal(j2.cpu().numpy(), h2["jac"]) and not s2.any().item()
+    assert b2.launches_per_eval() == 2 * bt.launches_per_eval()
+
+
 def test_full_size_properties_config2():
     """BASELINE configs[1] at full size (4096): determinism, instance independence (permutation
     equivariance), iterate-independent entries constant across the batch, and oracle parity on a
