@@ -398,3 +398,81 @@ def test_postprocessing_golden_fixtures():
         assert np.allclose(o.initial_guesses(x, z["times"]), z[f"{name}_initial_guesses"], rtol=1e-13, atol=1e-13)
         plan = o.footstep_plan(x, float(z["time_horizon"]))
         assert plan.shape == z[f"{name}_footstep_plan"].shape and np.allclose(plan, z[f"{name}_footstep_plan"], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("name,robot", [("anymal_trot_block", tb.ANYMAL), ("hyq_gallop_gap", tb.HYQ)])
+def test_dynamic_and_range_of_motion_values_against_scipy(name, robot):
+    """The oracle's constraint VALUES of the two big sets, recomputed with independent library code: scipy's rotations for the
+    Euler convention (intrinsic Z-Y'-X'', euler_converter.cc:207-221) and numerical differentiation of those rotations for the
+    angular velocity / acceleration in the world frame (euler_converter.cc:58-83), numpy for the single-rigid-body equations
+    (single_rigid_body_dynamics.cc:76-101) and the range-of-motion vector (range_of_motion_constraint.cc:58-66).  Pins the row
+    order (angular rows first), every sign, the inertia convention (products of inertia enter negated) and gravity."""
+    from scipy.spatial.transform import Rotation
+    spec = tb.make_formulation(name).to_spec()
+    o = oracle_lib.Oracle(spec)
+    p = tb.Problem(spec)
+    x = synthetic_iterates(p, 1, seed=11)[0]
+    g = o.eval(x)["g"]
+    info = tb.robot_info(robot)
+    n_ee, mass = info["n_ee"], info["mass"]
+    ixx, iyy, izz, ixy, ixz, iyz = info["inertia"]
+    I_b = np.array([[ixx, -ixy, -ixz], [-ixy, iyy, -iyz], [-ixz, -iyz, izz]])
+    sets = {nm: (r0, nr) for nm, r0, nr in o.constraint_sets()}
+
+    def rot(euler):                       # towr stores roll, pitch, yaw; applied Z (yaw), Y' (pitch), X'' (roll)
+        return Rotation.from_euler("ZYX", [euler[2], euler[1], euler[0]]).as_matrix()
+
+    def state(t):                         # base position, Euler angles; feet positions, forces; base acceleration
+        ig = o.initial_guesses(x, np.array([t]))[0]
+        return ig[1:4], ig[4:7], ig
+
+    def vee(S):
+        return np.array([S[2, 1] - S[1, 2], S[0, 2] - S[2, 0], S[1, 0] - S[0, 1]]) / 2.0
+
+    # The dynamic samples sit exactly on the junctions of the base polynomials (both 0.1 s), where the acceleration jumps and
+    # Spline::GetSegmentID selects the polynomial that ENDS there: derivatives from the left, 4th-order backward stencil.
+    def dleft(f, t, h):
+        return (25 * f(t) - 48 * f(t - h) + 36 * f(t - 2 * h) - 16 * f(t - 3 * h) + 3 * f(t - 4 * h)) / (12 * h)
+
+    def omega(t, h=1e-4):                 # vee(dR/dt R^T) of scipy rotations (truncation 6e-12 at this step: the error falls as h^4)
+        return vee(dleft(lambda u: rot(state(u)[1]), t, h) @ rot(state(t)[1]).T)
+
+    dt = 0.1
+    traj = o.trajectory(x, dt)            # samples at 0, 0.1, ...: base lin p v a | quaternion | omega | omega_dot | feet: contact, p, v, a, f
+    r0, nr = sets["dynamic"]
+    T = 2.0
+    worst = 0.0
+    for k in range(1, nr // 6 - 1):       # interior samples (the differences need t +- h inside the horizon)
+        t = k * dt
+        s = traj[k]
+        c, cdd = s[0:3], s[6:9]
+        R = rot(state(t)[1])
+        w = omega(t)
+        wd = dleft(omega, t, 5e-4)
+        I_w = R @ I_b @ R.T
+        fsum, tau = np.zeros(3), np.zeros(3)
+        for e in range(n_ee):
+            foot = s[19 + 13 * e: 19 + 13 * (e + 1)]
+            pe, f = foot[1:4], foot[10:13]
+            fsum += f
+            tau += np.cross(pe - c, f)
+        ang = I_w @ wd + np.cross(w, I_w @ w) - tau
+        lin = mass * cdd - fsum - np.array([0.0, 0.0, -mass * 9.80665])
+        ref = np.concatenate([ang, lin])
+        got = g[r0 + 6 * k: r0 + 6 * k + 6]
+        scale = max(1.0, np.abs(ref).max())
+        worst = max(worst, np.abs(got - ref).max() / scale)
+        # the oracle's own world-frame angular velocity / acceleration (fpowr::GetTrajectory) against the differentiated rotations
+        assert np.allclose(s[13:16], w, atol=1e-9, rtol=1e-9) and np.allclose(s[16:19], wd, atol=1e-6, rtol=1e-6)
+    assert worst < 1e-6, worst            # limited by the second numerical derivative, not by the formulas
+    # range of motion: g_e = R^T (p_e - c) at t = k * 0.08 (+ the horizon end)
+    dtr = 0.08
+    trr = o.trajectory(x, dtr)
+    for e in range(n_ee):
+        r0, nr = sets[f"rangeofmotion-{e}"]
+        for k in range(nr // 3 - 1):      # (the last sample sits at T, off the 0.08 grid)
+            s = trr[k]
+            R = rot(state(k * dtr)[1])
+            pe = s[19 + 13 * e + 1: 19 + 13 * e + 4]
+            ref = R.T @ (pe - s[0:3])
+            assert np.allclose(g[r0 + 3 * k: r0 + 3 * k + 3], ref, atol=1e-11, rtol=1e-11), (e, k)
