@@ -215,6 +215,17 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
                           double* cost, double* grad, int* status,
                           unsigned flags, void* stream);
 
+/* One step of a device-resident multi-start solver loop on the outputs of twb_batch_eval_device — the stand-in for the IPOPT
+ * solves of the reference's drivers (towr/test/hopper_example.cc:77-93, fpowr/src/footstep_plan_server.cc:222-236; IPOPT is
+ * not part of this library): a Levenberg-Marquardt FEASIBILITY step for every instance,
+ *   r = violation of g against the constraint bounds, Js = diag(s) J with s_i = 1 / max(1, max_k |J_ik|),
+ *   (Js^T Js + mu I) dx = -Js^T (s r) by `cg_iters` conjugate-gradient iterations, x <- clip(x + dx min(1, cap / max|dx|)).
+ * x [B][n] in / out, g [B][m] and jac [B][nnz] as written by twb_batch_eval_device, x_lower / x_upper [B][n] per-instance
+ * variable bounds (both NULL: the problem's own), violation [B] out = max |s r| before the step (may be NULL).  All device
+ * pointers; the call only enqueues on `stream`.  Deterministic (fixed summation orders, no atomics). */
+int twb_batch_lm_step_device(twb_batch* b, double* x, const double* g, const double* jac, const double* x_lower,
+                             const double* x_upper, double mu, double cap, int cg_iters, double* violation, void* stream);
+
 /* Host-pointer variant: copies x up, evaluates, copies the requested outputs
  * back and synchronises. Pinned host memory makes the copies asynchronous. */
 int twb_batch_eval_host(twb_batch* b, const double* x, double* g, double* jac,

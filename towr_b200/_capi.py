@@ -49,6 +49,7 @@ def _load():
         "twb_batch_goal_instances_device": (C.c_int, [P, P, P, P, P, P]),
         "twb_batch_eval_device": (C.c_int, [P, P, P, P, P, P, P, C.c_uint, P]),
         "twb_batch_eval_host": (C.c_int, [P, P, P, P, P, P, P, C.c_uint]),
+        "twb_batch_lm_step_device": (C.c_int, [P, P, P, P, P, P, C.c_double, C.c_double, C.c_int, P, P]),
         "twb_problem_trajectory_dims": (C.c_int, [P, C.c_double, I, I]),
         "twb_batch_sample_trajectory_host": (C.c_int, [P, P, C.c_double, P]),
         "twb_batch_initial_guess_host": (C.c_int, [P, P, P, C.c_int, P]),

@@ -94,6 +94,9 @@ struct twb_batch {
   struct EvalGraph { const void* x; void *g, *jac, *cost, *grad, *status; unsigned flags; cudaGraphExec_t exec; int launches; unsigned long long used; };
   std::vector<EvalGraph> graphs;
   unsigned long long graph_clock = 0;
+  twb::LmPattern lm_pat{};        // device copies of the pattern, its transpose and the bounds for twb_batch_lm_step_device (first use)
+  const double *d_xl = nullptr, *d_xu = nullptr;
+  bool lm_ready = false;
   int use_graphs = 1;             // TWB_GRAPH=0 disables; set to 0 when a capture fails
   // twb_batch_eval_device walks batches of 1.5 .. 3.5 x this many instances in chunks (one after the other on the same streams).
   // Measured (profiles/README.md, experiment 55; fixed durations): 8192 instances in one go cost 145.8 us per 4096 — the
@@ -659,6 +662,43 @@ int twb_batch_eval_device(twb_batch* b, const double* x, double* g, double* jac,
   int rc = enqueue(static_cast<cudaStream_t>(stream));
   if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "kernel launch");
   b->launches_last = launches;
+  return TWB_OK;
+}
+
+int twb_batch_lm_step_device(twb_batch* b, double* x, const double* g, const double* jac, const double* x_lower, const double* x_upper,
+                             double mu, double cap, int cg_iters, double* violation, void* stream) {
+  if (!b || !x || !g || !jac) return Fail(TWB_ERR_INVALID, "null argument");
+  if ((x_lower == nullptr) != (x_upper == nullptr)) return Fail(TWB_ERR_INVALID, "x_lower and x_upper: both or neither");
+  if (!(mu >= 0.0) || !(cap > 0.0) || cg_iters < 0 || cg_iters > 10000) return Fail(TWB_ERR_INVALID, "bad solver parameter");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return CudaFail(e, "cudaSetDevice");
+  const twb::Formulation& f = b->prob->f;
+  if (twb::LmSharedBytes(f.n, f.m) > 200 * 1024) return Fail(TWB_ERR_UNSUPPORTED, "problem too large for the shared-memory solver step");
+  if (!b->lm_ready) {   // the pattern's transpose: entries of column j in ascending row order (what a stable sort by column yields)
+    std::vector<int> col_ptr(f.n + 1, 0), slot_t(f.nnz), row_t(f.nnz);
+    for (int k = 0; k < f.nnz; ++k) col_ptr[f.col_idx[k] + 1]++;
+    for (int j = 0; j < f.n; ++j) col_ptr[j + 1] += col_ptr[j];
+    std::vector<int> fill(col_ptr.begin(), col_ptr.end() - 1);
+    for (int r = 0; r < f.m; ++r)
+      for (int k = f.row_ptr[r]; k < f.row_ptr[r + 1]; ++k) { const int at = fill[f.col_idx[k]]++; slot_t[at] = k; row_t[at] = r; }
+    if ((e = Upload(f.row_ptr, &b->lm_pat.row_ptr, &b->owned)) != cudaSuccess || (e = Upload(f.col_idx, &b->lm_pat.col_idx, &b->owned)) != cudaSuccess ||
+        (e = Upload(col_ptr, &b->lm_pat.col_ptr, &b->owned)) != cudaSuccess || (e = Upload(slot_t, &b->lm_pat.slot_t, &b->owned)) != cudaSuccess ||
+        (e = Upload(row_t, &b->lm_pat.row_t, &b->owned)) != cudaSuccess || (e = Upload(f.g_lower, &b->lm_pat.g_lower, &b->owned)) != cudaSuccess ||
+        (e = Upload(f.g_upper, &b->lm_pat.g_upper, &b->owned)) != cudaSuccess || (e = Upload(f.x_lower, &b->d_xl, &b->owned)) != cudaSuccess ||
+        (e = Upload(f.x_upper, &b->d_xu, &b->owned)) != cudaSuccess)
+      return CudaFail(e, "pattern upload");
+    if (f.n < 65536 && f.m < 65536 && f.nnz < 65536) {
+      std::vector<uint16_t> c16(f.col_idx.begin(), f.col_idx.end()), s16(slot_t.begin(), slot_t.end()), r16(row_t.begin(), row_t.end());
+      if ((e = Upload(c16, &b->lm_pat.col_idx16, &b->owned)) != cudaSuccess || (e = Upload(s16, &b->lm_pat.slot_t16, &b->owned)) != cudaSuccess ||
+          (e = Upload(r16, &b->lm_pat.row_t16, &b->owned)) != cudaSuccess)
+        return CudaFail(e, "pattern upload");
+    }
+    b->lm_ready = true;
+  }
+  const bool own = x_lower != nullptr;
+  int rc = twb::LaunchLmStep(b->lm_pat, f.n, f.m, f.nnz, x, g, jac, own ? x_lower : b->d_xl, own ? x_upper : b->d_xu, own ? (size_t)f.n : 0, mu, cap,
+                             cg_iters, violation, b->B, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return CudaFail(static_cast<cudaError_t>(rc), "solver step launch");
   return TWB_OK;
 }
 

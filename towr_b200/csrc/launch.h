@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdint>
 
 #include "device_tables.h"
 
@@ -40,6 +41,22 @@ int LaunchSoftConstraint(const Plan& P, const double* g, const double* jac, cons
 // x0 / variable bounds of `nb` goal-randomised instances (goals[b][6] = final base position, final base Euler angles)
 int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, const int* terrain_ids, int default_terrain, double* x0, double* lo,
                         double* up, int nb, cudaStream_t s);
+// ---- device-resident solver step (lm_kernel.cu): the shared sparsity pattern and its transpose, constraint bounds (device pointers)
+struct LmPattern {
+  const int* row_ptr;   // [m + 1]
+  const int* col_idx;   // [nnz]
+  const int* col_ptr;   // [n + 1]  transpose: entries of column j, ascending row
+  const int* slot_t;    // [nnz]    CSR slot of the transposed entry
+  const int* row_t;     // [nnz]    its row
+  const double* g_lower;
+  const double* g_upper;   // [m]
+  const uint16_t *col_idx16, *slot_t16, *row_t16;   // the same index arrays in 16 bits when n, m, nnz < 65 536 (else null)
+};
+size_t LmSharedBytes(int n, int m);
+// one Levenberg-Marquardt feasibility step for nb instances (CTA = instance): x[b][n] in / out, g[b][m], jac[b][nnz] in,
+// bounds x_lower / x_upper at b * bound_stride (0: the same bounds for every instance), violation[b] out (may be null)
+int LaunchLmStep(const LmPattern& pat, int n, int m, int nnz, double* x, const double* g, const double* jac, const double* x_lower,
+                 const double* x_upper, size_t bound_stride, double mu, double cap, int cg_iters, double* violation, int nb, cudaStream_t s);
 // L2 access-policy window applied to the evaluation kernels launched by this thread (null: none)
 void SetL2Window(const cudaAccessPolicyWindow* w);
 // number of output kernels one evaluation launches for this plan

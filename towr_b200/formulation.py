@@ -416,6 +416,20 @@ class Batch:
         check(lib.twb_batch_goal_instances_device(self._h, ptr(goals), ptr(x0), ptr(lo), ptr(up), C.c_void_p(stream.cuda_stream)))
         return x0, lo, up
 
+    def lm_step_device(self, x, g, jac, x_lower=None, x_upper=None, mu=1e-2, cap=0.1, cg_iters=25, violation=None, stream=None):
+        """twb_batch_lm_step_device: one Levenberg-Marquardt feasibility step for every instance on the outputs of
+        eval_device; x (B, n) is updated in place.  All arguments are torch CUDA float64 tensors (bounds: (B, n) or None)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device)
+        p = self.problem
+        for t, count in ((x, self.B * p.n), (g, self.B * p.m), (jac, self.B * p.nnz), (x_lower, self.B * p.n), (x_upper, self.B * p.n),
+                         (violation, self.B)):
+            assert t is None or (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == count), "bad tensor"
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        check(lib.twb_batch_lm_step_device(self._h, ptr(x), ptr(g), ptr(jac), ptr(x_lower), ptr(x_upper), float(mu), float(cap), int(cg_iters),
+                                           ptr(violation), C.c_void_p(stream.cuda_stream)))
+
     def eval_device(self, x, g=None, jac=None, cost=None, grad=None, status=None,
                     flags=capi.EVAL_G | capi.EVAL_JAC, stream=None):
         """Device-pointer variant. Arguments are torch CUDA float64 tensors (or None);

@@ -9,13 +9,13 @@ restoration phase minimises — for every instance of a batch in lock step:
     (Js^T Js + mu I) dx = -Js^T rs                                 (`cg_iters` conjugate-gradient iterations, matrix-free)
     x <- clip(x + dx * min(1, cap / max|dx|), x_lower, x_upper)
 
-The iterates, g, the Jacobian values and all solver vectors stay on the GPU; one `twb_batch_eval_device` call per
-iteration serves all instances.  The sparse products use the problem's ONE shared CSR pattern, laid out once as two
-padded (ELL) index maps — row-wise for J p, column-wise for J^T u — so that every product is a gather, a multiply and a
-fixed-order row sum (deterministic: no atomics).  tests/test_solver_loop.py holds the same algorithm in numpy, driven one
-instance at a time like ifopt by the CPU restatement of the reference; both must walk the same iterates.
-
-PyTorch is used for the dense vector algebra of the SOLVER only; the evaluation is the library's CUDA path.
+The iterates, g, the Jacobian values and all solver vectors stay on the GPU.  An iteration is two library calls:
+`twb_batch_eval_device` (g and the CSR Jacobian values of all instances) and `twb_batch_lm_step_device`
+(towr_b200/csrc/lm_kernel.cu: CTA = instance, the conjugate gradients run in shared memory on the problem's ONE shared
+CSR pattern and its transpose, fixed summation orders, no atomics).  `native=False` keeps the first implementation of the
+same step in PyTorch tensor algebra (padded ELL gathers) — 30 x slower, used by the tests as a second opinion.
+tests/test_solver_loop.py holds the same algorithm in numpy, driven one instance at a time like ifopt by the CPU
+restatement of the reference; all three must walk the same iterates.
 """
 import numpy as np
 
@@ -50,9 +50,10 @@ def ell_maps(row_ptr, col_idx, n):
 class BatchedLevenbergMarquardt:
     """All instances of a `Batch` in lock step, everything on the batch's GPU."""
 
-    def __init__(self, batch, x_lower=None, x_upper=None, mu=1e-2, cap=0.1, cg_iters=25):
+    def __init__(self, batch, x_lower=None, x_upper=None, mu=1e-2, cap=0.1, cg_iters=25, native=True):
         import torch
         self.torch = torch
+        self.native = native
         self.batch, p = batch, batch.problem
         self.p, self.B = p, batch.B
         self.dev = torch.device("cuda", batch.device)
@@ -66,9 +67,11 @@ class BatchedLevenbergMarquardt:
         self.mu, self.cap, self.cg_iters = mu, cap, cg_iters
         B = self.B
         self.g = torch.empty((B, p.m), dtype=torch.float64, device=self.dev)
-        self.jac = torch.empty((B, p.nnz + 1), dtype=torch.float64, device=self.dev)   # one extra zero: the pad slot
+        self.jac = None if native else torch.empty((B, p.nnz + 1), dtype=torch.float64, device=self.dev)   # one extra zero: the pad slot
         self.jac_vals = torch.empty((B, p.nnz), dtype=torch.float64, device=self.dev)
         self.status = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.viol = torch.zeros(B, dtype=torch.float64, device=self.dev)
+        self.xl_full = self.xl.expand(B, p.n).contiguous(); self.xu_full = self.xu.expand(B, p.n).contiguous()
 
     def _violation(self, g):
         t = self.torch
@@ -80,6 +83,9 @@ class BatchedLevenbergMarquardt:
         t = self.torch
         from . import capi
         self.batch.eval_device(X, g=self.g, jac=self.jac_vals, status=self.status, flags=capi.EVAL_G | capi.EVAL_JAC)
+        if self.native:
+            self.batch.lm_step_device(X, self.g, self.jac_vals, self.xl_full, self.xu_full, self.mu, self.cap, self.cg_iters, self.viol)
+            return self.viol.clone()
         self.jac[:, :-1] = self.jac_vals; self.jac[:, -1] = 0.0
         A = self.jac[:, self.rows]                                   # (B, m, W) rows of J
         s = 1.0 / t.clamp(A.abs().amax(dim=2), min=1.0)              # (B, m)
