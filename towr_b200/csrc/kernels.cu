@@ -1594,6 +1594,22 @@ __global__ void __launch_bounds__(32) PhaseJac(const Plan P, const double* __res
   }
 }
 
+// The K values each lane holds for its instance -> out[instance][offset .. offset + K - 1] (row stride `stride` doubles), staged
+// through the warp's shared-memory tile [K][33] so that consecutive lanes write consecutive addresses (a lane writing its own
+// row would touch 32 different sectors per store instruction).
+template <int K>
+__device__ __forceinline__ void StoreRowsCoalesced(const double* o, double* stage, double* __restrict__ out, size_t stride, size_t offset,
+                                                   int nc, int tile, int nb, int lane) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) stage[i * 33 + lane] = o[i];
+  __syncwarp();
+  const int n_inst = TileCount(nc, tile, nb);
+  for (int j = 0; j < n_inst; ++j) {
+    double* dst = out + (size_t)TileInstance(nc, tile, j) * stride + offset;
+    for (int i = lane; i < K; i += 32) dst[i] = stage[i * 33 + j];
+  }
+}
+
 // ---- solution post-processing: fpowr::GetTrajectory (footstep_plan_extractor.h:19-53) --------------------------
 // Eigen::Quaterniond(Matrix3d) (Eigen 3.3 Quaternion.h, quaternionbase_assign_impl<Other,3,3>); q = w, x, y, z
 __device__ __forceinline__ void QuaternionFromMatrix(const double m[3][3], double q[4]) {
@@ -1659,11 +1675,8 @@ __global__ void __launch_bounds__(128) TrajectoryKernel(const Plan P, const doub
       f[0] = (double)__ldg(contact + (size_t)ti * kNEE + e);
     }
   }
-  if (b < nb) {
-    double* dst = out + ((size_t)b * n_steps + ti) * K;
-#pragma unroll
-    for (int i = 0; i < K; ++i) dst[i] = o[i];
-  }
+  extern __shared__ __align__(16) double stage_smem[];
+  StoreRowsCoalesced<K>(o, stage_smem + (size_t)(threadIdx.x >> 5) * K * 33, out, (size_t)n_steps * K, (size_t)ti * K, P.nc_jac, blockIdx.y, nb, lane);
 }
 
 // fpowr::ExtractInitialGuess (initial_guess_extractor.h:17-34) at caller-given times: per sample 49 doubles —
@@ -1689,11 +1702,8 @@ __global__ void __launch_bounds__(128) InitialGuessKernel(const Plan P, const do
     EvalSpline<1, kPhase>(P, sp + 2 + e, xs, pos, unused, o + 13 + 3 * e);
     EvalSpline<0, kPhase>(P, sp + 2 + kNEE + e, xs, o + 13 + 24 + 3 * e, unused, unused);
   }
-  if (b < nb) {
-    double* dst = out + ((size_t)b * n_times + ti) * 49;
-#pragma unroll
-    for (int i = 0; i < 49; ++i) dst[i] = o[i];
-  }
+  extern __shared__ __align__(16) double stage_smem[];
+  StoreRowsCoalesced<49>(o, stage_smem + (size_t)(threadIdx.x >> 5) * 49 * 33, out, (size_t)n_times * 49, (size_t)ti * 49, P.nc_jac, blockIdx.y, nb, lane);
 }
 
 // fpowr::ExtractFootstepPlan (footstep_plan_extractor.h:68-133) without the nearest-plane lookup: the trajectory of
@@ -1999,8 +2009,12 @@ int LaunchTrajectory(const Plan& P, const double* x, double* XT, const SplineSam
   TransposeIn<<<dim3((P.n + 32 * kTinTiles - 1) / (32 * kTinTiles), tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
   const dim3 grid((n_steps + 3) / 4, tiles);
   const bool phase = P.n_phase_defs > 0;
-#define TWB_TRAJ(NEE) (phase ? TrajectoryKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, contact, n_steps, out, nb) \
-                             : TrajectoryKernel<NEE, false><<<grid, 128, 0, s>>>(P, XT, samples, contact, n_steps, out, nb))
+  // dynamic shared memory: the four warps' staging tiles [19 + 13 n_ee][33] of the coalesced stores
+#define TWB_TRAJ(NEE) { const size_t sm = 4 * (size_t)(19 + 13 * NEE) * 33 * sizeof(double);                                                     \
+    if (phase) { cudaFuncSetAttribute(TrajectoryKernel<NEE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                       \
+                 TrajectoryKernel<NEE, true><<<grid, 128, sm, s>>>(P, XT, samples, contact, n_steps, out, nb); }                                 \
+    else { cudaFuncSetAttribute(TrajectoryKernel<NEE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                            \
+           TrajectoryKernel<NEE, false><<<grid, 128, sm, s>>>(P, XT, samples, contact, n_steps, out, nb); } }
   switch (P.n_ee) {
     case 1: TWB_TRAJ(1); break;
     case 2: TWB_TRAJ(2); break;
@@ -2018,8 +2032,11 @@ int LaunchInitialGuess(const Plan& P, const double* x, double* XT, const SplineS
   TransposeIn<<<dim3((P.n + 32 * kTinTiles - 1) / (32 * kTinTiles), tiles), dim3(32, 8), 0, s>>>(x, XT, nullptr, P.n, nb, P.nc_jac);
   const dim3 grid((n_times + 3) / 4, tiles);
   const bool phase = P.n_phase_defs > 0;
-#define TWB_IG(NEE) (phase ? InitialGuessKernel<NEE, true><<<grid, 128, 0, s>>>(P, XT, samples, times, n_times, out, nb) \
-                           : InitialGuessKernel<NEE, false><<<grid, 128, 0, s>>>(P, XT, samples, times, n_times, out, nb))
+#define TWB_IG(NEE) { const size_t sm = 4 * (size_t)49 * 33 * sizeof(double);                                                                    \
+    if (phase) { cudaFuncSetAttribute(InitialGuessKernel<NEE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                     \
+                 InitialGuessKernel<NEE, true><<<grid, 128, sm, s>>>(P, XT, samples, times, n_times, out, nb); }                                 \
+    else { cudaFuncSetAttribute(InitialGuessKernel<NEE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                          \
+           InitialGuessKernel<NEE, false><<<grid, 128, sm, s>>>(P, XT, samples, times, n_times, out, nb); } }
   switch (P.n_ee) {
     case 1: TWB_IG(1); break;
     case 2: TWB_IG(2); break;
