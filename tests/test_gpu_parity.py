@@ -245,6 +245,36 @@ def test_device_variant_graph_cache_and_chunks():
     assert b2.launches_per_eval() == 2 * bt.launches_per_eval()
 
 
+@pytest.mark.parametrize("name,B,durations", [("anymal_trot_block", 45, False), ("biped_walk_stairs", 101, False), ("hyq_gallop_gap", 37, True),
+                                               ("biped_walk_stairs", 70, True), ("hopper", 3, False)])
+def test_no_write_outside_the_output_arrays(name, B, durations):
+    """compute-sanitizer is not available on this GPU pool (profiles/r2_compute_sanitizer_refused.txt): every output array of the
+    device-pointer variant sits between two guard zones filled with a sentinel; after the evaluation the guards are intact and
+    every element between them has been written (ragged batches, odd row lengths = interleaved tiles, optimised durations)."""
+    import torch
+    f = tb.make_formulation(name)
+    if durations:
+        f.params_.OptimizePhaseDurations()
+    p = tb.Problem(f.to_spec())
+    X = torch.from_numpy(synthetic_iterates_fast(p, B, seed=5)).cuda()
+    bt = p.batch(B)
+    guard, sentinel = 4096, -7.25e300
+
+    def guarded(count, dtype, fill):
+        buf = torch.full((count + 2 * guard,), fill, dtype=dtype, device="cuda")
+        return buf, buf[guard:guard + count]
+    gb, g = guarded(B * p.m, torch.float64, sentinel)
+    jb, jac = guarded(B * p.nnz, torch.float64, sentinel)
+    sb, st = guarded(B, torch.int32, 12345)
+    bt.eval_device(X, g=g, jac=jac, status=st)
+    torch.cuda.synchronize()
+    for buf, count, fill in ((gb, B * p.m, sentinel), (jb, B * p.nnz, sentinel), (sb, B, 12345)):
+        assert bool((buf[:guard] == fill).all()) and bool((buf[guard + count:] == fill).all()), "write outside the array"
+        assert not bool((buf[guard:guard + count] == fill).any()), "element left unwritten"
+    host = bt.eval_host(X.cpu().numpy())
+    assert np.array_equal(jac.cpu().numpy().reshape(B, p.nnz), host["jac"]) and np.array_equal(g.cpu().numpy().reshape(B, p.m), host["g"])
+
+
 def test_full_size_properties_config2():
     """BASELINE configs[1] at full size (4096): determinism, instance independence (permutation
     equivariance), iterate-independent entries constant across the batch, and oracle parity on a

@@ -687,6 +687,15 @@ int twb_batch_lm_step_device(twb_batch* b, double* x, const double* g, const dou
         (e = Upload(f.g_upper, &b->lm_pat.g_upper, &b->owned)) != cudaSuccess || (e = Upload(f.x_lower, &b->d_xl, &b->owned)) != cudaSuccess ||
         (e = Upload(f.x_upper, &b->d_xu, &b->owned)) != cudaSuccess)
       return CudaFail(e, "pattern upload");
+    {   // rows / columns in descending length (stable: ties keep their index order)
+      std::vector<int> ro(f.m), co(f.n);
+      for (int i = 0; i < f.m; ++i) ro[i] = i;
+      for (int j = 0; j < f.n; ++j) co[j] = j;
+      std::stable_sort(ro.begin(), ro.end(), [&](int a, int c) { return f.row_ptr[a + 1] - f.row_ptr[a] > f.row_ptr[c + 1] - f.row_ptr[c]; });
+      std::stable_sort(co.begin(), co.end(), [&](int a, int c) { return col_ptr[a + 1] - col_ptr[a] > col_ptr[c + 1] - col_ptr[c]; });
+      if ((e = Upload(ro, &b->lm_pat.row_order, &b->owned)) != cudaSuccess || (e = Upload(co, &b->lm_pat.col_order, &b->owned)) != cudaSuccess)
+        return CudaFail(e, "pattern upload");
+    }
     if (f.n < 65536 && f.m < 65536 && f.nnz < 65536) {
       std::vector<uint16_t> c16(f.col_idx.begin(), f.col_idx.end()), s16(slot_t.begin(), slot_t.end()), r16(row_t.begin(), row_t.end());
       if ((e = Upload(c16, &b->lm_pat.col_idx16, &b->owned)) != cudaSuccess || (e = Upload(s16, &b->lm_pat.slot_t16, &b->owned)) != cudaSuccess ||

@@ -50,6 +50,8 @@ struct LmPattern {
   const int* row_t;     // [nnz]    its row
   const double* g_lower;
   const double* g_upper;   // [m]
+  const int* row_order;    // [m] rows in descending length (balanced warps in the row pass)
+  const int* col_order;    // [n] columns in descending length
   const uint16_t *col_idx16, *slot_t16, *row_t16;   // the same index arrays in 16 bits when n, m, nnz < 65 536 (else null)
 };
 size_t LmSharedBytes(int n, int m);

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(512) LmStepKernel(LmPattern pat, const Idx* __
   const double* __restrict__ g = G + (size_t)b * m;
   // row scales, the scaled values and the scaled violation
   double vmax = 0.0;
-  for (int i = tid; i < m; i += nt) {
+  for (int q = tid; q < m; q += nt) {
+    const int i = __ldg(pat.row_order + q);   // rows in descending length: the lanes of a warp walk rows of similar length
     const int k0 = __ldg(pat.row_ptr + i), k1 = __ldg(pat.row_ptr + i + 1);
     double big = 0.0;
     for (int k = k0; k < k1; ++k) big = fmax(big, fabs(J[k]));
@@ -100,17 +101,19 @@ __global__ void __launch_bounds__(512) LmStepKernel(LmPattern pat, const Idx* __
   };
   // b = -Js^T rs
   double rr = 0.0;
-  for (int j = tid; j < n; j += nt) {
+  for (int q = tid; q < n; q += nt) {
+    const int j = __ldg(pat.col_order + q);
     const double bj = -col_dot(j);
     dx[j] = 0.0; res[j] = bj; pd[j] = bj;
     rr += bj * bj;
   }
   rr = BlockSum(rr, scratch);
   for (int it = 0; it < cg_iters; ++it) {
-    for (int i = tid; i < m; i += nt) u[i] = row_dot(i);
+    for (int q = tid; q < m; q += nt) { const int i = __ldg(pat.row_order + q); u[i] = row_dot(i); }
     __syncthreads();
     double pap = 0.0;
-    for (int j = tid; j < n; j += nt) {   // ap = Js^T (Js p) + mu p
+    for (int q = tid; q < n; q += nt) {   // ap = Js^T (Js p) + mu p
+      const int j = __ldg(pat.col_order + q);
       const double a = col_dot(j) + mu * pd[j];
       ap[j] = a;
       pap += pd[j] * a;
