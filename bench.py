@@ -161,7 +161,7 @@ def kernel_breakdown(p, B):
             name, us = parts[2], float(parts[parts.index("avg") + 1])
             res[name] = {"avg_us": us}
             if name == "TransposeIn":
-                res[name]["note"] = "first kernel of a step: includes the host launch gap of the serialised pass (ncu: 13 us)"
+                res[name]["note"] = "first kernel of a step: includes the host launch gap of the serialised pass (ncu: 8 us)"
                 continue
             if name in alg and us > 0:
                 res[name]["algorithmic_bytes"] = alg[name]

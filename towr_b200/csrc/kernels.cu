@@ -2262,6 +2262,14 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
     }
     if (e != cudaSuccess) return (int)e;
   }
+  if (out_flags && P.n_phase_units > 0) {   // TotalDurationConstraint rows: needs XT only, beside the output kernels on the third stream
+    switch (P.n_ee) {
+      case 1: PhaseJac<1><<<tiles, 32, 0, aux1>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      case 2: PhaseJac<2><<<tiles, 32, 0, aux1>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      default: PhaseJac<4><<<tiles, 32, 0, aux1>>>(P, XT, GT, jac, status, nb, out_flags); break;
+    }
+    ++count; TWB_MARK("PhaseJac", aux1);
+  }
   if (want_cost) {
     if (grad) cudaMemsetAsync(grad, 0, sizeof(double) * (size_t)nb * P.n, aux1);
     CostKernel<<<(nb + 127) / 128, 128, 0, aux1>>>(P, XT, cost, grad, nb); ++count; TWB_MARK("CostKernel", aux1);
@@ -2269,14 +2277,6 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
   if (fork) {
     cudaEventRecord(ev[1], aux0); cudaEventRecord(ev[2], aux1);
     cudaStreamWaitEvent(s, ev[1], 0); cudaStreamWaitEvent(s, ev[2], 0);
-  }
-  if (out_flags && P.n_phase_units > 0) {   // TotalDurationConstraint rows
-    switch (P.n_ee) {
-      case 1: PhaseJac<1><<<tiles, 32, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
-      case 2: PhaseJac<2><<<tiles, 32, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
-      default: PhaseJac<4><<<tiles, 32, 0, s>>>(P, XT, GT, jac, status, nb, out_flags); break;
-    }
-    ++count; TWB_MARK("PhaseJac", s);
   }
   if ((out_flags & 1u) && !direct) { LaunchK(TransposeOut, dim3((P.m + 31) / 32, tiles), dim3(32, 8), 0, s, false, (const double*)GT, g, P.m, nb, XT, P.n, P.nc_jac); ++count; TWB_MARK("TransposeOut", s); }
   if (launches) *launches += count;
