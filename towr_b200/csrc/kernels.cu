@@ -1297,6 +1297,9 @@ __device__ __forceinline__ void StoreCta(const Plan& P, const double* cta_smem, 
   }
 }
 // ---- constraint values straight into g[B][m] (TWB_GDIRECT) ----------------------------------------------------------------
+#ifndef TWB_GDIRECT_PHASE
+#define TWB_GDIRECT_PHASE 1   // 1: problems with optimised durations write g directly as well (their range-of-motion values lane = instance)
+#endif
 #ifndef TWB_G_ST
 #define TWB_G_ST 1   // cache operator of the direct constraint-value stores: 0 .cs (evict-first), 1 default (ships: 132.0 vs 134.5 us per step on config 2 — rows shared by two CTAs merge in the L2)
 #endif
@@ -1440,6 +1443,15 @@ __device__ __forceinline__ void RomBody(const Plan& P, const double* __restrict_
       if (status && chk != chk && b < nb) atomicOr(status + b, 1);
     }
 #endif
+    if (kPhase && TWB_GDIRECT && g != nullptr) {   // optimised durations: g_e exists in registers only; lane = instance straight into g
+#ifndef TWB_EXP_NOCOMPUTE
+      if (valid && (flags & 1u) && b < nb) {
+        double* gp = g + (size_t)b * P.m + P.rom_row0[e] + 3 * k;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) StoreG(gp + i, ge[i]);
+      }
+#endif
+    } else
     if (valid && (flags & 1u) && !g_direct) {   // rows rom_row0[e] + 3k .. + 2 (range_of_motion_constraint.cc:58-66), lane = instance into GT
       double* gt = GT + (((size_t)tile * P.m + (size_t)(P.rom_row0[e] + 3 * k)) * 32) + lane;
 #ifndef TWB_EXP_NOCOMPUTE
@@ -1615,7 +1627,7 @@ __global__ void __launch_bounds__(kNEE * 32, TWB_TAIL_CTAS) DynTailOut(const Pla
 // optimised durations, Jacobian = 1 in each of their columns, status bit 1 when the sum leaves nothing for the last phase
 // (phase_durations.cc:92).  warp = tile of 32 instances, lane = instance; 8 entries per foot at the very end of the CSR row.
 template <int kNEE>
-__global__ void __launch_bounds__(32) PhaseJac(const Plan P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ jac,
+__global__ void __launch_bounds__(32) PhaseJac(const Plan P, const double* __restrict__ XT, double* __restrict__ GT, double* __restrict__ g, double* __restrict__ jac,
                                                int* __restrict__ status, int nb, unsigned flags) {
   const int lane = threadIdx.x, b = TileInstance(P.nc_jac, blockIdx.x, lane);
   const bool live = b < nb;
@@ -1630,7 +1642,10 @@ __global__ void __launch_bounds__(32) PhaseJac(const Plan P, const double* __res
         sum += xs[def.sched0 + i];
         if (live && (flags & 2u)) StoreOut(jac + (size_t)b * P.nnz + slot0 + i, 1.0);
       }
-      if (flags & 1u) GT[((size_t)blockIdx.x * P.m + row) * 32 + lane] = sum;
+      if (flags & 1u) {
+        if (g) { if (live) StoreG(g + (size_t)b * P.m + row, sum); }
+        else GT[((size_t)blockIdx.x * P.m + row) * 32 + lane] = sum;
+      }
       if (live && status && !(def.t_total - sum > 0.0)) atomicOr(status + b, 2);
     }
   }
@@ -2208,7 +2223,7 @@ int LaunchGoalInstances(const Plan& P, const GoalSetup& S, const double* goals, 
 }
 
 // 1 when the constraint values go through GT and the TransposeOut kernel (optimised durations, experimental variants), else 0
-int TransposeOutPerEval(const Plan& P) { return (TWB_GDIRECT && TWB_ROMNODE && !TWB_FUSED && P.n_phase_defs == 0) ? 0 : 1; }
+int TransposeOutPerEval(const Plan& P) { return (TWB_GDIRECT && TWB_ROMNODE && !TWB_FUSED && (TWB_GDIRECT_PHASE || P.n_phase_defs == 0)) ? 0 : 1; }
 int OutKernelsPerEval(const Plan& P, unsigned flags) {
   const int dyn = (P.n_dyn > 0) * ((P.n_phase_defs > 0 && (flags & 2u)) ? 2 : 1);   // DynOut [+ DynTailOut]
 #if TWB_FUSED
@@ -2247,7 +2262,7 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
   if (fork) { cudaEventRecord(ev[0], s); cudaStreamWaitEvent(aux0, ev[0], 0); cudaStreamWaitEvent(aux1, ev[0], 0); }
   cudaError_t e = cudaSuccess;
   // fixed durations: the output kernels write the constraint values straight into g (no GT, no TransposeOut)
-  const bool direct = TWB_GDIRECT && TWB_ROMNODE && !TWB_FUSED && P.n_phase_defs == 0;
+  const bool direct = TWB_GDIRECT && TWB_ROMNODE && !TWB_FUSED && (TWB_GDIRECT_PHASE || P.n_phase_defs == 0);
   double* g_direct = (direct && (out_flags & 1u)) ? g : nullptr;
   if (out_flags) {
     const bool phase = P.n_phase_defs > 0;
@@ -2264,9 +2279,9 @@ int LaunchEval(const Plan& P, const double* x, double* XT, double* GT, double* F
   }
   if (out_flags && P.n_phase_units > 0) {   // TotalDurationConstraint rows: needs XT only, beside the output kernels on the third stream
     switch (P.n_ee) {
-      case 1: PhaseJac<1><<<tiles, 32, 0, aux1>>>(P, XT, GT, jac, status, nb, out_flags); break;
-      case 2: PhaseJac<2><<<tiles, 32, 0, aux1>>>(P, XT, GT, jac, status, nb, out_flags); break;
-      default: PhaseJac<4><<<tiles, 32, 0, aux1>>>(P, XT, GT, jac, status, nb, out_flags); break;
+      case 1: PhaseJac<1><<<tiles, 32, 0, aux1>>>(P, XT, GT, g_direct, jac, status, nb, out_flags); break;
+      case 2: PhaseJac<2><<<tiles, 32, 0, aux1>>>(P, XT, GT, g_direct, jac, status, nb, out_flags); break;
+      default: PhaseJac<4><<<tiles, 32, 0, aux1>>>(P, XT, GT, g_direct, jac, status, nb, out_flags); break;
     }
     ++count; TWB_MARK("PhaseJac", aux1);
   }
