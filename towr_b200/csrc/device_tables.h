@@ -64,7 +64,8 @@ struct PhaseUnit {
 // by the CTA that owns its last element; only sectors shared with another CTA fall back to 8-byte single-element
 // stores.  The alignment of an instance's row inside its sectors depends on (instance * row length) mod 4, so a
 // list exists per alignment class q = instance mod n_classes (n_classes = 1 when the row length is a multiple of 4).
-// The constraint values of a unit go, lane = instance, into the instance-tiled staging matrix GT.
+// The constraint values are written by the CTAs as well (kernels.cu: StoreValuesDirect); the instance-tiled staging matrix GT
+// of round 1 survives in the -DTWB_GDIRECT=0 variants.
 constexpr int kMaxClasses = 4;
 // ---- phase elements (optimised phase durations) ----------------------------------------------------------------------
 // With PhaseSplines a constraint sample's row is structurally dense in ALL node variables of the foot's set
@@ -240,7 +241,7 @@ struct Plan {
   int n, m, nnz, n_ee;
   int n_dyn, n_rom, n_groups, n_cost;
   int node_rows, dyn_rows, rom_rows;   // state rows of one unit's block: node groups (largest), dynamic samples, range-of-motion samples
-  int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz); nc_g = 1 (constraint values go through GT)
+  int nc_jac, nc_g;   // alignment classes of the Jacobian-value rows (length nnz); nc_g = 1 (unused)
   int dyn_list0, rom_list0, node_list0;   // first entry of cta_lists of the dynamic CTAs, (rom CTA, foot) pairs, node CTAs
   int tail_list0;                         // optimised durations: list of dynamic sample k's PhaseSpline columns (DynTailOut) = tail_list0 + k
   int stage_dyn, stage_rom, stage_node;   // longest contiguous run (in doubles, even) of a dynamic / range-of-motion / node list: staging row of the TMA store path

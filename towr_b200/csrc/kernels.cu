@@ -1,17 +1,19 @@
 // kernels.cu — sm_100a kernels of the batched NLP evaluation (fp64).
 //
 // Everything is a data-parallel map with LANE = PROBLEM INSTANCE.  The iterates are first brought into
-// an instance-tiled matrix XT[tile][n+1][32] (tile = 32 consecutive instances, lane = instance), so that
+// an instance-tiled matrix XT[tile][n+1][32] (tile = 32 instances of one alignment class, lane = instance), so that
 // every read of a node value by a warp is one 256-byte row segment:
 //
-//   TransposeIn   x[B][n]   -> XT[tile][n+1][32]   (row n stays 0: "not optimised" node values)
+//   TransposeInP  x[B][n]   -> XT[tile][n+1][32]   (row n stays 0: "not optimised" node values; persistent CTAs)
 //   DynOut        XT        -> CSR values + constraint values of the dynamic constraint (warp = sample x tile)
 //   RomNodeOut    XT        -> CSR values + constraint values of the range-of-motion constraints (warp = sample x
 //                              tile, all feet) and of the node-wise sets: terrain, force, swing, spline-acc,
-//                              base-motion (warp = group of consecutive nodes x tile); the CTAs of a tile in row order
-//   TransposeOut  GT[tile][m][32] -> g[B][m]       (the constraint values are staged instance-tiled)
-//   PhaseJac      (optimised phase durations only) per-instance entries of the PhaseSpline columns
+//                              base-motion (warp = group of consecutive nodes x tile); the CTAs of a tile in row order;
+//                              constant runs of the CSR rows by TMA bulk copies (ConstRunBody)
+//   DynTailOut    (optimised phase durations only) the PhaseSpline columns of the dynamic rows (warp = foot)
+//   PhaseJac      (optimised phase durations only) the TotalDurationConstraint rows
 //   CostKernel    XT        -> cost + gradient (only when the formulation has cost terms)
+//   (TransposeOut GT[tile][m][32] -> g[B][m]: only in the -DTWB_GDIRECT=0 variants; the output CTAs write g themselves)
 //
 // In the output kernels a warp owns one unit of 32 instances: each lane evaluates the splines its unit needs
 // (reference operation order) and computes its instance's unit state into a padded shared-memory block (row =
@@ -21,7 +23,7 @@
 // for the 32 instances from ONE list that covers the CTA's consecutive units (adjacent CSR rows): every store
 // instruction covers 512 contiguous bytes of one instance's CSR value row, whole 32-byte sectors only.  The
 // state never leaves the SM; HBM sees x once and g / jac exactly once.  DynOut runs beside RomNodeOut on a
-// second stream.
+// second stream; twb_batch_eval_device replays the whole evaluation as one CUDA graph.
 //
 // Reference math restated per device function (file:line cited there).  This translation unit is
 // compiled with -fmad=false: plain * and + round like the reference's scalar C++; fused
